@@ -1,0 +1,191 @@
+/* lasgun_b200.h — C ABI of the B200 render path for nfrasser/lasgun.
+ *
+ * The reference has no FFI; its drop-in surface is the Rust public API
+ *   lasgun::capture(&Scene, &mut Film)                      src/lib.rs:55
+ *   lasgun::capture_subset(k, n, &Accel, &mut impl Img)     src/lib.rs:110
+ *   lasgun::Accel::from(&Scene)                             src/lib.rs:42, src/accelerators/bvh.rs:135
+ * A Rust `capture` shim builds its BVHAccel as today, flattens the (crate-private) fields
+ * `nodes`, `order`, `primitives` (bvh.rs:48-69) into the arrays of `lgb_scene_desc`, and calls
+ * the functions below (INTEGRATION.md shows the binding).  Everything from camera ray generation
+ * (camera.rs:113-146) through traversal (bvh.rs:461-522), primitive intersection
+ * (sphere.rs:79, cuboid.rs:55, triangle.rs:161), shading (integrate.rs:23-80) and film
+ * quantisation (img.rs:56-67) then runs in sm_100a CUDA kernels.
+ *
+ * Conventions: every function returns LGB_OK (0) or a negative lgb_status; nothing aborts or
+ * unwinds across this boundary.  Host arrays passed in are borrowed for the duration of the
+ * call only.  One capture at a time per context.  One context drives one GPU; multi-GPU
+ * renders use one context per GPU (one process per GPU) and the tile-rank arguments.
+ */
+#ifndef LASGUN_B200_H
+#define LASGUN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGB_ABI_VERSION 1
+
+typedef enum lgb_status {
+    LGB_OK = 0,
+    LGB_ERR_INVALID = -1,      /* bad argument / malformed scene description */
+    LGB_ERR_CUDA = -2,         /* CUDA runtime failure (see lgb_last_error) */
+    LGB_ERR_UNSUPPORTED = -3,  /* feature outside the hot path (material, transform, depth > 64) */
+    LGB_ERR_NOMEM = -4,
+    LGB_ERR_NO_DEVICE = -5     /* no sm_100-class GPU: there is NO CPU fallback */
+} lgb_status;
+
+typedef struct lgb_ctx lgb_ctx;
+typedef struct lgb_scene lgb_scene;
+
+/* Primitive reference stored in a BVH leaf: (type << 30) | index into that type's array.
+ * Leaf order is the reference's `order[]` already applied (bvh.rs:484). */
+enum { LGB_PRIM_SPHERE = 0, LGB_PRIM_CUBOID = 1, LGB_PRIM_TRIANGLE = 2, LGB_PRIM_INSTANCE = 3 };
+#define LGB_PRIM_REF(type, index) (((uint32_t)(type) << 30) | (uint32_t)(index))
+#define LGB_MISS 0xFFFFFFFFu
+
+/* Flattened BVH node, 32 bytes, pre-order as flatten_bvh_tree (bvh.rs:430-453): the left child of
+ * an interior node is index + 1.  Boxes must contain the reference's f64 box (round outward).
+ *   interior: a = index of the second child, b = split axis (0..2)
+ *   leaf:     a = first entry in prim_refs, b = LGB_LEAF_FLAG | count
+ * Child indices and instance roots are absolute indices into the one `nodes` array. */
+#define LGB_LEAF_FLAG 0x80000000u
+typedef struct lgb_node {
+    float lo[3]; uint32_t a;
+    float hi[3]; uint32_t b;
+} lgb_node;
+
+typedef struct lgb_sphere {          /* Sphere, src/shape/sphere.rs:12-16 */
+    double center[3]; double radius;
+} lgb_sphere;
+
+typedef struct lgb_cuboid {          /* Cuboid bounds, src/shape/cuboid.rs:12-30 */
+    double min[3]; double max[3];
+} lgb_cuboid;
+
+typedef struct lgb_triangle {        /* the three f32 OBJ positions a Triangle reads, triangle.rs:40-55 */
+    float p0[3]; float p1[3]; float p2[3];
+} lgb_triangle;
+
+typedef struct lgb_tri_normals {     /* per-vertex f32 normals, triangle.rs:58-76 */
+    float n0[3]; float n1[3]; float n2[3];
+} lgb_tri_normals;
+
+/* Nested BVH used as a primitive (bvh.rs:141-162).  Only identity transforms are supported in
+ * ABI v1; `identity` must be 1. */
+typedef struct lgb_instance {
+    uint32_t root_node;              /* absolute index of the child BVH's node 0 */
+    uint32_t identity;
+    uint32_t swap_backface;          /* must be 0 in ABI v1 */
+    uint32_t reserved;
+} lgb_instance;
+
+/* Material after `Material::scattering` resolution (material/{plastic,matte}.rs).
+ * kind 0 = matte with sigma == 0 (Lambertian only), kind 1 = plastic. */
+typedef struct lgb_material {
+    double kd[3]; double roughness;
+    double ks[3]; uint32_t kind; uint32_t reserved;
+} lgb_material;
+
+typedef struct lgb_light {           /* PointLight, src/light/point.rs:14-18 */
+    double position[3]; double intensity[3]; double falloff[3];
+} lgb_light;
+
+typedef struct lgb_camera {          /* Camera after look_at, src/camera.rs:6-38 */
+    double origin[3], view[3], up[3], aux[3];
+    double image_plane_height;       /* camera.rs:93, :158-164 */
+    double pixel_separation;         /* 0 perspective, 1 orthographic (camera.rs:168-173) */
+    double sample_distance;          /* Supersampling::distance = 1 / root (camera.rs:189-193) */
+    uint32_t supersampling_root;     /* samples per pixel = root * root */
+    uint32_t reserved;
+} lgb_camera;
+
+typedef struct lgb_scene_desc {
+    uint32_t abi_version;            /* LGB_ABI_VERSION */
+    uint32_t flags;                  /* LGB_SCENE_* */
+    const lgb_node* nodes;           uint64_t n_nodes;       /* node 0 = root of the top-level BVH */
+    const uint32_t* prim_refs;       uint64_t n_prim_refs;
+    const lgb_sphere* spheres;       uint64_t n_spheres;
+    const uint32_t* sphere_material; const uint32_t* sphere_id;      /* n_spheres each */
+    const lgb_cuboid* cuboids;       uint64_t n_cuboids;
+    const uint32_t* cuboid_material; const uint32_t* cuboid_id;      /* n_cuboids each */
+    const lgb_triangle* triangles;   uint64_t n_triangles;
+    const uint32_t* triangle_material; const uint32_t* triangle_id;  /* n_triangles each */
+    const lgb_tri_normals* tri_normals;  /* NULL or n_triangles entries (mesh has normals and smoothing is on) */
+    const uint8_t* tri_has_normals;      /* NULL or n_triangles flags (meshes may differ) */
+    const lgb_instance* instances;   uint64_t n_instances;
+    const lgb_material* materials;   uint64_t n_materials;
+    const lgb_light* lights;         uint64_t n_lights;      /* at most LGB_MAX_LIGHTS */
+    lgb_camera camera;
+    double ambient[3];                                       /* scene.rs:22 */
+    double bg_inner[3], bg_outer[3], bg_scale;               /* material/background.rs:6-10 */
+} lgb_scene_desc;
+
+#define LGB_MAX_LIGHTS 32
+/* Leaves were re-split on the host below the reference's leaves: traversal order inside a
+ * reference leaf is then no longer the reference's, which can only change exact-t ties. */
+#define LGB_SCENE_RESPLIT 1u
+
+typedef struct lgb_stats {
+    uint64_t primary_rays;           /* w * h * spp rendered by this call */
+    uint64_t primary_hits;
+    uint64_t shadow_rays;            /* reference semantics: lights * primary_hits (integrate.rs:47-50) */
+    uint64_t shadow_rays_traced;     /* rays the device actually traversed */
+    uint64_t shadow_occluded;
+    uint64_t exact_tests;            /* f64 reference-arithmetic primitive tests executed */
+    uint64_t filter_tests;           /* conservative f32 primitive filter tests executed */
+    uint64_t node_tests;
+    float render_ms;                 /* device time of the render + resolve kernels */
+    float total_ms;                  /* device time incl. film copy back to the host */
+    uint32_t kernel_launches;
+    uint32_t stack_overflow;         /* 1 if a ray exceeded the 64-entry stack (bvh.rs:469) */
+} lgb_stats;
+
+/* Device / context --------------------------------------------------------------------- */
+int lgb_device_count(void);
+int lgb_init(int device, lgb_ctx** out);
+void lgb_shutdown(lgb_ctx* ctx);
+const char* lgb_last_error(lgb_ctx* ctx);          /* ctx may be NULL: last error of lgb_init */
+const char* lgb_status_string(int status);
+
+/* Scene: copies the caller's flat arrays to the device (replaces the data a BVHAccel owns). */
+int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* desc, lgb_scene** out);
+void lgb_scene_destroy(lgb_scene* scene);
+uint64_t lgb_scene_device_bytes(const lgb_scene* scene);
+
+/* capture (src/lib.rs:55): blocking; fills caller-owned row-major RGBA8, w*h*4 bytes (host). */
+int lgb_capture(lgb_ctx* ctx, lgb_scene* scene, uint32_t w, uint32_t h, uint8_t* rgba_out, lgb_stats* stats);
+
+/* capture_subset (src/lib.rs:110): pixels k, k+n, k+2n, ... of the row-major film only; all other
+ * bytes of rgba_inout (host) are left untouched. */
+int lgb_capture_subset(lgb_ctx* ctx, lgb_scene* scene, uint32_t k, uint32_t n, uint32_t w, uint32_t h,
+                       uint8_t* rgba_inout, lgb_stats* stats);
+
+/* Debug / parity: full-frame capture that also returns, per sample (index (y*w + x)*spp + s, sample
+ * order of camera.rs:137-145), the canonical id of the closest-hit primitive (LGB_MISS if none), its
+ * f64 ray parameter t (+inf if none) and a bit mask of occluded lights.  Any pointer may be NULL. */
+int lgb_capture_aov(lgb_ctx* ctx, lgb_scene* scene, uint32_t w, uint32_t h, uint8_t* rgba_out,
+                    uint32_t* prim_id, double* t, uint32_t* occluded, lgb_stats* stats);
+
+/* Device-resident capture for benchmarks and multi-GPU: renders the macro-tiles owned by
+ * `tile_rank` of `tile_ranks` (all tiles when tile_ranks == 1) into `d_film`, a DEVICE pointer to a
+ * full w*h*4 row-major film that may live on a peer GPU.  Asynchronous on `stream` (a cudaStream_t,
+ * NULL = the context's stream) unless `stats` is non-NULL, in which case it synchronises. */
+int lgb_capture_device(lgb_ctx* ctx, lgb_scene* scene, uint32_t w, uint32_t h, uint32_t tile_rank,
+                       uint32_t tile_ranks, void* d_film, void* stream, lgb_stats* stats);
+
+/* Trace caller-supplied rays (o[3], d[3] f64 each) through the scene: closest-hit id and t.
+ * Used by the known-answer and random-ray parity tests. */
+int lgb_trace_rays(lgb_ctx* ctx, lgb_scene* scene, const double* rays_od, uint64_t n_rays,
+                   uint32_t* prim_id, double* t, double* ng, double* ns);
+
+/* Measured device ceilings used for roofline reporting (bench only). */
+int lgb_measure_l2_read_gbs(lgb_ctx* ctx, uint64_t bytes, int iters, double* gbs_out);
+int lgb_measure_fp32_gops(lgb_ctx* ctx, int iters, double* glaneops_out);
+int lgb_measure_fp64_gops(lgb_ctx* ctx, int iters, double* glaneops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LASGUN_B200_H */

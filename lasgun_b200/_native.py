@@ -1,0 +1,360 @@
+"""ctypes binding of liblasgun_b200.so: the lgb_* C ABI (include/lasgun_b200.h) and the lgh_* host
+mirror (include/lasgun_host.hpp).  There is no fallback: if the library cannot be loaded, or no
+sm_100 GPU is visible, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import api
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "liblasgun_b200.so")
+_lib = None
+
+LGB_OK, LGB_ERR_INVALID, LGB_ERR_CUDA, LGB_ERR_UNSUPPORTED, LGB_ERR_NOMEM, LGB_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
+LGB_MISS = 0xFFFFFFFF
+LGB_LEAF_FLAG = 0x80000000
+
+# Every symbol include/lasgun_b200.h declares (checked by tests/test_abi.py without a GPU).
+ABI_SYMBOLS = [
+    "lgb_device_count", "lgb_init", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
+    "lgb_scene_destroy", "lgb_scene_device_bytes", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
+    "lgb_capture_device", "lgb_trace_rays", "lgb_measure_l2_read_gbs", "lgb_measure_fp32_gops", "lgb_measure_fp64_gops",
+]
+
+
+class LasgunError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"[{status}] {message}")
+        self.status = status
+
+
+class Node(C.Structure):
+    _fields_ = [("lo", C.c_float * 3), ("a", C.c_uint32), ("hi", C.c_float * 3), ("b", C.c_uint32)]
+
+
+class CameraDesc(C.Structure):
+    _fields_ = [("origin", C.c_double * 3), ("view", C.c_double * 3), ("up", C.c_double * 3), ("aux", C.c_double * 3),
+                ("image_plane_height", C.c_double), ("pixel_separation", C.c_double), ("sample_distance", C.c_double),
+                ("supersampling_root", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("flags", C.c_uint32),
+        ("nodes", C.c_void_p), ("n_nodes", C.c_uint64),
+        ("prim_refs", C.c_void_p), ("n_prim_refs", C.c_uint64),
+        ("spheres", C.c_void_p), ("n_spheres", C.c_uint64), ("sphere_material", C.c_void_p), ("sphere_id", C.c_void_p),
+        ("cuboids", C.c_void_p), ("n_cuboids", C.c_uint64), ("cuboid_material", C.c_void_p), ("cuboid_id", C.c_void_p),
+        ("triangles", C.c_void_p), ("n_triangles", C.c_uint64), ("triangle_material", C.c_void_p), ("triangle_id", C.c_void_p),
+        ("tri_normals", C.c_void_p), ("tri_has_normals", C.c_void_p),
+        ("instances", C.c_void_p), ("n_instances", C.c_uint64),
+        ("materials", C.c_void_p), ("n_materials", C.c_uint64),
+        ("lights", C.c_void_p), ("n_lights", C.c_uint64),
+        ("camera", CameraDesc),
+        ("ambient", C.c_double * 3), ("bg_inner", C.c_double * 3), ("bg_outer", C.c_double * 3), ("bg_scale", C.c_double),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [("primary_rays", C.c_uint64), ("primary_hits", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("shadow_rays_traced", C.c_uint64), ("shadow_occluded", C.c_uint64), ("exact_tests", C.c_uint64),
+                ("filter_tests", C.c_uint64), ("node_tests", C.c_uint64), ("render_ms", C.c_float), ("total_ms", C.c_float),
+                ("kernel_launches", C.c_uint32), ("stack_overflow", C.c_uint32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def lib():
+    """Loads the in-tree shared library; fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise LasgunError(LGB_ERR_NO_DEVICE, f"{SO_PATH} is missing: run `python -m lasgun_b200.build` (no CPU fallback exists)")
+    L = C.CDLL(SO_PATH)
+    vp, dp, fp, u32p, u64p, u8p, ip = (C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_uint32),
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_int))
+    sig = {
+        "lgb_device_count": (C.c_int, []), "lgb_init": (C.c_int, [C.c_int, C.POINTER(vp)]), "lgb_shutdown": (None, [vp]),
+        "lgb_last_error": (C.c_char_p, [vp]), "lgb_status_string": (C.c_char_p, [C.c_int]),
+        "lgb_scene_create": (C.c_int, [vp, C.POINTER(SceneDesc), C.POINTER(vp)]), "lgb_scene_destroy": (None, [vp]),
+        "lgb_scene_device_bytes": (C.c_uint64, [vp]),
+        "lgb_capture": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u8p, C.POINTER(Stats)]),
+        "lgb_capture_subset": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u8p, C.POINTER(Stats)]),
+        "lgb_capture_aov": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u8p, u32p, dp, u32p, C.POINTER(Stats)]),
+        "lgb_capture_device": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.POINTER(Stats)]),
+        "lgb_trace_rays": (C.c_int, [vp, vp, dp, C.c_uint64, u32p, dp, dp, dp]),
+        "lgb_measure_l2_read_gbs": (C.c_int, [vp, C.c_uint64, C.c_int, dp]),
+        "lgb_measure_fp32_gops": (C.c_int, [vp, C.c_int, dp]), "lgb_measure_fp64_gops": (C.c_int, [vp, C.c_int, dp]),
+        # host mirror
+        "lgh_last_error": (C.c_char_p, []), "lgh_scene_new": (vp, []), "lgh_scene_free": (None, [vp]),
+        "lgh_set_perspective_camera": (None, [vp, C.c_double]), "lgh_set_orthographic_camera": (None, [vp, C.c_double]),
+        "lgh_look_at": (None, [vp, dp, dp, dp]), "lgh_set_supersampling": (C.c_int, [vp, C.c_int]),
+        "lgh_set_ambient_light": (None, [vp, dp]), "lgh_set_radial_background": (None, [vp, dp, dp, C.c_double]),
+        "lgh_set_mesh_smoothing": (None, [vp, C.c_int]), "lgh_add_point_light": (None, [vp, dp, dp, dp]),
+        "lgh_add_mesh": (C.c_int, [vp, fp, C.c_uint64, u32p, C.c_uint64, fp, C.c_uint64, u32p, C.POINTER(C.c_int64)]),
+        "lgh_agg_new": (C.c_int, [vp]),
+        "lgh_agg_add_sphere": (None, [vp, C.c_int, dp, C.c_double, C.c_int, dp, dp, C.c_double]),
+        "lgh_agg_add_spheres": (None, [vp, C.c_int, C.c_uint64, dp, dp, C.c_int, ip, dp, dp, dp, ip]),
+        "lgh_agg_add_cube": (None, [vp, C.c_int, dp, C.c_double, C.c_int, dp, dp, C.c_double]),
+        "lgh_agg_add_box": (None, [vp, C.c_int, dp, dp, C.c_int, dp, dp, C.c_double]),
+        "lgh_agg_add_mesh": (None, [vp, C.c_int, C.c_int64, C.c_int, C.c_int, dp, dp, C.c_double]),
+        "lgh_agg_add_group": (None, [vp, C.c_int, C.c_int]), "lgh_agg_swap_backface": (None, [vp, C.c_int]),
+        "lgh_agg_translate": (None, [vp, C.c_int, dp]), "lgh_agg_scale": (None, [vp, C.c_int, C.c_double, C.c_double, C.c_double]),
+        "lgh_agg_rotate_axis": (None, [vp, C.c_int, C.c_int, C.c_double]), "lgh_agg_rotate": (None, [vp, C.c_int, C.c_double, dp]),
+        "lgh_flatten": (vp, [vp, C.c_int, C.c_uint32, C.c_int]), "lgh_flat_free": (None, [vp]),
+        "lgh_flat_describe": (None, [vp, C.POINTER(SceneDesc)]), "lgh_flat_build_ms": (C.c_double, [vp]),
+        "lgh_flat_prim_count": (C.c_uint32, [vp]), "lgh_flat_level_count": (C.c_uint64, [vp]),
+        "lgh_flat_level_dims": (C.c_int, [vp, C.c_uint64, u64p, u64p, u32p]),
+        "lgh_flat_level_dump": (C.c_int, [vp, C.c_uint64, dp, u32p, u64p]),
+        "lgh_capture": (C.c_int, [vp, C.c_uint32, C.c_uint32, u8p]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _d3(v):
+    return (C.c_double * 3)(*[float(c) for c in v])
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty)) if a is not None and a.size else None
+
+
+class HostScene:
+    """C++ `lasgun::Scene` built by replaying an api.Scene description (scene.rs / node.rs surface)."""
+
+    def __init__(self, scene: api.Scene):
+        L = lib()
+        self.desc = scene
+        self.h = L.lgh_scene_new()
+        cam = scene.camera
+        (L.lgh_set_perspective_camera if cam.perspective else L.lgh_set_orthographic_camera)(self.h, cam.param)
+        if cam.look is not None:
+            L.lgh_look_at(self.h, _d3(cam.look[0]), _d3(cam.look[1]), _d3(cam.look[2]))
+        self._check(L.lgh_set_supersampling(self.h, cam.supersampling))
+        L.lgh_set_ambient_light(self.h, _d3(scene.ambient))
+        L.lgh_set_radial_background(self.h, _d3(scene.background[0]), _d3(scene.background[1]), scene.background[2])
+        for p, i, f in scene.lights:
+            L.lgh_add_point_light(self.h, _d3(p), _d3(i), _d3(f))
+        for m in scene.meshes:
+            ref = C.c_int64(-1)
+            self._check(L.lgh_add_mesh(self.h, _ptr(m.positions, C.c_float), len(m.positions), _ptr(m.faces, C.c_uint32), len(m.faces),
+                                       _ptr(m.normals, C.c_float), len(m.normals), _ptr(m.normal_faces, C.c_uint32), C.byref(ref)))
+        self._fill(0, scene.root)
+
+    def _check(self, rc):
+        if rc != LGB_OK:
+            raise LasgunError(rc, lib().lgh_last_error().decode())
+
+    @staticmethod
+    def _mat(m):
+        return (m.kind, _d3(m.kd), _d3(m.ks), m.roughness)
+
+    def _fill(self, idx, agg):
+        L = lib()
+        for kind, *rest in agg.transforms:
+            if kind == "translate":
+                L.lgh_agg_translate(self.h, idx, _d3(rest[0]))
+            elif kind == "scale":
+                L.lgh_agg_scale(self.h, idx, *rest[0])
+            elif kind == "rotate_axis":
+                L.lgh_agg_rotate_axis(self.h, idx, rest[0], rest[1])
+            elif kind == "rotate":
+                L.lgh_agg_rotate(self.h, idx, rest[0], _d3(rest[1]))
+        if agg._swap_backface:
+            L.lgh_agg_swap_backface(self.h, idx)
+        for item in agg.contents:
+            k = item[0]
+            if k == "sphere":
+                L.lgh_agg_add_sphere(self.h, idx, _d3(item[1]), item[2], *self._mat(item[3]))
+            elif k == "spheres":
+                _, cen, rad, mats, midx = item
+                kinds = np.array([m.kind for m in mats], np.int32)
+                kd = np.array([m.kd for m in mats], np.float64); ks = np.array([m.ks for m in mats], np.float64)
+                rough = np.array([m.roughness for m in mats], np.float64)
+                L.lgh_agg_add_spheres(self.h, idx, len(rad), _ptr(cen, C.c_double), _ptr(rad, C.c_double), len(mats),
+                                      _ptr(kinds, C.c_int), _ptr(kd, C.c_double), _ptr(ks, C.c_double), _ptr(rough, C.c_double),
+                                      _ptr(midx, C.c_int))
+            elif k == "cube":
+                L.lgh_agg_add_cube(self.h, idx, _d3(item[1]), item[2], *self._mat(item[3]))
+            elif k == "box":
+                L.lgh_agg_add_box(self.h, idx, _d3(item[1]), _d3(item[2]), *self._mat(item[3]))
+            elif k == "mesh":
+                m = item[2] if item[2] is not None else api.Material.default()
+                L.lgh_agg_add_mesh(self.h, idx, item[1].index, 1 if item[2] is not None else 0, *self._mat(m))
+            elif k == "group":
+                child = L.lgh_agg_new(self.h)
+                self._fill(child, item[1])
+                L.lgh_agg_add_group(self.h, idx, child)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().lgh_scene_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class FlatScene:
+    """Host-side flattened scene (Accel::from without the upload): owns the arrays of an lgb_scene_desc."""
+
+    def __init__(self, scene, resplit=True, leaf_size=4, keep_levels=False):
+        L = lib()
+        self.host = scene if isinstance(scene, HostScene) else HostScene(scene)
+        self.h = L.lgh_flatten(self.host.h, 1 if resplit else 0, leaf_size, 1 if keep_levels else 0)
+        if not self.h:
+            msg = L.lgh_last_error().decode()
+            raise LasgunError(LGB_ERR_UNSUPPORTED if "not on the device path" in msg or "outside the device" in msg else LGB_ERR_INVALID, msg)
+        self.desc = SceneDesc()
+        L.lgh_flat_describe(self.h, C.byref(self.desc))
+        self.spp = self.desc.camera.supersampling_root ** 2
+        self.n_lights = self.desc.n_lights
+
+    @property
+    def build_ms(self):
+        return lib().lgh_flat_build_ms(self.h)
+
+    @property
+    def prim_count(self):
+        return lib().lgh_flat_prim_count(self.h)
+
+    def nodes(self):
+        n = self.desc.n_nodes
+        buf = (Node * n).from_address(self.desc.nodes)
+        return np.frombuffer(buf, dtype=np.dtype([("lo", "<f4", 3), ("a", "<u4"), ("hi", "<f4", 3), ("b", "<u4")]), count=n)
+
+    def prim_refs(self):
+        n = self.desc.n_prim_refs
+        return np.frombuffer((C.c_uint32 * n).from_address(self.desc.prim_refs), dtype=np.uint32, count=n)
+
+    def level(self, i):
+        L = lib()
+        nn, npr, off = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        if L.lgh_flat_level_dims(self.h, i, C.byref(nn), C.byref(npr), C.byref(off)):
+            raise IndexError(i)
+        b = np.zeros((nn.value, 6)); meta = np.zeros((nn.value, 3), np.uint32); order = np.zeros((npr.value,), np.uint64)
+        L.lgh_flat_level_dump(self.h, i, _ptr(b, C.c_double), _ptr(meta, C.c_uint32), _ptr(order, C.c_uint64))
+        return b, meta, order, off.value
+
+    def level_count(self):
+        return lib().lgh_flat_level_count(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().lgh_flat_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Context:
+    """lgb_ctx: one GPU."""
+
+    def __init__(self, device=0):
+        L = lib()
+        h = C.c_void_p()
+        rc = L.lgb_init(device, C.byref(h))
+        if rc:
+            raise LasgunError(rc, L.lgb_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc:
+            raise LasgunError(rc, lib().lgb_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            lib().lgb_shutdown(self.h)
+            self.h = None
+
+    def measure(self):
+        L = lib()
+        out = {}
+        v = C.c_double()
+        self.check(L.lgb_measure_l2_read_gbs(self.h, 32 << 20, 50, C.byref(v))); out["l2_read_gbs"] = v.value
+        self.check(L.lgb_measure_fp32_gops(self.h, 20000, C.byref(v))); out["fp32_ffma_glanes"] = v.value
+        self.check(L.lgb_measure_fp64_gops(self.h, 20000, C.byref(v))); out["fp64_dfma_glanes"] = v.value
+        return out
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")) if lib().lgb_device_count() > 1 else 0)
+    return _default_ctx
+
+
+class DeviceScene:
+    """lgb_scene: the flattened scene resident in HBM."""
+
+    def __init__(self, ctx: Context, flat: FlatScene):
+        L = lib()
+        self.ctx, self.flat = ctx, flat
+        h = C.c_void_p()
+        ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat.desc), C.byref(h)))
+        self.h = h
+        self.spp = flat.spp
+
+    @property
+    def device_bytes(self):
+        return lib().lgb_scene_device_bytes(self.h)
+
+    def capture(self, w, h, out=None):
+        rgba = out if out is not None else np.zeros((h, w, 4), np.uint8)
+        st = Stats()
+        self.ctx.check(lib().lgb_capture(self.ctx.h, self.h, w, h, _ptr(rgba, C.c_uint8), C.byref(st)))
+        return rgba, st.as_dict()
+
+    def capture_subset(self, k, n, w, h, rgba):
+        st = Stats()
+        self.ctx.check(lib().lgb_capture_subset(self.ctx.h, self.h, k, n, w, h, _ptr(rgba, C.c_uint8), C.byref(st)))
+        return st.as_dict()
+
+    def capture_aov(self, w, h):
+        ns = w * h * self.spp
+        rgba = np.zeros((h, w, 4), np.uint8)
+        ids = np.zeros((ns,), np.uint32); t = np.zeros((ns,), np.float64); occl = np.zeros((ns,), np.uint32)
+        st = Stats()
+        self.ctx.check(lib().lgb_capture_aov(self.ctx.h, self.h, w, h, _ptr(rgba, C.c_uint8), _ptr(ids, C.c_uint32),
+                                             _ptr(t, C.c_double), _ptr(occl, C.c_uint32), C.byref(st)))
+        return {"rgba": rgba, "prim_id": ids, "t": t, "occl": occl, "stats": st.as_dict()}
+
+    def capture_device(self, w, h, d_film_ptr, rank=0, ranks=1, stream=0, want_stats=False):
+        st = Stats() if want_stats else None
+        self.ctx.check(lib().lgb_capture_device(self.ctx.h, self.h, w, h, rank, ranks, C.c_void_p(d_film_ptr),
+                                                C.c_void_p(stream) if stream else None, C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+    def trace_rays(self, rays_od):
+        rays = np.ascontiguousarray(rays_od, np.float64).reshape(-1, 6)
+        n = len(rays)
+        ids = np.zeros((n,), np.uint32); t = np.zeros((n,), np.float64); ng = np.zeros((n, 3)); ns = np.zeros((n, 3))
+        self.ctx.check(lib().lgb_trace_rays(self.ctx.h, self.h, _ptr(rays, C.c_double), n, _ptr(ids, C.c_uint32), _ptr(t, C.c_double),
+                                            _ptr(ng, C.c_double), _ptr(ns, C.c_double)))
+        return ids, t, ng, ns
+
+    def destroy(self):
+        if self.h:
+            lib().lgb_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

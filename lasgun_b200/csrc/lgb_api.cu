@@ -1,0 +1,529 @@
+// C-ABI glue (include/lasgun_b200.h): context, scene upload, capture entry points.
+// No torch types, no CPU fallback: without an sm_100-class device lgb_init fails.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "lgb_types.cuh"
+
+namespace lgb {
+cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, bool stats, cudaStream_t);
+cudaError_t launch_trace(const DevScene&, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns, cudaStream_t);
+cudaError_t launch_l2_read(const void* buf, uint64_t bytes, int iters, float* sink, int sms, cudaStream_t);
+cudaError_t launch_fp32_peak(int iters, float* sink, int sms, cudaStream_t);
+cudaError_t launch_fp64_peak(int iters, double* sink, int sms, cudaStream_t);
+}  // namespace lgb
+
+using namespace lgb;
+
+static thread_local std::string g_init_error;
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct lgb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    std::string error;
+    DevBuf radiance, film, counters, tiles, aov_id, aov_t, aov_occl, scratch;
+    std::vector<uint32_t> tile_host;
+    uint32_t tile_key[4] = {0, 0, 0, 0};   // w, h, rank, ranks of the cached tile list
+    uint32_t tile_count = 0;
+};
+
+struct lgb_scene {
+    lgb_ctx* ctx = nullptr;
+    std::vector<void*> allocs;
+    uint64_t bytes = 0;
+    DevScene dev{};
+    DevCamera cam{};
+    DevShade shade{};
+    double max_abs = 0.0;      // max |coordinate| over geometry, camera origin and lights
+};
+
+static int fail(lgb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->error = msg; else g_init_error = msg;
+    return code;
+}
+static int cuda_fail(lgb_ctx* ctx, cudaError_t e, const char* what) {
+    return fail(ctx, LGB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); } while (0)
+
+extern "C" {
+
+const char* lgb_status_string(int s) {
+    switch (s) {
+    case LGB_OK: return "ok";
+    case LGB_ERR_INVALID: return "invalid argument";
+    case LGB_ERR_CUDA: return "CUDA error";
+    case LGB_ERR_UNSUPPORTED: return "unsupported on the device path";
+    case LGB_ERR_NOMEM: return "out of memory";
+    case LGB_ERR_NO_DEVICE: return "no sm_100 device";
+    default: return "unknown status";
+    }
+}
+
+int lgb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* lgb_last_error(lgb_ctx* ctx) { return ctx ? ctx->error.c_str() : g_init_error.c_str(); }
+
+int lgb_init(int device, lgb_ctx** out) {
+    if (!out) return fail(nullptr, LGB_ERR_INVALID, "lgb_init: out is NULL");
+    *out = nullptr;
+    int n = lgb_device_count();
+    if (n <= 0) return fail(nullptr, LGB_ERR_NO_DEVICE, "lgb_init: no CUDA device visible (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, LGB_ERR_INVALID, "lgb_init: device index out of range");
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(nullptr, LGB_ERR_NO_DEVICE, "lgb_init: device is not sm_100-class; kernels are built for sm_100a only");
+    CU(nullptr, cudaSetDevice(device));
+    lgb_ctx* c = new lgb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(nullptr, cudaEventCreate(&c->ev0)); CU(nullptr, cudaEventCreate(&c->ev1)); CU(nullptr, cudaEventCreate(&c->ev2));
+    *out = c;
+    return LGB_OK;
+}
+
+void lgb_shutdown(lgb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch}) b->release();
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------- scene
+static inline float f32_down(double v) { float f = (float)v; if ((double)f > v) f = nextafterf(f, -INFINITY); return f; }
+static inline float f32_up(double v) { float f = (float)v; if ((double)f < v) f = nextafterf(f, INFINITY); return f; }
+
+template <class T>
+static int upload(lgb_scene* s, const std::vector<T>& host, const T** dev) {
+    *dev = nullptr;
+    if (host.empty()) return LGB_OK;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, host.size() * sizeof(T));
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(s->ctx, LGB_ERR_NOMEM, "scene upload: cudaMalloc failed") : cuda_fail(s->ctx, e, "cudaMalloc");
+    s->allocs.push_back(p);
+    s->bytes += host.size() * sizeof(T);
+    e = cudaMemcpyAsync(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, s->ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(s->ctx, e, "cudaMemcpyAsync(H2D)");
+    *dev = reinterpret_cast<const T*>(p);
+    return LGB_OK;
+}
+
+extern "C" {
+
+void lgb_scene_destroy(lgb_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (void* p : s->allocs) cudaFree(p);
+    delete s;
+}
+uint64_t lgb_scene_device_bytes(const lgb_scene* s) { return s ? s->bytes : 0; }
+
+int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
+    if (!ctx || !d || !out) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: NULL argument");
+    *out = nullptr;
+    if (d->abi_version != LGB_ABI_VERSION) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: abi_version mismatch");
+    if (d->n_nodes == 0 || !d->nodes) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: empty BVH (the reference does not terminate on an empty aggregate, bvh.rs:240)");
+    if (d->n_nodes >= (1ull << 31) || d->n_prim_refs >= (1ull << 32) || d->n_spheres >= (1ull << 30) || d->n_cuboids >= (1ull << 30) ||
+        d->n_triangles >= (1ull << 30) || d->n_instances >= (1ull << 30))
+        return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: array too large for 30-bit primitive references");
+    if (d->n_lights > LGB_MAX_LIGHTS) return fail(ctx, LGB_ERR_UNSUPPORTED, "lgb_scene_create: more than LGB_MAX_LIGHTS point lights");
+    if (d->n_materials == 0 && (d->n_spheres || d->n_cuboids || d->n_triangles)) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: no materials");
+    if (d->camera.supersampling_root == 0 || d->camera.supersampling_root > 256) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: supersampling_root out of range");
+    CU(ctx, cudaSetDevice(ctx->device));
+
+    // ---- validate materials (only the plastic / Lambertian lobes are on the device path)
+    std::vector<double> mats(8 * d->n_materials);
+    for (uint64_t i = 0; i < d->n_materials; i++) {
+        const lgb_material& m = d->materials[i];
+        if (m.kind == 0) { if (m.roughness != 0.0) return fail(ctx, LGB_ERR_UNSUPPORTED, "material: matte with sigma != 0 (Oren-Nayar) is outside the device path"); }
+        else if (m.kind != 1) return fail(ctx, LGB_ERR_UNSUPPORTED, "material: only plastic and matte(sigma=0) are on the device path (metal/glass/mirror need Whitted recursion)");
+        bool diffuse = m.kind == 0 ? true : !(m.kd[0] == 0.0 && m.kd[1] == 0.0 && m.kd[2] == 0.0);   // plastic.rs:24, matte.rs:18-26
+        bool glossy = m.kind == 1 && !(m.ks[0] == 0.0 && m.ks[1] == 0.0 && m.ks[2] == 0.0);          // plastic.rs:29
+        double* o = &mats[8 * i];
+        o[0] = m.kd[0]; o[1] = m.kd[1]; o[2] = m.kd[2]; o[3] = m.roughness;
+        o[4] = m.ks[0]; o[5] = m.ks[1]; o[6] = m.ks[2];
+        long long fl = (diffuse ? 1 : 0) | (glossy ? 2 : 0);
+        std::memcpy(&o[7], &fl, 8);
+    }
+    auto mat_ok = [&](const uint32_t* arr, uint64_t n) { for (uint64_t i = 0; i < n; i++) if (arr[i] >= d->n_materials) return false; return true; };
+    if ((d->n_spheres && (!d->spheres || !d->sphere_material || !d->sphere_id)) || (d->n_cuboids && (!d->cuboids || !d->cuboid_material || !d->cuboid_id)) ||
+        (d->n_triangles && (!d->triangles || !d->triangle_material || !d->triangle_id)) || (d->n_instances && !d->instances) ||
+        (d->n_prim_refs && !d->prim_refs) || (d->n_lights && !d->lights))
+        return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: NULL array with non-zero count");
+    if (!mat_ok(d->sphere_material, d->n_spheres) || !mat_ok(d->cuboid_material, d->n_cuboids) || !mat_ok(d->triangle_material, d->n_triangles))
+        return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: material index out of range");
+    for (uint64_t i = 0; i < d->n_instances; i++) {
+        if (!d->instances[i].identity || d->instances[i].swap_backface)
+            return fail(ctx, LGB_ERR_UNSUPPORTED, "instance: group transforms / swap_backface are not supported by ABI v1 (SURVEY §8f item 1)");
+        if (d->instances[i].root_node >= d->n_nodes) return fail(ctx, LGB_ERR_INVALID, "instance: root_node out of range");
+    }
+
+    // ---- validate the node graph and bound the traversal stack (bvh.rs:469: 64 entries)
+    const uint64_t nn = d->n_nodes;
+    std::vector<uint32_t> need(nn, 0);
+    for (uint64_t ii = nn; ii-- > 0;) {
+        const lgb_node& n = d->nodes[ii];
+        if (n.b & LGB_LEAF_FLAG) {
+            uint64_t cnt = n.b & ~LGB_LEAF_FLAG, first = n.a;
+            if (first + cnt > d->n_prim_refs) return fail(ctx, LGB_ERR_INVALID, "node: leaf range outside prim_refs");
+            uint32_t k = 0, worst = 0;
+            for (uint64_t j = 0; j < cnt; j++) {
+                uint32_t ref = d->prim_refs[first + j], type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+                uint64_t lim = type == LGB_PRIM_SPHERE ? d->n_spheres : type == LGB_PRIM_CUBOID ? d->n_cuboids : type == LGB_PRIM_TRIANGLE ? d->n_triangles : d->n_instances;
+                if (idx >= lim) return fail(ctx, LGB_ERR_INVALID, "prim_refs: index out of range");
+                if (type == LGB_PRIM_INSTANCE) {
+                    uint32_t root = d->instances[idx].root_node;
+                    if (root <= ii) return fail(ctx, LGB_ERR_INVALID, "instance: child BVH nodes must follow the referencing leaf");
+                    k++;
+                    worst = std::max(worst, need[root]);
+                }
+            }
+            need[ii] = k ? (k - 1) + std::max(1u, worst) : 0;   // k roots pushed, popped one at a time
+        } else {
+            if (n.b > 2) return fail(ctx, LGB_ERR_INVALID, "node: split axis out of range");
+            if (ii + 1 >= nn || n.a <= ii + 1 || n.a >= nn) return fail(ctx, LGB_ERR_INVALID, "node: child index out of range (pre-order expected)");
+            need[ii] = 1 + std::max(need[ii + 1], need[n.a]);
+        }
+    }
+    if (need[0] > (uint32_t)kStackDepth) return fail(ctx, LGB_ERR_UNSUPPORTED, "BVH needs more than 64 traversal stack entries (the reference would panic, bvh.rs:469)");
+
+    lgb_scene* s = new lgb_scene();
+    s->ctx = ctx;
+    int rc = LGB_OK;
+    auto bail = [&](int code) { lgb_scene_destroy(s); return code; };
+
+    // ---- coordinate magnitude bound -> f32 error bound used by the conservative filters
+    double M = 0.0;
+    auto upd = [&](double v) { double a = std::fabs(v); if (a > M && std::isfinite(a)) M = a; };
+    for (int k = 0; k < 3; k++) { upd(d->nodes[0].lo[k]); upd(d->nodes[0].hi[k]); upd(d->camera.origin[k]); }
+    for (uint64_t i = 0; i < d->n_instances; i++) for (int k = 0; k < 3; k++) { upd(d->nodes[d->instances[i].root_node].lo[k]); upd(d->nodes[d->instances[i].root_node].hi[k]); }
+    // orthographic origins move across the image plane (camera.rs:126-128); aspect <= 4 assumed, checked per capture
+    M += 2.5 * std::fabs(d->camera.image_plane_height) * std::fabs(d->camera.pixel_separation);
+    s->max_abs = M;
+
+    // ---- nodes: pad boxes so that an f32-rounded ray stays conservative
+    // pad is finalised per capture (camera offsets); here the geometric part.
+    {
+        std::vector<float4> nodes(2 * nn);
+        const double pad = M * std::ldexp(1.0, -20);
+        for (uint64_t i = 0; i < nn; i++) {
+            const lgb_node& n = d->nodes[i];
+            float4 lo, hi;
+            lo.x = f32_down((double)n.lo[0] - pad); lo.y = f32_down((double)n.lo[1] - pad); lo.z = f32_down((double)n.lo[2] - pad);
+            hi.x = f32_up((double)n.hi[0] + pad); hi.y = f32_up((double)n.hi[1] + pad); hi.z = f32_up((double)n.hi[2] + pad);
+            std::memcpy(&lo.w, &n.a, 4); std::memcpy(&hi.w, &n.b, 4);
+            nodes[2 * i] = lo; nodes[2 * i + 1] = hi;
+        }
+        if ((rc = upload(s, nodes, &s->dev.nodes))) return bail(rc);
+        s->dev.n_nodes = (uint32_t)nn;
+        s->dev.err_abs = (float)(M * std::ldexp(1.0, -20));
+    }
+    {
+        std::vector<uint32_t> refs(d->prim_refs, d->prim_refs + d->n_prim_refs);
+        if ((rc = upload(s, refs, &s->dev.prim_refs))) return bail(rc);
+    }
+    if (d->n_spheres) {
+        std::vector<float4> s32(d->n_spheres); std::vector<double> s64(4 * d->n_spheres);
+        for (uint64_t i = 0; i < d->n_spheres; i++) {
+            const lgb_sphere& sp = d->spheres[i];
+            s32[i] = make_float4((float)sp.center[0], (float)sp.center[1], (float)sp.center[2], f32_up(sp.radius));
+            s64[4 * i] = sp.center[0]; s64[4 * i + 1] = sp.center[1]; s64[4 * i + 2] = sp.center[2]; s64[4 * i + 3] = sp.radius;
+        }
+        std::vector<uint32_t> m(d->sphere_material, d->sphere_material + d->n_spheres), id(d->sphere_id, d->sphere_id + d->n_spheres);
+        if ((rc = upload(s, s32, &s->dev.sph32)) || (rc = upload(s, s64, &s->dev.sph64)) || (rc = upload(s, m, &s->dev.sph_mat)) || (rc = upload(s, id, &s->dev.sph_id))) return bail(rc);
+    }
+    if (d->n_cuboids) {
+        std::vector<float4> c32(2 * d->n_cuboids); std::vector<double> c64(6 * d->n_cuboids);
+        const double pad = M * std::ldexp(1.0, -20);
+        for (uint64_t i = 0; i < d->n_cuboids; i++) {
+            const lgb_cuboid& c = d->cuboids[i];
+            c32[2 * i] = make_float4(f32_down(c.min[0] - pad), f32_down(c.min[1] - pad), f32_down(c.min[2] - pad), 0.f);
+            c32[2 * i + 1] = make_float4(f32_up(c.max[0] + pad), f32_up(c.max[1] + pad), f32_up(c.max[2] + pad), 0.f);
+            for (int k = 0; k < 3; k++) { c64[6 * i + k] = c.min[k]; c64[6 * i + 3 + k] = c.max[k]; }
+        }
+        std::vector<uint32_t> m(d->cuboid_material, d->cuboid_material + d->n_cuboids), id(d->cuboid_id, d->cuboid_id + d->n_cuboids);
+        if ((rc = upload(s, c32, &s->dev.cub32)) || (rc = upload(s, c64, &s->dev.cub64)) || (rc = upload(s, m, &s->dev.cub_mat)) || (rc = upload(s, id, &s->dev.cub_id))) return bail(rc);
+    }
+    if (d->n_triangles) {
+        std::vector<float4> t(3 * d->n_triangles);
+        std::vector<float> nrm;
+        for (uint64_t i = 0; i < d->n_triangles; i++) {
+            const lgb_triangle& tr = d->triangles[i];
+            uint32_t ni = kNoNormals;
+            if (d->tri_normals && (!d->tri_has_normals || d->tri_has_normals[i])) {
+                ni = (uint32_t)(nrm.size() / 9);
+                const lgb_tri_normals& q = d->tri_normals[i];
+                nrm.insert(nrm.end(), {q.n0[0], q.n0[1], q.n0[2], q.n1[0], q.n1[1], q.n1[2], q.n2[0], q.n2[1], q.n2[2]});
+            }
+            float4 a = make_float4(tr.p0[0], tr.p0[1], tr.p0[2], 0.f), b = make_float4(tr.p1[0], tr.p1[1], tr.p1[2], 0.f), c = make_float4(tr.p2[0], tr.p2[1], tr.p2[2], 0.f);
+            std::memcpy(&a.w, &d->triangle_id[i], 4); std::memcpy(&b.w, &d->triangle_material[i], 4); std::memcpy(&c.w, &ni, 4);
+            t[3 * i] = a; t[3 * i + 1] = b; t[3 * i + 2] = c;
+        }
+        if ((rc = upload(s, t, &s->dev.tri)) || (rc = upload(s, nrm, &s->dev.tri_nrm))) return bail(rc);
+    }
+    if (d->n_instances) {
+        std::vector<uint32_t> roots(d->n_instances);
+        for (uint64_t i = 0; i < d->n_instances; i++) roots[i] = d->instances[i].root_node;
+        if ((rc = upload(s, roots, &s->dev.inst_root))) return bail(rc);
+    }
+    if ((rc = upload(s, mats, &s->dev.materials))) return bail(rc);
+    {
+        std::vector<double> l(9 * d->n_lights);
+        for (uint64_t i = 0; i < d->n_lights; i++)
+            for (int k = 0; k < 3; k++) { l[9 * i + k] = d->lights[i].position[k]; l[9 * i + 3 + k] = d->lights[i].intensity[k]; l[9 * i + 6 + k] = d->lights[i].falloff[k]; }
+        if ((rc = upload(s, l, &s->dev.lights))) return bail(rc);
+        s->dev.n_lights = (uint32_t)d->n_lights;
+    }
+    for (int k = 0; k < 3; k++) {
+        s->cam.origin[k] = d->camera.origin[k]; s->cam.view[k] = d->camera.view[k]; s->cam.up[k] = d->camera.up[k]; s->cam.aux[k] = d->camera.aux[k];
+        s->shade.ambient[k] = d->ambient[k]; s->shade.bg_inner[k] = d->bg_inner[k]; s->shade.bg_outer[k] = d->bg_outer[k];
+    }
+    s->cam.image_plane_height = d->camera.image_plane_height;
+    s->cam.pixel_separation = d->camera.pixel_separation;
+    s->cam.sample_distance = d->camera.sample_distance;
+    s->cam.root = d->camera.supersampling_root;
+    s->shade.bg_scale = d->bg_scale;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);     // host vectors die at scope end
+    if (e != cudaSuccess) { cuda_fail(ctx, e, "scene upload"); return bail(LGB_ERR_CUDA); }
+    *out = s;
+    return LGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- capture
+// Macro tiles are dealt to ranks round-robin along anti-diagonals: owner = (mx + my) % ranks.
+static void build_tile_list(lgb_ctx* c, uint32_t w, uint32_t h, uint32_t rank, uint32_t ranks) {
+    if (c->tile_key[0] == w && c->tile_key[1] == h && c->tile_key[2] == rank && c->tile_key[3] == ranks && c->tile_count) return;
+    const uint32_t nmx = (w + kMacroTile - 1) / kMacroTile, nmy = (h + kMacroTile - 1) / kMacroTile;
+    c->tile_host.clear();
+    for (uint32_t my = 0; my < nmy; my++)
+        for (uint32_t mx = 0; mx < nmx; mx++)
+            if ((mx + my) % ranks == rank) c->tile_host.push_back(my * nmx + mx);
+    c->tile_key[0] = w; c->tile_key[1] = h; c->tile_key[2] = rank; c->tile_key[3] = ranks;
+    c->tile_count = 0;   // uploaded lazily
+}
+
+struct CaptureArgs {
+    uint32_t w, h;
+    uint32_t mode;               // 0 tiles, 1 stride subset
+    uint32_t rank, ranks, k, n;
+    bool aov;
+    void* d_film;                // device film or NULL (context film)
+    cudaStream_t stream;
+};
+
+static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats* stats, bool sync_stats) {
+    if (!c || !s || s->ctx != c) return fail(c, LGB_ERR_INVALID, "capture: scene does not belong to this context");
+    if (a.w == 0 || a.h == 0 || (uint64_t)a.w * a.h >= (1ull << 32)) return fail(c, LGB_ERR_INVALID, "capture: bad film size");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = a.stream ? a.stream : c->stream;
+    DevWork W{};
+    W.mode = a.mode; W.w = a.w; W.h = a.h;
+    W.winv = 1.0 / (double)a.w; W.hinv = 1.0 / (double)a.h; W.aspect = (double)a.w / (double)a.h;   // film.rs:36-45
+    W.spp = s->cam.root * s->cam.root;
+    if (a.mode == 0) {
+        if (a.ranks == 0 || a.rank >= a.ranks) return fail(c, LGB_ERR_INVALID, "capture: tile_rank out of range");
+        build_tile_list(c, a.w, a.h, a.rank, a.ranks);
+        if (!c->tile_count && !c->tile_host.empty()) {
+            CU(c, c->tiles.reserve(c->tile_host.size() * 4));
+            CU(c, cudaMemcpyAsync(c->tiles.p, c->tile_host.data(), c->tile_host.size() * 4, cudaMemcpyHostToDevice, st));
+            CU(c, cudaStreamSynchronize(st));
+            c->tile_count = (uint32_t)c->tile_host.size();
+        }
+        W.tile_list = (const uint32_t*)c->tiles.p;
+        W.n_tiles = (uint32_t)c->tile_host.size();
+        W.n_macro_x = (a.w + kMacroTile - 1) / kMacroTile;
+        W.n_pixels = (uint64_t)W.n_tiles * kMacroTile * kMacroTile;
+    } else {
+        if (a.n == 0 || a.k >= a.n) return fail(c, LGB_ERR_INVALID, "capture_subset: need k < n");
+        const uint64_t area = (uint64_t)a.w * a.h;
+        W.sub_k = a.k; W.sub_n = a.n;
+        W.n_pixels = area > a.k ? (area - a.k + a.n - 1) / a.n : 0;
+        W.compact_out = 1;
+    }
+    const uint64_t total = W.n_pixels * W.spp;
+    if (total >= (1ull << 32) * 256) return fail(c, LGB_ERR_INVALID, "capture: too many samples for one launch");
+    if (s->cam.pixel_separation != 0.0 && W.aspect > 4.0)
+        return fail(c, LGB_ERR_UNSUPPORTED, "orthographic capture with aspect > 4: the scene's coordinate bound assumed aspect <= 4");
+    const DevScene& S = s->dev;
+    CU(c, c->radiance.reserve(std::max<uint64_t>(total, 1) * 3 * sizeof(double)));
+    CU(c, c->counters.reserve(sizeof(DevCounters)));
+    DevOut O{};
+    O.radiance = (double*)c->radiance.p;
+    O.counters = (DevCounters*)c->counters.p;
+    const uint64_t area = (uint64_t)a.w * a.h;
+    if (a.d_film) O.film = (uint8_t*)a.d_film;
+    else {
+        CU(c, c->film.reserve(std::max<uint64_t>(a.mode == 0 ? area : W.n_pixels, 1) * 4));
+        O.film = (uint8_t*)c->film.p;
+    }
+    if (a.aov) {
+        CU(c, c->aov_id.reserve(area * W.spp * 4)); CU(c, c->aov_t.reserve(area * W.spp * 8)); CU(c, c->aov_occl.reserve(area * W.spp * 4));
+        O.aov_id = (uint32_t*)c->aov_id.p; O.aov_t = (double*)c->aov_t.p; O.aov_occl = (uint32_t*)c->aov_occl.p;
+    }
+    CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));
+    CU(c, cudaEventRecord(c->ev0, st));
+    CU(c, launch_render(S, s->cam, s->shade, W, O, a.aov, st));
+    CU(c, cudaEventRecord(c->ev1, st));
+    if (stats && sync_stats) {
+        DevCounters hc;
+        CU(c, cudaMemcpyAsync(&hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+        std::memset(stats, 0, sizeof *stats);
+        stats->primary_rays = hc.primary_rays; stats->primary_hits = hc.primary_hits;
+        stats->shadow_rays = hc.primary_hits * s->dev.n_lights;
+        stats->shadow_rays_traced = hc.shadow_traced; stats->shadow_occluded = hc.shadow_occluded;
+        stats->exact_tests = hc.exact_tests; stats->filter_tests = hc.filter_tests; stats->node_tests = hc.node_tests;
+        stats->stack_overflow = hc.stack_overflow;
+        stats->kernel_launches = total ? 2 : 0;
+        float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        stats->render_ms = ms; stats->total_ms = ms;
+    }
+    return LGB_OK;
+}
+
+int lgb_capture_device(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint32_t rank, uint32_t ranks, void* d_film, void* stream, lgb_stats* stats) {
+    if (!d_film) return fail(c, LGB_ERR_INVALID, "lgb_capture_device: d_film is NULL");
+    CaptureArgs a{w, h, 0, rank, ranks, 0, 0, false, d_film, (cudaStream_t)stream};
+    return run_capture(c, s, a, stats, stats != nullptr);
+}
+
+static int finish_host(lgb_ctx* c, const void* dev, void* host, size_t bytes, lgb_stats* stats) {
+    CU(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaEventRecord(c->ev2, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (stats) { float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev2)); stats->total_ms = ms; }
+    return LGB_OK;
+}
+
+int lgb_capture(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint8_t* rgba, lgb_stats* stats) {
+    if (!rgba) return fail(c, LGB_ERR_INVALID, "lgb_capture: rgba_out is NULL");
+    lgb_stats local; lgb_stats* stp = stats ? stats : &local;
+    CaptureArgs a{w, h, 0, 0, 1, 0, 0, false, nullptr, nullptr};
+    int rc = run_capture(c, s, a, stp, true);
+    if (rc) return rc;
+    if (stp->stack_overflow) return fail(c, LGB_ERR_UNSUPPORTED, "traversal stack overflow");
+    return finish_host(c, c->film.p, rgba, (size_t)w * h * 4, stp);
+}
+
+int lgb_capture_aov(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint8_t* rgba, uint32_t* prim_id, double* t, uint32_t* occl, lgb_stats* stats) {
+    lgb_stats local; lgb_stats* stp = stats ? stats : &local;
+    CaptureArgs a{w, h, 0, 0, 1, 0, 0, true, nullptr, nullptr};
+    int rc = run_capture(c, s, a, stp, true);
+    if (rc) return rc;
+    const uint64_t ns = (uint64_t)w * h * s->cam.root * s->cam.root;
+    if (prim_id) CU(c, cudaMemcpyAsync(prim_id, c->aov_id.p, ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (t) CU(c, cudaMemcpyAsync(t, c->aov_t.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (occl) CU(c, cudaMemcpyAsync(occl, c->aov_occl.p, ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (rgba) return finish_host(c, c->film.p, rgba, (size_t)w * h * 4, stp);
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LGB_OK;
+}
+
+int lgb_capture_subset(lgb_ctx* c, lgb_scene* s, uint32_t k, uint32_t n, uint32_t w, uint32_t h, uint8_t* rgba, lgb_stats* stats) {
+    if (!rgba) return fail(c, LGB_ERR_INVALID, "lgb_capture_subset: rgba_inout is NULL");
+    lgb_stats local; lgb_stats* stp = stats ? stats : &local;
+    CaptureArgs a{w, h, 1, 0, 1, k, n, false, nullptr, nullptr};
+    int rc = run_capture(c, s, a, stp, true);
+    if (rc) return rc;
+    const uint64_t area = (uint64_t)w * h;
+    const uint64_t np = area > k ? (area - k + n - 1) / n : 0;
+    std::vector<uint8_t> compact(np * 4);
+    if (np) { rc = finish_host(c, c->film.p, compact.data(), np * 4, stp); if (rc) return rc; }
+    for (uint64_t p = 0; p < np; p++) std::memcpy(rgba + (k + p * (uint64_t)n) * 4, &compact[4 * p], 4);   // lib.rs:152-161
+    return LGB_OK;
+}
+
+int lgb_trace_rays(lgb_ctx* c, lgb_scene* s, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns) {
+    if (!c || !s || (!rays && n)) return fail(c, LGB_ERR_INVALID, "lgb_trace_rays: NULL argument");
+    CU(c, cudaSetDevice(c->device));
+    if (n == 0) return LGB_OK;
+    const size_t need = n * (48 + 4 + 8 + 24 + 24);
+    CU(c, c->scratch.reserve(need));
+    char* base = (char*)c->scratch.p;
+    double* d_rays = (double*)base; double* d_t = (double*)(base + n * 48); double* d_ng = (double*)(base + n * 56); double* d_ns = (double*)(base + n * 80);
+    uint32_t* d_id = (uint32_t*)(base + n * 104);
+    CU(c, cudaMemcpyAsync(d_rays, rays, n * 48, cudaMemcpyHostToDevice, c->stream));
+    CU(c, launch_trace(s->dev, d_rays, n, d_id, d_t, d_ng, d_ns, c->stream));
+    if (ids) CU(c, cudaMemcpyAsync(ids, d_id, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (ts) CU(c, cudaMemcpyAsync(ts, d_t, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (ng) CU(c, cudaMemcpyAsync(ng, d_ng, n * 24, cudaMemcpyDeviceToHost, c->stream));
+    if (ns) CU(c, cudaMemcpyAsync(ns, d_ns, n * 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------- ceilings
+int lgb_measure_l2_read_gbs(lgb_ctx* c, uint64_t bytes, int iters, double* out) {
+    if (!c || !out || bytes < 4096 || iters < 1) return fail(c, LGB_ERR_INVALID, "lgb_measure_l2_read_gbs: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    bytes &= ~(uint64_t)15;
+    CU(c, c->scratch.reserve(bytes + 16));
+    CU(c, cudaMemsetAsync(c->scratch.p, 0, bytes + 16, c->stream));
+    float* sink = (float*)((char*)c->scratch.p + bytes);
+    CU(c, launch_l2_read(c->scratch.p, bytes, 2, sink, c->sm_count, c->stream));   // warm L2
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    CU(c, launch_l2_read(c->scratch.p, bytes, iters, sink, c->sm_count, c->stream));
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *out = (double)bytes * iters / (ms * 1e-3) / 1e9;
+    return LGB_OK;
+}
+int lgb_measure_fp32_gops(lgb_ctx* c, int iters, double* out) {
+    if (!c || !out || iters < 1) return fail(c, LGB_ERR_INVALID, "lgb_measure_fp32_gops: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, c->scratch.reserve(64));
+    CU(c, launch_fp32_peak(iters / 8 + 1, (float*)c->scratch.p, c->sm_count, c->stream));
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    CU(c, launch_fp32_peak(iters, (float*)c->scratch.p, c->sm_count, c->stream));
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *out = (double)c->sm_count * 8 * 256 * 8.0 * iters / (ms * 1e-3) / 1e9;    // FFMA lane-instructions per second (GHz-lanes)
+    return LGB_OK;
+}
+int lgb_measure_fp64_gops(lgb_ctx* c, int iters, double* out) {
+    if (!c || !out || iters < 1) return fail(c, LGB_ERR_INVALID, "lgb_measure_fp64_gops: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, c->scratch.reserve(64));
+    CU(c, launch_fp64_peak(iters / 8 + 1, (double*)c->scratch.p, c->sm_count, c->stream));
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    CU(c, launch_fp64_peak(iters, (double*)c->scratch.p, c->sm_count, c->stream));
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *out = (double)c->sm_count * 8 * 256 * 8.0 * iters / (ms * 1e-3) / 1e9;
+    return LGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,548 @@
+// Render kernels: camera rays -> closest-hit traversal -> plastic shading with point-light shadow
+// rays -> per-sample radiance; resolve -> RGBA8 film.  sm_100a, compiled with -fmad=false.
+//
+// Precision scheme: traversal culling and primitive *filters* run in f32 and are
+// conservative (they never reject what the reference's f64 test would accept); every candidate
+// that survives is re-tested with the reference's own f64 arithmetic (lgb_math.cuh), so the
+// closest-hit primitive and its t are the reference's, and shading runs in f64 in the
+// reference's operation order (integrate.rs:23-80).
+#include <math_constants.h>
+
+#include "lgb_math.cuh"
+
+namespace lgb {
+
+// ------------------------------------------------------------------ per-ray f32 state
+struct RayF {
+    float ox, oy, oz;
+    float ix, iy, iz;        // 1/d (rounded from the f64 reciprocal)
+    float dx, dy, dz;
+    float inv_dd, inv_len;   // 1/(d.d), 1/|d|
+    float sx, sy, sz;        // triangle shear (triangle.rs:199-201), f32 copies
+    float err;               // absolute coordinate error bound; +inf disables the filters
+    int kx, ky, kz;
+};
+
+__device__ __forceinline__ RayF make_rayf(const Ray64& r, float err_abs) {
+    RayF f;
+    f.ox = (float)r.o.x; f.oy = (float)r.o.y; f.oz = (float)r.o.z;
+    f.ix = (float)(1.0 / r.d.x); f.iy = (float)(1.0 / r.d.y); f.iz = (float)(1.0 / r.d.z);
+    f.dx = (float)r.d.x; f.dy = (float)r.d.y; f.dz = (float)r.d.z;
+    float dd = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
+    f.inv_dd = 1.0f / dd;
+    f.inv_len = rsqrtf(dd);
+    // |d| outside the comfortable f32 range: make every filter band infinite (exact tests only).
+    f.err = (dd > 1e-24f && dd < 1e24f) ? err_abs : CUDART_INF_F;
+    f.kz = max_dimension_abs(r.d);
+    f.kx = (f.kz + 1) % 3;
+    f.ky = (f.kx + 1) % 3;
+    float fdz = f.kz == 0 ? f.dx : (f.kz == 1 ? f.dy : f.dz);
+    float fdx = f.kx == 0 ? f.dx : (f.kx == 1 ? f.dy : f.dz);
+    float fdy = f.ky == 0 ? f.dx : (f.ky == 1 ? f.dy : f.dz);
+    f.sz = 1.0f / fdz;
+    f.sx = -fdx * f.sz;
+    f.sy = -fdy * f.sz;
+    return f;
+}
+
+__device__ __forceinline__ float pick(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
+
+// Conservative slab test of an f32 ray against a padded f32 box.  Returns false only if the exact
+// (f64) ray certainly misses the exact box or enters it beyond tbest.  See DESIGN.md §4.1.
+__device__ __forceinline__ bool slab_conservative(const float4 lo, const float4 hi, const RayF& f, float tbest) {
+    float t1x = (lo.x - f.ox) * f.ix, t2x = (hi.x - f.ox) * f.ix;
+    float t1y = (lo.y - f.oy) * f.iy, t2y = (hi.y - f.oy) * f.iy;
+    float t1z = (lo.z - f.oz) * f.iz, t2z = (hi.z - f.oz) * f.iz;
+    float tnear = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
+    float tfar = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
+    const float up = 1.0f + 4.76837158e-7f, dn = 1.0f - 4.76837158e-7f;   // 1 +- 2^-21
+    tfar = tfar * up;                      // tfar < 0 is rejected either way
+    tnear = tnear > 0.0f ? tnear * dn : tnear * up;
+    return tnear <= tfar && tfar > 0.0f && tnear <= tbest;
+}
+
+struct Hit { double t; uint32_t ref; };
+
+struct LocalCounters { unsigned int node_tests, filter_tests, exact_tests; };
+
+// Closest hit (ANYHIT = false) or "any hit with t < tmax" (ANYHIT = true, shadow rays: the
+// reference asks for the closest t and compares it with 1.0, light/point.rs:48-49, which is
+// equivalent).  Traversal order and push order follow bvh.rs:461-506; the extra
+// `tnear > best` cull is result-safe because every primitive rejects t >= isect.t itself.
+template <bool ANYHIT, bool STATS>
+__device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalCounters& lc, unsigned int& overflow) {
+    const RayF f = make_rayf(ray, S.err_abs);
+    const unsigned neg_mask = (f.ix < 0.0f ? 1u : 0u) | (f.iy < 0.0f ? 2u : 0u) | (f.iz < 0.0f ? 4u : 0u);
+    Hit best; best.t = tmax; best.ref = LGB_MISS;
+    float best_tf = __double2float_ru(tmax);
+    const float err = f.err;
+    uint32_t stack[kStackDepth];
+    int sp = 0;
+    uint32_t node = 0;
+    for (;;) {
+        const float4 n0 = __ldg(&S.nodes[2 * node]);
+        const float4 n1 = __ldg(&S.nodes[2 * node + 1]);
+        if (STATS) lc.node_tests++;
+        if (slab_conservative(n0, n1, f, best_tf)) {
+            const uint32_t a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
+            if (b & LGB_LEAF_FLAG) {
+                const uint32_t count = b & ~LGB_LEAF_FLAG;
+                for (uint32_t i = 0; i < count; i++) {
+                    const uint32_t ref = __ldg(&S.prim_refs[a + i]);
+                    const uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+                    if (type == LGB_PRIM_TRIANGLE) {
+                        const float4 q0 = __ldg(&S.tri[3 * idx]), q1 = __ldg(&S.tri[3 * idx + 1]), q2 = __ldg(&S.tri[3 * idx + 2]);
+                        if (STATS) lc.filter_tests++;
+                        // f32 watertight edge functions with an error band
+                        float ax = q0.x - f.ox, ay = q0.y - f.oy, az = q0.z - f.oz;
+                        float bx = q1.x - f.ox, by = q1.y - f.oy, bz = q1.z - f.oz;
+                        float cx = q2.x - f.ox, cy = q2.y - f.oy, cz = q2.z - f.oz;
+                        float Az = pick(ax, ay, az, f.kz), Bz = pick(bx, by, bz, f.kz), Cz = pick(cx, cy, cz, f.kz);
+                        float Ax = __fmaf_rn(f.sx, Az, pick(ax, ay, az, f.kx)), Ay = __fmaf_rn(f.sy, Az, pick(ax, ay, az, f.ky));
+                        float Bx = __fmaf_rn(f.sx, Bz, pick(bx, by, bz, f.kx)), By = __fmaf_rn(f.sy, Bz, pick(bx, by, bz, f.ky));
+                        float Cx = __fmaf_rn(f.sx, Cz, pick(cx, cy, cz, f.kx)), Cy = __fmaf_rn(f.sy, Cz, pick(cx, cy, cz, f.ky));
+                        float e0 = Bx * Cy - By * Cx, e1 = Cx * Ay - Cy * Ax, e2 = Ax * By - Ay * Bx;
+                        float m = fmaxf(fmaxf(fmaxf(fabsf(Ax), fabsf(Ay)), fmaxf(fabsf(Bx), fabsf(By))), fmaxf(fabsf(Cx), fabsf(Cy)));
+                        float band = 6.0f * m * err;
+                        float emin = fminf(fminf(e0, e1), e2), emax = fmaxf(fmaxf(e0, e1), e2);
+                        if (emin < -band && emax > band) continue;
+                        // depth range of the triangle along the ray
+                        float tz0 = Az * f.sz, tz1 = Bz * f.sz, tz2 = Cz * f.sz;
+                        float tlo = fminf(fminf(tz0, tz1), tz2), thi = fmaxf(fmaxf(tz0, tz1), tz2);
+                        float slack = err * fabsf(f.sz);
+                        if (tlo - slack - fabsf(tlo) * 1e-6f > best_tf) continue;
+                        if (thi + slack + fabsf(thi) * 1e-6f < 0.0f) continue;
+                        if (STATS) lc.exact_tests++;
+                        double t, b0, b1, b2;
+                        if (triangle_exact(d3(q0.x, q0.y, q0.z), d3(q1.x, q1.y, q1.z), d3(q2.x, q2.y, q2.z), ray, best.t, t, b0, b1, b2)) {
+                            best.t = t; best.ref = ref; best_tf = __double2float_ru(t);
+                            if (ANYHIT) return best;
+                        }
+                    } else if (type == LGB_PRIM_SPHERE) {
+                        const float4 s = __ldg(&S.sph32[idx]);
+                        if (STATS) lc.filter_tests++;
+                        float lx = s.x - f.ox, ly = s.y - f.oy, lz = s.z - f.oz;
+                        float bq = lx * f.dx + ly * f.dy + lz * f.dz;
+                        float tc = bq * f.inv_dd;
+                        float wx = __fmaf_rn(-tc, f.dx, lx), wy = __fmaf_rn(-tc, f.dy, ly), wz = __fmaf_rn(-tc, f.dz, lz);
+                        float perp2 = wx * wx + wy * wy + wz * wz;
+                        float rr = s.w + 2.0f * err;
+                        if (perp2 > rr * rr * (1.0f + 1e-6f)) continue;
+                        float half = rr * f.inv_len;
+                        float slack = fabsf(tc) * 2e-6f + 2.0f * err * f.inv_len;
+                        if (tc - half - slack > best_tf) continue;
+                        if (tc + half + slack < 0.0f) continue;
+                        if (STATS) lc.exact_tests++;
+                        const double2 c01 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx));
+                        const double2 c23 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx + 2));
+                        double t; bool inside;
+                        if (sphere_exact(d3(c01.x, c01.y, c23.x), c23.y, ray, best.t, t, inside)) {
+                            best.t = t; best.ref = ref; best_tf = __double2float_ru(t);
+                            if (ANYHIT) return best;
+                        }
+                    } else if (type == LGB_PRIM_CUBOID) {
+                        const float4 lo = __ldg(&S.cub32[2 * idx]), hi = __ldg(&S.cub32[2 * idx + 1]);
+                        if (STATS) lc.filter_tests++;
+                        if (!slab_conservative(lo, hi, f, CUDART_INF_F)) continue;
+                        if (STATS) lc.exact_tests++;
+                        double mn[3], mx[3];
+#pragma unroll
+                        for (int k = 0; k < 3; k++) { mn[k] = __ldg(&S.cub64[6 * (size_t)idx + k]); mx[k] = __ldg(&S.cub64[6 * (size_t)idx + 3 + k]); }
+                        double t; int ua, va;
+                        if (cuboid_exact(mn, mx, ray, best.t, t, ua, va)) {
+                            best.t = t; best.ref = ref; best_tf = __double2float_ru(t);
+                            if (ANYHIT) return best;
+                        }
+                    } else {   // nested BVH with identity transform (bvh.rs:141-162): descend later
+                        if (sp < kStackDepth) stack[sp++] = __ldg(&S.inst_root[idx]); else overflow = 1;
+                    }
+                }
+            } else {
+                // interior: far child on the stack, continue with the near one (bvh.rs:493-504)
+                const bool neg = (neg_mask >> b) & 1u;
+                const uint32_t near_child = neg ? a : node + 1, far_child = neg ? node + 1 : a;
+                if (sp < kStackDepth) stack[sp++] = far_child; else overflow = 1;
+                node = near_child;
+                continue;
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------ surface record of the winner
+struct Surf {
+    D3 g_dpdu, g_dpdv, s_dpdu, s_dpdv, n;
+    bool has_n;
+    uint32_t material, id;
+};
+
+// Re-derives the reference's RayIntersection for the closest primitive (sphere.rs:88-120,
+// cuboid.rs:97-99, triangle.rs:257-304).  The sphere differentials use sin(theta) = sqrt(1 - cos^2)
+// and cos/sin(phi) = p.xy / |p.xy| instead of acos/atan2/sin/cos (same vectors up to rounding).
+__device__ void surface_of(const DevScene& S, const Ray64& ray, uint32_t ref, double& t, Surf& sf) {
+    const uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+    const double PI = 3.14159265358979323846264338327950288;
+    sf.has_n = false; sf.n = d3(0, 0, 0);
+    if (type == LGB_PRIM_SPHERE) {
+        D3 c = d3(S.sph64[4 * (size_t)idx], S.sph64[4 * (size_t)idx + 1], S.sph64[4 * (size_t)idx + 2]);
+        double rad = S.sph64[4 * (size_t)idx + 3];
+        bool inside; double tt;
+        sphere_exact(c, rad, ray, CUDART_INF, tt, inside);
+        t = tt;
+        D3 p = ray.o + ray.d * tt - c;
+        if (p.x == 0.0 && p.y == 0.0) p.x = 1e-5 * rad;
+        double rho = sqrt(p.x * p.x + p.y * p.y);
+        double cphi = p.x / rho, sphi = p.y / rho;
+        double cz = fmin(fmax(p.z / rad, -1.0), 1.0);
+        double sth = sqrt(fmax(1.0 - cz * cz, 0.0));
+        D3 dpdu = d3(-2.0 * PI * p.y, 2.0 * PI * p.x, 0.0);
+        D3 dpdv = PI * d3(p.z * cphi, p.z * sphi, -rad * sth);
+        if (!inside) { D3 tmp = dpdu; dpdu = dpdv; dpdv = tmp; }
+        sf.g_dpdu = dpdu; sf.g_dpdv = dpdv; sf.s_dpdu = dpdu; sf.s_dpdv = dpdv;
+        sf.material = S.sph_mat[idx]; sf.id = S.sph_id[idx];
+    } else if (type == LGB_PRIM_CUBOID) {
+        double mn[3], mx[3];
+        for (int k = 0; k < 3; k++) { mn[k] = S.cub64[6 * (size_t)idx + k]; mx[k] = S.cub64[6 * (size_t)idx + 3 + k]; }
+        int ua = 1, va = 2; double tt = t;
+        cuboid_exact(mn, mx, ray, CUDART_INF, tt, ua, va);
+        t = tt;
+        D3 du = axis_vec(ua), dv = axis_vec(va);
+        sf.g_dpdu = du; sf.g_dpdv = dv; sf.s_dpdu = du; sf.s_dpdv = dv;
+        sf.has_n = true; sf.n = face_forward(cross(du, dv), -ray.d);
+        sf.material = S.cub_mat[idx]; sf.id = S.cub_id[idx];
+    } else {
+        const float4 q0 = S.tri[3 * (size_t)idx], q1 = S.tri[3 * (size_t)idx + 1], q2 = S.tri[3 * (size_t)idx + 2];
+        D3 p0 = d3(q0.x, q0.y, q0.z), p1 = d3(q1.x, q1.y, q1.z), p2 = d3(q2.x, q2.y, q2.z);
+        double tt = t, b0 = 0, b1 = 0, b2 = 0;
+        triangle_exact(p0, p1, p2, ray, CUDART_INF, tt, b0, b1, b2);
+        t = tt;
+        D3 dp02 = p0 - p2, dp12 = p1 - p2;
+        // default uvs (0,0) (1,0) (1,1): determinant 1, dpdu = -dp02 + dp12, dpdv = dp12 (triangle.rs:258-270)
+        D3 dpdu = (-1.0 * dp02 - -1.0 * dp12) * 1.0;
+        D3 dpdv = (-0.0 * dp02 - -1.0 * dp12) * 1.0;
+        sf.g_dpdu = dpdu; sf.g_dpdv = dpdv; sf.s_dpdu = dpdu; sf.s_dpdv = dpdv;
+        sf.has_n = true;
+        const uint32_t ni = __float_as_uint(q2.w);
+        if (ni != kNoNormals) {                                        // triangle.rs:284-299
+            const float* nn = S.tri_nrm + 9 * (size_t)ni;
+            D3 n0 = d3(nn[0], nn[1], nn[2]), n1 = d3(nn[3], nn[4], nn[5]), n2 = d3(nn[6], nn[7], nn[8]);
+            D3 ns = b0 * n0 + b1 * n1 + b2 * n2;
+            D3 ss = dpdu;
+            D3 ts = cross(ns, ss);
+            if (dot(ts, ts) > 0.0) ss = cross(ts, ns); else coordinate_system(ns, ss, ts);
+            sf.n = ns; sf.s_dpdu = ss; sf.s_dpdv = ts;
+        } else {                                                       // triangle.rs:300-304
+            sf.n = face_forward(cross(dp02, dp12), -ray.d);
+        }
+        sf.material = __float_as_uint(q1.w); sf.id = __float_as_uint(q0.w);
+    }
+}
+
+// ------------------------------------------------------------------ BSDF (bsdf.rs:73-92, bxdf/*)
+__device__ __forceinline__ double cos2_theta(D3 w) { return w.z * w.z; }
+__device__ __forceinline__ double sin2_theta(D3 w) { return fmax(1.0 - cos2_theta(w), 0.0); }
+__device__ __forceinline__ double sin_theta(D3 w) { return sqrt(sin2_theta(w)); }
+__device__ __forceinline__ double cos_phi(D3 w) { double s = sin_theta(w); return s == 0.0 ? 1.0 : fmin(fmax(w.x / s, -1.0), 1.0); }
+__device__ __forceinline__ double sin_phi(D3 w) { double s = sin_theta(w); return s == 0.0 ? 0.0 : fmin(fmax(w.y / s, -1.0), 1.0); }
+
+__device__ double dielectric(double cos_i, double eta_i, double eta_t) {     // fresnel.rs:37-64
+    cos_i = fmin(fmax(cos_i, -1.0), 1.0);
+    if (!(cos_i > 0.0)) { double tmp = eta_i; eta_i = eta_t; eta_t = tmp; cos_i = fabs(cos_i); }
+    double sin_i = sqrt(fmax(1.0 - cos_i * cos_i, 0.0));
+    double sin_t = eta_i / eta_t * sin_i;
+    if (sin_t >= 1.0) return 1.0;
+    double cos_t = sqrt(fmax(1.0 - sin_t * sin_t, 0.0));
+    double r_parl = ((eta_t * cos_i) - (eta_i * cos_t)) / ((eta_t * cos_i) + (eta_i * cos_t));
+    double r_perp = ((eta_i * cos_i) - (eta_t * cos_t)) / ((eta_i * cos_i) + (eta_t * cos_t));
+    return (r_parl * r_parl + r_perp * r_perp) * 0.5;
+}
+__device__ double tr_d(double ax, double ay, D3 wh) {                         // microfacet.rs:31-40
+    double t2 = sin2_theta(wh) / cos2_theta(wh);
+    if (isinf(t2)) return 0.0;
+    const double PI = 3.14159265358979323846264338327950288;
+    double cos4 = cos2_theta(wh) * cos2_theta(wh);
+    double cp = cos_phi(wh), sp = sin_phi(wh);
+    double e = ((cp * cp) / (ax * ax) + (sp * sp) / (ay * ay)) * t2;
+    return 1.0 / (PI * ax * ay * cos4 * (1.0 + e) * (1.0 + e));
+}
+__device__ double tr_lambda(double ax, double ay, D3 w) {                     // microfacet.rs:55-66
+    double att = fabs(sin_theta(w) / w.z);
+    if (isinf(att)) return 0.0;
+    double cp = cos_phi(w), sp = sin_phi(w);
+    double alpha = sqrt((cp * cp) * ax * ax + (sp * sp) * ay * ay);
+    double a2t2 = (alpha * att) * (alpha * att);
+    return (sqrt(1.0 + a2t2) - 1.0) / 2.0;
+}
+struct Bsdf { D3 ng, ns, ss, ts, kd, ks; double alpha; bool diffuse, glossy; };
+__device__ D3 bsdf_f(const Bsdf& B, D3 wo, D3 wi) {
+    bool reflect = dot(wi, B.ng) * dot(wo, B.ng) > 0.0;
+    D3 wo_l = d3(dot(wo, B.ss), dot(wo, B.ts), dot(wo, B.ns));
+    D3 wi_l = d3(dot(wi, B.ss), dot(wi, B.ts), dot(wi, B.ns));
+    D3 f = d3(0, 0, 0);
+    if (wo_l.z == 0.0) return f;
+    if (!reflect) return f;                 // every lobe on this path is REFLECTION (bxdf/mod.rs:145-147)
+    if (B.diffuse) f = f + B.kd * 0.318309886183790671537767526745028724;       // diffuse.rs:14
+    if (B.glossy) {                                                              // microfacet.rs:101-115
+        double cos_o = fabs(wo_l.z), cos_i = fabs(wi_l.z);
+        D3 wh = wi_l + wo_l;
+        D3 m = d3(0, 0, 0);
+        if (!(cos_i == 0.0 || cos_o == 0.0) && !(wh.x == 0.0 && wh.y == 0.0 && wh.z == 0.0)) {
+            wh = normalize(wh);
+            double F = dielectric(dot(wi_l, wh), 1.0, 1.5);
+            double g = 1.0 / (1.0 + tr_lambda(B.alpha, B.alpha, wo_l) + tr_lambda(B.alpha, B.alpha, wi_l));
+            m = mul_el(B.ks * tr_d(B.alpha, B.alpha, wh) * g, d3(F, F, F)) / (4.0 * cos_i * cos_o);
+        }
+        f = f + m;
+    }
+    return f;
+}
+
+__device__ __forceinline__ double lerp64(double t, double a, double b) { return a * (1.0 - t) + b * t; }
+
+struct SampleOut { D3 color; uint32_t id; double t; uint32_t occl; uint32_t hit; uint32_t shadow_traced; uint32_t shadow_occl; };
+
+// integrate.rs:23-80 for one ray.
+template <bool STATS, bool ALL_SHADOWS>
+__device__ void li(const DevScene& S, const DevShade& sh, const Ray64& ray, SampleOut& out, LocalCounters& lc, unsigned int& overflow) {
+    const double PI = 3.14159265358979323846264338327950288;
+    out.id = LGB_MISS; out.t = CUDART_INF; out.occl = 0; out.hit = 0; out.shadow_traced = 0; out.shadow_occl = 0;
+    Hit h = traverse<false, STATS>(S, ray, CUDART_INF, lc, overflow);
+    if (h.ref == LGB_MISS) {                                   // background.rs:25-34
+        D3 dn = normalize(ray.d);
+        double dz = fabs(0.0 * dn.x + 0.0 * dn.y + 1.0 * dn.z);
+        double t = fmin(sqrt(1.0 - dz * dz) / sh.bg_scale, 1.0);
+        out.color = d3(lerp64(t, sh.bg_inner[0], sh.bg_outer[0]), lerp64(t, sh.bg_inner[1], sh.bg_outer[1]),
+                       lerp64(t, sh.bg_inner[2], sh.bg_outer[2]));
+        return;
+    }
+    Surf sf; double t_again = h.t;
+    surface_of(S, ray, h.ref, t_again, sf);
+    out.id = sf.id; out.t = h.t; out.hit = 1;
+    // SurfaceInteraction::from, surface.rs:158-183
+    D3 wo = -normalize(ray.d);
+    D3 ng = face_forward(normalize(cross(sf.g_dpdu, sf.g_dpdv)), wo);
+    D3 ns = sf.has_n ? normalize(sf.n) : normalize(cross(sf.s_dpdu, sf.s_dpdv));
+    const double err = 2.220446049250313e-16 * 65536.0;
+    D3 p = ray.o + ray.d * h.t;
+    D3 p_err = ng * err;
+    D3 ps = p + p_err;
+    Bsdf B;
+    B.ng = ng; B.ns = ns; B.ss = normalize(sf.s_dpdu); B.ts = cross(ns, B.ss);
+    const double* M = S.materials + 8 * (size_t)sf.material;
+    B.kd = d3(M[0], M[1], M[2]); B.alpha = M[3]; B.ks = d3(M[4], M[5], M[6]);
+    const uint32_t flags = (uint32_t)__double_as_longlong(M[7]);
+    B.diffuse = flags & 1u; B.glossy = flags & 2u;
+    D3 output = d3(0, 0, 0);
+    for (uint32_t l = 0; l < S.n_lights; l++) {
+        const double* L = S.lights + 9 * (size_t)l;
+        D3 lp = d3(L[0], L[1], L[2]);
+        Ray64 sray; sray.o = ps; sray.d = lp - ps;                 // light/point.rs:43-44
+        D3 wi = lp - ps;
+        double dist = sqrt(dot(wi, wi));
+        wi = normalize(wi);
+        // bsdf.f is zero unless wi and wo are on the same side of ng (bsdf.rs:75,85-86): the light
+        // then adds exactly zero whether or not it is occluded, so the shadow ray is not traced
+        // (DESIGN.md §4.4).  ALL_SHADOWS (AOV / parity mode) traces every one, as the reference does.
+        const bool reflect = dot(wi, ng) * dot(wo, ng) > 0.0;
+        if (!reflect && !ALL_SHADOWS) continue;
+        out.shadow_traced++;
+        Hit sh_hit = traverse<true, STATS>(S, sray, 1.0, lc, overflow);
+        if (sh_hit.ref != LGB_MISS) { out.occl |= (1u << l); out.shadow_occl++; continue; }
+        double f_att = L[6] + L[7] * dist + L[8] * dist * dist;
+        if (f_att == 0.0) continue;
+        double wi_dot_n = dot(wi, ns);
+        D3 f = bsdf_f(B, wo, wi);
+        output = output + (mul_el(PI * d3(L[3], L[4], L[5]), f) * wi_dot_n / f_att);
+    }
+    output = output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), bsdf_f(B, wo, ns));
+    D3 zero = d3(0, 0, 0);
+    out.color = output + zero + zero;       // integrate.rs:79 (reflected + refracted are zero for plastic)
+}
+
+// ------------------------------------------------------------------ work mapping
+__device__ __forceinline__ bool slot_to_pixel(const DevWork& W, uint64_t p, uint32_t& x, uint32_t& y) {
+    if (W.mode == 0) {
+        uint32_t tile_local = (uint32_t)(p / (kMacroTile * kMacroTile));
+        uint32_t q = (uint32_t)(p % (kMacroTile * kMacroTile));
+        uint32_t tile = W.tile_list[tile_local];
+        uint32_t micro = q / 32, in = q % 32;
+        uint32_t px = (micro % (kMacroTile / kMicroW)) * kMicroW + in % kMicroW;
+        uint32_t py = (micro / (kMacroTile / kMicroW)) * kMicroH + in / kMicroW;
+        x = (tile % W.n_macro_x) * kMacroTile + px;
+        y = (tile / W.n_macro_x) * kMacroTile + py;
+        return x < W.w && y < W.h;
+    } else {
+        uint64_t off = (uint64_t)W.sub_k + p * (uint64_t)W.sub_n;   // lib.rs:152-154
+        x = (uint32_t)(off % W.w);
+        y = (uint32_t)(off / W.w);
+        return off < (uint64_t)W.w * W.h;
+    }
+}
+
+// camera.rs:113-146 for sample s of pixel (x, y)
+__device__ __forceinline__ Ray64 camera_ray(const DevCamera& C, const DevWork& W, uint32_t x, uint32_t y, uint32_t s) {
+    D3 up = d3(C.up[0], C.up[1], C.up[2]), aux = d3(C.aux[0], C.aux[1], C.aux[2]);
+    double iph = C.image_plane_height;
+    double ipw = iph * W.aspect;
+    double pixel_size = iph * W.hinv;
+    double sep = C.sample_distance * pixel_size;
+    double sox = ((double)x * W.winv - 0.5) * ipw;
+    double soy = (0.5 - (double)(y + 1) * W.hinv) * iph;
+    Ray64 r;
+    r.o = d3(C.origin[0], C.origin[1], C.origin[2]) + (soy * C.pixel_separation * up) + (sox * C.pixel_separation * aux);
+    D3 d = d3(C.view[0], C.view[1], C.view[2]) + (soy * up) + (sox * aux);
+    D3 updiff = up * sep, auxdiff = aux * sep;
+    D3 halfdiff = updiff * 0.5 + auxdiff * 0.5;
+    double fi = (double)(s / C.root), fj = (double)(s % C.root);
+    r.d = d + (fj * updiff) + (fi * auxdiff) + halfdiff;
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+template <bool STATS, bool ALL_SHADOWS>
+__global__ void __launch_bounds__(256) k_render(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = W.n_pixels * W.spp;
+    LocalCounters lc; lc.node_tests = lc.filter_tests = lc.exact_tests = 0;
+    unsigned int overflow = 0;
+    SampleOut out; out.hit = 0; out.shadow_traced = 0; out.shadow_occl = 0;
+    unsigned int primary = 0;
+    if (g < total) {
+        const uint64_t p = g / W.spp;
+        const uint32_t s = (uint32_t)(g % W.spp);
+        uint32_t x, y;
+        if (slot_to_pixel(W, p, x, y)) {
+            Ray64 ray = camera_ray(C, W, x, y, s);
+            li<STATS, ALL_SHADOWS>(S, sh, ray, out, lc, overflow);
+            primary = 1;
+            O.radiance[3 * g + 0] = out.color.x; O.radiance[3 * g + 1] = out.color.y; O.radiance[3 * g + 2] = out.color.z;
+            const uint64_t gi = ((uint64_t)y * W.w + x) * W.spp + s;
+            if (O.aov_id) O.aov_id[gi] = out.id;
+            if (O.aov_t) O.aov_t[gi] = out.t;
+            if (O.aov_occl) O.aov_occl[gi] = out.occl;
+        }
+    }
+    if (O.counters) {
+        unsigned long long v0 = warp_sum(primary), v1 = warp_sum(out.hit), v2 = warp_sum(out.shadow_traced), v3 = warp_sum(out.shadow_occl);
+        unsigned long long v4 = warp_sum(lc.exact_tests), v5 = warp_sum(lc.filter_tests), v6 = warp_sum(lc.node_tests);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1);
+            atomicAdd(&O.counters->shadow_traced, v2); atomicAdd(&O.counters->shadow_occluded, v3);
+            if (STATS) { atomicAdd(&O.counters->exact_tests, v4); atomicAdd(&O.counters->filter_tests, v5); atomicAdd(&O.counters->node_tests, v6); }
+        }
+        if (overflow) atomicOr(&O.counters->stack_overflow, 1u);
+    }
+}
+
+// integrate.rs:16-20 + img.rs:56-67: in-order sum of the samples, weight, quantise, store.
+__global__ void __launch_bounds__(256) k_resolve(DevWork W, DevOut O) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= W.n_pixels) return;
+    uint32_t x, y;
+    if (!slot_to_pixel(W, p, x, y)) return;
+    const double weight = 1.0 / (double)W.spp;
+    D3 c = d3(0, 0, 0);
+    const double* r = O.radiance + 3 * p * W.spp;
+    for (uint32_t s = 0; s < W.spp; s++) c = c + d3(r[3 * s], r[3 * s + 1], r[3 * s + 2]);
+    c = c * weight;
+    uchar4 px;
+    px.x = (unsigned char)round(fmin(fmax(c.x, 0.0), 1.0) * 255.0);
+    px.y = (unsigned char)round(fmin(fmax(c.y, 0.0), 1.0) * 255.0);
+    px.z = (unsigned char)round(fmin(fmax(c.z, 0.0), 1.0) * 255.0);
+    px.w = 255;
+    reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)y * W.w + x] = px;
+}
+
+// Caller-supplied rays (lgb_trace_rays): closest hit id, t, RayIntersection::ng()/ns() (surface.rs:107-118)
+__global__ void __launch_bounds__(128) k_trace(DevScene S, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ngs, double* nss) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray64 ray; ray.o = d3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]); ray.d = d3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+    LocalCounters lc; lc.node_tests = lc.filter_tests = lc.exact_tests = 0;
+    unsigned int overflow = 0;
+    Hit h = traverse<false, false>(S, ray, CUDART_INF, lc, overflow);
+    uint32_t id = LGB_MISS; D3 ng = d3(0, 0, 0), ns = d3(0, 0, 0);
+    if (h.ref != LGB_MISS) {
+        Surf sf; double t = h.t;
+        surface_of(S, ray, h.ref, t, sf);
+        id = sf.id;
+        ng = normalize(cross(sf.g_dpdu, sf.g_dpdv));
+        ns = sf.has_n ? normalize(sf.n) : normalize(cross(sf.s_dpdu, sf.s_dpdv));
+    }
+    if (ids) ids[i] = id;
+    if (ts) ts[i] = h.ref != LGB_MISS ? h.t : CUDART_INF;
+    if (ngs) { ngs[3 * i] = ng.x; ngs[3 * i + 1] = ng.y; ngs[3 * i + 2] = ng.z; }
+    if (nss) { nss[3 * i] = ns.x; nss[3 * i + 1] = ns.y; nss[3 * i + 2] = ns.z; }
+}
+
+// ------------------------------------------------------------------ ceilings for the roofline report
+__global__ void k_l2_read(const float4* __restrict__ buf, uint64_t n_vec, int iters, float* sink) {
+    float acc = 0.0f;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; it++)
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+            float4 v = __ldcg(&buf[i]);
+            acc += v.x + v.y + v.z + v.w;
+        }
+    if (acc == 123456.789f) *sink = acc;
+}
+__global__ void k_fp32_peak(int iters, float* sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.0f, a2 = a0 + 2.0f, a3 = a0 + 3.0f, a4 = a0 + 4.0f, a5 = a0 + 5.0f, a6 = a0 + 6.0f, a7 = a0 + 7.0f;
+    const float m = 1.0000001f, c = 1e-7f;
+    for (int i = 0; i < iters; i++) {
+        a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
+        a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+    }
+    float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123456.789f) *sink = s;
+}
+__global__ void k_fp64_peak(int iters, double* sink) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+        a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123456.789) *sink = s;
+}
+
+// ------------------------------------------------------------------ launch wrappers (called from lgb_api.cu)
+cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O,
+                          bool stats, cudaStream_t stream) {
+    const uint64_t total = W.n_pixels * W.spp;
+    if (total == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (stats) k_render<true, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O);
+    else k_render<false, false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
+    return cudaGetLastError();
+}
+cudaError_t launch_trace(const DevScene& S, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_trace<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(S, rays, n, ids, ts, ng, ns);
+    return cudaGetLastError();
+}
+cudaError_t launch_l2_read(const void* buf, uint64_t bytes, int iters, float* sink, int sms, cudaStream_t stream) {
+    k_l2_read<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(buf), bytes / 16, iters, sink);
+    return cudaGetLastError();
+}
+cudaError_t launch_fp32_peak(int iters, float* sink, int sms, cudaStream_t stream) {
+    k_fp32_peak<<<sms * 8, 256, 0, stream>>>(iters, sink);
+    return cudaGetLastError();
+}
+cudaError_t launch_fp64_peak(int iters, double* sink, int sms, cudaStream_t stream) {
+    k_fp64_peak<<<sms * 8, 256, 0, stream>>>(iters, sink);
+    return cudaGetLastError();
+}
+
+}  // namespace lgb

@@ -1,0 +1,89 @@
+// Device-side scene layout shared by the kernels and the C-ABI glue (lgb_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lasgun_b200.h"
+
+namespace lgb {
+
+constexpr int kStackDepth = 64;          // bvh.rs:469 — the reference's fixed traversal stack
+constexpr int kMacroTile = 32;           // macro tile edge in pixels (multi-GPU interleave unit)
+constexpr int kMicroW = 8, kMicroH = 4;  // one warp of pixels at 1 spp
+constexpr uint32_t kNoNormals = 0xFFFFFFFFu;
+
+// All pointers are device pointers.  Layout:
+//   nodes      2 x float4 per node : {lo.xyz, a} {hi.xyz, b}; boxes padded (conservative for f32 rays)
+//   prim_refs  u32 (type<<30 | index), reference leaf order
+//   sph32      float4 {c.xyz, r} nearest-f32 copy for the filter; sph64 4 doubles exact
+//   cub32      2 x float4 padded {lo, hi}; cub64 6 doubles exact
+//   tri        3 x float4 {p0, id} {p1, material} {p2, normals_index|kNoNormals}
+//   tri_nrm    9 floats per entry (indexed by the value stored in tri[3i+2].w)
+//   materials  8 doubles {kd.xyz, roughness, ks.xyz, flags(bit0 diffuse lobe, bit1 glossy lobe)}
+//   lights     9 doubles {pos, intensity, falloff}
+struct DevScene {
+    const float4* nodes;
+    const uint32_t* prim_refs;
+    const float4* sph32;
+    const double* sph64;
+    const uint32_t* sph_mat;
+    const uint32_t* sph_id;
+    const float4* cub32;
+    const double* cub64;
+    const uint32_t* cub_mat;
+    const uint32_t* cub_id;
+    const float4* tri;
+    const float* tri_nrm;
+    const uint32_t* inst_root;
+    const double* materials;
+    const double* lights;
+    uint32_t n_lights;
+    uint32_t n_nodes;
+    float err_abs;        // absolute coordinate error bound of an f32 ray against this scene (see lgb_api.cu)
+};
+
+struct DevCamera {
+    double origin[3], view[3], up[3], aux[3];
+    double image_plane_height, pixel_separation, sample_distance;
+    uint32_t root;
+};
+
+struct DevShade {
+    double ambient[3];
+    double bg_inner[3], bg_outer[3], bg_scale;
+};
+
+// Which pixels a launch renders.
+//   mode 0: macro tiles listed in tile_list (tile index = my * n_macro_x + mx)
+//   mode 1: capture_subset — pixels k, k+n, ... of the row-major film (lib.rs:152)
+//   mode 2: caller-supplied rays (lgb_trace_rays)
+struct DevWork {
+    uint32_t mode;
+    uint32_t w, h;
+    double winv, hinv, aspect;       // film.rs:36-45
+    const uint32_t* tile_list;
+    uint32_t n_tiles;
+    uint32_t n_macro_x;
+    uint32_t sub_k, sub_n;
+    uint64_t n_pixels;               // pixel slots in this launch
+    uint32_t spp;
+    uint32_t compact_out;            // resolve writes film[slot] instead of film[y*w + x]
+};
+
+struct DevCounters {
+    unsigned long long primary_rays, primary_hits, shadow_traced, shadow_occluded;
+    unsigned long long exact_tests, filter_tests, node_tests;
+    unsigned int stack_overflow;
+    unsigned int pad;
+};
+
+struct DevOut {
+    double* radiance;                // 3 doubles per sample slot (slot = pixel_slot * spp + s)
+    uint32_t* aov_id;                // optional, global sample index
+    double* aov_t;
+    uint32_t* aov_occl;
+    DevCounters* counters;           // optional
+    uint8_t* film;                   // row-major RGBA8 (may be a peer pointer)
+};
+
+}  // namespace lgb

@@ -1,0 +1,190 @@
+"""Deterministic synthetic scenes for the five BASELINE.json configs.
+
+Each recipe takes the API module's classes and returns (Scene, (width, height)).
+Vertex and sphere data are generated in f64; mesh vertices are then rounded to
+f32 exactly as OBJ storage does (src/shape/triangle.rs:41-42).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .api import Material, ObjData, Scene
+
+_MASK = (1 << 64) - 1
+
+
+def splitmix64_uniform(seed: int, count: int) -> np.ndarray:
+    """`count` draws u = (next_u64 >> 11) * 2^-53 of SplitMix64 seeded with `seed`."""
+    gamma = np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed & _MASK) + gamma * np.arange(1, count + 1, dtype=np.uint64)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (2.0 ** -53)
+
+
+def mesh_grid(n: int, s: float) -> ObjData:
+    """MESH(N, S) of SURVEY §8d: bumpy sphere, (N+1)^2 vertices (seam duplicated), 2*N^2 triangles."""
+    i = np.arange(n + 1, dtype=np.float64)
+    u = 2.0 * math.pi * i / n
+    v = math.pi * i / n
+    U, V = np.meshgrid(u, v, indexing="xy")            # V varies with row j, U with column i
+    rho = s * (1.0 + 0.05 * np.sin(7.0 * U) * np.cos(5.0 * V) + 0.03 * np.sin(23.0 * U + 1.0) * np.sin(19.0 * V))
+    pos = np.stack([rho * np.sin(V) * np.cos(U), rho * np.cos(V), rho * np.sin(V) * np.sin(U)], axis=-1)
+    pos32 = pos.reshape(-1, 3).astype(np.float32)
+    jj, ii = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")   # j outer, i inner
+    a = (jj * (n + 1) + ii).reshape(-1)
+    b = a + 1
+    c = a + (n + 1) + 1
+    d = a + (n + 1)
+    faces = np.empty((2 * n * n, 3), np.uint32)
+    faces[0::2] = np.stack([a, b, c], axis=-1)
+    faces[1::2] = np.stack([a, c, d], axis=-1)
+    return ObjData(pos32, faces)
+
+
+def star_mesh(radius_inner=70.0, radius_tip=100.0) -> ObjData:
+    """60-triangle star: icosahedron with raised face centres (stand-in for the
+    Git-LFS-only smstdodeca.obj of src/examples/simple.rs:25)."""
+    t = (1.0 + math.sqrt(5.0)) / 2.0
+    verts = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                      [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], np.float64)
+    verts *= radius_inner / np.linalg.norm(verts[0])
+    tris = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6),
+            (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10),
+            (8, 6, 7), (9, 8, 1)]
+    pos = [v for v in verts]
+    faces = []
+    for (a, b, c) in tris:
+        ctr = (verts[a] + verts[b] + verts[c]) / 3.0
+        ctr *= radius_tip / np.linalg.norm(ctr)
+        k = len(pos)
+        pos.append(ctr)
+        faces += [(a, b, k), (b, c, k), (c, a, k)]
+    return ObjData(np.array(pos).astype(np.float32), np.array(faces, np.uint32))
+
+
+def simple(variant="b", supersampling=2, res=512):
+    """C1: src/examples/simple.rs:11-36.  variant 'a' omits the mesh, 'b' substitutes star_mesh()."""
+    scene = Scene()
+    scene.set_ambient_light([0.2, 0.2, 0.2])
+    scene.set_radial_background([0.26, 0.78, 0.67], [0.1, 0.09, 0.33], 0.5)
+    camera = scene.set_perspective_camera(45.0)
+    camera.look_at([25.0, 0.0, 800.0], [25.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+    camera.set_supersampling(supersampling)
+    mat0 = Material.plastic([0.7, 1.0, 0.7], [0.5, 0.7, 0.5], 0.25)
+    mat1 = Material.plastic([0.5, 0.5, 0.5], [0.5, 0.7, 0.5], 0.25)
+    mat2 = Material.plastic([1.0, 0.6, 0.1], [0.5, 0.7, 0.5], 0.25)
+    mat3 = Material.plastic([0.7, 0.6, 1.0], [0.5, 0.4, 0.8], 0.25)
+    mesh = scene.add_obj(star_mesh()) if variant == "b" else None
+    scene.add_point_light([-100.0, 150.0, 400.0], [0.9, 0.9, 0.9], [1.0, 0.0, 0.0])
+    scene.add_point_light([400.0, 100.0, 150.0], [0.7, 0.0, 0.7], [1.0, 0.0, 0.0])
+    scene.root.add_sphere([0.0, 0.0, -400.0], 100.0, mat0)
+    scene.root.add_sphere([200.0, 50.0, -100.0], 150.0, mat0)
+    scene.root.add_sphere([0.0, -1200.0, -500.0], 1000.0, mat1)
+    scene.root.add_sphere([-100.0, 25.0, -300.0], 50.0, mat2)
+    scene.root.add_sphere([0.0, 100.0, -250.0], 25.0, mat0)
+    scene.root.add_cube([-200.0, -125.0, 0.0], 100.0, mat3)
+    if mesh is not None:
+        scene.root.add_obj_of(mesh, mat2)
+    return scene, (res, res)
+
+
+def mesh1m(n=708, res=1024):
+    """C2: one MESH(N, 1) (2*708^2 = 1,002,528 triangles), 2 point lights, 1 spp."""
+    scene = Scene()
+    scene.set_ambient_light([0.1, 0.1, 0.1])
+    scene.set_solid_background([0.05, 0.05, 0.08])
+    camera = scene.set_perspective_camera(45.0)
+    camera.look_at([0.0, 0.0, 4.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+    mat = Material.plastic([0.7, 0.6, 0.5], [0.4, 0.4, 0.4], 0.25)
+    mesh = scene.add_obj(mesh_grid(n, 1.0))
+    scene.add_point_light([-3.0, 4.0, 5.0], [0.8, 0.8, 0.8], [1.0, 0.0, 0.0])
+    scene.add_point_light([4.0, 2.0, 3.0], [0.5, 0.4, 0.3], [1.0, 0.0, 0.0])
+    scene.root.add_obj_of(mesh, mat)
+    return scene, (res, res)
+
+
+def cornell(res=(1920, 1080), supersampling=1):
+    """C3: cuboid walls + spheres + cube, plastic only, 4 spp."""
+    scene = Scene()
+    scene.set_ambient_light([0.2, 0.2, 0.2])
+    camera = scene.set_perspective_camera(60.0)
+    camera.look_at([0.0, 0.0, 5.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+    camera.set_supersampling(supersampling)
+    ks = [0.5, 0.7, 0.5]
+    white = Material.plastic([0.9, 0.9, 0.9], ks, 0.25)
+    red = Material.plastic([1.0, 0.0, 0.0], ks, 0.25)
+    green = Material.plastic([0.0, 1.0, 0.0], ks, 0.25)
+    scene.add_point_light([0.0, 1.75, 0.0], [0.9, 0.9, 0.9], [1.0, 0.0, 0.0])
+    r = scene.root
+    r.add_box([-2.1, -2.1, -2.1], [2.1, -2.0, 2.0], white)      # floor
+    r.add_box([-2.1, 2.0, -2.1], [2.1, 2.1, 2.0], white)        # ceiling
+    r.add_box([-2.1, -2.1, -2.1], [2.1, 2.1, -2.0], white)      # back
+    r.add_box([-2.1, -2.0, -2.0], [-2.0, 2.0, 2.0], red)        # left
+    r.add_box([2.0, -2.0, -2.0], [2.1, 2.0, 2.0], green)        # right
+    r.add_sphere([1.0, -0.999, 0.0], 1.0, white)
+    r.add_cube([-1.999, -1.999, 0.0], 1.0, white)
+    r.add_sphere([-0.5, -1.499, 1.0], 0.5, red)
+    r.add_sphere([0.3, -1.499, 1.4], 0.5, green)
+    return scene, tuple(res)
+
+
+def _cube_palette():
+    mats = []
+    for j in range(8):
+        kd = [0.8 * (0.25 + 0.75 * ((j >> b) & 1)) for b in range(3)]
+        mats.append(Material.plastic(kd, [0.3, 0.3, 0.3], 0.25))
+    return mats
+
+
+def spheres1m(count=1_000_000, res=2048):
+    """C4: random sphere field, SplitMix64 seed 0x5EED0004, 3 point lights, 1 spp."""
+    scene = Scene()
+    scene.set_ambient_light([0.1, 0.1, 0.1])
+    scene.set_solid_background([0.0, 0.0, 0.0])
+    camera = scene.set_perspective_camera(45.0)
+    camera.look_at([0.0, 0.0, 1400.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+    u = splitmix64_uniform(0x5EED0004, 4 * count).reshape(count, 4)
+    centers = -500.0 + 1000.0 * u[:, 0:3]
+    radii = 1.0 + 3.0 * u[:, 3]
+    for pos in ([-800.0, 900.0, 1200.0], [900.0, 400.0, 1000.0], [0.0, 1200.0, -200.0]):
+        scene.add_point_light(pos, [0.6, 0.6, 0.6], [1.0, 0.0, 0.0])
+    scene.root.add_spheres(centers, radii, _cube_palette(), np.arange(count) % 8)
+    return scene, (res, res)
+
+
+def mixed4k(mesh_n=500, nspheres=100_000, res=(3840, 2160), supersampling=3):
+    """C5: MESH(500, 100) + 100k spheres on a shell + ground box, 2 lights, 16 spp."""
+    scene = Scene()
+    scene.set_ambient_light([0.1, 0.1, 0.1])
+    camera = scene.set_perspective_camera(50.0)
+    camera.look_at([0.0, 60.0, 520.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+    camera.set_supersampling(supersampling)
+    mesh = scene.add_obj(mesh_grid(mesh_n, 100.0))
+    scene.add_point_light([-400.0, 500.0, 600.0], [0.8, 0.8, 0.8], [1.0, 0.0, 0.0])
+    scene.add_point_light([500.0, 300.0, 200.0], [0.5, 0.45, 0.4], [1.0, 0.0, 0.0])
+    scene.root.add_obj_of(mesh, Material.plastic([0.7, 0.6, 0.5], [0.4, 0.4, 0.4], 0.25))
+    u = splitmix64_uniform(0x5EED0005, 4 * nspheres).reshape(nspheres, 4)
+    theta = np.arccos(1.0 - 2.0 * u[:, 0])
+    phi = 2.0 * math.pi * u[:, 1]
+    R = 150.0 + 250.0 * u[:, 2]
+    rad = 0.5 + 2.5 * u[:, 3]
+    centers = np.stack([R * np.sin(theta) * np.cos(phi), R * np.cos(theta), R * np.sin(theta) * np.sin(phi)], axis=-1)
+    scene.root.add_spheres(centers, rad, _cube_palette(), np.arange(nspheres) % 8)
+    scene.root.add_box([-600.0, -130.0, -600.0], [600.0, -120.0, 600.0], Material.plastic([0.6, 0.6, 0.6], [0.0, 0.0, 0.0], 0.25))
+    return scene, tuple(res)
+
+
+CONFIGS = {
+    "simple": lambda: simple("b", 2),
+    "simple_nomesh": lambda: simple("a", 2),
+    "simple_1spp": lambda: simple("b", 0),
+    "mesh1m": mesh1m,
+    "cornell": cornell,
+    "spheres1m": spheres1m,
+    "mixed4k": mixed4k,
+}
