@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s (primary + shadow) and ms/frame of the lasgun render loop on 1/2/4/8 B200.
+
+  python bench.py --gpus N --steps K --warmup W [--workload mixed4k] [--impl reference]
+
+A step is one full frame of the workload (default: BASELINE.json's config 5, `mixed4k`, 3840x2160 at
+16 spp — the config the 1/2/4/8-GPU metric is quoted on; it fits one GPU).  Rays are counted with the
+reference's semantics: primary = w*h*spp, shadow = lights * primary hits (integrate.rs:47-50).
+  value  scene + BVH resident in HBM, frame rendered into a device film (rank 0 after the NVLink gather)
+  e2e    the C-ABI call with HOST buffers: lgb_scene_create (H2D of the flattened scene) +
+         lgb_capture (render + D2H of the film) + lgb_scene_destroy, every step
+--impl reference times the CPU oracle (C++ restatement of the reference algorithm — the Rust build
+cannot be compiled here) on all host threads over a bounded sample of the same frame.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from lasgun_b200 import scenes  # noqa: E402
+
+METRIC = "Mrays/s (primary+shadow)"
+# Constants of record, SURVEY.md §8(d): FP32 operations (FMA = 2) and bytes fetched per unit of work.
+OPS = {"node": 26, "sphere": (26, 39), "tri": (47, 68), "cuboid": 31, "camera": 30, "hit": 110, "light": 25 + 120, "ambient": 120,
+       "background": 15, "film": 12}
+BYTES = {"node": 32, "sphere": 16, "tri": 48, "cuboid": 32, "ref": 4, "film": 4}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "sm_max_mhz": float(p.get("sm_max_mhz", 1965.0)), "source": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (nvidia_ml_py)."""
+    HW = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag, self.max_mhz, self.thread = [], set(), False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.HW.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def workload(name, args):
+    if name == "mixed4k" and args.small:
+        return scenes.mixed4k(mesh_n=80, nspheres=8000, res=(480, 270), supersampling=1)
+    return scenes.CONFIGS[name]()
+
+
+def reference_sample(osc, w, h, threads, target_s, spp, n_lights):
+    """Bounded sample of the frame on the CPU oracle: capture_subset(k, n) for k < threads."""
+    probe_n = max(threads, (w * h) // (threads * 64))
+    t0 = time.time(); r = osc.capture(w, h, threads=threads, counters=True, subset=(probe_n, 0, threads)); dt = max(time.time() - t0, 1e-4)
+    pixels = threads * ((w * h + probe_n - 1) // probe_n)
+    rate = pixels / dt
+    want_pixels = min(w * h, max(pixels, int(rate * target_s)))
+    n = max(threads, (w * h * threads) // want_pixels)
+    return n
+
+
+def run_reference(args):
+    from oracle import pyoracle as po
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sc, (w, h) = workload(args.workload, args)
+    threads = po.hardware_threads()
+    osc = po.OracleScene(sc)
+    spp, nl = sc.camera.num_samples(), len(sc.lights)
+    n = reference_sample(osc, w, h, threads, args.ref_seconds / max(1, args.steps + args.warmup), spp, nl)
+    times, rays = [], 0
+    for i in range(args.warmup + args.steps):
+        r = osc.capture(w, h, threads=threads, counters=True, subset=(n, 0, threads))
+        if i >= args.warmup:
+            times.append(r["render_ms"]); rays = r["counters"]["primary"] + r["counters"]["shadow"]
+    ms = sum(times) / len(times)
+    value = rays / (ms * 1e-3) / 1e6
+    frame_rays_est = rays * (n / threads)
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": args.workload, "film": [w, h], "spp": spp, "lights": nl},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                         "sample": f"capture_subset(k, n={n}) for k in 0..{threads} of the {w}x{h} frame ({rays} rays/step); "
+                                   "C++ restatement of the reference algorithm, not the Rust build",
+                         "bvh_build_ms": osc.build_ms, "ms_per_frame_est": ms * n / threads},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "est_frame_rays": frame_rays_est,
+    }
+    print(json.dumps(line))
+
+
+def algorithmic_work(st, w, h, spp, n_lights):
+    """Algorithmic FP32 ops and bytes of one frame from the device's own work counters."""
+    f, e = st["filter_tests"], st["exact_tests"]
+    ops = st["node_tests"] * OPS["node"]
+    ops += (f[0] - e[0]) * OPS["sphere"][0] + e[0] * OPS["sphere"][1]
+    ops += f[1] * OPS["cuboid"]
+    ops += (f[2] - e[2]) * OPS["tri"][0] + e[2] * OPS["tri"][1]
+    hits, prim = st["primary_hits"], st["primary_rays"]
+    ops += prim * OPS["camera"] + hits * OPS["hit"] + st["shadow_rays_traced"] * OPS["light"] + hits * OPS["ambient"]
+    ops += (prim - hits) * OPS["background"] + w * h * OPS["film"]
+    byts = st["node_tests"] * BYTES["node"] + f[0] * BYTES["sphere"] + f[1] * BYTES["cuboid"] + f[2] * BYTES["tri"]
+    byts += (f[0] + f[1] + f[2]) * BYTES["ref"] + w * h * BYTES["film"]
+    return ops, byts
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from lasgun_b200 import _native as N
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = N.Context(local)
+    sc, (w, h) = workload(args.workload, args)
+    spp, nl = sc.camera.num_samples(), len(sc.lights)
+    t0 = time.time(); flat = N.FlatScene(sc, resplit=not args.no_resplit, leaf_size=args.leaf_size); host_flatten_s = time.time() - t0
+    dev = N.DeviceScene(ctx, flat)
+    film = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    # everything (our kernels, NCCL, the timing events) runs on ONE non-default torch stream so that
+    # torch.cuda.Event brackets exactly the launches it is supposed to
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+
+    def step():
+        if world > 1:
+            film.zero_()
+        dev.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream)
+        if world > 1:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)    # disjoint tiles: SUM == gather, over NVLink
+
+    # one counted frame: ray counts + work counters (not timed)
+    ctx.set_count_work(True)
+    st = dev.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream, want_stats=True)
+    ctx.set_count_work(False)
+    cnt = torch.tensor([st["primary_rays"], st["primary_hits"], st["shadow_rays_traced"], st["node_tests"]] + st["filter_tests"] + st["exact_tests"],
+                       dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cnt)
+    tot = cnt.tolist()
+    frame = {"primary_rays": tot[0], "primary_hits": tot[1], "shadow_rays_traced": tot[2], "node_tests": tot[3],
+             "filter_tests": tot[4:7], "exact_tests": tot[7:10]}
+    rays_frame = frame["primary_rays"] + nl * frame["primary_hits"]
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local); sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kern_ms = []
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(args.steps):
+        step()
+    ev[1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    total_ms = torch.tensor([ev[0].elapsed_time(ev[1])], device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    value = rays_frame / (ms_per_step * 1e-3) / 1e6
+
+    # render-kernel time alone (CUDA events inside the library, on its launch stream), a few frames
+    for _ in range(3):
+        s2 = dev.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream, want_stats=True)
+        kern_ms.append(s2["render_ms"])
+    kms = torch.tensor([statistics.median(kern_ms)], device="cuda")
+    if world > 1:
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    kernel_ms = float(kms.item())
+
+    # e2e through the C ABI with host buffers (rank-local frame share; film gathered on the host side of rank 0)
+    host_film = np.zeros((h, w, 4), np.uint8)
+    e2e_ms = []
+    L = N.lib()
+    for i in range(args.e2e_steps + 1):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        hscene = C.c_void_p()
+        ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat.desc), C.byref(hscene)))
+        if world == 1:
+            ctx.check(L.lgb_capture(ctx.h, hscene, w, h, host_film.ctypes.data_as(C.POINTER(C.c_uint8)), None))
+        else:
+            film.zero_()
+            ctx.check(L.lgb_capture_device(ctx.h, hscene, w, h, rank, world, C.c_void_p(film.data_ptr()), C.c_void_p(stream), None))
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                host_film[...] = film.cpu().numpy()
+            torch.cuda.synchronize()
+        L.lgb_scene_destroy(hscene)
+        dt = torch.tensor([(time.perf_counter() - t0) * 1e3], device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if i > 0:
+            e2e_ms.append(float(dt.item()))
+    e2e = statistics.median(e2e_ms)
+    scene_bytes = int(dev.device_bytes)
+
+    if rank == 0:
+        peaks = load_peaks()
+        ceil = ctx.measure()
+        ops, byts = algorithmic_work(frame, w, h, spp, nl)
+        fp32_peak = 2.0 * ceil["fp32_ffma_glanes"]                 # Gop/s with FMA = 2, measured live on this GPU
+        ach = ops / (kernel_ms * 1e-3) / 1e9 / world                # per GPU
+        l2_ach = byts / (kernel_ms * 1e-3) / 1e9 / world
+        hbm_bytes = scene_bytes + frame["primary_rays"] * 48 / world + w * h * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "film": [w, h], "spp": spp, "lights": nl, "triangles": int(flat.desc.n_triangles),
+                       "spheres": int(flat.desc.n_spheres), "cuboids": int(flat.desc.n_cuboids), "bvh_nodes": int(flat.desc.n_nodes),
+                       "resplit_leaf": 0 if args.no_resplit else args.leaf_size, "parallelism": f"tiles{world}",
+                       "l2_policy": "per-frame working set (radiance buffer %.0f MB + scene %.0f MB) exceeds the 126 MB L2" % (frame["primary_rays"] * 24 / 1e6 / world, scene_bytes / 1e6)},
+            "ms_per_frame": ms_per_step, "kernel_ms_per_frame": kernel_ms, "rays_per_frame": rays_frame,
+            "rays_traced_per_frame": frame["primary_rays"] + frame["shadow_rays_traced"],
+            "e2e": {"value": rays_frame / (e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e,
+                    "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": w * h * 4,
+                    "host_bvh_build_flatten_ms": host_flatten_s * 1e3},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "fp32_issue", "achieved": ach, "peak": fp32_peak, "unit": "Gop/s (FMA=2)", "frac": ach / fp32_peak,
+                         "traffic": None, "peak_source": "lgb_measure_fp32_gops, live on this GPU",
+                         "algorithmic_ops_per_frame": ops, "algorithmic_bytes_per_frame": byts,
+                         "l2": {"achieved_gbs": l2_ach, "peak_gbs": ceil["l2_read_gbs"], "frac": l2_ach / ceil["l2_read_gbs"]},
+                         "hbm": {"achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                                 "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"]},
+                         "fp64_dfma_glanes_peak": ceil["fp64_dfma_glanes"]},
+            "work_per_frame": frame,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import pyoracle as po
+            threads = po.hardware_threads()
+            osc = po.OracleScene(sc)
+            n = reference_sample(osc, w, h, threads, args.cpu_seconds, spp, nl)
+            r = osc.capture(w, h, threads=threads, counters=True, subset=(n, 0, threads))
+            rays = r["counters"]["primary"] + r["counters"]["shadow"]
+            # spot-check the device film at the oracle's sampled pixels (the checker, not the product)
+            idx = np.concatenate([np.arange(k, w * h, n) for k in range(threads)])
+            same = (host_film.reshape(-1, 4)[idx] == r["rgba"].reshape(-1, 4)[idx]).all(axis=1).mean()
+            line["cpu_baseline"] = {"value": rays / (r["render_ms"] * 1e-3) / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                                    "sample": f"capture_subset(k, n={n}) for k in 0..{threads} of the {w}x{h} frame ({rays} rays, {r['render_ms']:.0f} ms); "
+                                              "C++ restatement of the reference algorithm, not the Rust build",
+                                    "bvh_build_ms": osc.build_ms, "device_film_identical_frac_at_sample": float(same)}
+        print(json.dumps(line))
+    dev.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="mixed4k", choices=sorted(scenes.CONFIGS))
+    ap.add_argument("--small", action="store_true", help="tiny variant of mixed4k (CPU smoke of the bench logic)")
+    ap.add_argument("--leaf-size", type=int, default=4)
+    ap.add_argument("--no-resplit", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-seconds", type=float, default=60.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -133,8 +133,10 @@ typedef struct lgb_stats {
     uint64_t shadow_rays;            /* reference semantics: lights * primary_hits (integrate.rs:47-50) */
     uint64_t shadow_rays_traced;     /* rays the device actually traversed */
     uint64_t shadow_occluded;
-    uint64_t exact_tests;            /* f64 reference-arithmetic primitive tests executed */
-    uint64_t filter_tests;           /* conservative f32 primitive filter tests executed */
+    /* Work counters, filled only by lgb_capture_aov or with LGB_OPT_COUNT_WORK (slower kernel variant);
+     * index 0 sphere, 1 cuboid, 2 triangle. */
+    uint64_t exact_tests[3];         /* f64 reference-arithmetic primitive tests executed */
+    uint64_t filter_tests[3];        /* conservative f32 primitive filter tests executed */
     uint64_t node_tests;
     float render_ms;                 /* device time of the render + resolve kernels */
     float total_ms;                  /* device time incl. film copy back to the host */
@@ -146,6 +148,8 @@ typedef struct lgb_stats {
 int lgb_device_count(void);
 int lgb_init(int device, lgb_ctx** out);
 void lgb_shutdown(lgb_ctx* ctx);
+#define LGB_OPT_COUNT_WORK 1        /* value != 0: captures also fill the work counters of lgb_stats */
+int lgb_set_option(lgb_ctx* ctx, int option, int value);
 const char* lgb_last_error(lgb_ctx* ctx);          /* ctx may be NULL: last error of lgb_init */
 const char* lgb_status_string(int status);
 

@@ -20,7 +20,7 @@ LGB_LEAF_FLAG = 0x80000000
 
 # Every symbol include/lasgun_b200.h declares (checked by tests/test_abi.py without a GPU).
 ABI_SYMBOLS = [
-    "lgb_device_count", "lgb_init", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
+    "lgb_device_count", "lgb_init", "lgb_set_option", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
     "lgb_scene_destroy", "lgb_scene_device_bytes", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
     "lgb_capture_device", "lgb_trace_rays", "lgb_measure_l2_read_gbs", "lgb_measure_fp32_gops", "lgb_measure_fp64_gops",
 ]
@@ -61,12 +61,12 @@ class SceneDesc(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("primary_hits", C.c_uint64), ("shadow_rays", C.c_uint64),
-                ("shadow_rays_traced", C.c_uint64), ("shadow_occluded", C.c_uint64), ("exact_tests", C.c_uint64),
-                ("filter_tests", C.c_uint64), ("node_tests", C.c_uint64), ("render_ms", C.c_float), ("total_ms", C.c_float),
+                ("shadow_rays_traced", C.c_uint64), ("shadow_occluded", C.c_uint64), ("exact_tests", C.c_uint64 * 3),
+                ("filter_tests", C.c_uint64 * 3), ("node_tests", C.c_uint64), ("render_ms", C.c_float), ("total_ms", C.c_float),
                 ("kernel_launches", C.c_uint32), ("stack_overflow", C.c_uint32)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n in ("exact_tests", "filter_tests") else getattr(self, n)) for n, _ in self._fields_}
 
 
 def lib():
@@ -81,6 +81,7 @@ def lib():
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_int))
     sig = {
         "lgb_device_count": (C.c_int, []), "lgb_init": (C.c_int, [C.c_int, C.POINTER(vp)]), "lgb_shutdown": (None, [vp]),
+        "lgb_set_option": (C.c_int, [vp, C.c_int, C.c_int]),
         "lgb_last_error": (C.c_char_p, [vp]), "lgb_status_string": (C.c_char_p, [C.c_int]),
         "lgb_scene_create": (C.c_int, [vp, C.POINTER(SceneDesc), C.POINTER(vp)]), "lgb_scene_destroy": (None, [vp]),
         "lgb_scene_device_bytes": (C.c_uint64, [vp]),
@@ -278,6 +279,9 @@ class Context:
         if self.h:
             lib().lgb_shutdown(self.h)
             self.h = None
+
+    def set_count_work(self, on: bool):
+        self.check(lib().lgb_set_option(self.h, 1, 1 if on else 0))
 
     def measure(self):
         L = lib()

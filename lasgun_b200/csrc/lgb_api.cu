@@ -10,7 +10,7 @@
 #include "lgb_types.cuh"
 
 namespace lgb {
-cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, bool stats, cudaStream_t);
+cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, bool stats, bool all_shadows, cudaStream_t);
 cudaError_t launch_trace(const DevScene&, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns, cudaStream_t);
 cudaError_t launch_l2_read(const void* buf, uint64_t bytes, int iters, float* sink, int sms, cudaStream_t);
 cudaError_t launch_fp32_peak(int iters, float* sink, int sms, cudaStream_t);
@@ -44,6 +44,7 @@ struct lgb_ctx {
     std::vector<uint32_t> tile_host;
     uint32_t tile_key[4] = {0, 0, 0, 0};   // w, h, rank, ranks of the cached tile list
     uint32_t tile_count = 0;
+    int count_work = 0;                    // LGB_OPT_COUNT_WORK
 };
 
 struct lgb_scene {
@@ -104,6 +105,12 @@ int lgb_init(int device, lgb_ctx** out) {
     CU(nullptr, cudaEventCreate(&c->ev0)); CU(nullptr, cudaEventCreate(&c->ev1)); CU(nullptr, cudaEventCreate(&c->ev2));
     *out = c;
     return LGB_OK;
+}
+
+int lgb_set_option(lgb_ctx* c, int option, int value) {
+    if (!c) return LGB_ERR_INVALID;
+    if (option == LGB_OPT_COUNT_WORK) { c->count_work = value != 0; return LGB_OK; }
+    return fail(c, LGB_ERR_INVALID, "lgb_set_option: unknown option");
 }
 
 void lgb_shutdown(lgb_ctx* c) {
@@ -392,7 +399,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     }
     CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));
     CU(c, cudaEventRecord(c->ev0, st));
-    CU(c, launch_render(S, s->cam, s->shade, W, O, a.aov, st));
+    CU(c, launch_render(S, s->cam, s->shade, W, O, a.aov || c->count_work, a.aov, st));
     CU(c, cudaEventRecord(c->ev1, st));
     if (stats && sync_stats) {
         DevCounters hc;
@@ -402,7 +409,8 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         stats->primary_rays = hc.primary_rays; stats->primary_hits = hc.primary_hits;
         stats->shadow_rays = hc.primary_hits * s->dev.n_lights;
         stats->shadow_rays_traced = hc.shadow_traced; stats->shadow_occluded = hc.shadow_occluded;
-        stats->exact_tests = hc.exact_tests; stats->filter_tests = hc.filter_tests; stats->node_tests = hc.node_tests;
+        stats->node_tests = hc.node_tests;
+        for (int k = 0; k < 3; k++) { stats->filter_tests[k] = hc.filter[k]; stats->exact_tests[k] = hc.exact[k]; }
         stats->stack_overflow = hc.stack_overflow;
         stats->kernel_launches = total ? 2 : 0;
         float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));

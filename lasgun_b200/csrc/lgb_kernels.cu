@@ -63,7 +63,7 @@ __device__ __forceinline__ bool slab_conservative(const float4 lo, const float4 
 
 struct Hit { double t; uint32_t ref; };
 
-struct LocalCounters { unsigned int node_tests, filter_tests, exact_tests; };
+struct LocalCounters { unsigned int node_tests, filter[3], exact[3]; };
 
 // Closest hit (ANYHIT = false) or "any hit with t < tmax" (ANYHIT = true, shadow rays: the
 // reference asks for the closest t and compares it with 1.0, light/point.rs:48-49, which is
@@ -92,7 +92,7 @@ __device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalC
                     const uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
                     if (type == LGB_PRIM_TRIANGLE) {
                         const float4 q0 = __ldg(&S.tri[3 * idx]), q1 = __ldg(&S.tri[3 * idx + 1]), q2 = __ldg(&S.tri[3 * idx + 2]);
-                        if (STATS) lc.filter_tests++;
+                        if (STATS) lc.filter[2]++;
                         // f32 watertight edge functions with an error band
                         float ax = q0.x - f.ox, ay = q0.y - f.oy, az = q0.z - f.oz;
                         float bx = q1.x - f.ox, by = q1.y - f.oy, bz = q1.z - f.oz;
@@ -112,7 +112,7 @@ __device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalC
                         float slack = err * fabsf(f.sz);
                         if (tlo - slack - fabsf(tlo) * 1e-6f > best_tf) continue;
                         if (thi + slack + fabsf(thi) * 1e-6f < 0.0f) continue;
-                        if (STATS) lc.exact_tests++;
+                        if (STATS) lc.exact[2]++;
                         double t, b0, b1, b2;
                         if (triangle_exact(d3(q0.x, q0.y, q0.z), d3(q1.x, q1.y, q1.z), d3(q2.x, q2.y, q2.z), ray, best.t, t, b0, b1, b2)) {
                             best.t = t; best.ref = ref; best_tf = __double2float_ru(t);
@@ -120,7 +120,7 @@ __device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalC
                         }
                     } else if (type == LGB_PRIM_SPHERE) {
                         const float4 s = __ldg(&S.sph32[idx]);
-                        if (STATS) lc.filter_tests++;
+                        if (STATS) lc.filter[0]++;
                         float lx = s.x - f.ox, ly = s.y - f.oy, lz = s.z - f.oz;
                         float bq = lx * f.dx + ly * f.dy + lz * f.dz;
                         float tc = bq * f.inv_dd;
@@ -132,7 +132,7 @@ __device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalC
                         float slack = fabsf(tc) * 2e-6f + 2.0f * err * f.inv_len;
                         if (tc - half - slack > best_tf) continue;
                         if (tc + half + slack < 0.0f) continue;
-                        if (STATS) lc.exact_tests++;
+                        if (STATS) lc.exact[0]++;
                         const double2 c01 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx));
                         const double2 c23 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx + 2));
                         double t; bool inside;
@@ -142,9 +142,9 @@ __device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalC
                         }
                     } else if (type == LGB_PRIM_CUBOID) {
                         const float4 lo = __ldg(&S.cub32[2 * idx]), hi = __ldg(&S.cub32[2 * idx + 1]);
-                        if (STATS) lc.filter_tests++;
+                        if (STATS) lc.filter[1]++;
                         if (!slab_conservative(lo, hi, f, CUDART_INF_F)) continue;
-                        if (STATS) lc.exact_tests++;
+                        if (STATS) lc.exact[1]++;
                         double mn[3], mx[3];
 #pragma unroll
                         for (int k = 0; k < 3; k++) { mn[k] = __ldg(&S.cub64[6 * (size_t)idx + k]); mx[k] = __ldg(&S.cub64[6 * (size_t)idx + 3 + k]); }
@@ -410,7 +410,7 @@ template <bool STATS, bool ALL_SHADOWS>
 __global__ void __launch_bounds__(256) k_render(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O) {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t total = W.n_pixels * W.spp;
-    LocalCounters lc; lc.node_tests = lc.filter_tests = lc.exact_tests = 0;
+    LocalCounters lc = {};
     unsigned int overflow = 0;
     SampleOut out; out.hit = 0; out.shadow_traced = 0; out.shadow_occl = 0;
     unsigned int primary = 0;
@@ -431,11 +431,17 @@ __global__ void __launch_bounds__(256) k_render(DevScene S, DevCamera C, DevShad
     }
     if (O.counters) {
         unsigned long long v0 = warp_sum(primary), v1 = warp_sum(out.hit), v2 = warp_sum(out.shadow_traced), v3 = warp_sum(out.shadow_occl);
-        unsigned long long v4 = warp_sum(lc.exact_tests), v5 = warp_sum(lc.filter_tests), v6 = warp_sum(lc.node_tests);
         if ((threadIdx.x & 31) == 0) {
             atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1);
             atomicAdd(&O.counters->shadow_traced, v2); atomicAdd(&O.counters->shadow_occluded, v3);
-            if (STATS) { atomicAdd(&O.counters->exact_tests, v4); atomicAdd(&O.counters->filter_tests, v5); atomicAdd(&O.counters->node_tests, v6); }
+        }
+        if (STATS) {
+            unsigned long long n = warp_sum(lc.node_tests);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&O.counters->node_tests, n);
+            for (int k = 0; k < 3; k++) {
+                unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
+                if ((threadIdx.x & 31) == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); }
+            }
         }
         if (overflow) atomicOr(&O.counters->stack_overflow, 1u);
     }
@@ -465,7 +471,7 @@ __global__ void __launch_bounds__(128) k_trace(DevScene S, const double* rays, u
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Ray64 ray; ray.o = d3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]); ray.d = d3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
-    LocalCounters lc; lc.node_tests = lc.filter_tests = lc.exact_tests = 0;
+    LocalCounters lc = {};
     unsigned int overflow = 0;
     Hit h = traverse<false, false>(S, ray, CUDART_INF, lc, overflow);
     uint32_t id = LGB_MISS; D3 ng = d3(0, 0, 0), ns = d3(0, 0, 0);
@@ -516,11 +522,13 @@ __global__ void k_fp64_peak(int iters, double* sink) {
 
 // ------------------------------------------------------------------ launch wrappers (called from lgb_api.cu)
 cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O,
-                          bool stats, cudaStream_t stream) {
+                          bool stats, bool all_shadows, cudaStream_t stream) {
     const uint64_t total = W.n_pixels * W.spp;
     if (total == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (stats) k_render<true, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O);
+    if (stats && all_shadows) k_render<true, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O);
+    else if (stats) k_render<true, false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O);
+    else if (all_shadows) k_render<false, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O);
     else k_render<false, false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -72,7 +72,9 @@ struct DevWork {
 
 struct DevCounters {
     unsigned long long primary_rays, primary_hits, shadow_traced, shadow_occluded;
-    unsigned long long exact_tests, filter_tests, node_tests;
+    unsigned long long node_tests;
+    unsigned long long filter[3];    // f32 filter tests by primitive type (sphere, cuboid, triangle)
+    unsigned long long exact[3];     // f64 reference-arithmetic tests by primitive type
     unsigned int stack_overflow;
     unsigned int pad;
 };

@@ -1,0 +1,18 @@
+"""Renders a few frames of one workload (target for ncu)."""
+import sys
+import torch
+sys.path.insert(0, ".")
+from lasgun_b200 import _native as N, scenes
+name = sys.argv[1] if len(sys.argv) > 1 else "mixed4k"
+frames = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+scale = sys.argv[3] if len(sys.argv) > 3 else "full"
+if name == "mixed4k" and scale != "full":
+    sc, (w, h) = scenes.mixed4k(res=(1920, 1080), supersampling=1)
+else:
+    sc, (w, h) = scenes.CONFIGS[name]()
+ctx = N.Context(0)
+dev = N.DeviceScene(ctx, N.FlatScene(sc))
+film = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+for i in range(frames):
+    st = dev.capture_device(w, h, film.data_ptr(), want_stats=True)
+    print(name, w, h, "frame", i, "render_ms", st["render_ms"])
