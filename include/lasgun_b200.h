@@ -123,8 +123,12 @@ typedef struct lgb_scene_desc {
 } lgb_scene_desc;
 
 #define LGB_MAX_LIGHTS 32
-/* Leaves were re-split on the host below the reference's leaves: traversal order inside a
- * reference leaf is then no longer the reference's, which can only change exact-t ties. */
+/* The caller's tree is the REFERENCE tree.  lgb_scene_create uses it (a) to validate the scene and bound
+ * the traversal stack as the reference would, and (b) to record, per ray-direction octant, the order in
+ * which the reference tests primitives, which is how exact-t ties are resolved (first tested wins,
+ * sphere.rs:86 / cuboid.rs:95 / triangle.rs:251).  The device traverses its own SAH BVH over the same
+ * primitives; results are the reference's for any such BVH.  LGB_SCENE_RESPLIT only records that the
+ * caller already re-split the reference's fat leaves (it is informational). */
 #define LGB_SCENE_RESPLIT 1u
 
 typedef struct lgb_stats {
@@ -157,6 +161,17 @@ const char* lgb_status_string(int status);
 int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* desc, lgb_scene** out);
 void lgb_scene_destroy(lgb_scene* scene);
 uint64_t lgb_scene_device_bytes(const lgb_scene* scene);
+double lgb_scene_build_ms(const lgb_scene* scene);       /* host time spent building the device BVH */
+uint32_t lgb_scene_node_count(const lgb_scene* scene);   /* nodes of the device BVH */
+
+/* Host-only probe (no GPU needed): runs the same validation, rank-table and device-BVH construction as
+ * lgb_scene_create and checks the result (every primitive in exactly one leaf, boxes nested). */
+typedef struct lgb_build_info {
+    uint32_t nodes, max_depth, leaves, max_leaf;
+    uint32_t prims, ranks_ok, boxes_ok, reserved;
+    double build_ms, rank_ms, sah_cost;
+} lgb_build_info;
+int lgb_build_probe(const lgb_scene_desc* desc, lgb_build_info* out);
 
 /* capture (src/lib.rs:55): blocking; fills caller-owned row-major RGBA8, w*h*4 bytes (host). */
 int lgb_capture(lgb_ctx* ctx, lgb_scene* scene, uint32_t w, uint32_t h, uint8_t* rgba_out, lgb_stats* stats);

@@ -20,8 +20,8 @@ LGB_LEAF_FLAG = 0x80000000
 
 # Every symbol include/lasgun_b200.h declares (checked by tests/test_abi.py without a GPU).
 ABI_SYMBOLS = [
-    "lgb_device_count", "lgb_init", "lgb_set_option", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
-    "lgb_scene_destroy", "lgb_scene_device_bytes", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
+    "lgb_build_probe", "lgb_device_count", "lgb_init", "lgb_set_option", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
+    "lgb_scene_destroy", "lgb_scene_device_bytes", "lgb_scene_build_ms", "lgb_scene_node_count", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
     "lgb_capture_device", "lgb_trace_rays", "lgb_measure_l2_read_gbs", "lgb_measure_fp32_gops", "lgb_measure_fp64_gops",
 ]
 
@@ -59,6 +59,15 @@ class SceneDesc(C.Structure):
     ]
 
 
+class BuildInfo(C.Structure):
+    _fields_ = [("nodes", C.c_uint32), ("max_depth", C.c_uint32), ("leaves", C.c_uint32), ("max_leaf", C.c_uint32),
+                ("prims", C.c_uint32), ("ranks_ok", C.c_uint32), ("boxes_ok", C.c_uint32), ("reserved", C.c_uint32),
+                ("build_ms", C.c_double), ("rank_ms", C.c_double), ("sah_cost", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class Stats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("primary_hits", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("shadow_rays_traced", C.c_uint64), ("shadow_occluded", C.c_uint64), ("exact_tests", C.c_uint64 * 3),
@@ -82,9 +91,11 @@ def lib():
     sig = {
         "lgb_device_count": (C.c_int, []), "lgb_init": (C.c_int, [C.c_int, C.POINTER(vp)]), "lgb_shutdown": (None, [vp]),
         "lgb_set_option": (C.c_int, [vp, C.c_int, C.c_int]),
+        "lgb_build_probe": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(BuildInfo)]),
         "lgb_last_error": (C.c_char_p, [vp]), "lgb_status_string": (C.c_char_p, [C.c_int]),
         "lgb_scene_create": (C.c_int, [vp, C.POINTER(SceneDesc), C.POINTER(vp)]), "lgb_scene_destroy": (None, [vp]),
-        "lgb_scene_device_bytes": (C.c_uint64, [vp]),
+        "lgb_scene_device_bytes": (C.c_uint64, [vp]), "lgb_scene_build_ms": (C.c_double, [vp]),
+        "lgb_scene_node_count": (C.c_uint32, [vp]),
         "lgb_capture": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u8p, C.POINTER(Stats)]),
         "lgb_capture_subset": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u8p, C.POINTER(Stats)]),
         "lgb_capture_aov": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u8p, u32p, dp, u32p, C.POINTER(Stats)]),
@@ -250,6 +261,14 @@ class FlatScene:
     def level_count(self):
         return lib().lgh_flat_level_count(self.h)
 
+    def build_probe(self):
+        """Host-only run of lgb_scene_create's device-BVH + rank-table construction (no GPU needed)."""
+        info = BuildInfo()
+        rc = lib().lgb_build_probe(C.byref(self.desc), C.byref(info))
+        if rc:
+            raise LasgunError(rc, "lgb_build_probe failed")
+        return info.as_dict()
+
     def __del__(self):
         try:
             if self.h:
@@ -317,6 +336,14 @@ class DeviceScene:
     @property
     def device_bytes(self):
         return lib().lgb_scene_device_bytes(self.h)
+
+    @property
+    def build_ms(self):
+        return lib().lgb_scene_build_ms(self.h)
+
+    @property
+    def node_count(self):
+        return lib().lgb_scene_node_count(self.h)
 
     def capture(self, w, h, out=None):
         rgba = out if out is not None else np.zeros((h, w, 4), np.uint8)

@@ -1,5 +1,6 @@
 // C-ABI glue (include/lasgun_b200.h): context, scene upload, capture entry points.
 // No torch types, no CPU fallback: without an sm_100-class device lgb_init fails.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -7,6 +8,9 @@
 #include <string>
 #include <vector>
 
+#include <thread>
+
+#include "lgb_build.hpp"
 #include "lgb_types.cuh"
 
 namespace lgb {
@@ -55,6 +59,7 @@ struct lgb_scene {
     DevCamera cam{};
     DevShade shade{};
     double max_abs = 0.0;      // max |coordinate| over geometry, camera origin and lights
+    double build_ms = 0.0;     // host time of the device-BVH build inside lgb_scene_create
 };
 
 static int fail(lgb_ctx* ctx, int code, const std::string& msg) {
@@ -144,7 +149,78 @@ static int upload(lgb_scene* s, const std::vector<T>& host, const T** dev) {
     return LGB_OK;
 }
 
+static void make_prim_boxes(const lgb_scene_desc* d, std::vector<PrimBox>& prims) {
+    prims.clear(); prims.reserve(d->n_spheres + d->n_cuboids + d->n_triangles);
+    for (uint64_t i = 0; i < d->n_spheres; i++) {
+        const lgb_sphere& sp = d->spheres[i]; PrimBox b; b.type = LGB_PRIM_SPHERE; b.index = (uint32_t)i;
+        for (int k = 0; k < 3; k++) { double lo = sp.center[k] - sp.radius, hi = sp.center[k] + sp.radius; b.lo[k] = f32_down(std::min(lo, hi)); b.hi[k] = f32_up(std::max(lo, hi)); }
+        prims.push_back(b);
+    }
+    for (uint64_t i = 0; i < d->n_cuboids; i++) {
+        const lgb_cuboid& c = d->cuboids[i]; PrimBox b; b.type = LGB_PRIM_CUBOID; b.index = (uint32_t)i;
+        for (int k = 0; k < 3; k++) { b.lo[k] = f32_down(std::min(c.min[k], c.max[k])); b.hi[k] = f32_up(std::max(c.min[k], c.max[k])); }
+        prims.push_back(b);
+    }
+    for (uint64_t i = 0; i < d->n_triangles; i++) {
+        const lgb_triangle& t = d->triangles[i]; PrimBox b; b.type = LGB_PRIM_TRIANGLE; b.index = (uint32_t)i;
+        for (int k = 0; k < 3; k++) { b.lo[k] = std::min(t.p0[k], std::min(t.p1[k], t.p2[k])); b.hi[k] = std::max(t.p0[k], std::max(t.p1[k], t.p2[k])); }
+        prims.push_back(b);
+    }
+}
+
 extern "C" {
+
+int lgb_build_probe(const lgb_scene_desc* d, lgb_build_info* out) {
+    if (!d || !out || !d->n_nodes) return LGB_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    const uint32_t prim_count = (uint32_t)(d->n_spheres + d->n_cuboids + d->n_triangles);
+    const int threads = (int)std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency()));
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<uint32_t> rank;
+    out->ranks_ok = build_rank_tables(d, prim_count, threads, rank) ? 1 : 0;
+    out->rank_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::vector<PrimBox> prims; make_prim_boxes(d, prims);
+    BuiltBVH bvh;
+    if (build_sah(prims, 0.0f, threads, bvh)) return LGB_ERR_INVALID;
+    out->nodes = (uint32_t)bvh.nodes.size(); out->max_depth = bvh.max_depth; out->prims = prim_count; out->build_ms = bvh.build_ms;
+    // verify: every primitive in exactly one leaf, leaf boxes contain their primitives, child boxes nest
+    std::vector<uint8_t> seen[3];
+    for (int t = 0; t < 3; t++) seen[t].assign(bvh.order[t].size(), 0);
+    std::vector<std::vector<const PrimBox*>> by_type(3);
+    for (const PrimBox& p : prims) { if (by_type[p.type].size() <= p.index) by_type[p.type].resize(p.index + 1); by_type[p.type][p.index] = &p; }
+    bool ok = true; double cost = 0.0;
+    struct E { uint32_t node; float lo[3], hi[3]; };
+    std::vector<E> st; E root; root.node = 0; for (int k = 0; k < 3; k++) { root.lo[k] = -INFINITY; root.hi[k] = INFINITY; } st.push_back(root);
+    auto area = [](const float* lo, const float* hi) { float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2]; return (double)(x * y + x * z + y * z); };
+    double root_area = 0.0;
+    while (!st.empty()) {
+        E e = st.back(); st.pop_back();
+        const HostNode& n = bvh.nodes[e.node];
+        for (int c = 0; c < 2; c++) {
+            const float* lo = n.v + 6 * c; const float* hi = n.v + 6 * c + 3; const uint32_t w = c ? n.c1 : n.c0;
+            if (lo[0] != lo[0]) continue;     // empty child
+            for (int k = 0; k < 3; k++) if (lo[k] < e.lo[k] || hi[k] > e.hi[k]) ok = false;
+            if (e.node == 0) root_area += area(lo, hi);
+            if (w & kLeafBit) {
+                const uint32_t type = (w >> 29) & 3u, cnt = ((w >> 24) & 31u) + 1u, first = w & kLeafFirstMask;
+                out->leaves++; out->max_leaf = std::max(out->max_leaf, cnt); cost += area(lo, hi) * cnt;
+                for (uint32_t i = 0; i < cnt; i++) {
+                    if (first + i >= bvh.order[type].size()) { ok = false; continue; }
+                    if (seen[type][first + i]++) ok = false;
+                    const PrimBox* p = by_type[type][bvh.order[type][first + i]];
+                    for (int k = 0; k < 3; k++) if (p->lo[k] < lo[k] || p->hi[k] > hi[k]) ok = false;
+                }
+            } else {
+                cost += area(lo, hi) * 1.0;
+                E ch; ch.node = w; std::memcpy(ch.lo, lo, 12); std::memcpy(ch.hi, hi, 12); st.push_back(ch);
+            }
+        }
+    }
+    for (int t = 0; t < 3; t++) for (uint8_t v : seen[t]) if (v != 1) ok = false;
+    out->boxes_ok = ok ? 1 : 0;
+    out->sah_cost = root_area > 0 ? cost / root_area : 0.0;
+    return LGB_OK;
+}
 
 void lgb_scene_destroy(lgb_scene* s) {
     if (!s) return;
@@ -154,6 +230,8 @@ void lgb_scene_destroy(lgb_scene* s) {
     delete s;
 }
 uint64_t lgb_scene_device_bytes(const lgb_scene* s) { return s ? s->bytes : 0; }
+double lgb_scene_build_ms(const lgb_scene* s) { return s ? s->build_ms : 0.0; }
+uint32_t lgb_scene_node_count(const lgb_scene* s) { return s ? s->dev.n_nodes : 0; }
 
 int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     if (!ctx || !d || !out) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: NULL argument");
@@ -238,53 +316,67 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     M += 2.5 * std::fabs(d->camera.image_plane_height) * std::fabs(d->camera.pixel_separation);
     s->max_abs = M;
 
-    // ---- nodes: pad boxes so that an f32-rounded ray stays conservative
-    // pad is finalised per capture (camera offsets); here the geometric part.
+    // ---- device acceleration structure: binned-SAH BVH over the same primitives, rank tables from the
+    //      caller's reference tree (lgb_build.hpp); everything is stored in leaf order.
+    const uint32_t prim_count = (uint32_t)(d->n_spheres + d->n_cuboids + d->n_triangles);
+    if (prim_count == 0) return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: no primitives"));
+    const int threads = (int)std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<uint32_t> rank;
+    if (!build_rank_tables(d, prim_count, threads, rank))
+        return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: primitive ids must be a permutation of 0..n-1 and every primitive must be referenced by exactly one leaf"));
+    const double padd = M * std::ldexp(1.0, -20);
+    s->dev.err_abs = (float)padd;
+    BuiltBVH bvh;
     {
-        std::vector<float4> nodes(2 * nn);
-        const double pad = M * std::ldexp(1.0, -20);
-        for (uint64_t i = 0; i < nn; i++) {
-            const lgb_node& n = d->nodes[i];
-            float4 lo, hi;
-            lo.x = f32_down((double)n.lo[0] - pad); lo.y = f32_down((double)n.lo[1] - pad); lo.z = f32_down((double)n.lo[2] - pad);
-            hi.x = f32_up((double)n.hi[0] + pad); hi.y = f32_up((double)n.hi[1] + pad); hi.z = f32_up((double)n.hi[2] + pad);
-            std::memcpy(&lo.w, &n.a, 4); std::memcpy(&hi.w, &n.b, 4);
-            nodes[2 * i] = lo; nodes[2 * i + 1] = hi;
-        }
-        if ((rc = upload(s, nodes, &s->dev.nodes))) return bail(rc);
-        s->dev.n_nodes = (uint32_t)nn;
-        s->dev.err_abs = (float)(M * std::ldexp(1.0, -20));
+        std::vector<PrimBox> prims; make_prim_boxes(d, prims);
+        int brc = build_sah(prims, (float)padd, threads, bvh);
+        if (brc == -2) return bail(fail(ctx, LGB_ERR_UNSUPPORTED, "lgb_scene_create: more than 16.7M primitives of one type"));
+        if (brc) return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: BVH build failed"));
+        if (bvh.max_depth + 1 > (uint32_t)kStackDepth) return bail(fail(ctx, LGB_ERR_UNSUPPORTED, "device BVH deeper than the 64-entry traversal stack"));
     }
+    s->build_ms = bvh.build_ms;
     {
-        std::vector<uint32_t> refs(d->prim_refs, d->prim_refs + d->n_prim_refs);
-        if ((rc = upload(s, refs, &s->dev.prim_refs))) return bail(rc);
+        static_assert(sizeof(HostNode) == 64, "node layout");
+        std::vector<float4> nodes(4 * bvh.nodes.size());
+        std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size() * sizeof(HostNode));
+        if ((rc = upload(s, nodes, &s->dev.nodes))) return bail(rc);
+        s->dev.n_nodes = (uint32_t)bvh.nodes.size();
+        if ((rc = upload(s, rank, &s->dev.rank))) return bail(rc);
+        s->dev.prim_count = prim_count;
     }
     if (d->n_spheres) {
+        const std::vector<uint32_t>& ord = bvh.order[LGB_PRIM_SPHERE];
         std::vector<float4> s32(d->n_spheres); std::vector<double> s64(4 * d->n_spheres);
-        for (uint64_t i = 0; i < d->n_spheres; i++) {
+        std::vector<uint32_t> m(d->n_spheres), id(d->n_spheres);
+        for (uint64_t j = 0; j < d->n_spheres; j++) {
+            const uint32_t i = ord[j];
             const lgb_sphere& sp = d->spheres[i];
-            s32[i] = make_float4((float)sp.center[0], (float)sp.center[1], (float)sp.center[2], f32_up(sp.radius));
-            s64[4 * i] = sp.center[0]; s64[4 * i + 1] = sp.center[1]; s64[4 * i + 2] = sp.center[2]; s64[4 * i + 3] = sp.radius;
+            s32[j] = make_float4((float)sp.center[0], (float)sp.center[1], (float)sp.center[2], f32_up(std::fabs(sp.radius)));
+            s64[4 * j] = sp.center[0]; s64[4 * j + 1] = sp.center[1]; s64[4 * j + 2] = sp.center[2]; s64[4 * j + 3] = sp.radius;
+            m[j] = d->sphere_material[i]; id[j] = d->sphere_id[i];
         }
-        std::vector<uint32_t> m(d->sphere_material, d->sphere_material + d->n_spheres), id(d->sphere_id, d->sphere_id + d->n_spheres);
         if ((rc = upload(s, s32, &s->dev.sph32)) || (rc = upload(s, s64, &s->dev.sph64)) || (rc = upload(s, m, &s->dev.sph_mat)) || (rc = upload(s, id, &s->dev.sph_id))) return bail(rc);
     }
     if (d->n_cuboids) {
+        const std::vector<uint32_t>& ord = bvh.order[LGB_PRIM_CUBOID];
         std::vector<float4> c32(2 * d->n_cuboids); std::vector<double> c64(6 * d->n_cuboids);
-        const double pad = M * std::ldexp(1.0, -20);
-        for (uint64_t i = 0; i < d->n_cuboids; i++) {
+        std::vector<uint32_t> m(d->n_cuboids), id(d->n_cuboids);
+        for (uint64_t j = 0; j < d->n_cuboids; j++) {
+            const uint32_t i = ord[j];
             const lgb_cuboid& c = d->cuboids[i];
-            c32[2 * i] = make_float4(f32_down(c.min[0] - pad), f32_down(c.min[1] - pad), f32_down(c.min[2] - pad), 0.f);
-            c32[2 * i + 1] = make_float4(f32_up(c.max[0] + pad), f32_up(c.max[1] + pad), f32_up(c.max[2] + pad), 0.f);
-            for (int k = 0; k < 3; k++) { c64[6 * i + k] = c.min[k]; c64[6 * i + 3 + k] = c.max[k]; }
+            c32[2 * j] = make_float4(f32_down(c.min[0] - padd), f32_down(c.min[1] - padd), f32_down(c.min[2] - padd), 0.f);
+            c32[2 * j + 1] = make_float4(f32_up(c.max[0] + padd), f32_up(c.max[1] + padd), f32_up(c.max[2] + padd), 0.f);
+            for (int k = 0; k < 3; k++) { c64[6 * j + k] = c.min[k]; c64[6 * j + 3 + k] = c.max[k]; }
+            m[j] = d->cuboid_material[i]; id[j] = d->cuboid_id[i];
         }
-        std::vector<uint32_t> m(d->cuboid_material, d->cuboid_material + d->n_cuboids), id(d->cuboid_id, d->cuboid_id + d->n_cuboids);
         if ((rc = upload(s, c32, &s->dev.cub32)) || (rc = upload(s, c64, &s->dev.cub64)) || (rc = upload(s, m, &s->dev.cub_mat)) || (rc = upload(s, id, &s->dev.cub_id))) return bail(rc);
     }
     if (d->n_triangles) {
+        const std::vector<uint32_t>& ord = bvh.order[LGB_PRIM_TRIANGLE];
         std::vector<float4> t(3 * d->n_triangles);
         std::vector<float> nrm;
-        for (uint64_t i = 0; i < d->n_triangles; i++) {
+        for (uint64_t j = 0; j < d->n_triangles; j++) {
+            const uint32_t i = ord[j];
             const lgb_triangle& tr = d->triangles[i];
             uint32_t ni = kNoNormals;
             if (d->tri_normals && (!d->tri_has_normals || d->tri_has_normals[i])) {
@@ -294,14 +386,9 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
             }
             float4 a = make_float4(tr.p0[0], tr.p0[1], tr.p0[2], 0.f), b = make_float4(tr.p1[0], tr.p1[1], tr.p1[2], 0.f), c = make_float4(tr.p2[0], tr.p2[1], tr.p2[2], 0.f);
             std::memcpy(&a.w, &d->triangle_id[i], 4); std::memcpy(&b.w, &d->triangle_material[i], 4); std::memcpy(&c.w, &ni, 4);
-            t[3 * i] = a; t[3 * i + 1] = b; t[3 * i + 2] = c;
+            t[3 * j] = a; t[3 * j + 1] = b; t[3 * j + 2] = c;
         }
         if ((rc = upload(s, t, &s->dev.tri)) || (rc = upload(s, nrm, &s->dev.tri_nrm))) return bail(rc);
-    }
-    if (d->n_instances) {
-        std::vector<uint32_t> roots(d->n_instances);
-        for (uint64_t i = 0; i < d->n_instances; i++) roots[i] = d->instances[i].root_node;
-        if ((rc = upload(s, roots, &s->dev.inst_root))) return bail(rc);
     }
     if ((rc = upload(s, mats, &s->dev.materials))) return bail(rc);
     {

@@ -15,18 +15,28 @@ namespace lgb {
 // ------------------------------------------------------------------ per-ray f32 state
 struct RayF {
     float ox, oy, oz;
-    float ix, iy, iz;        // 1/d (rounded from the f64 reciprocal)
+    float ix, iy, iz;        // 1/d, clamped to +-1e30 (rounded from the f64 reciprocal)
+    float nx, ny, nz;        // -o * (1/d): slab planes are evaluated as fma(plane, 1/d, -o/d)
     float dx, dy, dz;
     float inv_dd, inv_len;   // 1/(d.d), 1/|d|
     float sx, sy, sz;        // triangle shear (triangle.rs:199-201), f32 copies
     float err;               // absolute coordinate error bound; +inf disables the filters
-    int kx, ky, kz;
+    int kz;
+    unsigned oct;            // bit a set <=> dir_is_neg[a] (bvh.rs:463)
 };
+
+__device__ __forceinline__ float clamp_idir(double d) {
+    float v = (float)(1.0 / d);
+    return fabsf(v) > 1e30f ? copysignf(1e30f, v) : v;
+}
 
 __device__ __forceinline__ RayF make_rayf(const Ray64& r, float err_abs) {
     RayF f;
     f.ox = (float)r.o.x; f.oy = (float)r.o.y; f.oz = (float)r.o.z;
-    f.ix = (float)(1.0 / r.d.x); f.iy = (float)(1.0 / r.d.y); f.iz = (float)(1.0 / r.d.z);
+    const double rx = 1.0 / r.d.x, ry = 1.0 / r.d.y, rz = 1.0 / r.d.z;
+    f.oct = (rx < 0.0 ? 1u : 0u) | (ry < 0.0 ? 2u : 0u) | (rz < 0.0 ? 4u : 0u);
+    f.ix = clamp_idir(r.d.x); f.iy = clamp_idir(r.d.y); f.iz = clamp_idir(r.d.z);
+    f.nx = -f.ox * f.ix; f.ny = -f.oy * f.iy; f.nz = -f.oz * f.iz;
     f.dx = (float)r.d.x; f.dy = (float)r.d.y; f.dz = (float)r.d.z;
     float dd = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
     f.inv_dd = 1.0f / dd;
@@ -34,140 +44,174 @@ __device__ __forceinline__ RayF make_rayf(const Ray64& r, float err_abs) {
     // |d| outside the comfortable f32 range: make every filter band infinite (exact tests only).
     f.err = (dd > 1e-24f && dd < 1e24f) ? err_abs : CUDART_INF_F;
     f.kz = max_dimension_abs(r.d);
-    f.kx = (f.kz + 1) % 3;
-    f.ky = (f.kx + 1) % 3;
+    const int kx = (f.kz + 1) % 3, ky = (kx + 1) % 3;
     float fdz = f.kz == 0 ? f.dx : (f.kz == 1 ? f.dy : f.dz);
-    float fdx = f.kx == 0 ? f.dx : (f.kx == 1 ? f.dy : f.dz);
-    float fdy = f.ky == 0 ? f.dx : (f.ky == 1 ? f.dy : f.dz);
+    float fdx = kx == 0 ? f.dx : (kx == 1 ? f.dy : f.dz);
+    float fdy = ky == 0 ? f.dx : (ky == 1 ? f.dy : f.dz);
     f.sz = 1.0f / fdz;
     f.sx = -fdx * f.sz;
     f.sy = -fdy * f.sz;
     return f;
 }
 
-__device__ __forceinline__ float pick(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
-
-// Conservative slab test of an f32 ray against a padded f32 box.  Returns false only if the exact
-// (f64) ray certainly misses the exact box or enters it beyond tbest.  See DESIGN.md §4.1.
-__device__ __forceinline__ bool slab_conservative(const float4 lo, const float4 hi, const RayF& f, float tbest) {
-    float t1x = (lo.x - f.ox) * f.ix, t2x = (hi.x - f.ox) * f.ix;
-    float t1y = (lo.y - f.oy) * f.iy, t2y = (hi.y - f.oy) * f.iy;
-    float t1z = (lo.z - f.oz) * f.iz, t2z = (hi.z - f.oz) * f.iz;
+// Conservative slab test of an f32 ray against a padded f32 box: returns false only if
+// the exact f64 ray certainly misses the exact box or enters it beyond tbest.  tnear_out orders children.
+__device__ __forceinline__ bool slab2(float lx, float ly, float lz, float hx, float hy, float hz, const RayF& f, float tbest, float& tnear_out) {
+    float t1x = __fmaf_rn(lx, f.ix, f.nx), t2x = __fmaf_rn(hx, f.ix, f.nx);
+    float t1y = __fmaf_rn(ly, f.iy, f.ny), t2y = __fmaf_rn(hy, f.iy, f.ny);
+    float t1z = __fmaf_rn(lz, f.iz, f.nz), t2z = __fmaf_rn(hz, f.iz, f.nz);
     float tnear = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
     float tfar = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
     const float up = 1.0f + 4.76837158e-7f, dn = 1.0f - 4.76837158e-7f;   // 1 +- 2^-21
     tfar = tfar * up;                      // tfar < 0 is rejected either way
     tnear = tnear > 0.0f ? tnear * dn : tnear * up;
+    tnear_out = tnear;
     return tnear <= tfar && tfar > 0.0f && tnear <= tbest;
 }
 
-struct Hit { double t; uint32_t ref; };
+struct Hit { double t; uint32_t ref; };     // ref = type << 30 | index in the leaf-ordered arrays
 
 struct LocalCounters { unsigned int node_tests, filter[3], exact[3]; };
 
-// Closest hit (ANYHIT = false) or "any hit with t < tmax" (ANYHIT = true, shadow rays: the
-// reference asks for the closest t and compares it with 1.0, light/point.rs:48-49, which is
-// equivalent).  Traversal order and push order follow bvh.rs:461-506; the extra
-// `tnear > best` cull is result-safe because every primitive rejects t >= isect.t itself.
+__device__ __forceinline__ uint32_t canonical_id(const DevScene& S, uint32_t ref) {
+    const uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+    if (type == LGB_PRIM_SPHERE) return S.sph_id[idx];
+    if (type == LGB_PRIM_CUBOID) return S.cub_id[idx];
+    return __float_as_uint(S.tri[3 * (size_t)idx].w);
+}
+
+// A candidate with exact parameter t replaces the current best iff it is nearer, or equally near and
+// earlier in the reference's own traversal order for this ray's octant (lgb_build.hpp).
+__device__ __forceinline__ bool accepts(const DevScene& S, const RayF& f, const Hit& best, double t, uint32_t ref) {
+    if (t < best.t) return true;
+    if (t == best.t && best.ref != LGB_MISS) {
+        const uint32_t* r = S.rank + (size_t)f.oct * S.prim_count;
+        return r[canonical_id(S, ref)] < r[canonical_id(S, best.ref)];
+    }
+    return false;
+}
+
+// f32 filter for one triangle, specialised on the ray's dominant axis (no per-vertex selects).
+template <int KZ>
+__device__ __forceinline__ bool tri_filter(const float4 q0, const float4 q1, const float4 q2, const RayF& f, float best_tf) {
+    constexpr int KX = (KZ + 1) % 3, KY = (KX + 1) % 3;
+    const float o[3] = {f.ox, f.oy, f.oz};
+    const float a[3] = {q0.x - o[0], q0.y - o[1], q0.z - o[2]};
+    const float b[3] = {q1.x - o[0], q1.y - o[1], q1.z - o[2]};
+    const float c[3] = {q2.x - o[0], q2.y - o[1], q2.z - o[2]};
+    const float Ax = __fmaf_rn(f.sx, a[KZ], a[KX]), Ay = __fmaf_rn(f.sy, a[KZ], a[KY]);
+    const float Bx = __fmaf_rn(f.sx, b[KZ], b[KX]), By = __fmaf_rn(f.sy, b[KZ], b[KY]);
+    const float Cx = __fmaf_rn(f.sx, c[KZ], c[KX]), Cy = __fmaf_rn(f.sy, c[KZ], c[KY]);
+    const float e0 = __fmaf_rn(Bx, Cy, -By * Cx), e1 = __fmaf_rn(Cx, Ay, -Cy * Ax), e2 = __fmaf_rn(Ax, By, -Ay * Bx);
+    const float m = fmaxf(fmaxf(fmaxf(fabsf(Ax), fabsf(Ay)), fmaxf(fabsf(Bx), fabsf(By))), fmaxf(fabsf(Cx), fabsf(Cy)));
+    const float band = 6.0f * m * f.err;
+    const float emin = fminf(fminf(e0, e1), e2), emax = fmaxf(fmaxf(e0, e1), e2);
+    if (emin < -band && emax > band) return false;
+    // depth range of the triangle along the ray
+    const float tz0 = a[KZ] * f.sz, tz1 = b[KZ] * f.sz, tz2 = c[KZ] * f.sz;
+    const float tlo = fminf(fminf(tz0, tz1), tz2), thi = fmaxf(fmaxf(tz0, tz1), tz2);
+    const float slack = f.err * fabsf(f.sz);
+    if (tlo - slack - fabsf(tlo) * 1e-6f > best_tf) return false;
+    if (thi + slack + fabsf(thi) * 1e-6f < 0.0f) return false;
+    return true;
+}
+
+// Closest hit (ANYHIT = false) or "any hit with t < tmax" (ANYHIT = true, shadow rays: the reference
+// asks for the closest t and compares it with 1.0, light/point.rs:48-49, which is equivalent).
+// while-while traversal of the device BVH: the inner loop descends interior nodes (two child boxes per
+// fetch, nearer child first), the outer loop intersects one homogeneous leaf.  The `tnear > best` cull is
+// result-safe because every primitive rejects t >= isect.t itself (bvh.rs:473 never looks at isect.t).
 template <bool ANYHIT, bool STATS>
 __device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalCounters& lc, unsigned int& overflow) {
     const RayF f = make_rayf(ray, S.err_abs);
-    const unsigned neg_mask = (f.ix < 0.0f ? 1u : 0u) | (f.iy < 0.0f ? 2u : 0u) | (f.iz < 0.0f ? 4u : 0u);
     Hit best; best.t = tmax; best.ref = LGB_MISS;
     float best_tf = __double2float_ru(tmax);
-    const float err = f.err;
     uint32_t stack[kStackDepth];
     int sp = 0;
-    uint32_t node = 0;
+    uint32_t cur = 0;
     for (;;) {
-        const float4 n0 = __ldg(&S.nodes[2 * node]);
-        const float4 n1 = __ldg(&S.nodes[2 * node + 1]);
-        if (STATS) lc.node_tests++;
-        if (slab_conservative(n0, n1, f, best_tf)) {
-            const uint32_t a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
-            if (b & LGB_LEAF_FLAG) {
-                const uint32_t count = b & ~LGB_LEAF_FLAG;
+        while (!(cur & kLeafBit) && cur != kDone) {
+            const float4* np = S.nodes + 4 * (size_t)cur;
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+            if (STATS) lc.node_tests++;
+            float tn0, tn1;
+            const bool h0 = slab2(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, f, best_tf, tn0);
+            const bool h1 = slab2(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, f, best_tf, tn1);
+            const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+            if (h0 && h1) {
+                const bool swap = tn1 < tn0;
+                cur = swap ? c1 : c0;
+                if (sp < kStackDepth) stack[sp++] = swap ? c0 : c1; else overflow = 1;
+            } else if (h0) cur = c0;
+            else if (h1) cur = c1;
+            else cur = sp ? stack[--sp] : kDone;
+        }
+        if (cur == kDone) break;
+        {
+            const uint32_t type = (cur >> 29) & 3u, count = ((cur >> 24) & 31u) + 1u, first = cur & kLeafFirstMask;
+            if (type == LGB_PRIM_TRIANGLE) {
                 for (uint32_t i = 0; i < count; i++) {
-                    const uint32_t ref = __ldg(&S.prim_refs[a + i]);
-                    const uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
-                    if (type == LGB_PRIM_TRIANGLE) {
-                        const float4 q0 = __ldg(&S.tri[3 * idx]), q1 = __ldg(&S.tri[3 * idx + 1]), q2 = __ldg(&S.tri[3 * idx + 2]);
-                        if (STATS) lc.filter[2]++;
-                        // f32 watertight edge functions with an error band
-                        float ax = q0.x - f.ox, ay = q0.y - f.oy, az = q0.z - f.oz;
-                        float bx = q1.x - f.ox, by = q1.y - f.oy, bz = q1.z - f.oz;
-                        float cx = q2.x - f.ox, cy = q2.y - f.oy, cz = q2.z - f.oz;
-                        float Az = pick(ax, ay, az, f.kz), Bz = pick(bx, by, bz, f.kz), Cz = pick(cx, cy, cz, f.kz);
-                        float Ax = __fmaf_rn(f.sx, Az, pick(ax, ay, az, f.kx)), Ay = __fmaf_rn(f.sy, Az, pick(ax, ay, az, f.ky));
-                        float Bx = __fmaf_rn(f.sx, Bz, pick(bx, by, bz, f.kx)), By = __fmaf_rn(f.sy, Bz, pick(bx, by, bz, f.ky));
-                        float Cx = __fmaf_rn(f.sx, Cz, pick(cx, cy, cz, f.kx)), Cy = __fmaf_rn(f.sy, Cz, pick(cx, cy, cz, f.ky));
-                        float e0 = Bx * Cy - By * Cx, e1 = Cx * Ay - Cy * Ax, e2 = Ax * By - Ay * Bx;
-                        float m = fmaxf(fmaxf(fmaxf(fabsf(Ax), fabsf(Ay)), fmaxf(fabsf(Bx), fabsf(By))), fmaxf(fabsf(Cx), fabsf(Cy)));
-                        float band = 6.0f * m * err;
-                        float emin = fminf(fminf(e0, e1), e2), emax = fmaxf(fmaxf(e0, e1), e2);
-                        if (emin < -band && emax > band) continue;
-                        // depth range of the triangle along the ray
-                        float tz0 = Az * f.sz, tz1 = Bz * f.sz, tz2 = Cz * f.sz;
-                        float tlo = fminf(fminf(tz0, tz1), tz2), thi = fmaxf(fmaxf(tz0, tz1), tz2);
-                        float slack = err * fabsf(f.sz);
-                        if (tlo - slack - fabsf(tlo) * 1e-6f > best_tf) continue;
-                        if (thi + slack + fabsf(thi) * 1e-6f < 0.0f) continue;
-                        if (STATS) lc.exact[2]++;
-                        double t, b0, b1, b2;
-                        if (triangle_exact(d3(q0.x, q0.y, q0.z), d3(q1.x, q1.y, q1.z), d3(q2.x, q2.y, q2.z), ray, best.t, t, b0, b1, b2)) {
-                            best.t = t; best.ref = ref; best_tf = __double2float_ru(t);
-                            if (ANYHIT) return best;
-                        }
-                    } else if (type == LGB_PRIM_SPHERE) {
-                        const float4 s = __ldg(&S.sph32[idx]);
-                        if (STATS) lc.filter[0]++;
-                        float lx = s.x - f.ox, ly = s.y - f.oy, lz = s.z - f.oz;
-                        float bq = lx * f.dx + ly * f.dy + lz * f.dz;
-                        float tc = bq * f.inv_dd;
-                        float wx = __fmaf_rn(-tc, f.dx, lx), wy = __fmaf_rn(-tc, f.dy, ly), wz = __fmaf_rn(-tc, f.dz, lz);
-                        float perp2 = wx * wx + wy * wy + wz * wz;
-                        float rr = s.w + 2.0f * err;
-                        if (perp2 > rr * rr * (1.0f + 1e-6f)) continue;
-                        float half = rr * f.inv_len;
-                        float slack = fabsf(tc) * 2e-6f + 2.0f * err * f.inv_len;
-                        if (tc - half - slack > best_tf) continue;
-                        if (tc + half + slack < 0.0f) continue;
-                        if (STATS) lc.exact[0]++;
-                        const double2 c01 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx));
-                        const double2 c23 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx + 2));
-                        double t; bool inside;
-                        if (sphere_exact(d3(c01.x, c01.y, c23.x), c23.y, ray, best.t, t, inside)) {
-                            best.t = t; best.ref = ref; best_tf = __double2float_ru(t);
-                            if (ANYHIT) return best;
-                        }
-                    } else if (type == LGB_PRIM_CUBOID) {
-                        const float4 lo = __ldg(&S.cub32[2 * idx]), hi = __ldg(&S.cub32[2 * idx + 1]);
-                        if (STATS) lc.filter[1]++;
-                        if (!slab_conservative(lo, hi, f, CUDART_INF_F)) continue;
-                        if (STATS) lc.exact[1]++;
-                        double mn[3], mx[3];
-#pragma unroll
-                        for (int k = 0; k < 3; k++) { mn[k] = __ldg(&S.cub64[6 * (size_t)idx + k]); mx[k] = __ldg(&S.cub64[6 * (size_t)idx + 3 + k]); }
-                        double t; int ua, va;
-                        if (cuboid_exact(mn, mx, ray, best.t, t, ua, va)) {
-                            best.t = t; best.ref = ref; best_tf = __double2float_ru(t);
-                            if (ANYHIT) return best;
-                        }
-                    } else {   // nested BVH with identity transform (bvh.rs:141-162): descend later
-                        if (sp < kStackDepth) stack[sp++] = __ldg(&S.inst_root[idx]); else overflow = 1;
+                    const uint32_t idx = first + i;
+                    const float4* tp = S.tri + 3 * (size_t)idx;
+                    const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+                    if (STATS) lc.filter[2]++;
+                    const bool pass = f.kz == 0 ? tri_filter<0>(q0, q1, q2, f, best_tf) : f.kz == 1 ? tri_filter<1>(q0, q1, q2, f, best_tf) : tri_filter<2>(q0, q1, q2, f, best_tf);
+                    if (!pass) continue;
+                    if (STATS) lc.exact[2]++;
+                    double t, b0, b1, b2;
+                    if (triangle_exact(d3(q0.x, q0.y, q0.z), d3(q1.x, q1.y, q1.z), d3(q2.x, q2.y, q2.z), ray, t, b0, b1, b2)) {
+                        const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_TRIANGLE, idx);
+                        if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; return best; } }
+                        else if (accepts(S, f, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); }
+                    }
+                }
+            } else if (type == LGB_PRIM_SPHERE) {
+                for (uint32_t i = 0; i < count; i++) {
+                    const uint32_t idx = first + i;
+                    const float4 s = __ldg(&S.sph32[idx]);
+                    if (STATS) lc.filter[0]++;
+                    float lx = s.x - f.ox, ly = s.y - f.oy, lz = s.z - f.oz;
+                    float bq = lx * f.dx + ly * f.dy + lz * f.dz;
+                    float tc = bq * f.inv_dd;
+                    float wx = __fmaf_rn(-tc, f.dx, lx), wy = __fmaf_rn(-tc, f.dy, ly), wz = __fmaf_rn(-tc, f.dz, lz);
+                    float perp2 = wx * wx + wy * wy + wz * wz;
+                    float rr = s.w + 2.0f * f.err;
+                    if (perp2 > rr * rr * (1.0f + 1e-6f)) continue;
+                    float half = rr * f.inv_len;
+                    float slack = fabsf(tc) * 2e-6f + 2.0f * f.err * f.inv_len;
+                    if (tc - half - slack > best_tf) continue;
+                    if (tc + half + slack < 0.0f) continue;
+                    if (STATS) lc.exact[0]++;
+                    const double2 c01 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx));
+                    const double2 c23 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx + 2));
+                    double t; bool inside;
+                    if (sphere_exact(d3(c01.x, c01.y, c23.x), c23.y, ray, t, inside)) {
+                        const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_SPHERE, idx);
+                        if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; return best; } }
+                        else if (accepts(S, f, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); }
                     }
                 }
             } else {
-                // interior: far child on the stack, continue with the near one (bvh.rs:493-504)
-                const bool neg = (neg_mask >> b) & 1u;
-                const uint32_t near_child = neg ? a : node + 1, far_child = neg ? node + 1 : a;
-                if (sp < kStackDepth) stack[sp++] = far_child; else overflow = 1;
-                node = near_child;
-                continue;
+                for (uint32_t i = 0; i < count; i++) {
+                    const uint32_t idx = first + i;
+                    const float4 lo = __ldg(&S.cub32[2 * idx]), hi = __ldg(&S.cub32[2 * idx + 1]);
+                    if (STATS) lc.filter[1]++;
+                    float tn;
+                    if (!slab2(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, f, CUDART_INF_F, tn)) continue;
+                    if (STATS) lc.exact[1]++;
+                    double mn[3], mx[3];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) { mn[k] = __ldg(&S.cub64[6 * (size_t)idx + k]); mx[k] = __ldg(&S.cub64[6 * (size_t)idx + 3 + k]); }
+                    double t; int ua, va;
+                    if (cuboid_exact(mn, mx, ray, t, ua, va)) {
+                        const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_CUBOID, idx);
+                        if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; return best; } }
+                        else if (accepts(S, f, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); }
+                    }
+                }
             }
         }
-        if (sp == 0) break;
-        node = stack[--sp];
+        cur = sp ? stack[--sp] : kDone;
     }
     return best;
 }
@@ -190,7 +234,7 @@ __device__ void surface_of(const DevScene& S, const Ray64& ray, uint32_t ref, do
         D3 c = d3(S.sph64[4 * (size_t)idx], S.sph64[4 * (size_t)idx + 1], S.sph64[4 * (size_t)idx + 2]);
         double rad = S.sph64[4 * (size_t)idx + 3];
         bool inside; double tt;
-        sphere_exact(c, rad, ray, CUDART_INF, tt, inside);
+        sphere_exact(c, rad, ray, tt, inside);
         t = tt;
         D3 p = ray.o + ray.d * tt - c;
         if (p.x == 0.0 && p.y == 0.0) p.x = 1e-5 * rad;
@@ -207,7 +251,7 @@ __device__ void surface_of(const DevScene& S, const Ray64& ray, uint32_t ref, do
         double mn[3], mx[3];
         for (int k = 0; k < 3; k++) { mn[k] = S.cub64[6 * (size_t)idx + k]; mx[k] = S.cub64[6 * (size_t)idx + 3 + k]; }
         int ua = 1, va = 2; double tt = t;
-        cuboid_exact(mn, mx, ray, CUDART_INF, tt, ua, va);
+        cuboid_exact(mn, mx, ray, tt, ua, va);
         t = tt;
         D3 du = axis_vec(ua), dv = axis_vec(va);
         sf.g_dpdu = du; sf.g_dpdv = dv; sf.s_dpdu = du; sf.s_dpdv = dv;
@@ -217,7 +261,7 @@ __device__ void surface_of(const DevScene& S, const Ray64& ray, uint32_t ref, do
         const float4 q0 = S.tri[3 * (size_t)idx], q1 = S.tri[3 * (size_t)idx + 1], q2 = S.tri[3 * (size_t)idx + 2];
         D3 p0 = d3(q0.x, q0.y, q0.z), p1 = d3(q1.x, q1.y, q1.z), p2 = d3(q2.x, q2.y, q2.z);
         double tt = t, b0 = 0, b1 = 0, b2 = 0;
-        triangle_exact(p0, p1, p2, ray, CUDART_INF, tt, b0, b1, b2);
+        triangle_exact(p0, p1, p2, ray, tt, b0, b1, b2);
         t = tt;
         D3 dp02 = p0 - p2, dp12 = p1 - p2;
         // default uvs (0,0) (1,0) (1,1): determinant 1, dpdu = -dp02 + dp12, dpdv = dp12 (triangle.rs:258-270)

@@ -30,7 +30,9 @@ __device__ __forceinline__ D3 axis_vec(int i) { return d3(i == 0 ? 1.0 : 0.0, i 
 struct Ray64 { D3 o, d; };
 
 // ---- sphere.rs:30-69, 79-86 with math.rs:7-30 inlined -----------------------------------
-__device__ __forceinline__ bool sphere_exact(D3 c, double rad, const Ray64& ray, double tbest, double& t_out, bool& inside) {
+// The `t >= isect.t` rejection (sphere.rs:86, cuboid.rs:95, triangle.rs:251) is applied by the caller,
+// together with the reference-order tie rule.
+__device__ __forceinline__ bool sphere_exact(D3 c, double rad, const Ray64& ray, double& t_out, bool& inside) {
     D3 d = ray.d;
     D3 l = ray.o - c;
     double a = dot(d, d);
@@ -52,13 +54,12 @@ __device__ __forceinline__ bool sphere_exact(D3 c, double rad, const Ray64& ray,
         if (t0 < 0.0) { t = t1; inside = true; } else { t = t0; }
     }
     if (t < 0.0) return false;
-    if (t >= tbest) return false;
     t_out = t;
     return true;
 }
 
 // ---- cuboid.rs:55-95.  (u_axis, v_axis): dpdu = e_u, dpdv = e_v of the chosen face -------
-__device__ __forceinline__ bool cuboid_exact(const double* mn, const double* mx, const Ray64& ray, double tbest,
+__device__ __forceinline__ bool cuboid_exact(const double* mn, const double* mx, const Ray64& ray,
                                              double& t_out, int& u_axis, int& v_axis) {
     double tnear = -CUDART_INF, tfar = CUDART_INF;
     int nu = 1, nv = 2, fu = 1, fv = 2;          // CUBE_DIFFERENTIALS[0] = (y, z)
@@ -79,7 +80,6 @@ __device__ __forceinline__ bool cuboid_exact(const double* mn, const double* mx,
     if (tnear > tfar || tfar <= 0.0) return false;
     double t;
     if (tnear <= 0.0) { t = tfar; u_axis = fu; v_axis = fv; } else { t = tnear; u_axis = nu; v_axis = nv; }
-    if (t >= tbest) return false;
     t_out = t;
     return true;
 }
@@ -90,7 +90,7 @@ __device__ __forceinline__ int max_dimension_abs(D3 d) {                       /
     if (x > y) return x > z ? 0 : 2;
     return y > z ? 1 : 2;
 }
-__device__ __forceinline__ bool triangle_exact(D3 p0, D3 p1, D3 p2, const Ray64& ray, double tbest, double& t_out,
+__device__ __forceinline__ bool triangle_exact(D3 p0, D3 p1, D3 p2, const Ray64& ray, double& t_out,
                                                double& b0, double& b1, double& b2) {
     D3 p0t = p0 - ray.o, p1t = p1 - ray.o, p2t = p2 - ray.o;
     int kz = max_dimension_abs(ray.d);
@@ -116,7 +116,6 @@ __device__ __forceinline__ bool triangle_exact(D3 p0, D3 p1, D3 p2, const Ray64&
     double invdet = 1.0 / det;
     b0 = e0 * invdet; b1 = e1 * invdet; b2 = e2 * invdet;
     double t = tscaled * invdet;
-    if (t >= tbest) return false;
     t_out = t;
     return true;
 }

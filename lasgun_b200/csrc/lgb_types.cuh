@@ -11,19 +11,26 @@ constexpr int kStackDepth = 64;          // bvh.rs:469 — the reference's fixed
 constexpr int kMacroTile = 32;           // macro tile edge in pixels (multi-GPU interleave unit)
 constexpr int kMicroW = 8, kMicroH = 4;  // one warp of pixels at 1 spp
 constexpr uint32_t kNoNormals = 0xFFFFFFFFu;
+#ifndef LGB_LEAF_CONSTANTS
+#define LGB_LEAF_CONSTANTS
+constexpr uint32_t kLeafBit = 0x80000000u;       // child word encoding, see lgb_build.hpp
+constexpr uint32_t kLeafFirstMask = 0x00FFFFFFu;
+#endif
+constexpr uint32_t kDone = 0x7FFFFFFFu;          // traversal sentinel (never a valid node index)
 
 // All pointers are device pointers.  Layout:
-//   nodes      2 x float4 per node : {lo.xyz, a} {hi.xyz, b}; boxes padded (conservative for f32 rays)
-//   prim_refs  u32 (type<<30 | index), reference leaf order
-//   sph32      float4 {c.xyz, r} nearest-f32 copy for the filter; sph64 4 doubles exact
+//   nodes      4 x float4 per node: child0 {lo.xyz, hi.xyz}, child1 {lo.xyz, hi.xyz}, {child0, child1, -, -};
+//              boxes padded (conservative for f32 rays); child word = node index, or
+//              kLeafBit | type << 29 | (count - 1) << 24 | first  (homogeneous leaf, primitives stored in leaf order)
+//   sph32      float4 {c.xyz, r} f32 copy for the filter; sph64 4 doubles exact (same index)
 //   cub32      2 x float4 padded {lo, hi}; cub64 6 doubles exact
 //   tri        3 x float4 {p0, id} {p1, material} {p2, normals_index|kNoNormals}
 //   tri_nrm    9 floats per entry (indexed by the value stored in tri[3i+2].w)
+//   rank       8 x prim_count u32: reference traversal position per direction octant (exact-t ties only)
 //   materials  8 doubles {kd.xyz, roughness, ks.xyz, flags(bit0 diffuse lobe, bit1 glossy lobe)}
 //   lights     9 doubles {pos, intensity, falloff}
 struct DevScene {
     const float4* nodes;
-    const uint32_t* prim_refs;
     const float4* sph32;
     const double* sph64;
     const uint32_t* sph_mat;
@@ -34,9 +41,10 @@ struct DevScene {
     const uint32_t* cub_id;
     const float4* tri;
     const float* tri_nrm;
-    const uint32_t* inst_root;
+    const uint32_t* rank;
     const double* materials;
     const double* lights;
+    uint32_t prim_count;
     uint32_t n_lights;
     uint32_t n_nodes;
     float err_abs;        // absolute coordinate error bound of an f32 ray against this scene (see lgb_api.cu)
@@ -72,7 +80,7 @@ struct DevWork {
 
 struct DevCounters {
     unsigned long long primary_rays, primary_hits, shadow_traced, shadow_occluded;
-    unsigned long long node_tests;
+    unsigned long long node_tests;     // node fetches (each tests two child boxes)
     unsigned long long filter[3];    // f32 filter tests by primitive type (sphere, cuboid, triangle)
     unsigned long long exact[3];     // f64 reference-arithmetic tests by primitive type
     unsigned int stack_overflow;
