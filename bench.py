@@ -279,7 +279,7 @@ def run_gpu(args):
             "e2e": {"value": rays_frame / (e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e,
                     "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": w * h * 4,
                     "host_bvh_build_flatten_ms": host_flatten_s * 1e3},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": (4 + nl) * args.steps,
             "roofline": {"bound": "fp32_issue", "achieved": ach, "peak": fp32_peak, "unit": "Gop/s (FMA=2)", "frac": ach / fp32_peak,
                          "traffic": None, "peak_source": "lgb_measure_fp32_gops, live on this GPU",
                          "algorithmic_ops_per_frame": ops, "algorithmic_bytes_per_frame": byts,

@@ -11,7 +11,7 @@ import numpy as np
 from . import api
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "liblasgun_b200.so")
+SO_PATH = os.environ.get("LASGUN_B200_SO") or os.path.join(_HERE, "liblasgun_b200.so")   # env override: kernel experiments only
 _lib = None
 
 LGB_OK, LGB_ERR_INVALID, LGB_ERR_CUDA, LGB_ERR_UNSUPPORTED, LGB_ERR_NOMEM, LGB_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5

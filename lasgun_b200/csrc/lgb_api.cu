@@ -14,7 +14,7 @@
 #include "lgb_types.cuh"
 
 namespace lgb {
-cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, bool stats, bool all_shadows, cudaStream_t);
+cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t);
 cudaError_t launch_trace(const DevScene&, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns, cudaStream_t);
 cudaError_t launch_l2_read(const void* buf, uint64_t bytes, int iters, float* sink, int sms, cudaStream_t);
 cudaError_t launch_fp32_peak(int iters, float* sink, int sms, cudaStream_t);
@@ -44,7 +44,7 @@ struct lgb_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     std::string error;
-    DevBuf radiance, film, counters, tiles, aov_id, aov_t, aov_occl, scratch;
+    DevBuf radiance, film, counters, tiles, aov_id, aov_t, aov_occl, scratch, wave, wave_ctr;
     std::vector<uint32_t> tile_host;
     uint32_t tile_key[4] = {0, 0, 0, 0};   // w, h, rank, ranks of the cached tile list
     uint32_t tile_count = 0;
@@ -122,7 +122,7 @@ void lgb_shutdown(lgb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch}) b->release();
+    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr}) b->release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -465,12 +465,28 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         W.compact_out = 1;
     }
     const uint64_t total = W.n_pixels * W.spp;
-    if (total >= (1ull << 32) * 256) return fail(c, LGB_ERR_INVALID, "capture: too many samples for one launch");
+    if (total >= (1ull << 32) - 64) return fail(c, LGB_ERR_INVALID, "capture: more than 2^32 samples in one launch");
     if (s->cam.pixel_separation != 0.0 && W.aspect > 4.0)
         return fail(c, LGB_ERR_UNSUPPORTED, "orthographic capture with aspect > 4: the scene's coordinate bound assumed aspect <= 4");
     const DevScene& S = s->dev;
     CU(c, c->radiance.reserve(std::max<uint64_t>(total, 1) * 3 * sizeof(double)));
     CU(c, c->counters.reserve(sizeof(DevCounters)));
+    // wavefront buffers: hit_t 8 + ps 24 + hit_ref 4 + occl 4 + queue 4 * lights bytes per sample slot
+    const uint64_t nslots = std::max<uint64_t>(total, 1), nl = std::max<uint32_t>(S.n_lights, 1);
+    CU(c, c->wave.reserve(nslots * (8 + 24 + 4 + 4 + 4 * nl)));
+    CU(c, c->wave_ctr.reserve(8 + 4 * LGB_MAX_LIGHTS * 2));
+    DevWave V{};
+    {
+        char* base = (char*)c->wave.p;
+        V.hit_t = (double*)base; base += nslots * 8;
+        V.ps = (double*)base; base += nslots * 24;
+        V.hit_ref = (uint32_t*)base; base += nslots * 4;
+        V.occl = (uint32_t*)base; base += nslots * 4;
+        V.queue = (uint32_t*)base; V.queue_stride = nslots;
+        V.work_counter = (unsigned long long*)c->wave_ctr.p;
+        V.queue_count = (uint32_t*)((char*)c->wave_ctr.p + 8);
+        V.shadow_counter = V.queue_count + LGB_MAX_LIGHTS;
+    }
     DevOut O{};
     O.radiance = (double*)c->radiance.p;
     O.counters = (DevCounters*)c->counters.p;
@@ -486,7 +502,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     }
     CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));
     CU(c, cudaEventRecord(c->ev0, st));
-    CU(c, launch_render(S, s->cam, s->shade, W, O, a.aov || c->count_work, a.aov, st));
+    CU(c, launch_render(S, s->cam, s->shade, W, O, V, a.aov || c->count_work, a.aov, c->sm_count, st));
     CU(c, cudaEventRecord(c->ev1, st));
     if (stats && sync_stats) {
         DevCounters hc;
@@ -499,7 +515,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         stats->node_tests = hc.node_tests;
         for (int k = 0; k < 3; k++) { stats->filter_tests[k] = hc.filter[k]; stats->exact_tests[k] = hc.exact[k]; }
         stats->stack_overflow = hc.stack_overflow;
-        stats->kernel_launches = total ? 2 : 0;
+        stats->kernel_launches = total ? 4 + s->dev.n_lights : 0;
         float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         stats->render_ms = ms; stats->total_ms = ms;
     }

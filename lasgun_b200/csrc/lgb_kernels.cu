@@ -8,6 +8,8 @@
 // reference's operation order (integrate.rs:23-80).
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "lgb_math.cuh"
 
 namespace lgb {
@@ -54,20 +56,20 @@ __device__ __forceinline__ RayF make_rayf(const Ray64& r, float err_abs) {
     return f;
 }
 
-// Conservative slab test of an f32 ray against a padded f32 box: returns false only if
-// the exact f64 ray certainly misses the exact box or enters it beyond tbest.  tnear_out orders children.
-__device__ __forceinline__ bool slab2(float lx, float ly, float lz, float hx, float hy, float hz, const RayF& f, float tbest, float& tnear_out) {
+// Conservative slab test of an f32 ray against a padded f32 box: returns false only if the
+// exact f64 ray certainly misses the exact box or enters it beyond the best hit.  Every computed t carries a
+// relative error <= ~3 ulp, so the interval test widens tfar by (1 + 2^-20) and the caller passes
+// tbest_up = best * (1 + 2^-20); the sign of tfar is exact.  tnear (raw) orders the children.
+__device__ __forceinline__ bool slab2(float lx, float ly, float lz, float hx, float hy, float hz, const RayF& f, float tbest_up, float& tnear_out) {
     float t1x = __fmaf_rn(lx, f.ix, f.nx), t2x = __fmaf_rn(hx, f.ix, f.nx);
     float t1y = __fmaf_rn(ly, f.iy, f.ny), t2y = __fmaf_rn(hy, f.iy, f.ny);
     float t1z = __fmaf_rn(lz, f.iz, f.nz), t2z = __fmaf_rn(hz, f.iz, f.nz);
     float tnear = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
     float tfar = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
-    const float up = 1.0f + 4.76837158e-7f, dn = 1.0f - 4.76837158e-7f;   // 1 +- 2^-21
-    tfar = tfar * up;                      // tfar < 0 is rejected either way
-    tnear = tnear > 0.0f ? tnear * dn : tnear * up;
     tnear_out = tnear;
-    return tnear <= tfar && tfar > 0.0f && tnear <= tbest;
+    return tnear <= tfar * (1.0f + 9.5367431640625e-7f) && tfar > 0.0f && tnear <= tbest_up;
 }
+__device__ __forceinline__ float inflate_up(double t) { return __double2float_ru(t) * (1.0f + 9.5367431640625e-7f); }
 
 struct Hit { double t; uint32_t ref; };     // ref = type << 30 | index in the leaf-ordered arrays
 
@@ -121,32 +123,43 @@ __device__ __forceinline__ bool tri_filter(const float4 q0, const float4 q1, con
 // while-while traversal of the device BVH: the inner loop descends interior nodes (two child boxes per
 // fetch, nearer child first), the outer loop intersects one homogeneous leaf.  The `tnear > best` cull is
 // result-safe because every primitive rejects t >= isect.t itself (bvh.rs:473 never looks at isect.t).
-template <bool ANYHIT, bool STATS>
-__device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalCounters& lc, unsigned int& overflow) {
-    const RayF f = make_rayf(ray, S.err_abs);
-    Hit best; best.t = tmax; best.ref = LGB_MISS;
-    float best_tf = __double2float_ru(tmax);
-    uint32_t stack[kStackDepth];
-    int sp = 0;
-    uint32_t cur = 0;
+struct Trav {                 // resumable traversal state of one ray
+    Hit best;
+    float best_tf, best_up;
+    uint32_t cur;
+    int sp;
+    __device__ __forceinline__ void init(double tmax) {
+        best.t = tmax; best.ref = LGB_MISS; best_tf = __double2float_ru(tmax); best_up = inflate_up(tmax); cur = 0; sp = 0;
+    }
+};
+
+// Runs until the ray is finished (returns true; T.cur == kDone) or, with REFILL, until fewer than
+// `refill_below` lanes of the warp are still traversing (returns false: the caller tops the warp up with
+// new rays and calls again; persistent threads with dynamic fetch).
+template <bool ANYHIT, bool STATS, bool REFILL>
+__device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& ray, const RayF& f, Trav& T, uint32_t* stack, double tmax,
+                                         LocalCounters& lc, int refill_below) {
+    Hit& best = T.best;
+    float& best_tf = T.best_tf; float& best_up = T.best_up;
+    uint32_t& cur = T.cur; int& sp = T.sp;
     for (;;) {
         while (!(cur & kLeafBit) && cur != kDone) {
             const float4* np = S.nodes + 4 * (size_t)cur;
             const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
             if (STATS) lc.node_tests++;
             float tn0, tn1;
-            const bool h0 = slab2(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, f, best_tf, tn0);
-            const bool h1 = slab2(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, f, best_tf, tn1);
+            const bool h0 = slab2(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, f, best_up, tn0);
+            const bool h1 = slab2(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, f, best_up, tn1);
             const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
             if (h0 && h1) {
                 const bool swap = tn1 < tn0;
                 cur = swap ? c1 : c0;
-                if (sp < kStackDepth) stack[sp++] = swap ? c0 : c1; else overflow = 1;
+                stack[sp++] = swap ? c0 : c1;
             } else if (h0) cur = c0;
             else if (h1) cur = c1;
             else cur = sp ? stack[--sp] : kDone;
         }
-        if (cur == kDone) break;
+        if (cur == kDone) return true;
         {
             const uint32_t type = (cur >> 29) & 3u, count = ((cur >> 24) & 31u) + 1u, first = cur & kLeafFirstMask;
             if (type == LGB_PRIM_TRIANGLE) {
@@ -161,8 +174,8 @@ __device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalC
                     double t, b0, b1, b2;
                     if (triangle_exact(d3(q0.x, q0.y, q0.z), d3(q1.x, q1.y, q1.z), d3(q2.x, q2.y, q2.z), ray, t, b0, b1, b2)) {
                         const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_TRIANGLE, idx);
-                        if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; return best; } }
-                        else if (accepts(S, f, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); }
+                        if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; cur = kDone; return true; } }
+                        else if (accepts(S, f, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
                     }
                 }
             } else if (type == LGB_PRIM_SPHERE) {
@@ -187,8 +200,8 @@ __device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalC
                     double t; bool inside;
                     if (sphere_exact(d3(c01.x, c01.y, c23.x), c23.y, ray, t, inside)) {
                         const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_SPHERE, idx);
-                        if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; return best; } }
-                        else if (accepts(S, f, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); }
+                        if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; cur = kDone; return true; } }
+                        else if (accepts(S, f, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
                     }
                 }
             } else {
@@ -205,15 +218,24 @@ __device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalC
                     double t; int ua, va;
                     if (cuboid_exact(mn, mx, ray, t, ua, va)) {
                         const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_CUBOID, idx);
-                        if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; return best; } }
-                        else if (accepts(S, f, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); }
+                        if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; cur = kDone; return true; } }
+                        else if (accepts(S, f, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
                     }
                 }
             }
         }
         cur = sp ? stack[--sp] : kDone;
+        if (REFILL && __popc(__activemask()) < refill_below) return cur == kDone;
     }
-    return best;
+}
+
+template <bool ANYHIT, bool STATS>
+__device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalCounters& lc) {
+    const RayF f = make_rayf(ray, S.err_abs);
+    uint32_t stack[kStackDepth];      // depth is bounded at scene creation (lgb_api.cu), so pushes are unchecked
+    Trav T; T.init(tmax);
+    trav_run<ANYHIT, STATS, false>(S, ray, f, T, stack, tmax, lc, 0);
+    return T.best;
 }
 
 // ------------------------------------------------------------------ surface record of the winner
@@ -346,64 +368,26 @@ __device__ D3 bsdf_f(const Bsdf& B, D3 wo, D3 wi) {
 
 __device__ __forceinline__ double lerp64(double t, double a, double b) { return a * (1.0 - t) + b * t; }
 
-struct SampleOut { D3 color; uint32_t id; double t; uint32_t occl; uint32_t hit; uint32_t shadow_traced; uint32_t shadow_occl; };
+// Everything the lighting loop needs about the closest hit (SurfaceInteraction::from, surface.rs:158-183,
+// + Material::scattering, plastic.rs:20-37 / matte.rs:18-26).
+struct ShadePoint { D3 wo, ng, ns, ps; Bsdf B; };
 
-// integrate.rs:23-80 for one ray.
-template <bool STATS, bool ALL_SHADOWS>
-__device__ void li(const DevScene& S, const DevShade& sh, const Ray64& ray, SampleOut& out, LocalCounters& lc, unsigned int& overflow) {
-    const double PI = 3.14159265358979323846264338327950288;
-    out.id = LGB_MISS; out.t = CUDART_INF; out.occl = 0; out.hit = 0; out.shadow_traced = 0; out.shadow_occl = 0;
-    Hit h = traverse<false, STATS>(S, ray, CUDART_INF, lc, overflow);
-    if (h.ref == LGB_MISS) {                                   // background.rs:25-34
-        D3 dn = normalize(ray.d);
-        double dz = fabs(0.0 * dn.x + 0.0 * dn.y + 1.0 * dn.z);
-        double t = fmin(sqrt(1.0 - dz * dz) / sh.bg_scale, 1.0);
-        out.color = d3(lerp64(t, sh.bg_inner[0], sh.bg_outer[0]), lerp64(t, sh.bg_inner[1], sh.bg_outer[1]),
-                       lerp64(t, sh.bg_inner[2], sh.bg_outer[2]));
-        return;
-    }
-    Surf sf; double t_again = h.t;
-    surface_of(S, ray, h.ref, t_again, sf);
-    out.id = sf.id; out.t = h.t; out.hit = 1;
-    // SurfaceInteraction::from, surface.rs:158-183
-    D3 wo = -normalize(ray.d);
-    D3 ng = face_forward(normalize(cross(sf.g_dpdu, sf.g_dpdv)), wo);
-    D3 ns = sf.has_n ? normalize(sf.n) : normalize(cross(sf.s_dpdu, sf.s_dpdv));
-    const double err = 2.220446049250313e-16 * 65536.0;
-    D3 p = ray.o + ray.d * h.t;
-    D3 p_err = ng * err;
-    D3 ps = p + p_err;
-    Bsdf B;
-    B.ng = ng; B.ns = ns; B.ss = normalize(sf.s_dpdu); B.ts = cross(ns, B.ss);
+__device__ __forceinline__ void shade_point(const DevScene& S, const Ray64& ray, double t, uint32_t ref, ShadePoint& P, uint32_t& id) {
+    Surf sf; double t_again = t;
+    surface_of(S, ray, ref, t_again, sf);
+    id = sf.id;
+    P.wo = -normalize(ray.d);
+    P.ng = face_forward(normalize(cross(sf.g_dpdu, sf.g_dpdv)), P.wo);
+    P.ns = sf.has_n ? normalize(sf.n) : normalize(cross(sf.s_dpdu, sf.s_dpdv));
+    const double err = 2.220446049250313e-16 * 65536.0;        // EPSILON * 2^16, surface.rs:168
+    D3 p = ray.o + ray.d * t;
+    D3 p_err = P.ng * err;
+    P.ps = p + p_err;                                          // integrate.rs:40
+    P.B.ng = P.ng; P.B.ns = P.ns; P.B.ss = normalize(sf.s_dpdu); P.B.ts = cross(P.ns, P.B.ss);
     const double* M = S.materials + 8 * (size_t)sf.material;
-    B.kd = d3(M[0], M[1], M[2]); B.alpha = M[3]; B.ks = d3(M[4], M[5], M[6]);
+    P.B.kd = d3(M[0], M[1], M[2]); P.B.alpha = M[3]; P.B.ks = d3(M[4], M[5], M[6]);
     const uint32_t flags = (uint32_t)__double_as_longlong(M[7]);
-    B.diffuse = flags & 1u; B.glossy = flags & 2u;
-    D3 output = d3(0, 0, 0);
-    for (uint32_t l = 0; l < S.n_lights; l++) {
-        const double* L = S.lights + 9 * (size_t)l;
-        D3 lp = d3(L[0], L[1], L[2]);
-        Ray64 sray; sray.o = ps; sray.d = lp - ps;                 // light/point.rs:43-44
-        D3 wi = lp - ps;
-        double dist = sqrt(dot(wi, wi));
-        wi = normalize(wi);
-        // bsdf.f is zero unless wi and wo are on the same side of ng (bsdf.rs:75,85-86): the light
-        // then adds exactly zero whether or not it is occluded, so the shadow ray is not traced
-        // (DESIGN.md §4.4).  ALL_SHADOWS (AOV / parity mode) traces every one, as the reference does.
-        const bool reflect = dot(wi, ng) * dot(wo, ng) > 0.0;
-        if (!reflect && !ALL_SHADOWS) continue;
-        out.shadow_traced++;
-        Hit sh_hit = traverse<true, STATS>(S, sray, 1.0, lc, overflow);
-        if (sh_hit.ref != LGB_MISS) { out.occl |= (1u << l); out.shadow_occl++; continue; }
-        double f_att = L[6] + L[7] * dist + L[8] * dist * dist;
-        if (f_att == 0.0) continue;
-        double wi_dot_n = dot(wi, ns);
-        D3 f = bsdf_f(B, wo, wi);
-        output = output + (mul_el(PI * d3(L[3], L[4], L[5]), f) * wi_dot_n / f_att);
-    }
-    output = output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), bsdf_f(B, wo, ns));
-    D3 zero = d3(0, 0, 0);
-    out.color = output + zero + zero;       // integrate.rs:79 (reflected + refracted are zero for plastic)
+    P.B.diffuse = flags & 1u; P.B.glossy = flags & 2u;
 }
 
 // ------------------------------------------------------------------ work mapping
@@ -450,45 +434,237 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     return v;
 }
 
-template <bool STATS, bool ALL_SHADOWS>
-__global__ void __launch_bounds__(256) k_render(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O) {
-    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#ifndef LGB_MIN_BLOCKS
+#define LGB_MIN_BLOCKS 3
+#endif
+
+// ================================================================== wavefront pipeline
+// k_primary  persistent warps pull 32 consecutive sample slots: camera ray -> closest hit -> (t, ref)
+// k_setup    per slot: miss -> background radiance; hit -> shadow origin ps and, per light, whether the
+//            light can contribute at all (bsdf.rs:75: wi and wo on the same side of ng); those rays are
+//            appended to that light's queue with one warp-aggregated atomic
+// k_shadow   per light, persistent warps over the compacted queue: any-hit traversal to t < 1
+// k_shade    per slot: BSDF evaluation for the unoccluded lights + ambient -> radiance (integrate.rs:47-67)
+// k_resolve  per pixel: in-order sample sum, weight, quantise, uchar4 store (integrate.rs:16-20, img.rs:56-67)
+
+__device__ __forceinline__ bool slot_ray(const DevCamera& C, const DevWork& W, uint64_t g, Ray64& ray, uint32_t& x, uint32_t& y, uint32_t& s) {
+    const uint64_t p = g / W.spp;
+    s = (uint32_t)(g % W.spp);
+    if (!slot_to_pixel(W, p, x, y)) return false;
+    ray = camera_ray(C, W, x, y, s);
+    return true;
+}
+
+#ifndef LGB_REFILL_BELOW
+#define LGB_REFILL_BELOW 0       // >0: top a warp up with new rays once fewer lanes than this are still traversing (measured: slower)
+#endif
+
+// Warp-level work fetch for the persistent kernels: every lane whose `need` is set receives the index of a
+// fresh work item (or >= total when the queue is drained) with one atomic per warp.
+template <class CounterT>
+__device__ __forceinline__ unsigned long long warp_fetch(CounterT* counter, bool need, unsigned lane) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, need);
+    if (!m) return ~0ull;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = (unsigned long long)atomicAdd(counter, (CounterT)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return need ? base + __popc(m & ((1u << lane) - 1u)) : ~0ull;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
     const uint64_t total = W.n_pixels * W.spp;
+    const unsigned lane = threadIdx.x & 31u;
     LocalCounters lc = {};
-    unsigned int overflow = 0;
-    SampleOut out; out.hit = 0; out.shadow_traced = 0; out.shadow_occl = 0;
-    unsigned int primary = 0;
-    if (g < total) {
-        const uint64_t p = g / W.spp;
-        const uint32_t s = (uint32_t)(g % W.spp);
-        uint32_t x, y;
-        if (slot_to_pixel(W, p, x, y)) {
-            Ray64 ray = camera_ray(C, W, x, y, s);
-            li<STATS, ALL_SHADOWS>(S, sh, ray, out, lc, overflow);
-            primary = 1;
-            O.radiance[3 * g + 0] = out.color.x; O.radiance[3 * g + 1] = out.color.y; O.radiance[3 * g + 2] = out.color.z;
-            const uint64_t gi = ((uint64_t)y * W.w + x) * W.spp + s;
-            if (O.aov_id) O.aov_id[gi] = out.id;
-            if (O.aov_t) O.aov_t[gi] = out.t;
-            if (O.aov_occl) O.aov_occl[gi] = out.occl;
+    unsigned int hits = 0, primary = 0;
+    uint32_t stack[kStackDepth];
+    Ray64 ray; RayF f; Trav T;
+    uint64_t g = 0;
+    bool active = false, drained = false;
+    for (;;) {
+        // refill: lanes without a ray take the next sample slots
+        if (!drained) {
+            const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+            if (idle == 0xFFFFFFFFu || __popc(idle) > 32 - LGB_REFILL_BELOW) {
+                bool need = !active;
+                while (__any_sync(0xFFFFFFFFu, need) && !drained) {
+                    const unsigned long long idx = warp_fetch(V.work_counter, need, lane);
+                    if (need) {
+                        if (idx >= total) { need = false; }
+                        else {
+                            uint32_t x, y, s;
+                            if (slot_ray(C, W, idx, ray, x, y, s)) {
+                                g = idx; f = make_rayf(ray, S.err_abs); T.init(CUDART_INF); active = true; need = false; primary++;
+                            } else {
+                                V.hit_t[idx] = CUDART_INF; V.hit_ref[idx] = kSlotUnused;       // pixel outside the film: take another
+                            }
+                        }
+                    }
+                    drained = __any_sync(0xFFFFFFFFu, idx != ~0ull && idx >= total);
+                }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        if (active) {
+            const bool done = trav_run<false, STATS, true>(S, ray, f, T, stack, CUDART_INF, lc, drained ? 0 : LGB_REFILL_BELOW);
+            if (done) {
+                const bool hit = T.best.ref != LGB_MISS;
+                V.hit_t[g] = hit ? T.best.t : CUDART_INF; V.hit_ref[g] = T.best.ref;
+                hits += hit ? 1u : 0u;
+                active = false;
+            }
         }
     }
     if (O.counters) {
-        unsigned long long v0 = warp_sum(primary), v1 = warp_sum(out.hit), v2 = warp_sum(out.shadow_traced), v3 = warp_sum(out.shadow_occl);
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1);
-            atomicAdd(&O.counters->shadow_traced, v2); atomicAdd(&O.counters->shadow_occluded, v3);
-        }
+        unsigned long long v0 = warp_sum(primary), v1 = warp_sum(hits);
+        if (lane == 0) { atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1); }
         if (STATS) {
             unsigned long long n = warp_sum(lc.node_tests);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&O.counters->node_tests, n);
+            if (lane == 0) atomicAdd(&O.counters->node_tests, n);
             for (int k = 0; k < 3; k++) {
                 unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
-                if ((threadIdx.x & 31) == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); }
+                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); }
             }
         }
-        if (overflow) atomicOr(&O.counters->stack_overflow, 1u);
     }
+}
+
+template <bool ALL_SHADOWS>
+__global__ void __launch_bounds__(256) k_setup(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
+    const uint64_t total = W.n_pixels * W.spp;
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t need = 0;
+    bool live = false;
+    if (g < total) {
+        const uint32_t ref = V.hit_ref[g];
+        Ray64 ray; uint32_t x, y, s;
+        if (ref != kSlotUnused && slot_ray(C, W, g, ray, x, y, s)) {
+            const uint64_t gi = ((uint64_t)y * W.w + x) * W.spp + s;
+            if (ref == LGB_MISS) {                                   // background.rs:25-34
+                D3 dn = normalize(ray.d);
+                double dz = fabs(0.0 * dn.x + 0.0 * dn.y + 1.0 * dn.z);
+                double t = fmin(sqrt(1.0 - dz * dz) / sh.bg_scale, 1.0);
+                O.radiance[3 * g + 0] = lerp64(t, sh.bg_inner[0], sh.bg_outer[0]);
+                O.radiance[3 * g + 1] = lerp64(t, sh.bg_inner[1], sh.bg_outer[1]);
+                O.radiance[3 * g + 2] = lerp64(t, sh.bg_inner[2], sh.bg_outer[2]);
+                if (O.aov_id) O.aov_id[gi] = LGB_MISS;
+                if (O.aov_t) O.aov_t[gi] = CUDART_INF;
+                if (O.aov_occl) O.aov_occl[gi] = 0;
+            } else {
+                live = true;
+                const double t = V.hit_t[g];
+                ShadePoint P; uint32_t id;
+                shade_point(S, ray, t, ref, P, id);
+                V.ps[3 * g + 0] = P.ps.x; V.ps[3 * g + 1] = P.ps.y; V.ps[3 * g + 2] = P.ps.z;
+                if (O.aov_id) O.aov_id[gi] = id;
+                if (O.aov_t) O.aov_t[gi] = t;
+                const double wo_ng = dot(P.wo, P.ng);
+                for (uint32_t l = 0; l < S.n_lights; l++) {
+                    const double* L = S.lights + 9 * (size_t)l;
+                    D3 wi = normalize(d3(L[0], L[1], L[2]) - P.ps);
+                    // bsdf.f is zero unless wi and wo are on the same side of ng (bsdf.rs:75,85-86): the light then
+                    // adds exactly zero whether or not it is occluded, so no shadow ray is traced.
+                    if (ALL_SHADOWS || dot(wi, P.ng) * wo_ng > 0.0) need |= 1u << l;
+                }
+                V.occl[g] = 0;
+            }
+        }
+    }
+    // compacted per-light shadow queues: one atomic per warp per light
+    for (uint32_t l = 0; l < S.n_lights; l++) {
+        const bool want = live && ((need >> l) & 1u);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
+        if (!m) continue;
+        unsigned base = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&V.queue_count[l], (unsigned)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+        if (want) V.queue[(size_t)l * V.queue_stride + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)g;
+    }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevOut O, DevWave V, uint32_t light) {
+    const unsigned total = V.queue_count[light];
+    const uint32_t* q = V.queue + (size_t)light * V.queue_stride;
+    const double* L = S.lights + 9 * (size_t)light;
+    const D3 lp = d3(L[0], L[1], L[2]);
+    const unsigned lane = threadIdx.x & 31u;
+    LocalCounters lc = {};
+    unsigned int occluded = 0;
+    uint32_t stack[kStackDepth];
+    Ray64 ray; RayF f; Trav T;
+    uint32_t g = 0;
+    bool active = false, drained = false;
+    for (;;) {
+        if (!drained) {
+            const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+            if (idle == 0xFFFFFFFFu || __popc(idle) > 32 - LGB_REFILL_BELOW) {
+                const unsigned long long idx = warp_fetch(V.shadow_counter + light, !active, lane);
+                if (!active && idx < total) {
+                    g = q[idx];
+                    ray.o = d3(V.ps[3 * (size_t)g], V.ps[3 * (size_t)g + 1], V.ps[3 * (size_t)g + 2]);
+                    ray.d = lp - ray.o;                                          // light/point.rs:43-44
+                    f = make_rayf(ray, S.err_abs); T.init(1.0); active = true;
+                }
+                drained = __any_sync(0xFFFFFFFFu, idx != ~0ull && idx >= total);
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        if (active) {
+            const bool done = trav_run<true, STATS, true>(S, ray, f, T, stack, 1.0, lc, drained ? 0 : LGB_REFILL_BELOW);
+            if (done) {
+                if (T.best.ref != LGB_MISS) { atomicOr(&V.occl[g], 1u << light); occluded++; }
+                active = false;
+            }
+        }
+    }
+    if (O.counters) {
+        unsigned long long v = warp_sum(occluded);
+        if (lane == 0) atomicAdd(&O.counters->shadow_occluded, v);
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&O.counters->shadow_traced, (unsigned long long)total);
+        if (STATS) {
+            unsigned long long n = warp_sum(lc.node_tests);
+            if (lane == 0) atomicAdd(&O.counters->node_tests, n);
+            for (int k = 0; k < 3; k++) {
+                unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
+                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_shade(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
+    const double PI = 3.14159265358979323846264338327950288;
+    const uint64_t total = W.n_pixels * W.spp;
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const uint32_t ref = V.hit_ref[g];
+    if (ref == LGB_MISS || ref == kSlotUnused) return;
+    Ray64 ray; uint32_t x, y, s;
+    if (!slot_ray(C, W, g, ray, x, y, s)) return;
+    ShadePoint P; uint32_t id;
+    shade_point(S, ray, V.hit_t[g], ref, P, id);
+    const uint32_t occl = V.occl[g];
+    if (O.aov_occl) O.aov_occl[((uint64_t)y * W.w + x) * W.spp + s] = occl;
+    D3 output = d3(0, 0, 0);
+    for (uint32_t l = 0; l < S.n_lights; l++) {                        // integrate.rs:47-66
+        if ((occl >> l) & 1u) continue;
+        const double* L = S.lights + 9 * (size_t)l;
+        D3 wi = d3(L[0], L[1], L[2]) - P.ps;
+        double dist = sqrt(dot(wi, wi));
+        double f_att = L[6] + L[7] * dist + L[8] * dist * dist;
+        if (f_att == 0.0) continue;
+        wi = normalize(wi);
+        double wi_dot_n = dot(wi, P.ns);
+        D3 f = bsdf_f(P.B, P.wo, wi);                                  // zero when the shadow ray was skipped
+        output = output + (mul_el(PI * d3(L[3], L[4], L[5]), f) * wi_dot_n / f_att);
+    }
+    output = output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), bsdf_f(P.B, P.wo, P.ns));   // integrate.rs:67
+    D3 zero = d3(0, 0, 0);
+    output = output + zero + zero;          // integrate.rs:79 (reflected + refracted are zero for plastic)
+    O.radiance[3 * g + 0] = output.x; O.radiance[3 * g + 1] = output.y; O.radiance[3 * g + 2] = output.z;
 }
 
 // integrate.rs:16-20 + img.rs:56-67: in-order sum of the samples, weight, quantise, store.
@@ -516,8 +692,7 @@ __global__ void __launch_bounds__(128) k_trace(DevScene S, const double* rays, u
     if (i >= n) return;
     Ray64 ray; ray.o = d3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]); ray.d = d3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
     LocalCounters lc = {};
-    unsigned int overflow = 0;
-    Hit h = traverse<false, false>(S, ray, CUDART_INF, lc, overflow);
+    Hit h = traverse<false, false>(S, ray, CUDART_INF, lc);
     uint32_t id = LGB_MISS; D3 ng = d3(0, 0, 0), ns = d3(0, 0, 0);
     if (h.ref != LGB_MISS) {
         Surf sf; double t = h.t;
@@ -566,16 +741,23 @@ __global__ void k_fp64_peak(int iters, double* sink) {
 
 // ------------------------------------------------------------------ launch wrappers (called from lgb_api.cu)
 cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O,
-                          bool stats, bool all_shadows, cudaStream_t stream) {
+                          const DevWave& V, bool stats, bool all_shadows, int sms, cudaStream_t stream) {
     const uint64_t total = W.n_pixels * W.spp;
     if (total == 0) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(V.work_counter, 0, 8 + 4 * (size_t)LGB_MAX_LIGHTS * 2, stream)) != cudaSuccess) return e;
+    const unsigned pblocks = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)sms * LGB_MIN_BLOCKS);
+    if (stats) k_primary<true><<<pblocks, 256, 0, stream>>>(S, C, W, O, V);
+    else k_primary<false><<<pblocks, 256, 0, stream>>>(S, C, W, O, V);
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (stats && all_shadows) k_render<true, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O);
-    else if (stats) k_render<true, false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O);
-    else if (all_shadows) k_render<false, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O);
-    else k_render<false, false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (all_shadows) k_setup<true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+    else k_setup<false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+    for (uint32_t l = 0; l < S.n_lights; l++) {
+        if (stats) k_shadow<true><<<pblocks, 256, 0, stream>>>(S, O, V, l);
+        else k_shadow<false><<<pblocks, 256, 0, stream>>>(S, O, V, l);
+    }
+    k_shade<<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
     return cudaGetLastError();
 }

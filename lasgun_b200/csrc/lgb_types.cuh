@@ -87,6 +87,20 @@ struct DevCounters {
     unsigned int pad;
 };
 
+// Wavefront buffers, one entry per sample slot g = pixel_slot * spp + s.
+struct DevWave {
+    double* hit_t;                   // closest-hit parameter (f64, reference arithmetic)
+    uint32_t* hit_ref;               // type << 30 | index, LGB_MISS, or kSlotUnused (pixel outside the film)
+    double* ps;                      // shadow-ray origin p + p_err (3 per slot)
+    uint32_t* occl;                  // bit l set: light l occluded
+    uint32_t* queue;                 // n_lights x queue_stride slot indices
+    uint64_t queue_stride;
+    unsigned long long* work_counter;   // [0] primary; followed by u32 queue_count[LGB_MAX_LIGHTS], shadow_counter[LGB_MAX_LIGHTS]
+    uint32_t* queue_count;
+    uint32_t* shadow_counter;
+};
+constexpr uint32_t kSlotUnused = 0xFFFFFFFEu;
+
 struct DevOut {
     double* radiance;                // 3 doubles per sample slot (slot = pixel_slot * spp + s)
     uint32_t* aov_id;                // optional, global sample index
