@@ -162,6 +162,7 @@ def run_gpu(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = N.Context(local)
@@ -177,12 +178,10 @@ def run_gpu(args):
     stream = tstream.cuda_stream
     assert stream != 0
 
+    from lasgun_b200 import multi
+
     def step():
-        if world > 1:
-            film.zero_()
-        dev.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream)
-        if world > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)    # disjoint tiles: SUM == gather, over NVLink
+        multi.capture_distributed(dev, w, h, film, rank, world, stream)   # disjoint tiles: SUM reduce == gather, over NVLink
 
     # one counted frame: ray counts + work counters (not timed)
     ctx.set_count_work(True)
