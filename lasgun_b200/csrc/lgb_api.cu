@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -60,6 +61,7 @@ struct lgb_scene {
     DevShade shade{};
     double max_abs = 0.0;      // max |coordinate| over geometry, camera origin and lights
     double build_ms = 0.0;     // host time of the device-BVH build inside lgb_scene_create
+    double t_validate = 0, t_rank = 0, t_build = 0, t_convert_upload = 0, t_total = 0;   // ms, lgb_scene_create phases
 };
 
 static int fail(lgb_ctx* ctx, int code, const std::string& msg) {
@@ -246,6 +248,8 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     if (d->camera.supersampling_root == 0 || d->camera.supersampling_root > 256) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: supersampling_root out of range");
     CU(ctx, cudaSetDevice(ctx->device));
 
+    auto tc0 = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     // ---- validate materials (only the plastic / Lambertian lobes are on the device path)
     std::vector<double> mats(8 * d->n_materials);
     for (uint64_t i = 0; i < d->n_materials; i++) {
@@ -322,10 +326,14 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     if (prim_count == 0) return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: no primitives"));
     const int threads = (int)std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency()));
     std::vector<uint32_t> rank;
+    s->t_validate = ms_since(tc0);
+    auto tc1 = std::chrono::steady_clock::now();
     if (!build_rank_tables(d, prim_count, threads, rank))
         return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: primitive ids must be a permutation of 0..n-1 and every primitive must be referenced by exactly one leaf"));
     const double padd = M * std::ldexp(1.0, -20);
     s->dev.err_abs = (float)padd;
+    s->t_rank = ms_since(tc1);
+    auto tc2 = std::chrono::steady_clock::now();
     BuiltBVH bvh;
     {
         std::vector<PrimBox> prims; make_prim_boxes(d, prims);
@@ -335,6 +343,8 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         if (bvh.max_depth + 1 > (uint32_t)kStackDepth) return bail(fail(ctx, LGB_ERR_UNSUPPORTED, "device BVH deeper than the 64-entry traversal stack"));
     }
     s->build_ms = bvh.build_ms;
+    s->t_build = ms_since(tc2);
+    auto tc3 = std::chrono::steady_clock::now();
     {
         static_assert(sizeof(HostNode) == 64, "node layout");
         std::vector<float4> nodes(4 * bvh.nodes.size());
@@ -409,6 +419,10 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     s->shade.bg_scale = d->bg_scale;
     cudaError_t e = cudaStreamSynchronize(ctx->stream);     // host vectors die at scope end
     if (e != cudaSuccess) { cuda_fail(ctx, e, "scene upload"); return bail(LGB_ERR_CUDA); }
+    s->t_convert_upload = ms_since(tc3);
+    s->t_total = ms_since(tc0);
+    if (getenv("LGB_TIMING")) fprintf(stderr, "[lgb_scene_create] validate %.1f rank %.1f build %.1f (sah %.1f) convert+upload %.1f total %.1f ms, %u threads\n",
+                                      s->t_validate, s->t_rank, s->t_build, s->build_ms, s->t_convert_upload, s->t_total, (unsigned)threads);
     *out = s;
     return LGB_OK;
 }
