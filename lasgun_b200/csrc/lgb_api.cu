@@ -200,7 +200,7 @@ int lgb_build_probe(const lgb_scene_desc* d, lgb_build_info* out) {
         const HostNode& n = bvh.nodes[e.node];
         for (int c = 0; c < 2; c++) {
             const float* lo = n.v + 6 * c; const float* hi = n.v + 6 * c + 3; const uint32_t w = c ? n.c1 : n.c0;
-            if (lo[0] != lo[0]) continue;     // empty child
+            if (c == 1 && n.c1 == n.c0) continue;     // tiny scene: both children are the same leaf
             for (int k = 0; k < 3; k++) if (lo[k] < e.lo[k] || hi[k] > e.hi[k]) ok = false;
             if (e.node == 0) root_area += area(lo, hi);
             if (w & kLeafBit) {

@@ -180,12 +180,11 @@ int build_sah(std::vector<PrimBox>& prims, float pad, int threads, BuiltBVH& out
     Box3 box;
     bool homogeneous = true;
     for (size_t i = 1; i < n && homogeneous; i++) homogeneous = items[i].type == items[0].type;
-    if (n <= (size_t)kMaxLeaf && homogeneous) {      // tiny scene: root with one leaf child and one empty child
+    if (n <= (size_t)kMaxLeaf && homogeneous) {      // tiny scene: the root's two children are the same leaf (testing it twice changes nothing)
         B.node_count.store(1);
         uint32_t w = B.build(0, n, box, 1);
         HostNode& nd = out.nodes[0];
-        const float nanv = std::numeric_limits<float>::quiet_NaN();
-        for (int k = 0; k < 3; k++) { nd.v[k] = box.lo[k]; nd.v[3 + k] = box.hi[k]; nd.v[6 + k] = nanv; nd.v[9 + k] = nanv; }
+        for (int k = 0; k < 3; k++) { nd.v[k] = box.lo[k]; nd.v[3 + k] = box.hi[k]; nd.v[6 + k] = box.lo[k]; nd.v[9 + k] = box.hi[k]; }
         nd.c0 = w; nd.c1 = w; nd.pad0 = nd.pad1 = 0;
     } else {
         uint32_t w = B.build(0, n, box, 0);

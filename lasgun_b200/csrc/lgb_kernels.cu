@@ -69,6 +69,20 @@ __device__ __forceinline__ bool slab2(float lx, float ly, float lz, float hx, fl
     tnear_out = tnear;
     return tnear <= tfar * (1.0f + 9.5367431640625e-7f) && tfar > 0.0f && tnear <= tbest_up;
 }
+// Same test specialised on the ray's direction octant (bit a of OCT set <=> d[a] < 0): the near / far plane of
+// every axis is known at compile time, so the six min/max that order t1, t2 disappear, and the `tfar > 0` and
+// best-hit tests fold into one compare: max(tnear, 0) <= min(tfar (1 + 2^-20), tbest_up).  It accepts
+// whatever slab2 accepts (plus tfar == 0, which is merely conservative).
+template <int OCT>
+__device__ __forceinline__ bool slab_oct(float lx, float ly, float lz, float hx, float hy, float hz, const RayF& f, float tbest_up, float& tnear_out) {
+    const float tnx = __fmaf_rn((OCT & 1) ? hx : lx, f.ix, f.nx), tfx = __fmaf_rn((OCT & 1) ? lx : hx, f.ix, f.nx);
+    const float tny = __fmaf_rn((OCT & 2) ? hy : ly, f.iy, f.ny), tfy = __fmaf_rn((OCT & 2) ? ly : hy, f.iy, f.ny);
+    const float tnz = __fmaf_rn((OCT & 4) ? hz : lz, f.iz, f.nz), tfz = __fmaf_rn((OCT & 4) ? lz : hz, f.iz, f.nz);
+    const float tnear = fmaxf(fmaxf(tnx, tny), tnz);
+    const float tfar = fminf(fminf(tfx, tfy), tfz) * (1.0f + 9.5367431640625e-7f);
+    tnear_out = tnear;
+    return fmaxf(tnear, 0.0f) <= fminf(tfar, tbest_up);
+}
 __device__ __forceinline__ float inflate_up(double t) { return __double2float_ru(t) * (1.0f + 9.5367431640625e-7f); }
 
 struct Hit { double t; uint32_t ref; };     // ref = type << 30 | index in the leaf-ordered arrays
@@ -133,31 +147,55 @@ struct Trav {                 // resumable traversal state of one ray
     }
 };
 
+// Inner loop of the while-while traversal: descend interior nodes until `cur` is a leaf or kDone.
+// OCT < 8: every ray of the warp has that direction octant (slab_oct); OCT == 8: mixed warp (slab2).
+template <int OCT, bool STATS>
+__device__ __forceinline__ void node_loop(const DevScene& S, const RayF& f, float best_up, uint32_t& cur, int& sp, uint32_t* stack, LocalCounters& lc) {
+    while (!(cur & kLeafBit) && cur != kDone) {
+        const float4* np = S.nodes + 4 * (size_t)cur;
+        const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+        const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+        if (STATS) lc.node_tests++;
+        float tn0, tn1;
+        bool h0, h1;
+        if (OCT < 8) {
+            h0 = slab_oct<OCT & 7>(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, f, best_up, tn0);
+            h1 = slab_oct<OCT & 7>(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, f, best_up, tn1);
+        } else {
+            h0 = slab2(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, f, best_up, tn0);
+            h1 = slab2(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, f, best_up, tn1);
+        }
+        const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+        if (h0 && h1) {
+            const bool swap = tn1 < tn0;
+            cur = swap ? c1 : c0;
+            stack[sp++] = swap ? c0 : c1;
+        } else if (h0) cur = c0;
+        else if (h1) cur = c1;
+        else cur = sp ? stack[--sp] : kDone;
+    }
+}
+
 // Runs until the ray is finished (returns true; T.cur == kDone) or, with REFILL, until fewer than
 // `refill_below` lanes of the warp are still traversing (returns false: the caller tops the warp up with
 // new rays and calls again; persistent threads with dynamic fetch).
 template <bool ANYHIT, bool STATS, bool REFILL>
 __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& ray, const RayF& f, Trav& T, uint32_t* stack, double tmax,
-                                         LocalCounters& lc, int refill_below) {
+                                         LocalCounters& lc, int refill_below, unsigned octw) {
     Hit& best = T.best;
     float& best_tf = T.best_tf; float& best_up = T.best_up;
     uint32_t& cur = T.cur; int& sp = T.sp;
     for (;;) {
-        while (!(cur & kLeafBit) && cur != kDone) {
-            const float4* np = S.nodes + 4 * (size_t)cur;
-            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-            if (STATS) lc.node_tests++;
-            float tn0, tn1;
-            const bool h0 = slab2(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, f, best_up, tn0);
-            const bool h1 = slab2(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, f, best_up, tn1);
-            const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
-            if (h0 && h1) {
-                const bool swap = tn1 < tn0;
-                cur = swap ? c1 : c0;
-                stack[sp++] = swap ? c0 : c1;
-            } else if (h0) cur = c0;
-            else if (h1) cur = c1;
-            else cur = sp ? stack[--sp] : kDone;
+        switch (octw) {        // warp-uniform: the octant shared by every ray of the warp, or 8 (mixed)
+        case 0: node_loop<0, STATS>(S, f, best_up, cur, sp, stack, lc); break;
+        case 1: node_loop<1, STATS>(S, f, best_up, cur, sp, stack, lc); break;
+        case 2: node_loop<2, STATS>(S, f, best_up, cur, sp, stack, lc); break;
+        case 3: node_loop<3, STATS>(S, f, best_up, cur, sp, stack, lc); break;
+        case 4: node_loop<4, STATS>(S, f, best_up, cur, sp, stack, lc); break;
+        case 5: node_loop<5, STATS>(S, f, best_up, cur, sp, stack, lc); break;
+        case 6: node_loop<6, STATS>(S, f, best_up, cur, sp, stack, lc); break;
+        case 7: node_loop<7, STATS>(S, f, best_up, cur, sp, stack, lc); break;
+        default: node_loop<8, STATS>(S, f, best_up, cur, sp, stack, lc); break;
         }
         if (cur == kDone) return true;
         {
@@ -234,7 +272,7 @@ __device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalC
     const RayF f = make_rayf(ray, S.err_abs);
     uint32_t stack[kStackDepth];      // depth is bounded at scene creation (lgb_api.cu), so pushes are unchecked
     Trav T; T.init(tmax);
-    trav_run<ANYHIT, STATS, false>(S, ray, f, T, stack, tmax, lc, 0);
+    trav_run<ANYHIT, STATS, false>(S, ray, f, T, stack, tmax, lc, 0, 8u);
     return T.best;
 }
 
@@ -505,9 +543,12 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, Dev
                 }
             }
         }
-        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        const unsigned amask = __ballot_sync(0xFFFFFFFFu, active);
+        if (!amask) break;
+        const unsigned oct0 = __shfl_sync(0xFFFFFFFFu, f.oct, __ffs(amask) - 1);
+        const unsigned octw = __all_sync(0xFFFFFFFFu, !active || f.oct == oct0) ? oct0 : 8u;
         if (active) {
-            const bool done = trav_run<false, STATS, true>(S, ray, f, T, stack, CUDART_INF, lc, drained ? 0 : LGB_REFILL_BELOW);
+            const bool done = trav_run<false, STATS, true>(S, ray, f, T, stack, CUDART_INF, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
             if (done) {
                 const bool hit = T.best.ref != LGB_MISS;
                 V.hit_t[g] = hit ? T.best.t : CUDART_INF; V.hit_ref[g] = T.best.ref;
@@ -611,9 +652,12 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevO
                 drained = __any_sync(0xFFFFFFFFu, idx != ~0ull && idx >= total);
             }
         }
-        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        const unsigned amask = __ballot_sync(0xFFFFFFFFu, active);
+        if (!amask) break;
+        const unsigned oct0 = __shfl_sync(0xFFFFFFFFu, f.oct, __ffs(amask) - 1);
+        const unsigned octw = __all_sync(0xFFFFFFFFu, !active || f.oct == oct0) ? oct0 : 8u;
         if (active) {
-            const bool done = trav_run<true, STATS, true>(S, ray, f, T, stack, 1.0, lc, drained ? 0 : LGB_REFILL_BELOW);
+            const bool done = trav_run<true, STATS, true>(S, ray, f, T, stack, 1.0, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
             if (done) {
                 if (T.best.ref != LGB_MISS) { atomicOr(&V.occl[g], 1u << light); occluded++; }
                 active = false;
