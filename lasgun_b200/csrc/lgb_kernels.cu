@@ -346,60 +346,68 @@ __device__ void surface_of(const DevScene& S, const Ray64& ray, uint32_t ref, do
 }
 
 // ------------------------------------------------------------------ BSDF (bsdf.rs:73-92, bxdf/*)
-__device__ __forceinline__ double cos2_theta(D3 w) { return w.z * w.z; }
-__device__ __forceinline__ double sin2_theta(D3 w) { return fmax(1.0 - cos2_theta(w), 0.0); }
-__device__ __forceinline__ double sin_theta(D3 w) { return sqrt(sin2_theta(w)); }
-__device__ __forceinline__ double cos_phi(D3 w) { double s = sin_theta(w); return s == 0.0 ? 1.0 : fmin(fmax(w.x / s, -1.0), 1.0); }
-__device__ __forceinline__ double sin_phi(D3 w) { double s = sin_theta(w); return s == 0.0 ? 0.0 : fmin(fmax(w.y / s, -1.0), 1.0); }
-
-__device__ double dielectric(double cos_i, double eta_i, double eta_t) {     // fresnel.rs:37-64
+// f64 throughout.  The reference evaluates the anisotropic Trowbridge-Reitz forms with alpha_x = alpha_y =
+// roughness (plastic.rs:31-33); with equal alphas cos^2(phi) + sin^2(phi) = 1 drops out, so the device
+// evaluates the isotropic closed forms (same zero / infinity guards, results equal up to f64 rounding):
+//   D(wh)     = alpha^2 / (pi (alpha^2 cos^2 + sin^2)^2)                    microfacet.rs:31-40
+//   Lambda(w) = (sqrt(1 + alpha^2 tan^2) - 1) / 2                           microfacet.rs:55-66
+//   F         = dielectric(wi.wh, 1, 1.5) with both ratios over one divisor  fresnel.rs:37-64
+//   f         = kd / pi + ks D F / (4 cos_i cos_o (1 + Lambda_o + Lambda_i)) microfacet.rs:101-115
+__device__ __forceinline__ double dielectric(double cos_i) {                  // eta_i = 1, eta_t = 1.5
     cos_i = fmin(fmax(cos_i, -1.0), 1.0);
-    if (!(cos_i > 0.0)) { double tmp = eta_i; eta_i = eta_t; eta_t = tmp; cos_i = fabs(cos_i); }
-    double sin_i = sqrt(fmax(1.0 - cos_i * cos_i, 0.0));
-    double sin_t = eta_i / eta_t * sin_i;
+    double eta_i = 1.0, eta_t = 1.5, ratio = 1.0 / 1.5;
+    if (!(cos_i > 0.0)) { eta_i = 1.5; eta_t = 1.0; ratio = 1.5; cos_i = fabs(cos_i); }
+    const double sin_i = sqrt(fmax(1.0 - cos_i * cos_i, 0.0));
+    const double sin_t = ratio * sin_i;
     if (sin_t >= 1.0) return 1.0;
-    double cos_t = sqrt(fmax(1.0 - sin_t * sin_t, 0.0));
-    double r_parl = ((eta_t * cos_i) - (eta_i * cos_t)) / ((eta_t * cos_i) + (eta_i * cos_t));
-    double r_perp = ((eta_i * cos_i) - (eta_t * cos_t)) / ((eta_i * cos_i) + (eta_t * cos_t));
-    return (r_parl * r_parl + r_perp * r_perp) * 0.5;
+    const double cos_t = sqrt(fmax(1.0 - sin_t * sin_t, 0.0));
+    const double a = eta_t * cos_i - eta_i * cos_t, b = eta_t * cos_i + eta_i * cos_t;   // r_parl = a / b
+    const double c = eta_i * cos_i - eta_t * cos_t, d = eta_i * cos_i + eta_t * cos_t;   // r_perp = c / d
+    const double ad = a * d, cb = c * b, bd = b * d;
+    return (ad * ad + cb * cb) / (bd * bd) * 0.5;
 }
-__device__ double tr_d(double ax, double ay, D3 wh) {                         // microfacet.rs:31-40
-    double t2 = sin2_theta(wh) / cos2_theta(wh);
+__device__ __forceinline__ double tr_lambda(double alpha2, D3 w) {
+    const double c2 = w.z * w.z, s2 = fmax(1.0 - c2, 0.0);
+    const double t2 = s2 / c2;
     if (isinf(t2)) return 0.0;
-    const double PI = 3.14159265358979323846264338327950288;
-    double cos4 = cos2_theta(wh) * cos2_theta(wh);
-    double cp = cos_phi(wh), sp = sin_phi(wh);
-    double e = ((cp * cp) / (ax * ax) + (sp * sp) / (ay * ay)) * t2;
-    return 1.0 / (PI * ax * ay * cos4 * (1.0 + e) * (1.0 + e));
+    return (sqrt(1.0 + alpha2 * t2) - 1.0) * 0.5;
 }
-__device__ double tr_lambda(double ax, double ay, D3 w) {                     // microfacet.rs:55-66
-    double att = fabs(sin_theta(w) / w.z);
-    if (isinf(att)) return 0.0;
-    double cp = cos_phi(w), sp = sin_phi(w);
-    double alpha = sqrt((cp * cp) * ax * ax + (sp * sp) * ay * ay);
-    double a2t2 = (alpha * att) * (alpha * att);
-    return (sqrt(1.0 + a2t2) - 1.0) / 2.0;
+// Per-hit part of the BSDF: everything that depends on wo only is evaluated once for the L + 1 evaluations
+// of integrate.rs:47-67.
+struct Bsdf {
+    D3 ng, ns, ss, ts, kd_pi, ks, wo_l;
+    double alpha2, wo_ng, cos_o, lambda_o;
+    bool diffuse, glossy;
+};
+__device__ __forceinline__ void bsdf_prepare(Bsdf& B, D3 wo) {
+    B.wo_ng = dot(wo, B.ng);
+    B.wo_l = d3(dot(wo, B.ss), dot(wo, B.ts), dot(wo, B.ns));
+    B.cos_o = fabs(B.wo_l.z);
+    B.lambda_o = B.glossy ? tr_lambda(B.alpha2, B.wo_l) : 0.0;
 }
-struct Bsdf { D3 ng, ns, ss, ts, kd, ks; double alpha; bool diffuse, glossy; };
-__device__ D3 bsdf_f(const Bsdf& B, D3 wo, D3 wi) {
-    bool reflect = dot(wi, B.ng) * dot(wo, B.ng) > 0.0;
-    D3 wo_l = d3(dot(wo, B.ss), dot(wo, B.ts), dot(wo, B.ns));
-    D3 wi_l = d3(dot(wi, B.ss), dot(wi, B.ts), dot(wi, B.ns));
+__device__ __forceinline__ D3 bsdf_f(const Bsdf& B, D3 wi) {
+    const bool reflect = dot(wi, B.ng) * B.wo_ng > 0.0;
     D3 f = d3(0, 0, 0);
-    if (wo_l.z == 0.0) return f;
+    if (B.wo_l.z == 0.0) return f;
     if (!reflect) return f;                 // every lobe on this path is REFLECTION (bxdf/mod.rs:145-147)
-    if (B.diffuse) f = f + B.kd * 0.318309886183790671537767526745028724;       // diffuse.rs:14
+    if (B.diffuse) f = B.kd_pi;                                                  // diffuse.rs:14
     if (B.glossy) {                                                              // microfacet.rs:101-115
-        double cos_o = fabs(wo_l.z), cos_i = fabs(wi_l.z);
-        D3 wh = wi_l + wo_l;
-        D3 m = d3(0, 0, 0);
-        if (!(cos_i == 0.0 || cos_o == 0.0) && !(wh.x == 0.0 && wh.y == 0.0 && wh.z == 0.0)) {
-            wh = normalize(wh);
-            double F = dielectric(dot(wi_l, wh), 1.0, 1.5);
-            double g = 1.0 / (1.0 + tr_lambda(B.alpha, B.alpha, wo_l) + tr_lambda(B.alpha, B.alpha, wi_l));
-            m = mul_el(B.ks * tr_d(B.alpha, B.alpha, wh) * g, d3(F, F, F)) / (4.0 * cos_i * cos_o);
+        const D3 wi_l = d3(dot(wi, B.ss), dot(wi, B.ts), dot(wi, B.ns));
+        const double cos_i = fabs(wi_l.z);
+        const D3 wh = wi_l + B.wo_l;
+        const double hh = dot(wh, wh);
+        if (!(cos_i == 0.0 || B.cos_o == 0.0) && hh != 0.0) {
+            const double inv = rsqrt(hh);
+            const double whz = wh.z * inv;
+            const double c2 = whz * whz, s2 = fmax(1.0 - c2, 0.0);
+            if (c2 != 0.0) {                                                     // tan^2 infinite: D = 0
+                const double F = dielectric(dot(wi_l, wh) * inv);
+                const double q = B.alpha2 * c2 + s2;
+                const double PI = 3.14159265358979323846264338327950288;
+                const double den = PI * (q * q) * (4.0 * cos_i * B.cos_o) * (1.0 + B.lambda_o + tr_lambda(B.alpha2, wi_l));
+                f = f + B.ks * (B.alpha2 * F / den);
+            }
         }
-        f = f + m;
     }
     return f;
 }
@@ -410,6 +418,7 @@ __device__ __forceinline__ double lerp64(double t, double a, double b) { return 
 // + Material::scattering, plastic.rs:20-37 / matte.rs:18-26).
 struct ShadePoint { D3 wo, ng, ns, ps; Bsdf B; };
 
+template <bool WITH_BSDF>
 __device__ __forceinline__ void shade_point(const DevScene& S, const Ray64& ray, double t, uint32_t ref, ShadePoint& P, uint32_t& id) {
     Surf sf; double t_again = t;
     surface_of(S, ray, ref, t_again, sf);
@@ -421,11 +430,13 @@ __device__ __forceinline__ void shade_point(const DevScene& S, const Ray64& ray,
     D3 p = ray.o + ray.d * t;
     D3 p_err = P.ng * err;
     P.ps = p + p_err;                                          // integrate.rs:40
+    if (!WITH_BSDF) return;
     P.B.ng = P.ng; P.B.ns = P.ns; P.B.ss = normalize(sf.s_dpdu); P.B.ts = cross(P.ns, P.B.ss);
     const double* M = S.materials + 8 * (size_t)sf.material;
-    P.B.kd = d3(M[0], M[1], M[2]); P.B.alpha = M[3]; P.B.ks = d3(M[4], M[5], M[6]);
+    P.B.kd_pi = d3(M[0], M[1], M[2]) * 0.318309886183790671537767526745028724; P.B.alpha2 = M[3] * M[3]; P.B.ks = d3(M[4], M[5], M[6]);
     const uint32_t flags = (uint32_t)__double_as_longlong(M[7]);
     P.B.diffuse = flags & 1u; P.B.glossy = flags & 2u;
+    bsdf_prepare(P.B, P.wo);
 }
 
 // ------------------------------------------------------------------ work mapping
@@ -597,7 +608,7 @@ __global__ void __launch_bounds__(256) k_setup(DevScene S, DevCamera C, DevShade
                 live = true;
                 const double t = V.hit_t[g];
                 ShadePoint P; uint32_t id;
-                shade_point(S, ray, t, ref, P, id);
+                shade_point<false>(S, ray, t, ref, P, id);
                 V.ps[3 * g + 0] = P.ps.x; V.ps[3 * g + 1] = P.ps.y; V.ps[3 * g + 2] = P.ps.z;
                 if (O.aov_id) O.aov_id[gi] = id;
                 if (O.aov_t) O.aov_t[gi] = t;
@@ -689,7 +700,7 @@ __global__ void __launch_bounds__(256) k_shade(DevScene S, DevCamera C, DevShade
     Ray64 ray; uint32_t x, y, s;
     if (!slot_ray(C, W, g, ray, x, y, s)) return;
     ShadePoint P; uint32_t id;
-    shade_point(S, ray, V.hit_t[g], ref, P, id);
+    shade_point<true>(S, ray, V.hit_t[g], ref, P, id);
     const uint32_t occl = V.occl[g];
     if (O.aov_occl) O.aov_occl[((uint64_t)y * W.w + x) * W.spp + s] = occl;
     D3 output = d3(0, 0, 0);
@@ -700,12 +711,12 @@ __global__ void __launch_bounds__(256) k_shade(DevScene S, DevCamera C, DevShade
         double dist = sqrt(dot(wi, wi));
         double f_att = L[6] + L[7] * dist + L[8] * dist * dist;
         if (f_att == 0.0) continue;
-        wi = normalize(wi);
+        wi = wi * (1.0 / dist);
         double wi_dot_n = dot(wi, P.ns);
-        D3 f = bsdf_f(P.B, P.wo, wi);                                  // zero when the shadow ray was skipped
-        output = output + (mul_el(PI * d3(L[3], L[4], L[5]), f) * wi_dot_n / f_att);
+        D3 f = bsdf_f(P.B, wi);                                        // zero when the shadow ray was skipped
+        output = output + mul_el(PI * d3(L[3], L[4], L[5]), f) * (wi_dot_n / f_att);
     }
-    output = output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), bsdf_f(P.B, P.wo, P.ns));   // integrate.rs:67
+    output = output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), bsdf_f(P.B, P.ns));   // integrate.rs:67
     D3 zero = d3(0, 0, 0);
     output = output + zero + zero;          // integrate.rs:79 (reflected + refracted are zero for plastic)
     O.radiance[3 * g + 0] = output.x; O.radiance[3 * g + 1] = output.y; O.radiance[3 * g + 2] = output.z;
