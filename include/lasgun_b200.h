@@ -135,8 +135,9 @@ typedef struct lgb_stats {
     uint64_t primary_rays;           /* w * h * spp rendered by this call */
     uint64_t primary_hits;
     uint64_t shadow_rays;            /* reference semantics: lights * primary_hits (integrate.rs:47-50) */
-    uint64_t shadow_rays_traced;     /* rays the device actually traversed */
+    uint64_t shadow_rays_traced;     /* shadow rays the device resolved (lights that can contribute, bsdf.rs:75) */
     uint64_t shadow_occluded;
+    uint64_t shadow_cache_hits;      /* of those: blocked by the occluder of the pixel's anchor sample, no traversal */
     /* Work counters, filled only by lgb_capture_aov or with LGB_OPT_COUNT_WORK (slower kernel variant);
      * index 0 sphere, 1 cuboid, 2 triangle. */
     uint64_t exact_tests[3];         /* f64 reference-arithmetic primitive tests executed */

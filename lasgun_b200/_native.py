@@ -70,7 +70,7 @@ class BuildInfo(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("primary_hits", C.c_uint64), ("shadow_rays", C.c_uint64),
-                ("shadow_rays_traced", C.c_uint64), ("shadow_occluded", C.c_uint64), ("exact_tests", C.c_uint64 * 3),
+                ("shadow_rays_traced", C.c_uint64), ("shadow_occluded", C.c_uint64), ("shadow_cache_hits", C.c_uint64), ("exact_tests", C.c_uint64 * 3),
                 ("filter_tests", C.c_uint64 * 3), ("node_tests", C.c_uint64), ("render_ms", C.c_float), ("total_ms", C.c_float),
                 ("kernel_launches", C.c_uint32), ("stack_overflow", C.c_uint32)]
 

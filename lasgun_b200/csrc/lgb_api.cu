@@ -458,6 +458,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     W.mode = a.mode; W.w = a.w; W.h = a.h;
     W.winv = 1.0 / (double)a.w; W.hinv = 1.0 / (double)a.h; W.aspect = (double)a.w / (double)a.h;   // film.rs:36-45
     W.spp = s->cam.root * s->cam.root;
+    W.anchor = (s->cam.root / 2) * s->cam.root + s->cam.root / 2;      // camera.rs:143: sample (i, j) = i * root + j
     if (a.mode == 0) {
         if (a.ranks == 0 || a.rank >= a.ranks) return fail(c, LGB_ERR_INVALID, "capture: tile_rank out of range");
         build_tile_list(c, a.w, a.h, a.rank, a.ranks);
@@ -485,10 +486,11 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     const DevScene& S = s->dev;
     CU(c, c->radiance.reserve(std::max<uint64_t>(total, 1) * 3 * sizeof(double)));
     CU(c, c->counters.reserve(sizeof(DevCounters)));
-    // wavefront buffers: hit_t 8 + ps 24 + hit_ref 4 + occl 4 + queue 4 * lights bytes per sample slot
-    const uint64_t nslots = std::max<uint64_t>(total, 1), nl = std::max<uint32_t>(S.n_lights, 1);
-    CU(c, c->wave.reserve(nslots * (8 + 24 + 4 + 4 + 4 * nl)));
-    CU(c, c->wave_ctr.reserve(8 + 4 * LGB_MAX_LIGHTS * 2));
+    // wavefront buffers: hit_t 8 + ps 24 + hit_ref 4 + occl 4 + 3 queues x 4 x lights bytes per sample slot,
+    // + occluder 4 x lights bytes per pixel slot
+    const uint64_t nslots = std::max<uint64_t>(total, 1), nl = std::max<uint32_t>(S.n_lights, 1), npix = std::max<uint64_t>(W.n_pixels, 1);
+    CU(c, c->wave.reserve(nslots * (8 + 24 + 4 + 4 + 12 * nl) + npix * 4 * nl));
+    CU(c, c->wave_ctr.reserve(kWaveCtrBytes));
     DevWave V{};
     {
         char* base = (char*)c->wave.p;
@@ -496,10 +498,11 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         V.ps = (double*)base; base += nslots * 24;
         V.hit_ref = (uint32_t*)base; base += nslots * 4;
         V.occl = (uint32_t*)base; base += nslots * 4;
-        V.queue = (uint32_t*)base; V.queue_stride = nslots;
+        V.queue = (uint32_t*)base; V.queue_stride = nslots; base += nslots * 12 * nl;
+        V.occluder = (uint32_t*)base;
         V.work_counter = (unsigned long long*)c->wave_ctr.p;
         V.queue_count = (uint32_t*)((char*)c->wave_ctr.p + 8);
-        V.shadow_counter = V.queue_count + LGB_MAX_LIGHTS;
+        V.queue_fetch = V.queue_count + LGB_MAX_LIGHTS * 3;
     }
     DevOut O{};
     O.radiance = (double*)c->radiance.p;
@@ -525,11 +528,11 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         std::memset(stats, 0, sizeof *stats);
         stats->primary_rays = hc.primary_rays; stats->primary_hits = hc.primary_hits;
         stats->shadow_rays = hc.primary_hits * s->dev.n_lights;
-        stats->shadow_rays_traced = hc.shadow_traced; stats->shadow_occluded = hc.shadow_occluded;
+        stats->shadow_rays_traced = hc.shadow_traced; stats->shadow_occluded = hc.shadow_occluded; stats->shadow_cache_hits = hc.shadow_cached;
         stats->node_tests = hc.node_tests;
         for (int k = 0; k < 3; k++) { stats->filter_tests[k] = hc.filter[k]; stats->exact_tests[k] = hc.exact[k]; }
         stats->stack_overflow = hc.stack_overflow;
-        stats->kernel_launches = total ? 4 + s->dev.n_lights : 0;
+        stats->kernel_launches = total ? 4 + s->dev.n_lights * (W.spp > 1 ? 3 : 1) : 0;
         float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         stats->render_ms = ms; stats->total_ms = ms;
     }

@@ -492,7 +492,9 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 // k_setup    per slot: miss -> background radiance; hit -> shadow origin ps and, per light, whether the
 //            light can contribute at all (bsdf.rs:75: wi and wo on the same side of ng); those rays are
 //            appended to that light's queue with one warp-aggregated atomic
-// k_shadow   per light, persistent warps over the compacted queue: any-hit traversal to t < 1
+// k_shadow   per light, persistent warps over a compacted queue: any-hit traversal to t < 1; run on queue A (the
+//            centre sample of every pixel, whose occluder is remembered) and on queue C
+// k_pretest  per light: the other samples try the remembered occluder first (one exact test); survivors -> queue C
 // k_shade    per slot: BSDF evaluation for the unoccluded lights + ambient -> radiance (integrate.rs:47-67)
 // k_resolve  per pixel: in-order sample sum, weight, quantise, uchar4 store (integrate.rs:16-20, img.rs:56-67)
 
@@ -519,6 +521,34 @@ __device__ __forceinline__ unsigned long long warp_fetch(CounterT* counter, bool
     if ((int)lane == leader) base = (unsigned long long)atomicAdd(counter, (CounterT)__popc(m));
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
     return need ? base + __popc(m & ((1u << lane) - 1u)) : ~0ull;
+}
+
+
+// Order-preserving append of one block's items to a global queue: per-warp counts in shared memory, an
+// exclusive scan over the warps, ONE global atomic per block and queue (same-address atomics serialise, and a
+// warp-by-warp append would interleave the warps of different blocks, which destroys ray coherence downstream).
+// Every thread of the block must call it (it synchronises); `mine` marks the threads that append `value`.
+constexpr int kAppendThreads = 512;
+struct AppendScratch { uint32_t warp_off[kAppendThreads / 32]; uint32_t base; };
+__device__ __forceinline__ void block_append(AppendScratch& sc, bool mine, uint32_t value, uint32_t* queue, uint32_t* count) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
+    if (lane == 0) sc.warp_off[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const unsigned nw = blockDim.x >> 5;
+        const uint32_t c = lane < nw ? sc.warp_off[lane] : 0u;
+        uint32_t incl = c;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += v; }
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0 && tot) base = atomicAdd(count, tot);
+        if (lane == 0) sc.base = base;
+        if (lane < nw) sc.warp_off[lane] = incl - c;
+    }
+    __syncthreads();
+    if (mine) queue[sc.base + sc.warp_off[warp] + __popc(m & ((1u << lane) - 1u))] = value;
+    __syncthreads();          // scratch is reused by the next call
 }
 
 template <bool STATS>
@@ -583,10 +613,9 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, Dev
 }
 
 template <bool ALL_SHADOWS>
-__global__ void __launch_bounds__(256) k_setup(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
+__global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
     const uint64_t total = W.n_pixels * W.spp;
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
     uint32_t need = 0;
     bool live = false;
     if (g < total) {
@@ -624,22 +653,78 @@ __global__ void __launch_bounds__(256) k_setup(DevScene S, DevCamera C, DevShade
             }
         }
     }
-    // compacted per-light shadow queues: one atomic per warp per light
+    // compacted per-light shadow queues (A: anchor sample of the pixel, B: the others), block-ordered
+    __shared__ AppendScratch sc;
+    const bool anchor = W.spp == 1 || (uint32_t)(g % W.spp) == W.anchor;
     for (uint32_t l = 0; l < S.n_lights; l++) {
         const bool want = live && ((need >> l) & 1u);
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
-        if (!m) continue;
-        unsigned base = 0;
-        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&V.queue_count[l], (unsigned)__popc(m));
-        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-        if (want) V.queue[(size_t)l * V.queue_stride + base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)g;
+        block_append(sc, want && anchor, (uint32_t)g, V.queue + (size_t)(l * 3 + kQueueA) * V.queue_stride, &V.queue_count[l * 3 + kQueueA]);
+        if (W.spp > 1)
+            block_append(sc, want && !anchor, (uint32_t)g, V.queue + (size_t)(l * 3 + kQueueB) * V.queue_stride, &V.queue_count[l * 3 + kQueueB]);
+    }
+}
+
+// Exact test of ONE primitive against a shadow ray: true iff the reference's intersect accepts it with t < 1
+// (the same calls the traversal makes for a candidate, light/point.rs:48-49).
+__device__ __forceinline__ bool occludes(const DevScene& S, uint32_t ref, const Ray64& ray) {
+    const uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+    double t;
+    if (type == LGB_PRIM_TRIANGLE) {
+        const float4* tp = S.tri + 3 * (size_t)idx;
+        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+        double b0, b1, b2;
+        return triangle_exact(d3(q0.x, q0.y, q0.z), d3(q1.x, q1.y, q1.z), d3(q2.x, q2.y, q2.z), ray, t, b0, b1, b2) && t < 1.0;
+    }
+    if (type == LGB_PRIM_SPHERE) {
+        const double2 c01 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx));
+        const double2 c23 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx + 2));
+        bool inside;
+        return sphere_exact(d3(c01.x, c01.y, c23.x), c23.y, ray, t, inside) && t < 1.0;
+    }
+    double mn[3], mx[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { mn[k] = __ldg(&S.cub64[6 * (size_t)idx + k]); mx[k] = __ldg(&S.cub64[6 * (size_t)idx + 3 + k]); }
+    int ua, va;
+    return cuboid_exact(mn, mx, ray, t, ua, va) && t < 1.0;
+}
+
+// Queue B -> occl bit (blocked by the occluder the pixel's anchor ray found) or queue C (needs a traversal).
+__global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light) {
+    __shared__ AppendScratch sc;
+    const unsigned total = V.queue_count[light * 3 + kQueueB];
+    const unsigned lane = threadIdx.x & 31u;
+    const double* L = S.lights + 9 * (size_t)light;
+    const D3 lp = d3(L[0], L[1], L[2]);
+    unsigned ncached = 0;
+    for (unsigned i0 = blockIdx.x * blockDim.x; i0 < total; i0 += gridDim.x * blockDim.x) {      // block-uniform trip count
+        const unsigned i = i0 + threadIdx.x;
+        bool to_c = false;
+        uint32_t g = 0;
+        if (i < total) {
+            g = V.queue[(size_t)(light * 3 + kQueueB) * V.queue_stride + i];
+            const uint32_t oc = V.occluder[(size_t)light * W.n_pixels + g / W.spp];
+            to_c = true;
+            if (oc != LGB_MISS) {
+                Ray64 ray;
+                ray.o = d3(V.ps[3 * (size_t)g], V.ps[3 * (size_t)g + 1], V.ps[3 * (size_t)g + 2]);
+                ray.d = lp - ray.o;                                                  // light/point.rs:43-44
+                if (occludes(S, oc, ray)) { V.occl[g] |= 1u << light; to_c = false; ncached++; }   // sole writer of occl[g] in this launch
+            }
+        }
+        block_append(sc, to_c, g, V.queue + (size_t)(light * 3 + kQueueC) * V.queue_stride, &V.queue_count[light * 3 + kQueueC]);
+    }
+    if (O.counters) {
+        const unsigned long long n = warp_sum(ncached);
+        if (lane == 0 && n) { atomicAdd(&O.counters->shadow_cached, n); atomicAdd(&O.counters->shadow_occluded, n); }
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&O.counters->shadow_traced, (unsigned long long)total);
     }
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevOut O, DevWave V, uint32_t light) {
-    const unsigned total = V.queue_count[light];
-    const uint32_t* q = V.queue + (size_t)light * V.queue_stride;
+__global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light, int which) {
+    const unsigned total = V.queue_count[light * 3 + which];
+    const uint32_t* q = V.queue + (size_t)(light * 3 + which) * V.queue_stride;
+    const bool record = which == kQueueA && W.spp > 1;      // anchor rays remember their occluder for k_pretest
     const double* L = S.lights + 9 * (size_t)light;
     const D3 lp = d3(L[0], L[1], L[2]);
     const unsigned lane = threadIdx.x & 31u;
@@ -653,7 +738,7 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevO
         if (!drained) {
             const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
             if (idle == 0xFFFFFFFFu || __popc(idle) > 32 - LGB_REFILL_BELOW) {
-                const unsigned long long idx = warp_fetch(V.shadow_counter + light, !active, lane);
+                const unsigned long long idx = warp_fetch(V.queue_fetch + light * 3 + which, !active, lane);
                 if (!active && idx < total) {
                     g = q[idx];
                     ray.o = d3(V.ps[3 * (size_t)g], V.ps[3 * (size_t)g + 1], V.ps[3 * (size_t)g + 2]);
@@ -671,6 +756,7 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevO
             const bool done = trav_run<true, STATS, true>(S, ray, f, T, stack, 1.0, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
             if (done) {
                 if (T.best.ref != LGB_MISS) { atomicOr(&V.occl[g], 1u << light); occluded++; }
+                if (record) V.occluder[(size_t)light * W.n_pixels + g / W.spp] = T.best.ref;
                 active = false;
             }
         }
@@ -678,7 +764,7 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevO
     if (O.counters) {
         unsigned long long v = warp_sum(occluded);
         if (lane == 0) atomicAdd(&O.counters->shadow_occluded, v);
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&O.counters->shadow_traced, (unsigned long long)total);
+        if (which == kQueueA && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&O.counters->shadow_traced, (unsigned long long)total);
         if (STATS) {
             unsigned long long n = warp_sum(lc.node_tests);
             if (lane == 0) atomicAdd(&O.counters->node_tests, n);
@@ -800,16 +886,23 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     const uint64_t total = W.n_pixels * W.spp;
     if (total == 0) return cudaSuccess;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(V.work_counter, 0, 8 + 4 * (size_t)LGB_MAX_LIGHTS * 2, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(V.work_counter, 0, kWaveCtrBytes, stream)) != cudaSuccess) return e;
+    const bool cache = W.spp > 1;
+    if (cache && S.n_lights && (e = cudaMemsetAsync(V.occluder, 0xFF, (size_t)S.n_lights * W.n_pixels * 4, stream)) != cudaSuccess) return e;
     const unsigned pblocks = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)sms * LGB_MIN_BLOCKS);
     if (stats) k_primary<true><<<pblocks, 256, 0, stream>>>(S, C, W, O, V);
     else k_primary<false><<<pblocks, 256, 0, stream>>>(S, C, W, O, V);
-    const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (all_shadows) k_setup<true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
-    else k_setup<false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
-    for (uint32_t l = 0; l < S.n_lights; l++) {
-        if (stats) k_shadow<true><<<pblocks, 256, 0, stream>>>(S, O, V, l);
-        else k_shadow<false><<<pblocks, 256, 0, stream>>>(S, O, V, l);
+    const unsigned blocks = (unsigned)((total + 255) / 256), ablocks = (unsigned)((total + kAppendThreads - 1) / kAppendThreads);
+    if (all_shadows) k_setup<true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
+    else k_setup<false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
+    // anchor rays (queue A), then the cached-occluder test of the rest (B -> C), then the survivors (queue C)
+    for (int which = kQueueA; which <= (cache ? kQueueC : kQueueA); which += 2) {
+        const unsigned sb = which == kQueueA ? (unsigned)std::min<uint64_t>((W.n_pixels + 255) / 256, pblocks) : pblocks;
+        for (uint32_t l = 0; l < S.n_lights; l++) {
+            if (which == kQueueC) k_pretest<<<(unsigned)std::min<uint64_t>(ablocks, (uint64_t)sms * 4), kAppendThreads, 0, stream>>>(S, W, O, V, l);
+            if (stats) k_shadow<true><<<sb, 256, 0, stream>>>(S, W, O, V, l, which);
+            else k_shadow<false><<<sb, 256, 0, stream>>>(S, W, O, V, l, which);
+        }
     }
     k_shade<<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;

@@ -75,11 +75,12 @@ struct DevWork {
     uint32_t sub_k, sub_n;
     uint64_t n_pixels;               // pixel slots in this launch
     uint32_t spp;
+    uint32_t anchor;                 // sample index of the pixel's anchor shadow ray (centre of the sample grid)
     uint32_t compact_out;            // resolve writes film[slot] instead of film[y*w + x]
 };
 
 struct DevCounters {
-    unsigned long long primary_rays, primary_hits, shadow_traced, shadow_occluded;
+    unsigned long long primary_rays, primary_hits, shadow_traced, shadow_occluded, shadow_cached;
     unsigned long long node_tests;     // node fetches (each tests two child boxes)
     unsigned long long filter[3];    // f32 filter tests by primitive type (sphere, cuboid, triangle)
     unsigned long long exact[3];     // f64 reference-arithmetic tests by primitive type
@@ -93,12 +94,20 @@ struct DevWave {
     uint32_t* hit_ref;               // type << 30 | index, LGB_MISS, or kSlotUnused (pixel outside the film)
     double* ps;                      // shadow-ray origin p + p_err (3 per slot)
     uint32_t* occl;                  // bit l set: light l occluded
-    uint32_t* queue;                 // n_lights x queue_stride slot indices
+    // Shadow-ray queues of slot indices, three per light (kQueueA/B/C), each queue_stride entries:
+    //   A  anchor rays: the centre sample of every pixel (every ray at 1 spp); traced first, their occluder
+    //      is remembered per (light, pixel) in `occluder`
+    //   B  the other samples of the pixel: k_pretest runs the exact test of the remembered occluder alone
+    //   C  the B rays that the remembered occluder does not block: full any-hit traversal
+    uint32_t* queue;                 // [(light * 3 + which) * queue_stride + i]
     uint64_t queue_stride;
-    unsigned long long* work_counter;   // [0] primary; followed by u32 queue_count[LGB_MAX_LIGHTS], shadow_counter[LGB_MAX_LIGHTS]
+    uint32_t* occluder;              // [light * n_pixels + pixel_slot]: ref of the anchor ray's occluder or LGB_MISS
+    unsigned long long* work_counter;   // [0] primary fetch counter; then u32 queue_count[lights][3], queue_fetch[lights][3]
     uint32_t* queue_count;
-    uint32_t* shadow_counter;
+    uint32_t* queue_fetch;
 };
+constexpr int kQueueA = 0, kQueueB = 1, kQueueC = 2;
+constexpr size_t kWaveCtrBytes = 8 + 4 * (size_t)LGB_MAX_LIGHTS * 3 * 2;
 constexpr uint32_t kSlotUnused = 0xFFFFFFFEu;
 
 struct DevOut {

@@ -15,4 +15,4 @@ dev = N.DeviceScene(ctx, N.FlatScene(sc))
 film = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
 for i in range(frames):
     st = dev.capture_device(w, h, film.data_ptr(), want_stats=True)
-    print(name, w, h, "frame", i, "render_ms", round(st["render_ms"], 3), {k: st[k] for k in ("primary_hits", "shadow_rays", "shadow_rays_traced", "shadow_occluded")})
+    print(name, w, h, "frame", i, "render_ms", round(st["render_ms"], 3), {k: st[k] for k in ("primary_hits", "shadow_rays", "shadow_rays_traced", "shadow_occluded", "shadow_cache_hits")})
