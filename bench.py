@@ -7,8 +7,9 @@ A step is one full frame of the workload (default: BASELINE.json's config 5, `mi
 16 spp — the config the 1/2/4/8-GPU metric is quoted on; it fits one GPU).  Rays are counted with the
 reference's semantics: primary = w*h*spp, shadow = lights * primary hits (integrate.rs:47-50).
   value  scene + BVH resident in HBM, frame rendered into a device film (rank 0 after the NVLink gather)
-  e2e    the C-ABI call with HOST buffers: lgb_scene_create (H2D of the flattened scene) +
-         lgb_capture (render + D2H of the film) + lgb_scene_destroy, every step
+  e2e    `capture(scene, film)` as the reference defines it (lib.rs:55-104), with HOST buffers, every step:
+         the reference's HLBVH build + flatten of the host scene, lgb_scene_create (device BVH build, H2D of
+         the scene), lgb_capture (render + D2H of the film), lgb_scene_destroy
 --impl reference times the CPU oracle (C++ restatement of the reference algorithm — the Rust build
 cannot be compiled here) on all host threads over a bounded sample of the same frame.
 """
@@ -168,7 +169,8 @@ def run_gpu(args):
     ctx = N.Context(local)
     sc, (w, h) = workload(args.workload, args)
     spp, nl = sc.camera.num_samples(), len(sc.lights)
-    t0 = time.time(); flat = N.FlatScene(sc, resplit=not args.no_resplit, leaf_size=args.leaf_size); host_flatten_s = time.time() - t0
+    hscene_host = N.HostScene(sc)                      # the built `Scene` (scene construction is not part of capture)
+    flat = N.FlatScene(hscene_host)
     dev = N.DeviceScene(ctx, flat)
     film = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
     # everything (our kernels, NCCL, the timing events) runs on ONE non-default torch stream so that
@@ -230,15 +232,18 @@ def run_gpu(args):
 
     # e2e through the C ABI with host buffers (rank-local frame share; film gathered on the host side of rank 0)
     host_film = np.zeros((h, w, 4), np.uint8)
-    e2e_ms = []
+    e2e_ms, e2e_parts = [], []
     L = N.lib()
     for i in range(args.e2e_steps + 1):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
+        flat_i = N.FlatScene(hscene_host)              # Accel::from: the reference's BVH build + flatten (bvh.rs:135-453)
+        t1 = time.perf_counter()
         hscene = C.c_void_p()
-        ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat.desc), C.byref(hscene)))
+        ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat_i.desc), C.byref(hscene)))
+        t2 = time.perf_counter()
         if world == 1:
             ctx.check(L.lgb_capture(ctx.h, hscene, w, h, host_film.ctypes.data_as(C.POINTER(C.c_uint8)), None))
         else:
@@ -249,7 +254,9 @@ def run_gpu(args):
                 host_film[...] = film.cpu().numpy()
             torch.cuda.synchronize()
         L.lgb_scene_destroy(hscene)
-        dt = torch.tensor([(time.perf_counter() - t0) * 1e3], device="cuda")
+        t3 = time.perf_counter()
+        e2e_parts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
+        dt = torch.tensor([(t3 - t0) * 1e3], device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         if i > 0:
@@ -271,13 +278,14 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": args.workload, "film": [w, h], "spp": spp, "lights": nl, "triangles": int(flat.desc.n_triangles),
                        "spheres": int(flat.desc.n_spheres), "cuboids": int(flat.desc.n_cuboids), "bvh_nodes": int(flat.desc.n_nodes),
-                       "resplit_leaf": 0 if args.no_resplit else args.leaf_size, "parallelism": f"tiles{world}",
+                       "device_bvh_nodes": int(dev.node_count) if hasattr(dev, "node_count") else None, "parallelism": f"tiles{world}",
                        "l2_policy": "per-frame working set (radiance buffer %.0f MB + scene %.0f MB) exceeds the 126 MB L2" % (frame["primary_rays"] * 24 / 1e6 / world, scene_bytes / 1e6)},
             "ms_per_frame": ms_per_step, "kernel_ms_per_frame": kernel_ms, "rays_per_frame": rays_frame,
             "rays_traced_per_frame": frame["primary_rays"] + frame["shadow_rays_traced"],
             "e2e": {"value": rays_frame / (e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e,
                     "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": w * h * 4,
-                    "host_bvh_build_flatten_ms": host_flatten_s * 1e3},
+                    "parts_ms": dict(zip(("reference_bvh_build_flatten", "scene_create_device_bvh_upload", "render_readback_destroy"),
+                                         [statistics.median(p[i] for p in e2e_parts[1:]) for i in range(3)]))},
             "gpu_launches": (4 + nl) * args.steps,
             "roofline": {"bound": "fp32_issue", "achieved": ach, "peak": fp32_peak, "unit": "Gop/s (FMA=2)", "frac": ach / fp32_peak,
                          "traffic": None, "peak_source": "lgb_measure_fp32_gops, live on this GPU",
@@ -317,8 +325,6 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="mixed4k", choices=sorted(scenes.CONFIGS))
     ap.add_argument("--small", action="store_true", help="tiny variant of mixed4k (CPU smoke of the bench logic)")
-    ap.add_argument("--leaf-size", type=int, default=4)
-    ap.add_argument("--no-resplit", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds", type=float, default=60.0)

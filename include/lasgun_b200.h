@@ -127,9 +127,8 @@ typedef struct lgb_scene_desc {
  * the traversal stack as the reference would, and (b) to record, per ray-direction octant, the order in
  * which the reference tests primitives, which is how exact-t ties are resolved (first tested wins,
  * sphere.rs:86 / cuboid.rs:95 / triangle.rs:251).  The device traverses its own SAH BVH over the same
- * primitives; results are the reference's for any such BVH.  LGB_SCENE_RESPLIT only records that the
- * caller already re-split the reference's fat leaves (it is informational). */
-#define LGB_SCENE_RESPLIT 1u
+ * primitives; results are the reference's for any such BVH.  Pass the tree exactly as the reference built
+ * it (leaves of up to 254 primitives, bvh.rs:289): re-splitting its leaves would change the test order. */
 
 typedef struct lgb_stats {
     uint64_t primary_rays;           /* w * h * spp rendered by this call */

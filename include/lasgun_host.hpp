@@ -10,13 +10,28 @@
 #pragma once
 #include <cstdint>
 #include <memory>
+#include <new>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "lasgun_b200.h"
 
 namespace lasgun {
+
+// std::vector whose resize() leaves trivially-constructible elements uninitialised: the big scene arrays are
+// filled by all threads right after they are sized, and a sequential zero-fill (plus its page faults) first
+// would cost more than the fill itself.
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+    template <class U> struct rebind { using other = default_init_allocator<U>; };
+    using std::allocator<T>::allocator;
+    template <class U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void*>(p)) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using raw_vector = std::vector<T, default_init_allocator<T>>;
 
 struct Error : std::runtime_error {
     int status;
@@ -131,10 +146,10 @@ private:
 struct FlatScene {
     std::vector<lgb_node> nodes;
     std::vector<uint32_t> prim_refs;
-    std::vector<lgb_sphere> spheres; std::vector<uint32_t> sphere_material, sphere_id;
-    std::vector<lgb_cuboid> cuboids; std::vector<uint32_t> cuboid_material, cuboid_id;
-    std::vector<lgb_triangle> triangles; std::vector<uint32_t> triangle_material, triangle_id;
-    std::vector<lgb_tri_normals> tri_normals; std::vector<uint8_t> tri_has_normals;
+    raw_vector<lgb_sphere> spheres; raw_vector<uint32_t> sphere_material, sphere_id;
+    raw_vector<lgb_cuboid> cuboids; raw_vector<uint32_t> cuboid_material, cuboid_id;
+    raw_vector<lgb_triangle> triangles; raw_vector<uint32_t> triangle_material, triangle_id;
+    raw_vector<lgb_tri_normals> tri_normals; raw_vector<uint8_t> tri_has_normals;
     std::vector<lgb_instance> instances;
     std::vector<lgb_material> materials;
     std::vector<lgb_light> lights;
@@ -150,8 +165,6 @@ struct FlatScene {
 };
 
 struct BuildOptions {
-    bool resplit = true;               // re-split the reference's fat leaves (<= 254 prims) on the host
-    uint32_t leaf_size = 4;
     bool keep_levels = false;          // keep per-level reference arrays (tests)
 };
 

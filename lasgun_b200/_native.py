@@ -119,7 +119,7 @@ def lib():
         "lgh_agg_add_group": (None, [vp, C.c_int, C.c_int]), "lgh_agg_swap_backface": (None, [vp, C.c_int]),
         "lgh_agg_translate": (None, [vp, C.c_int, dp]), "lgh_agg_scale": (None, [vp, C.c_int, C.c_double, C.c_double, C.c_double]),
         "lgh_agg_rotate_axis": (None, [vp, C.c_int, C.c_int, C.c_double]), "lgh_agg_rotate": (None, [vp, C.c_int, C.c_double, dp]),
-        "lgh_flatten": (vp, [vp, C.c_int, C.c_uint32, C.c_int]), "lgh_flat_free": (None, [vp]),
+        "lgh_flatten": (vp, [vp, C.c_int]), "lgh_flat_free": (None, [vp]),
         "lgh_flat_describe": (None, [vp, C.POINTER(SceneDesc)]), "lgh_flat_build_ms": (C.c_double, [vp]),
         "lgh_flat_prim_count": (C.c_uint32, [vp]), "lgh_flat_level_count": (C.c_uint64, [vp]),
         "lgh_flat_level_dims": (C.c_int, [vp, C.c_uint64, u64p, u64p, u32p]),
@@ -220,10 +220,10 @@ class HostScene:
 class FlatScene:
     """Host-side flattened scene (Accel::from without the upload): owns the arrays of an lgb_scene_desc."""
 
-    def __init__(self, scene, resplit=True, leaf_size=4, keep_levels=False):
+    def __init__(self, scene, keep_levels=False):
         L = lib()
         self.host = scene if isinstance(scene, HostScene) else HostScene(scene)
-        self.h = L.lgh_flatten(self.host.h, 1 if resplit else 0, leaf_size, 1 if keep_levels else 0)
+        self.h = L.lgh_flatten(self.host.h, 1 if keep_levels else 0)
         if not self.h:
             msg = L.lgh_last_error().decode()
             raise LasgunError(LGB_ERR_UNSUPPORTED if "not on the device path" in msg or "outside the device" in msg else LGB_ERR_INVALID, msg)

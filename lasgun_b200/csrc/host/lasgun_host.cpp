@@ -3,9 +3,14 @@
 // Product code: does not include or link anything under oracle/.
 #include "../../../include/lasgun_host.hpp"
 
+#include "../lgb_parallel.hpp"
+
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -178,49 +183,84 @@ struct BuildNode { Box box; int left = -1, right = -1; uint32_t first = 0, count
 // One BVH level (BVHAccel::new, bvh.rs:164-202).  `boxes[i]` is primitive i's bound.
 struct LevelTree {
     std::vector<BuildNode> nodes;
-    std::vector<uint32_t> order;      // bvh.rs:56-59
+    raw_vector<uint32_t> order;       // bvh.rs:56-59
     int root = -1;
     size_t total_nodes = 0;
 
-    void build(const std::vector<Box>& boxes, size_t per_node) {
+    void build(const raw_vector<Box>& boxes, size_t per_node) {
         const size_t n = boxes.size();
         if (n == 0) throw Error(LGB_ERR_INVALID, "empty aggregate: the reference's BVH build does not terminate (bvh.rs:240,355-356)");
         const size_t max_prims = std::min<size_t>(per_node, 255);
-        order.assign(n, 0xFFFFFFFFu);
-        nodes.reserve(2 * n + 512);
+        lgb::Pool& pool = lgb::Pool::get();
+        order.resize(n);             // every slot is written exactly once by the treelet emission below
+        // scene bounds (bvh.rs:212-213): min / max folds are order-independent, so the chunks may run in parallel
         Box bounds = Box::none();
-        for (const Box& b : boxes) bounds.grow(b);
+        {
+            const size_t nc = pool.chunks_of(n, 1 << 14);
+            std::vector<Box> part(nc, Box::none());
+            pool.for_range(n, 1 << 14, [&](size_t b, size_t e, size_t c) { for (size_t i = b; i < e; i++) part[c].grow(boxes[i]); });
+            for (const Box& b : part) bounds.grow(b);
+        }
         // Morton codes (bvh.rs:217-224, 575-579: z, y, z)
-        std::vector<uint32_t> code(n), idx(n), code2(n), idx2(n);
-        for (size_t i = 0; i < n; i++) {
-            double off[3];
-            for (int k = 0; k < 3; k++) {
-                double c = 0.5 * boxes[i].mn[k] + 0.5 * boxes[i].mx[k];        // bvh.rs:530
-                double o = c - bounds.mn[k];
-                if (bounds.mx[k] > bounds.mn[k]) o /= bounds.mx[k] - bounds.mn[k];   // bounds.rs:133-139
-                off[k] = o * 1024.0;
+        raw_vector<uint32_t> code(n), idx(n), code2(n), idx2(n);
+        pool.for_range(n, 1 << 14, [&](size_t b, size_t e, size_t) {
+            for (size_t i = b; i < e; i++) {
+                double off[3];
+                for (int k = 0; k < 3; k++) {
+                    double c = 0.5 * boxes[i].mn[k] + 0.5 * boxes[i].mx[k];        // bvh.rs:530
+                    double o = c - bounds.mn[k];
+                    if (bounds.mx[k] > bounds.mn[k]) o /= bounds.mx[k] - bounds.mn[k];   // bounds.rs:133-139
+                    off[k] = o * 1024.0;
+                }
+                uint32_t z = spread10(sat_u32(off[2])), y = spread10(sat_u32(off[1]));
+                code[i] = (z << 2) | (y << 1) | z;
+                idx[i] = (uint32_t)i;
             }
-            uint32_t z = spread10(sat_u32(off[2])), y = spread10(sat_u32(off[1]));
-            code[i] = (z << 2) | (y << 1) | z;
-            idx[i] = (uint32_t)i;
+        });
+        // Stable LSD radix sort on the 30-bit key: the same permutation as the reference's 5 x 6-bit passes
+        // (bvh.rs:600-635), three 10-bit passes with per-chunk histograms so that every pass is parallel and stable.
+        {
+            const size_t nc = std::max<size_t>(1, pool.chunks_of(n, 1 << 15));
+            const size_t per = (n + nc - 1) / nc;
+            std::vector<uint32_t> hist(nc * 1024);
+            for (int pass = 0; pass < 3; pass++) {
+                const int shift = 10 * pass;
+                pool.run(nc, [&](size_t c) {
+                    uint32_t* h = hist.data() + c * 1024; std::fill(h, h + 1024, 0u);
+                    const size_t b = c * per, e = std::min(n, b + per);
+                    for (size_t i = b; i < e; i++) h[(code[i] >> shift) & 1023u]++;
+                });
+                uint32_t run = 0;
+                for (int d = 0; d < 1024; d++) for (size_t c = 0; c < nc; c++) { uint32_t v = hist[c * 1024 + d]; hist[c * 1024 + d] = run; run += v; }
+                pool.run(nc, [&](size_t c) {
+                    uint32_t* h = hist.data() + c * 1024;
+                    const size_t b = c * per, e = std::min(n, b + per);
+                    for (size_t i = b; i < e; i++) { const uint32_t d = h[(code[i] >> shift) & 1023u]++; code2[d] = code[i]; idx2[d] = idx[i]; }
+                });
+                code.swap(code2); idx.swap(idx2);
+            }
         }
-        // Stable LSD radix sort on the 30-bit key (same permutation as the reference's 5 x 6-bit passes)
-        for (int pass = 0; pass < 3; pass++) {
-            const int shift = 10 * pass;
-            size_t cnt[1025] = {0};
-            for (size_t i = 0; i < n; i++) cnt[((code[i] >> shift) & 1023u) + 1]++;
-            for (int b = 0; b < 1024; b++) cnt[b + 1] += cnt[b];
-            for (size_t i = 0; i < n; i++) { size_t d = cnt[(code[i] >> shift) & 1023u]++; code2[d] = code[i]; idx2[d] = idx[i]; }
-            code.swap(code2); idx.swap(idx2);
+        // Treelets: runs with equal top 12 bits (bvh.rs:240-265).  Each one is emitted into its own node array
+        // (its slice of `order` starts at the treelet's first sorted position, as in the sequential build).
+        struct Treelet { size_t start, count; std::vector<BuildNode> nodes; int root; };
+        std::vector<Treelet> tl;
+        for (size_t start = 0, end = 1; end <= n; end++) {
+            if (end == n || ((code[start] ^ code[end]) & 0x3FFC0000u)) { tl.push_back({start, end - start, {}, -1}); start = end; }
         }
-        // Treelets: runs with equal top 12 bits (bvh.rs:240-265)
+        pool.run(tl.size(), [&](size_t t) {
+            Treelet& T = tl[t];
+            uint32_t ordered = (uint32_t)T.start;
+            T.nodes.reserve(2 * (T.count / std::max<size_t>(1, max_prims / 4)) + 8);
+            T.root = emit(T.nodes, code.data() + T.start, idx.data() + T.start, T.count, boxes, max_prims, ordered, 17);
+        });
+        size_t total = 0;
+        for (const Treelet& T : tl) total += T.nodes.size();
+        nodes.clear(); nodes.reserve(total + 2 * tl.size() + 8);
         std::vector<int> treelets;
-        size_t start = 0; uint32_t ordered = 0;
-        for (size_t end = 1; end <= n; end++) {
-            if (end == n || ((code[start] ^ code[end]) & 0x3FFC0000u)) {
-                treelets.push_back(emit(code.data() + start, idx.data() + start, end - start, boxes, max_prims, ordered, 17));
-                start = end;
-            }
+        for (Treelet& T : tl) {
+            const int base = (int)nodes.size();
+            for (BuildNode bn : T.nodes) { if (bn.left >= 0) { bn.left += base; bn.right += base; } nodes.push_back(bn); }
+            treelets.push_back(T.root + base);
         }
         total_nodes = nodes.size();
         root = upper_sah(treelets.data(), treelets.size(), 0);
@@ -228,7 +268,7 @@ struct LevelTree {
     }
 
     // emit_lbvh, bvh.rs:278-347
-    int emit(const uint32_t* code, const uint32_t* idx, size_t n, const std::vector<Box>& boxes, size_t max_prims, uint32_t& ordered, int bit) {
+    int emit(std::vector<BuildNode>& nodes, const uint32_t* code, const uint32_t* idx, size_t n, const raw_vector<Box>& boxes, size_t max_prims, uint32_t& ordered, int bit) {
         while (true) {
             if (bit == -1 || n < max_prims) {
                 BuildNode bn; bn.box = Box::none(); bn.first = ordered; bn.count = (uint32_t)n;
@@ -243,8 +283,8 @@ struct LevelTree {
             while (s + 1 != e) { size_t mid = (s + e) / 2; if ((code[s] & mask) == (code[mid] & mask)) s = mid; else e = mid; }
             const int me = (int)nodes.size();
             nodes.push_back(BuildNode());
-            int l = emit(code, idx, e, boxes, max_prims, ordered, bit - 1);
-            int r = emit(code + e, idx + e, n - e, boxes, max_prims, ordered, bit - 1);
+            int l = emit(nodes, code, idx, e, boxes, max_prims, ordered, bit - 1);
+            int r = emit(nodes, code + e, idx + e, n - e, boxes, max_prims, ordered, bit - 1);
             BuildNode& bn = nodes[me];
             bn.left = l; bn.right = r; bn.axis = (uint8_t)(bit % 3);
             bn.box = nodes[l].box; bn.box.grow(nodes[r].box);
@@ -304,8 +344,8 @@ struct LevelTree {
 // A level being assembled: its reference tree plus what each primitive is.
 struct Level {
     LevelTree tree;
-    std::vector<Box> boxes;
-    std::vector<uint32_t> refs;               // prim ref per primitive (instances: index into `children`)
+    raw_vector<Box> boxes;
+    raw_vector<uint32_t> refs;                // prim ref per primitive (instances: index into `children`)
     std::vector<std::unique_ptr<Level>> children;
     std::vector<uint32_t> child_instance;     // instance slot per child
 };
@@ -344,9 +384,19 @@ struct Flattener {
         auto lv = std::make_unique<Level>();
         lv->boxes.resize(ntri); lv->refs.resize(ntri);
         const size_t base = out.triangles.size();
-        out.triangles.resize(base + ntri); out.triangle_material.resize(base + ntri, mi); out.triangle_id.resize(base + ntri);
-        if (has_n || !out.tri_normals.empty()) { out.tri_normals.resize(base + ntri); out.tri_has_normals.resize(base + ntri, 0); }
-        for (size_t t = 0; t < ntri; t++) {
+        out.triangles.resize(base + ntri); out.triangle_material.resize(base + ntri); out.triangle_id.resize(base + ntri);
+        const bool track_n = has_n || !out.tri_normals.empty();
+        if (track_n) {
+            const size_t had = out.tri_has_normals.size();
+            out.tri_normals.resize(base + ntri); out.tri_has_normals.resize(base + ntri);
+            std::fill(out.tri_has_normals.begin() + had, out.tri_has_normals.begin() + base, (uint8_t)0);   // earlier meshes without normals
+        }
+        const uint32_t id0 = next_id; next_id += (uint32_t)ntri;
+        for (size_t t = 0; t < ntri; t++)
+            for (int v = 0; v < 3; v++)
+                if ((size_t)m.faces[3 * t + v] * 3 + 2 >= m.positions.size()) throw Error(LGB_ERR_INVALID, "mesh face references a vertex out of range");
+        lgb::Pool::get().for_range(ntri, 1 << 14, [&](size_t t0, size_t t1, size_t) {
+          for (size_t t = t0; t < t1; t++) {
             lgb_triangle& tr = out.triangles[base + t];
             const float* p0 = &m.positions[3 * (size_t)m.faces[3 * t]], *p1 = &m.positions[3 * (size_t)m.faces[3 * t + 1]], *p2 = &m.positions[3 * (size_t)m.faces[3 * t + 2]];
             Box b;
@@ -364,12 +414,17 @@ struct Flattener {
                     q.n2[k] = m.normals[3 * (size_t)m.normal_faces[3 * t + 2] + k];
                 }
                 out.tri_has_normals[base + t] = 1;
-            }
-            out.triangle_id[base + t] = next_id++;
+            } else if (track_n) out.tri_has_normals[base + t] = 0;
+            out.triangle_material[base + t] = mi;
+            out.triangle_id[base + t] = id0 + (uint32_t)t;
             lv->boxes[t] = b;
             lv->refs[t] = LGB_PRIM_REF(LGB_PRIM_TRIANGLE, base + t);
-        }
+          }
+        });
+        const auto tb = std::chrono::steady_clock::now();
         lv->tree.build(lv->boxes, ntri);
+        if (std::getenv("LGB_TIMING")) std::fprintf(stderr, "[flatten] mesh of %zu: tree.build %.1f ms\n", ntri,
+                                                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb).count());
         return lv;
     }
 
@@ -380,43 +435,82 @@ struct Flattener {
             throw Error(LGB_ERR_UNSUPPORTED, "group transforms / swap_backface are not on the device path yet (SURVEY §8f item 1)");
         }
         auto lv = std::make_unique<Level>();
-        for (const Aggregate::Node& n : ag.contents) {
-            Box b;
+        // Pass 1 (sequential, construction order): canonical ids, array slots, nested levels.
+        const size_t nn = ag.contents.size();
+        raw_vector<uint32_t> slot(nn), ids(nn);
+        const size_t s_base = out.spheres.size(), c_base = out.cuboids.size();
+        size_t n_s = 0, n_c = 0;
+        lv->boxes.resize(nn); lv->refs.resize(nn);
+        for (size_t i = 0; i < nn; i++) {
+            const Aggregate::Node& n = ag.contents[i];
             switch (n.kind) {
-            case Aggregate::Node::Sphere: {
-                lgb_sphere s; for (int k = 0; k < 3; k++) { s.center[k] = n.a[k]; double lo = n.a[k] - n.r, hi = n.a[k] + n.r; b.mn[k] = lo < hi ? lo : hi; b.mx[k] = lo < hi ? hi : lo; }   // sphere.rs:73-77
-                s.radius = n.r;
-                out.spheres.push_back(s); out.sphere_material.push_back(material_index(n.mat)); out.sphere_id.push_back(next_id++);
-                lv->refs.push_back(LGB_PRIM_REF(LGB_PRIM_SPHERE, out.spheres.size() - 1));
-                break;
-            }
+            case Aggregate::Node::Sphere: slot[i] = (uint32_t)(s_base + n_s++); ids[i] = next_id++; break;
             case Aggregate::Node::Cube:
-            case Aggregate::Node::Cuboid: {
-                lgb_cuboid c;
-                for (int k = 0; k < 3; k++) {
-                    double p0 = n.a[k], p1 = n.kind == Aggregate::Node::Cube ? n.a[k] + n.r : n.b[k];   // cuboid.rs:18-30
-                    c.min[k] = p0 < p1 ? p0 : p1; c.max[k] = p0 < p1 ? p1 : p0;                          // Bounds::new, bounds.rs:37-42
-                    b.mn[k] = c.min[k]; b.mx[k] = c.max[k];
-                }
-                out.cuboids.push_back(c); out.cuboid_material.push_back(material_index(n.mat)); out.cuboid_id.push_back(next_id++);
-                lv->refs.push_back(LGB_PRIM_REF(LGB_PRIM_CUBOID, out.cuboids.size() - 1));
-                break;
-            }
+            case Aggregate::Node::Cuboid: slot[i] = (uint32_t)(c_base + n_c++); ids[i] = next_id++; break;
             case Aggregate::Node::Mesh:
             case Aggregate::Node::Group: {
                 std::unique_ptr<Level> child = n.kind == Aggregate::Node::Mesh ? level_from_mesh(n.ref, n.has_mat, n.mat)
                                                                                 : level_from_aggregate(ag.groups[n.ref], false);
-                b = child->tree.nodes[child->tree.root].box;        // identity transform_bounds, bvh.rs:457-459
+                lv->boxes[i] = child->tree.nodes[child->tree.root].box;        // identity transform_bounds, bvh.rs:457-459
                 out.instances.push_back(lgb_instance{0, 1, 0, 0});
-                lv->refs.push_back(LGB_PRIM_REF(LGB_PRIM_INSTANCE, out.instances.size() - 1));
+                lv->refs[i] = LGB_PRIM_REF(LGB_PRIM_INSTANCE, out.instances.size() - 1);
                 lv->child_instance.push_back((uint32_t)out.instances.size() - 1);
                 lv->children.push_back(std::move(child));
                 break;
             }
             }
-            lv->boxes.push_back(b);
         }
+        if (out.spheres.size() != s_base || out.cuboids.size() != c_base)
+            throw Error(LGB_ERR_INVALID, "internal: primitive arrays grew while a level was being assembled");
+        out.spheres.resize(s_base + n_s); out.sphere_material.resize(s_base + n_s); out.sphere_id.resize(s_base + n_s);
+        out.cuboids.resize(c_base + n_c); out.cuboid_material.resize(c_base + n_c); out.cuboid_id.resize(c_base + n_c);
+        // Pass 2 (all threads): primitive records and bounds.  Materials are interned through a small per-chunk
+        // cache; a miss takes the lock.
+        std::mutex mat_mutex;
+        std::atomic<bool> failed{false};
+        std::string fail_msg; int fail_status = LGB_ERR_INVALID;
+        lgb::Pool::get().for_range(nn, 1 << 13, [&](size_t b0, size_t e0, size_t) {
+            struct Cached { Material m; uint32_t index; };
+            std::vector<Cached> cache;
+            auto intern = [&](const Material& m) -> uint32_t {
+                for (const Cached& c : cache)
+                    if (c.m.kind == m.kind && c.m.roughness == m.roughness && !std::memcmp(c.m.kd, m.kd, 24) && !std::memcmp(c.m.ks, m.ks, 24)) return c.index;
+                std::lock_guard<std::mutex> lock(mat_mutex);
+                const uint32_t idx = material_index(m);
+                if (cache.size() < 64) cache.push_back({m, idx});
+                return idx;
+            };
+            try {
+                for (size_t i = b0; i < e0; i++) {
+                    const Aggregate::Node& n = ag.contents[i];
+                    Box b;
+                    if (n.kind == Aggregate::Node::Sphere) {
+                        lgb_sphere s; for (int k = 0; k < 3; k++) { s.center[k] = n.a[k]; double lo = n.a[k] - n.r, hi = n.a[k] + n.r; b.mn[k] = lo < hi ? lo : hi; b.mx[k] = lo < hi ? hi : lo; }   // sphere.rs:73-77
+                        s.radius = n.r;
+                        out.spheres[slot[i]] = s; out.sphere_material[slot[i]] = intern(n.mat); out.sphere_id[slot[i]] = ids[i];
+                        lv->refs[i] = LGB_PRIM_REF(LGB_PRIM_SPHERE, slot[i]);
+                    } else if (n.kind == Aggregate::Node::Cube || n.kind == Aggregate::Node::Cuboid) {
+                        lgb_cuboid c;
+                        for (int k = 0; k < 3; k++) {
+                            double p0 = n.a[k], p1 = n.kind == Aggregate::Node::Cube ? n.a[k] + n.r : n.b[k];   // cuboid.rs:18-30
+                            c.min[k] = p0 < p1 ? p0 : p1; c.max[k] = p0 < p1 ? p1 : p0;                          // Bounds::new, bounds.rs:37-42
+                            b.mn[k] = c.min[k]; b.mx[k] = c.max[k];
+                        }
+                        out.cuboids[slot[i]] = c; out.cuboid_material[slot[i]] = intern(n.mat); out.cuboid_id[slot[i]] = ids[i];
+                        lv->refs[i] = LGB_PRIM_REF(LGB_PRIM_CUBOID, slot[i]);
+                    } else continue;
+                    lv->boxes[i] = b;
+                }
+            } catch (const Error& e) {
+                std::lock_guard<std::mutex> lock(mat_mutex);
+                if (!failed.exchange(true)) { fail_msg = e.what(); fail_status = e.status; }
+            }
+        });
+        if (failed.load()) throw Error(fail_status, fail_msg);
+        const auto tb = std::chrono::steady_clock::now();
         lv->tree.build(lv->boxes, lv->boxes.size());
+        if (std::getenv("LGB_TIMING")) std::fprintf(stderr, "[flatten] aggregate of %zu: tree.build %.1f ms\n", lv->boxes.size(),
+                                                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb).count());
         return lv;
     }
 
@@ -427,76 +521,13 @@ struct Flattener {
         n.a = 0; n.b = 0;
         return n;
     }
-    void emit_leaf_refs(const Level& lv, uint32_t first, uint32_t count, std::vector<uint32_t>& refs, std::vector<Box>& boxes) {
-        for (uint32_t i = 0; i < count; i++) { uint32_t p = lv.tree.order[first + i]; refs.push_back(lv.refs[p]); boxes.push_back(lv.boxes[p]); }
-    }
-    // Binned-SAH split of a fat reference leaf into a sub-tree (device-side optimisation only).
-    void emit_subtree(uint32_t* refs, Box* boxes, size_t n, int depth) {
-        Box bounds = Box::none(), cb = Box::none();
-        for (size_t i = 0; i < n; i++) { bounds.grow(boxes[i]); double c[3]; for (int k = 0; k < 3; k++) c[k] = 0.5 * (boxes[i].mn[k] + boxes[i].mx[k]); cb.grow_pt(c); }
-        const uint32_t me = (uint32_t)out.nodes.size();
-        out.nodes.push_back(node_box(bounds));
-        if (n <= opt.leaf_size || depth > 40) {
-            out.nodes[me].a = (uint32_t)out.prim_refs.size();
-            out.nodes[me].b = LGB_LEAF_FLAG | (uint32_t)n;
-            out.prim_refs.insert(out.prim_refs.end(), refs, refs + n);
-            return;
-        }
-        const int NB = 16;
-        double best_cost = std::numeric_limits<double>::infinity(); int best_axis = -1, best_bin = -1;
-        for (int ax = 0; ax < 3; ax++) {
-            double lo = cb.mn[ax], ext = cb.mx[ax] - cb.mn[ax];
-            if (!(ext > 0.0)) continue;
-            size_t cnt[NB] = {0}; Box bb[NB]; for (auto& b : bb) b = Box::none();
-            for (size_t i = 0; i < n; i++) {
-                double c = 0.5 * (boxes[i].mn[ax] + boxes[i].mx[ax]);
-                int k = (int)((c - lo) / ext * NB); if (k >= NB) k = NB - 1; if (k < 0) k = 0;
-                cnt[k]++; bb[k].grow(boxes[i]);
-            }
-            Box acc = Box::none(); size_t c0 = 0; double la[NB]; size_t lc[NB];
-            for (int i = 0; i < NB; i++) { acc.grow(bb[i]); c0 += cnt[i]; la[i] = c0 ? acc.area() : 0.0; lc[i] = c0; }
-            acc = Box::none(); size_t c1 = 0;
-            for (int i = NB - 1; i >= 1; i--) {
-                acc.grow(bb[i]); c1 += cnt[i];
-                if (lc[i - 1] == 0 || c1 == 0) continue;
-                double cost = la[i - 1] * (double)lc[i - 1] + acc.area() * (double)c1;
-                if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = i - 1; }
-            }
-        }
-        size_t nl;
-        int axis;
-        if (best_axis < 0) { nl = n / 2; axis = 0; }       // coincident centroids: split by position in the leaf
-        else {
-            axis = best_axis;
-            double lo = cb.mn[axis], ext = cb.mx[axis] - cb.mn[axis];
-            // stable partition keeps the reference's leaf order inside each side
-            std::vector<uint32_t> r2(n); std::vector<Box> b2(n); size_t a = 0;
-            std::vector<char> side(n);
-            for (size_t i = 0; i < n; i++) {
-                double c = 0.5 * (boxes[i].mn[axis] + boxes[i].mx[axis]);
-                int k = (int)((c - lo) / ext * NB); if (k >= NB) k = NB - 1; if (k < 0) k = 0;
-                side[i] = k <= best_bin;
-            }
-            for (size_t i = 0; i < n; i++) if (side[i]) { r2[a] = refs[i]; b2[a] = boxes[i]; a++; }
-            nl = a;
-            for (size_t i = 0; i < n; i++) if (!side[i]) { r2[a] = refs[i]; b2[a] = boxes[i]; a++; }
-            std::copy(r2.begin(), r2.end(), refs); std::copy(b2.begin(), b2.end(), boxes);
-        }
-        emit_subtree(refs, boxes, nl, depth + 1);
-        const uint32_t second = (uint32_t)out.nodes.size();
-        emit_subtree(refs + nl, boxes + nl, n - nl, depth + 1);
-        out.nodes[me].a = second; out.nodes[me].b = (uint32_t)axis;
-    }
     void emit_node(const Level& lv, int bi) {
         const BuildNode& bn = lv.tree.nodes[bi];
         if (bn.left < 0) {
-            std::vector<uint32_t> refs; std::vector<Box> boxes;
-            emit_leaf_refs(lv, bn.first, bn.count, refs, boxes);
-            if (opt.resplit && bn.count > opt.leaf_size) { emit_subtree(refs.data(), boxes.data(), refs.size(), 0); return; }
             lgb_node n = node_box(bn.box);
             n.a = (uint32_t)out.prim_refs.size(); n.b = LGB_LEAF_FLAG | bn.count;
             out.nodes.push_back(n);
-            out.prim_refs.insert(out.prim_refs.end(), refs.begin(), refs.end());
+            for (uint32_t i = 0; i < bn.count; i++) out.prim_refs.push_back(lv.refs[lv.tree.order[bn.first + i]]);    // bvh.rs:484
             return;
         }
         const uint32_t me = (uint32_t)out.nodes.size();
@@ -548,9 +579,12 @@ FlatScene flatten(const Scene& scene, const BuildOptions& opt) {
     FlatScene out;
     Flattener f{scene, opt, out, {}, 0};
     std::unique_ptr<Level> root = f.level_from_aggregate(scene.root, true);
+    const double t_levels = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     f.emit_level(*root);
+    if (std::getenv("LGB_TIMING")) std::fprintf(stderr, "[flatten] levels (reference HLBVH builds) %.1f ms, emit %.1f ms\n", t_levels,
+                                                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() - t_levels);
     out.prim_count = f.next_id;
-    out.flags = opt.resplit ? LGB_SCENE_RESPLIT : 0;
+    out.flags = 0;
     if (scene.lights.size() > LGB_MAX_LIGHTS) throw Error(LGB_ERR_UNSUPPORTED, "more than LGB_MAX_LIGHTS point lights");
     for (const Scene::Light& l : scene.lights) {
         lgb_light q; std::memcpy(q.position, l.position, 24); std::memcpy(q.intensity, l.intensity, 24); std::memcpy(q.falloff, l.falloff, 24);
@@ -699,10 +733,10 @@ void lgh_agg_rotate_axis(void* s, int ag, int axis, double deg) {
 void lgh_agg_rotate(void* s, int ag, double deg, const double* axis) { ((HostScene*)s)->agg(ag).rotate(deg, axis); }
 
 // Accel::from minus the upload: build + flatten on the host.
-void* lgh_flatten(void* s, int resplit, uint32_t leaf_size, int keep_levels) {
+void* lgh_flatten(void* s, int keep_levels) {
     FlatScene* out = nullptr;
     int rc = guarded([&] {
-        BuildOptions o; o.resplit = resplit != 0; o.leaf_size = leaf_size ? leaf_size : 4; o.keep_levels = keep_levels != 0;
+        BuildOptions o; o.keep_levels = keep_levels != 0;
         out = new FlatScene(flatten(((HostScene*)s)->scene, o));
     });
     (void)rc;

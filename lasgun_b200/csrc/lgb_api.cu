@@ -12,6 +12,7 @@
 #include <thread>
 
 #include "lgb_build.hpp"
+#include "lgb_parallel.hpp"
 #include "lgb_types.cuh"
 
 namespace lgb {
@@ -50,11 +51,20 @@ struct lgb_ctx {
     uint32_t tile_key[4] = {0, 0, 0, 0};   // w, h, rank, ranks of the cached tile list
     uint32_t tile_count = 0;
     int count_work = 0;                    // LGB_OPT_COUNT_WORK
+    void* staging = nullptr; size_t staging_cap = 0;   // pinned host buffer the scene arrays are assembled in
+    cudaError_t reserve_staging(size_t bytes) {
+        if (bytes <= staging_cap) return cudaSuccess;
+        if (staging) cudaFreeHost(staging);
+        staging = nullptr; staging_cap = 0;
+        cudaError_t e = cudaHostAlloc(&staging, bytes + bytes / 4, cudaHostAllocDefault);
+        if (e == cudaSuccess) staging_cap = bytes + bytes / 4;
+        return e;
+    }
 };
 
 struct lgb_scene {
     lgb_ctx* ctx = nullptr;
-    std::vector<void*> allocs;
+    void* arena = nullptr;     // one stream-ordered device allocation holding every array of the scene
     uint64_t bytes = 0;
     DevScene dev{};
     DevCamera cam{};
@@ -110,6 +120,13 @@ int lgb_init(int device, lgb_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(nullptr, cudaEventCreate(&c->ev0)); CU(nullptr, cudaEventCreate(&c->ev1)); CU(nullptr, cudaEventCreate(&c->ev2));
+    {   // scene arenas come from the stream-ordered pool and are kept cached between scenes (cudaMalloc/cudaFree cost ms)
+        cudaMemPool_t mp;
+        if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     *out = c;
     return LGB_OK;
 }
@@ -125,6 +142,7 @@ void lgb_shutdown(lgb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr}) b->release();
+    if (c->staging) cudaFreeHost(c->staging);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -136,38 +154,26 @@ void lgb_shutdown(lgb_ctx* c) {
 static inline float f32_down(double v) { float f = (float)v; if ((double)f > v) f = nextafterf(f, -INFINITY); return f; }
 static inline float f32_up(double v) { float f = (float)v; if ((double)f < v) f = nextafterf(f, INFINITY); return f; }
 
-template <class T>
-static int upload(lgb_scene* s, const std::vector<T>& host, const T** dev) {
-    *dev = nullptr;
-    if (host.empty()) return LGB_OK;
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, host.size() * sizeof(T));
-    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? fail(s->ctx, LGB_ERR_NOMEM, "scene upload: cudaMalloc failed") : cuda_fail(s->ctx, e, "cudaMalloc");
-    s->allocs.push_back(p);
-    s->bytes += host.size() * sizeof(T);
-    e = cudaMemcpyAsync(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, s->ctx->stream);
-    if (e != cudaSuccess) return cuda_fail(s->ctx, e, "cudaMemcpyAsync(H2D)");
-    *dev = reinterpret_cast<const T*>(p);
-    return LGB_OK;
-}
-
-static void make_prim_boxes(const lgb_scene_desc* d, std::vector<PrimBox>& prims) {
-    prims.clear(); prims.reserve(d->n_spheres + d->n_cuboids + d->n_triangles);
-    for (uint64_t i = 0; i < d->n_spheres; i++) {
-        const lgb_sphere& sp = d->spheres[i]; PrimBox b; b.type = LGB_PRIM_SPHERE; b.index = (uint32_t)i;
-        for (int k = 0; k < 3; k++) { double lo = sp.center[k] - sp.radius, hi = sp.center[k] + sp.radius; b.lo[k] = f32_down(std::min(lo, hi)); b.hi[k] = f32_up(std::max(lo, hi)); }
-        prims.push_back(b);
-    }
-    for (uint64_t i = 0; i < d->n_cuboids; i++) {
-        const lgb_cuboid& c = d->cuboids[i]; PrimBox b; b.type = LGB_PRIM_CUBOID; b.index = (uint32_t)i;
+static void make_prim_boxes(const lgb_scene_desc* d, raw_vector<PrimBox>& prims) {
+    const size_t ns = d->n_spheres, nc = d->n_cuboids, nt = d->n_triangles;
+    prims.resize(ns + nc + nt);
+    Pool& pool = Pool::get();
+    pool.for_range(ns, 1 << 14, [&](size_t b0, size_t e0, size_t) {
+        for (size_t i = b0; i < e0; i++) {
+            const lgb_sphere& sp = d->spheres[i]; PrimBox& b = prims[i]; b.type = LGB_PRIM_SPHERE; b.index = (uint32_t)i;
+            for (int k = 0; k < 3; k++) { double lo = sp.center[k] - sp.radius, hi = sp.center[k] + sp.radius; b.lo[k] = f32_down(std::min(lo, hi)); b.hi[k] = f32_up(std::max(lo, hi)); }
+        }
+    });
+    for (size_t i = 0; i < nc; i++) {
+        const lgb_cuboid& c = d->cuboids[i]; PrimBox& b = prims[ns + i]; b.type = LGB_PRIM_CUBOID; b.index = (uint32_t)i;
         for (int k = 0; k < 3; k++) { b.lo[k] = f32_down(std::min(c.min[k], c.max[k])); b.hi[k] = f32_up(std::max(c.min[k], c.max[k])); }
-        prims.push_back(b);
     }
-    for (uint64_t i = 0; i < d->n_triangles; i++) {
-        const lgb_triangle& t = d->triangles[i]; PrimBox b; b.type = LGB_PRIM_TRIANGLE; b.index = (uint32_t)i;
-        for (int k = 0; k < 3; k++) { b.lo[k] = std::min(t.p0[k], std::min(t.p1[k], t.p2[k])); b.hi[k] = std::max(t.p0[k], std::max(t.p1[k], t.p2[k])); }
-        prims.push_back(b);
-    }
+    pool.for_range(nt, 1 << 14, [&](size_t b0, size_t e0, size_t) {
+        for (size_t i = b0; i < e0; i++) {
+            const lgb_triangle& t = d->triangles[i]; PrimBox& b = prims[ns + nc + i]; b.type = LGB_PRIM_TRIANGLE; b.index = (uint32_t)i;
+            for (int k = 0; k < 3; k++) { b.lo[k] = std::min(t.p0[k], std::min(t.p1[k], t.p2[k])); b.hi[k] = std::max(t.p0[k], std::max(t.p1[k], t.p2[k])); }
+        }
+    });
 }
 
 extern "C" {
@@ -178,12 +184,12 @@ int lgb_build_probe(const lgb_scene_desc* d, lgb_build_info* out) {
     const uint32_t prim_count = (uint32_t)(d->n_spheres + d->n_cuboids + d->n_triangles);
     const int threads = (int)std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency()));
     auto t0 = std::chrono::steady_clock::now();
-    std::vector<uint32_t> rank;
-    out->ranks_ok = build_rank_tables(d, prim_count, threads, rank) ? 1 : 0;
+    std::vector<uint32_t> rank((size_t)8 * prim_count);
+    out->ranks_ok = build_rank_tables(d, prim_count, threads, rank.data()) ? 1 : 0;
     out->rank_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    std::vector<PrimBox> prims; make_prim_boxes(d, prims);
+    raw_vector<PrimBox> prims; make_prim_boxes(d, prims);
     BuiltBVH bvh;
-    if (build_sah(prims, 0.0f, threads, bvh)) return LGB_ERR_INVALID;
+    if (build_sah(prims.data(), prims.size(), 0.0f, threads, bvh)) return LGB_ERR_INVALID;
     out->nodes = (uint32_t)bvh.nodes.size(); out->max_depth = bvh.max_depth; out->prims = prim_count; out->build_ms = bvh.build_ms;
     // verify: every primitive in exactly one leaf, leaf boxes contain their primitives, child boxes nest
     std::vector<uint8_t> seen[3];
@@ -227,8 +233,7 @@ int lgb_build_probe(const lgb_scene_desc* d, lgb_build_info* out) {
 void lgb_scene_destroy(lgb_scene* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    cudaStreamSynchronize(s->ctx->stream);
-    for (void* p : s->allocs) cudaFree(p);
+    if (s->arena) cudaFreeAsync(s->arena, s->ctx->stream);      // stream-ordered: later work of this context is behind it
     delete s;
 }
 uint64_t lgb_scene_device_bytes(const lgb_scene* s) { return s ? s->bytes : 0; }
@@ -308,7 +313,6 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
 
     lgb_scene* s = new lgb_scene();
     s->ctx = ctx;
-    int rc = LGB_OK;
     auto bail = [&](int code) { lgb_scene_destroy(s); return code; };
 
     // ---- coordinate magnitude bound -> f32 error bound used by the conservative filters
@@ -324,89 +328,119 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     //      caller's reference tree (lgb_build.hpp); everything is stored in leaf order.
     const uint32_t prim_count = (uint32_t)(d->n_spheres + d->n_cuboids + d->n_triangles);
     if (prim_count == 0) return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: no primitives"));
-    const int threads = (int)std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency()));
-    std::vector<uint32_t> rank;
-    s->t_validate = ms_since(tc0);
-    auto tc1 = std::chrono::steady_clock::now();
-    if (!build_rank_tables(d, prim_count, threads, rank))
-        return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: primitive ids must be a permutation of 0..n-1 and every primitive must be referenced by exactly one leaf"));
+    const int threads = Pool::get().threads();
     const double padd = M * std::ldexp(1.0, -20);
     s->dev.err_abs = (float)padd;
-    s->t_rank = ms_since(tc1);
+    s->t_validate = ms_since(tc0);
     auto tc2 = std::chrono::steady_clock::now();
     BuiltBVH bvh;
     {
-        std::vector<PrimBox> prims; make_prim_boxes(d, prims);
-        int brc = build_sah(prims, (float)padd, threads, bvh);
+        raw_vector<PrimBox> prims; make_prim_boxes(d, prims);
+        int brc = build_sah(prims.data(), prims.size(), (float)padd, threads, bvh);
         if (brc == -2) return bail(fail(ctx, LGB_ERR_UNSUPPORTED, "lgb_scene_create: more than 16.7M primitives of one type"));
         if (brc) return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: BVH build failed"));
         if (bvh.max_depth + 1 > (uint32_t)kStackDepth) return bail(fail(ctx, LGB_ERR_UNSUPPORTED, "device BVH deeper than the 64-entry traversal stack"));
     }
     s->build_ms = bvh.build_ms;
     s->t_build = ms_since(tc2);
+
+    // ---- layout of the scene arena: every array at a 256-byte aligned offset of ONE allocation, assembled in
+    //      pinned host memory by all threads and moved with one H2D copy
+    static_assert(sizeof(HostNode) == 64, "node layout");
+    const size_t ns = d->n_spheres, ncb = d->n_cuboids, nt = d->n_triangles, nnodes = bvh.nodes.size();
+    const bool any_normals = nt && d->tri_normals;
+    size_t off = 0;
+    auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_nodes = place(nnodes * 64), o_rank = place((size_t)8 * prim_count * 4);
+    const size_t o_s32 = place(ns * 16), o_s64 = place(ns * 32), o_smat = place(ns * 4), o_sid = place(ns * 4);
+    const size_t o_c32 = place(ncb * 32), o_c64 = place(ncb * 48), o_cmat = place(ncb * 4), o_cid = place(ncb * 4);
+    const size_t o_tri = place(nt * 48), o_nrm = place(any_normals ? nt * 36 : 0);
+    const size_t o_mat = place(mats.size() * 8), o_lights = place(d->n_lights * 72);
+    const size_t arena_bytes = off;
+    {
+        cudaError_t e = ctx->reserve_staging(arena_bytes);
+        if (e != cudaSuccess) return bail(e == cudaErrorMemoryAllocation ? fail(ctx, LGB_ERR_NOMEM, "scene upload: pinned staging allocation failed") : cuda_fail(ctx, e, "cudaHostAlloc"));
+        e = cudaMallocAsync(&s->arena, arena_bytes, ctx->stream);
+        if (e != cudaSuccess) { s->arena = nullptr; return bail(e == cudaErrorMemoryAllocation ? fail(ctx, LGB_ERR_NOMEM, "scene upload: device allocation failed") : cuda_fail(ctx, e, "cudaMallocAsync")); }
+        s->bytes = arena_bytes;
+        // the previous scene's H2D copy out of the staging buffer is complete: lgb_scene_create synchronises before returning
+    }
+    char* H = (char*)ctx->staging;
+    char* D = (char*)s->arena;
+    auto tc1 = std::chrono::steady_clock::now();
+    if (!build_rank_tables(d, prim_count, threads, (uint32_t*)(H + o_rank)))
+        return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: primitive ids must be a permutation of 0..n-1 and every primitive must be referenced by exactly one leaf"));
+    s->t_rank = ms_since(tc1);
     auto tc3 = std::chrono::steady_clock::now();
-    {
-        static_assert(sizeof(HostNode) == 64, "node layout");
-        std::vector<float4> nodes(4 * bvh.nodes.size());
-        std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size() * sizeof(HostNode));
-        if ((rc = upload(s, nodes, &s->dev.nodes))) return bail(rc);
-        s->dev.n_nodes = (uint32_t)bvh.nodes.size();
-        if ((rc = upload(s, rank, &s->dev.rank))) return bail(rc);
-        s->dev.prim_count = prim_count;
-    }
-    if (d->n_spheres) {
-        const std::vector<uint32_t>& ord = bvh.order[LGB_PRIM_SPHERE];
-        std::vector<float4> s32(d->n_spheres); std::vector<double> s64(4 * d->n_spheres);
-        std::vector<uint32_t> m(d->n_spheres), id(d->n_spheres);
-        for (uint64_t j = 0; j < d->n_spheres; j++) {
-            const uint32_t i = ord[j];
-            const lgb_sphere& sp = d->spheres[i];
-            s32[j] = make_float4((float)sp.center[0], (float)sp.center[1], (float)sp.center[2], f32_up(std::fabs(sp.radius)));
-            s64[4 * j] = sp.center[0]; s64[4 * j + 1] = sp.center[1]; s64[4 * j + 2] = sp.center[2]; s64[4 * j + 3] = sp.radius;
-            m[j] = d->sphere_material[i]; id[j] = d->sphere_id[i];
-        }
-        if ((rc = upload(s, s32, &s->dev.sph32)) || (rc = upload(s, s64, &s->dev.sph64)) || (rc = upload(s, m, &s->dev.sph_mat)) || (rc = upload(s, id, &s->dev.sph_id))) return bail(rc);
-    }
-    if (d->n_cuboids) {
-        const std::vector<uint32_t>& ord = bvh.order[LGB_PRIM_CUBOID];
-        std::vector<float4> c32(2 * d->n_cuboids); std::vector<double> c64(6 * d->n_cuboids);
-        std::vector<uint32_t> m(d->n_cuboids), id(d->n_cuboids);
-        for (uint64_t j = 0; j < d->n_cuboids; j++) {
-            const uint32_t i = ord[j];
-            const lgb_cuboid& c = d->cuboids[i];
-            c32[2 * j] = make_float4(f32_down(c.min[0] - padd), f32_down(c.min[1] - padd), f32_down(c.min[2] - padd), 0.f);
-            c32[2 * j + 1] = make_float4(f32_up(c.max[0] + padd), f32_up(c.max[1] + padd), f32_up(c.max[2] + padd), 0.f);
-            for (int k = 0; k < 3; k++) { c64[6 * j + k] = c.min[k]; c64[6 * j + 3 + k] = c.max[k]; }
-            m[j] = d->cuboid_material[i]; id[j] = d->cuboid_id[i];
-        }
-        if ((rc = upload(s, c32, &s->dev.cub32)) || (rc = upload(s, c64, &s->dev.cub64)) || (rc = upload(s, m, &s->dev.cub_mat)) || (rc = upload(s, id, &s->dev.cub_id))) return bail(rc);
-    }
-    if (d->n_triangles) {
-        const std::vector<uint32_t>& ord = bvh.order[LGB_PRIM_TRIANGLE];
-        std::vector<float4> t(3 * d->n_triangles);
-        std::vector<float> nrm;
-        for (uint64_t j = 0; j < d->n_triangles; j++) {
-            const uint32_t i = ord[j];
-            const lgb_triangle& tr = d->triangles[i];
-            uint32_t ni = kNoNormals;
-            if (d->tri_normals && (!d->tri_has_normals || d->tri_has_normals[i])) {
-                ni = (uint32_t)(nrm.size() / 9);
-                const lgb_tri_normals& q = d->tri_normals[i];
-                nrm.insert(nrm.end(), {q.n0[0], q.n0[1], q.n0[2], q.n1[0], q.n1[1], q.n1[2], q.n2[0], q.n2[1], q.n2[2]});
+    Pool& pool = Pool::get();
+    pool.for_range(nnodes, 1 << 14, [&](size_t b, size_t e, size_t) { std::memcpy(H + o_nodes + b * 64, bvh.nodes.data() + b, (e - b) * 64); });
+    s->dev.nodes = (const float4*)(D + o_nodes); s->dev.n_nodes = (uint32_t)nnodes;
+    s->dev.rank = (const uint32_t*)(D + o_rank); s->dev.prim_count = prim_count;
+    if (ns) {
+        const uint32_t* ord = bvh.order[LGB_PRIM_SPHERE].data();
+        float4* s32 = (float4*)(H + o_s32); double* s64 = (double*)(H + o_s64); uint32_t* m = (uint32_t*)(H + o_smat); uint32_t* id = (uint32_t*)(H + o_sid);
+        pool.for_range(ns, 1 << 14, [&](size_t b, size_t e, size_t) {
+            for (size_t j = b; j < e; j++) {
+                const uint32_t i = ord[j];
+                const lgb_sphere& sp = d->spheres[i];
+                s32[j] = make_float4((float)sp.center[0], (float)sp.center[1], (float)sp.center[2], f32_up(std::fabs(sp.radius)));
+                s64[4 * j] = sp.center[0]; s64[4 * j + 1] = sp.center[1]; s64[4 * j + 2] = sp.center[2]; s64[4 * j + 3] = sp.radius;
+                m[j] = d->sphere_material[i]; id[j] = d->sphere_id[i];
             }
-            float4 a = make_float4(tr.p0[0], tr.p0[1], tr.p0[2], 0.f), b = make_float4(tr.p1[0], tr.p1[1], tr.p1[2], 0.f), c = make_float4(tr.p2[0], tr.p2[1], tr.p2[2], 0.f);
-            std::memcpy(&a.w, &d->triangle_id[i], 4); std::memcpy(&b.w, &d->triangle_material[i], 4); std::memcpy(&c.w, &ni, 4);
-            t[3 * j] = a; t[3 * j + 1] = b; t[3 * j + 2] = c;
-        }
-        if ((rc = upload(s, t, &s->dev.tri)) || (rc = upload(s, nrm, &s->dev.tri_nrm))) return bail(rc);
+        });
+        s->dev.sph32 = (const float4*)(D + o_s32); s->dev.sph64 = (const double*)(D + o_s64);
+        s->dev.sph_mat = (const uint32_t*)(D + o_smat); s->dev.sph_id = (const uint32_t*)(D + o_sid);
     }
-    if ((rc = upload(s, mats, &s->dev.materials))) return bail(rc);
+    if (ncb) {
+        const uint32_t* ord = bvh.order[LGB_PRIM_CUBOID].data();
+        float4* c32 = (float4*)(H + o_c32); double* c64 = (double*)(H + o_c64); uint32_t* m = (uint32_t*)(H + o_cmat); uint32_t* id = (uint32_t*)(H + o_cid);
+        pool.for_range(ncb, 1 << 14, [&](size_t b, size_t e, size_t) {
+            for (size_t j = b; j < e; j++) {
+                const uint32_t i = ord[j];
+                const lgb_cuboid& c = d->cuboids[i];
+                c32[2 * j] = make_float4(f32_down(c.min[0] - padd), f32_down(c.min[1] - padd), f32_down(c.min[2] - padd), 0.f);
+                c32[2 * j + 1] = make_float4(f32_up(c.max[0] + padd), f32_up(c.max[1] + padd), f32_up(c.max[2] + padd), 0.f);
+                for (int k = 0; k < 3; k++) { c64[6 * j + k] = c.min[k]; c64[6 * j + 3 + k] = c.max[k]; }
+                m[j] = d->cuboid_material[i]; id[j] = d->cuboid_id[i];
+            }
+        });
+        s->dev.cub32 = (const float4*)(D + o_c32); s->dev.cub64 = (const double*)(D + o_c64);
+        s->dev.cub_mat = (const uint32_t*)(D + o_cmat); s->dev.cub_id = (const uint32_t*)(D + o_cid);
+    }
+    if (nt) {
+        const uint32_t* ord = bvh.order[LGB_PRIM_TRIANGLE].data();
+        float4* t = (float4*)(H + o_tri); float* nrm = (float*)(H + o_nrm);
+        pool.for_range(nt, 1 << 14, [&](size_t b0, size_t e0, size_t) {
+            for (size_t j = b0; j < e0; j++) {
+                const uint32_t i = ord[j];
+                const lgb_triangle& tr = d->triangles[i];
+                uint32_t ni = kNoNormals;
+                if (any_normals && (!d->tri_has_normals || d->tri_has_normals[i])) {      // normals slot j (leaf order)
+                    ni = (uint32_t)j;
+                    const lgb_tri_normals& q = d->tri_normals[i];
+                    float* o = nrm + 9 * j;
+                    for (int k = 0; k < 3; k++) { o[k] = q.n0[k]; o[3 + k] = q.n1[k]; o[6 + k] = q.n2[k]; }
+                } else if (any_normals) std::memset(nrm + 9 * j, 0, 36);
+                float4 a = make_float4(tr.p0[0], tr.p0[1], tr.p0[2], 0.f), b = make_float4(tr.p1[0], tr.p1[1], tr.p1[2], 0.f), c = make_float4(tr.p2[0], tr.p2[1], tr.p2[2], 0.f);
+                std::memcpy(&a.w, &d->triangle_id[i], 4); std::memcpy(&b.w, &d->triangle_material[i], 4); std::memcpy(&c.w, &ni, 4);
+                t[3 * j] = a; t[3 * j + 1] = b; t[3 * j + 2] = c;
+            }
+        });
+        s->dev.tri = (const float4*)(D + o_tri);
+        s->dev.tri_nrm = any_normals ? (const float*)(D + o_nrm) : nullptr;
+    }
+    std::memcpy(H + o_mat, mats.data(), mats.size() * 8);
+    s->dev.materials = (const double*)(D + o_mat);
     {
-        std::vector<double> l(9 * d->n_lights);
+        double* l = (double*)(H + o_lights);
         for (uint64_t i = 0; i < d->n_lights; i++)
             for (int k = 0; k < 3; k++) { l[9 * i + k] = d->lights[i].position[k]; l[9 * i + 3 + k] = d->lights[i].intensity[k]; l[9 * i + 6 + k] = d->lights[i].falloff[k]; }
-        if ((rc = upload(s, l, &s->dev.lights))) return bail(rc);
+        s->dev.lights = (const double*)(D + o_lights);
         s->dev.n_lights = (uint32_t)d->n_lights;
+    }
+    {
+        cudaError_t e = cudaMemcpyAsync(D, H, arena_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)"); return bail(LGB_ERR_CUDA); }
     }
     for (int k = 0; k < 3; k++) {
         s->cam.origin[k] = d->camera.origin[k]; s->cam.view[k] = d->camera.view[k]; s->cam.up[k] = d->camera.up[k]; s->cam.aux[k] = d->camera.aux[k];
@@ -417,7 +451,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     s->cam.sample_distance = d->camera.sample_distance;
     s->cam.root = d->camera.supersampling_root;
     s->shade.bg_scale = d->bg_scale;
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);     // host vectors die at scope end
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);     // the staging buffer is free for the next scene
     if (e != cudaSuccess) { cuda_fail(ctx, e, "scene upload"); return bail(LGB_ERR_CUDA); }
     s->t_convert_upload = ms_since(tc3);
     s->t_total = ms_since(tc0);

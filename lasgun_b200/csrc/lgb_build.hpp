@@ -36,10 +36,10 @@ struct BuiltBVH {
 };
 
 // Binned-SAH build over all primitives (multi-threaded).  `pad` widens every box (see lgb_api.cu).
-int build_sah(std::vector<PrimBox>& prims, float pad, int threads, BuiltBVH& out);
+int build_sah(const PrimBox* prims, size_t n, float pad, int threads, BuiltBVH& out);
 
 // rank[o * prim_count + id]: position of canonical primitive `id` in the reference's traversal order
 // for direction octant o (bit a set <=> dir_is_neg[a], bvh.rs:463).  Returns false on a malformed tree.
-bool build_rank_tables(const lgb_scene_desc* d, uint32_t prim_count, int threads, std::vector<uint32_t>& rank);
+bool build_rank_tables(const lgb_scene_desc* d, uint32_t prim_count, int threads, uint32_t* rank);   // rank: 8 * prim_count words
 
 }  // namespace lgb

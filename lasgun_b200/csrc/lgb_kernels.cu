@@ -149,8 +149,18 @@ struct Trav {                 // resumable traversal state of one ray
 
 // Inner loop of the while-while traversal: descend interior nodes until `cur` is a leaf or kDone.
 // OCT < 8: every ray of the warp has that direction octant (slab_oct); OCT == 8: mixed warp (slab2).
-template <int OCT, bool STATS>
-__device__ __forceinline__ void node_loop(const DevScene& S, const RayF& f, float best_up, uint32_t& cur, int& sp, uint32_t* stack, LocalCounters& lc) {
+// TSTACK (closest-hit rays): the entry distance of a deferred child is kept beside it, and a popped entry
+// that now starts beyond the best hit is dropped without fetching its node.
+template <bool TSTACK>
+__device__ __forceinline__ uint32_t stack_pop(int& sp, const uint32_t* stack, const float* tstack, float best_up) {
+    while (sp) {
+        --sp;
+        if (!TSTACK || tstack[sp] <= best_up) return stack[sp];
+    }
+    return kDone;
+}
+template <int OCT, bool STATS, bool TSTACK>
+__device__ __forceinline__ void node_loop(const DevScene& S, const RayF& f, float best_up, uint32_t& cur, int& sp, uint32_t* stack, float* tstack, LocalCounters& lc) {
     while (!(cur & kLeafBit) && cur != kDone) {
         const float4* np = S.nodes + 4 * (size_t)cur;
         const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
@@ -169,10 +179,11 @@ __device__ __forceinline__ void node_loop(const DevScene& S, const RayF& f, floa
         if (h0 && h1) {
             const bool swap = tn1 < tn0;
             cur = swap ? c1 : c0;
+            if (TSTACK) tstack[sp] = swap ? tn0 : tn1;
             stack[sp++] = swap ? c0 : c1;
         } else if (h0) cur = c0;
         else if (h1) cur = c1;
-        else cur = sp ? stack[--sp] : kDone;
+        else cur = stack_pop<TSTACK>(sp, stack, tstack, best_up);
     }
 }
 
@@ -180,22 +191,22 @@ __device__ __forceinline__ void node_loop(const DevScene& S, const RayF& f, floa
 // `refill_below` lanes of the warp are still traversing (returns false: the caller tops the warp up with
 // new rays and calls again; persistent threads with dynamic fetch).
 template <bool ANYHIT, bool STATS, bool REFILL>
-__device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& ray, const RayF& f, Trav& T, uint32_t* stack, double tmax,
+__device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& ray, const RayF& f, Trav& T, uint32_t* stack, float* tstack, double tmax,
                                          LocalCounters& lc, int refill_below, unsigned octw) {
     Hit& best = T.best;
     float& best_tf = T.best_tf; float& best_up = T.best_up;
     uint32_t& cur = T.cur; int& sp = T.sp;
     for (;;) {
         switch (octw) {        // warp-uniform: the octant shared by every ray of the warp, or 8 (mixed)
-        case 0: node_loop<0, STATS>(S, f, best_up, cur, sp, stack, lc); break;
-        case 1: node_loop<1, STATS>(S, f, best_up, cur, sp, stack, lc); break;
-        case 2: node_loop<2, STATS>(S, f, best_up, cur, sp, stack, lc); break;
-        case 3: node_loop<3, STATS>(S, f, best_up, cur, sp, stack, lc); break;
-        case 4: node_loop<4, STATS>(S, f, best_up, cur, sp, stack, lc); break;
-        case 5: node_loop<5, STATS>(S, f, best_up, cur, sp, stack, lc); break;
-        case 6: node_loop<6, STATS>(S, f, best_up, cur, sp, stack, lc); break;
-        case 7: node_loop<7, STATS>(S, f, best_up, cur, sp, stack, lc); break;
-        default: node_loop<8, STATS>(S, f, best_up, cur, sp, stack, lc); break;
+        case 0: node_loop<0, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 1: node_loop<1, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 2: node_loop<2, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 3: node_loop<3, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 4: node_loop<4, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 5: node_loop<5, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 6: node_loop<6, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 7: node_loop<7, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        default: node_loop<8, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
         }
         if (cur == kDone) return true;
         {
@@ -262,7 +273,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& ray, co
                 }
             }
         }
-        cur = sp ? stack[--sp] : kDone;
+        cur = stack_pop<!ANYHIT>(sp, stack, tstack, best_up);
         if (REFILL && __popc(__activemask()) < refill_below) return cur == kDone;
     }
 }
@@ -271,8 +282,9 @@ template <bool ANYHIT, bool STATS>
 __device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalCounters& lc) {
     const RayF f = make_rayf(ray, S.err_abs);
     uint32_t stack[kStackDepth];      // depth is bounded at scene creation (lgb_api.cu), so pushes are unchecked
+    float tstack[ANYHIT ? 1 : kStackDepth];
     Trav T; T.init(tmax);
-    trav_run<ANYHIT, STATS, false>(S, ray, f, T, stack, tmax, lc, 0, 8u);
+    trav_run<ANYHIT, STATS, false>(S, ray, f, T, stack, tstack, tmax, lc, 0, 8u);
     return T.best;
 }
 
@@ -558,6 +570,7 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, Dev
     LocalCounters lc = {};
     unsigned int hits = 0, primary = 0;
     uint32_t stack[kStackDepth];
+    float tstack[kStackDepth];
     Ray64 ray; RayF f; Trav T;
     uint64_t g = 0;
     bool active = false, drained = false;
@@ -589,7 +602,7 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, Dev
         const unsigned oct0 = __shfl_sync(0xFFFFFFFFu, f.oct, __ffs(amask) - 1);
         const unsigned octw = __all_sync(0xFFFFFFFFu, !active || f.oct == oct0) ? oct0 : 8u;
         if (active) {
-            const bool done = trav_run<false, STATS, true>(S, ray, f, T, stack, CUDART_INF, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
+            const bool done = trav_run<false, STATS, true>(S, ray, f, T, stack, tstack, CUDART_INF, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
             if (done) {
                 const bool hit = T.best.ref != LGB_MISS;
                 V.hit_t[g] = hit ? T.best.t : CUDART_INF; V.hit_ref[g] = T.best.ref;
@@ -753,7 +766,7 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevW
         const unsigned oct0 = __shfl_sync(0xFFFFFFFFu, f.oct, __ffs(amask) - 1);
         const unsigned octw = __all_sync(0xFFFFFFFFu, !active || f.oct == oct0) ? oct0 : 8u;
         if (active) {
-            const bool done = trav_run<true, STATS, true>(S, ray, f, T, stack, 1.0, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
+            const bool done = trav_run<true, STATS, true>(S, ray, f, T, stack, nullptr, 1.0, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
             if (done) {
                 if (T.best.ref != LGB_MISS) { atomicOr(&V.occl[g], 1u << light); occluded++; }
                 if (record) V.occluder[(size_t)light * W.n_pixels + g / W.spp] = T.best.ref;

@@ -12,10 +12,10 @@ from .api import Film, Scene
 class Accel:
     """`Accel::from(&scene)` (lib.rs:42, bvh.rs:135): the scene's BVH, flattened and resident on the GPU."""
 
-    def __init__(self, scene: Scene, ctx: N.Context | None = None, resplit=True, leaf_size=4):
+    def __init__(self, scene: Scene, ctx: N.Context | None = None):
         self.scene = scene
         self.ctx = ctx or N.default_context()
-        self.flat = N.FlatScene(scene, resplit=resplit, leaf_size=leaf_size)
+        self.flat = N.FlatScene(scene)
         self.dev = N.DeviceScene(self.ctx, self.flat)
 
     @staticmethod

@@ -26,8 +26,8 @@ for name, mk in CASES:
     sc, (w, h) = mk()
     o = po.OracleScene(sc)
     t0 = time.time(); ref = o.capture(w, h, aov=True, counters=True); t_ref = time.time() - t0
-    for resplit in (False, True):
-        flat = N.FlatScene(sc, resplit=resplit)
+    for resplit in (False,):
+        flat = N.FlatScene(sc)
         dev = N.DeviceScene(ctx, flat)
         out = dev.capture_aov(w, h)
         rgba, st = dev.capture(w, h)

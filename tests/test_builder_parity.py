@@ -30,7 +30,7 @@ CASES = {
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_reference_tree_identical(native, oracle, name):
     sc = CASES[name]()
-    flat = native.FlatScene(sc, resplit=False, keep_levels=True)
+    flat = native.FlatScene(sc, keep_levels=True)
     o = oracle.OracleScene(sc)
     assert flat.prim_count == o.prim_count
     paths = list(oracle_levels(o))
@@ -54,21 +54,17 @@ def _walk(nodes, refs, i, depth, out):
         _walk(nodes, refs, c, depth + 1, out)
 
 
-@pytest.mark.parametrize("resplit", [False, True])
-def test_flat_scene_structure(native, resplit):
-    """Every primitive is referenced exactly once; child boxes nest; re-split leaves are small."""
+def test_flat_scene_structure(native):
+    """Every primitive is referenced exactly once; child boxes nest; leaves keep the reference's size bound."""
     sc = scenes.mixed4k(mesh_n=40, nspheres=3000)[0]
-    flat = native.FlatScene(sc, resplit=resplit, leaf_size=4)
+    flat = native.FlatScene(sc)
     nodes, refs = flat.nodes(), flat.prim_refs()
     d = flat.desc
     assert len(refs) == d.n_spheres + d.n_cuboids + d.n_triangles + d.n_instances
     assert len(np.unique(refs)) == len(refs)
     out = {"leaves": [], "depth": 0}
     _walk(nodes, refs, 0, 0, out)
-    if resplit:
-        assert max(c for _, c in out["leaves"]) <= 4
-    else:
-        assert max(c for _, c in out["leaves"]) <= 254
+    assert max(c for _, c in out["leaves"]) <= 254          # bvh.rs:289
 
 
 def test_reference_hazards_are_errors(native):

@@ -23,8 +23,8 @@ def one_prim_scene(kind, *args):
     return sc
 
 
-def trace(native, gpu_ctx, sc, o, d, resplit=False):
-    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc, resplit=resplit))
+def trace(native, gpu_ctx, sc, o, d):
+    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
     ids, t, ng, ns = dev.trace_rays(np.array([list(o) + list(d)], np.float64))
     dev.destroy()
     return int(ids[0]), float(t[0]), ng[0], ns[0]
@@ -69,13 +69,12 @@ SMALL = {
 }
 
 
-@pytest.mark.parametrize("resplit", [False, True])
 @pytest.mark.parametrize("name", sorted(SMALL))
-def test_small_config_parity(native, oracle, gpu_ctx, name, resplit):
+def test_small_config_parity(native, oracle, gpu_ctx, name):
     sc, (w, h) = SMALL[name]()
     o = oracle.OracleScene(sc)
     ref = o.capture(w, h, aov=True)
-    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc, resplit=resplit))
+    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
     out = dev.capture_aov(w, h)
     rgba, st = dev.capture(w, h)
     dev.destroy()
@@ -92,7 +91,7 @@ def test_small_config_parity(native, oracle, gpu_ctx, name, resplit):
     assert a["occl_diff"] == 0, a
     f = parity.film_report(rgba, ref["rgba"])
     assert f["alpha_equal"] and f["within_1_frac"] >= 0.999, f
-    assert f["identical_frac"] >= 0.9999, f                # stronger than the bar: f64 shading in reference order
+    assert f["identical_frac"] >= 0.9999, f                # stronger than the bar: shading is f64 end to end
     assert np.array_equal(rgba, out["rgba"])               # all-shadow-rays (AOV) mode renders the same film
     assert st["primary_rays"] == w * h * spp and st["stack_overflow"] == 0
     assert st["shadow_rays"] == len(sc.lights) * st["primary_hits"]
@@ -109,11 +108,10 @@ FULL = {
 @pytest.mark.parametrize("name", sorted(FULL))
 def test_full_size_sampled_against_oracle(native, oracle, gpu_ctx, name):
     """BASELINE.json's full sizes: the oracle renders every n-th pixel (capture_subset(0, n),
-    lib.rs:110) of the full-size scene; the device film must agree at those pixels, and the
-    film from the reference's own leaves must equal the film from re-split leaves everywhere."""
+    lib.rs:110) of the full-size scene; the device film must agree at those pixels."""
     mk, n = FULL[name]
     sc, (w, h) = mk()
-    flat = native.FlatScene(sc, resplit=True)
+    flat = native.FlatScene(sc)
     dev = native.DeviceScene(gpu_ctx, flat)
     rgba, st = dev.capture(w, h)
     dev.destroy()
@@ -122,11 +120,6 @@ def test_full_size_sampled_against_oracle(native, oracle, gpu_ctx, name):
     idx = np.arange(0, w * h, n)
     f = parity.film_report(rgba.reshape(-1, 4)[idx][None], ref[idx][None])
     assert f["alpha_equal"] and f["within_1_frac"] >= 0.999 and f["identical_frac"] >= 0.999, f
-    if name in ("C1_simple", "C3_cornell"):
-        dev2 = native.DeviceScene(gpu_ctx, native.FlatScene(sc, resplit=False))
-        rgba2, _ = dev2.capture(w, h)
-        dev2.destroy()
-        assert np.array_equal(rgba, rgba2)
 
 
 def test_capture_subset_union_equals_capture(native, gpu_ctx):
