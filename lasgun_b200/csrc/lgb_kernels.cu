@@ -496,7 +496,7 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 }
 
 #ifndef LGB_MIN_BLOCKS
-#define LGB_MIN_BLOCKS 3
+#define LGB_MIN_BLOCKS 4
 #endif
 
 // ================================================================== wavefront pipeline
@@ -540,7 +540,10 @@ __device__ __forceinline__ unsigned long long warp_fetch(CounterT* counter, bool
 // exclusive scan over the warps, ONE global atomic per block and queue (same-address atomics serialise, and a
 // warp-by-warp append would interleave the warps of different blocks, which destroys ray coherence downstream).
 // Every thread of the block must call it (it synchronises); `mine` marks the threads that append `value`.
-constexpr int kAppendThreads = 512;
+#ifndef LGB_APPEND_THREADS
+#define LGB_APPEND_THREADS 512
+#endif
+constexpr int kAppendThreads = LGB_APPEND_THREADS;
 struct AppendScratch { uint32_t warp_off[kAppendThreads / 32]; uint32_t base; };
 __device__ __forceinline__ void block_append(AppendScratch& sc, bool mine, uint32_t value, uint32_t* queue, uint32_t* count) {
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -789,7 +792,10 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevW
     }
 }
 
-__global__ void __launch_bounds__(256) k_shade(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
+#ifndef LGB_SHADE_MIN_BLOCKS
+#define LGB_SHADE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, LGB_SHADE_MIN_BLOCKS) k_shade(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
     const double PI = 3.14159265358979323846264338327950288;
     const uint64_t total = W.n_pixels * W.spp;
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
