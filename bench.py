@@ -137,19 +137,42 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def algorithmic_work(st, w, h, spp, n_lights):
-    """Algorithmic FP32 ops and bytes of one frame from the device's own work counters (SURVEY §8d)."""
-    f, e = st["filter_tests"], st["exact_tests"]
-    ops = st["node_tests"] * OPS["node"]
+def traversal_work(node_fetches, f, e):
+    """Algorithmic FP32 ops and bytes of BVH traversal (SURVEY §8d): one node fetch = two slab tests of 26 ops / 32 B each;
+    f / e = primitive tests started / carried to the hit path, per type (sphere, cuboid, triangle)."""
+    ops = 2 * node_fetches * OPS["node"]
     ops += (f[0] - e[0]) * OPS["sphere"][0] + e[0] * OPS["sphere"][1]
     ops += f[1] * OPS["cuboid"]
     ops += (f[2] - e[2]) * OPS["tri"][0] + e[2] * OPS["tri"][1]
+    byts = 2 * node_fetches * BYTES["node"] + f[0] * BYTES["sphere"] + f[1] * BYTES["cuboid"] + f[2] * BYTES["tri"]
+    return ops, byts
+
+
+def algorithmic_work(st, w, h, spp, n_lights):
+    """Algorithmic FP32 ops and bytes of one frame from the device's own work counters (SURVEY §8d)."""
+    ops, byts = traversal_work(st["node_tests"], st["filter_tests"], st["exact_tests"])
     hits, prim = st["primary_hits"], st["primary_rays"]
     ops += prim * OPS["camera"] + hits * OPS["hit"] + st["shadow_rays_traced"] * OPS["light"] + hits * OPS["ambient"]
     ops += (prim - hits) * OPS["background"] + w * h * OPS["film"]
-    byts = st["node_tests"] * BYTES["node"] + f[0] * BYTES["sphere"] + f[1] * BYTES["cuboid"] + f[2] * BYTES["tri"]
-    byts += (f[0] + f[1] + f[2]) * BYTES["ref"] + w * h * BYTES["film"]
+    byts += w * h * BYTES["film"]
     return ops, byts
+
+
+def primary_kernel_work(st):
+    """The dominant kernel (k_primary: camera ray + closest-hit traversal of every sample)."""
+    ops, byts = traversal_work(st["primary_node_tests"], st["primary_filter_tests"], st["primary_exact_tests"])
+    return ops + st["primary_rays"] * OPS["camera"], byts
+
+
+def ncu_traffic(workload, world):
+    """dram read + write bytes of one k_primary launch from the committed `ncu --set full` capture (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        e = t.get(workload)
+        return (e["k_primary_dram_bytes"] / world) if e and world == 1 else None
+    except Exception:
+        return None
 
 
 def run_gpu(args):
@@ -189,13 +212,15 @@ def run_gpu(args):
     ctx.set_count_work(True)
     st = dev.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream, want_stats=True)
     ctx.set_count_work(False)
-    cnt = torch.tensor([st["primary_rays"], st["primary_hits"], st["shadow_rays_traced"], st["node_tests"]] + st["filter_tests"] + st["exact_tests"],
+    cnt = torch.tensor([st["primary_rays"], st["primary_hits"], st["shadow_rays_traced"], st["node_tests"]] + st["filter_tests"] + st["exact_tests"]
+                       + [st["primary_node_tests"]] + st["primary_filter_tests"] + st["primary_exact_tests"] + [st["shadow_cache_hits"]],
                        dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(cnt)
     tot = cnt.tolist()
     frame = {"primary_rays": tot[0], "primary_hits": tot[1], "shadow_rays_traced": tot[2], "node_tests": tot[3],
-             "filter_tests": tot[4:7], "exact_tests": tot[7:10]}
+             "filter_tests": tot[4:7], "exact_tests": tot[7:10], "primary_node_tests": tot[10], "primary_filter_tests": tot[11:14],
+             "primary_exact_tests": tot[14:17], "shadow_cache_hits": tot[17]}
     rays_frame = frame["primary_rays"] + nl * frame["primary_hits"]
 
     for _ in range(args.warmup):
@@ -222,13 +247,15 @@ def run_gpu(args):
     value = rays_frame / (ms_per_step * 1e-3) / 1e6
 
     # render-kernel time alone (CUDA events inside the library, on its launch stream), a few frames
-    for _ in range(3):
+    phase_ms = []
+    for _ in range(max(3, args.steps)):
         s2 = dev.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream, want_stats=True)
-        kern_ms.append(s2["render_ms"])
-    kms = torch.tensor([statistics.median(kern_ms)], device="cuda")
+        kern_ms.append(s2["render_ms"]); phase_ms.append(s2["kernel_ms"])
+    kms = torch.tensor([statistics.median(kern_ms)] + [sum(p[i] for p in phase_ms) / len(phase_ms) for i in range(6)], device="cuda")
     if world > 1:
         dist.all_reduce(kms, op=dist.ReduceOp.MAX)
-    kernel_ms = float(kms.item())
+    kernel_ms = float(kms[0].item())
+    phases = [float(v) for v in kms[1:].tolist()]      # average launch duration per phase, CUDA events on the launch stream
 
     # e2e through the C ABI with host buffers (rank-local frame share; film gathered on the host side of rank 0)
     host_film = np.zeros((h, w, 4), np.uint8)
@@ -269,7 +296,9 @@ def run_gpu(args):
         ceil = ctx.measure()
         ops, byts = algorithmic_work(frame, w, h, spp, nl)
         fp32_peak = 2.0 * ceil["fp32_ffma_glanes"]                 # Gop/s with FMA = 2, measured live on this GPU
-        ach = ops / (kernel_ms * 1e-3) / 1e9 / world                # per GPU
+        ach = ops / (kernel_ms * 1e-3) / 1e9 / world                # per GPU, whole frame
+        p_ops, p_bytes = primary_kernel_work(frame)
+        p_ach = p_ops / (phases[0] * 1e-3) / 1e9 / world           # dominant kernel alone
         l2_ach = byts / (kernel_ms * 1e-3) / 1e9 / world
         hbm_bytes = scene_bytes + frame["primary_rays"] * 48 / world + w * h * 4
         line = {
@@ -286,10 +315,15 @@ def run_gpu(args):
                     "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": w * h * 4,
                     "parts_ms": dict(zip(("reference_bvh_build_flatten", "scene_create_device_bvh_upload", "render_readback_destroy"),
                                          [statistics.median(p[i] for p in e2e_parts[1:]) for i in range(3)]))},
-            "gpu_launches": (4 + nl) * args.steps,
-            "roofline": {"bound": "fp32_issue", "achieved": ach, "peak": fp32_peak, "unit": "Gop/s (FMA=2)", "frac": ach / fp32_peak,
-                         "traffic": None, "peak_source": "lgb_measure_fp32_gops, live on this GPU",
-                         "algorithmic_ops_per_frame": ops, "algorithmic_bytes_per_frame": byts,
+            "gpu_launches": (4 + nl * (3 if spp > 1 else 1)) * args.steps,
+            "roofline": {"kernel": "k_primary (camera rays + closest-hit traversal), %.1f%% of the frame" % (100.0 * phases[0] / max(sum(phases), 1e-9)),
+                         "bound": "fp32_issue", "achieved": p_ach, "peak": fp32_peak, "unit": "Gop/s (FMA=2)", "frac": p_ach / fp32_peak,
+                         "traffic": ncu_traffic(args.workload, world), "peak_source": "lgb_measure_fp32_gops, live on this GPU",
+                         "algorithmic_ops_per_launch": p_ops, "algorithmic_bytes_per_launch": p_bytes, "launch_ms": phases[0],
+                         "l1_l2_fetch": {"achieved_gbs": p_bytes / (phases[0] * 1e-3) / 1e9 / world, "peak_gbs": ceil["l2_read_gbs"],
+                                         "frac": p_bytes / (phases[0] * 1e-3) / 1e9 / world / ceil["l2_read_gbs"]},
+                         "frame": {"achieved": ach, "frac": ach / fp32_peak, "algorithmic_ops_per_frame": ops, "algorithmic_bytes_per_frame": byts},
+                         "phase_ms": dict(zip(("primary", "setup", "shadow_anchor", "pretest_shadow_rest", "shade", "resolve"), phases)),
                          "l2": {"achieved_gbs": l2_ach, "peak_gbs": ceil["l2_read_gbs"], "frac": l2_ach / ceil["l2_read_gbs"]},
                          "hbm": {"achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
                                  "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"]},

@@ -141,7 +141,13 @@ typedef struct lgb_stats {
      * index 0 sphere, 1 cuboid, 2 triangle. */
     uint64_t exact_tests[3];         /* f64 reference-arithmetic primitive tests executed */
     uint64_t filter_tests[3];        /* conservative f32 primitive filter tests executed */
-    uint64_t node_tests;
+    uint64_t node_tests;             /* node fetches; each one tests two child boxes */
+    uint64_t primary_node_tests;     /* the share of the closest-hit (primary ray) kernel in the three counters above */
+    uint64_t primary_exact_tests[3];
+    uint64_t primary_filter_tests[3];
+    /* device time of each phase of the frame (CUDA events on the launch stream): 0 primary rays, 1 hit setup +
+     * shadow queues, 2 anchor shadow rays, 3 cached-occluder test + remaining shadow rays, 4 shade, 5 resolve */
+    float kernel_ms[6];
     float render_ms;                 /* device time of the render + resolve kernels */
     float total_ms;                  /* device time incl. film copy back to the host */
     uint32_t kernel_launches;

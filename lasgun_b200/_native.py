@@ -71,11 +71,12 @@ class BuildInfo(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("primary_hits", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("shadow_rays_traced", C.c_uint64), ("shadow_occluded", C.c_uint64), ("shadow_cache_hits", C.c_uint64), ("exact_tests", C.c_uint64 * 3),
-                ("filter_tests", C.c_uint64 * 3), ("node_tests", C.c_uint64), ("render_ms", C.c_float), ("total_ms", C.c_float),
+                ("filter_tests", C.c_uint64 * 3), ("node_tests", C.c_uint64), ("primary_node_tests", C.c_uint64),
+                ("primary_exact_tests", C.c_uint64 * 3), ("primary_filter_tests", C.c_uint64 * 3), ("kernel_ms", C.c_float * 6), ("render_ms", C.c_float), ("total_ms", C.c_float),
                 ("kernel_launches", C.c_uint32), ("stack_overflow", C.c_uint32)]
 
     def as_dict(self):
-        return {n: (list(getattr(self, n)) if n in ("exact_tests", "filter_tests") else getattr(self, n)) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n in ("exact_tests", "filter_tests", "primary_exact_tests", "primary_filter_tests", "kernel_ms") else getattr(self, n)) for n, _ in self._fields_}
 
 
 def lib():

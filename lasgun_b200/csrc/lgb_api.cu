@@ -16,7 +16,8 @@
 #include "lgb_types.cuh"
 
 namespace lgb {
-cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t);
+constexpr int kRenderEvents = 7;
+cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev);
 cudaError_t launch_trace(const DevScene&, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns, cudaStream_t);
 cudaError_t launch_l2_read(const void* buf, uint64_t bytes, int iters, float* sink, int sms, cudaStream_t);
 cudaError_t launch_fp32_peak(int iters, float* sink, int sms, cudaStream_t);
@@ -45,6 +46,7 @@ struct lgb_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    cudaEvent_t phase[kRenderEvents] = {};
     std::string error;
     DevBuf radiance, film, counters, tiles, aov_id, aov_t, aov_occl, scratch, wave, wave_ctr;
     std::vector<uint32_t> tile_host;
@@ -120,6 +122,7 @@ int lgb_init(int device, lgb_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(nullptr, cudaEventCreate(&c->ev0)); CU(nullptr, cudaEventCreate(&c->ev1)); CU(nullptr, cudaEventCreate(&c->ev2));
+    for (auto& e : c->phase) CU(nullptr, cudaEventCreate(&e));
     {   // scene arenas come from the stream-ordered pool and are kept cached between scenes (cudaMalloc/cudaFree cost ms)
         cudaMemPool_t mp;
         if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
@@ -144,6 +147,7 @@ void lgb_shutdown(lgb_ctx* c) {
     for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr}) b->release();
     if (c->staging) cudaFreeHost(c->staging);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
+    for (auto& e : c->phase) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -553,7 +557,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     }
     CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));
     CU(c, cudaEventRecord(c->ev0, st));
-    CU(c, launch_render(S, s->cam, s->shade, W, O, V, a.aov || c->count_work, a.aov, c->sm_count, st));
+    CU(c, launch_render(S, s->cam, s->shade, W, O, V, a.aov || c->count_work, a.aov, c->sm_count, st, (stats && sync_stats && total) ? c->phase : nullptr));
     CU(c, cudaEventRecord(c->ev1, st));
     if (stats && sync_stats) {
         DevCounters hc;
@@ -563,7 +567,9 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         stats->primary_rays = hc.primary_rays; stats->primary_hits = hc.primary_hits;
         stats->shadow_rays = hc.primary_hits * s->dev.n_lights;
         stats->shadow_rays_traced = hc.shadow_traced; stats->shadow_occluded = hc.shadow_occluded; stats->shadow_cache_hits = hc.shadow_cached;
-        stats->node_tests = hc.node_tests;
+        stats->node_tests = hc.node_tests; stats->primary_node_tests = hc.p_node_tests;
+        for (int k = 0; k < 3; k++) { stats->primary_filter_tests[k] = hc.p_filter[k]; stats->primary_exact_tests[k] = hc.p_exact[k]; }
+        if (total) for (int k = 0; k < 6; k++) { float pm = 0.f; CU(c, cudaEventElapsedTime(&pm, c->phase[k], c->phase[k + 1])); stats->kernel_ms[k] = pm; }
         for (int k = 0; k < 3; k++) { stats->filter_tests[k] = hc.filter[k]; stats->exact_tests[k] = hc.exact[k]; }
         stats->stack_overflow = hc.stack_overflow;
         stats->kernel_launches = total ? 4 + s->dev.n_lights * (W.spp > 1 ? 3 : 1) : 0;

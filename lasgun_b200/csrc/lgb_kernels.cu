@@ -619,10 +619,10 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, Dev
         if (lane == 0) { atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1); }
         if (STATS) {
             unsigned long long n = warp_sum(lc.node_tests);
-            if (lane == 0) atomicAdd(&O.counters->node_tests, n);
+            if (lane == 0) { atomicAdd(&O.counters->node_tests, n); atomicAdd(&O.counters->p_node_tests, n); }
             for (int k = 0; k < 3; k++) {
                 unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
-                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); }
+                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); atomicAdd(&O.counters->p_filter[k], a); atomicAdd(&O.counters->p_exact[k], b); }
             }
         }
     }
@@ -900,8 +900,12 @@ __global__ void k_fp64_peak(int iters, double* sink) {
 }
 
 // ------------------------------------------------------------------ launch wrappers (called from lgb_api.cu)
+// `ev` (optional): kRenderEvents events recorded around the phases: start | primary | setup | anchor shadow rays |
+// pretest + remaining shadow rays | shade | resolve.
 cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O,
-                          const DevWave& V, bool stats, bool all_shadows, int sms, cudaStream_t stream) {
+                          const DevWave& V, bool stats, bool all_shadows, int sms, cudaStream_t stream, cudaEvent_t* ev) {
+    auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], stream); };
+    mark(0);
     const uint64_t total = W.n_pixels * W.spp;
     if (total == 0) return cudaSuccess;
     cudaError_t e;
@@ -911,9 +915,11 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     const unsigned pblocks = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)sms * LGB_MIN_BLOCKS);
     if (stats) k_primary<true><<<pblocks, 256, 0, stream>>>(S, C, W, O, V);
     else k_primary<false><<<pblocks, 256, 0, stream>>>(S, C, W, O, V);
+    mark(1);
     const unsigned blocks = (unsigned)((total + 255) / 256), ablocks = (unsigned)((total + kAppendThreads - 1) / kAppendThreads);
     if (all_shadows) k_setup<true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
     else k_setup<false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
+    mark(2);
     // anchor rays (queue A), then the cached-occluder test of the rest (B -> C), then the survivors (queue C)
     for (int which = kQueueA; which <= (cache ? kQueueC : kQueueA); which += 2) {
         const unsigned sb = which == kQueueA ? (unsigned)std::min<uint64_t>((W.n_pixels + 255) / 256, pblocks) : pblocks;
@@ -922,10 +928,14 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
             if (stats) k_shadow<true><<<sb, 256, 0, stream>>>(S, W, O, V, l, which);
             else k_shadow<false><<<sb, 256, 0, stream>>>(S, W, O, V, l, which);
         }
+        if (which == kQueueA) mark(3);
     }
+    mark(4);
     k_shade<<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+    mark(5);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
+    mark(6);
     return cudaGetLastError();
 }
 cudaError_t launch_trace(const DevScene& S, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns, cudaStream_t stream) {

@@ -84,6 +84,7 @@ struct DevCounters {
     unsigned long long node_tests;     // node fetches (each tests two child boxes)
     unsigned long long filter[3];    // f32 filter tests by primitive type (sphere, cuboid, triangle)
     unsigned long long exact[3];     // f64 reference-arithmetic tests by primitive type
+    unsigned long long p_node_tests, p_filter[3], p_exact[3];   // the share of k_primary in the three counters above
     unsigned int stack_overflow;
     unsigned int pad;
 };
