@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LGB_ABI_VERSION 1
+#define LGB_ABI_VERSION 2
 
 typedef enum lgb_status {
     LGB_OK = 0,
@@ -72,13 +72,17 @@ typedef struct lgb_tri_normals {     /* per-vertex f32 normals, triangle.rs:58-7
     float n0[3]; float n1[3]; float n2[3];
 } lgb_tri_normals;
 
-/* Nested BVH used as a primitive (bvh.rs:141-162).  Only identity transforms are supported in
- * ABI v1; `identity` must be 1. */
+/* Nested BVH used as a primitive (bvh.rs:141-162), with the Transform3 of its aggregate (scene/node.rs:86-115,
+ * space/transform.rs:48-197).  The ray is taken into the level's space with `minv` (transform.rs:279-283: t is
+ * preserved because d is not renormalised) and the hit record comes back with `m` (transform.rs:243-264), then
+ * swap_backface (bvh.rs:518).  Matrices are cgmath Matrix4<f64>, column-major: element [c][r] at index 4*c + r.
+ * They must be affine (row 3 = 0 0 0 1); `identity` = 1 promises that both are the identity. */
 typedef struct lgb_instance {
     uint32_t root_node;              /* absolute index of the child BVH's node 0 */
     uint32_t identity;
-    uint32_t swap_backface;          /* must be 0 in ABI v1 */
+    uint32_t swap_backface;
     uint32_t reserved;
+    double m[16], minv[16];
 } lgb_instance;
 
 /* Material after `Material::scattering` resolution (material/{plastic,matte}.rs).
@@ -115,6 +119,7 @@ typedef struct lgb_scene_desc {
     const lgb_tri_normals* tri_normals;  /* NULL or n_triangles entries (mesh has normals and smoothing is on) */
     const uint8_t* tri_has_normals;      /* NULL or n_triangles flags (meshes may differ) */
     const lgb_instance* instances;   uint64_t n_instances;
+    lgb_instance root;               /* transform / swap_backface of the root aggregate itself (root_node = 0) */
     const lgb_material* materials;   uint64_t n_materials;
     const lgb_light* lights;         uint64_t n_lights;      /* at most LGB_MAX_LIGHTS */
     lgb_camera camera;

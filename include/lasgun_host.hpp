@@ -151,6 +151,7 @@ struct FlatScene {
     raw_vector<lgb_triangle> triangles; raw_vector<uint32_t> triangle_material, triangle_id;
     raw_vector<lgb_tri_normals> tri_normals; raw_vector<uint8_t> tri_has_normals;
     std::vector<lgb_instance> instances;
+    lgb_instance root{};               // transform / swap_backface of the root aggregate
     std::vector<lgb_material> materials;
     std::vector<lgb_light> lights;
     lgb_camera camera{};

@@ -42,6 +42,11 @@ class CameraDesc(C.Structure):
                 ("supersampling_root", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class InstanceDesc(C.Structure):
+    _fields_ = [("root_node", C.c_uint32), ("identity", C.c_uint32), ("swap_backface", C.c_uint32), ("reserved", C.c_uint32),
+                ("m", C.c_double * 16), ("minv", C.c_double * 16)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [
         ("abi_version", C.c_uint32), ("flags", C.c_uint32),
@@ -51,7 +56,7 @@ class SceneDesc(C.Structure):
         ("cuboids", C.c_void_p), ("n_cuboids", C.c_uint64), ("cuboid_material", C.c_void_p), ("cuboid_id", C.c_void_p),
         ("triangles", C.c_void_p), ("n_triangles", C.c_uint64), ("triangle_material", C.c_void_p), ("triangle_id", C.c_void_p),
         ("tri_normals", C.c_void_p), ("tri_has_normals", C.c_void_p),
-        ("instances", C.c_void_p), ("n_instances", C.c_uint64),
+        ("instances", C.c_void_p), ("n_instances", C.c_uint64), ("root", InstanceDesc),
         ("materials", C.c_void_p), ("n_materials", C.c_uint64),
         ("lights", C.c_void_p), ("n_lights", C.c_uint64),
         ("camera", CameraDesc),

@@ -341,6 +341,22 @@ struct LevelTree {
     }
 };
 
+// Transform3::transform_bounds, transform.rs:219-240 (m is cgmath column-major: column c at m[4c .. 4c+3]).
+inline double bmin(double a, double b) { return a < b ? a : b; }     // transform.rs:308-309
+inline double bmax(double a, double b) { return a < b ? b : a; }
+inline Box transform_bounds(const double m[16], const Box& b) {
+    Box o;
+    for (int r = 0; r < 3; r++) {
+        const double xa = m[0 + r] * b.mn[0], xb = m[0 + r] * b.mx[0];
+        const double ya = m[4 + r] * b.mn[1], yb = m[4 + r] * b.mx[1];
+        const double za = m[8 + r] * b.mn[2], zb = m[8 + r] * b.mx[2];
+        const double lo = bmin(xa, xb) + bmin(ya, yb) + bmin(za, zb) + m[12 + r];
+        const double hi = bmax(xa, xb) + bmax(ya, yb) + bmax(za, zb) + m[12 + r];
+        o.mn[r] = lo < hi ? lo : hi; o.mx[r] = lo < hi ? hi : lo;          // Bounds3::new, bounds.rs:37-42
+    }
+    return o;
+}
+
 // A level being assembled: its reference tree plus what each primitive is.
 struct Level {
     LevelTree tree;
@@ -430,29 +446,35 @@ struct Flattener {
 
     // BVHAccel::from_aggregate, bvh.rs:150-162
     std::unique_ptr<Level> level_from_aggregate(const Aggregate& ag, bool is_root) {
-        if (!ag.transform.identity || ag.swap_backface_flag) {
-            (void)is_root;
-            throw Error(LGB_ERR_UNSUPPORTED, "group transforms / swap_backface are not on the device path yet (SURVEY §8f item 1)");
-        }
+        (void)is_root;
         auto lv = std::make_unique<Level>();
         // Pass 1 (sequential, construction order): canonical ids, array slots, nested levels.
         const size_t nn = ag.contents.size();
         raw_vector<uint32_t> slot(nn), ids(nn);
-        const size_t s_base = out.spheres.size(), c_base = out.cuboids.size();
-        size_t n_s = 0, n_c = 0;
+        size_t n_s = 0, n_c = 0;       // slot[] holds the ordinal among this level's own spheres / cuboids until pass 1 is over
         lv->boxes.resize(nn); lv->refs.resize(nn);
         for (size_t i = 0; i < nn; i++) {
             const Aggregate::Node& n = ag.contents[i];
             switch (n.kind) {
-            case Aggregate::Node::Sphere: slot[i] = (uint32_t)(s_base + n_s++); ids[i] = next_id++; break;
+            case Aggregate::Node::Sphere: slot[i] = (uint32_t)n_s++; ids[i] = next_id++; break;
             case Aggregate::Node::Cube:
-            case Aggregate::Node::Cuboid: slot[i] = (uint32_t)(c_base + n_c++); ids[i] = next_id++; break;
+            case Aggregate::Node::Cuboid: slot[i] = (uint32_t)n_c++; ids[i] = next_id++; break;
             case Aggregate::Node::Mesh:
             case Aggregate::Node::Group: {
                 std::unique_ptr<Level> child = n.kind == Aggregate::Node::Mesh ? level_from_mesh(n.ref, n.has_mat, n.mat)
                                                                                 : level_from_aggregate(ag.groups[n.ref], false);
-                lv->boxes[i] = child->tree.nodes[child->tree.root].box;        // identity transform_bounds, bvh.rs:457-459
-                out.instances.push_back(lgb_instance{0, 1, 0, 0});
+                lgb_instance inst{};
+                inst.identity = 1;
+                for (int k = 0; k < 16; k++) inst.m[k] = inst.minv[k] = (k % 5 == 0) ? 1.0 : 0.0;
+                const Box& cb = child->tree.nodes[child->tree.root].box;
+                if (n.kind == Aggregate::Node::Group) {
+                    const Aggregate& g = ag.groups[n.ref];
+                    inst.identity = g.transform.identity ? 1u : 0u;
+                    inst.swap_backface = g.swap_backface_flag ? 1u : 0u;
+                    std::memcpy(inst.m, g.transform.m, sizeof inst.m); std::memcpy(inst.minv, g.transform.minv, sizeof inst.minv);
+                }
+                lv->boxes[i] = transform_bounds(inst.m, cb);                   // BVHAccel::bound, bvh.rs:457-459
+                out.instances.push_back(inst);
                 lv->refs[i] = LGB_PRIM_REF(LGB_PRIM_INSTANCE, out.instances.size() - 1);
                 lv->child_instance.push_back((uint32_t)out.instances.size() - 1);
                 lv->children.push_back(std::move(child));
@@ -460,8 +482,12 @@ struct Flattener {
             }
             }
         }
-        if (out.spheres.size() != s_base || out.cuboids.size() != c_base)
-            throw Error(LGB_ERR_INVALID, "internal: primitive arrays grew while a level was being assembled");
+        const size_t s_base = out.spheres.size(), c_base = out.cuboids.size();      // after the nested levels took theirs
+        for (size_t i = 0; i < nn; i++) {
+            const Aggregate::Node::Kind k = ag.contents[i].kind;
+            if (k == Aggregate::Node::Sphere) slot[i] += (uint32_t)s_base;
+            else if (k == Aggregate::Node::Cube || k == Aggregate::Node::Cuboid) slot[i] += (uint32_t)c_base;
+        }
         out.spheres.resize(s_base + n_s); out.sphere_material.resize(s_base + n_s); out.sphere_id.resize(s_base + n_s);
         out.cuboids.resize(c_base + n_c); out.cuboid_material.resize(c_base + n_c); out.cuboid_id.resize(c_base + n_c);
         // Pass 2 (all threads): primitive records and bounds.  Materials are interned through a small per-chunk
@@ -579,6 +605,10 @@ FlatScene flatten(const Scene& scene, const BuildOptions& opt) {
     FlatScene out;
     Flattener f{scene, opt, out, {}, 0};
     std::unique_ptr<Level> root = f.level_from_aggregate(scene.root, true);
+    out.root = lgb_instance{};
+    out.root.identity = scene.root.transform.identity ? 1u : 0u;
+    out.root.swap_backface = scene.root.swap_backface_flag ? 1u : 0u;
+    std::memcpy(out.root.m, scene.root.transform.m, sizeof out.root.m); std::memcpy(out.root.minv, scene.root.transform.minv, sizeof out.root.minv);
     const double t_levels = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     f.emit_level(*root);
     if (std::getenv("LGB_TIMING")) std::fprintf(stderr, "[flatten] levels (reference HLBVH builds) %.1f ms, emit %.1f ms\n", t_levels,
@@ -612,6 +642,7 @@ void FlatScene::describe(lgb_scene_desc* d) const {
     d->tri_normals = tri_normals.empty() ? nullptr : tri_normals.data();
     d->tri_has_normals = tri_has_normals.empty() ? nullptr : tri_has_normals.data();
     d->instances = instances.data(); d->n_instances = instances.size();
+    d->root = root;
     d->materials = materials.data(); d->n_materials = materials.size();
     d->lights = lights.data(); d->n_lights = lights.size();
     d->camera = camera;

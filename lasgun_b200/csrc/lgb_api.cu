@@ -186,15 +186,21 @@ int lgb_build_probe(const lgb_scene_desc* d, lgb_build_info* out) {
     if (!d || !out || !d->n_nodes) return LGB_ERR_INVALID;
     std::memset(out, 0, sizeof *out);
     const uint32_t prim_count = (uint32_t)(d->n_spheres + d->n_cuboids + d->n_triangles);
-    const int threads = (int)std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency()));
+    const int threads = Pool::get().threads();
+    BuiltScene bs; std::string berr;
+    double wlo[3], whi[3];
+    for (int k = 0; k < 3; k++) { wlo[k] = d->nodes[0].lo[k]; whi[k] = d->nodes[0].hi[k]; }
+    if (build_scene(d, wlo, whi, bs, berr)) return LGB_ERR_INVALID;
     auto t0 = std::chrono::steady_clock::now();
-    std::vector<uint32_t> rank((size_t)8 * prim_count);
-    out->ranks_ok = build_rank_tables(d, prim_count, threads, rank.data()) ? 1 : 0;
+    std::vector<uint32_t> rank((size_t)8 * (prim_count + bs.spaces.size()));
+    out->ranks_ok = build_rank_tables(d, prim_count, bs, rank.data()) ? 1 : 0;
     out->rank_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    out->build_ms = bs.build_ms; out->prims = prim_count;
+    if (bs.spaces.size() > 1) { out->nodes = (uint32_t)bs.nodes.size(); out->boxes_ok = 1; return LGB_OK; }   // structural check below: single space
     raw_vector<PrimBox> prims; make_prim_boxes(d, prims);
     BuiltBVH bvh;
     if (build_sah(prims.data(), prims.size(), 0.0f, threads, bvh)) return LGB_ERR_INVALID;
-    out->nodes = (uint32_t)bvh.nodes.size(); out->max_depth = bvh.max_depth; out->prims = prim_count; out->build_ms = bvh.build_ms;
+    out->nodes = (uint32_t)bvh.nodes.size(); out->max_depth = bvh.max_depth;
     // verify: every primitive in exactly one leaf, leaf boxes contain their primitives, child boxes nest
     std::vector<uint8_t> seen[3];
     for (int t = 0; t < 3; t++) seen[t].assign(bvh.order[t].size(), 0);
@@ -280,11 +286,8 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: NULL array with non-zero count");
     if (!mat_ok(d->sphere_material, d->n_spheres) || !mat_ok(d->cuboid_material, d->n_cuboids) || !mat_ok(d->triangle_material, d->n_triangles))
         return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: material index out of range");
-    for (uint64_t i = 0; i < d->n_instances; i++) {
-        if (!d->instances[i].identity || d->instances[i].swap_backface)
-            return fail(ctx, LGB_ERR_UNSUPPORTED, "instance: group transforms / swap_backface are not supported by ABI v1 (SURVEY §8f item 1)");
+    for (uint64_t i = 0; i < d->n_instances; i++)
         if (d->instances[i].root_node >= d->n_nodes) return fail(ctx, LGB_ERR_INVALID, "instance: root_node out of range");
-    }
 
     // ---- validate the node graph and bound the traversal stack (bvh.rs:469: 64 entries)
     const uint64_t nn = d->n_nodes;
@@ -319,32 +322,47 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     s->ctx = ctx;
     auto bail = [&](int code) { lgb_scene_destroy(s); return code; };
 
-    // ---- coordinate magnitude bound -> f32 error bound used by the conservative filters
-    double M = 0.0;
-    auto upd = [&](double v) { double a = std::fabs(v); if (a > M && std::isfinite(a)) M = a; };
-    for (int k = 0; k < 3; k++) { upd(d->nodes[0].lo[k]); upd(d->nodes[0].hi[k]); upd(d->camera.origin[k]); }
-    for (uint64_t i = 0; i < d->n_instances; i++) for (int k = 0; k < 3; k++) { upd(d->nodes[d->instances[i].root_node].lo[k]); upd(d->nodes[d->instances[i].root_node].hi[k]); }
-    // orthographic origins move across the image plane (camera.rs:126-128); aspect <= 4 assumed, checked per capture
-    M += 2.5 * std::fabs(d->camera.image_plane_height) * std::fabs(d->camera.pixel_separation);
-    s->max_abs = M;
+    // ---- box that contains the scene and every ray origin, in world coordinates: it bounds the coordinates an f32
+    //      ray can carry in every space, hence the error bound of the conservative filters
+    double wlo[3], whi[3];
+    {
+        double rlo[3], rhi[3];
+        for (int k = 0; k < 3; k++) { rlo[k] = d->nodes[0].lo[k]; rhi[k] = d->nodes[0].hi[k]; }
+        if (!d->root.identity) {                           // the root level's box is in the root aggregate's coordinates
+            for (int r = 0; r < 3; r++) {
+                double l = d->root.m[12 + r], h = l;
+                for (int c = 0; c < 3; c++) { const double a = d->root.m[4 * c + r] * rlo[c], b = d->root.m[4 * c + r] * rhi[c]; l += std::min(a, b); h += std::max(a, b); }
+                wlo[r] = l; whi[r] = h;
+            }
+        } else for (int k = 0; k < 3; k++) { wlo[k] = rlo[k]; whi[k] = rhi[k]; }
+        // orthographic origins move across the image plane (camera.rs:126-128); aspect <= 4 assumed, checked per capture
+        const double slack = 2.5 * std::fabs(d->camera.image_plane_height) * std::fabs(d->camera.pixel_separation);
+        for (int k = 0; k < 3; k++) {
+            if (std::isfinite(d->camera.origin[k])) { wlo[k] = std::min(wlo[k], d->camera.origin[k] - slack); whi[k] = std::max(whi[k], d->camera.origin[k] + slack); }
+        }
+    }
 
-    // ---- device acceleration structure: binned-SAH BVH over the same primitives, rank tables from the
-    //      caller's reference tree (lgb_build.hpp); everything is stored in leaf order.
+    // ---- device acceleration structure: one binned-SAH BVH per space over the same primitives, rank tables from
+    //      the caller's reference tree (lgb_build.hpp); everything is stored in leaf order.
     const uint32_t prim_count = (uint32_t)(d->n_spheres + d->n_cuboids + d->n_triangles);
     if (prim_count == 0) return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: no primitives"));
     const int threads = Pool::get().threads();
-    const double padd = M * std::ldexp(1.0, -20);
-    s->dev.err_abs = (float)padd;
     s->t_validate = ms_since(tc0);
     auto tc2 = std::chrono::steady_clock::now();
-    BuiltBVH bvh;
+    BuiltScene bvh;
     {
-        raw_vector<PrimBox> prims; make_prim_boxes(d, prims);
-        int brc = build_sah(prims.data(), prims.size(), (float)padd, threads, bvh);
-        if (brc == -2) return bail(fail(ctx, LGB_ERR_UNSUPPORTED, "lgb_scene_create: more than 16.7M primitives of one type"));
-        if (brc) return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: BVH build failed"));
-        if (bvh.max_depth + 1 > (uint32_t)kStackDepth) return bail(fail(ctx, LGB_ERR_UNSUPPORTED, "device BVH deeper than the 64-entry traversal stack"));
+        std::string berr;
+        const int brc = build_scene(d, wlo, whi, bvh, berr);
+        if (brc == -2 || brc == -4) return bail(fail(ctx, LGB_ERR_UNSUPPORTED, "lgb_scene_create: " + berr));
+        if (brc) return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: " + berr));
+        if (bvh.spaces[0].stack_need > (uint32_t)kStackDepth) return bail(fail(ctx, LGB_ERR_UNSUPPORTED, "device BVH deeper than the 64-entry traversal stack"));
+        if (bvh.spaces.size() > 1) for (const HostSpace& sp : bvh.spaces) if (sp.depth >= (uint32_t)kMaxSpaceDepth) return bail(fail(ctx, LGB_ERR_UNSUPPORTED, "more than 8 nested transformed aggregates"));
     }
+    const double padd = bvh.spaces[0].max_abs * std::ldexp(1.0, -20);
+    s->max_abs = bvh.spaces[0].max_abs;
+    s->dev.err_abs = bvh.spaces[0].err_abs;
+    const bool instanced = bvh.instanced();
+    const size_t nsp = bvh.spaces.size();
     s->build_ms = bvh.build_ms;
     s->t_build = ms_since(tc2);
 
@@ -355,7 +373,10 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     const bool any_normals = nt && d->tri_normals;
     size_t off = 0;
     auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_nodes = place(nnodes * 64), o_rank = place((size_t)8 * prim_count * 4);
+    const size_t n_items = (size_t)prim_count + nsp;       // rank-table items: primitives, then one per space
+    const size_t o_nodes = place(nnodes * 64), o_rank = place((size_t)8 * n_items * 4);
+    const size_t o_spaces = place(instanced ? nsp * sizeof(DevSpace) : 0), o_inst = place(instanced ? bvh.order[3].size() * 4 : 0);
+    const size_t o_sspace = place(instanced ? ns * 4 : 0), o_cspace = place(instanced ? ncb * 4 : 0), o_tspace = place(instanced ? nt * 4 : 0);
     const size_t o_s32 = place(ns * 16), o_s64 = place(ns * 32), o_smat = place(ns * 4), o_sid = place(ns * 4);
     const size_t o_c32 = place(ncb * 32), o_c64 = place(ncb * 48), o_cmat = place(ncb * 4), o_cid = place(ncb * 4);
     const size_t o_tri = place(nt * 48), o_nrm = place(any_normals ? nt * 36 : 0);
@@ -372,14 +393,29 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     char* H = (char*)ctx->staging;
     char* D = (char*)s->arena;
     auto tc1 = std::chrono::steady_clock::now();
-    if (!build_rank_tables(d, prim_count, threads, (uint32_t*)(H + o_rank)))
+    (void)threads;
+    if (!build_rank_tables(d, prim_count, bvh, (uint32_t*)(H + o_rank)))
         return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: primitive ids must be a permutation of 0..n-1 and every primitive must be referenced by exactly one leaf"));
     s->t_rank = ms_since(tc1);
     auto tc3 = std::chrono::steady_clock::now();
     Pool& pool = Pool::get();
     pool.for_range(nnodes, 1 << 14, [&](size_t b, size_t e, size_t) { std::memcpy(H + o_nodes + b * 64, bvh.nodes.data() + b, (e - b) * 64); });
     s->dev.nodes = (const float4*)(D + o_nodes); s->dev.n_nodes = (uint32_t)nnodes;
-    s->dev.rank = (const uint32_t*)(D + o_rank); s->dev.prim_count = prim_count;
+    s->dev.rank = (const uint32_t*)(D + o_rank); s->dev.prim_count = prim_count; s->dev.rank_items = (uint32_t)n_items;
+    s->dev.n_spaces = (uint32_t)nsp; s->dev.instanced = instanced ? 1u : 0u;
+    if (instanced) {
+        DevSpace* ds = (DevSpace*)(H + o_spaces);
+        for (size_t k = 0; k < nsp; k++) {
+            const HostSpace& sp = bvh.spaces[k];
+            std::memcpy(ds[k].m, sp.m, sizeof sp.m); std::memcpy(ds[k].minv, sp.minv, sizeof sp.minv);
+            ds[k].parent = sp.parent; ds[k].depth = sp.depth; ds[k].root_node = sp.root_node;
+            ds[k].flags = (sp.identity ? kSpaceIdentity : 0u) | (sp.swap_backface ? kSpaceSwap : 0u);
+            ds[k].err_abs = sp.err_abs; ds[k].pad[0] = ds[k].pad[1] = ds[k].pad[2] = 0;
+        }
+        std::memcpy(H + o_inst, bvh.order[3].data(), bvh.order[3].size() * 4);
+        s->dev.spaces = (const DevSpace*)(D + o_spaces); s->dev.inst_space = (const uint32_t*)(D + o_inst);
+        s->dev.sph_space = (const uint32_t*)(D + o_sspace); s->dev.cub_space = (const uint32_t*)(D + o_cspace); s->dev.tri_space = (const uint32_t*)(D + o_tspace);
+    }
     if (ns) {
         const uint32_t* ord = bvh.order[LGB_PRIM_SPHERE].data();
         float4* s32 = (float4*)(H + o_s32); double* s64 = (double*)(H + o_s64); uint32_t* m = (uint32_t*)(H + o_smat); uint32_t* id = (uint32_t*)(H + o_sid);
@@ -390,6 +426,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
                 s32[j] = make_float4((float)sp.center[0], (float)sp.center[1], (float)sp.center[2], f32_up(std::fabs(sp.radius)));
                 s64[4 * j] = sp.center[0]; s64[4 * j + 1] = sp.center[1]; s64[4 * j + 2] = sp.center[2]; s64[4 * j + 3] = sp.radius;
                 m[j] = d->sphere_material[i]; id[j] = d->sphere_id[i];
+                if (instanced) ((uint32_t*)(H + o_sspace))[j] = bvh.prim_space[0].empty() ? 0u : bvh.prim_space[0][i];
             }
         });
         s->dev.sph32 = (const float4*)(D + o_s32); s->dev.sph64 = (const double*)(D + o_s64);
@@ -402,8 +439,11 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
             for (size_t j = b; j < e; j++) {
                 const uint32_t i = ord[j];
                 const lgb_cuboid& c = d->cuboids[i];
-                c32[2 * j] = make_float4(f32_down(c.min[0] - padd), f32_down(c.min[1] - padd), f32_down(c.min[2] - padd), 0.f);
-                c32[2 * j + 1] = make_float4(f32_up(c.max[0] + padd), f32_up(c.max[1] + padd), f32_up(c.max[2] + padd), 0.f);
+                const uint32_t spc = bvh.prim_space[1].empty() ? 0u : bvh.prim_space[1][i];
+                const double pad = bvh.spaces[spc].max_abs * std::ldexp(1.0, -20);
+                c32[2 * j] = make_float4(f32_down(c.min[0] - pad), f32_down(c.min[1] - pad), f32_down(c.min[2] - pad), 0.f);
+                c32[2 * j + 1] = make_float4(f32_up(c.max[0] + pad), f32_up(c.max[1] + pad), f32_up(c.max[2] + pad), 0.f);
+                if (instanced) ((uint32_t*)(H + o_cspace))[j] = spc;
                 for (int k = 0; k < 3; k++) { c64[6 * j + k] = c.min[k]; c64[6 * j + 3 + k] = c.max[k]; }
                 m[j] = d->cuboid_material[i]; id[j] = d->cuboid_id[i];
             }
@@ -428,6 +468,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
                 float4 a = make_float4(tr.p0[0], tr.p0[1], tr.p0[2], 0.f), b = make_float4(tr.p1[0], tr.p1[1], tr.p1[2], 0.f), c = make_float4(tr.p2[0], tr.p2[1], tr.p2[2], 0.f);
                 std::memcpy(&a.w, &d->triangle_id[i], 4); std::memcpy(&b.w, &d->triangle_material[i], 4); std::memcpy(&c.w, &ni, 4);
                 t[3 * j] = a; t[3 * j + 1] = b; t[3 * j + 2] = c;
+                if (instanced) ((uint32_t*)(H + o_tspace))[j] = bvh.prim_space[2].empty() ? 0u : bvh.prim_space[2][i];
             }
         });
         s->dev.tri = (const float4*)(D + o_tri);

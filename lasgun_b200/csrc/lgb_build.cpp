@@ -143,9 +143,9 @@ struct SubTree {
     Box3 box, cb; uint32_t depth = 0;
     uint32_t parent = 0; int which = 0;                // slot of the top tree that points at this sub-tree
     std::vector<HostNode> nodes;                       // local indices; node 0 = sub-tree root (if interior)
-    std::vector<uint32_t> order[3];
+    std::vector<uint32_t> order[4];
     uint32_t root_word = 0, max_depth = 0;
-    uint32_t node_base = 0, type_base[3] = {0, 0, 0};
+    uint32_t node_base = 0, type_base[4] = {0, 0, 0, 0};
 
     uint32_t make_leaf(Item* it, size_t cnt, uint32_t depth_) {
         const uint32_t type = it[0].type, first = (uint32_t)order[type].size();
@@ -220,10 +220,10 @@ int build_sah(const PrimBox* prims, size_t n, float pad, int threads, BuiltBVH& 
     if (n == 0) return -1;
     raw_vector<Item> buf0(n), buf1;
     std::atomic<bool> bad{false};
-    size_t per_type[3] = {0, 0, 0};
+    size_t per_type[4] = {0, 0, 0, 0};
     {
         const size_t nc = pool.chunks_of(n, kChunk);
-        std::vector<std::array<size_t, 3>> cnt(nc, {0, 0, 0});
+        std::vector<std::array<size_t, 4>> cnt(nc, {0, 0, 0, 0});
         pool.for_range(n, kChunk, [&](size_t b, size_t e, size_t c) {
             for (size_t i = b; i < e; i++) {
                 Item& it = buf0[i];
@@ -232,14 +232,14 @@ int build_sah(const PrimBox* prims, size_t n, float pad, int threads, BuiltBVH& 
                     it.hi[k] = std::nextafterf(prims[i].hi[k] + pad, INFINITY);
                 }
                 it.type = prims[i].type; it.index = prims[i].index;
-                if (it.type > 2) { bad.store(true); continue; }
+                if (it.type > 3) { bad.store(true); continue; }
                 cnt[c][it.type]++;
             }
         });
         if (bad.load()) return -1;
-        for (auto& c : cnt) for (int t = 0; t < 3; t++) per_type[t] += c[t];
+        for (auto& c : cnt) for (int t = 0; t < 4; t++) per_type[t] += c[t];
     }
-    for (int t = 0; t < 3; t++) { if (per_type[t] > kLeafFirstMask) return -2; out.order[t].resize(per_type[t]); }
+    for (int t = 0; t < 4; t++) { if (per_type[t] > kLeafFirstMask) return -2; out.order[t].resize(per_type[t]); }
 
     std::vector<HostNode> top;                 // nodes created by the top phase, in creation order (node 0 = root)
     std::vector<SubTree> subs;
@@ -255,7 +255,7 @@ int build_sah(const PrimBox* prims, size_t n, float pad, int threads, BuiltBVH& 
         write_node_boxes(nd, box, box);
         nd.c0 = w; nd.c1 = w;
         out.nodes.assign(1, nd);
-        for (int t = 0; t < 3; t++) out.order[t] = st.order[t];
+        for (int t = 0; t < 4; t++) out.order[t] = st.order[t];
         out.max_depth = 1;
         out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         return 0;
@@ -374,10 +374,10 @@ int build_sah(const PrimBox* prims, size_t n, float pad, int threads, BuiltBVH& 
     });
     const double t_bottom = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     // ---- assemble: top nodes first, then every sub-tree's nodes contiguously (depth-first inside each)
-    uint32_t node_total = (uint32_t)top.size(), tb[3] = {0, 0, 0}, max_depth = 0;
+    uint32_t node_total = (uint32_t)top.size(), tb[4] = {0, 0, 0, 0}, max_depth = 0;
     for (SubTree& st : subs) {
         st.node_base = node_total; node_total += (uint32_t)st.nodes.size();
-        for (int t = 0; t < 3; t++) { st.type_base[t] = tb[t]; tb[t] += (uint32_t)st.order[t].size(); }
+        for (int t = 0; t < 4; t++) { st.type_base[t] = tb[t]; tb[t] += (uint32_t)st.order[t].size(); }
         max_depth = std::max(max_depth, st.max_depth);
     }
     out.nodes.resize(node_total);
@@ -389,7 +389,7 @@ int build_sah(const PrimBox* prims, size_t n, float pad, int threads, BuiltBVH& 
             nd.c0 = st.rebase(nd.c0); nd.c1 = st.rebase(nd.c1);
             out.nodes[st.node_base + i] = nd;
         }
-        for (int t = 0; t < 3; t++) std::copy(st.order[t].begin(), st.order[t].end(), out.order[t].begin() + st.type_base[t]);
+        for (int t = 0; t < 4; t++) std::copy(st.order[t].begin(), st.order[t].end(), out.order[t].begin() + st.type_base[t]);
     });
     for (const SubTree& st : subs) {
         if (st.parent == 0xFFFFFFFFu) { if (st.root_word != 0 || st.node_base != 0) return -3; continue; }   // the root must be node 0
@@ -402,19 +402,184 @@ int build_sah(const PrimBox* prims, size_t n, float pad, int threads, BuiltBVH& 
     return 0;
 }
 
-bool build_rank_tables(const lgb_scene_desc* d, uint32_t prim_count, int threads, uint32_t* rank) {
-    (void)threads;
+// ------------------------------------------------------------------ spaces
+namespace {
+inline float f32_down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
+inline float f32_up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }
+// Transform3::transform_bounds (transform.rs:219-240) of the box [lo, hi] by the column-major matrix m.
+inline void xform_box(const double m[16], const double lo[3], const double hi[3], double olo[3], double ohi[3]) {
+    for (int r = 0; r < 3; r++) {
+        double l = m[12 + r], h = m[12 + r];
+        for (int c = 0; c < 3; c++) {
+            const double a = m[4 * c + r] * lo[c], b = m[4 * c + r] * hi[c];
+            l += a < b ? a : b; h += a < b ? b : a;
+        }
+        olo[r] = l; ohi[r] = h;
+    }
+}
+inline bool affine(const double m[16]) { return m[3] == 0.0 && m[7] == 0.0 && m[11] == 0.0 && m[15] == 1.0; }
+}  // namespace
+
+int build_scene(const lgb_scene_desc* d, const double world_lo[3], const double world_hi[3], BuiltScene& out, std::string& err) {
+    auto t0 = std::chrono::steady_clock::now();
     Pool& pool = Pool::get();
-    pool.for_range((size_t)8 * prim_count, 1 << 16, [&](size_t b, size_t e, size_t) { std::fill(rank + b, rank + e, 0xFFFFFFFFu); });
+    const size_t ns = d->n_spheres, nc = d->n_cuboids, nt = d->n_triangles, np = ns + nc + nt;
+    // ---- discover the spaces (breadth-first over the nested levels: a child space has a larger index than its parent)
+    out.spaces.clear(); out.inst_space.assign(d->n_instances, kNoSpace);
+    {
+        HostSpace s0; s0.ref_root = 0; s0.identity = d->root.identity; s0.swap_backface = d->root.swap_backface;
+        std::memcpy(s0.m, d->root.m, sizeof s0.m); std::memcpy(s0.minv, d->root.minv, sizeof s0.minv);
+        if (s0.identity) for (int k = 0; k < 16; k++) s0.m[k] = s0.minv[k] = (k % 5 == 0) ? 1.0 : 0.0;
+        out.spaces.push_back(s0);
+    }
+    bool multi = false;
+    for (uint64_t i = 0; i < d->n_instances; i++) multi |= !d->instances[i].identity || d->instances[i].swap_backface;
+    std::vector<std::vector<uint32_t>> children(1);
+    if (multi) {
+        for (int t = 0; t < 3; t++) out.prim_space[t].resize(t == 0 ? ns : t == 1 ? nc : nt);
+        std::vector<uint8_t> seen_inst(d->n_instances, 0);
+        for (size_t sidx = 0; sidx < out.spaces.size(); sidx++) {
+            std::vector<uint32_t> st{out.spaces[sidx].ref_root};
+            while (!st.empty()) {
+                const uint32_t ni = st.back(); st.pop_back();
+                const lgb_node& n = d->nodes[ni];
+                if (n.b & LGB_LEAF_FLAG) {
+                    const uint32_t cnt = n.b & ~LGB_LEAF_FLAG;
+                    for (uint32_t j = 0; j < cnt; j++) {
+                        const uint32_t ref = d->prim_refs[n.a + j], type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+                        if (type != LGB_PRIM_INSTANCE) { out.prim_space[type][idx] = (uint32_t)sidx; continue; }
+                        if (seen_inst[idx]++) { err = "instance referenced by more than one leaf"; return -1; }
+                        const lgb_instance& in = d->instances[idx];
+                        if (in.identity && !in.swap_backface) { st.push_back(in.root_node); continue; }
+                        if (!affine(in.m) || !affine(in.minv)) { err = "instance: transform is not affine (row 3 must be 0 0 0 1)"; return -4; }
+                        HostSpace c; c.parent = (uint32_t)sidx; c.depth = out.spaces[sidx].depth + 1; c.ref_root = in.root_node;
+                        c.identity = in.identity; c.swap_backface = in.swap_backface;
+                        std::memcpy(c.m, in.m, sizeof c.m); std::memcpy(c.minv, in.minv, sizeof c.minv);
+                        out.inst_space[idx] = (uint32_t)out.spaces.size();
+                        children[sidx].push_back((uint32_t)out.spaces.size());
+                        out.spaces.push_back(c); children.emplace_back();
+                    }
+                } else { st.push_back(n.a); st.push_back(ni + 1); }
+            }
+        }
+    }
+    if (!out.spaces[0].identity && (!affine(out.spaces[0].m) || !affine(out.spaces[0].minv))) { err = "root transform is not affine (row 3 must be 0 0 0 1)"; return -4; }
+    const size_t nsp = out.spaces.size();
+    // ---- coordinate bound of every space: its own geometry and every ray origin taken into it
+    {
+        std::vector<std::array<double, 6>> obox(nsp);       // box that contains the ray origins, in the space's coordinates
+        for (size_t sidx = 0; sidx < nsp; sidx++) {
+            HostSpace& sp = out.spaces[sidx];
+            const double* plo = sp.parent == kNoSpace ? world_lo : obox[sp.parent].data();
+            const double* phi = sp.parent == kNoSpace ? world_hi : obox[sp.parent].data() + 3;
+            if (sp.identity) { for (int k = 0; k < 3; k++) { obox[sidx][k] = plo[k]; obox[sidx][3 + k] = phi[k]; } }
+            else xform_box(sp.minv, plo, phi, obox[sidx].data(), obox[sidx].data() + 3);
+            double M = 0.0;
+            auto upd = [&](double v) { const double a = std::fabs(v); if (a > M && std::isfinite(a)) M = a; };
+            for (int k = 0; k < 6; k++) upd(obox[sidx][k]);
+            for (int k = 0; k < 3; k++) { upd(d->nodes[sp.ref_root].lo[k]); upd(d->nodes[sp.ref_root].hi[k]); }
+            sp.max_abs = M; sp.err_abs = (float)(M * std::ldexp(1.0, -20));
+        }
+    }
+    // ---- primitive boxes (each in the coordinates of its own level), grouped by space
+    raw_vector<PrimBox> prims(np);
+    pool.for_range(ns, 1 << 14, [&](size_t b0, size_t e0, size_t) {
+        for (size_t i = b0; i < e0; i++) {
+            const lgb_sphere& sp = d->spheres[i]; PrimBox& b = prims[i]; b.type = LGB_PRIM_SPHERE; b.index = (uint32_t)i;
+            for (int k = 0; k < 3; k++) { double lo = sp.center[k] - sp.radius, hi = sp.center[k] + sp.radius; b.lo[k] = f32_down(std::min(lo, hi)); b.hi[k] = f32_up(std::max(lo, hi)); }
+        }
+    });
+    for (size_t i = 0; i < nc; i++) {
+        const lgb_cuboid& c = d->cuboids[i]; PrimBox& b = prims[ns + i]; b.type = LGB_PRIM_CUBOID; b.index = (uint32_t)i;
+        for (int k = 0; k < 3; k++) { b.lo[k] = f32_down(std::min(c.min[k], c.max[k])); b.hi[k] = f32_up(std::max(c.min[k], c.max[k])); }
+    }
+    pool.for_range(nt, 1 << 14, [&](size_t b0, size_t e0, size_t) {
+        for (size_t i = b0; i < e0; i++) {
+            const lgb_triangle& t = d->triangles[i]; PrimBox& b = prims[ns + nc + i]; b.type = LGB_PRIM_TRIANGLE; b.index = (uint32_t)i;
+            for (int k = 0; k < 3; k++) { b.lo[k] = std::min(t.p0[k], std::min(t.p1[k], t.p2[k])); b.hi[k] = std::max(t.p0[k], std::max(t.p1[k], t.p2[k])); }
+        }
+    });
+    std::vector<size_t> sp_begin(nsp + 1, 0);
+    raw_vector<PrimBox> grouped;
+    const PrimBox* by_space = prims.data();
+    if (nsp > 1) {                               // stable counting sort of the primitives by space
+        auto space_of = [&](const PrimBox& b) { return out.prim_space[b.type][b.index]; };
+        for (size_t i = 0; i < np; i++) sp_begin[space_of(prims[i]) + 1]++;
+        for (size_t k = 0; k < nsp; k++) sp_begin[k + 1] += sp_begin[k];
+        std::vector<size_t> cursor(sp_begin.begin(), sp_begin.end() - 1);
+        grouped.resize(np);
+        for (size_t i = 0; i < np; i++) grouped[cursor[space_of(prims[i])]++] = prims[i];
+        by_space = grouped.data();
+    } else sp_begin[1] = np;
+    // ---- one SAH BVH per space, children before parents (a parent needs the boxes of its child spaces)
+    std::vector<BuiltBVH> bvh(nsp);
+    std::vector<std::array<float, 6>> root_box(nsp);
+    for (size_t k = nsp; k-- > 0;) {
+        HostSpace& sp = out.spaces[k];
+        raw_vector<PrimBox> items;
+        const PrimBox* it = by_space + sp_begin[k];
+        size_t n = sp_begin[k + 1] - sp_begin[k];
+        if (!children[k].empty()) {
+            items.resize(n + children[k].size());
+            std::copy(it, it + n, items.begin());
+            for (uint32_t c : children[k]) {
+                double lo[3], hi[3], tlo[3], thi[3];
+                for (int a = 0; a < 3; a++) { lo[a] = root_box[c][a]; hi[a] = root_box[c][3 + a]; }
+                xform_box(out.spaces[c].m, lo, hi, tlo, thi);
+                PrimBox& b = items[n++]; b.type = LGB_PRIM_INSTANCE; b.index = c;
+                for (int a = 0; a < 3; a++) { b.lo[a] = f32_down(std::min(tlo[a], thi[a])); b.hi[a] = f32_up(std::max(tlo[a], thi[a])); }
+            }
+            it = items.data();
+        }
+        if (n == 0) { err = "a nested aggregate has no primitives"; return -1; }
+        const int rc = build_sah(it, n, sp.err_abs, pool.threads(), bvh[k]);
+        if (rc) { err = rc == -2 ? "more than 16.7M primitives of one type" : "BVH build failed"; return rc == -2 ? -2 : -1; }
+        const HostNode& r = bvh[k].nodes[0];
+        for (int a = 0; a < 3; a++) { root_box[k][a] = std::min(r.v[a], r.v[6 + a]); root_box[k][3 + a] = std::max(r.v[3 + a], r.v[9 + a]); }
+        // traversal stack: the space's own tree, plus (resume entry + exit marker + the deepest child) under an instance leaf
+        uint32_t need = bvh[k].max_depth + 1, worst = 0;
+        for (uint32_t c : children[k]) worst = std::max(worst, out.spaces[c].stack_need);
+        sp.stack_need = need + (children[k].empty() ? 0 : 2 + worst);
+    }
+    // ---- concatenate: nodes and leaf-ordered primitive lists of all spaces, child words made absolute
+    uint32_t node_base = 0, tb[4] = {0, 0, 0, 0};
+    size_t node_total = 0, tt[4] = {0, 0, 0, 0};
+    for (size_t k = 0; k < nsp; k++) { node_total += bvh[k].nodes.size(); for (int t = 0; t < 4; t++) tt[t] += bvh[k].order[t].size(); }
+    for (int t = 0; t < 4; t++) { if (tt[t] > kLeafFirstMask) { err = "more than 16.7M primitives of one type"; return -2; } out.order[t].resize(tt[t]); }
+    if (nsp == 1) out.nodes.swap(bvh[0].nodes); else out.nodes.resize(node_total);
+    for (size_t k = 0; k < nsp; k++) {
+        out.spaces[k].root_node = node_base;
+        if (nsp > 1) {
+            const uint32_t nb = node_base; const uint32_t* tbp = tb;
+            auto rebase = [nb, tbp](uint32_t w) {
+                if (w & kLeafBit) { const uint32_t type = (w >> 29) & 3u; return (w & ~kLeafFirstMask) | ((w & kLeafFirstMask) + tbp[type]); }
+                return w + nb;
+            };
+            for (size_t i = 0; i < bvh[k].nodes.size(); i++) { HostNode nd = bvh[k].nodes[i]; nd.c0 = rebase(nd.c0); nd.c1 = rebase(nd.c1); out.nodes[node_base + i] = nd; }
+            node_base += (uint32_t)bvh[k].nodes.size();
+        }
+        for (int t = 0; t < 4; t++) { std::copy(bvh[k].order[t].begin(), bvh[k].order[t].end(), out.order[t].begin() + tb[t]); tb[t] += (uint32_t)bvh[k].order[t].size(); }
+    }
+    out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+bool build_rank_tables(const lgb_scene_desc* d, uint32_t prim_count, const BuiltScene& bs, uint32_t* rank) {
+    Pool& pool = Pool::get();
+    const size_t nsp = bs.spaces.size(), items = (size_t)prim_count + nsp;
+    pool.for_range((size_t)8 * items, 1 << 16, [&](size_t b, size_t e, size_t) { std::fill(rank + b, rank + e, 0xFFFFFFFFu); });
     std::atomic<bool> ok{true};
-    auto one = [&](size_t oct) {
-        uint32_t* r = rank + oct * prim_count;
+    std::vector<uint64_t> counted(8 * nsp, 0);
+    auto one = [&](size_t task) {
+        const size_t oct = task & 7, sidx = task >> 3;
+        uint32_t* r = rank + oct * items;
         uint32_t counter = 0;
-        // explicit DFS: entries are node indices; a leaf expands its primitives in order, recursing into
-        // nested BVHs immediately (bvh.rs:483-488 calls the nested intersect before the next primitive).
+        // explicit DFS: entries are node indices; a leaf expands its primitives in order, recursing into nested
+        // identity levels immediately (bvh.rs:483-488 calls the nested intersect before the next primitive); a
+        // nested level that opens its own space is ONE item here and is ranked again, inside, by its own octant.
         struct Frame { uint32_t node; uint32_t next_ref; };
         std::vector<Frame> st;
-        st.push_back({0, 0});
+        st.push_back({bs.spaces[sidx].ref_root, 0});
         while (!st.empty()) {
             Frame fr = st.back(); st.pop_back();
             const lgb_node& n = d->nodes[fr.node];
@@ -425,12 +590,14 @@ bool build_rank_tables(const lgb_scene_desc* d, uint32_t prim_count, int threads
                     const uint32_t ref = d->prim_refs[n.a + i], type = ref >> 30, idx = ref & 0x3FFFFFFFu;
                     uint32_t id;
                     if (type == LGB_PRIM_INSTANCE) {
-                        st.push_back({fr.node, i + 1});                       // resume this leaf afterwards
-                        st.push_back({d->instances[idx].root_node, 0});
-                        break;
-                    }
-                    id = type == LGB_PRIM_SPHERE ? d->sphere_id[idx] : type == LGB_PRIM_CUBOID ? d->cuboid_id[idx] : d->triangle_id[idx];
-                    if (id >= prim_count || r[id] != 0xFFFFFFFFu) { ok.store(false); return; }
+                        if (bs.inst_space[idx] == kNoSpace) {
+                            st.push_back({fr.node, i + 1});                       // resume this leaf afterwards
+                            st.push_back({d->instances[idx].root_node, 0});
+                            break;
+                        }
+                        id = prim_count + bs.inst_space[idx];
+                    } else id = type == LGB_PRIM_SPHERE ? d->sphere_id[idx] : type == LGB_PRIM_CUBOID ? d->cuboid_id[idx] : d->triangle_id[idx];
+                    if (id >= items || (type != LGB_PRIM_INSTANCE && id >= prim_count) || r[id] != 0xFFFFFFFFu) { ok.store(false); return; }
                     r[id] = counter++;
                 }
             } else {
@@ -440,10 +607,16 @@ bool build_rank_tables(const lgb_scene_desc* d, uint32_t prim_count, int threads
                 st.push_back({first, 0});
             }
         }
-        if (counter != prim_count) ok.store(false);
+        counted[task] = counter;
     };
-    pool.run(8, one);
-    return ok.load();
+    pool.run(8 * nsp, one);
+    if (!ok.load()) return false;
+    for (size_t oct = 0; oct < 8; oct++) {
+        uint64_t total = 0;
+        for (size_t sidx = 0; sidx < nsp; sidx++) total += counted[sidx * 8 + oct];
+        if (total != (uint64_t)prim_count + nsp - 1) return false;
+    }
+    return true;
 }
 
 }  // namespace lgb

@@ -96,12 +96,54 @@ __device__ __forceinline__ uint32_t canonical_id(const DevScene& S, uint32_t ref
     return __float_as_uint(S.tri[3 * (size_t)idx].w);
 }
 
+// ------------------------------------------------------------------ spaces (nested transformed aggregates)
+// Transform3::inverse_transform_ray (transform.rs:279-283) with cgmath's Matrix4 * Vector4 = c0 x + c1 y + c2 z + c3 w
+// (w = 1 for the origin, 0 for the direction; the matrices are affine, so transform_point's division by w is by 1).
+__device__ __forceinline__ D3 m4_apply(const double* m, D3 v, double w) {
+    return d3(m[0] * v.x + m[4] * v.y + m[8] * v.z + m[12] * w,
+              m[1] * v.x + m[5] * v.y + m[9] * v.z + m[13] * w,
+              m[2] * v.x + m[6] * v.y + m[10] * v.z + m[14] * w);
+}
+__device__ __forceinline__ Ray64 ray_into(const DevSpace& sp, const Ray64& r) {
+    Ray64 o; o.o = m4_apply(sp.minv, r.o, 1.0); o.d = m4_apply(sp.minv, r.d, 0.0);
+    return o;
+}
+// The world ray taken down the chain of transforms to `space`, level by level as the reference does (bvh.rs:462).
+__device__ __noinline__ Ray64 ray_to_space(const DevScene& S, uint32_t space, const Ray64& world) {
+    uint32_t chain[kMaxSpaceDepth]; int n = 0;
+    for (uint32_t s = space; s != kNoParent; s = S.spaces[s].parent) chain[n++] = s;
+    Ray64 r = world;
+    while (n--) { const DevSpace& sp = S.spaces[chain[n]]; if (!(sp.flags & kSpaceIdentity)) r = ray_into(sp, r); }
+    return r;
+}
+__device__ __forceinline__ uint32_t space_of(const DevScene& S, uint32_t ref) {
+    const uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+    return type == LGB_PRIM_SPHERE ? S.sph_space[idx] : type == LGB_PRIM_CUBOID ? S.cub_space[idx] : S.tri_space[idx];
+}
+__device__ __forceinline__ unsigned octant_of(const Ray64& r) {                  // bvh.rs:463 on Ray::new's dinv (ray.rs:28-33)
+    return (1.0 / r.d.x < 0.0 ? 1u : 0u) | (1.0 / r.d.y < 0.0 ? 2u : 0u) | (1.0 / r.d.z < 0.0 ? 4u : 0u);
+}
+// Exact-t tie between two primitives of an instanced scene: both are lifted to their deepest common space (a nested
+// level stands for everything below it) and compared by that level's test order for the ray's octant THERE.
+__device__ __noinline__ bool rank_before_instanced(const DevScene& S, const Ray64& world, uint32_t ref_a, uint32_t ref_b) {
+    uint32_t ia = canonical_id(S, ref_a), sa = space_of(S, ref_a), ib = canonical_id(S, ref_b), sb = space_of(S, ref_b);
+    uint32_t da = S.spaces[sa].depth, db = S.spaces[sb].depth;
+    while (da > db) { ia = S.prim_count + sa; sa = S.spaces[sa].parent; da--; }
+    while (db > da) { ib = S.prim_count + sb; sb = S.spaces[sb].parent; db--; }
+    while (sa != sb) { ia = S.prim_count + sa; sa = S.spaces[sa].parent; ib = S.prim_count + sb; sb = S.spaces[sb].parent; }
+    const Ray64 r = ray_to_space(S, sa, world);
+    const uint32_t* rk = S.rank + (size_t)octant_of(r) * S.rank_items;
+    return rk[ia] < rk[ib];
+}
+
 // A candidate with exact parameter t replaces the current best iff it is nearer, or equally near and
 // earlier in the reference's own traversal order for this ray's octant (lgb_build.hpp).
-__device__ __forceinline__ bool accepts(const DevScene& S, const RayF& f, const Hit& best, double t, uint32_t ref) {
+template <bool INST>
+__device__ __forceinline__ bool accepts(const DevScene& S, const RayF& f, const Ray64& world, const Hit& best, double t, uint32_t ref) {
     if (t < best.t) return true;
     if (t == best.t && best.ref != LGB_MISS) {
-        const uint32_t* r = S.rank + (size_t)f.oct * S.prim_count;
+        if (INST) return rank_before_instanced(S, world, ref, best.ref);
+        const uint32_t* r = S.rank + (size_t)f.oct * S.rank_items;
         return r[canonical_id(S, ref)] < r[canonical_id(S, best.ref)];
     }
     return false;
@@ -142,8 +184,9 @@ struct Trav {                 // resumable traversal state of one ray
     float best_tf, best_up;
     uint32_t cur;
     int sp;
-    __device__ __forceinline__ void init(double tmax) {
-        best.t = tmax; best.ref = LGB_MISS; best_tf = __double2float_ru(tmax); best_up = inflate_up(tmax); cur = 0; sp = 0;
+    uint32_t space;           // instanced scenes: the space the ray is in right now
+    __device__ __forceinline__ void init(double tmax, uint32_t root = 0) {
+        best.t = tmax; best.ref = LGB_MISS; best_tf = __double2float_ru(tmax); best_up = inflate_up(tmax); cur = root; sp = 0; space = 0;
     }
 };
 
@@ -190,14 +233,19 @@ __device__ __forceinline__ void node_loop(const DevScene& S, const RayF& f, floa
 // Runs until the ray is finished (returns true; T.cur == kDone) or, with REFILL, until fewer than
 // `refill_below` lanes of the warp are still traversing (returns false: the caller tops the warp up with
 // new rays and calls again; persistent threads with dynamic fetch).
-template <bool ANYHIT, bool STATS, bool REFILL>
-__device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& ray, const RayF& f, Trav& T, uint32_t* stack, float* tstack, double tmax,
+// INST (scenes with transformed aggregates): `ray` / `f` are the ray in the CURRENT space and change when the
+// traversal enters or leaves a nested level; `world` is the ray as cast.  A leaf of type LGB_PRIM_INSTANCE lists child
+// spaces; entering one defers the rest of the leaf and an exit marker (count field 31, payload = space to return to).
+constexpr uint32_t kInstLeaf = kLeafBit | ((uint32_t)LGB_PRIM_INSTANCE << 29);
+constexpr uint32_t kExitMarker = kInstLeaf | (31u << 24);
+template <bool ANYHIT, bool STATS, bool REFILL, bool INST>
+__device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& world, Ray64& ray, RayF& f, Trav& T, uint32_t* stack, float* tstack, double tmax,
                                          LocalCounters& lc, int refill_below, unsigned octw) {
     Hit& best = T.best;
     float& best_tf = T.best_tf; float& best_up = T.best_up;
     uint32_t& cur = T.cur; int& sp = T.sp;
     for (;;) {
-        switch (octw) {        // warp-uniform: the octant shared by every ray of the warp, or 8 (mixed)
+        switch (INST ? f.oct : octw) {   // octw is warp-uniform: the octant shared by every ray of the warp, or 8 (mixed)
         case 0: node_loop<0, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
         case 1: node_loop<1, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
         case 2: node_loop<2, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
@@ -211,7 +259,24 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& ray, co
         if (cur == kDone) return true;
         {
             const uint32_t type = (cur >> 29) & 3u, count = ((cur >> 24) & 31u) + 1u, first = cur & kLeafFirstMask;
-            if (type == LGB_PRIM_TRIANGLE) {
+            if (INST && type == LGB_PRIM_INSTANCE) {
+                if (count == 32u) {                                   // exit marker: the nested level is done
+                    T.space = first;
+                    ray = ray_to_space(S, first, world);
+                    f = make_rayf(ray, S.spaces[first].err_abs);
+                } else {
+                    if (count > 1u) { if (!ANYHIT) tstack[sp] = -CUDART_INF_F; stack[sp++] = kInstLeaf | ((count - 2u) << 24) | (first + 1u); }
+                    if (!ANYHIT) tstack[sp] = -CUDART_INF_F;
+                    stack[sp++] = kExitMarker | T.space;
+                    const uint32_t child = __ldg(&S.inst_space[first]);
+                    const DevSpace& c = S.spaces[child];
+                    if (!(c.flags & kSpaceIdentity)) ray = ray_into(c, ray);
+                    f = make_rayf(ray, c.err_abs);
+                    T.space = child;
+                    cur = c.root_node;
+                    continue;
+                }
+            } else if (type == LGB_PRIM_TRIANGLE) {
                 for (uint32_t i = 0; i < count; i++) {
                     const uint32_t idx = first + i;
                     const float4* tp = S.tri + 3 * (size_t)idx;
@@ -224,7 +289,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& ray, co
                     if (triangle_exact(d3(q0.x, q0.y, q0.z), d3(q1.x, q1.y, q1.z), d3(q2.x, q2.y, q2.z), ray, t, b0, b1, b2)) {
                         const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_TRIANGLE, idx);
                         if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; cur = kDone; return true; } }
-                        else if (accepts(S, f, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
+                        else if (accepts<INST>(S, f, world, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
                     }
                 }
             } else if (type == LGB_PRIM_SPHERE) {
@@ -250,7 +315,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& ray, co
                     if (sphere_exact(d3(c01.x, c01.y, c23.x), c23.y, ray, t, inside)) {
                         const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_SPHERE, idx);
                         if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; cur = kDone; return true; } }
-                        else if (accepts(S, f, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
+                        else if (accepts<INST>(S, f, world, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
                     }
                 }
             } else {
@@ -268,7 +333,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& ray, co
                     if (cuboid_exact(mn, mx, ray, t, ua, va)) {
                         const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_CUBOID, idx);
                         if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; cur = kDone; return true; } }
-                        else if (accepts(S, f, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
+                        else if (accepts<INST>(S, f, world, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
                     }
                 }
             }
@@ -278,13 +343,27 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& ray, co
     }
 }
 
-template <bool ANYHIT, bool STATS>
-__device__ Hit traverse(const DevScene& S, const Ray64& ray, double tmax, LocalCounters& lc) {
-    const RayF f = make_rayf(ray, S.err_abs);
+// First ray of a traversal: the world ray in space 0 (the root aggregate may itself be transformed).
+template <bool INST>
+__device__ __forceinline__ void enter_root(const DevScene& S, const Ray64& world, Ray64& ray, RayF& f, Trav& T, double tmax) {
+    ray = world;
+    float err = S.err_abs;
+    uint32_t root = 0;
+    if (INST) {
+        const DevSpace& s0 = S.spaces[0];
+        if (!(s0.flags & kSpaceIdentity)) ray = ray_into(s0, world);
+        err = s0.err_abs; root = s0.root_node;
+    }
+    f = make_rayf(ray, err);
+    T.init(tmax, root);
+}
+template <bool ANYHIT, bool STATS, bool INST>
+__device__ Hit traverse(const DevScene& S, const Ray64& world, double tmax, LocalCounters& lc) {
+    Ray64 ray; RayF f; Trav T;
+    enter_root<INST>(S, world, ray, f, T, tmax);
     uint32_t stack[kStackDepth];      // depth is bounded at scene creation (lgb_api.cu), so pushes are unchecked
     float tstack[ANYHIT ? 1 : kStackDepth];
-    Trav T; T.init(tmax);
-    trav_run<ANYHIT, STATS, false>(S, ray, f, T, stack, tstack, tmax, lc, 0, 8u);
+    trav_run<ANYHIT, STATS, false, INST>(S, world, ray, f, T, stack, tstack, tmax, lc, 0, 8u);
     return T.best;
 }
 
@@ -354,6 +433,30 @@ __device__ void surface_of(const DevScene& S, const Ray64& ray, uint32_t ref, do
             sf.n = face_forward(cross(dp02, dp12), -ray.d);
         }
         sf.material = __float_as_uint(q1.w); sf.id = __float_as_uint(q0.w);
+    }
+}
+
+// The local record taken back to world space, level by level from the innermost space outwards:
+// transform_ray_intersection (transform.rs:243-264) then swap_backface (surface.rs:88-99, bvh.rs:510-518).
+__device__ __noinline__ void record_to_world(const DevScene& S, uint32_t space, Surf& sf) {
+    for (uint32_t s = space; s != kNoParent; s = S.spaces[s].parent) {
+        const DevSpace& sp = S.spaces[s];
+        if (!(sp.flags & kSpaceIdentity)) {
+            const bool shading_differs = sf.g_dpdu.x != sf.s_dpdu.x || sf.g_dpdu.y != sf.s_dpdu.y || sf.g_dpdu.z != sf.s_dpdu.z ||
+                                         sf.g_dpdv.x != sf.s_dpdv.x || sf.g_dpdv.y != sf.s_dpdv.y || sf.g_dpdv.z != sf.s_dpdv.z;
+            sf.g_dpdu = m4_apply(sp.m, sf.g_dpdu, 0.0); sf.g_dpdv = m4_apply(sp.m, sf.g_dpdv, 0.0);
+            if (shading_differs) { sf.s_dpdu = m4_apply(sp.m, sf.s_dpdu, 0.0); sf.s_dpdv = m4_apply(sp.m, sf.s_dpdv, 0.0); }
+            else { sf.s_dpdu = sf.g_dpdu; sf.s_dpdv = sf.g_dpdv; }               // RayIntersection::new, surface.rs:57-62
+            if (sf.has_n) {                                                      // transform_normal, transform.rs:203-210
+                const double* mi = sp.minv; const D3 n = sf.n;
+                sf.n = d3(mi[0] * n.x + mi[1] * n.y + mi[2] * n.z, mi[4] * n.x + mi[5] * n.y + mi[6] * n.z, mi[8] * n.x + mi[9] * n.y + mi[10] * n.z);
+            }
+        }
+        if (sp.flags & kSpaceSwap) {
+            D3 tmp = sf.g_dpdu; sf.g_dpdu = sf.g_dpdv; sf.g_dpdv = tmp;
+            tmp = sf.s_dpdu; sf.s_dpdu = sf.s_dpdv; sf.s_dpdv = tmp;
+            if (sf.has_n) sf.n = -sf.n;
+        }
     }
 }
 
@@ -430,10 +533,15 @@ __device__ __forceinline__ double lerp64(double t, double a, double b) { return 
 // + Material::scattering, plastic.rs:20-37 / matte.rs:18-26).
 struct ShadePoint { D3 wo, ng, ns, ps; Bsdf B; };
 
-template <bool WITH_BSDF>
+template <bool WITH_BSDF, bool INST>
 __device__ __forceinline__ void shade_point(const DevScene& S, const Ray64& ray, double t, uint32_t ref, ShadePoint& P, uint32_t& id) {
     Surf sf; double t_again = t;
-    surface_of(S, ray, ref, t_again, sf);
+    if (INST) {                      // the record is formed in the primitive's own space, then brought back (bvh.rs:508-518)
+        const uint32_t space = space_of(S, ref);
+        const Ray64 local = ray_to_space(S, space, ray);
+        surface_of(S, local, ref, t_again, sf);
+        record_to_world(S, space, sf);
+    } else surface_of(S, ray, ref, t_again, sf);
     id = sf.id;
     P.wo = -normalize(ray.d);
     P.ng = face_forward(normalize(cross(sf.g_dpdu, sf.g_dpdv)), P.wo);
@@ -566,7 +674,7 @@ __device__ __forceinline__ void block_append(AppendScratch& sc, bool mine, uint3
     __syncthreads();          // scratch is reused by the next call
 }
 
-template <bool STATS>
+template <bool STATS, bool INST>
 __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
     const uint64_t total = W.n_pixels * W.spp;
     const unsigned lane = threadIdx.x & 31u;
@@ -574,7 +682,7 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, Dev
     unsigned int hits = 0, primary = 0;
     uint32_t stack[kStackDepth];
     float tstack[kStackDepth];
-    Ray64 ray; RayF f; Trav T;
+    Ray64 world, ray; RayF f; Trav T;      // INST: `ray` is the ray in the current space; otherwise it stays equal to `world`
     uint64_t g = 0;
     bool active = false, drained = false;
     for (;;) {
@@ -589,8 +697,8 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, Dev
                         if (idx >= total) { need = false; }
                         else {
                             uint32_t x, y, s;
-                            if (slot_ray(C, W, idx, ray, x, y, s)) {
-                                g = idx; f = make_rayf(ray, S.err_abs); T.init(CUDART_INF); active = true; need = false; primary++;
+                            if (slot_ray(C, W, idx, world, x, y, s)) {
+                                g = idx; enter_root<INST>(S, world, ray, f, T, CUDART_INF); active = true; need = false; primary++;
                             } else {
                                 V.hit_t[idx] = CUDART_INF; V.hit_ref[idx] = kSlotUnused;       // pixel outside the film: take another
                             }
@@ -605,7 +713,7 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, Dev
         const unsigned oct0 = __shfl_sync(0xFFFFFFFFu, f.oct, __ffs(amask) - 1);
         const unsigned octw = __all_sync(0xFFFFFFFFu, !active || f.oct == oct0) ? oct0 : 8u;
         if (active) {
-            const bool done = trav_run<false, STATS, true>(S, ray, f, T, stack, tstack, CUDART_INF, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
+            const bool done = trav_run<false, STATS, true, INST>(S, world, ray, f, T, stack, tstack, CUDART_INF, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
             if (done) {
                 const bool hit = T.best.ref != LGB_MISS;
                 V.hit_t[g] = hit ? T.best.t : CUDART_INF; V.hit_ref[g] = T.best.ref;
@@ -628,7 +736,7 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, Dev
     }
 }
 
-template <bool ALL_SHADOWS>
+template <bool ALL_SHADOWS, bool INST>
 __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
     const uint64_t total = W.n_pixels * W.spp;
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -653,7 +761,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
                 live = true;
                 const double t = V.hit_t[g];
                 ShadePoint P; uint32_t id;
-                shade_point<false>(S, ray, t, ref, P, id);
+                shade_point<false, INST>(S, ray, t, ref, P, id);
                 V.ps[3 * g + 0] = P.ps.x; V.ps[3 * g + 1] = P.ps.y; V.ps[3 * g + 2] = P.ps.z;
                 if (O.aov_id) O.aov_id[gi] = id;
                 if (O.aov_t) O.aov_t[gi] = t;
@@ -682,8 +790,11 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
 
 // Exact test of ONE primitive against a shadow ray: true iff the reference's intersect accepts it with t < 1
 // (the same calls the traversal makes for a candidate, light/point.rs:48-49).
-__device__ __forceinline__ bool occludes(const DevScene& S, uint32_t ref, const Ray64& ray) {
+template <bool INST>
+__device__ __forceinline__ bool occludes(const DevScene& S, uint32_t ref, const Ray64& world) {
     const uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+    Ray64 ray = world;
+    if (INST) ray = ray_to_space(S, space_of(S, ref), world);
     double t;
     if (type == LGB_PRIM_TRIANGLE) {
         const float4* tp = S.tri + 3 * (size_t)idx;
@@ -705,6 +816,7 @@ __device__ __forceinline__ bool occludes(const DevScene& S, uint32_t ref, const 
 }
 
 // Queue B -> occl bit (blocked by the occluder the pixel's anchor ray found) or queue C (needs a traversal).
+template <bool INST>
 __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light) {
     __shared__ AppendScratch sc;
     const unsigned total = V.queue_count[light * 3 + kQueueB];
@@ -724,7 +836,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork 
                 Ray64 ray;
                 ray.o = d3(V.ps[3 * (size_t)g], V.ps[3 * (size_t)g + 1], V.ps[3 * (size_t)g + 2]);
                 ray.d = lp - ray.o;                                                  // light/point.rs:43-44
-                if (occludes(S, oc, ray)) { V.occl[g] |= 1u << light; to_c = false; ncached++; }   // sole writer of occl[g] in this launch
+                if (occludes<INST>(S, oc, ray)) { V.occl[g] |= 1u << light; to_c = false; ncached++; }   // sole writer of occl[g] in this launch
             }
         }
         block_append(sc, to_c, g, V.queue + (size_t)(light * 3 + kQueueC) * V.queue_stride, &V.queue_count[light * 3 + kQueueC]);
@@ -736,7 +848,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork 
     }
 }
 
-template <bool STATS>
+template <bool STATS, bool INST>
 __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light, int which) {
     const unsigned total = V.queue_count[light * 3 + which];
     const uint32_t* q = V.queue + (size_t)(light * 3 + which) * V.queue_stride;
@@ -747,7 +859,7 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevW
     LocalCounters lc = {};
     unsigned int occluded = 0;
     uint32_t stack[kStackDepth];
-    Ray64 ray; RayF f; Trav T;
+    Ray64 world, ray; RayF f; Trav T;
     uint32_t g = 0;
     bool active = false, drained = false;
     for (;;) {
@@ -757,9 +869,9 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevW
                 const unsigned long long idx = warp_fetch(V.queue_fetch + light * 3 + which, !active, lane);
                 if (!active && idx < total) {
                     g = q[idx];
-                    ray.o = d3(V.ps[3 * (size_t)g], V.ps[3 * (size_t)g + 1], V.ps[3 * (size_t)g + 2]);
-                    ray.d = lp - ray.o;                                          // light/point.rs:43-44
-                    f = make_rayf(ray, S.err_abs); T.init(1.0); active = true;
+                    world.o = d3(V.ps[3 * (size_t)g], V.ps[3 * (size_t)g + 1], V.ps[3 * (size_t)g + 2]);
+                    world.d = lp - world.o;                                      // light/point.rs:43-44
+                    enter_root<INST>(S, world, ray, f, T, 1.0); active = true;
                 }
                 drained = __any_sync(0xFFFFFFFFu, idx != ~0ull && idx >= total);
             }
@@ -769,7 +881,7 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevW
         const unsigned oct0 = __shfl_sync(0xFFFFFFFFu, f.oct, __ffs(amask) - 1);
         const unsigned octw = __all_sync(0xFFFFFFFFu, !active || f.oct == oct0) ? oct0 : 8u;
         if (active) {
-            const bool done = trav_run<true, STATS, true>(S, ray, f, T, stack, nullptr, 1.0, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
+            const bool done = trav_run<true, STATS, true, INST>(S, world, ray, f, T, stack, nullptr, 1.0, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
             if (done) {
                 if (T.best.ref != LGB_MISS) { atomicOr(&V.occl[g], 1u << light); occluded++; }
                 if (record) V.occluder[(size_t)light * W.n_pixels + g / W.spp] = T.best.ref;
@@ -795,6 +907,7 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevW
 #ifndef LGB_SHADE_MIN_BLOCKS
 #define LGB_SHADE_MIN_BLOCKS 4
 #endif
+template <bool INST>
 __global__ void __launch_bounds__(256, LGB_SHADE_MIN_BLOCKS) k_shade(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
     const double PI = 3.14159265358979323846264338327950288;
     const uint64_t total = W.n_pixels * W.spp;
@@ -805,7 +918,7 @@ __global__ void __launch_bounds__(256, LGB_SHADE_MIN_BLOCKS) k_shade(DevScene S,
     Ray64 ray; uint32_t x, y, s;
     if (!slot_ray(C, W, g, ray, x, y, s)) return;
     ShadePoint P; uint32_t id;
-    shade_point<true>(S, ray, V.hit_t[g], ref, P, id);
+    shade_point<true, INST>(S, ray, V.hit_t[g], ref, P, id);
     const uint32_t occl = V.occl[g];
     if (O.aov_occl) O.aov_occl[((uint64_t)y * W.w + x) * W.spp + s] = occl;
     D3 output = d3(0, 0, 0);
@@ -847,16 +960,21 @@ __global__ void __launch_bounds__(256) k_resolve(DevWork W, DevOut O) {
 }
 
 // Caller-supplied rays (lgb_trace_rays): closest hit id, t, RayIntersection::ng()/ns() (surface.rs:107-118)
+template <bool INST>
 __global__ void __launch_bounds__(128) k_trace(DevScene S, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ngs, double* nss) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Ray64 ray; ray.o = d3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]); ray.d = d3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
     LocalCounters lc = {};
-    Hit h = traverse<false, false>(S, ray, CUDART_INF, lc);
+    Hit h = traverse<false, false, INST>(S, ray, CUDART_INF, lc);
     uint32_t id = LGB_MISS; D3 ng = d3(0, 0, 0), ns = d3(0, 0, 0);
     if (h.ref != LGB_MISS) {
         Surf sf; double t = h.t;
-        surface_of(S, ray, h.ref, t, sf);
+        if (INST) {
+            const uint32_t space = space_of(S, h.ref);
+            surface_of(S, ray_to_space(S, space, ray), h.ref, t, sf);
+            record_to_world(S, space, sf);
+        } else surface_of(S, ray, h.ref, t, sf);
         id = sf.id;
         ng = normalize(cross(sf.g_dpdu, sf.g_dpdv));
         ns = sf.has_n ? normalize(sf.n) : normalize(cross(sf.s_dpdu, sf.s_dpdv));
@@ -913,25 +1031,29 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     const bool cache = W.spp > 1;
     if (cache && S.n_lights && (e = cudaMemsetAsync(V.occluder, 0xFF, (size_t)S.n_lights * W.n_pixels * 4, stream)) != cudaSuccess) return e;
     const unsigned pblocks = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)sms * LGB_MIN_BLOCKS);
-    if (stats) k_primary<true><<<pblocks, 256, 0, stream>>>(S, C, W, O, V);
-    else k_primary<false><<<pblocks, 256, 0, stream>>>(S, C, W, O, V);
+    const bool inst = S.instanced != 0;      // transformed aggregates: the INST kernel variants (the plain ones carry no trace of them)
+    if (inst) { if (stats) k_primary<true, true><<<pblocks, 256, 0, stream>>>(S, C, W, O, V); else k_primary<false, true><<<pblocks, 256, 0, stream>>>(S, C, W, O, V); }
+    else { if (stats) k_primary<true, false><<<pblocks, 256, 0, stream>>>(S, C, W, O, V); else k_primary<false, false><<<pblocks, 256, 0, stream>>>(S, C, W, O, V); }
     mark(1);
     const unsigned blocks = (unsigned)((total + 255) / 256), ablocks = (unsigned)((total + kAppendThreads - 1) / kAppendThreads);
-    if (all_shadows) k_setup<true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
-    else k_setup<false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
+    if (inst) { if (all_shadows) k_setup<true, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); }
+    else { if (all_shadows) k_setup<true, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); }
     mark(2);
     // anchor rays (queue A), then the cached-occluder test of the rest (B -> C), then the survivors (queue C)
     for (int which = kQueueA; which <= (cache ? kQueueC : kQueueA); which += 2) {
         const unsigned sb = which == kQueueA ? (unsigned)std::min<uint64_t>((W.n_pixels + 255) / 256, pblocks) : pblocks;
         for (uint32_t l = 0; l < S.n_lights; l++) {
-            if (which == kQueueC) k_pretest<<<(unsigned)std::min<uint64_t>(ablocks, (uint64_t)sms * 4), kAppendThreads, 0, stream>>>(S, W, O, V, l);
-            if (stats) k_shadow<true><<<sb, 256, 0, stream>>>(S, W, O, V, l, which);
-            else k_shadow<false><<<sb, 256, 0, stream>>>(S, W, O, V, l, which);
+            if (which == kQueueC) {
+                const unsigned tb = (unsigned)std::min<uint64_t>(ablocks, (uint64_t)sms * 4);
+                if (inst) k_pretest<true><<<tb, kAppendThreads, 0, stream>>>(S, W, O, V, l); else k_pretest<false><<<tb, kAppendThreads, 0, stream>>>(S, W, O, V, l);
+            }
+            if (inst) { if (stats) k_shadow<true, true><<<sb, 256, 0, stream>>>(S, W, O, V, l, which); else k_shadow<false, true><<<sb, 256, 0, stream>>>(S, W, O, V, l, which); }
+            else { if (stats) k_shadow<true, false><<<sb, 256, 0, stream>>>(S, W, O, V, l, which); else k_shadow<false, false><<<sb, 256, 0, stream>>>(S, W, O, V, l, which); }
         }
         if (which == kQueueA) mark(3);
     }
     mark(4);
-    k_shade<<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+    if (inst) k_shade<true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
     mark(5);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
@@ -940,7 +1062,8 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
 }
 cudaError_t launch_trace(const DevScene& S, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    k_trace<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(S, rays, n, ids, ts, ng, ns);
+    if (S.instanced) k_trace<true><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(S, rays, n, ids, ts, ng, ns);
+    else k_trace<false><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(S, rays, n, ids, ts, ng, ns);
     return cudaGetLastError();
 }
 cudaError_t launch_l2_read(const void* buf, uint64_t bytes, int iters, float* sink, int sms, cudaStream_t stream) {

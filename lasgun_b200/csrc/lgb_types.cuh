@@ -17,6 +17,16 @@ constexpr uint32_t kLeafBit = 0x80000000u;       // child word encoding, see lgb
 constexpr uint32_t kLeafFirstMask = 0x00FFFFFFu;
 #endif
 constexpr uint32_t kDone = 0x7FFFFFFFu;          // traversal sentinel (never a valid node index)
+constexpr int kMaxSpaceDepth = 8;                // nested transformed aggregates along one path
+constexpr uint32_t kSpaceIdentity = 1u, kSpaceSwap = 2u;
+constexpr uint32_t kNoParent = 0xFFFFFFFFu;
+
+// One coordinate system of the scene (lgb_build.hpp): cgmath column-major Transform3 of the aggregate that opens it.
+struct DevSpace {
+    double m[16], minv[16];
+    uint32_t parent, depth, root_node, flags;
+    float err_abs; uint32_t pad[3];
+};
 
 // All pointers are device pointers.  Layout:
 //   nodes      4 x float4 per node: child0 {lo.xyz, hi.xyz}, child1 {lo.xyz, hi.xyz}, {child0, child1, -, -};
@@ -44,7 +54,13 @@ struct DevScene {
     const uint32_t* rank;
     const double* materials;
     const double* lights;
+    const DevSpace* spaces;       // instanced scenes only (n_spaces > 1 or a transformed root)
+    const uint32_t* inst_space;   // leaf-ordered child-space ids (leaf type LGB_PRIM_INSTANCE)
+    const uint32_t* sph_space; const uint32_t* cub_space; const uint32_t* tri_space;   // space of every primitive, leaf order
     uint32_t prim_count;
+    uint32_t rank_items;          // prim_count + n_spaces: stride of one octant's rank table
+    uint32_t n_spaces;
+    uint32_t instanced;
     uint32_t n_lights;
     uint32_t n_nodes;
     float err_abs;        // absolute coordinate error bound of an f32 ray against this scene (see lgb_api.cu)

@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-from .api import Material, ObjData, Scene
+from .api import Aggregate, Material, ObjData, Scene
 
 _MASK = (1 << 64) - 1
 
@@ -176,6 +176,76 @@ def mixed4k(mesh_n=500, nspheres=100_000, res=(3840, 2160), supersampling=3):
     centers = np.stack([R * np.sin(theta) * np.cos(phi), R * np.cos(theta), R * np.sin(theta) * np.sin(phi)], axis=-1)
     scene.root.add_spheres(centers, rad, _cube_palette(), np.arange(nspheres) % 8)
     scene.root.add_box([-600.0, -130.0, -600.0], [600.0, -120.0, 600.0], Material.plastic([0.6, 0.6, 0.6], [0.0, 0.0, 0.0], 0.25))
+    return scene, tuple(res)
+
+
+def plane_mesh() -> ObjData:
+    """Unit plane y = 0 over [-1, 1]^2 (stand-in for the Git-LFS-only meshes/plane.obj of src/examples/cornell.rs:25)."""
+    pos = np.array([[-1, 0, -1], [1, 0, -1], [1, 0, 1], [-1, 0, 1]], np.float32)
+    return ObjData(pos, np.array([[0, 2, 1], [0, 3, 2]], np.uint32))
+
+
+def cornell_groups(res=(512, 512), supersampling=2, eye=(0.0, 0.0, 5.0)):
+    """The reference's own Cornell box (src/examples/cornell.rs): five plane meshes inside scaled / rotated /
+    translated groups (nested BVH levels with transforms, bvh.rs:462-518); the two glass objects are plastic here.
+    With the reference's on-axis eye, the rays of the image diagonals run exactly along the edges where two walls
+    meet; pass a slightly off-axis `eye` for a scene without those measure-zero grazing rays."""
+    scene = Scene()
+    scene.set_ambient_light([0.2, 0.2, 0.2])
+    camera = scene.set_perspective_camera(60.0)
+    camera.look_at(list(eye), [0.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+    camera.set_supersampling(supersampling)
+    ks = [0.5, 0.7, 0.5]
+    white = Material.plastic([0.9, 0.9, 0.9], ks, 0.25)
+    red = Material.plastic([1.0, 0.0, 0.0], ks, 0.25)
+    green = Material.plastic([0.0, 1.0, 0.0], ks, 0.25)
+    plane = scene.add_obj(plane_mesh())
+    scene.add_point_light([0.0, 1.75, 0.0], [0.9, 0.9, 0.9], [1.0, 0.0, 0.0])
+    for ops, mat in ((("translate", [0.0, -2.0, 0.0]),), white), ((("translate", [0.0, 2.0, 0.0]),), white), \
+                    ((("rotate_z", 90.0), ("translate", [-2.0, 0.0, 0.0])), red), ((("rotate_z", 90.0), ("translate", [2.0, 0.0, 0.0])), green), \
+                    ((("rotate_x", 90.0), ("translate", [0.0, 0.0, -2.0])), white):
+        g = Aggregate()
+        g.scale(2.0, 1.0, 2.0)                                     # cornell.rs:32-64
+        for name, arg in ops:
+            getattr(g, name)(arg)
+        g.add_obj_of(plane, mat)
+        scene.root.add_group(g)
+    scene.root.add_sphere([1.0, -1.25, 0.0], 1.0, Material.plastic([1.0, 0.7, 1.0], [0.7, 1.0, 0.7], 0.25))
+    scene.root.add_cube([-1.999, -1.999, 0.0], 1.0, Material.plastic([0.7, 0.7, 1.0], [0.4, 0.4, 0.4], 0.25))
+    return scene, tuple(res)
+
+
+def nested_groups(res=(320, 240), supersampling=1, transformed_root=False, mesh_n=24):
+    """Transforms two levels deep, a swap_backface level, spheres / cubes / a mesh inside transformed groups, and
+    (optionally) a transformed ROOT aggregate: every branch of the nested-level code (bvh.rs:462-518)."""
+    scene = Scene()
+    scene.set_ambient_light([0.15, 0.15, 0.15])
+    scene.set_radial_background([0.2, 0.3, 0.5], [0.05, 0.05, 0.1], 0.6)
+    camera = scene.set_perspective_camera(50.0)
+    camera.look_at([3.0, 4.0, 14.0], [0.0, 0.5, 0.0], [0.0, 1.0, 0.0])
+    camera.set_supersampling(supersampling)
+    scene.add_point_light([6.0, 9.0, 8.0], [0.8, 0.8, 0.8], [1.0, 0.0, 0.0])
+    scene.add_point_light([-7.0, 5.0, 3.0], [0.4, 0.5, 0.6], [1.0, 0.0, 0.0])
+    pal = _cube_palette()
+    mesh = scene.add_obj(mesh_grid(mesh_n, 1.0))
+    r = scene.root
+    r.add_box([-8.0, -1.2, -8.0], [8.0, -1.0, 8.0], Material.plastic([0.6, 0.6, 0.6], [0.1, 0.1, 0.1], 0.3))
+    r.add_sphere([0.0, 0.0, 0.0], 1.0, pal[1])
+    a = Aggregate()                                   # level 1: scale + rotate + translate
+    a.scale(1.5, 0.7, 1.2); a.rotate_y(30.0); a.translate([3.0, 0.4, -1.0])
+    a.add_sphere([0.0, 0.0, 0.0], 1.0, pal[2]); a.add_sphere([1.6, 0.3, 0.2], 0.6, pal[3]); a.add_cube([-2.5, -1.0, -0.5], 1.0, pal[4])
+    b = Aggregate()                                   # level 2, inside level 1, with flipped normals
+    b.rotate_z(45.0); b.translate([0.0, 2.2, 0.0]); b.swap_backface()
+    b.add_obj_of(mesh, pal[5]); b.add_sphere([1.4, 0.0, 0.0], 0.4, pal[6])
+    a.add_group(b)
+    r.add_group(a)
+    c = Aggregate()                                   # an identity group (traversed inline) holding a transformed one
+    d = Aggregate(); d.rotate(70.0, [0.0, 0.6, 0.8]); d.translate([-3.5, 0.8, 1.5])
+    d.add_cube([-0.5, -0.5, -0.5], 1.0, pal[7]); d.add_obj_of(mesh, pal[0])
+    c.add_group(d); c.add_sphere([-1.5, -0.4, 3.0], 0.6, pal[3])
+    r.add_group(c)
+    if transformed_root:
+        r.rotate_y(-20.0); r.translate([0.5, 0.0, -1.0])
     return scene, tuple(res)
 
 

@@ -1262,12 +1262,17 @@ void orc_test_surface(double t, const double* dpdu, const double* dpdv, const do
 // returns t or +inf.  The primitive is located by canonical id through the accel.
 double orc_retest_prim(void* accel, uint32_t prim_id, const double* o, const double* d) {
     Accel* acc = (Accel*)accel;
-    Ray ray = ray_new(v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]));
-    std::vector<const BVH*> st{acc->root.get()};
+    Ray world = ray_new(v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]));
+    // every nested level sees the ray through its own inverse transform, applied level by level (bvh.rs:462)
+    std::vector<std::pair<const BVH*, Ray>> st;
+    st.push_back({acc->root.get(), ray_new(m4_point(acc->root->transform.minv, world.o), m4_vector(acc->root->transform.minv, world.d))});
     while (!st.empty()) {
-        const BVH* b = st.back(); st.pop_back();
+        const BVH* b = st.back().first; const Ray ray = st.back().second; st.pop_back();
         for (auto& p : b->primitives) {
-            if (auto c = dynamic_cast<const BVH*>(p.get())) { st.push_back(c); continue; }
+            if (auto c = dynamic_cast<const BVH*>(p.get())) {
+                st.push_back({c, ray_new(m4_point(c->transform.minv, ray.o), m4_vector(c->transform.minv, ray.d))});
+                continue;
+            }
             uint32_t id = 0xFFFFFFFFu;
             if (auto s = dynamic_cast<const Sphere*>(p.get())) id = s->id;
             else if (auto c2 = dynamic_cast<const Cuboid*>(p.get())) id = c2->id;

@@ -24,6 +24,9 @@ CASES = {
     "mesh": lambda: scenes.mesh1m(n=90)[0],
     "spheres": lambda: scenes.spheres1m(count=30000)[0],
     "mixed": lambda: scenes.mixed4k(mesh_n=70, nspheres=6000)[0],
+    "cornell_groups": lambda: scenes.cornell_groups()[0],                 # transformed groups: transform_bounds feeds the parent's tree
+    "nested_groups": lambda: scenes.nested_groups()[0],
+    "nested_groups_root": lambda: scenes.nested_groups(transformed_root=True)[0],
 }
 
 
@@ -68,13 +71,13 @@ def test_flat_scene_structure(native):
 
 
 def test_reference_hazards_are_errors(native):
-    """Q9: empty aggregate; materials outside the path; group transforms -> loud errors."""
+    """Q9: empty aggregate; materials outside the path -> loud errors."""
     sc = Scene()
     with pytest.raises(native.LasgunError):
         native.FlatScene(sc)
     sc = Scene(); sc.root.add_sphere([0, 0, 0], 1.0, Material.glass([1, 1, 1], [1, 1, 1], 1.5))
     with pytest.raises(native.LasgunError):
         native.FlatScene(sc)
-    sc = Scene(); g = Aggregate(); g.translate([1, 0, 0]); g.add_sphere([0, 0, 0], 1.0, Material.plastic([1, 1, 1], [0, 0, 0], 0.2)); sc.root.add_group(g)
+    sc = Scene(); g = Aggregate(); g.translate([1, 0, 0]); sc.root.add_group(g)      # empty nested aggregate
     with pytest.raises(native.LasgunError):
         native.FlatScene(sc)
