@@ -258,7 +258,8 @@ def run_gpu(args):
     phases = [float(v) for v in kms[1:].tolist()]      # average launch duration per phase, CUDA events on the launch stream
 
     # e2e through the C ABI with host buffers (rank-local frame share; film gathered on the host side of rank 0)
-    host_film = np.zeros((h, w, 4), np.uint8)
+    host_film_t = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()       # the caller's film: pinned host memory
+    host_film = host_film_t.numpy()
     e2e_ms, e2e_parts = [], []
     L = N.lib()
     for i in range(args.e2e_steps + 1):
@@ -266,21 +267,28 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        flat_i = N.FlatScene(hscene_host)              # Accel::from: the reference's BVH build + flatten (bvh.rs:135-453)
-        t1 = time.perf_counter()
-        hscene = C.c_void_p()
-        ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat_i.desc), C.byref(hscene)))
-        t2 = time.perf_counter()
         if world == 1:
+            flat_i = N.FlatScene(hscene_host)          # Accel::from: the reference's BVH build + flatten (bvh.rs:135-453)
+            t1 = time.perf_counter()
+            hscene = C.c_void_p()
+            ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat_i.desc), C.byref(hscene)))
+            t2 = time.perf_counter()
             ctx.check(L.lgb_capture(ctx.h, hscene, w, h, host_film.ctypes.data_as(C.POINTER(C.c_uint8)), None))
+            L.lgb_scene_destroy(hscene)
         else:
+            # the BVHs are built once, on rank 0, and the device arena is broadcast over NVLink (multi.replicate_scene)
+            tf = [t0]
+            def build_flat():
+                f = N.FlatScene(hscene_host); tf[0] = time.perf_counter(); return f
+            dev_i = multi.replicate_scene(ctx, build_flat, rank, world, N)
+            t1 = tf[0]; t2 = time.perf_counter()
             film.zero_()
-            ctx.check(L.lgb_capture_device(ctx.h, hscene, w, h, rank, world, C.c_void_p(film.data_ptr()), C.c_void_p(stream), None))
+            dev_i.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream)
             dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
-                host_film[...] = film.cpu().numpy()
+                host_film_t.copy_(film, non_blocking=True)
             torch.cuda.synchronize()
-        L.lgb_scene_destroy(hscene)
+            dev_i.destroy()
         t3 = time.perf_counter()
         e2e_parts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
         dt = torch.tensor([(t3 - t0) * 1e3], device="cuda")

@@ -172,6 +172,13 @@ const char* lgb_status_string(int status);
 int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* desc, lgb_scene** out);
 void lgb_scene_destroy(lgb_scene* scene);
 uint64_t lgb_scene_device_bytes(const lgb_scene* scene);
+/* Replication across GPUs (one process per GPU): the device scene is ONE relocatable arena plus a small layout
+ * record.  The rank that built it exports both; the others receive the arena bytes over NVLink (NCCL broadcast, or
+ * a peer copy) into memory they own and import it -- the BVH is built once, not once per GPU.
+ * The imported scene borrows `arena_dev`: keep it alive until lgb_scene_destroy. */
+uint64_t lgb_scene_layout_bytes(void);
+int lgb_scene_export(const lgb_scene* scene, void* layout_out, uint64_t layout_bytes, void** arena_dev, uint64_t* arena_bytes);
+int lgb_scene_import(lgb_ctx* ctx, const void* layout, uint64_t layout_bytes, void* arena_dev, lgb_scene** out);
 double lgb_scene_build_ms(const lgb_scene* scene);       /* host time spent building the device BVH */
 uint32_t lgb_scene_node_count(const lgb_scene* scene);   /* nodes of the device BVH */
 

@@ -21,7 +21,7 @@ LGB_LEAF_FLAG = 0x80000000
 # Every symbol include/lasgun_b200.h declares (checked by tests/test_abi.py without a GPU).
 ABI_SYMBOLS = [
     "lgb_build_probe", "lgb_device_count", "lgb_init", "lgb_set_option", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
-    "lgb_scene_destroy", "lgb_scene_device_bytes", "lgb_scene_build_ms", "lgb_scene_node_count", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
+    "lgb_scene_destroy", "lgb_scene_layout_bytes", "lgb_scene_export", "lgb_scene_import", "lgb_scene_device_bytes", "lgb_scene_build_ms", "lgb_scene_node_count", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
     "lgb_capture_device", "lgb_trace_rays", "lgb_measure_l2_read_gbs", "lgb_measure_fp32_gops", "lgb_measure_fp64_gops",
 ]
 
@@ -100,6 +100,9 @@ def lib():
         "lgb_build_probe": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(BuildInfo)]),
         "lgb_last_error": (C.c_char_p, [vp]), "lgb_status_string": (C.c_char_p, [C.c_int]),
         "lgb_scene_create": (C.c_int, [vp, C.POINTER(SceneDesc), C.POINTER(vp)]), "lgb_scene_destroy": (None, [vp]),
+        "lgb_scene_layout_bytes": (C.c_uint64, []),
+        "lgb_scene_export": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+        "lgb_scene_import": (C.c_int, [vp, vp, C.c_uint64, vp, C.POINTER(C.c_void_p)]),
         "lgb_scene_device_bytes": (C.c_uint64, [vp]), "lgb_scene_build_ms": (C.c_double, [vp]),
         "lgb_scene_node_count": (C.c_uint32, [vp]),
         "lgb_capture": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u8p, C.POINTER(Stats)]),
@@ -331,13 +334,35 @@ def default_context():
 class DeviceScene:
     """lgb_scene: the flattened scene resident in HBM."""
 
-    def __init__(self, ctx: Context, flat: FlatScene):
+    def __init__(self, ctx: Context, flat: FlatScene | None, _handle=None, _spp=None, _keep=None):
         L = lib()
         self.ctx, self.flat = ctx, flat
+        self._keep = _keep                       # imported scenes: the object that owns the arena memory
+        if _handle is not None:
+            self.h, self.spp = _handle, _spp
+            return
         h = C.c_void_p()
         ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat.desc), C.byref(h)))
         self.h = h
         self.spp = flat.spp
+
+    def export(self):
+        """(layout bytes, arena device pointer, arena bytes): what another rank needs to import this scene."""
+        L = lib()
+        n = L.lgb_scene_layout_bytes()
+        buf = (C.c_uint8 * n)()
+        ptr, nbytes = C.c_void_p(), C.c_uint64()
+        self.ctx.check(L.lgb_scene_export(self.h, buf, n, C.byref(ptr), C.byref(nbytes)))
+        return bytes(buf), ptr.value, nbytes.value
+
+    @staticmethod
+    def adopt(ctx: Context, layout: bytes, arena_ptr: int, spp: int, keep=None):
+        """Scene over an arena this rank received from the rank that built it (lgb_scene_import)."""
+        L = lib()
+        h = C.c_void_p()
+        buf = (C.c_uint8 * len(layout)).from_buffer_copy(layout)
+        ctx.check(L.lgb_scene_import(ctx.h, buf, len(layout), C.c_void_p(arena_ptr), C.byref(h)))
+        return DeviceScene(ctx, None, _handle=h, _spp=spp, _keep=keep)
 
     @property
     def device_bytes(self):
@@ -389,6 +414,7 @@ class DeviceScene:
         if self.h:
             lib().lgb_scene_destroy(self.h)
             self.h = None
+            self._keep = None
 
     def __del__(self):
         try:

@@ -67,6 +67,7 @@ struct lgb_ctx {
 struct lgb_scene {
     lgb_ctx* ctx = nullptr;
     void* arena = nullptr;     // one stream-ordered device allocation holding every array of the scene
+    bool owns_arena = true;    // false: imported (lgb_scene_import), the caller owns the memory
     uint64_t bytes = 0;
     DevScene dev{};
     DevCamera cam{};
@@ -180,6 +181,19 @@ static void make_prim_boxes(const lgb_scene_desc* d, raw_vector<PrimBox>& prims)
     });
 }
 
+// ---- export / import: the arena is position independent once DevScene's pointers are written as offsets
+namespace {
+struct SceneLayout { uint64_t magic, arena_bytes; DevScene dev; DevCamera cam; DevShade shade; double max_abs; };
+constexpr uint64_t kLayoutMagic = 0x4C47423253434E32ull;       // "LGB2SCN2"
+constexpr uint64_t kNullOffset = ~0ull;
+template <class F> void for_each_pointer(DevScene& d, F f) {
+    f((const void*&)d.nodes); f((const void*&)d.sph32); f((const void*&)d.sph64); f((const void*&)d.sph_mat); f((const void*&)d.sph_id);
+    f((const void*&)d.cub32); f((const void*&)d.cub64); f((const void*&)d.cub_mat); f((const void*&)d.cub_id);
+    f((const void*&)d.tri); f((const void*&)d.tri_nrm); f((const void*&)d.rank); f((const void*&)d.materials); f((const void*&)d.lights);
+    f((const void*&)d.spaces); f((const void*&)d.inst_space); f((const void*&)d.sph_space); f((const void*&)d.cub_space); f((const void*&)d.tri_space);
+}
+}  // namespace
+
 extern "C" {
 
 int lgb_build_probe(const lgb_scene_desc* d, lgb_build_info* out) {
@@ -243,10 +257,40 @@ int lgb_build_probe(const lgb_scene_desc* d, lgb_build_info* out) {
 void lgb_scene_destroy(lgb_scene* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    if (s->arena) cudaFreeAsync(s->arena, s->ctx->stream);      // stream-ordered: later work of this context is behind it
+    if (s->arena && s->owns_arena) cudaFreeAsync(s->arena, s->ctx->stream);      // stream-ordered: later work of this context is behind it
+    else if (s->arena) cudaStreamSynchronize(s->ctx->stream);                    // borrowed arena: the caller may free it right after
     delete s;
 }
 uint64_t lgb_scene_device_bytes(const lgb_scene* s) { return s ? s->bytes : 0; }
+
+uint64_t lgb_scene_layout_bytes(void) { return sizeof(SceneLayout); }
+int lgb_scene_export(const lgb_scene* s, void* layout_out, uint64_t layout_bytes, void** arena_dev, uint64_t* arena_bytes) {
+    if (!s || !layout_out || layout_bytes < sizeof(SceneLayout) || !arena_dev || !arena_bytes) return LGB_ERR_INVALID;
+    SceneLayout L{};
+    L.magic = kLayoutMagic; L.arena_bytes = s->bytes; L.dev = s->dev; L.cam = s->cam; L.shade = s->shade; L.max_abs = s->max_abs;
+    const char* base = (const char*)s->arena;
+    for_each_pointer(L.dev, [&](const void*& p) { p = (const void*)(p ? (uint64_t)((const char*)p - base) : kNullOffset); });
+    std::memcpy(layout_out, &L, sizeof L);
+    *arena_dev = s->arena; *arena_bytes = s->bytes;
+    return LGB_OK;
+}
+int lgb_scene_import(lgb_ctx* ctx, const void* layout, uint64_t layout_bytes, void* arena_dev, lgb_scene** out) {
+    if (!ctx || !layout || layout_bytes < sizeof(SceneLayout) || !arena_dev || !out) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_import: bad argument");
+    SceneLayout L; std::memcpy(&L, layout, sizeof L);
+    if (L.magic != kLayoutMagic) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_import: not a scene layout of this library version");
+    lgb_scene* s = new lgb_scene();
+    s->ctx = ctx; s->arena = arena_dev; s->owns_arena = false; s->bytes = L.arena_bytes;
+    s->dev = L.dev; s->cam = L.cam; s->shade = L.shade; s->max_abs = L.max_abs;
+    const char* base = (const char*)arena_dev;
+    bool ok = true;
+    for_each_pointer(s->dev, [&](const void*& p) {
+        const uint64_t off = (uint64_t)p;
+        if (off == kNullOffset) p = nullptr; else if (off >= L.arena_bytes) ok = false; else p = base + off;
+    });
+    if (!ok) { delete s; return fail(ctx, LGB_ERR_INVALID, "lgb_scene_import: offset outside the arena"); }
+    *out = s;
+    return LGB_OK;
+}
 double lgb_scene_build_ms(const lgb_scene* s) { return s ? s->build_ms : 0.0; }
 uint32_t lgb_scene_node_count(const lgb_scene* s) { return s ? s->dev.n_nodes : 0; }
 

@@ -22,6 +22,40 @@ def gather_film(film, dst: int = 0, group=None):
     return film
 
 
+class _DevicePointer:
+    """Zero-copy torch view of library-owned device memory (`__cuda_array_interface__`)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def replicate_scene(ctx, flat_builder, rank: int, ranks: int, native):
+    """Scene + BVH on every GPU, built ONCE: rank 0 runs `flat_builder()` (the reference BVH build + flatten) and
+    lgb_scene_create, then broadcasts the relocatable device arena over NCCL / NVLink; the other ranks import it.
+    Returns the rank's DeviceScene."""
+    import torch
+    import torch.distributed as dist
+    if ranks == 1:
+        return native.DeviceScene(ctx, flat_builder())
+    nl = int(native.lib().lgb_scene_layout_bytes())
+    if rank == 0:
+        dev = native.DeviceScene(ctx, flat_builder())
+        layout, ptr, nbytes = dev.export()
+        head = torch.frombuffer(bytearray(layout) + int(dev.spp).to_bytes(8, "little"), dtype=torch.uint8).cuda()
+        dist.broadcast(head, src=0)
+        dist.broadcast(torch.as_tensor(_DevicePointer(ptr, nbytes), device="cuda"), src=0)
+        return dev
+    head = torch.empty(nl + 8, dtype=torch.uint8, device="cuda")
+    dist.broadcast(head, src=0)
+    raw = bytes(head.cpu().numpy())
+    layout, spp = raw[:nl], int.from_bytes(raw[nl:], "little")
+    nbytes = int.from_bytes(layout[8:16], "little")          # SceneLayout.arena_bytes
+    arena = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dist.broadcast(arena, src=0)
+    torch.cuda.current_stream().synchronize()
+    return native.DeviceScene.adopt(ctx, layout, arena.data_ptr(), spp, keep=arena)
+
+
 def capture_distributed(dev_scene, w: int, h: int, film, rank: int, ranks: int, stream: int = 0):
     """One frame across `ranks` GPUs: render this rank's tiles into `film` (CUDA uint8 tensor), gather to rank 0."""
     if ranks > 1:
