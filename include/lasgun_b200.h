@@ -190,6 +190,10 @@ typedef struct lgb_build_info {
     double build_ms, rank_ms, sah_cost;
 } lgb_build_info;
 int lgb_build_probe(const lgb_scene_desc* desc, lgb_build_info* out);
+/* Reads the resident device BVH of a single-space scene back and checks it: every primitive in exactly one leaf
+ * (canonical ids 0 .. prims-1 seen once), every primitive inside its leaf box, leaves <= 4 primitives.  Fills
+ * nodes / max_depth / leaves / max_leaf / prims / boxes_ok / sah_cost; ranks_ok = 1 if the tree was built on the device. */
+int lgb_scene_verify(lgb_ctx* ctx, const lgb_scene* scene, lgb_build_info* out);
 
 /* capture (src/lib.rs:55): blocking; fills caller-owned row-major RGBA8, w*h*4 bytes (host). */
 int lgb_capture(lgb_ctx* ctx, lgb_scene* scene, uint32_t w, uint32_t h, uint8_t* rgba_out, lgb_stats* stats);

@@ -21,7 +21,7 @@ LGB_LEAF_FLAG = 0x80000000
 # Every symbol include/lasgun_b200.h declares (checked by tests/test_abi.py without a GPU).
 ABI_SYMBOLS = [
     "lgb_build_probe", "lgb_device_count", "lgb_init", "lgb_set_option", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
-    "lgb_scene_destroy", "lgb_scene_layout_bytes", "lgb_scene_export", "lgb_scene_import", "lgb_scene_device_bytes", "lgb_scene_build_ms", "lgb_scene_node_count", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
+    "lgb_scene_destroy", "lgb_scene_layout_bytes", "lgb_scene_export", "lgb_scene_import", "lgb_scene_verify", "lgb_scene_device_bytes", "lgb_scene_build_ms", "lgb_scene_node_count", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
     "lgb_capture_device", "lgb_trace_rays", "lgb_measure_l2_read_gbs", "lgb_measure_fp32_gops", "lgb_measure_fp64_gops",
 ]
 
@@ -103,6 +103,7 @@ def lib():
         "lgb_scene_layout_bytes": (C.c_uint64, []),
         "lgb_scene_export": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
         "lgb_scene_import": (C.c_int, [vp, vp, C.c_uint64, vp, C.POINTER(C.c_void_p)]),
+        "lgb_scene_verify": (C.c_int, [vp, vp, C.POINTER(BuildInfo)]),
         "lgb_scene_device_bytes": (C.c_uint64, [vp]), "lgb_scene_build_ms": (C.c_double, [vp]),
         "lgb_scene_node_count": (C.c_uint32, [vp]),
         "lgb_capture": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u8p, C.POINTER(Stats)]),
@@ -345,6 +346,12 @@ class DeviceScene:
         ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat.desc), C.byref(h)))
         self.h = h
         self.spp = flat.spp
+
+    def verify(self):
+        """Structural check of the resident device BVH (lgb_scene_verify)."""
+        info = BuildInfo()
+        self.ctx.check(lib().lgb_scene_verify(self.ctx.h, self.h, C.byref(info)))
+        return info.as_dict()
 
     def export(self):
         """(layout bytes, arena device pointer, arena bytes): what another rank needs to import this scene."""

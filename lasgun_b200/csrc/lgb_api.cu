@@ -12,6 +12,7 @@
 #include <thread>
 
 #include "lgb_build.hpp"
+#include "lgb_gpubuild.cuh"
 #include "lgb_parallel.hpp"
 #include "lgb_types.cuh"
 
@@ -68,6 +69,7 @@ struct lgb_scene {
     lgb_ctx* ctx = nullptr;
     void* arena = nullptr;     // one stream-ordered device allocation holding every array of the scene
     bool owns_arena = true;    // false: imported (lgb_scene_import), the caller owns the memory
+    bool gpu_built = false;    // the device BVH was built on the device (lgb_gpubuild.cu)
     uint64_t bytes = 0;
     DevScene dev{};
     DevCamera cam{};
@@ -254,6 +256,76 @@ int lgb_build_probe(const lgb_scene_desc* d, lgb_build_info* out) {
     return LGB_OK;
 }
 
+int lgb_scene_verify(lgb_ctx* ctx, const lgb_scene* s, lgb_build_info* out) {
+    if (!ctx || !s || !out || s->ctx != ctx) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_verify: bad argument");
+    if (s->dev.instanced) return fail(ctx, LGB_ERR_UNSUPPORTED, "lgb_scene_verify: single-space scenes only");
+    std::memset(out, 0, sizeof *out);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const DevScene& S = s->dev;
+    const uint32_t P = S.prim_count;
+    std::vector<HostNode> nodes(S.n_nodes);
+    CU(ctx, cudaMemcpy(nodes.data(), S.nodes, (size_t)S.n_nodes * 64, cudaMemcpyDeviceToHost));
+    // per type: how many primitives, their boxes (from the exact records) and canonical ids, in leaf order
+    uint32_t cnt[3] = {0, 0, 0};
+    for (const HostNode& n : nodes) for (int c = 0; c < 2; c++) {
+        const uint32_t w = c ? n.c1 : n.c0;
+        if (w & kLeafBit) { const uint32_t t = (w >> 29) & 3u; if (t < 3) cnt[t] = std::max(cnt[t], (w & kLeafFirstMask) + ((w >> 24) & 31u) + 1u); }
+    }
+    std::vector<double> s64((size_t)4 * cnt[0]), c64((size_t)6 * cnt[1]);
+    std::vector<float4> tri((size_t)3 * cnt[2]);
+    std::vector<uint32_t> sid(cnt[0]), cid(cnt[1]);
+    if (cnt[0]) { CU(ctx, cudaMemcpy(s64.data(), S.sph64, s64.size() * 8, cudaMemcpyDeviceToHost)); CU(ctx, cudaMemcpy(sid.data(), S.sph_id, sid.size() * 4, cudaMemcpyDeviceToHost)); }
+    if (cnt[1]) { CU(ctx, cudaMemcpy(c64.data(), S.cub64, c64.size() * 8, cudaMemcpyDeviceToHost)); CU(ctx, cudaMemcpy(cid.data(), S.cub_id, cid.size() * 4, cudaMemcpyDeviceToHost)); }
+    if (cnt[2]) CU(ctx, cudaMemcpy(tri.data(), S.tri, tri.size() * 16, cudaMemcpyDeviceToHost));
+    bool ok = cnt[0] + cnt[1] + cnt[2] == P;
+    std::vector<uint8_t> seen_id(P, 0), seen_slot[3];
+    for (int t = 0; t < 3; t++) seen_slot[t].assign(cnt[t], 0);
+    auto prim_box = [&](uint32_t t, uint32_t i, double* lo, double* hi, uint32_t& id) {
+        if (t == 0) { for (int k = 0; k < 3; k++) { const double a = s64[4 * (size_t)i + k] - s64[4 * (size_t)i + 3], b = s64[4 * (size_t)i + k] + s64[4 * (size_t)i + 3]; lo[k] = std::min(a, b); hi[k] = std::max(a, b); } id = sid[i]; }
+        else if (t == 1) { for (int k = 0; k < 3; k++) { lo[k] = std::min(c64[6 * (size_t)i + k], c64[6 * (size_t)i + 3 + k]); hi[k] = std::max(c64[6 * (size_t)i + k], c64[6 * (size_t)i + 3 + k]); } id = cid[i]; }
+        else {
+            const float4 a = tri[3 * (size_t)i], b = tri[3 * (size_t)i + 1], c = tri[3 * (size_t)i + 2];
+            const float x[3][3] = {{a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}};
+            for (int k = 0; k < 3; k++) { lo[k] = std::min(x[0][k], std::min(x[1][k], x[2][k])); hi[k] = std::max(x[0][k], std::max(x[1][k], x[2][k])); }
+            std::memcpy(&id, &a.w, 4);
+        }
+    };
+    struct E { uint32_t node, depth; float lo[3], hi[3]; };
+    std::vector<E> st; E root{}; root.node = 0; root.depth = 0; for (int k = 0; k < 3; k++) { root.lo[k] = -INFINITY; root.hi[k] = INFINITY; } st.push_back(root);
+    auto area = [](const float* lo, const float* hi) { float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2]; return (double)(x * y + x * z + y * z); };
+    double cost = 0.0, root_area = 0.0; uint64_t visited = 0;
+    while (!st.empty() && ok) {
+        const E e = st.back(); st.pop_back();
+        if (e.node >= S.n_nodes || ++visited > S.n_nodes) { ok = false; break; }
+        const HostNode& n = nodes[e.node];
+        for (int c = 0; c < 2; c++) {
+            const float* lo = n.v + 6 * c; const float* hi = n.v + 6 * c + 3; const uint32_t w = c ? n.c1 : n.c0;
+            for (int k = 0; k < 3; k++) if (!(lo[k] >= e.lo[k] && hi[k] <= e.hi[k])) ok = false;
+            if (e.node == 0) root_area += area(lo, hi);
+            if (w & kLeafBit) {
+                const uint32_t t = (w >> 29) & 3u, k = ((w >> 24) & 31u) + 1u, first = w & kLeafFirstMask;
+                out->leaves++; out->max_leaf = std::max(out->max_leaf, k); out->max_depth = std::max(out->max_depth, e.depth + 1);
+                cost += area(lo, hi) * k;
+                if (t > 2 || first + k > cnt[t]) { ok = false; continue; }
+                for (uint32_t i = 0; i < k; i++) {
+                    double plo[3], phi[3]; uint32_t id = 0;
+                    prim_box(t, first + i, plo, phi, id);
+                    if (seen_slot[t][first + i]++) ok = false;
+                    if (id >= P || seen_id[id]++) ok = false;
+                    for (int a = 0; a < 3; a++) if (!(plo[a] >= (double)lo[a] && phi[a] <= (double)hi[a])) ok = false;
+                }
+            } else {
+                cost += area(lo, hi);
+                E ch{}; ch.node = w; ch.depth = e.depth + 1; std::memcpy(ch.lo, lo, 12); std::memcpy(ch.hi, hi, 12); st.push_back(ch);
+            }
+        }
+    }
+    for (uint32_t i = 0; i < P && ok; i++) if (seen_id[i] != 1) ok = false;
+    out->nodes = S.n_nodes; out->prims = P; out->boxes_ok = ok ? 1 : 0; out->ranks_ok = s->gpu_built ? 1 : 0;
+    out->sah_cost = root_area > 0 ? cost / root_area : 0.0; out->build_ms = s->build_ms;
+    return LGB_OK;
+}
+
 void lgb_scene_destroy(lgb_scene* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
@@ -392,6 +464,122 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     if (prim_count == 0) return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: no primitives"));
     const int threads = Pool::get().threads();
     s->t_validate = ms_since(tc0);
+    bool has_spaces = !d->root.identity || d->root.swap_backface;
+    for (uint64_t i = 0; i < d->n_instances && !has_spaces; i++) has_spaces = !d->instances[i].identity || d->instances[i].swap_backface;
+    // Large single-space scenes: the device BVH is built ON the device (lgb_gpubuild.cu); the host builder stays for
+    // scenes with nested spaces and for small ones (LGB_HOST_BUILD=1 forces it: A/B runs and tests).
+    const bool gpu_build = !has_spaces && prim_count >= 32768u && prim_count <= kLeafFirstMask && !std::getenv("LGB_HOST_BUILD");
+    if (gpu_build) {
+        auto tg0 = std::chrono::steady_clock::now();
+        static_assert(sizeof(HostNode) == 64, "node layout");
+        const size_t ns = d->n_spheres, ncb = d->n_cuboids, nt = d->n_triangles, n = prim_count;
+        const bool any_normals = nt && d->tri_normals;
+        double M = 0.0;
+        auto upd = [&](double v) { const double a = std::fabs(v); if (a > M && std::isfinite(a)) M = a; };
+        for (int k = 0; k < 3; k++) { upd(wlo[k]); upd(whi[k]); upd(d->nodes[0].lo[k]); upd(d->nodes[0].hi[k]); }
+        const double padd = M * std::ldexp(1.0, -20);
+        s->max_abs = M; s->dev.err_abs = (float)padd;
+        // arena: what the render kernels read (nodes last: their number is known only after the build)
+        size_t off = 0;
+        auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t n_items = n + 1;
+        const size_t o_rank = place((size_t)8 * n_items * 4);
+        const size_t o_s32 = place(ns * 16), o_s64 = place(ns * 32), o_smat = place(ns * 4), o_sid = place(ns * 4);
+        const size_t o_c32 = place(ncb * 32), o_c64 = place(ncb * 48), o_cmat = place(ncb * 4), o_cid = place(ncb * 4);
+        const size_t o_tri = place(nt * 48), o_nrm = place(any_normals ? nt * 36 : 0);
+        const size_t o_mat = place(mats.size() * 8), o_lights = place(d->n_lights * 72);
+        const size_t o_nodes = place(n * 64);
+        const size_t arena_cap = off;
+        // scratch: the caller's arrays as they are, the items, the builder's work space
+        off = 0;
+        const size_t r_sph = place(ns * sizeof(lgb_sphere)), r_smat = place(ns * 4), r_sid = place(ns * 4);
+        const size_t r_cub = place(ncb * sizeof(lgb_cuboid)), r_cmat = place(ncb * 4), r_cid = place(ncb * 4);
+        const size_t r_tri = place(nt * sizeof(lgb_triangle)), r_tmat = place(nt * 4), r_tid = place(nt * 4);
+        const size_t r_nrm = place(any_normals ? nt * sizeof(lgb_tri_normals) : 0), r_has = place(any_normals && d->tri_has_normals ? nt : 0);
+        const size_t raw_bytes = off;
+        const size_t t_items = place(n * sizeof(GItem)), t_final = place(n * sizeof(GItem));
+        const size_t build_bytes = gpu_build_temp_bytes((uint32_t)n);
+        const size_t t_build = place(build_bytes);
+        const size_t scratch_bytes = off;
+        // pinned staging: [rank | materials | lights | raw arrays]
+        const size_t st_rank = 0, st_mat = ((size_t)8 * n_items * 4 + 255) & ~(size_t)255, st_lights = st_mat + ((mats.size() * 8 + 255) & ~(size_t)255);
+        const size_t st_raw = st_lights + ((d->n_lights * 72 + 255) & ~(size_t)255);
+        void* scratch = nullptr;
+        {
+            cudaError_t e = ctx->reserve_staging(st_raw + raw_bytes);
+            if (e != cudaSuccess) return bail(e == cudaErrorMemoryAllocation ? fail(ctx, LGB_ERR_NOMEM, "scene upload: pinned staging allocation failed") : cuda_fail(ctx, e, "cudaHostAlloc"));
+            e = cudaMallocAsync(&s->arena, arena_cap, ctx->stream);
+            if (e != cudaSuccess) { s->arena = nullptr; return bail(e == cudaErrorMemoryAllocation ? fail(ctx, LGB_ERR_NOMEM, "scene upload: device allocation failed") : cuda_fail(ctx, e, "cudaMallocAsync")); }
+            e = cudaMallocAsync(&scratch, scratch_bytes, ctx->stream);
+            if (e != cudaSuccess) return bail(e == cudaErrorMemoryAllocation ? fail(ctx, LGB_ERR_NOMEM, "scene build: device scratch allocation failed") : cuda_fail(ctx, e, "cudaMallocAsync"));
+        }
+        char* H = (char*)ctx->staging; char* D = (char*)s->arena; char* T = (char*)scratch;
+        auto gfail = [&](int code) { cudaFreeAsync(scratch, ctx->stream); return bail(code); };
+        Pool& pool = Pool::get();
+        auto stage = [&](size_t at, const void* src, size_t bytes) {
+            if (!bytes) return;
+            pool.for_range(bytes, 1 << 20, [&](size_t b, size_t e, size_t) { std::memcpy(H + st_raw + at + b, (const char*)src + b, e - b); });
+        };
+        stage(r_sph, d->spheres, ns * sizeof(lgb_sphere)); stage(r_smat, d->sphere_material, ns * 4); stage(r_sid, d->sphere_id, ns * 4);
+        stage(r_cub, d->cuboids, ncb * sizeof(lgb_cuboid)); stage(r_cmat, d->cuboid_material, ncb * 4); stage(r_cid, d->cuboid_id, ncb * 4);
+        stage(r_tri, d->triangles, nt * sizeof(lgb_triangle)); stage(r_tmat, d->triangle_material, nt * 4); stage(r_tid, d->triangle_id, nt * 4);
+        if (any_normals) { stage(r_nrm, d->tri_normals, nt * sizeof(lgb_tri_normals)); if (d->tri_has_normals) stage(r_has, d->tri_has_normals, nt); }
+        cudaError_t e = cudaMemcpyAsync(T, H + st_raw, raw_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaMemcpyAsync(H2D raw scene)"); return gfail(LGB_ERR_CUDA); }
+        RawScene raw{};
+        raw.spheres = (const lgb_sphere*)(T + r_sph); raw.sphere_material = (const uint32_t*)(T + r_smat); raw.sphere_id = (const uint32_t*)(T + r_sid); raw.n_spheres = (uint32_t)ns;
+        raw.cuboids = (const lgb_cuboid*)(T + r_cub); raw.cuboid_material = (const uint32_t*)(T + r_cmat); raw.cuboid_id = (const uint32_t*)(T + r_cid); raw.n_cuboids = (uint32_t)ncb;
+        raw.triangles = (const lgb_triangle*)(T + r_tri); raw.triangle_material = (const uint32_t*)(T + r_tmat); raw.triangle_id = (const uint32_t*)(T + r_tid); raw.n_triangles = (uint32_t)nt;
+        raw.tri_normals = any_normals ? (const lgb_tri_normals*)(T + r_nrm) : nullptr;
+        raw.tri_has_normals = any_normals && d->tri_has_normals ? (const uint8_t*)(T + r_has) : nullptr;
+        GItem* items = (GItem*)(T + t_items); GItem* final_items = (GItem*)(T + t_final);
+        if ((e = launch_make_items(raw, (float)padd, items, ctx->stream)) != cudaSuccess) { cuda_fail(ctx, e, "k_make_items"); return gfail(LGB_ERR_CUDA); }
+        s->t_validate = ms_since(tc0);
+        // while the copy and the item kernel run: rank tables from the caller's reference tree, materials, lights
+        auto tr0 = std::chrono::steady_clock::now();
+        {
+            BuiltScene one; one.spaces.emplace_back(); one.inst_space.assign(d->n_instances, kNoSpace);
+            if (!build_rank_tables(d, prim_count, one, (uint32_t*)(H + st_rank)))
+                return gfail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: primitive ids must be a permutation of 0..n-1 and every primitive must be referenced by exactly one leaf"));
+        }
+        std::memcpy(H + st_mat, mats.data(), mats.size() * 8);
+        {
+            double* l = (double*)(H + st_lights);
+            for (uint64_t i = 0; i < d->n_lights; i++)
+                for (int k = 0; k < 3; k++) { l[9 * i + k] = d->lights[i].position[k]; l[9 * i + 3 + k] = d->lights[i].intensity[k]; l[9 * i + 6 + k] = d->lights[i].falloff[k]; }
+        }
+        s->t_rank = ms_since(tr0);
+        if ((e = cudaMemcpyAsync(D + o_rank, H + st_rank, (size_t)8 * n_items * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(D + o_mat, H + st_mat, mats.size() * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+            (d->n_lights && (e = cudaMemcpyAsync(D + o_lights, H + st_lights, d->n_lights * 72, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)) {
+            cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)"); return gfail(LGB_ERR_CUDA);
+        }
+        auto tb0 = std::chrono::steady_clock::now();
+        GpuBuildInfo info{};
+        uint32_t* typepos[3] = {nullptr, nullptr, nullptr};
+        e = gpu_build_sah(items, (uint32_t)n, (HostNode*)(D + o_nodes), final_items, typepos, T + t_build, build_bytes, ctx->stream, &info);
+        if (e != cudaSuccess) { cuda_fail(ctx, e, "gpu_build_sah"); return gfail(LGB_ERR_CUDA); }
+        if (info.max_depth + 1 > (uint32_t)kStackDepth) return gfail(fail(ctx, LGB_ERR_UNSUPPORTED, "device BVH deeper than the 64-entry traversal stack"));
+        LeafArrays la{};
+        la.sph32 = (float4*)(D + o_s32); la.sph64 = (double*)(D + o_s64); la.sph_mat = (uint32_t*)(D + o_smat); la.sph_id = (uint32_t*)(D + o_sid);
+        la.cub32 = (float4*)(D + o_c32); la.cub64 = (double*)(D + o_c64); la.cub_mat = (uint32_t*)(D + o_cmat); la.cub_id = (uint32_t*)(D + o_cid);
+        la.tri = (float4*)(D + o_tri); la.tri_nrm = any_normals ? (float*)(D + o_nrm) : nullptr;
+        if ((e = launch_convert(raw, la, final_items, (uint32_t)n, typepos, padd, ctx->stream)) != cudaSuccess) { cuda_fail(ctx, e, "k_convert"); return gfail(LGB_ERR_CUDA); }
+        cudaFreeAsync(scratch, ctx->stream);
+        s->build_ms = ms_since(tb0);
+        s->t_build = s->build_ms;
+        s->bytes = o_nodes + (size_t)info.n_nodes * 64;
+        s->dev.nodes = (const float4*)(D + o_nodes); s->dev.n_nodes = info.n_nodes;
+        s->dev.rank = (const uint32_t*)(D + o_rank); s->dev.prim_count = prim_count; s->dev.rank_items = (uint32_t)n_items;
+        s->dev.n_spaces = 1; s->dev.instanced = 0;
+        if (ns) { s->dev.sph32 = la.sph32; s->dev.sph64 = la.sph64; s->dev.sph_mat = la.sph_mat; s->dev.sph_id = la.sph_id; }
+        if (ncb) { s->dev.cub32 = la.cub32; s->dev.cub64 = la.cub64; s->dev.cub_mat = la.cub_mat; s->dev.cub_id = la.cub_id; }
+        if (nt) { s->dev.tri = la.tri; s->dev.tri_nrm = la.tri_nrm; }
+        s->dev.materials = (const double*)(D + o_mat);
+        s->dev.lights = (const double*)(D + o_lights); s->dev.n_lights = (uint32_t)d->n_lights;
+        s->gpu_built = true;
+        (void)tg0;
+    } else {
     auto tc2 = std::chrono::steady_clock::now();
     BuiltScene bvh;
     {
@@ -531,6 +719,8 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         cudaError_t e = cudaMemcpyAsync(D, H, arena_bytes, cudaMemcpyHostToDevice, ctx->stream);
         if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)"); return bail(LGB_ERR_CUDA); }
     }
+    s->t_convert_upload = ms_since(tc3);
+    }
     for (int k = 0; k < 3; k++) {
         s->cam.origin[k] = d->camera.origin[k]; s->cam.view[k] = d->camera.view[k]; s->cam.up[k] = d->camera.up[k]; s->cam.aux[k] = d->camera.aux[k];
         s->shade.ambient[k] = d->ambient[k]; s->shade.bg_inner[k] = d->bg_inner[k]; s->shade.bg_outer[k] = d->bg_outer[k];
@@ -542,10 +732,9 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     s->shade.bg_scale = d->bg_scale;
     cudaError_t e = cudaStreamSynchronize(ctx->stream);     // the staging buffer is free for the next scene
     if (e != cudaSuccess) { cuda_fail(ctx, e, "scene upload"); return bail(LGB_ERR_CUDA); }
-    s->t_convert_upload = ms_since(tc3);
     s->t_total = ms_since(tc0);
-    if (getenv("LGB_TIMING")) fprintf(stderr, "[lgb_scene_create] validate %.1f rank %.1f build %.1f (sah %.1f) convert+upload %.1f total %.1f ms, %u threads\n",
-                                      s->t_validate, s->t_rank, s->t_build, s->build_ms, s->t_convert_upload, s->t_total, (unsigned)threads);
+    if (getenv("LGB_TIMING")) fprintf(stderr, "[lgb_scene_create] %s build: validate%s %.1f rank %.1f build %.1f (sah %.1f) convert+upload %.1f total %.1f ms, %u threads\n",
+                                      s->gpu_built ? "device" : "host", s->gpu_built ? "+stage" : "", s->t_validate, s->t_rank, s->t_build, s->build_ms, s->t_convert_upload, s->t_total, (unsigned)threads);
     *out = s;
     return LGB_OK;
 }

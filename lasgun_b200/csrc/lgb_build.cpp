@@ -45,7 +45,10 @@ inline __m128 item_hi(const Item& it) { return _mm_and_ps(_mm_load_ps(it.hi), la
 inline __m128 centroid(const Item& it) { const __m128 h = _mm_set1_ps(0.5f); return _mm_add_ps(_mm_mul_ps(h, item_lo(it)), _mm_mul_ps(h, item_hi(it))); }
 inline float centroid_axis(const Item& it, int a) { return 0.5f * it.lo[a] + 0.5f * it.hi[a]; }
 
-constexpr int NB = 16;
+#ifndef LGB_SAH_BINS
+#define LGB_SAH_BINS 16
+#endif
+constexpr int NB = LGB_SAH_BINS;
 // Per axis and bin: bounds of the primitives and their count.
 struct Bins {
     Box3 box[3][NB]; uint32_t cnt[3][NB];

@@ -26,7 +26,10 @@ struct HostNode { float v[12]; uint32_t c0, c1, pad0, pad1; };   // 64 B: child0
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kLeafFirstMask = 0x00FFFFFFu;
 #endif
-constexpr int kMaxLeaf = 4;
+#ifndef LGB_MAX_LEAF
+#define LGB_MAX_LEAF 4
+#endif
+constexpr int kMaxLeaf = LGB_MAX_LEAF;
 
 struct PrimBox { float lo[3], hi[3]; uint32_t type, index; };    // type 3 (LGB_PRIM_INSTANCE): index = child space
 
