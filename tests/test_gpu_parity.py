@@ -155,6 +155,29 @@ def test_full_size_sampled_against_oracle(native, oracle, gpu_ctx, name):
     assert f["alpha_equal"] and f["within_1_frac"] >= 0.999 and f["identical_frac"] >= 0.999, f
 
 
+@pytest.mark.parametrize("name", ["mesh", "spheres", "mixed"])
+def test_device_built_bvh(native, gpu_ctx, monkeypatch, name):
+    """Scenes of >= 32768 primitives get their BVH built ON the device (lgb_gpubuild.cu): every primitive in exactly one
+    leaf, boxes conservative and nested, and the film byte-identical to the one rendered from the host-built tree."""
+    sc, (w, h) = {"mesh": lambda: scenes.mesh1m(n=150, res=160), "spheres": lambda: scenes.spheres1m(count=60000, res=160),
+                  "mixed": lambda: scenes.mixed4k(mesh_n=120, nspheres=12000, res=(240, 136), supersampling=1)}[name]()
+    flat = native.FlatScene(sc)
+    dev = native.DeviceScene(gpu_ctx, flat)
+    v = dev.verify()
+    assert v["ranks_ok"] == 1, "expected the device-side builder for this many primitives"
+    assert v["boxes_ok"] == 1 and v["max_leaf"] <= 4 and v["max_depth"] < 64, v
+    film_dev, _ = dev.capture(w, h)
+    dev.destroy()
+    monkeypatch.setenv("LGB_HOST_BUILD", "1")
+    host = native.DeviceScene(gpu_ctx, flat)
+    vh = host.verify()
+    assert vh["ranks_ok"] == 0 and vh["boxes_ok"] == 1
+    assert vh["nodes"] == v["nodes"] and abs(vh["sah_cost"] - v["sah_cost"]) <= 1e-6 * vh["sah_cost"]     # the same tree
+    film_host, _ = host.capture(w, h)
+    host.destroy()
+    assert np.array_equal(film_dev, film_host)
+
+
 def test_capture_subset_union_equals_capture(native, gpu_ctx):
     """capture_subset(k, n) for k in 0..n tiles the film exactly (lib.rs:114-141) and leaves other pixels untouched."""
     sc, (w, h) = scenes.simple("b", 1, 160)
