@@ -19,6 +19,7 @@
 namespace lgb {
 constexpr int kRenderEvents = 7;
 cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev);
+bool render_fused(uint32_t spp);
 cudaError_t launch_trace(const DevScene&, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns, cudaStream_t);
 cudaError_t launch_l2_read(const void* buf, uint64_t bytes, int iters, float* sink, int sms, cudaStream_t);
 cudaError_t launch_fp32_peak(int iters, float* sink, int sms, cudaStream_t);
@@ -796,7 +797,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     if (s->cam.pixel_separation != 0.0 && W.aspect > 4.0)
         return fail(c, LGB_ERR_UNSUPPORTED, "orthographic capture with aspect > 4: the scene's coordinate bound assumed aspect <= 4");
     const DevScene& S = s->dev;
-    CU(c, c->radiance.reserve(std::max<uint64_t>(total, 1) * 3 * sizeof(double)));
+    if (!render_fused(W.spp)) CU(c, c->radiance.reserve(std::max<uint64_t>(total, 1) * 3 * sizeof(double)));      // spp > 256 only
     CU(c, c->counters.reserve(sizeof(DevCounters)));
     // wavefront buffers: hit_t 8 + ps 24 + hit_ref 4 + occl 4 + 3 queues x 4 x lights bytes per sample slot,
     // + occluder 4 x lights bytes per pixel slot
@@ -846,7 +847,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         if (total) for (int k = 0; k < 6; k++) { float pm = 0.f; CU(c, cudaEventElapsedTime(&pm, c->phase[k], c->phase[k + 1])); stats->kernel_ms[k] = pm; }
         for (int k = 0; k < 3; k++) { stats->filter_tests[k] = hc.filter[k]; stats->exact_tests[k] = hc.exact[k]; }
         stats->stack_overflow = hc.stack_overflow;
-        stats->kernel_launches = total ? 4 + s->dev.n_lights * (W.spp > 1 ? 3 : 1) : 0;
+        stats->kernel_launches = total ? (render_fused(W.spp) ? 3 : 4) + s->dev.n_lights * (W.spp > 1 ? 3 : 1) : 0;
         float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         stats->render_ms = ms; stats->total_ms = ms;
     }

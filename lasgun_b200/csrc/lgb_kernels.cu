@@ -674,6 +674,33 @@ __device__ __forceinline__ void block_append(AppendScratch& sc, bool mine, uint3
     __syncthreads();          // scratch is reused by the next call
 }
 
+// The same for up to 2 x LGB_MAX_LIGHTS queues at once (k_setup: one pass over the block instead of one per queue).
+// flags: bit q set <=> this thread appends `value` to queue q (queue words: V.queue / V.queue_count index q' = map[q]).
+struct MultiAppendScratch { uint32_t warp_off[2 * LGB_MAX_LIGHTS][kAppendThreads / 32]; uint32_t base[2 * LGB_MAX_LIGHTS]; };
+__device__ __forceinline__ void block_append_multi(MultiAppendScratch& sc, uint32_t nq, unsigned long long flags, uint32_t value,
+                                                   uint32_t* queues, uint64_t queue_stride, uint32_t* counts, const uint32_t* qmap) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (uint32_t q = 0; q < nq; q++) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, (flags >> q) & 1ull);
+        if (lane == 0) sc.warp_off[q][warp] = __popc(m);
+    }
+    __syncthreads();
+    for (uint32_t q = warp; q < nq; q += nw) {               // warp q (and q + nw, ...) scans the per-warp counts of queue q
+        const uint32_t c = lane < nw ? sc.warp_off[q][lane] : 0u;
+        uint32_t incl = c;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += v; }
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (lane == 0) sc.base[q] = tot ? atomicAdd(&counts[qmap[q]], tot) : 0u;
+        if (lane < nw) sc.warp_off[q][lane] = incl - c;
+    }
+    __syncthreads();
+    for (uint32_t q = 0; q < nq; q++) {
+        const bool mine = (flags >> q) & 1ull;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, mine);
+        if (mine) queues[(size_t)qmap[q] * queue_stride + sc.base[q] + sc.warp_off[q][warp] + __popc(m & ((1u << lane) - 1u))] = value;
+    }
+}
+
 template <bool STATS, bool INST>
 __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
     const uint64_t total = W.n_pixels * W.spp;
@@ -747,13 +774,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
         Ray64 ray; uint32_t x, y, s;
         if (ref != kSlotUnused && slot_ray(C, W, g, ray, x, y, s)) {
             const uint64_t gi = ((uint64_t)y * W.w + x) * W.spp + s;
-            if (ref == LGB_MISS) {                                   // background.rs:25-34
-                D3 dn = normalize(ray.d);
-                double dz = fabs(0.0 * dn.x + 0.0 * dn.y + 1.0 * dn.z);
-                double t = fmin(sqrt(1.0 - dz * dz) / sh.bg_scale, 1.0);
-                O.radiance[3 * g + 0] = lerp64(t, sh.bg_inner[0], sh.bg_outer[0]);
-                O.radiance[3 * g + 1] = lerp64(t, sh.bg_inner[1], sh.bg_outer[1]);
-                O.radiance[3 * g + 2] = lerp64(t, sh.bg_inner[2], sh.bg_outer[2]);
+            if (ref == LGB_MISS) {                                   // the background is evaluated by k_shade
                 if (O.aov_id) O.aov_id[gi] = LGB_MISS;
                 if (O.aov_t) O.aov_t[gi] = CUDART_INF;
                 if (O.aov_occl) O.aov_occl[gi] = 0;
@@ -777,15 +798,16 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
             }
         }
     }
-    // compacted per-light shadow queues (A: anchor sample of the pixel, B: the others), block-ordered
-    __shared__ AppendScratch sc;
+    // compacted per-light shadow queues (A: anchor sample of the pixel, B: the others), block-ordered, all at once:
+    // flag bit 2l = queue A of light l, bit 2l + 1 = queue B
+    __shared__ MultiAppendScratch sc;
+    __shared__ uint32_t qmap[2 * LGB_MAX_LIGHTS];
+    if (threadIdx.x < 2 * S.n_lights) qmap[threadIdx.x] = (threadIdx.x >> 1) * 3 + ((threadIdx.x & 1) ? kQueueB : kQueueA);
+    __syncthreads();
     const bool anchor = W.spp == 1 || (uint32_t)(g % W.spp) == W.anchor;
-    for (uint32_t l = 0; l < S.n_lights; l++) {
-        const bool want = live && ((need >> l) & 1u);
-        block_append(sc, want && anchor, (uint32_t)g, V.queue + (size_t)(l * 3 + kQueueA) * V.queue_stride, &V.queue_count[l * 3 + kQueueA]);
-        if (W.spp > 1)
-            block_append(sc, want && !anchor, (uint32_t)g, V.queue + (size_t)(l * 3 + kQueueB) * V.queue_stride, &V.queue_count[l * 3 + kQueueB]);
-    }
+    unsigned long long flags = 0;
+    if (live) for (uint32_t l = 0; l < S.n_lights; l++) if ((need >> l) & 1u) flags |= 1ull << (2 * l + (anchor ? 0 : 1));
+    block_append_multi(sc, 2 * S.n_lights, flags, (uint32_t)g, V.queue, V.queue_stride, V.queue_count, qmap);
 }
 
 // Exact test of ONE primitive against a shadow ray: true iff the reference's intersect accepts it with t < 1
@@ -907,37 +929,84 @@ __global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevW
 #ifndef LGB_SHADE_MIN_BLOCKS
 #define LGB_SHADE_MIN_BLOCKS 4
 #endif
-template <bool INST>
+__device__ __forceinline__ uchar4 quantise(D3 c) {                     // img.rs:56-67
+    uchar4 px;
+    px.x = (unsigned char)round(fmin(fmax(c.x, 0.0), 1.0) * 255.0);
+    px.y = (unsigned char)round(fmin(fmax(c.y, 0.0), 1.0) * 255.0);
+    px.z = (unsigned char)round(fmin(fmax(c.z, 0.0), 1.0) * 255.0);
+    px.w = 255;
+    return px;
+}
+// Radiance of every sample slot (integrate.rs:23-80) and, FUSED (spp <= 256: a block holds whole pixels), the film:
+// the samples of a pixel meet in shared memory and are summed in sample order (integrate.rs:16-20), so the
+// 24 B/sample radiance buffer and k_resolve drop out.  Thread t of a block: pixel t / spp of the block, sample t % spp.
+template <bool INST, bool FUSED>
 __global__ void __launch_bounds__(256, LGB_SHADE_MIN_BLOCKS) k_shade(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
     const double PI = 3.14159265358979323846264338327950288;
     const uint64_t total = W.n_pixels * W.spp;
-    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total) return;
-    const uint32_t ref = V.hit_ref[g];
-    if (ref == LGB_MISS || ref == kSlotUnused) return;
-    Ray64 ray; uint32_t x, y, s;
-    if (!slot_ray(C, W, g, ray, x, y, s)) return;
-    ShadePoint P; uint32_t id;
-    shade_point<true, INST>(S, ray, V.hit_t[g], ref, P, id);
-    const uint32_t occl = V.occl[g];
-    if (O.aov_occl) O.aov_occl[((uint64_t)y * W.w + x) * W.spp + s] = occl;
-    D3 output = d3(0, 0, 0);
-    for (uint32_t l = 0; l < S.n_lights; l++) {                        // integrate.rs:47-66
-        if ((occl >> l) & 1u) continue;
-        const double* L = S.lights + 9 * (size_t)l;
-        D3 wi = d3(L[0], L[1], L[2]) - P.ps;
-        double dist = sqrt(dot(wi, wi));
-        double f_att = L[6] + L[7] * dist + L[8] * dist * dist;
-        if (f_att == 0.0) continue;
-        wi = wi * (1.0 / dist);
-        double wi_dot_n = dot(wi, P.ns);
-        D3 f = bsdf_f(P.B, wi);                                        // zero when the shadow ray was skipped
-        output = output + mul_el(PI * d3(L[3], L[4], L[5]), f) * (wi_dot_n / f_att);
+    __shared__ double rad[FUSED ? 256 * 3 : 3];
+    __shared__ unsigned char valid[FUSED ? 256 : 1];
+    uint64_t g;
+    bool mine;
+    if (FUSED) {
+        const uint32_t ppb = 256u / W.spp;                              // pixels per block
+        const uint64_t p = (uint64_t)blockIdx.x * ppb + threadIdx.x / W.spp;
+        mine = threadIdx.x < ppb * W.spp && p < W.n_pixels;
+        g = p * W.spp + threadIdx.x % W.spp;
+    } else {
+        g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        mine = g < total;
     }
-    output = output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), bsdf_f(P.B, P.ns));   // integrate.rs:67
-    D3 zero = d3(0, 0, 0);
-    output = output + zero + zero;          // integrate.rs:79 (reflected + refracted are zero for plastic)
-    O.radiance[3 * g + 0] = output.x; O.radiance[3 * g + 1] = output.y; O.radiance[3 * g + 2] = output.z;
+    D3 output = d3(0, 0, 0);
+    bool have = false;
+    uint32_t x = 0, y = 0, s = 0;
+    if (mine) {
+        const uint32_t ref = V.hit_ref[g];
+        Ray64 ray;
+        if (ref != kSlotUnused && slot_ray(C, W, g, ray, x, y, s)) {
+            have = true;
+            if (ref == LGB_MISS) {                                       // background.rs:25-34
+                D3 dn = normalize(ray.d);
+                double dz = fabs(0.0 * dn.x + 0.0 * dn.y + 1.0 * dn.z);
+                double t = fmin(sqrt(1.0 - dz * dz) / sh.bg_scale, 1.0);
+                output = d3(lerp64(t, sh.bg_inner[0], sh.bg_outer[0]), lerp64(t, sh.bg_inner[1], sh.bg_outer[1]), lerp64(t, sh.bg_inner[2], sh.bg_outer[2]));
+            } else {
+                ShadePoint P; uint32_t id;
+                shade_point<true, INST>(S, ray, V.hit_t[g], ref, P, id);
+                const uint32_t occl = V.occl[g];
+                if (O.aov_occl) O.aov_occl[((uint64_t)y * W.w + x) * W.spp + s] = occl;
+                for (uint32_t l = 0; l < S.n_lights; l++) {              // integrate.rs:47-66
+                    if ((occl >> l) & 1u) continue;
+                    const double* L = S.lights + 9 * (size_t)l;
+                    D3 wi = d3(L[0], L[1], L[2]) - P.ps;
+                    double dist = sqrt(dot(wi, wi));
+                    double f_att = L[6] + L[7] * dist + L[8] * dist * dist;
+                    if (f_att == 0.0) continue;
+                    wi = wi * (1.0 / dist);
+                    double wi_dot_n = dot(wi, P.ns);
+                    D3 f = bsdf_f(P.B, wi);                              // zero when the shadow ray was skipped
+                    output = output + mul_el(PI * d3(L[3], L[4], L[5]), f) * (wi_dot_n / f_att);
+                }
+                output = output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), bsdf_f(P.B, P.ns));   // integrate.rs:67
+                D3 zero = d3(0, 0, 0);
+                output = output + zero + zero;          // integrate.rs:79 (reflected + refracted are zero for plastic)
+            }
+        }
+    }
+    if (!FUSED) {
+        if (have) { O.radiance[3 * g + 0] = output.x; O.radiance[3 * g + 1] = output.y; O.radiance[3 * g + 2] = output.z; }
+        return;
+    }
+    rad[3 * threadIdx.x] = output.x; rad[3 * threadIdx.x + 1] = output.y; rad[3 * threadIdx.x + 2] = output.z;
+    valid[threadIdx.x] = have ? 1 : 0;
+    __syncthreads();
+    if (mine && threadIdx.x % W.spp == 0 && valid[threadIdx.x]) {        // sample 0 of a pixel inside the film: resolve it
+        D3 c = d3(0, 0, 0);
+        for (uint32_t k = 0; k < W.spp; k++) c = c + d3(rad[3 * (threadIdx.x + k)], rad[3 * (threadIdx.x + k) + 1], rad[3 * (threadIdx.x + k) + 2]);
+        c = c * (1.0 / (double)W.spp);
+        const uint64_t p = g / W.spp;
+        reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)y * W.w + x] = quantise(c);
+    }
 }
 
 // integrate.rs:16-20 + img.rs:56-67: in-order sum of the samples, weight, quantise, store.
@@ -951,12 +1020,7 @@ __global__ void __launch_bounds__(256) k_resolve(DevWork W, DevOut O) {
     const double* r = O.radiance + 3 * p * W.spp;
     for (uint32_t s = 0; s < W.spp; s++) c = c + d3(r[3 * s], r[3 * s + 1], r[3 * s + 2]);
     c = c * weight;
-    uchar4 px;
-    px.x = (unsigned char)round(fmin(fmax(c.x, 0.0), 1.0) * 255.0);
-    px.y = (unsigned char)round(fmin(fmax(c.y, 0.0), 1.0) * 255.0);
-    px.z = (unsigned char)round(fmin(fmax(c.z, 0.0), 1.0) * 255.0);
-    px.w = 255;
-    reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)y * W.w + x] = px;
+    reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)y * W.w + x] = quantise(c);
 }
 
 // Caller-supplied rays (lgb_trace_rays): closest hit id, t, RayIntersection::ng()/ns() (surface.rs:107-118)
@@ -1018,6 +1082,8 @@ __global__ void k_fp64_peak(int iters, double* sink) {
 }
 
 // ------------------------------------------------------------------ launch wrappers (called from lgb_api.cu)
+bool render_fused(uint32_t spp) { return spp >= 1 && spp <= 256; }
+
 // `ev` (optional): kRenderEvents events recorded around the phases: start | primary | setup | anchor shadow rays |
 // pretest + remaining shadow rays | shade | resolve.
 cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O,
@@ -1053,10 +1119,17 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
         if (which == kQueueA) mark(3);
     }
     mark(4);
-    if (inst) k_shade<true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
-    mark(5);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
+    if (render_fused(W.spp)) {          // whole pixels per block: shade and resolve in one kernel, no radiance buffer
+        const unsigned fb = (unsigned)((W.n_pixels + (256u / W.spp) - 1) / (256u / W.spp));
+        if (inst) k_shade<true, true><<<fb, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, true><<<fb, 256, 0, stream>>>(S, C, sh, W, O, V);
+        mark(5);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    } else {
+        if (inst) k_shade<true, false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+        mark(5);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
+    }
     mark(6);
     return cudaGetLastError();
 }
