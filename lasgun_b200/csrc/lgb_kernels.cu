@@ -192,6 +192,9 @@ struct Trav {                 // resumable traversal state of one ray
 
 // Inner loop of the while-while traversal: descend interior nodes until `cur` is a leaf or kDone.
 // OCT < 8: every ray of the warp has that direction octant (slab_oct); OCT == 8: mixed warp (slab2).
+#ifndef LGB_TSTACK
+#define LGB_TSTACK 1
+#endif
 // TSTACK (closest-hit rays): the entry distance of a deferred child is kept beside it, and a popped entry
 // that now starts beyond the best hit is dropped without fetching its node.
 template <bool TSTACK>
@@ -246,15 +249,15 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& world, 
     uint32_t& cur = T.cur; int& sp = T.sp;
     for (;;) {
         switch (INST ? f.oct : octw) {   // octw is warp-uniform: the octant shared by every ray of the warp, or 8 (mixed)
-        case 0: node_loop<0, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 1: node_loop<1, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 2: node_loop<2, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 3: node_loop<3, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 4: node_loop<4, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 5: node_loop<5, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 6: node_loop<6, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 7: node_loop<7, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        default: node_loop<8, STATS, !ANYHIT>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 0: node_loop<0, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 1: node_loop<1, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 2: node_loop<2, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 3: node_loop<3, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 4: node_loop<4, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 5: node_loop<5, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 6: node_loop<6, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 7: node_loop<7, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        default: node_loop<8, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
         }
         if (cur == kDone) return true;
         {
@@ -265,8 +268,8 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& world, 
                     ray = ray_to_space(S, first, world);
                     f = make_rayf(ray, S.spaces[first].err_abs);
                 } else {
-                    if (count > 1u) { if (!ANYHIT) tstack[sp] = -CUDART_INF_F; stack[sp++] = kInstLeaf | ((count - 2u) << 24) | (first + 1u); }
-                    if (!ANYHIT) tstack[sp] = -CUDART_INF_F;
+                    if (count > 1u) { if (!ANYHIT && LGB_TSTACK) tstack[sp] = -CUDART_INF_F; stack[sp++] = kInstLeaf | ((count - 2u) << 24) | (first + 1u); }
+                    if (!ANYHIT && LGB_TSTACK) tstack[sp] = -CUDART_INF_F;
                     stack[sp++] = kExitMarker | T.space;
                     const uint32_t child = __ldg(&S.inst_space[first]);
                     const DevSpace& c = S.spaces[child];
@@ -338,7 +341,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& world, 
                 }
             }
         }
-        cur = stack_pop<!ANYHIT>(sp, stack, tstack, best_up);
+        cur = stack_pop<(!ANYHIT && LGB_TSTACK)>(sp, stack, tstack, best_up);
         if (REFILL && __popc(__activemask()) < refill_below) return cur == kDone;
     }
 }
@@ -362,7 +365,7 @@ __device__ Hit traverse(const DevScene& S, const Ray64& world, double tmax, Loca
     Ray64 ray; RayF f; Trav T;
     enter_root<INST>(S, world, ray, f, T, tmax);
     uint32_t stack[kStackDepth];      // depth is bounded at scene creation (lgb_api.cu), so pushes are unchecked
-    float tstack[ANYHIT ? 1 : kStackDepth];
+    float tstack[(ANYHIT || !LGB_TSTACK) ? 1 : kStackDepth];
     trav_run<ANYHIT, STATS, false, INST>(S, world, ray, f, T, stack, tstack, tmax, lc, 0, 8u);
     return T.best;
 }
@@ -606,6 +609,9 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #ifndef LGB_MIN_BLOCKS
 #define LGB_MIN_BLOCKS 4
 #endif
+#ifndef LGB_TRAV_THREADS
+#define LGB_TRAV_THREADS 256          // threads per block of the persistent traversal kernels
+#endif
 
 // ================================================================== wavefront pipeline
 // k_primary  persistent warps pull 32 consecutive sample slots: camera ray -> closest hit -> (t, ref)
@@ -702,13 +708,13 @@ __device__ __forceinline__ void block_append_multi(MultiAppendScratch& sc, uint3
 }
 
 template <bool STATS, bool INST>
-__global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_primary(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
+__global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_primary(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
     const uint64_t total = W.n_pixels * W.spp;
     const unsigned lane = threadIdx.x & 31u;
     LocalCounters lc = {};
     unsigned int hits = 0, primary = 0;
     uint32_t stack[kStackDepth];
-    float tstack[kStackDepth];
+    float tstack[LGB_TSTACK ? kStackDepth : 1];
     Ray64 world, ray; RayF f; Trav T;      // INST: `ray` is the ray in the current space; otherwise it stays equal to `world`
     uint64_t g = 0;
     bool active = false, drained = false;
@@ -871,7 +877,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork 
 }
 
 template <bool STATS, bool INST>
-__global__ void __launch_bounds__(256, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light, int which) {
+__global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_shadow(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light, int which) {
     const unsigned total = V.queue_count[light * 3 + which];
     const uint32_t* q = V.queue + (size_t)(light * 3 + which) * V.queue_stride;
     const bool record = which == kQueueA && W.spp > 1;      // anchor rays remember their occluder for k_pretest
@@ -1096,10 +1102,10 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     if ((e = cudaMemsetAsync(V.work_counter, 0, kWaveCtrBytes, stream)) != cudaSuccess) return e;
     const bool cache = W.spp > 1;
     if (cache && S.n_lights && (e = cudaMemsetAsync(V.occluder, 0xFF, (size_t)S.n_lights * W.n_pixels * 4, stream)) != cudaSuccess) return e;
-    const unsigned pblocks = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)sms * LGB_MIN_BLOCKS);
+    const unsigned pblocks = (unsigned)std::min<uint64_t>((total + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, (uint64_t)sms * LGB_MIN_BLOCKS);
     const bool inst = S.instanced != 0;      // transformed aggregates: the INST kernel variants (the plain ones carry no trace of them)
-    if (inst) { if (stats) k_primary<true, true><<<pblocks, 256, 0, stream>>>(S, C, W, O, V); else k_primary<false, true><<<pblocks, 256, 0, stream>>>(S, C, W, O, V); }
-    else { if (stats) k_primary<true, false><<<pblocks, 256, 0, stream>>>(S, C, W, O, V); else k_primary<false, false><<<pblocks, 256, 0, stream>>>(S, C, W, O, V); }
+    if (inst) { if (stats) k_primary<true, true><<<pblocks, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, true><<<pblocks, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); }
+    else { if (stats) k_primary<true, false><<<pblocks, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, false><<<pblocks, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); }
     mark(1);
     const unsigned blocks = (unsigned)((total + 255) / 256), ablocks = (unsigned)((total + kAppendThreads - 1) / kAppendThreads);
     if (inst) { if (all_shadows) k_setup<true, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); }
@@ -1107,14 +1113,14 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     mark(2);
     // anchor rays (queue A), then the cached-occluder test of the rest (B -> C), then the survivors (queue C)
     for (int which = kQueueA; which <= (cache ? kQueueC : kQueueA); which += 2) {
-        const unsigned sb = which == kQueueA ? (unsigned)std::min<uint64_t>((W.n_pixels + 255) / 256, pblocks) : pblocks;
+        const unsigned sb = which == kQueueA ? (unsigned)std::min<uint64_t>((W.n_pixels + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, pblocks) : pblocks;
         for (uint32_t l = 0; l < S.n_lights; l++) {
             if (which == kQueueC) {
                 const unsigned tb = (unsigned)std::min<uint64_t>(ablocks, (uint64_t)sms * 4);
                 if (inst) k_pretest<true><<<tb, kAppendThreads, 0, stream>>>(S, W, O, V, l); else k_pretest<false><<<tb, kAppendThreads, 0, stream>>>(S, W, O, V, l);
             }
-            if (inst) { if (stats) k_shadow<true, true><<<sb, 256, 0, stream>>>(S, W, O, V, l, which); else k_shadow<false, true><<<sb, 256, 0, stream>>>(S, W, O, V, l, which); }
-            else { if (stats) k_shadow<true, false><<<sb, 256, 0, stream>>>(S, W, O, V, l, which); else k_shadow<false, false><<<sb, 256, 0, stream>>>(S, W, O, V, l, which); }
+            if (inst) { if (stats) k_shadow<true, true><<<sb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, which); else k_shadow<false, true><<<sb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, which); }
+            else { if (stats) k_shadow<true, false><<<sb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, which); else k_shadow<false, false><<<sb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, which); }
         }
         if (which == kQueueA) mark(3);
     }

@@ -178,6 +178,27 @@ def test_device_built_bvh(native, gpu_ctx, monkeypatch, name):
     assert np.array_equal(film_dev, film_host)
 
 
+@pytest.mark.parametrize("name", ["plain", "instanced"])
+def test_scene_export_import(native, gpu_ctx, name):
+    """Multi-GPU replication path on one GPU: the exported arena, copied byte for byte into memory the 'other rank' owns,
+    imports into a scene that renders the same film (lgb_scene_export / lgb_scene_import)."""
+    import torch
+    from lasgun_b200 import multi
+    sc, (w, h) = scenes.mixed4k(mesh_n=64, nspheres=5000, res=(192, 108), supersampling=1) if name == "plain" else scenes.nested_groups((192, 144), 1)
+    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+    film, _ = dev.capture(w, h)
+    layout, ptr, nbytes = dev.export()
+    assert len(layout) == native.lib().lgb_scene_layout_bytes() and nbytes == dev.device_bytes
+    arena = torch.as_tensor(multi._DevicePointer(ptr, nbytes), device="cuda").clone()
+    dev.destroy()
+    twin = native.DeviceScene.adopt(gpu_ctx, layout, arena.data_ptr(), dev.spp, keep=arena)
+    film2, _ = twin.capture(w, h)
+    twin.destroy()
+    assert np.array_equal(film, film2)
+    with pytest.raises(native.LasgunError):
+        native.DeviceScene.adopt(gpu_ctx, b"\0" * len(layout), arena.data_ptr(), 1)
+
+
 def test_capture_subset_union_equals_capture(native, gpu_ctx):
     """capture_subset(k, n) for k in 0..n tiles the film exactly (lib.rs:114-141) and leaves other pixels untouched."""
     sc, (w, h) = scenes.simple("b", 1, 160)
