@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LGB_ABI_VERSION 2
+#define LGB_ABI_VERSION 3
 
 typedef enum lgb_status {
     LGB_OK = 0,
@@ -105,6 +105,21 @@ typedef struct lgb_camera {          /* Camera after look_at, src/camera.rs:6-38
     uint32_t reserved;
 } lgb_camera;
 
+/* Lazy reference tree.  The device traverses its own BVH; the caller's (reference) tree is consulted for ONE thing:
+ * the order in which the reference tests primitives, which decides exact-t ties (see below).  Most frames contain no
+ * such tie.  A caller may therefore leave `nodes` NULL and give a callback instead: it is invoked -- from the thread
+ * that calls lgb_capture*, at most once per scene -- only if a closest-hit ray meets two primitives at bit-identical t;
+ * the affected rays are then re-traced with the order known.  The reference BVH build (the larger part of the host
+ * time of `capture`) is skipped otherwise.  Lazy scenes must not contain transformed instances (their spaces are
+ * derived from the tree) and need `bounds_lo/hi`: a world box containing every primitive (the reference root box).
+ * The primitive arrays of the desc must stay valid until the scene is destroyed. */
+typedef struct lgb_reference_tree {
+    const lgb_node* nodes;           uint64_t n_nodes;
+    const uint32_t* prim_refs;       uint64_t n_prim_refs;
+    const lgb_instance* instances;   uint64_t n_instances;
+} lgb_reference_tree;
+typedef int (*lgb_reference_tree_fn)(void* user, lgb_reference_tree* out);   /* 0 = ok; arrays stay owned by the caller */
+
 typedef struct lgb_scene_desc {
     uint32_t abi_version;            /* LGB_ABI_VERSION */
     uint32_t flags;                  /* LGB_SCENE_* */
@@ -125,6 +140,9 @@ typedef struct lgb_scene_desc {
     lgb_camera camera;
     double ambient[3];                                       /* scene.rs:22 */
     double bg_inner[3], bg_outer[3], bg_scale;               /* material/background.rs:6-10 */
+    lgb_reference_tree_fn reference_tree;                    /* lazy mode (nodes == NULL), else NULL */
+    void* reference_tree_user;
+    double bounds_lo[3], bounds_hi[3];                       /* lazy mode: world box of all primitives */
 } lgb_scene_desc;
 
 #define LGB_MAX_LIGHTS 32

@@ -162,11 +162,19 @@ struct FlatScene {
     struct Level { std::vector<double> bounds; std::vector<uint32_t> meta; std::vector<uint64_t> order; uint32_t node_offset; };
     std::vector<Level> levels;
     double build_ms = 0.0;
+    double bounds_lo[3] = {0, 0, 0}, bounds_hi[3] = {0, 0, 0};   // the reference root box (root aggregate's coordinates)
+    // Lazy mode (BuildOptions::lazy_tree): nodes / prim_refs / instances[].root_node are filled by build_reference_tree(),
+    // which lgb_scene_desc::reference_tree calls if the device ever meets an exact-t tie.  The FlatScene must not move
+    // (its address is the callback's user pointer) while a device scene created from it is alive.
+    bool tree_built = false, keep_levels = false;
+    std::shared_ptr<void> pending;     // the assembled levels, until their trees are built
+    void build_reference_tree();
     void describe(lgb_scene_desc* out) const;
 };
 
 struct BuildOptions {
     bool keep_levels = false;          // keep per-level reference arrays (tests)
+    bool lazy_tree = false;            // defer the reference BVH build until the device needs it (exact-t ties only)
 };
 
 FlatScene flatten(const Scene& scene, const BuildOptions& opt);   // Accel::from + flatten (bvh.rs:135-453)

@@ -61,6 +61,7 @@ class SceneDesc(C.Structure):
         ("lights", C.c_void_p), ("n_lights", C.c_uint64),
         ("camera", CameraDesc),
         ("ambient", C.c_double * 3), ("bg_inner", C.c_double * 3), ("bg_outer", C.c_double * 3), ("bg_scale", C.c_double),
+        ("reference_tree", C.c_void_p), ("reference_tree_user", C.c_void_p), ("bounds_lo", C.c_double * 3), ("bounds_hi", C.c_double * 3),
     ]
 
 
@@ -129,7 +130,7 @@ def lib():
         "lgh_agg_add_group": (None, [vp, C.c_int, C.c_int]), "lgh_agg_swap_backface": (None, [vp, C.c_int]),
         "lgh_agg_translate": (None, [vp, C.c_int, dp]), "lgh_agg_scale": (None, [vp, C.c_int, C.c_double, C.c_double, C.c_double]),
         "lgh_agg_rotate_axis": (None, [vp, C.c_int, C.c_int, C.c_double]), "lgh_agg_rotate": (None, [vp, C.c_int, C.c_double, dp]),
-        "lgh_flatten": (vp, [vp, C.c_int]), "lgh_flat_free": (None, [vp]),
+        "lgh_flatten": (vp, [vp, C.c_int, C.c_int]), "lgh_flat_tree_built": (C.c_int, [vp]), "lgh_flat_build_tree": (C.c_int, [vp]), "lgh_flat_free": (None, [vp]),
         "lgh_flat_describe": (None, [vp, C.POINTER(SceneDesc)]), "lgh_flat_build_ms": (C.c_double, [vp]),
         "lgh_flat_prim_count": (C.c_uint32, [vp]), "lgh_flat_level_count": (C.c_uint64, [vp]),
         "lgh_flat_level_dims": (C.c_int, [vp, C.c_uint64, u64p, u64p, u32p]),
@@ -230,16 +231,29 @@ class HostScene:
 class FlatScene:
     """Host-side flattened scene (Accel::from without the upload): owns the arrays of an lgb_scene_desc."""
 
-    def __init__(self, scene, keep_levels=False):
+    def __init__(self, scene, keep_levels=False, lazy=False):
+        """lazy=True: the reference BVH is not built now; the device asks for it (reference_tree callback) only if a
+        closest-hit ray meets two primitives at bit-identical t.  Accessors that need the tree build it."""
         L = lib()
         self.host = scene if isinstance(scene, HostScene) else HostScene(scene)
-        self.h = L.lgh_flatten(self.host.h, 1 if keep_levels else 0)
+        self.h = L.lgh_flatten(self.host.h, 1 if keep_levels else 0, 1 if lazy else 0)
         if not self.h:
             msg = L.lgh_last_error().decode()
             raise LasgunError(LGB_ERR_UNSUPPORTED if "not on the device path" in msg or "outside the device" in msg else LGB_ERR_INVALID, msg)
         self.desc = SceneDesc()
         L.lgh_flat_describe(self.h, C.byref(self.desc))
         self.spp = self.desc.camera.supersampling_root ** 2
+
+    @property
+    def tree_built(self):
+        return bool(lib().lgh_flat_tree_built(self.h))
+
+    def build_tree(self):
+        """Builds the reference BVH now (no-op if it exists) and refreshes the desc."""
+        L = lib()
+        if L.lgh_flat_build_tree(self.h):
+            raise LasgunError(LGB_ERR_INVALID, L.lgh_last_error().decode())
+        L.lgh_flat_describe(self.h, C.byref(self.desc))
         self.n_lights = self.desc.n_lights
 
     @property
@@ -251,11 +265,13 @@ class FlatScene:
         return lib().lgh_flat_prim_count(self.h)
 
     def nodes(self):
+        self.build_tree()
         n = self.desc.n_nodes
         buf = (Node * n).from_address(self.desc.nodes)
         return np.frombuffer(buf, dtype=np.dtype([("lo", "<f4", 3), ("a", "<u4"), ("hi", "<f4", 3), ("b", "<u4")]), count=n)
 
     def prim_refs(self):
+        self.build_tree()
         n = self.desc.n_prim_refs
         return np.frombuffer((C.c_uint32 * n).from_address(self.desc.prim_refs), dtype=np.uint32, count=n)
 

@@ -364,7 +364,24 @@ struct Level {
     raw_vector<uint32_t> refs;                // prim ref per primitive (instances: index into `children`)
     std::vector<std::unique_ptr<Level>> children;
     std::vector<uint32_t> child_instance;     // instance slot per child
+    size_t per_node = 0;                      // max_prims_per_node argument of BVHAccel::new for this level (bvh.rs:141-162)
+    // The level's root box: the union of its primitive bounds (bvh.rs:212-213); min / max folds do not depend on the tree.
+    Box bounds() const {
+        lgb::Pool& pool = lgb::Pool::get();
+        const size_t n = boxes.size(), nc = std::max<size_t>(1, pool.chunks_of(n, 1 << 14));
+        std::vector<Box> part(nc, Box::none());
+        pool.for_range(n, 1 << 14, [&](size_t b, size_t e, size_t c) { for (size_t i = b; i < e; i++) part[c].grow(boxes[i]); });
+        Box all = Box::none();
+        for (const Box& b : part) all.grow(b);
+        return all;
+    }
+    void build_trees() {                      // nested levels first, as the reference's recursion does
+        for (auto& c : children) c->build_trees();
+        tree.build(boxes, per_node);
+    }
 };
+
+using HostLevel = Level;                   // FlatScene has a nested type of the same name
 
 inline float f32_down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
 inline float f32_up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }
@@ -437,10 +454,7 @@ struct Flattener {
             lv->refs[t] = LGB_PRIM_REF(LGB_PRIM_TRIANGLE, base + t);
           }
         });
-        const auto tb = std::chrono::steady_clock::now();
-        lv->tree.build(lv->boxes, ntri);
-        if (std::getenv("LGB_TIMING")) std::fprintf(stderr, "[flatten] mesh of %zu: tree.build %.1f ms\n", ntri,
-                                                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb).count());
+        lv->per_node = ntri;
         return lv;
     }
 
@@ -466,7 +480,7 @@ struct Flattener {
                 lgb_instance inst{};
                 inst.identity = 1;
                 for (int k = 0; k < 16; k++) inst.m[k] = inst.minv[k] = (k % 5 == 0) ? 1.0 : 0.0;
-                const Box& cb = child->tree.nodes[child->tree.root].box;
+                const Box cb = child->bounds();
                 if (n.kind == Aggregate::Node::Group) {
                     const Aggregate& g = ag.groups[n.ref];
                     inst.identity = g.transform.identity ? 1u : 0u;
@@ -533,13 +547,17 @@ struct Flattener {
             }
         });
         if (failed.load()) throw Error(fail_status, fail_msg);
-        const auto tb = std::chrono::steady_clock::now();
-        lv->tree.build(lv->boxes, lv->boxes.size());
-        if (std::getenv("LGB_TIMING")) std::fprintf(stderr, "[flatten] aggregate of %zu: tree.build %.1f ms\n", lv->boxes.size(),
-                                                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb).count());
+        if (lv->boxes.empty()) throw Error(LGB_ERR_INVALID, "empty aggregate: the reference's BVH build does not terminate (bvh.rs:240,355-356)");
+        lv->per_node = lv->boxes.size();
         return lv;
     }
 
+};
+
+// Emission of the built reference trees in pre-order (flatten_bvh_tree, bvh.rs:430-453).
+struct Emitter {
+    FlatScene& out;
+    bool keep_levels;
     // ---- emission: reference tree in pre-order (flatten_bvh_tree, bvh.rs:430-453)
     static lgb_node node_box(const Box& b) {
         lgb_node n;
@@ -589,7 +607,7 @@ struct Flattener {
     }
     void emit_level(const Level& lv) {
         const uint32_t offset = (uint32_t)out.nodes.size();
-        if (opt.keep_levels) dump_level(lv, offset);
+        if (keep_levels) dump_level(lv, offset);
         emit_node(lv, lv.tree.root);
         for (size_t c = 0; c < lv.children.size(); c++) {
             out.instances[lv.child_instance[c]].root_node = (uint32_t)out.nodes.size();
@@ -610,8 +628,16 @@ FlatScene flatten(const Scene& scene, const BuildOptions& opt) {
     out.root.swap_backface = scene.root.swap_backface_flag ? 1u : 0u;
     std::memcpy(out.root.m, scene.root.transform.m, sizeof out.root.m); std::memcpy(out.root.minv, scene.root.transform.minv, sizeof out.root.minv);
     const double t_levels = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    f.emit_level(*root);
-    if (std::getenv("LGB_TIMING")) std::fprintf(stderr, "[flatten] levels (reference HLBVH builds) %.1f ms, emit %.1f ms\n", t_levels,
+    {
+        const Box wb = root->bounds();                       // = the reference root box, in the root aggregate's coordinates
+        for (int k = 0; k < 3; k++) { out.bounds_lo[k] = wb.mn[k]; out.bounds_hi[k] = wb.mx[k]; }
+    }
+    out.keep_levels = opt.keep_levels;
+    out.pending = std::shared_ptr<void>(root.release(), [](void* p) { delete static_cast<Level*>(p); });
+    bool transformed = !out.root.identity || out.root.swap_backface;
+    for (const lgb_instance& in : out.instances) transformed |= !in.identity || in.swap_backface;
+    if (!opt.lazy_tree || transformed) out.build_reference_tree();      // nested spaces are derived from the tree: no lazy mode for them
+    if (std::getenv("LGB_TIMING")) std::fprintf(stderr, "[flatten] primitives and levels %.1f ms, reference trees %s %.1f ms\n", t_levels, out.tree_built ? "built" : "deferred",
                                                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() - t_levels);
     out.prim_count = f.next_id;
     out.flags = 0;
@@ -631,17 +657,43 @@ FlatScene flatten(const Scene& scene, const BuildOptions& opt) {
     return out;
 }
 
+// BVHAccel::from for every level (bvh.rs:135-453) and the pre-order emission.  Lazy scenes reach this only through the
+// reference_tree callback, i.e. when the device met an exact-t tie.
+void FlatScene::build_reference_tree() {
+    if (tree_built) return;
+    HostLevel* root = static_cast<HostLevel*>(pending.get());
+    if (!root) throw Error(LGB_ERR_INVALID, "FlatScene: no pending levels");
+    root->build_trees();
+    Emitter em{*this, keep_levels};
+    em.emit_level(*root);
+    tree_built = true;
+    pending.reset();
+}
+static int reference_tree_trampoline(void* user, lgb_reference_tree* out) {
+    FlatScene* f = static_cast<FlatScene*>(user);
+    try { f->build_reference_tree(); } catch (...) { return -1; }
+    out->nodes = f->nodes.data(); out->n_nodes = f->nodes.size();
+    out->prim_refs = f->prim_refs.data(); out->n_prim_refs = f->prim_refs.size();
+    out->instances = f->instances.data(); out->n_instances = f->instances.size();
+    return 0;
+}
+
 void FlatScene::describe(lgb_scene_desc* d) const {
     std::memset(d, 0, sizeof *d);
     d->abi_version = LGB_ABI_VERSION; d->flags = flags;
-    d->nodes = nodes.data(); d->n_nodes = nodes.size();
-    d->prim_refs = prim_refs.data(); d->n_prim_refs = prim_refs.size();
+    if (tree_built) {
+        d->nodes = nodes.data(); d->n_nodes = nodes.size();
+        d->prim_refs = prim_refs.data(); d->n_prim_refs = prim_refs.size();
+    } else {                                                  // lazy: the device asks for the tree if it ever needs it
+        d->reference_tree = reference_tree_trampoline; d->reference_tree_user = const_cast<FlatScene*>(this);
+    }
+    std::memcpy(d->bounds_lo, bounds_lo, 24); std::memcpy(d->bounds_hi, bounds_hi, 24);
     d->spheres = spheres.data(); d->n_spheres = spheres.size(); d->sphere_material = sphere_material.data(); d->sphere_id = sphere_id.data();
     d->cuboids = cuboids.data(); d->n_cuboids = cuboids.size(); d->cuboid_material = cuboid_material.data(); d->cuboid_id = cuboid_id.data();
     d->triangles = triangles.data(); d->n_triangles = triangles.size(); d->triangle_material = triangle_material.data(); d->triangle_id = triangle_id.data();
     d->tri_normals = tri_normals.empty() ? nullptr : tri_normals.data();
     d->tri_has_normals = tri_has_normals.empty() ? nullptr : tri_has_normals.data();
-    d->instances = instances.data(); d->n_instances = instances.size();
+    if (tree_built) { d->instances = instances.data(); d->n_instances = instances.size(); }
     d->root = root;
     d->materials = materials.data(); d->n_materials = materials.size();
     d->lights = lights.data(); d->n_lights = lights.size();
@@ -674,7 +726,8 @@ std::unique_ptr<Accel> Accel::from(const Scene& scene, lgb_ctx* ctx, const Build
 Accel::~Accel() { if (dev) lgb_scene_destroy(dev); }
 
 void capture(const Scene& scene, Film& film) {                   // lib.rs:55-104
-    std::unique_ptr<Accel> root = Accel::from(scene, nullptr);
+    BuildOptions opt; opt.lazy_tree = true;                      // the reference BVH is built only if a ray meets an exact-t tie
+    std::unique_ptr<Accel> root = Accel::from(scene, nullptr, opt);
     int rc = lgb_capture(root->ctx, root->dev, film.w, film.h, film.data(), nullptr);
     if (rc) throw Error(rc, std::string("lgb_capture: ") + lgb_last_error(root->ctx));
 }
@@ -764,16 +817,18 @@ void lgh_agg_rotate_axis(void* s, int ag, int axis, double deg) {
 void lgh_agg_rotate(void* s, int ag, double deg, const double* axis) { ((HostScene*)s)->agg(ag).rotate(deg, axis); }
 
 // Accel::from minus the upload: build + flatten on the host.
-void* lgh_flatten(void* s, int keep_levels) {
+void* lgh_flatten(void* s, int keep_levels, int lazy_tree) {
     FlatScene* out = nullptr;
     int rc = guarded([&] {
-        BuildOptions o; o.keep_levels = keep_levels != 0;
+        BuildOptions o; o.keep_levels = keep_levels != 0; o.lazy_tree = lazy_tree != 0;
         out = new FlatScene(flatten(((HostScene*)s)->scene, o));
     });
     (void)rc;
     return out;
 }
 void lgh_flat_free(void* f) { delete (FlatScene*)f; }
+int lgh_flat_tree_built(void* f) { return ((FlatScene*)f)->tree_built ? 1 : 0; }
+int lgh_flat_build_tree(void* f) { return guarded([&] { ((FlatScene*)f)->build_reference_tree(); }); }
 void lgh_flat_describe(void* f, lgb_scene_desc* out) { ((FlatScene*)f)->describe(out); }
 double lgh_flat_build_ms(void* f) { return ((FlatScene*)f)->build_ms; }
 uint32_t lgh_flat_prim_count(void* f) { return ((FlatScene*)f)->prim_count; }

@@ -18,7 +18,7 @@
 
 namespace lgb {
 constexpr int kRenderEvents = 7;
-cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev);
+cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev, int part);
 bool render_fused(uint32_t spp);
 cudaError_t launch_trace(const DevScene&, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns, cudaStream_t);
 cudaError_t launch_l2_read(const void* buf, uint64_t bytes, int iters, float* sink, int sms, cudaStream_t);
@@ -50,7 +50,7 @@ struct lgb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaEvent_t phase[kRenderEvents] = {};
     std::string error;
-    DevBuf radiance, film, counters, tiles, aov_id, aov_t, aov_occl, scratch, wave, wave_ctr;
+    DevBuf radiance, film, counters, tiles, aov_id, aov_t, aov_occl, scratch, wave, wave_ctr, ties;
     std::vector<uint32_t> tile_host;
     uint32_t tile_key[4] = {0, 0, 0, 0};   // w, h, rank, ranks of the cached tile list
     uint32_t tile_count = 0;
@@ -71,6 +71,11 @@ struct lgb_scene {
     void* arena = nullptr;     // one stream-ordered device allocation holding every array of the scene
     bool owns_arena = true;    // false: imported (lgb_scene_import), the caller owns the memory
     bool gpu_built = false;    // the device BVH was built on the device (lgb_gpubuild.cu)
+    // lazy reference tree (lasgun_b200.h): asked for only when a frame holds an exact-t tie
+    lgb_reference_tree_fn lazy_fn = nullptr; void* lazy_user = nullptr;
+    lgb_scene_desc lazy_desc{};                      // the caller's primitive / id arrays (they stay valid for the scene's lifetime)
+    void* rank_buf = nullptr;                        // rank tables uploaded later live outside the arena
+    uint64_t tie_retraces = 0;
     uint64_t bytes = 0;
     DevScene dev{};
     DevCamera cam{};
@@ -148,7 +153,7 @@ void lgb_shutdown(lgb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr}) b->release();
+    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties}) b->release();
     if (c->staging) cudaFreeHost(c->staging);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
     for (auto& e : c->phase) cudaEventDestroy(e);
@@ -182,6 +187,67 @@ static void make_prim_boxes(const lgb_scene_desc* d, raw_vector<PrimBox>& prims)
             for (int k = 0; k < 3; k++) { b.lo[k] = std::min(t.p0[k], std::min(t.p1[k], t.p2[k])); b.hi[k] = std::max(t.p0[k], std::max(t.p1[k], t.p2[k])); }
         }
     });
+}
+
+// The caller's reference tree: indices in range, pre-order layout, and the traversal stack the reference itself would
+// need (bvh.rs:469: 64 entries, it panics beyond).  Returns LGB_OK or an error code with `msg` set.
+static int validate_reference_tree(const lgb_scene_desc* d, std::string& msg) {
+    for (uint64_t i = 0; i < d->n_instances; i++)
+        if (d->instances[i].root_node >= d->n_nodes) { msg = "instance: root_node out of range"; return LGB_ERR_INVALID; }
+    const uint64_t nn = d->n_nodes;
+    std::vector<uint32_t> need(nn, 0);
+    for (uint64_t ii = nn; ii-- > 0;) {
+        const lgb_node& n = d->nodes[ii];
+        if (n.b & LGB_LEAF_FLAG) {
+            uint64_t cnt = n.b & ~LGB_LEAF_FLAG, first = n.a;
+            if (first + cnt > d->n_prim_refs) { msg = "node: leaf range outside prim_refs"; return LGB_ERR_INVALID; }
+            uint32_t k = 0, worst = 0;
+            for (uint64_t j = 0; j < cnt; j++) {
+                uint32_t ref = d->prim_refs[first + j], type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+                uint64_t lim = type == LGB_PRIM_SPHERE ? d->n_spheres : type == LGB_PRIM_CUBOID ? d->n_cuboids : type == LGB_PRIM_TRIANGLE ? d->n_triangles : d->n_instances;
+                if (idx >= lim) { msg = "prim_refs: index out of range"; return LGB_ERR_INVALID; }
+                if (type == LGB_PRIM_INSTANCE) {
+                    uint32_t root = d->instances[idx].root_node;
+                    if (root <= ii) { msg = "instance: child BVH nodes must follow the referencing leaf"; return LGB_ERR_INVALID; }
+                    k++;
+                    worst = std::max(worst, need[root]);
+                }
+            }
+            need[ii] = k ? (k - 1) + std::max(1u, worst) : 0;   // k roots pushed, popped one at a time
+        } else {
+            if (n.b > 2) { msg = "node: split axis out of range"; return LGB_ERR_INVALID; }
+            if (ii + 1 >= nn || n.a <= ii + 1 || n.a >= nn) { msg = "node: child index out of range (pre-order expected)"; return LGB_ERR_INVALID; }
+            need[ii] = 1 + std::max(need[ii + 1], need[n.a]);
+        }
+    }
+    if (need[0] > (uint32_t)kStackDepth) { msg = "BVH needs more than 64 traversal stack entries (the reference would panic, bvh.rs:469)"; return LGB_ERR_UNSUPPORTED; }
+    return LGB_OK;
+}
+
+// Lazy scenes: fetch the reference tree from the caller, build the rank tables and make them resident.
+static int ensure_rank_tables(lgb_ctx* ctx, lgb_scene* s) {
+    if (s->dev.rank || !s->lazy_fn) return LGB_OK;
+    lgb_reference_tree tree{};
+    if (s->lazy_fn(s->lazy_user, &tree) != 0 || !tree.nodes || !tree.n_nodes) return fail(ctx, LGB_ERR_INVALID, "reference_tree callback failed");
+    lgb_scene_desc d = s->lazy_desc;
+    d.nodes = tree.nodes; d.n_nodes = tree.n_nodes; d.prim_refs = tree.prim_refs; d.n_prim_refs = tree.n_prim_refs;
+    d.instances = tree.instances; d.n_instances = tree.n_instances;
+    for (uint64_t i = 0; i < d.n_instances; i++)
+        if (!d.instances[i].identity || d.instances[i].swap_backface) return fail(ctx, LGB_ERR_INVALID, "lazy reference tree: transformed instances need the tree at lgb_scene_create");
+    std::string msg;
+    if (int rc = validate_reference_tree(&d, msg)) return fail(ctx, rc, "reference tree: " + msg);
+    const uint32_t P = s->dev.prim_count;
+    const size_t bytes = (size_t)8 * (P + 1) * 4;
+    cudaError_t e = ctx->reserve_staging(bytes);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaHostAlloc");
+    BuiltScene one; one.spaces.emplace_back(); one.inst_space.assign(d.n_instances, kNoSpace);
+    if (!build_rank_tables(&d, P, one, (uint32_t*)ctx->staging))
+        return fail(ctx, LGB_ERR_INVALID, "reference tree: primitive ids must be a permutation of 0..n-1 and every primitive must be referenced by exactly one leaf");
+    CU(ctx, cudaMallocAsync(&s->rank_buf, bytes, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(s->rank_buf, ctx->staging, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    s->dev.rank = (const uint32_t*)s->rank_buf; s->dev.rank_items = P + 1;
+    return LGB_OK;
 }
 
 // ---- export / import: the arena is position independent once DevScene's pointers are written as offsets
@@ -330,6 +396,7 @@ int lgb_scene_verify(lgb_ctx* ctx, const lgb_scene* s, lgb_build_info* out) {
 void lgb_scene_destroy(lgb_scene* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
+    if (s->rank_buf) cudaFreeAsync(s->rank_buf, s->ctx->stream);
     if (s->arena && s->owns_arena) cudaFreeAsync(s->arena, s->ctx->stream);      // stream-ordered: later work of this context is behind it
     else if (s->arena) cudaStreamSynchronize(s->ctx->stream);                    // borrowed arena: the caller may free it right after
     delete s;
@@ -339,6 +406,7 @@ uint64_t lgb_scene_device_bytes(const lgb_scene* s) { return s ? s->bytes : 0; }
 uint64_t lgb_scene_layout_bytes(void) { return sizeof(SceneLayout); }
 int lgb_scene_export(const lgb_scene* s, void* layout_out, uint64_t layout_bytes, void** arena_dev, uint64_t* arena_bytes) {
     if (!s || !layout_out || layout_bytes < sizeof(SceneLayout) || !arena_dev || !arena_bytes) return LGB_ERR_INVALID;
+    if (s->lazy_fn) return LGB_ERR_UNSUPPORTED;       // a lazy scene's rank tables live outside the arena: create it with the tree to replicate it
     SceneLayout L{};
     L.magic = kLayoutMagic; L.arena_bytes = s->bytes; L.dev = s->dev; L.cam = s->cam; L.shade = s->shade; L.max_abs = s->max_abs;
     const char* base = (const char*)s->arena;
@@ -371,7 +439,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     if (!ctx || !d || !out) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: NULL argument");
     *out = nullptr;
     if (d->abi_version != LGB_ABI_VERSION) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: abi_version mismatch");
-    if (d->n_nodes == 0 || !d->nodes) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: empty BVH (the reference does not terminate on an empty aggregate, bvh.rs:240)");
+    if (!d->reference_tree && (d->n_nodes == 0 || !d->nodes)) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: empty BVH (the reference does not terminate on an empty aggregate, bvh.rs:240)");
     if (d->n_nodes >= (1ull << 31) || d->n_prim_refs >= (1ull << 32) || d->n_spheres >= (1ull << 30) || d->n_cuboids >= (1ull << 30) ||
         d->n_triangles >= (1ull << 30) || d->n_instances >= (1ull << 30))
         return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: array too large for 30-bit primitive references");
@@ -403,37 +471,24 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: NULL array with non-zero count");
     if (!mat_ok(d->sphere_material, d->n_spheres) || !mat_ok(d->cuboid_material, d->n_cuboids) || !mat_ok(d->triangle_material, d->n_triangles))
         return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: material index out of range");
-    for (uint64_t i = 0; i < d->n_instances; i++)
-        if (d->instances[i].root_node >= d->n_nodes) return fail(ctx, LGB_ERR_INVALID, "instance: root_node out of range");
 
-    // ---- validate the node graph and bound the traversal stack (bvh.rs:469: 64 entries)
-    const uint64_t nn = d->n_nodes;
-    std::vector<uint32_t> need(nn, 0);
-    for (uint64_t ii = nn; ii-- > 0;) {
-        const lgb_node& n = d->nodes[ii];
-        if (n.b & LGB_LEAF_FLAG) {
-            uint64_t cnt = n.b & ~LGB_LEAF_FLAG, first = n.a;
-            if (first + cnt > d->n_prim_refs) return fail(ctx, LGB_ERR_INVALID, "node: leaf range outside prim_refs");
-            uint32_t k = 0, worst = 0;
-            for (uint64_t j = 0; j < cnt; j++) {
-                uint32_t ref = d->prim_refs[first + j], type = ref >> 30, idx = ref & 0x3FFFFFFFu;
-                uint64_t lim = type == LGB_PRIM_SPHERE ? d->n_spheres : type == LGB_PRIM_CUBOID ? d->n_cuboids : type == LGB_PRIM_TRIANGLE ? d->n_triangles : d->n_instances;
-                if (idx >= lim) return fail(ctx, LGB_ERR_INVALID, "prim_refs: index out of range");
-                if (type == LGB_PRIM_INSTANCE) {
-                    uint32_t root = d->instances[idx].root_node;
-                    if (root <= ii) return fail(ctx, LGB_ERR_INVALID, "instance: child BVH nodes must follow the referencing leaf");
-                    k++;
-                    worst = std::max(worst, need[root]);
-                }
-            }
-            need[ii] = k ? (k - 1) + std::max(1u, worst) : 0;   // k roots pushed, popped one at a time
-        } else {
-            if (n.b > 2) return fail(ctx, LGB_ERR_INVALID, "node: split axis out of range");
-            if (ii + 1 >= nn || n.a <= ii + 1 || n.a >= nn) return fail(ctx, LGB_ERR_INVALID, "node: child index out of range (pre-order expected)");
-            need[ii] = 1 + std::max(need[ii + 1], need[n.a]);
-        }
+    // ---- the reference tree: given now, or on demand (lazy: only an exact-t tie ever needs it)
+    lgb_scene_desc eager;                                    // lazy desc of a scene the device-side builder does not take: fetch the tree now
+    const uint32_t prim_total = (uint32_t)(d->n_spheres + d->n_cuboids + d->n_triangles);
+    bool lazy = !d->nodes && d->reference_tree;
+    if (lazy && !(prim_total >= 32768u && prim_total <= kLeafFirstMask && !std::getenv("LGB_HOST_BUILD"))) {
+        lgb_reference_tree tree{};
+        if (d->reference_tree(d->reference_tree_user, &tree) != 0 || !tree.nodes || !tree.n_nodes) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: reference_tree callback failed");
+        eager = *d;
+        eager.nodes = tree.nodes; eager.n_nodes = tree.n_nodes; eager.prim_refs = tree.prim_refs; eager.n_prim_refs = tree.n_prim_refs;
+        eager.instances = tree.instances; eager.n_instances = tree.n_instances;
+        d = &eager; lazy = false;
     }
-    if (need[0] > (uint32_t)kStackDepth) return fail(ctx, LGB_ERR_UNSUPPORTED, "BVH needs more than 64 traversal stack entries (the reference would panic, bvh.rs:469)");
+    if (!lazy) {
+        if (d->n_nodes == 0 || !d->nodes) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: empty BVH (the reference does not terminate on an empty aggregate, bvh.rs:240)");
+        std::string vmsg;
+        if (int vrc = validate_reference_tree(d, vmsg)) return fail(ctx, vrc, vmsg);
+    } else if (!d->root.identity || d->root.swap_backface) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: a lazy reference tree needs an untransformed root");
 
     lgb_scene* s = new lgb_scene();
     s->ctx = ctx;
@@ -444,7 +499,8 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     double wlo[3], whi[3];
     {
         double rlo[3], rhi[3];
-        for (int k = 0; k < 3; k++) { rlo[k] = d->nodes[0].lo[k]; rhi[k] = d->nodes[0].hi[k]; }
+        for (int k = 0; k < 3; k++) { rlo[k] = lazy ? d->bounds_lo[k] : (double)d->nodes[0].lo[k]; rhi[k] = lazy ? d->bounds_hi[k] : (double)d->nodes[0].hi[k]; }
+        for (int k = 0; k < 3; k++) if (!(rlo[k] <= rhi[k]) || !std::isfinite(rlo[k]) || !std::isfinite(rhi[k])) return bail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: bad scene bounds"));
         if (!d->root.identity) {                           // the root level's box is in the root aggregate's coordinates
             for (int r = 0; r < 3; r++) {
                 double l = d->root.m[12 + r], h = l;
@@ -477,14 +533,14 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         const bool any_normals = nt && d->tri_normals;
         double M = 0.0;
         auto upd = [&](double v) { const double a = std::fabs(v); if (a > M && std::isfinite(a)) M = a; };
-        for (int k = 0; k < 3; k++) { upd(wlo[k]); upd(whi[k]); upd(d->nodes[0].lo[k]); upd(d->nodes[0].hi[k]); }
+        for (int k = 0; k < 3; k++) { upd(wlo[k]); upd(whi[k]); }
         const double padd = M * std::ldexp(1.0, -20);
         s->max_abs = M; s->dev.err_abs = (float)padd;
         // arena: what the render kernels read (nodes last: their number is known only after the build)
         size_t off = 0;
         auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
         const size_t n_items = n + 1;
-        const size_t o_rank = place((size_t)8 * n_items * 4);
+        const size_t o_rank = place(lazy ? 0 : (size_t)8 * n_items * 4);
         const size_t o_s32 = place(ns * 16), o_s64 = place(ns * 32), o_smat = place(ns * 4), o_sid = place(ns * 4);
         const size_t o_c32 = place(ncb * 32), o_c64 = place(ncb * 48), o_cmat = place(ncb * 4), o_cid = place(ncb * 4);
         const size_t o_tri = place(nt * 48), o_nrm = place(any_normals ? nt * 36 : 0);
@@ -503,7 +559,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         const size_t t_build = place(build_bytes);
         const size_t scratch_bytes = off;
         // pinned staging: [rank | materials | lights | raw arrays]
-        const size_t st_rank = 0, st_mat = ((size_t)8 * n_items * 4 + 255) & ~(size_t)255, st_lights = st_mat + ((mats.size() * 8 + 255) & ~(size_t)255);
+        const size_t st_rank = 0, st_mat = ((lazy ? 0 : (size_t)8 * n_items * 4) + 255) & ~(size_t)255, st_lights = st_mat + ((mats.size() * 8 + 255) & ~(size_t)255);
         const size_t st_raw = st_lights + ((d->n_lights * 72 + 255) & ~(size_t)255);
         void* scratch = nullptr;
         {
@@ -538,7 +594,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         s->t_validate = ms_since(tc0);
         // while the copy and the item kernel run: rank tables from the caller's reference tree, materials, lights
         auto tr0 = std::chrono::steady_clock::now();
-        {
+        if (!lazy) {
             BuiltScene one; one.spaces.emplace_back(); one.inst_space.assign(d->n_instances, kNoSpace);
             if (!build_rank_tables(d, prim_count, one, (uint32_t*)(H + st_rank)))
                 return gfail(fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: primitive ids must be a permutation of 0..n-1 and every primitive must be referenced by exactly one leaf"));
@@ -550,7 +606,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
                 for (int k = 0; k < 3; k++) { l[9 * i + k] = d->lights[i].position[k]; l[9 * i + 3 + k] = d->lights[i].intensity[k]; l[9 * i + 6 + k] = d->lights[i].falloff[k]; }
         }
         s->t_rank = ms_since(tr0);
-        if ((e = cudaMemcpyAsync(D + o_rank, H + st_rank, (size_t)8 * n_items * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        if ((!lazy && (e = cudaMemcpyAsync(D + o_rank, H + st_rank, (size_t)8 * n_items * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) ||
             (e = cudaMemcpyAsync(D + o_mat, H + st_mat, mats.size() * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
             (d->n_lights && (e = cudaMemcpyAsync(D + o_lights, H + st_lights, d->n_lights * 72, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)) {
             cuda_fail(ctx, e, "cudaMemcpyAsync(H2D)"); return gfail(LGB_ERR_CUDA);
@@ -571,8 +627,9 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         s->t_build = s->build_ms;
         s->bytes = o_nodes + (size_t)info.n_nodes * 64;
         s->dev.nodes = (const float4*)(D + o_nodes); s->dev.n_nodes = info.n_nodes;
-        s->dev.rank = (const uint32_t*)(D + o_rank); s->dev.prim_count = prim_count; s->dev.rank_items = (uint32_t)n_items;
+        s->dev.rank = lazy ? nullptr : (const uint32_t*)(D + o_rank); s->dev.prim_count = prim_count; s->dev.rank_items = (uint32_t)n_items;
         s->dev.n_spaces = 1; s->dev.instanced = 0;
+        if (lazy) { s->lazy_fn = d->reference_tree; s->lazy_user = d->reference_tree_user; s->lazy_desc = *d; }
         if (ns) { s->dev.sph32 = la.sph32; s->dev.sph64 = la.sph64; s->dev.sph_mat = la.sph_mat; s->dev.sph_id = la.sph_id; }
         if (ncb) { s->dev.cub32 = la.cub32; s->dev.cub64 = la.cub64; s->dev.cub_mat = la.cub_mat; s->dev.cub_id = la.cub_id; }
         if (nt) { s->dev.tri = la.tri; s->dev.tri_nrm = la.tri_nrm; }
@@ -816,6 +873,13 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         V.work_counter = (unsigned long long*)c->wave_ctr.p;
         V.queue_count = (uint32_t*)((char*)c->wave_ctr.p + 8);
         V.queue_fetch = V.queue_count + LGB_MAX_LIGHTS * 3;
+        V.tie_count = V.queue_fetch + LGB_MAX_LIGHTS * 3;
+        V.tie_list = nullptr; V.tie_cap = 0;
+        if (s->lazy_fn && !s->dev.rank) {
+            CU(c, c->ties.reserve((size_t)kTieCap * 4));
+            V.tie_list = (uint32_t*)c->ties.p; V.tie_cap = kTieCap;
+            if (const char* e = std::getenv("LGB_TIE_CAP")) V.tie_cap = std::min<uint32_t>(kTieCap, (uint32_t)std::strtoul(e, nullptr, 10));   // tests: force the whole-frame re-trace
+        }
     }
     DevOut O{};
     O.radiance = (double*)c->radiance.p;
@@ -832,7 +896,27 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     }
     CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));
     CU(c, cudaEventRecord(c->ev0, st));
-    CU(c, launch_render(S, s->cam, s->shade, W, O, V, a.aov || c->count_work, a.aov, c->sm_count, st, (stats && sync_stats && total) ? c->phase : nullptr));
+    cudaEvent_t* pev = (stats && sync_stats && total) ? c->phase : nullptr;
+    const bool st_on = a.aov || c->count_work;
+    if (s->lazy_fn && !s->dev.rank && total) {
+        // no rank tables yet: trace the primary rays, and only if one met two primitives at bit-identical t fetch the
+        // caller's reference tree, build the tables and re-trace those slots (lasgun_b200.h, "Lazy reference tree")
+        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 1));
+        uint32_t ties = 0;
+        CU(c, cudaMemcpyAsync(&ties, V.tie_count, 4, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+        if (ties) {
+            if (int rc = ensure_rank_tables(c, s)) return rc;
+            s->tie_retraces += ties;
+            DevWork W2 = W;
+            if (ties <= V.tie_cap) { W2.slot_list = V.tie_list; W2.n_list = ties; }
+            else CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));          // too many to list: the whole frame again
+            CU(c, launch_render(s->dev, s->cam, s->shade, W2, O, V, st_on, a.aov, c->sm_count, st, ties <= V.tie_cap ? nullptr : pev, 1));
+        }
+        CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 2));
+    } else {
+        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 3));
+    }
     CU(c, cudaEventRecord(c->ev1, st));
     if (stats && sync_stats) {
         DevCounters hc;

@@ -138,10 +138,13 @@ __device__ __noinline__ bool rank_before_instanced(const DevScene& S, const Ray6
 
 // A candidate with exact parameter t replaces the current best iff it is nearer, or equally near and
 // earlier in the reference's own traversal order for this ray's octant (lgb_build.hpp).
+// Without resident rank tables (lazy reference tree, lgb_api.cu) the tie is only RECORDED: the caller re-traces the ray
+// once the tables exist.
 template <bool INST>
-__device__ __forceinline__ bool accepts(const DevScene& S, const RayF& f, const Ray64& world, const Hit& best, double t, uint32_t ref) {
+__device__ __forceinline__ bool accepts(const DevScene& S, const RayF& f, const Ray64& world, const Hit& best, double t, uint32_t ref, uint32_t& tied) {
     if (t < best.t) return true;
-    if (t == best.t && best.ref != LGB_MISS) {
+    if (t == best.t && best.ref != LGB_MISS && best.ref != ref) {
+        if (!S.rank) { tied = 1u; return false; }
         if (INST) return rank_before_instanced(S, world, ref, best.ref);
         const uint32_t* r = S.rank + (size_t)f.oct * S.rank_items;
         return r[canonical_id(S, ref)] < r[canonical_id(S, best.ref)];
@@ -185,8 +188,9 @@ struct Trav {                 // resumable traversal state of one ray
     uint32_t cur;
     int sp;
     uint32_t space;           // instanced scenes: the space the ray is in right now
+    uint32_t tied;            // an exact-t tie could not be resolved (no rank tables resident)
     __device__ __forceinline__ void init(double tmax, uint32_t root = 0) {
-        best.t = tmax; best.ref = LGB_MISS; best_tf = __double2float_ru(tmax); best_up = inflate_up(tmax); cur = root; sp = 0; space = 0;
+        best.t = tmax; best.ref = LGB_MISS; best_tf = __double2float_ru(tmax); best_up = inflate_up(tmax); cur = root; sp = 0; space = 0; tied = 0;
     }
 };
 
@@ -292,7 +296,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& world, 
                     if (triangle_exact(d3(q0.x, q0.y, q0.z), d3(q1.x, q1.y, q1.z), d3(q2.x, q2.y, q2.z), ray, t, b0, b1, b2)) {
                         const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_TRIANGLE, idx);
                         if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; cur = kDone; return true; } }
-                        else if (accepts<INST>(S, f, world, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
+                        else if (accepts<INST>(S, f, world, best, t, ref, T.tied)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
                     }
                 }
             } else if (type == LGB_PRIM_SPHERE) {
@@ -318,7 +322,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& world, 
                     if (sphere_exact(d3(c01.x, c01.y, c23.x), c23.y, ray, t, inside)) {
                         const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_SPHERE, idx);
                         if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; cur = kDone; return true; } }
-                        else if (accepts<INST>(S, f, world, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
+                        else if (accepts<INST>(S, f, world, best, t, ref, T.tied)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
                     }
                 }
             } else {
@@ -336,7 +340,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& world, 
                     if (cuboid_exact(mn, mx, ray, t, ua, va)) {
                         const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_CUBOID, idx);
                         if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; cur = kDone; return true; } }
-                        else if (accepts<INST>(S, f, world, best, t, ref)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
+                        else if (accepts<INST>(S, f, world, best, t, ref, T.tied)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
                     }
                 }
             }
@@ -709,7 +713,7 @@ __device__ __forceinline__ void block_append_multi(MultiAppendScratch& sc, uint3
 
 template <bool STATS, bool INST>
 __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_primary(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
-    const uint64_t total = W.n_pixels * W.spp;
+    const uint64_t total = W.slot_list ? W.n_list : W.n_pixels * W.spp;      // every sample slot, or the listed ones (tie re-trace)
     const unsigned lane = threadIdx.x & 31u;
     LocalCounters lc = {};
     unsigned int hits = 0, primary = 0;
@@ -730,10 +734,11 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_primary(De
                         if (idx >= total) { need = false; }
                         else {
                             uint32_t x, y, s;
-                            if (slot_ray(C, W, idx, world, x, y, s)) {
-                                g = idx; enter_root<INST>(S, world, ray, f, T, CUDART_INF); active = true; need = false; primary++;
+                            const uint64_t slot = W.slot_list ? W.slot_list[idx] : idx;
+                            if (slot_ray(C, W, slot, world, x, y, s)) {
+                                g = slot; enter_root<INST>(S, world, ray, f, T, CUDART_INF); active = true; need = false; primary++;
                             } else {
-                                V.hit_t[idx] = CUDART_INF; V.hit_ref[idx] = kSlotUnused;       // pixel outside the film: take another
+                                V.hit_t[slot] = CUDART_INF; V.hit_ref[slot] = kSlotUnused;     // pixel outside the film: take another
                             }
                         }
                     }
@@ -751,11 +756,12 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_primary(De
                 const bool hit = T.best.ref != LGB_MISS;
                 V.hit_t[g] = hit ? T.best.t : CUDART_INF; V.hit_ref[g] = T.best.ref;
                 hits += hit ? 1u : 0u;
+                if (T.tied) { const uint32_t k = atomicAdd(V.tie_count, 1u); if (k < V.tie_cap) V.tie_list[k] = (uint32_t)g; }
                 active = false;
             }
         }
     }
-    if (O.counters) {
+    if (O.counters && !W.slot_list) {          // a re-trace of tied slots is not counted twice
         unsigned long long v0 = warp_sum(primary), v1 = warp_sum(hits);
         if (lane == 0) { atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1); }
         if (STATS) {
@@ -1092,20 +1098,32 @@ bool render_fused(uint32_t spp) { return spp >= 1 && spp <= 256; }
 
 // `ev` (optional): kRenderEvents events recorded around the phases: start | primary | setup | anchor shadow rays |
 // pretest + remaining shadow rays | shade | resolve.
+// part 1 = k_primary (every slot, or W.slot_list: the re-trace of tied slots), 2 = everything after it, 3 = both.
 cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O,
-                          const DevWave& V, bool stats, bool all_shadows, int sms, cudaStream_t stream, cudaEvent_t* ev) {
+                          const DevWave& V, bool stats, bool all_shadows, int sms, cudaStream_t stream, cudaEvent_t* ev, int part) {
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], stream); };
-    mark(0);
     const uint64_t total = W.n_pixels * W.spp;
-    if (total == 0) return cudaSuccess;
-    cudaError_t e;
-    if ((e = cudaMemsetAsync(V.work_counter, 0, kWaveCtrBytes, stream)) != cudaSuccess) return e;
     const bool cache = W.spp > 1;
-    if (cache && S.n_lights && (e = cudaMemsetAsync(V.occluder, 0xFF, (size_t)S.n_lights * W.n_pixels * 4, stream)) != cudaSuccess) return e;
     const unsigned pblocks = (unsigned)std::min<uint64_t>((total + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, (uint64_t)sms * LGB_MIN_BLOCKS);
     const bool inst = S.instanced != 0;      // transformed aggregates: the INST kernel variants (the plain ones carry no trace of them)
-    if (inst) { if (stats) k_primary<true, true><<<pblocks, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, true><<<pblocks, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); }
-    else { if (stats) k_primary<true, false><<<pblocks, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, false><<<pblocks, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); }
+    cudaError_t e;
+    if (part & 1) {
+        if (!W.slot_list) mark(0);
+        if (total == 0) return cudaSuccess;
+        if (!W.slot_list) {
+            if ((e = cudaMemsetAsync(V.work_counter, 0, kWaveCtrBytes, stream)) != cudaSuccess) return e;
+            if (cache && S.n_lights && (e = cudaMemsetAsync(V.occluder, 0xFF, (size_t)S.n_lights * W.n_pixels * 4, stream)) != cudaSuccess) return e;
+        } else if ((e = cudaMemsetAsync(V.work_counter, 0, 8, stream)) != cudaSuccess) return e;      // the fetch counter restarts for the listed slots
+        const uint64_t work = W.slot_list ? W.n_list : total;
+        const unsigned pb = (unsigned)std::min<uint64_t>((work + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, (uint64_t)sms * LGB_MIN_BLOCKS);
+        if (pb) {
+            if (inst) { if (stats) k_primary<true, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); }
+            else { if (stats) k_primary<true, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); }
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (!(part & 2)) return cudaSuccess;
+    if (total == 0) return cudaSuccess;
     mark(1);
     const unsigned blocks = (unsigned)((total + 255) / 256), ablocks = (unsigned)((total + kAppendThreads - 1) / kAppendThreads);
     if (inst) { if (all_shadows) k_setup<true, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); }

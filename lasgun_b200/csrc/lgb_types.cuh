@@ -92,6 +92,8 @@ struct DevWork {
     uint64_t n_pixels;               // pixel slots in this launch
     uint32_t spp;
     uint32_t anchor;                 // sample index of the pixel's anchor shadow ray (centre of the sample grid)
+    const uint32_t* slot_list;       // k_primary: trace only these sample slots (re-trace of unresolved exact-t ties) ...
+    uint64_t n_list;                 // ... this many of them
     uint32_t compact_out;            // resolve writes film[slot] instead of film[y*w + x]
 };
 
@@ -122,9 +124,13 @@ struct DevWave {
     unsigned long long* work_counter;   // [0] primary fetch counter; then u32 queue_count[lights][3], queue_fetch[lights][3]
     uint32_t* queue_count;
     uint32_t* queue_fetch;
+    uint32_t* tie_count;             // exact-t ties k_primary could not resolve (scene without resident rank tables)
+    uint32_t* tie_list;              // their sample slots (first tie_cap of them)
+    uint32_t tie_cap;
 };
 constexpr int kQueueA = 0, kQueueB = 1, kQueueC = 2;
-constexpr size_t kWaveCtrBytes = 8 + 4 * (size_t)LGB_MAX_LIGHTS * 3 * 2;
+constexpr size_t kWaveCtrBytes = 8 + 4 * (size_t)LGB_MAX_LIGHTS * 3 * 2 + 8;      // + tie_count (+ pad)
+constexpr uint32_t kTieCap = 1u << 20;
 constexpr uint32_t kSlotUnused = 0xFFFFFFFEu;
 
 struct DevOut {

@@ -12,10 +12,10 @@ from .api import Film, Scene
 class Accel:
     """`Accel::from(&scene)` (lib.rs:42, bvh.rs:135): the scene's BVH, flattened and resident on the GPU."""
 
-    def __init__(self, scene: Scene, ctx: N.Context | None = None):
+    def __init__(self, scene: Scene, ctx: N.Context | None = None, lazy: bool = False):
         self.scene = scene
         self.ctx = ctx or N.default_context()
-        self.flat = N.FlatScene(scene)
+        self.flat = N.FlatScene(scene, lazy=lazy)
         self.dev = N.DeviceScene(self.ctx, self.flat)
 
     @staticmethod
@@ -28,7 +28,7 @@ class Accel:
 
 def capture(scene: Scene, film: Film, ctx: N.Context | None = None):
     """lib.rs:55.  Blocking; fills film.pixels() (row-major RGBA8).  Returns the device stats."""
-    root = Accel(scene, ctx)
+    root = Accel(scene, ctx, lazy=True)          # the reference BVH is built only if a ray meets an exact-t tie
     try:
         _, stats = root.dev.capture(film.w, film.h, out=film.output)
     finally:

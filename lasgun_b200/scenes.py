@@ -215,6 +215,28 @@ def cornell_groups(res=(512, 512), supersampling=2, eye=(0.0, 0.0, 5.0)):
     return scene, tuple(res)
 
 
+def coincident_planes(nspheres=34000, res=(160, 120), supersampling=0):
+    """Every ray that reaches the floor meets TWO coincident triangles at bit-identical t (the mesh lists each of its two
+    triangles twice), and the walls are cuboids sharing edges: the reference's "first primitive tested wins"
+    (triangle.rs:251) decides most pixels.  The sphere field only makes the scene large enough for the device-side builder."""
+    scene = Scene()
+    scene.set_ambient_light([0.2, 0.2, 0.2])
+    camera = scene.set_perspective_camera(55.0)
+    camera.look_at([0.3, 2.5, 6.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+    camera.set_supersampling(supersampling)
+    scene.add_point_light([2.0, 6.0, 3.0], [0.9, 0.9, 0.9], [1.0, 0.0, 0.0])
+    pos = np.array([[-4, 0, -4], [4, 0, -4], [4, 0, 4], [-4, 0, 4]], np.float32)
+    faces = np.array([[0, 2, 1], [0, 3, 2], [0, 2, 1], [0, 3, 2]], np.uint32)
+    floor = scene.add_obj(ObjData(pos, faces))
+    pal = _cube_palette()
+    scene.root.add_obj_of(floor, pal[3])
+    scene.root.add_box([-1.0, 0.0, -1.0], [0.0, 1.0, 0.0], pal[5]); scene.root.add_box([0.0, 0.0, -1.0], [1.0, 1.0, 0.0], pal[6])   # share a face
+    u = splitmix64_uniform(0x5EED00C0, 4 * nspheres).reshape(nspheres, 4)
+    centers = np.stack([-4.0 + 8.0 * u[:, 0], 2.0 + 3.0 * u[:, 1], -6.0 + 4.0 * u[:, 2]], axis=-1)
+    scene.root.add_spheres(centers, 0.01 + 0.02 * u[:, 3], pal, np.arange(nspheres) % 8)
+    return scene, tuple(res)
+
+
 def nested_groups(res=(320, 240), supersampling=1, transformed_root=False, mesh_n=24):
     """Transforms two levels deep, a swap_backface level, spheres / cubes / a mesh inside transformed groups, and
     (optionally) a transformed ROOT aggregate: every branch of the nested-level code (bvh.rs:462-518)."""

@@ -178,6 +178,35 @@ def test_device_built_bvh(native, gpu_ctx, monkeypatch, name):
     assert np.array_equal(film_dev, film_host)
 
 
+@pytest.mark.parametrize("case", ["no_ties", "ties_listed", "ties_whole_frame", "small_scene"])
+def test_lazy_reference_tree(native, oracle, gpu_ctx, monkeypatch, case):
+    """Lazy reference tree (lasgun_b200.h): the reference BVH is not built unless a closest-hit ray meets two primitives at
+    bit-identical t; then the device fetches it through the callback, builds the rank tables and re-traces the tied
+    slots.  Ids, t and film must be the oracle's either way."""
+    if case == "no_ties":
+        sc, (w, h) = scenes.mixed4k(mesh_n=130, nspheres=8000, res=(192, 108), supersampling=1)
+    elif case == "small_scene":
+        sc, (w, h) = scenes.simple("b", 1, 96)                 # below the device-builder threshold: the tree is fetched at creation
+    else:
+        sc, (w, h) = scenes.coincident_planes()
+    if case == "ties_whole_frame":
+        monkeypatch.setenv("LGB_TIE_CAP", "16")
+    flat = native.FlatScene(sc, lazy=True)
+    assert not flat.tree_built
+    dev = native.DeviceScene(gpu_ctx, flat)
+    assert flat.tree_built == (case == "small_scene")
+    out = dev.capture_aov(w, h)
+    rgba, _ = dev.capture(w, h)
+    assert flat.tree_built == (case != "no_ties")             # built exactly when a tie (or a small scene) needed it
+    dev.destroy()
+    ref = oracle.OracleScene(sc).capture(w, h, aov=True)
+    a = parity.aov_report(out, ref)
+    assert a["id_mismatch"] == 0 and a["t_bit_equal"] == a["t_compared"] and a["occl_diff"] == 0, a
+    assert np.array_equal(out["rgba"], ref["rgba"]) and np.array_equal(rgba, ref["rgba"])
+    if case.startswith("ties"):                                # the ties are real: an eager scene resolves thousands of them too
+        assert (ref["prim_id"].reshape(-1) < 4).sum() > 1000
+
+
 @pytest.mark.parametrize("name", ["plain", "instanced"])
 def test_scene_export_import(native, gpu_ctx, name):
     """Multi-GPU replication path on one GPU: the exported arena, copied byte for byte into memory the 'other rank' owns,
