@@ -50,7 +50,8 @@ struct lgb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaEvent_t phase[kRenderEvents] = {};
     std::string error;
-    DevBuf radiance, film, counters, tiles, aov_id, aov_t, aov_occl, scratch, wave, wave_ctr, ties;
+    DevBuf radiance, film, counters, tiles, aov_id, aov_t, aov_occl, scratch, wave, wave_ctr, ties, beam;
+    int beams = -1;                        // LGB_OPT_BEAMS: 0 off, 1 on, -1 automatic
     std::vector<uint32_t> tile_host;
     uint32_t tile_key[4] = {0, 0, 0, 0};   // w, h, rank, ranks of the cached tile list
     uint32_t tile_count = 0;
@@ -129,6 +130,7 @@ int lgb_init(int device, lgb_ctx** out) {
     lgb_ctx* c = new lgb_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char* e = std::getenv("LGB_BEAMS")) { const int v = std::atoi(e); c->beams = v < 0 ? -1 : (v != 0); }
     CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(nullptr, cudaEventCreate(&c->ev0)); CU(nullptr, cudaEventCreate(&c->ev1)); CU(nullptr, cudaEventCreate(&c->ev2));
     for (auto& e : c->phase) CU(nullptr, cudaEventCreate(&e));
@@ -146,6 +148,7 @@ int lgb_init(int device, lgb_ctx** out) {
 int lgb_set_option(lgb_ctx* c, int option, int value) {
     if (!c) return LGB_ERR_INVALID;
     if (option == LGB_OPT_COUNT_WORK) { c->count_work = value != 0; return LGB_OK; }
+    if (option == LGB_OPT_BEAMS) { c->beams = value < 0 ? -1 : (value != 0); return LGB_OK; }
     return fail(c, LGB_ERR_INVALID, "lgb_set_option: unknown option");
 }
 
@@ -153,7 +156,7 @@ void lgb_shutdown(lgb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties}) b->release();
+    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties, &c->beam}) b->release();
     if (c->staging) cudaFreeHost(c->staging);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
     for (auto& e : c->phase) cudaEventDestroy(e);
@@ -874,6 +877,17 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         V.queue_count = (uint32_t*)((char*)c->wave_ctr.p + 8);
         V.queue_fetch = V.queue_count + LGB_MAX_LIGHTS * 3;
         V.tie_count = V.queue_fetch + LGB_MAX_LIGHTS * 3;
+        V.fallback_count = V.tie_count + 1;
+        V.fallback_list = V.queue;                       // the shadow queues are written only after the primary phase
+        // automatic: where a bundle of >= 8 rays shares a traversal that is long enough to be worth sharing (measured: a loss on
+        // scenes of a few dozen primitives, a gain on large ones)
+        W.beams = (W.spp >= 4 && !S.instanced && (c->beams == 1 || (c->beams < 0 && W.spp >= 8 && S.n_nodes >= 4096u))) ? 1u : 0u;
+        if (W.beams) {
+            const uint64_t npx = std::max<uint64_t>(W.n_pixels, 1);
+            CU(c, c->beam.reserve(npx * kBeamList * sizeof(uint2) + npx * 8));
+            V.beam_list = (uint2*)c->beam.p; V.beam_count = (uint32_t*)((char*)c->beam.p + npx * kBeamList * sizeof(uint2));
+            V.beam_bound = (float*)(V.beam_count + npx);
+        }
         V.tie_list = nullptr; V.tie_cap = 0;
         if (s->lazy_fn && !s->dev.rank) {
             CU(c, c->ties.reserve((size_t)kTieCap * 4));

@@ -27,19 +27,19 @@ struct RayF {
     unsigned oct;            // bit a set <=> dir_is_neg[a] (bvh.rs:463)
 };
 
-__device__ __forceinline__ float clamp_idir(double d) {
-    float v = (float)(1.0 / d);
+__device__ __forceinline__ float clamp_idir(float d) {
+    const float v = 1.0f / d;                  // <= 1 ulp from the exact reciprocal: inside the 2^-20 slack of the node test
     return fabsf(v) > 1e30f ? copysignf(1e30f, v) : v;
 }
 
 __device__ __forceinline__ RayF make_rayf(const Ray64& r, float err_abs) {
     RayF f;
     f.ox = (float)r.o.x; f.oy = (float)r.o.y; f.oz = (float)r.o.z;
-    const double rx = 1.0 / r.d.x, ry = 1.0 / r.d.y, rz = 1.0 / r.d.z;
-    f.oct = (rx < 0.0 ? 1u : 0u) | (ry < 0.0 ? 2u : 0u) | (rz < 0.0 ? 4u : 0u);
-    f.ix = clamp_idir(r.d.x); f.iy = clamp_idir(r.d.y); f.iz = clamp_idir(r.d.z);
-    f.nx = -f.ox * f.ix; f.ny = -f.oy * f.iy; f.nz = -f.oz * f.iz;
     f.dx = (float)r.d.x; f.dy = (float)r.d.y; f.dz = (float)r.d.z;
+    // dir_is_neg[a] = (1 / d[a] < 0) (bvh.rs:463, ray.rs:28-33) is the sign bit of d[a], -0 included: no f64 division needed
+    f.oct = (signbit(r.d.x) ? 1u : 0u) | (signbit(r.d.y) ? 2u : 0u) | (signbit(r.d.z) ? 4u : 0u);
+    f.ix = clamp_idir(f.dx); f.iy = clamp_idir(f.dy); f.iz = clamp_idir(f.dz);
+    f.nx = -f.ox * f.ix; f.ny = -f.oy * f.iy; f.nz = -f.oz * f.iz;
     float dd = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
     f.inv_dd = 1.0f / dd;
     f.inv_len = rsqrtf(dd);
@@ -237,6 +237,78 @@ __device__ __forceinline__ void node_loop(const DevScene& S, const RayF& f, floa
     }
 }
 
+// The primitives of one leaf against one ray: conservative f32 filter, then the reference's exact f64 test
+// (DESIGN.md 4).  ANYHIT: returns true as soon as one is hit with t < tmax (T.best holds it); otherwise T.best is
+// updated and the result is false.
+template <bool ANYHIT, bool STATS, bool INST>
+__device__ __forceinline__ bool leaf_prims(const DevScene& S, const Ray64& world, const Ray64& ray, const RayF& f, Trav& T,
+                                           uint32_t type, uint32_t count, uint32_t first, double tmax, LocalCounters& lc) {
+    Hit& best = T.best;
+    float& best_tf = T.best_tf; float& best_up = T.best_up;
+    if (type == LGB_PRIM_TRIANGLE) {
+        for (uint32_t i = 0; i < count; i++) {
+            const uint32_t idx = first + i;
+            const float4* tp = S.tri + 3 * (size_t)idx;
+            const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+            if (STATS) lc.filter[2]++;
+            const bool pass = f.kz == 0 ? tri_filter<0>(q0, q1, q2, f, best_tf) : f.kz == 1 ? tri_filter<1>(q0, q1, q2, f, best_tf) : tri_filter<2>(q0, q1, q2, f, best_tf);
+            if (!pass) continue;
+            if (STATS) lc.exact[2]++;
+            double t, b0, b1, b2;
+            if (triangle_exact(d3(q0.x, q0.y, q0.z), d3(q1.x, q1.y, q1.z), d3(q2.x, q2.y, q2.z), ray, t, b0, b1, b2)) {
+                const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_TRIANGLE, idx);
+                if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; return true; } }
+                else if (accepts<INST>(S, f, world, best, t, ref, T.tied)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
+            }
+        }
+    } else if (type == LGB_PRIM_SPHERE) {
+        for (uint32_t i = 0; i < count; i++) {
+            const uint32_t idx = first + i;
+            const float4 s = __ldg(&S.sph32[idx]);
+            if (STATS) lc.filter[0]++;
+            float lx = s.x - f.ox, ly = s.y - f.oy, lz = s.z - f.oz;
+            float bq = lx * f.dx + ly * f.dy + lz * f.dz;
+            float tc = bq * f.inv_dd;
+            float wx = __fmaf_rn(-tc, f.dx, lx), wy = __fmaf_rn(-tc, f.dy, ly), wz = __fmaf_rn(-tc, f.dz, lz);
+            float perp2 = wx * wx + wy * wy + wz * wz;
+            float rr = s.w + 2.0f * f.err;
+            if (perp2 > rr * rr * (1.0f + 1e-6f)) continue;
+            float half = rr * f.inv_len;
+            float slack = fabsf(tc) * 2e-6f + 2.0f * f.err * f.inv_len;
+            if (tc - half - slack > best_tf) continue;
+            if (tc + half + slack < 0.0f) continue;
+            if (STATS) lc.exact[0]++;
+            const double2 c01 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx));
+            const double2 c23 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx + 2));
+            double t; bool inside;
+            if (sphere_exact(d3(c01.x, c01.y, c23.x), c23.y, ray, t, inside)) {
+                const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_SPHERE, idx);
+                if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; return true; } }
+                else if (accepts<INST>(S, f, world, best, t, ref, T.tied)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
+            }
+        }
+    } else {
+        for (uint32_t i = 0; i < count; i++) {
+            const uint32_t idx = first + i;
+            const float4 lo = __ldg(&S.cub32[2 * idx]), hi = __ldg(&S.cub32[2 * idx + 1]);
+            if (STATS) lc.filter[1]++;
+            float tn;
+            if (!slab2(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, f, CUDART_INF_F, tn)) continue;
+            if (STATS) lc.exact[1]++;
+            double mn[3], mx[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { mn[k] = __ldg(&S.cub64[6 * (size_t)idx + k]); mx[k] = __ldg(&S.cub64[6 * (size_t)idx + 3 + k]); }
+            double t; int ua, va;
+            if (cuboid_exact(mn, mx, ray, t, ua, va)) {
+                const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_CUBOID, idx);
+                if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; return true; } }
+                else if (accepts<INST>(S, f, world, best, t, ref, T.tied)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
+            }
+        }
+    }
+    return false;
+}
+
 // Runs until the ray is finished (returns true; T.cur == kDone) or, with REFILL, until fewer than
 // `refill_below` lanes of the warp are still traversing (returns false: the caller tops the warp up with
 // new rays and calls again; persistent threads with dynamic fetch).
@@ -283,67 +355,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& world, 
                     cur = c.root_node;
                     continue;
                 }
-            } else if (type == LGB_PRIM_TRIANGLE) {
-                for (uint32_t i = 0; i < count; i++) {
-                    const uint32_t idx = first + i;
-                    const float4* tp = S.tri + 3 * (size_t)idx;
-                    const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-                    if (STATS) lc.filter[2]++;
-                    const bool pass = f.kz == 0 ? tri_filter<0>(q0, q1, q2, f, best_tf) : f.kz == 1 ? tri_filter<1>(q0, q1, q2, f, best_tf) : tri_filter<2>(q0, q1, q2, f, best_tf);
-                    if (!pass) continue;
-                    if (STATS) lc.exact[2]++;
-                    double t, b0, b1, b2;
-                    if (triangle_exact(d3(q0.x, q0.y, q0.z), d3(q1.x, q1.y, q1.z), d3(q2.x, q2.y, q2.z), ray, t, b0, b1, b2)) {
-                        const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_TRIANGLE, idx);
-                        if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; cur = kDone; return true; } }
-                        else if (accepts<INST>(S, f, world, best, t, ref, T.tied)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
-                    }
-                }
-            } else if (type == LGB_PRIM_SPHERE) {
-                for (uint32_t i = 0; i < count; i++) {
-                    const uint32_t idx = first + i;
-                    const float4 s = __ldg(&S.sph32[idx]);
-                    if (STATS) lc.filter[0]++;
-                    float lx = s.x - f.ox, ly = s.y - f.oy, lz = s.z - f.oz;
-                    float bq = lx * f.dx + ly * f.dy + lz * f.dz;
-                    float tc = bq * f.inv_dd;
-                    float wx = __fmaf_rn(-tc, f.dx, lx), wy = __fmaf_rn(-tc, f.dy, ly), wz = __fmaf_rn(-tc, f.dz, lz);
-                    float perp2 = wx * wx + wy * wy + wz * wz;
-                    float rr = s.w + 2.0f * f.err;
-                    if (perp2 > rr * rr * (1.0f + 1e-6f)) continue;
-                    float half = rr * f.inv_len;
-                    float slack = fabsf(tc) * 2e-6f + 2.0f * f.err * f.inv_len;
-                    if (tc - half - slack > best_tf) continue;
-                    if (tc + half + slack < 0.0f) continue;
-                    if (STATS) lc.exact[0]++;
-                    const double2 c01 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx));
-                    const double2 c23 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx + 2));
-                    double t; bool inside;
-                    if (sphere_exact(d3(c01.x, c01.y, c23.x), c23.y, ray, t, inside)) {
-                        const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_SPHERE, idx);
-                        if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; cur = kDone; return true; } }
-                        else if (accepts<INST>(S, f, world, best, t, ref, T.tied)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
-                    }
-                }
-            } else {
-                for (uint32_t i = 0; i < count; i++) {
-                    const uint32_t idx = first + i;
-                    const float4 lo = __ldg(&S.cub32[2 * idx]), hi = __ldg(&S.cub32[2 * idx + 1]);
-                    if (STATS) lc.filter[1]++;
-                    float tn;
-                    if (!slab2(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, f, CUDART_INF_F, tn)) continue;
-                    if (STATS) lc.exact[1]++;
-                    double mn[3], mx[3];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) { mn[k] = __ldg(&S.cub64[6 * (size_t)idx + k]); mx[k] = __ldg(&S.cub64[6 * (size_t)idx + 3 + k]); }
-                    double t; int ua, va;
-                    if (cuboid_exact(mn, mx, ray, t, ua, va)) {
-                        const uint32_t ref = LGB_PRIM_REF(LGB_PRIM_CUBOID, idx);
-                        if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; cur = kDone; return true; } }
-                        else if (accepts<INST>(S, f, world, best, t, ref, T.tied)) { best.t = t; best.ref = ref; best_tf = __double2float_ru(t); best_up = inflate_up(t); }
-                    }
-                }
-            }
+            } else if (leaf_prims<ANYHIT, STATS, INST>(S, world, ray, f, T, type, count, first, tmax, lc)) { cur = kDone; return true; }
         }
         cur = stack_pop<(!ANYHIT && LGB_TSTACK)>(sp, stack, tstack, best_up);
         if (REFILL && __popc(__activemask()) < refill_below) return cur == kDone;
@@ -567,10 +579,12 @@ __device__ __forceinline__ void shade_point(const DevScene& S, const Ray64& ray,
 }
 
 // ------------------------------------------------------------------ work mapping
-__device__ __forceinline__ bool slot_to_pixel(const DevWork& W, uint64_t p, uint32_t& x, uint32_t& y) {
+// Slot indices fit 32 bits (run_capture rejects launches of 2^32 samples or more): no 64-bit divisions on this path.
+__device__ __forceinline__ bool slot_to_pixel(const DevWork& W, uint64_t p64, uint32_t& x, uint32_t& y) {
+    const uint32_t p = (uint32_t)p64;
     if (W.mode == 0) {
-        uint32_t tile_local = (uint32_t)(p / (kMacroTile * kMacroTile));
-        uint32_t q = (uint32_t)(p % (kMacroTile * kMacroTile));
+        uint32_t tile_local = p / (uint32_t)(kMacroTile * kMacroTile);
+        uint32_t q = p % (uint32_t)(kMacroTile * kMacroTile);
         uint32_t tile = W.tile_list[tile_local];
         uint32_t micro = q / 32, in = q % 32;
         uint32_t px = (micro % (kMacroTile / kMicroW)) * kMicroW + in % kMicroW;
@@ -579,10 +593,12 @@ __device__ __forceinline__ bool slot_to_pixel(const DevWork& W, uint64_t p, uint
         y = (tile / W.n_macro_x) * kMacroTile + py;
         return x < W.w && y < W.h;
     } else {
-        uint64_t off = (uint64_t)W.sub_k + p * (uint64_t)W.sub_n;   // lib.rs:152-154
-        x = (uint32_t)(off % W.w);
-        y = (uint32_t)(off / W.w);
-        return off < (uint64_t)W.w * W.h;
+        const uint64_t off64 = (uint64_t)W.sub_k + (uint64_t)p * (uint64_t)W.sub_n;   // lib.rs:152-154
+        if (off64 >= (uint64_t)W.w * W.h) return false;                              // (w * h < 2^32)
+        const uint32_t off = (uint32_t)off64;
+        y = off / W.w;
+        x = off - y * W.w;
+        return true;
     }
 }
 
@@ -629,8 +645,8 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 // k_resolve  per pixel: in-order sample sum, weight, quantise, uchar4 store (integrate.rs:16-20, img.rs:56-67)
 
 __device__ __forceinline__ bool slot_ray(const DevCamera& C, const DevWork& W, uint64_t g, Ray64& ray, uint32_t& x, uint32_t& y, uint32_t& s) {
-    const uint64_t p = g / W.spp;
-    s = (uint32_t)(g % W.spp);
+    const uint32_t g32 = (uint32_t)g, p = g32 / W.spp;
+    s = g32 - p * W.spp;
     if (!slot_to_pixel(W, p, x, y)) return false;
     ray = camera_ray(C, W, x, y, s);
     return true;
@@ -713,7 +729,7 @@ __device__ __forceinline__ void block_append_multi(MultiAppendScratch& sc, uint3
 
 template <bool STATS, bool INST>
 __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_primary(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
-    const uint64_t total = W.slot_list ? W.n_list : W.n_pixels * W.spp;      // every sample slot, or the listed ones (tie re-trace)
+    const uint64_t total = W.slot_list ? (W.n_list_dev ? (uint64_t)*W.n_list_dev : W.n_list) : W.n_pixels * W.spp;   // every sample slot, or the listed ones
     const unsigned lane = threadIdx.x & 31u;
     LocalCounters lc = {};
     unsigned int hits = 0, primary = 0;
@@ -761,12 +777,215 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_primary(De
             }
         }
     }
-    if (O.counters && !W.slot_list) {          // a re-trace of tied slots is not counted twice
+    if (O.counters && (!W.slot_list || W.n_list_dev)) {          // a re-trace of tied slots is not counted twice (beam fallback slots are new)
         unsigned long long v0 = warp_sum(primary), v1 = warp_sum(hits);
         if (lane == 0) { atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1); }
         if (STATS) {
             unsigned long long n = warp_sum(lc.node_tests);
             if (lane == 0) { atomicAdd(&O.counters->node_tests, n); atomicAdd(&O.counters->p_node_tests, n); }
+            for (int k = 0; k < 3; k++) {
+                unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
+                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); atomicAdd(&O.counters->p_filter[k], a); atomicAdd(&O.counters->p_exact[k], b); }
+            }
+        }
+    }
+}
+
+// ================================================================== pixel beams
+// At >= 4 samples per pixel the rays of a pixel are a thin bundle with a common origin, and each of them repeats
+// almost the same interior-node tests.  k_beam traverses the BVH ONCE per pixel with the whole bundle -- a slab test
+// on the per-axis interval of 1/d over the bundle, conservative for every ray in it -- and writes the leaves it
+// reaches, sorted by entry distance; k_leafp then gives every sample ray only those leaves (f32 filter + exact f64
+// test as everywhere else; a leaf whose entry distance is beyond the ray's best hit ends the walk).  Pixels whose
+// bundle reaches more than kBeamList leaves fall back to the per-ray traversal (k_primary over a slot list).
+// The bundle is described by its centre ray plus, per axis, the relative spread of 1/d over the bundle: for every ray r
+// of the bundle and every plane, t_a(r) = (plane - o) / d_a(r) lies within t_a(centre) (1 -+ spread_a), because the
+// origin is common.  So the bundle test is the centre ray's slab test with every entry distance taken as early and every
+// exit distance as late as the spread allows: six more FMAs, and conservative for every ray of the bundle.
+struct BeamF { float sx, sy, sz; };
+__device__ __forceinline__ BeamF make_beam(const DevCamera& C, const DevWork& W, uint32_t x, uint32_t y, const Ray64& centre) {
+    const uint32_t r = C.root;
+    const uint32_t corner[4] = {0u, r - 1u, (r - 1u) * r, r * r - 1u};         // sample (i, j) = i * root + j; d is affine in (i, j)
+    double dmin[3] = {CUDART_INF, CUDART_INF, CUDART_INF}, dmax[3] = {-CUDART_INF, -CUDART_INF, -CUDART_INF};
+    for (int c = 0; c < 4; c++) {
+        const Ray64 q = camera_ray(C, W, x, y, corner[c]);
+        dmin[0] = fmin(dmin[0], q.d.x); dmax[0] = fmax(dmax[0], q.d.x);
+        dmin[1] = fmin(dmin[1], q.d.y); dmax[1] = fmax(dmax[1], q.d.y);
+        dmin[2] = fmin(dmin[2], q.d.z); dmax[2] = fmax(dmax[2], q.d.z);
+    }
+    const double dc[3] = {centre.d.x, centre.d.y, centre.d.z};
+    float sp[3];
+    for (int a = 0; a < 3; a++) {
+        // 1/d over [dmin, dmax] relative to 1/dc; a component that changes sign inside the bundle does not constrain at all
+        if (!(dmin[a] > 0.0) && !(dmax[a] < 0.0)) { sp[a] = 1e30f; continue; }
+        const double lo = fmin(fabs(dmin[a]), fabs(dmax[a])), hi = fmax(fabs(dmin[a]), fabs(dmax[a])), c = fabs(dc[a]);
+        const double up = c / lo - 1.0, dn = 1.0 - c / hi;                      // |1/d| in |1/dc| [1 - dn, 1 + up]
+        sp[a] = __double2float_ru(fmax(fmax(up, dn), 0.0) * 1.0000001 + 4e-7);   // + the f32 rounding of the centre ray's own 1/d and products
+    }
+    BeamF B; B.sx = sp[0]; B.sy = sp[1]; B.sz = sp[2];
+    return B;
+}
+// OCT: direction octant of the centre ray (bit a set <=> d[a] < 0), or 8 for the generic form.
+template <int OCT>
+__device__ __forceinline__ bool beam_slab(float lx, float ly, float lz, float hx, float hy, float hz, const RayF& f, const BeamF& B, float& tn_out) {
+    float tnx, tfx, tny, tfy, tnz, tfz;
+    if (OCT < 8) {
+        tnx = __fmaf_rn((OCT & 1) ? hx : lx, f.ix, f.nx); tfx = __fmaf_rn((OCT & 1) ? lx : hx, f.ix, f.nx);
+        tny = __fmaf_rn((OCT & 2) ? hy : ly, f.iy, f.ny); tfy = __fmaf_rn((OCT & 2) ? ly : hy, f.iy, f.ny);
+        tnz = __fmaf_rn((OCT & 4) ? hz : lz, f.iz, f.nz); tfz = __fmaf_rn((OCT & 4) ? lz : hz, f.iz, f.nz);
+    } else {
+        const float ax = __fmaf_rn(lx, f.ix, f.nx), bx = __fmaf_rn(hx, f.ix, f.nx), ay = __fmaf_rn(ly, f.iy, f.ny), by = __fmaf_rn(hy, f.iy, f.ny);
+        const float az = __fmaf_rn(lz, f.iz, f.nz), bz = __fmaf_rn(hz, f.iz, f.nz);
+        tnx = fminf(ax, bx); tfx = fmaxf(ax, bx); tny = fminf(ay, by); tfy = fmaxf(ay, by); tnz = fminf(az, bz); tfz = fmaxf(az, bz);
+    }
+    // widen: entry distances down, exit distances up, by |t| * spread
+    tnx = __fmaf_rn(-fabsf(tnx), B.sx, tnx); tfx = __fmaf_rn(fabsf(tfx), B.sx, tfx);
+    tny = __fmaf_rn(-fabsf(tny), B.sy, tny); tfy = __fmaf_rn(fabsf(tfy), B.sy, tfy);
+    tnz = __fmaf_rn(-fabsf(tnz), B.sz, tnz); tfz = __fmaf_rn(fabsf(tfz), B.sz, tfz);
+    const float tn = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), 0.0f);
+    const float tf = fminf(fminf(tfx, tfy), tfz) * (1.0f + 9.5367431640625e-7f);
+    tn_out = tn;
+    return !(tn > tf);            // a NaN (inf - inf on a degenerate axis) must not reject
+}
+
+// k_beam also traces the pixel's CENTRE sample exactly while it walks (nearer child first): its closest hit t_c bounds
+// the walk -- a node or leaf whose bundle entry distance exceeds B = t_c (1 + 1/32) is not visited.  The list is then
+// complete for every ray of the pixel whose own closest hit is not farther than B; k_leafp sends the others (depth
+// discontinuities inside the pixel) and the pixels with more than kBeamList leaves to the per-ray traversal.
+constexpr float kBeamMargin = 1.03125f;
+template <bool STATS>
+__global__ void __launch_bounds__(256, 4) k_beam(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    LocalCounters lc = {};
+    unsigned int hits = 0, primary = 0;
+    if (p < W.n_pixels) {
+        uint32_t x, y;
+        uint32_t n = 0;
+        float bound = CUDART_INF_F;
+        if (slot_to_pixel(W, p, x, y)) {
+            const uint64_t g = p * W.spp + W.anchor;
+            const Ray64 world = camera_ray(C, W, x, y, W.anchor);
+            const BeamF B = make_beam(C, W, x, y, world);
+            Ray64 ray; RayF f; Trav T;
+            enter_root<false>(S, world, ray, f, T, CUDART_INF);
+            primary++;
+            uint32_t stack[kStackDepth]; float tstack[kStackDepth]; int sp = 0;
+            uint2 list[kBeamList];                     // (leaf word, entry distance) in visiting order: nearer child first, so nearly sorted
+            uint32_t cur = 0;
+            float cur_t = 0.0f;                        // bundle entry distance of `cur`
+            bool over = false;
+            while (cur != kDone && !over) {
+                if (cur & kLeafBit) {                  // a leaf the bundle enters before the bound: list it, test the centre ray
+                    const float t = cur_t;
+                    if (n == (uint32_t)kBeamList) { over = true; break; }
+                    list[n++] = make_uint2(cur, __float_as_uint(t));
+                    leaf_prims<false, STATS, false>(S, world, ray, f, T, (cur >> 29) & 3u, ((cur >> 24) & 31u) + 1u, cur & kLeafFirstMask, CUDART_INF, lc);
+                    bound = T.best_up * kBeamMargin;
+                    cur = kDone;
+                } else {
+                    const float4* np = S.nodes + 4 * (size_t)cur;
+                    const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+                    const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+                    if (STATS) lc.node_tests++;
+                    float t0, t1;
+                    bool h0, h1;
+                    switch (f.oct) {
+#define LGB_BEAM_CASE(o) case o: h0 = beam_slab<o>(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, f, B, t0); h1 = beam_slab<o>(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, f, B, t1); break;
+                    LGB_BEAM_CASE(0) LGB_BEAM_CASE(1) LGB_BEAM_CASE(2) LGB_BEAM_CASE(3) LGB_BEAM_CASE(4) LGB_BEAM_CASE(5) LGB_BEAM_CASE(6)
+                    default: h0 = beam_slab<7>(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, f, B, t0); h1 = beam_slab<7>(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, f, B, t1); break;
+#undef LGB_BEAM_CASE
+                    }
+                    h0 = h0 && t0 <= bound; h1 = h1 && t1 <= bound;
+                    const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+                    if (h0 && h1) {
+                        const bool swap = t1 < t0;
+                        cur = swap ? c1 : c0; cur_t = swap ? t1 : t0;
+                        tstack[sp] = swap ? t0 : t1; stack[sp++] = swap ? c0 : c1;
+                    } else if (h0) { cur = c0; cur_t = t0; }
+                    else if (h1) { cur = c1; cur_t = t1; }
+                    else cur = kDone;
+                }
+                while (cur == kDone && sp) {           // nearest deferred entry that still starts before the bound
+                    --sp;
+                    if (tstack[sp] <= bound) { cur = stack[sp]; cur_t = tstack[sp]; }
+                }
+            }
+            if (over) {
+                n = kBeamOverflow; primary--;              // the walk was cut short: every sample of the pixel, the centre one included, is traced on its own
+            } else {
+                const bool hit = T.best.ref != LGB_MISS;
+                V.hit_t[g] = hit ? T.best.t : CUDART_INF; V.hit_ref[g] = T.best.ref;      // the centre sample is done
+                hits += hit ? 1u : 0u;
+                if (T.tied) { const uint32_t k = atomicAdd(V.tie_count, 1u); if (k < V.tie_cap) V.tie_list[k] = (uint32_t)g; }
+                uint32_t m = 0;
+                for (uint32_t i = 0; i < n; i++) {         // entries listed before the bound tightened may lie beyond it now
+                    if (__uint_as_float(list[i].y) > bound) continue;
+                    V.beam_list[(size_t)m * W.n_pixels + p] = list[i]; m++;
+                }
+                n = m;
+            }
+        }
+        V.beam_count[p] = n;
+        V.beam_bound[p] = bound;
+    }
+    if (O.counters) {
+        unsigned long long v0 = warp_sum(primary), v1 = warp_sum(hits);
+        if (lane == 0) { atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1); }
+        if (STATS) {
+            const unsigned long long v = warp_sum(lc.node_tests);
+            if (lane == 0) { atomicAdd(&O.counters->node_tests, v); atomicAdd(&O.counters->p_node_tests, v); atomicAdd(&O.counters->beam_node_tests, v); }
+            for (int k = 0; k < 3; k++) {
+                unsigned long long a = warp_sum(lc.filter[k]), b2 = warp_sum(lc.exact[k]);
+                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b2); atomicAdd(&O.counters->p_filter[k], a); atomicAdd(&O.counters->p_exact[k], b2); }
+            }
+        }
+    }
+}
+
+// One thread per sample slot (the centre sample is already done): the leaves of its pixel's beam, nearest first.
+template <bool STATS>
+__global__ void __launch_bounds__(256, 4) k_leafp(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
+    __shared__ AppendScratch sc;
+    const uint64_t total = W.n_pixels * W.spp;
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    LocalCounters lc = {};
+    unsigned int hits = 0, primary = 0;
+    bool fallback = false;
+    if (g < total && (uint32_t)g % W.spp != W.anchor) {
+        const uint64_t p = (uint32_t)g / W.spp;
+        const uint32_t n = V.beam_count[p];
+        Ray64 world; uint32_t x, y, s;
+        if (!slot_ray(C, W, g, world, x, y, s)) { V.hit_t[g] = CUDART_INF; V.hit_ref[g] = kSlotUnused; }
+        else if (n == kBeamOverflow) fallback = true;
+        else {
+            const float bound = V.beam_bound[p];
+            Ray64 ray; RayF f; Trav T;
+            enter_root<false>(S, world, ray, f, T, CUDART_INF);
+            for (uint32_t i = 0; i < n; i++) {
+                const uint2 e = __ldg(&V.beam_list[(size_t)i * W.n_pixels + p]);
+                if (__uint_as_float(e.y) > T.best_up) continue;            // starts beyond the best hit (the list is only nearly sorted)
+                leaf_prims<false, STATS, false>(S, world, ray, f, T, (e.x >> 29) & 3u, ((e.x >> 24) & 31u) + 1u, e.x & kLeafFirstMask, CUDART_INF, lc);
+            }
+            if (T.best_up <= bound) {              // the list held every leaf that starts before the bound: the result is final
+                const bool hit = T.best.ref != LGB_MISS;
+                primary++;
+                V.hit_t[g] = hit ? T.best.t : CUDART_INF; V.hit_ref[g] = T.best.ref;
+                hits += hit ? 1u : 0u;
+                if (T.tied) { const uint32_t k = atomicAdd(V.tie_count, 1u); if (k < V.tie_cap) V.tie_list[k] = (uint32_t)g; }
+            } else fallback = true;                // hit beyond the bound, or none: this ray needs its own traversal
+        }
+    } else if (g < total) {                        // centre sample: done by k_beam, unless ...
+        uint32_t x, y;
+        if (!slot_to_pixel(W, (uint32_t)g / W.spp, x, y)) { V.hit_t[g] = CUDART_INF; V.hit_ref[g] = kSlotUnused; }      // ... the pixel is outside the film
+        else if (V.beam_count[(uint32_t)g / W.spp] == kBeamOverflow) fallback = true;                                      // ... or its walk was cut short
+    }
+    block_append(sc, fallback, (uint32_t)g, V.fallback_list, V.fallback_count);
+    if (O.counters) {
+        unsigned long long v0 = warp_sum(primary), v1 = warp_sum(hits);
+        if (lane == 0) { atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1); }
+        if (STATS) {
             for (int k = 0; k < 3; k++) {
                 unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
                 if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); atomicAdd(&O.counters->p_filter[k], a); atomicAdd(&O.counters->p_exact[k], b); }
@@ -816,7 +1035,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
     __shared__ uint32_t qmap[2 * LGB_MAX_LIGHTS];
     if (threadIdx.x < 2 * S.n_lights) qmap[threadIdx.x] = (threadIdx.x >> 1) * 3 + ((threadIdx.x & 1) ? kQueueB : kQueueA);
     __syncthreads();
-    const bool anchor = W.spp == 1 || (uint32_t)(g % W.spp) == W.anchor;
+    const bool anchor = W.spp == 1 || (uint32_t)g % W.spp == W.anchor;
     unsigned long long flags = 0;
     if (live) for (uint32_t l = 0; l < S.n_lights; l++) if ((need >> l) & 1u) flags |= 1ull << (2 * l + (anchor ? 0 : 1));
     block_append_multi(sc, 2 * S.n_lights, flags, (uint32_t)g, V.queue, V.queue_stride, V.queue_count, qmap);
@@ -1016,7 +1235,7 @@ __global__ void __launch_bounds__(256, LGB_SHADE_MIN_BLOCKS) k_shade(DevScene S,
         D3 c = d3(0, 0, 0);
         for (uint32_t k = 0; k < W.spp; k++) c = c + d3(rad[3 * (threadIdx.x + k)], rad[3 * (threadIdx.x + k) + 1], rad[3 * (threadIdx.x + k) + 2]);
         c = c * (1.0 / (double)W.spp);
-        const uint64_t p = g / W.spp;
+        const uint64_t p = (uint32_t)g / W.spp;
         reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)y * W.w + x] = quantise(c);
     }
 }
@@ -1116,7 +1335,15 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
         } else if ((e = cudaMemsetAsync(V.work_counter, 0, 8, stream)) != cudaSuccess) return e;      // the fetch counter restarts for the listed slots
         const uint64_t work = W.slot_list ? W.n_list : total;
         const unsigned pb = (unsigned)std::min<uint64_t>((work + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, (uint64_t)sms * LGB_MIN_BLOCKS);
-        if (pb) {
+        if (W.beams && W.spp >= 4 && !inst && !W.slot_list) {
+            // one bundle traversal per pixel, then every sample ray walks its pixel's leaf list; pixels whose bundle
+            // reaches too many leaves go through the per-ray traversal (their slots are listed by k_leafp)
+            const unsigned bb = (unsigned)((W.n_pixels + 255) / 256), lb = (unsigned)((total + 255) / 256);
+            if (stats) { k_beam<true><<<bb, 256, 0, stream>>>(S, C, W, O, V); k_leafp<true><<<lb, 256, 0, stream>>>(S, C, W, O, V); }
+            else { k_beam<false><<<bb, 256, 0, stream>>>(S, C, W, O, V); k_leafp<false><<<lb, 256, 0, stream>>>(S, C, W, O, V); }
+            DevWork Wf = W; Wf.slot_list = V.fallback_list; Wf.n_list = 0; Wf.n_list_dev = V.fallback_count;
+            if (stats) k_primary<true, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, Wf, O, V); else k_primary<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, Wf, O, V);
+        } else if (pb) {
             if (inst) { if (stats) k_primary<true, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); }
             else { if (stats) k_primary<true, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); }
         }

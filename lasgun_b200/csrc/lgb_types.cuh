@@ -93,8 +93,10 @@ struct DevWork {
     uint32_t spp;
     uint32_t anchor;                 // sample index of the pixel's anchor shadow ray (centre of the sample grid)
     const uint32_t* slot_list;       // k_primary: trace only these sample slots (re-trace of unresolved exact-t ties) ...
-    uint64_t n_list;                 // ... this many of them
+    uint64_t n_list;                 // ... this many of them ...
+    const uint32_t* n_list_dev;      // ... or as many as this device counter says (beam fallback)
     uint32_t compact_out;            // resolve writes film[slot] instead of film[y*w + x]
+    uint32_t beams;                  // primary rays through pixel beams (k_beam / k_leafp) when spp >= 4
 };
 
 struct DevCounters {
@@ -102,7 +104,8 @@ struct DevCounters {
     unsigned long long node_tests;     // node fetches (each tests two child boxes)
     unsigned long long filter[3];    // f32 filter tests by primitive type (sphere, cuboid, triangle)
     unsigned long long exact[3];     // f64 reference-arithmetic tests by primitive type
-    unsigned long long p_node_tests, p_filter[3], p_exact[3];   // the share of k_primary in the three counters above
+    unsigned long long p_node_tests, p_filter[3], p_exact[3];   // the share of the primary-ray kernels in the three counters above
+    unsigned long long beam_node_tests;                         // of those: node fetches of the pixel beams (k_beam)
     unsigned int stack_overflow;
     unsigned int pad;
 };
@@ -127,10 +130,18 @@ struct DevWave {
     uint32_t* tie_count;             // exact-t ties k_primary could not resolve (scene without resident rank tables)
     uint32_t* tie_list;              // their sample slots (first tie_cap of them)
     uint32_t tie_cap;
+    // pixel beams (k_beam / k_leafp): leaves reached by the bundle of a pixel's sample rays, nearest first
+    uint2* beam_list;                // [i * n_pixels + pixel_slot] = (leaf word, entry distance bits)
+    uint32_t* beam_count;            // per pixel slot; kBeamOverflow: fall back to the per-ray traversal
+    float* beam_bound;               // per pixel slot: the list is complete for rays whose closest hit is not beyond it
+    uint32_t* fallback_list;         // sample slots of such pixels (aliases the shadow queues, which are not yet in use)
+    uint32_t* fallback_count;
 };
 constexpr int kQueueA = 0, kQueueB = 1, kQueueC = 2;
-constexpr size_t kWaveCtrBytes = 8 + 4 * (size_t)LGB_MAX_LIGHTS * 3 * 2 + 8;      // + tie_count (+ pad)
+constexpr size_t kWaveCtrBytes = 8 + 4 * (size_t)LGB_MAX_LIGHTS * 3 * 2 + 8;      // + tie_count, fallback_count
 constexpr uint32_t kTieCap = 1u << 20;
+constexpr int kBeamList = 48;                  // leaves a pixel beam may reach before the pixel falls back to per-ray traversal
+constexpr uint32_t kBeamOverflow = 0xFFFFFFFFu;
 constexpr uint32_t kSlotUnused = 0xFFFFFFFEu;
 
 struct DevOut {
