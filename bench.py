@@ -329,8 +329,9 @@ def run_gpu(args):
                     "reference_tree_built": bool(world > 1 or flat_i.tree_built),
                     "parts_ms": dict(zip(("flatten", "scene_create_device_bvh_upload", "render_readback_destroy"),
                                          [statistics.median(p[i] for p in e2e_parts[1:]) for i in range(3)]))},
-            "gpu_launches": (4 + nl * (3 if spp > 1 else 1)) * args.steps,
-            "roofline": {"kernel": "k_primary (camera rays + closest-hit traversal), %.1f%% of the frame" % (100.0 * phases[0] / max(sum(phases), 1e-9)),
+            "gpu_launches": int(s2["kernel_launches"]) * args.steps,
+            "roofline": {"kernel": ("primary-ray phase (k_beam bundle traversal + k_leafp leaf walk + k_primary fallback)" if s2["beams"] else
+                                    "k_primary (camera rays + closest-hit traversal)") + ", %.1f%% of the frame" % (100.0 * phases[0] / max(sum(phases), 1e-9)),
                          "bound": "fp32_issue", "achieved": p_ach, "peak": fp32_peak, "unit": "Gop/s (FMA=2)", "frac": p_ach / fp32_peak,
                          "traffic": ncu_traffic(args.workload, world), "peak_source": "lgb_measure_fp32_gops, live on this GPU",
                          "algorithmic_ops_per_launch": p_ops, "algorithmic_bytes_per_launch": p_bytes, "launch_ms": phases[0],

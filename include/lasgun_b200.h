@@ -175,6 +175,8 @@ typedef struct lgb_stats {
     float total_ms;                  /* device time incl. film copy back to the host */
     uint32_t kernel_launches;
     uint32_t stack_overflow;         /* 1 if a ray exceeded the 64-entry stack (bvh.rs:469) */
+    uint32_t beams;                  /* 1 if the primary rays went through pixel beams (LGB_OPT_BEAMS) */
+    uint32_t tie_retraces;           /* lazy reference tree: sample slots re-traced because of an exact-t tie (this call) */
 } lgb_stats;
 
 /* Device / context --------------------------------------------------------------------- */

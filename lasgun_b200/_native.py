@@ -79,7 +79,7 @@ class Stats(C.Structure):
                 ("shadow_rays_traced", C.c_uint64), ("shadow_occluded", C.c_uint64), ("shadow_cache_hits", C.c_uint64), ("exact_tests", C.c_uint64 * 3),
                 ("filter_tests", C.c_uint64 * 3), ("node_tests", C.c_uint64), ("primary_node_tests", C.c_uint64),
                 ("primary_exact_tests", C.c_uint64 * 3), ("primary_filter_tests", C.c_uint64 * 3), ("kernel_ms", C.c_float * 6), ("render_ms", C.c_float), ("total_ms", C.c_float),
-                ("kernel_launches", C.c_uint32), ("stack_overflow", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("stack_overflow", C.c_uint32), ("beams", C.c_uint32), ("tie_retraces", C.c_uint32)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n in ("exact_tests", "filter_tests", "primary_exact_tests", "primary_filter_tests", "kernel_ms") else getattr(self, n)) for n, _ in self._fields_}
@@ -327,6 +327,10 @@ class Context:
 
     def set_count_work(self, on: bool):
         self.check(lib().lgb_set_option(self.h, 1, 1 if on else 0))
+
+    def set_beams(self, mode: int):
+        """LGB_OPT_BEAMS: 1 on (whenever spp >= 4), 0 off, -1 automatic (the default)."""
+        self.check(lib().lgb_set_option(self.h, 2, int(mode)))
 
     def measure(self):
         L = lib()

@@ -911,6 +911,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));
     CU(c, cudaEventRecord(c->ev0, st));
     cudaEvent_t* pev = (stats && sync_stats && total) ? c->phase : nullptr;
+    uint32_t tie_slots = 0;
     const bool st_on = a.aov || c->count_work;
     if (s->lazy_fn && !s->dev.rank && total) {
         // no rank tables yet: trace the primary rays, and only if one met two primitives at bit-identical t fetch the
@@ -921,7 +922,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         CU(c, cudaStreamSynchronize(st));
         if (ties) {
             if (int rc = ensure_rank_tables(c, s)) return rc;
-            s->tie_retraces += ties;
+            s->tie_retraces += ties; tie_slots = ties;
             DevWork W2 = W;
             if (ties <= V.tie_cap) { W2.slot_list = V.tie_list; W2.n_list = ties; }
             else CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));          // too many to list: the whole frame again
@@ -945,7 +946,8 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         if (total) for (int k = 0; k < 6; k++) { float pm = 0.f; CU(c, cudaEventElapsedTime(&pm, c->phase[k], c->phase[k + 1])); stats->kernel_ms[k] = pm; }
         for (int k = 0; k < 3; k++) { stats->filter_tests[k] = hc.filter[k]; stats->exact_tests[k] = hc.exact[k]; }
         stats->stack_overflow = hc.stack_overflow;
-        stats->kernel_launches = total ? (render_fused(W.spp) ? 3 : 4) + s->dev.n_lights * (W.spp > 1 ? 3 : 1) : 0;
+        stats->beams = W.beams; stats->tie_retraces = tie_slots;
+        stats->kernel_launches = total ? (render_fused(W.spp) ? 3 : 4) + (W.beams ? 2 : 0) + s->dev.n_lights * (W.spp > 1 ? 3 : 1) : 0;
         float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         stats->render_ms = ms; stats->total_ms = ms;
     }

@@ -178,6 +178,36 @@ def test_device_built_bvh(native, gpu_ctx, monkeypatch, name):
     assert np.array_equal(film_dev, film_host)
 
 
+@pytest.mark.parametrize("name", ["mixed_16spp", "simple_9spp", "cornell_4spp", "coincident_4spp", "spheres_9spp_ragged"])
+def test_pixel_beams(native, oracle, gpu_ctx, name):
+    """LGB_OPT_BEAMS: the sample rays of a pixel share one bundle traversal (k_beam) and walk its leaf list (k_leafp), with a
+    per-ray fallback.  Ids, t, occlusion bits and film must be the oracle's -- and identical to the per-ray path."""
+    sc, (w, h) = {"mixed_16spp": lambda: scenes.mixed4k(mesh_n=64, nspheres=6000, res=(96, 54), supersampling=3),
+                  "simple_9spp": lambda: scenes.simple("b", 2, 96),
+                  "cornell_4spp": lambda: scenes.cornell((160, 90), 1),
+                  "coincident_4spp": lambda: scenes.coincident_planes(nspheres=3000, res=(96, 72), supersampling=1),
+                  "spheres_9spp_ragged": lambda: scenes.spheres1m(count=30000, res=77)[0:1] + ((77, 45),)}[name]()
+    if name == "spheres_9spp_ragged":
+        sc.camera.set_supersampling(2)
+    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+    try:
+        gpu_ctx.set_beams(1)
+        out = dev.capture_aov(w, h)
+        film_on, st_on = dev.capture(w, h)
+        gpu_ctx.set_beams(0)
+        film_off, st_off = dev.capture(w, h)
+    finally:
+        gpu_ctx.set_beams(-1)
+        dev.destroy()
+    assert np.array_equal(film_on, film_off) and np.array_equal(out["rgba"], film_on)
+    for k in ("primary_rays", "primary_hits", "shadow_rays", "shadow_rays_traced", "shadow_occluded"):
+        assert st_on[k] == st_off[k], k
+    ref = oracle.OracleScene(sc).capture(w, h, aov=True)
+    a = parity.aov_report(out, ref)
+    assert a["id_mismatch"] == 0 and a["t_bit_equal"] == a["t_compared"] and a["occl_diff"] == 0, a
+    assert np.array_equal(film_on, ref["rgba"])
+
+
 @pytest.mark.parametrize("case", ["no_ties", "ties_listed", "ties_whole_frame", "small_scene"])
 def test_lazy_reference_tree(native, oracle, gpu_ctx, monkeypatch, case):
     """Lazy reference tree (lasgun_b200.h): the reference BVH is not built unless a closest-hit ray meets two primitives at
