@@ -166,12 +166,13 @@ def primary_kernel_work(st):
 
 
 def ncu_traffic(workload, world):
-    """dram read + write bytes of one k_primary launch from the committed `ncu --set full` capture (or None)."""
+    """dram read + write bytes of the primary-ray phase of one frame (k_beam + k_leafp + k_primary fallback) from the committed
+    `ncu --set full` capture (or None)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)
         e = t.get(workload)
-        return (e["k_primary_dram_bytes"] / world) if e and world == 1 else None
+        return (e["primary_phase_dram_bytes"] / world) if e and world == 1 else None
     except Exception:
         return None
 
@@ -209,10 +210,20 @@ def run_gpu(args):
     def step():
         multi.capture_distributed(dev, w, h, film, rank, world, stream)   # disjoint tiles: SUM reduce == gather, over NVLink
 
-    # one counted frame: ray counts + work counters (not timed)
+    # one counted frame: ray counts + work counters (not timed).  The algorithmic work of SURVEY 8d is the PER-RAY walk of the
+    # device BVH, so it is counted with the pixel beams off; the timed frames (beams automatic) share the interior-node tests
+    # of a pixel's rays and execute fewer (roofline.executed_ops_per_launch).
     ctx.set_count_work(True)
+    ctx.set_beams(0)
     st = dev.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream, want_stats=True)
+    ctx.set_beams(-1)
+    st_exec = dev.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream, want_stats=True)
     ctx.set_count_work(False)
+    cnt_e = torch.tensor([st_exec["primary_rays"], st_exec["primary_node_tests"]] + st_exec["primary_filter_tests"] + st_exec["primary_exact_tests"], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cnt_e)
+    te = cnt_e.tolist()
+    frame_exec = {"primary_rays": te[0], "primary_node_tests": te[1], "primary_filter_tests": te[2:5], "primary_exact_tests": te[5:8]}
     cnt = torch.tensor([st["primary_rays"], st["primary_hits"], st["shadow_rays_traced"], st["node_tests"]] + st["filter_tests"] + st["exact_tests"]
                        + [st["primary_node_tests"]] + st["primary_filter_tests"] + st["primary_exact_tests"] + [st["shadow_cache_hits"]],
                        dtype=torch.int64, device="cuda")
@@ -310,6 +321,11 @@ def run_gpu(args):
         fp32_peak = 2.0 * ceil["fp32_ffma_glanes"]                 # Gop/s with FMA = 2, measured live on this GPU
         ach = ops / (kernel_ms * 1e-3) / 1e9 / world                # per GPU, whole frame
         p_ops, p_bytes = primary_kernel_work(frame)
+        e_ops, e_bytes = primary_kernel_work(frame_exec)
+        sh_ops, sh_bytes = traversal_work(frame["node_tests"] - frame["primary_node_tests"],
+                                          [a - b for a, b in zip(frame["filter_tests"], frame["primary_filter_tests"])],
+                                          [a - b for a, b in zip(frame["exact_tests"], frame["primary_exact_tests"])])
+        sh_ms = phases[2] + phases[3]
         l1_peak = 128.0 * torch.cuda.get_device_properties(local).multi_processor_count * float(clocks["sm_mhz"] or peaks["sm_max_mhz"]) * 1e6 / 1e9
         p_ach = p_ops / (phases[0] * 1e-3) / 1e9 / world           # dominant kernel alone
         l2_ach = byts / (kernel_ms * 1e-3) / 1e9 / world
@@ -335,6 +351,11 @@ def run_gpu(args):
                          "bound": "fp32_issue", "achieved": p_ach, "peak": fp32_peak, "unit": "Gop/s (FMA=2)", "frac": p_ach / fp32_peak,
                          "traffic": ncu_traffic(args.workload, world), "peak_source": "lgb_measure_fp32_gops, live on this GPU",
                          "algorithmic_ops_per_launch": p_ops, "algorithmic_bytes_per_launch": p_bytes, "launch_ms": phases[0],
+                         "algorithmic_definition": "per-ray walk of the device BVH (SURVEY 8d), counted on a frame with LGB_OPT_BEAMS=0",
+                         "executed_ops_per_launch": e_ops, "executed_bytes_per_launch": e_bytes,
+                         "shadow_phase": {"kernels": "k_shadow (anchor rays) + k_pretest + k_shadow (rest)", "launch_ms": sh_ms,
+                                          "algorithmic_ops": sh_ops, "achieved": sh_ops / (sh_ms * 1e-3) / 1e9 / world,
+                                          "frac": sh_ops / (sh_ms * 1e-3) / 1e9 / world / fp32_peak},
                          # node / primitive fetches are L1 hits (96 %): the ceiling that binds is the L1 data pipe, 128 B/clk/SM
                          "l1_fetch": {"achieved_gbs": p_bytes / (phases[0] * 1e-3) / 1e9 / world, "peak_gbs": l1_peak,
                                       "frac": p_bytes / (phases[0] * 1e-3) / 1e9 / world / l1_peak,
