@@ -178,6 +178,46 @@ def test_device_built_bvh(native, gpu_ctx, monkeypatch, name):
     assert np.array_equal(film_dev, film_host)
 
 
+def _variant(name):
+    """Corners of the configuration space the five configs do not reach."""
+    if name == "orthographic_9spp":                      # camera.rs:126-128, 168-173: origins move across the image plane
+        sc, _ = scenes.mixed4k(mesh_n=48, nspheres=3000, res=(96, 54), supersampling=2)
+        cam = sc.set_orthographic_camera(700.0)
+        cam.look_at([40.0, 90.0, 520.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0]); cam.set_supersampling(2)
+        return sc, (96, 54)
+    if name == "spp_289":                                # more samples than a block holds: radiance buffer + k_resolve
+        sc, _ = scenes.simple("b", 0, 16)
+        sc.camera.set_supersampling(16)
+        return sc, (20, 12)
+    if name == "lights_6":
+        sc, _ = scenes.spheres1m(count=4000, res=64)
+        for i in range(3):
+            sc.add_point_light([300.0 * (i - 1), -700.0, 900.0 - 200.0 * i], [0.2, 0.3, 0.25], [1.0, 0.0, 0.0])
+        sc.camera.set_supersampling(1)
+        return sc, (80, 64)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("beams", [0, 1])
+@pytest.mark.parametrize("name", ["orthographic_9spp", "spp_289", "lights_6"])
+def test_variants(native, oracle, gpu_ctx, name, beams):
+    sc, (w, h) = _variant(name)
+    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+    try:
+        gpu_ctx.set_beams(beams)
+        out = dev.capture_aov(w, h)
+        rgba, st = dev.capture(w, h)
+    finally:
+        gpu_ctx.set_beams(-1)
+        dev.destroy()
+    ref = oracle.OracleScene(sc).capture(w, h, aov=True)
+    a = parity.aov_report(out, ref)
+    assert a["id_mismatch"] == 0 and a["t_bit_equal"] == a["t_compared"] and a["occl_diff"] == 0, a
+    f = parity.film_report(rgba, ref["rgba"])
+    assert f["alpha_equal"] and f["within_1_frac"] >= 0.999 and f["identical_frac"] >= 0.999, f
+    assert np.array_equal(rgba, out["rgba"]) and st["beams"] == (1 if beams and sc.camera.num_samples() >= 4 else 0)
+
+
 @pytest.mark.parametrize("name", ["mixed_16spp", "simple_9spp", "cornell_4spp", "coincident_4spp", "spheres_9spp_ragged"])
 def test_pixel_beams(native, oracle, gpu_ctx, name):
     """LGB_OPT_BEAMS: the sample rays of a pixel share one bundle traversal (k_beam) and walk its leaf list (k_leafp), with a
