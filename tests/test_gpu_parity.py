@@ -178,6 +178,23 @@ def test_device_built_bvh(native, gpu_ctx, monkeypatch, name):
     assert np.array_equal(film_dev, film_host)
 
 
+def test_golden_films(native, gpu_ctx):
+    """The committed oracle films of tests/golden/films.npz (a small version of every config + two nested-group scenes): the device
+    film must equal them byte for byte -- no oracle is run here."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(here, "golden", "films.npz"))
+    for name, mk in mg.CASES.items():
+        sc, (w, h) = mk()
+        dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+        rgba, _ = dev.capture(w, h)
+        dev.destroy()
+        assert np.array_equal(rgba, gold[name]), name
+
+
 def _variant(name):
     """Corners of the configuration space the five configs do not reach."""
     if name == "orthographic_9spp":                      # camera.rs:126-128, 168-173: origins move across the image plane

@@ -86,3 +86,18 @@ def test_quantisation_and_camera_shapes(oracle):
         assert (np.delete(sub, idx, axis=0) == 0).all()
         parts.reshape(-1, 4)[idx] = sub[idx]
     assert np.array_equal(parts, full)
+
+
+def test_oracle_reproduces_golden_films(oracle):
+    """tests/golden/films.npz (made by tests/golden/make_golden.py) pins the oracle's own output for a small version of every
+    config: an edit of the oracle that changes a single byte of any film fails here."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(here, "golden", "films.npz"))
+    assert sorted(gold.files) == sorted(mg.CASES)
+    for name, mk in mg.CASES.items():
+        sc, (w, h) = mk()
+        assert np.array_equal(oracle.OracleScene(sc).capture(w, h)["rgba"], gold[name]), name
