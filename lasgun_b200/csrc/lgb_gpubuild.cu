@@ -13,6 +13,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
+#include <vector>
 
 #include "lgb_build.hpp"
 #include "lgb_gpubuild.cuh"
@@ -111,6 +113,45 @@ __global__ void k_bin(const GItem* items, const uint32_t* node_of, uint32_t n, c
         agg_min(b + 0, fkey(it.lo[0]), peers, leader); agg_min(b + 1, fkey(it.lo[1]), peers, leader); agg_min(b + 2, fkey(it.lo[2]), peers, leader);
         agg_max(b + 3, fkey(it.hi[0]), peers, leader); agg_max(b + 4, fkey(it.hi[1]), peers, leader); agg_max(b + 5, fkey(it.hi[2]), peers, leader);
         if (leader) atomicAdd(b + 6, (uint32_t)__popc(peers));
+    }
+}
+
+// Top of the tree: a handful of nodes own all the items, so k_bin's global atomics all land on the same few hundred words.
+// Here every block bins into a private copy in shared memory (slots 0 .. kTopNodes-1 of the bin pool) and merges it once.
+constexpr int kTopNodes = 32;            // 32 x 336 words = 42 KB of shared memory
+__global__ void __launch_bounds__(256) k_bin_top(const GItem* items, const uint32_t* node_of, uint32_t n, const Work* work, uint32_t* bins) {
+    __shared__ uint32_t sb[kTopNodes * kBinWords];
+    for (int i = threadIdx.x; i < kTopNodes * kBinWords; i += blockDim.x) sb[i] = (i % 7) < 3 ? kKeyMax : 0u;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {       // block-uniform trip count
+        const uint32_t i = i0 + threadIdx.x;
+        uint32_t slot = kInvalid;
+        GItem it; const Work* W = nullptr;
+        if (i < n) {
+            const uint32_t w = node_of[i];
+            if (w != kInvalid) { W = &work[w]; slot = W->bins; if (slot != kInvalid) it = items[i]; }
+        }
+        for (int a = 0; a < 3; a++) {
+            uint32_t target = kInvalid;
+            if (slot != kInvalid) target = slot * (3 * NB) + a * NB + bin_of(centroid(it, a), W->cmin[a], W->scale[a]);
+            const unsigned act = __ballot_sync(0xFFFFFFFFu, target != kInvalid);
+            if (target == kInvalid) continue;
+            const unsigned peers = __match_any_sync(act, target);
+            const bool leader = lane == (unsigned)(__ffs(peers) - 1);
+            uint32_t* b = sb + (size_t)target * 7;
+            agg_min(b + 0, fkey(it.lo[0]), peers, leader); agg_min(b + 1, fkey(it.lo[1]), peers, leader); agg_min(b + 2, fkey(it.lo[2]), peers, leader);
+            agg_max(b + 3, fkey(it.hi[0]), peers, leader); agg_max(b + 4, fkey(it.hi[1]), peers, leader); agg_max(b + 5, fkey(it.hi[2]), peers, leader);
+            if (leader) atomicAdd(b + 6, (uint32_t)__popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kTopNodes * kBinWords; i += blockDim.x) {
+        const uint32_t v = sb[i];
+        const int f = i % 7;
+        if (f < 3) { if (v != kKeyMax) atomicMin(bins + i, v); }
+        else if (f < 6) { if (v != 0u) atomicMax(bins + i, v); }
+        else if (v) atomicAdd(bins + i, v);
     }
 }
 
@@ -399,13 +440,19 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
     if ((e = check("k_root", 0)) != cudaSuccess) return e;
     uint32_t count = 1, levels = 0, node_count = 1, max_depth = 0;
     int cur = 0;
+    const bool timing = std::getenv("LGB_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_start = now();
+    std::vector<double> level_ms; std::vector<uint32_t> level_nodes;
     while (count) {
+        auto t_level = now();
         const unsigned wb = (count + 127) / 128;
         if ((e = cudaMemsetAsync(&ctl->next_count, 0, 4, st)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(&ctl->bin_slots, 0, 4, st)) != cudaSuccess) return e;
         k_prep<<<wb, 128, 0, st>>>(work[cur], count, bins, ctl);
         if ((e = check("k_prep", levels)) != cudaSuccess) return e;
-        k_bin<<<ib, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], bins);
+        if (count <= (uint32_t)kTopNodes) k_bin_top<<<296, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], bins);     // every bin slot < count <= kTopNodes
+        else k_bin<<<ib, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], bins);
         if ((e = check("k_bin", levels)) != cudaSuccess) return e;
         k_split<<<wb, 128, 0, st>>>(work[cur], count, bins, buf[cur], nodes_out, work[cur ^ 1], ctl, n + 2);
         if ((e = check("k_split", levels)) != cudaSuccess) return e;
@@ -415,6 +462,7 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
         Ctl h;
         if ((e = cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        if (timing) { level_ms.push_back(std::chrono::duration<double, std::milli>(now() - t_level).count()); level_nodes.push_back(count); }
         count = h.next_count; node_count = h.node_count; max_depth = h.max_depth;
         cur ^= 1;
         if (++levels > 96) return cudaErrorUnknown;         // depth guard (splits by position halve every node from depth 40 on)
@@ -429,6 +477,11 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
     k_patch_leaves<<<(node_count + 255) / 256, 256, 0, st>>>(nodes_out, node_count, d_typepos);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;      // h_tp is on this stack frame
+    if (timing) {
+        std::fprintf(stderr, "[gpu_build_sah] %u items, %u levels, %.2f ms total; per level (nodes: ms):", n, levels, std::chrono::duration<double, std::milli>(now() - t_start).count());
+        for (size_t i = 0; i < level_ms.size(); i++) std::fprintf(stderr, " %u:%.2f", level_nodes[i], level_ms[i]);
+        std::fprintf(stderr, "\n");
+    }
     for (int t = 0; t < 3; t++) typepos_out[t] = typepos[t];
     info->n_nodes = node_count; info->max_depth = max_depth; info->levels = levels;
     return cudaSuccess;
