@@ -251,12 +251,15 @@ def test_pixel_beams(native, oracle, gpu_ctx, name):
         gpu_ctx.set_beams(1)
         out = dev.capture_aov(w, h)
         film_on, st_on = dev.capture(w, h)
+        sub_on = np.zeros((h, w, 4), np.uint8); dev.capture_subset(1, 3, w, h, sub_on)        # capture_subset through the beams too
         gpu_ctx.set_beams(0)
         film_off, st_off = dev.capture(w, h)
+        sub_off = np.zeros((h, w, 4), np.uint8); dev.capture_subset(1, 3, w, h, sub_off)
     finally:
         gpu_ctx.set_beams(-1)
         dev.destroy()
     assert np.array_equal(film_on, film_off) and np.array_equal(out["rgba"], film_on)
+    assert np.array_equal(sub_on, sub_off) and np.array_equal(sub_on.reshape(-1, 4)[1::3], film_on.reshape(-1, 4)[1::3]) and not sub_on.reshape(-1, 4)[0::3].any()
     for k in ("primary_rays", "primary_hits", "shadow_rays", "shadow_rays_traced", "shadow_occluded"):
         assert st_on[k] == st_off[k], k
     ref = oracle.OracleScene(sc).capture(w, h, aov=True)
