@@ -207,8 +207,12 @@ def run_gpu(args):
 
     from lasgun_b200 import multi
 
+    # N > 1: rank 0 owns the film, the other ranks' kernels store their tiles into it over NVLink (multi.SharedFilm);
+    # --gather nccl keeps per-rank films and SUM-reduces them instead
+    shared = multi.SharedFilm(ctx, w, h, rank, world, N) if (world > 1 and args.gather == "p2p") else None
+
     def step():
-        multi.capture_distributed(dev, w, h, film, rank, world, stream)   # disjoint tiles: SUM reduce == gather, over NVLink
+        multi.capture_distributed(dev, w, h, film, rank, world, stream, shared=shared)
 
     # one counted frame: ray counts + work counters (not timed).  The algorithmic work of SURVEY 8d is the PER-RAY walk of the
     # device BVH, so it is counted with the pixel beams off; the timed frames (beams automatic) share the interior-node tests
@@ -258,6 +262,13 @@ def run_gpu(args):
     ms_per_step = float(total_ms.item()) / args.steps
     value = rays_frame / (ms_per_step * 1e-3) / 1e6
 
+    gather_same = None
+    if shared is not None:                       # not timed: the peer-stored film against the NCCL-gathered one, every byte
+        multi.capture_distributed(dev, w, h, film, rank, world, stream)
+        torch.cuda.synchronize()
+        if rank == 0:
+            gather_same = bool(torch.equal(film, shared.tensor))
+
     # render-kernel time alone (CUDA events inside the library, on its launch stream), a few frames
     phase_ms = []
     for _ in range(max(3, args.steps)):
@@ -294,11 +305,9 @@ def run_gpu(args):
                 f = N.FlatScene(hscene_host); tf[0] = time.perf_counter(); return f
             dev_i = multi.replicate_scene(ctx, build_flat, rank, world, N)
             t1 = tf[0]; t2 = time.perf_counter()
-            film.zero_()
-            dev_i.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream)
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+            out = multi.capture_distributed(dev_i, w, h, film, rank, world, stream, shared=shared)
             if rank == 0:
-                host_film_t.copy_(film, non_blocking=True)
+                host_film_t.copy_(out, non_blocking=True)
             torch.cuda.synchronize()
             dev_i.destroy()
         t3 = time.perf_counter()
@@ -337,6 +346,8 @@ def run_gpu(args):
             "config": {"workload": args.workload, "film": [w, h], "spp": spp, "lights": nl, "triangles": int(flat.desc.n_triangles),
                        "spheres": int(flat.desc.n_spheres), "cuboids": int(flat.desc.n_cuboids), "bvh_nodes": int(flat.desc.n_nodes),
                        "device_bvh_nodes": int(dev.node_count) if hasattr(dev, "node_count") else None, "parallelism": f"tiles{world}",
+                       "film_gather": None if world == 1 else ("peer stores into rank 0's film (CUDA IPC over NVLink), identical to the NCCL-reduced film: %s" % gather_same
+                                                               if shared is not None else "NCCL reduce(SUM) of disjoint tiles"),
                        "l2_policy": "per-frame working set (radiance buffer %.0f MB + scene %.0f MB) exceeds the 126 MB L2" % (frame["primary_rays"] * 24 / 1e6 / world, scene_bytes / 1e6)},
             "ms_per_frame": ms_per_step, "kernel_ms_per_frame": kernel_ms, "rays_per_frame": rays_frame,
             "rays_traced_per_frame": frame["primary_rays"] + frame["shadow_rays_traced"],
@@ -385,6 +396,13 @@ def run_gpu(args):
                                     "bvh_build_ms": osc.build_ms, "device_film_identical_frac_at_sample": float(same)}
         print(json.dumps(line))
     dev.destroy()
+    if shared is not None:
+        torch.cuda.synchronize(); dist.barrier()
+        if rank != 0:
+            shared.close()
+        dist.barrier()
+        if rank == 0:
+            shared.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -395,6 +413,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1 film gather: peer stores into rank 0's film, or NCCL reduce")
     ap.add_argument("--workload", default="mixed4k", choices=sorted(scenes.CONFIGS))
     ap.add_argument("--small", action="store_true", help="tiny variant of mixed4k (CPU smoke of the bench logic)")
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -179,6 +179,15 @@ typedef struct lgb_stats {
     uint32_t tie_retraces;           /* lazy reference tree: sample slots re-traced because of an exact-t tie (this call) */
 } lgb_stats;
 
+/* Shared film (multi-GPU, one process per GPU): rank 0 allocates the film and hands the 64-byte handle to the other
+ * processes; they map it and pass the mapped pointer as `d_film` of lgb_capture_device, so their resolve stage stores
+ * its uchar4 pixels straight into rank 0's HBM over NVLink -- the gather IS the kernel's stores, there is no collective
+ * on the data path.  The tiles of the ranks are disjoint; a barrier after the captures completes the frame. */
+#define LGB_IPC_HANDLE_BYTES 64
+int lgb_film_alloc_shared(lgb_ctx* ctx, uint64_t bytes, void** d_film, uint8_t handle_out[LGB_IPC_HANDLE_BYTES]);
+int lgb_film_open_shared(lgb_ctx* ctx, const uint8_t handle[LGB_IPC_HANDLE_BYTES], void** d_film);
+int lgb_film_release_shared(lgb_ctx* ctx, void* d_film, int owner);   /* owner != 0: cudaFree, else cudaIpcCloseMemHandle */
+
 /* Device / context --------------------------------------------------------------------- */
 int lgb_device_count(void);
 int lgb_init(int device, lgb_ctx** out);

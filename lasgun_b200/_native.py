@@ -21,7 +21,7 @@ LGB_LEAF_FLAG = 0x80000000
 # Every symbol include/lasgun_b200.h declares (checked by tests/test_abi.py without a GPU).
 ABI_SYMBOLS = [
     "lgb_build_probe", "lgb_device_count", "lgb_init", "lgb_set_option", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
-    "lgb_scene_destroy", "lgb_scene_layout_bytes", "lgb_scene_export", "lgb_scene_import", "lgb_scene_verify", "lgb_scene_device_bytes", "lgb_scene_build_ms", "lgb_scene_node_count", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
+    "lgb_film_alloc_shared", "lgb_film_open_shared", "lgb_film_release_shared", "lgb_scene_destroy", "lgb_scene_layout_bytes", "lgb_scene_export", "lgb_scene_import", "lgb_scene_verify", "lgb_scene_device_bytes", "lgb_scene_build_ms", "lgb_scene_node_count", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
     "lgb_capture_device", "lgb_trace_rays", "lgb_measure_l2_read_gbs", "lgb_measure_fp32_gops", "lgb_measure_fp64_gops",
 ]
 
@@ -101,6 +101,9 @@ def lib():
         "lgb_build_probe": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(BuildInfo)]),
         "lgb_last_error": (C.c_char_p, [vp]), "lgb_status_string": (C.c_char_p, [C.c_int]),
         "lgb_scene_create": (C.c_int, [vp, C.POINTER(SceneDesc), C.POINTER(vp)]), "lgb_scene_destroy": (None, [vp]),
+        "lgb_film_alloc_shared": (C.c_int, [vp, C.c_uint64, C.POINTER(C.c_void_p), u8p]),
+        "lgb_film_open_shared": (C.c_int, [vp, u8p, C.POINTER(C.c_void_p)]),
+        "lgb_film_release_shared": (C.c_int, [vp, vp, C.c_int]),
         "lgb_scene_layout_bytes": (C.c_uint64, []),
         "lgb_scene_export": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
         "lgb_scene_import": (C.c_int, [vp, vp, C.c_uint64, vp, C.POINTER(C.c_void_p)]),

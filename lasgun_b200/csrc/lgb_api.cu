@@ -145,6 +145,34 @@ int lgb_init(int device, lgb_ctx** out) {
     return LGB_OK;
 }
 
+int lgb_film_alloc_shared(lgb_ctx* c, uint64_t bytes, void** d_film, uint8_t handle_out[LGB_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == LGB_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!c || !bytes || !d_film || !handle_out) return fail(c, LGB_ERR_INVALID, "lgb_film_alloc_shared: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    void* p = nullptr;
+    CU(c, cudaMalloc(&p, bytes));                       // IPC handles need a whole cudaMalloc allocation (no pool, no sub-allocation)
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(c, e, "cudaIpcGetMemHandle"); }
+    std::memcpy(handle_out, &h, sizeof h);
+    *d_film = p;
+    return LGB_OK;
+}
+int lgb_film_open_shared(lgb_ctx* c, const uint8_t handle[LGB_IPC_HANDLE_BYTES], void** d_film) {
+    if (!c || !handle || !d_film) return fail(c, LGB_ERR_INVALID, "lgb_film_open_shared: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h; std::memcpy(&h, handle, sizeof h);
+    CU(c, cudaIpcOpenMemHandle(d_film, h, cudaIpcMemLazyEnablePeerAccess));
+    return LGB_OK;
+}
+int lgb_film_release_shared(lgb_ctx* c, void* d_film, int owner) {
+    if (!c || !d_film) return LGB_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (owner) CU(c, cudaFree(d_film)); else CU(c, cudaIpcCloseMemHandle(d_film));
+    return LGB_OK;
+}
+
 int lgb_set_option(lgb_ctx* c, int option, int value) {
     if (!c) return LGB_ERR_INVALID;
     if (option == LGB_OPT_COUNT_WORK) { c->count_work = value != 0; return LGB_OK; }

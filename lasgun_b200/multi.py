@@ -1,7 +1,11 @@
 """Multi-GPU frame sharding: scene + BVH replicated on every GPU, the film split into
 32x32 macro tiles dealt round-robin along anti-diagonals (owner = (mx + my) % ranks, lgb_api.cu
-build_tile_list), and one exchange step — the film to rank 0.  Tiles are disjoint, so a SUM reduction of
-the zero-initialised per-rank films IS the gather (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+build_tile_list), and one exchange step — the film to rank 0.
+
+On GPUs the exchange is fused into the render: rank 0 owns the film (SharedFilm), the other ranks map it through a CUDA IPC
+handle and their resolve stage stores its pixels straight into rank 0's HBM over NVLink; a barrier ends the frame.  The
+NCCL form (a SUM reduction of zero-initialised per-rank films: tiles are disjoint, so SUM is the gather) remains for the
+gloo CPU tests and as a fallback."""
 from __future__ import annotations
 
 import numpy as np
@@ -56,8 +60,47 @@ def replicate_scene(ctx, flat_builder, rank: int, ranks: int, native):
     return native.DeviceScene.adopt(ctx, layout, arena.data_ptr(), spp, keep=arena)
 
 
-def capture_distributed(dev_scene, w: int, h: int, film, rank: int, ranks: int, stream: int = 0):
-    """One frame across `ranks` GPUs: render this rank's tiles into `film` (CUDA uint8 tensor), gather to rank 0."""
+class SharedFilm:
+    """The frame's film in rank 0's HBM, mapped by every other rank (lgb_film_alloc_shared / lgb_film_open_shared).
+    Collective: every rank constructs it.  `tensor` (rank 0 only) is a zero-copy (h, w, 4) uint8 view."""
+
+    def __init__(self, ctx, w: int, h: int, rank: int, ranks: int, native):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.rank, self.native, self.w, self.h = ctx, rank, native, w, h
+        L = native.lib()
+        handle = (C.c_uint8 * 64)()
+        ptr = C.c_void_p()
+        if rank == 0:
+            ctx.check(L.lgb_film_alloc_shared(ctx.h, w * h * 4, C.byref(ptr), handle))
+        t = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device="cuda")
+        if ranks > 1:
+            dist.broadcast(t, src=0)
+        if rank != 0:
+            hb = (C.c_uint8 * 64)(*t.cpu().tolist())
+            ctx.check(L.lgb_film_open_shared(ctx.h, hb, C.byref(ptr)))
+        self.ptr = ptr.value
+        self.tensor = torch.as_tensor(_DevicePointer(self.ptr, w * h * 4), device="cuda").view(h, w, 4) if rank == 0 else None
+        self._sync = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def close(self):
+        if self.ptr:
+            self.ctx.check(self.native.lib().lgb_film_release_shared(self.ctx.h, self.native.C.c_void_p(self.ptr), 1 if self.rank == 0 else 0))
+            self.ptr = None
+
+
+def capture_distributed(dev_scene, w: int, h: int, film, rank: int, ranks: int, stream: int = 0, shared: SharedFilm | None = None):
+    """One frame across `ranks` GPUs.  With `shared`: every rank's kernels store their tiles into rank 0's film over NVLink
+    and a stream-ordered barrier completes the frame (no collective moves pixels).  Otherwise: render this rank's tiles into
+    `film` (CUDA uint8 tensor) and SUM-reduce to rank 0."""
+    if shared is not None:
+        import torch.distributed as dist
+        dev_scene.capture_device(w, h, shared.ptr, rank=rank, ranks=ranks, stream=stream)
+        if ranks > 1:
+            dist.all_reduce(shared._sync)            # on the current stream, i.e. after this rank's stores: the frame is whole on return
+        return shared.tensor
     if ranks > 1:
         film.zero_()
     dev_scene.capture_device(w, h, film.data_ptr(), rank=rank, ranks=ranks, stream=stream)
