@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LGB_ABI_VERSION 3
+#define LGB_ABI_VERSION 4
 
 typedef enum lgb_status {
     LGB_OK = 0,
@@ -85,11 +85,18 @@ typedef struct lgb_instance {
     double m[16], minv[16];
 } lgb_instance;
 
-/* Material after `Material::scattering` resolution (material/{plastic,matte}.rs).
- * kind 0 = matte with sigma == 0 (Lambertian only), kind 1 = plastic. */
+/* `Material` (material/mod.rs:4-46), one record for the five variants:
+ *   LGB_MAT_MATTE    kd, roughness = sigma in degrees, already clamped to [0, 90] (matte.rs:15); sigma == 0: Lambertian only
+ *   LGB_MAT_PLASTIC  kd, ks, roughness (plastic.rs)
+ *   LGB_MAT_METAL    kd = eta, ks = k, roughness = u_roughness, roughness_v = v_roughness (metal.rs)
+ *   LGB_MAT_GLASS    kd = kr, ks = kt, roughness = eta (glass.rs; Material::glass passes no microfacet roughness, mod.rs:36-41)
+ *   LGB_MAT_MIRROR   kd = kr (mirror.rs)
+ * Glass and mirror scatter through the Whitted recursion of integrate.rs:69-132, to depth lgb_scene_desc.recursion. */
+enum { LGB_MAT_MATTE = 0, LGB_MAT_PLASTIC = 1, LGB_MAT_METAL = 2, LGB_MAT_GLASS = 3, LGB_MAT_MIRROR = 4 };
 typedef struct lgb_material {
     double kd[3]; double roughness;
-    double ks[3]; uint32_t kind; uint32_t reserved;
+    double ks[3]; double roughness_v;
+    uint32_t kind; uint32_t reserved;
 } lgb_material;
 
 typedef struct lgb_light {           /* PointLight, src/light/point.rs:14-18 */
@@ -140,6 +147,8 @@ typedef struct lgb_scene_desc {
     lgb_camera camera;
     double ambient[3];                                       /* scene.rs:22 */
     double bg_inner[3], bg_outer[3], bg_scale;               /* material/background.rs:6-10 */
+    uint32_t recursion;                                      /* scene.recursion (scene.rs:60, default 3): Whitted depth, at most 12 */
+    uint32_t reserved;
     lgb_reference_tree_fn reference_tree;                    /* lazy mode (nodes == NULL), else NULL */
     void* reference_tree_user;
     double bounds_lo[3], bounds_hi[3];                       /* lazy mode: world box of all primitives */
@@ -177,6 +186,7 @@ typedef struct lgb_stats {
     uint32_t stack_overflow;         /* 1 if a ray exceeded the 64-entry stack (bvh.rs:469) */
     uint32_t beams;                  /* 1 if the primary rays went through pixel beams (LGB_OPT_BEAMS) */
     uint32_t tie_retraces;           /* lazy reference tree: sample slots re-traced because of an exact-t tie (this call) */
+    uint64_t secondary_rays;         /* rays below specular hits (reflected, transmitted and their shadow rays), integrate.rs:69-132 */
 } lgb_stats;
 
 /* Shared film (multi-GPU, one process per GPU): rank 0 allocates the film and hands the 64-byte handle to the other

@@ -42,10 +42,14 @@ struct Material {                      // material/mod.rs:4-46
     enum Kind : int { Matte = 0, Plastic = 1, Metal = 2, Glass = 3, Mirror = 4 };
     int kind = Matte;
     double kd[3] = {0.5, 0.5, 0.5}, ks[3] = {0, 0, 0};
-    double roughness = 0.0;            // matte: sigma
+    double roughness = 0.0;            // matte: sigma; metal: u_roughness; glass: eta
+    double roughness_v = 0.0;          // metal: v_roughness
     static Material default_() { return Material{}; }
     static Material matte(const double kd[3], double sigma);
     static Material plastic(const double kd[3], const double ks[3], double roughness);
+    static Material metal(const double eta[3], const double k[3], double u_roughness, double v_roughness);   // eta in kd, k in ks
+    static Material glass(const double kr[3], const double kt[3], double eta);                               // kr in kd, kt in ks
+    static Material mirror(const double kr[3]);                                                              // kr in kd
 };
 
 struct ObjData {                       // what the `obj` crate yields for one file
@@ -156,6 +160,7 @@ struct FlatScene {
     std::vector<lgb_light> lights;
     lgb_camera camera{};
     double ambient[3], bg_inner[3], bg_outer[3], bg_scale;
+    uint32_t recursion = 3;
     uint32_t flags = 0;
     uint32_t prim_count = 0;           // canonical primitive ids are 0 .. prim_count-1
     // Per BVH level (pre-order of construction): the reference's own arrays, for builder parity tests.

@@ -61,6 +61,7 @@ class SceneDesc(C.Structure):
         ("lights", C.c_void_p), ("n_lights", C.c_uint64),
         ("camera", CameraDesc),
         ("ambient", C.c_double * 3), ("bg_inner", C.c_double * 3), ("bg_outer", C.c_double * 3), ("bg_scale", C.c_double),
+        ("recursion", C.c_uint32), ("reserved", C.c_uint32),
         ("reference_tree", C.c_void_p), ("reference_tree_user", C.c_void_p), ("bounds_lo", C.c_double * 3), ("bounds_hi", C.c_double * 3),
     ]
 
@@ -79,7 +80,7 @@ class Stats(C.Structure):
                 ("shadow_rays_traced", C.c_uint64), ("shadow_occluded", C.c_uint64), ("shadow_cache_hits", C.c_uint64), ("exact_tests", C.c_uint64 * 3),
                 ("filter_tests", C.c_uint64 * 3), ("node_tests", C.c_uint64), ("primary_node_tests", C.c_uint64),
                 ("primary_exact_tests", C.c_uint64 * 3), ("primary_filter_tests", C.c_uint64 * 3), ("kernel_ms", C.c_float * 6), ("render_ms", C.c_float), ("total_ms", C.c_float),
-                ("kernel_launches", C.c_uint32), ("stack_overflow", C.c_uint32), ("beams", C.c_uint32), ("tie_retraces", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("stack_overflow", C.c_uint32), ("beams", C.c_uint32), ("tie_retraces", C.c_uint32), ("secondary_rays", C.c_uint64)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n in ("exact_tests", "filter_tests", "primary_exact_tests", "primary_filter_tests", "kernel_ms") else getattr(self, n)) for n, _ in self._fields_}
@@ -125,11 +126,12 @@ def lib():
         "lgh_set_mesh_smoothing": (None, [vp, C.c_int]), "lgh_add_point_light": (None, [vp, dp, dp, dp]),
         "lgh_add_mesh": (C.c_int, [vp, fp, C.c_uint64, u32p, C.c_uint64, fp, C.c_uint64, u32p, C.POINTER(C.c_int64)]),
         "lgh_agg_new": (C.c_int, [vp]),
-        "lgh_agg_add_sphere": (None, [vp, C.c_int, dp, C.c_double, C.c_int, dp, dp, C.c_double]),
-        "lgh_agg_add_spheres": (None, [vp, C.c_int, C.c_uint64, dp, dp, C.c_int, ip, dp, dp, dp, ip]),
-        "lgh_agg_add_cube": (None, [vp, C.c_int, dp, C.c_double, C.c_int, dp, dp, C.c_double]),
-        "lgh_agg_add_box": (None, [vp, C.c_int, dp, dp, C.c_int, dp, dp, C.c_double]),
-        "lgh_agg_add_mesh": (None, [vp, C.c_int, C.c_int64, C.c_int, C.c_int, dp, dp, C.c_double]),
+        "lgh_agg_add_sphere": (None, [vp, C.c_int, dp, C.c_double, C.c_int, dp, dp, C.c_double, C.c_double]),
+        "lgh_agg_add_spheres": (None, [vp, C.c_int, C.c_uint64, dp, dp, C.c_int, ip, dp, dp, dp, dp, ip]),
+        "lgh_agg_add_cube": (None, [vp, C.c_int, dp, C.c_double, C.c_int, dp, dp, C.c_double, C.c_double]),
+        "lgh_agg_add_box": (None, [vp, C.c_int, dp, dp, C.c_int, dp, dp, C.c_double, C.c_double]),
+        "lgh_agg_add_mesh": (None, [vp, C.c_int, C.c_int64, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double]),
+        "lgh_set_max_recursion_depth": (None, [vp, C.c_uint32]),
         "lgh_agg_add_group": (None, [vp, C.c_int, C.c_int]), "lgh_agg_swap_backface": (None, [vp, C.c_int]),
         "lgh_agg_translate": (None, [vp, C.c_int, dp]), "lgh_agg_scale": (None, [vp, C.c_int, C.c_double, C.c_double, C.c_double]),
         "lgh_agg_rotate_axis": (None, [vp, C.c_int, C.c_int, C.c_double]), "lgh_agg_rotate": (None, [vp, C.c_int, C.c_double, dp]),
@@ -168,6 +170,7 @@ class HostScene:
             L.lgh_look_at(self.h, _d3(cam.look[0]), _d3(cam.look[1]), _d3(cam.look[2]))
         self._check(L.lgh_set_supersampling(self.h, cam.supersampling))
         L.lgh_set_ambient_light(self.h, _d3(scene.ambient))
+        L.lgh_set_max_recursion_depth(self.h, int(scene.recursion))
         L.lgh_set_radial_background(self.h, _d3(scene.background[0]), _d3(scene.background[1]), scene.background[2])
         for p, i, f in scene.lights:
             L.lgh_add_point_light(self.h, _d3(p), _d3(i), _d3(f))
@@ -183,7 +186,7 @@ class HostScene:
 
     @staticmethod
     def _mat(m):
-        return (m.kind, _d3(m.kd), _d3(m.ks), m.roughness)
+        return (m.kind, _d3(m.kd), _d3(m.ks), m.roughness, m.roughness2)
 
     def _fill(self, idx, agg):
         L = lib()
@@ -207,9 +210,10 @@ class HostScene:
                 kinds = np.array([m.kind for m in mats], np.int32)
                 kd = np.array([m.kd for m in mats], np.float64); ks = np.array([m.ks for m in mats], np.float64)
                 rough = np.array([m.roughness for m in mats], np.float64)
+                rough2 = np.array([m.roughness2 for m in mats], np.float64)
                 L.lgh_agg_add_spheres(self.h, idx, len(rad), _ptr(cen, C.c_double), _ptr(rad, C.c_double), len(mats),
                                       _ptr(kinds, C.c_int), _ptr(kd, C.c_double), _ptr(ks, C.c_double), _ptr(rough, C.c_double),
-                                      _ptr(midx, C.c_int))
+                                      _ptr(rough2, C.c_double), _ptr(midx, C.c_int))
             elif k == "cube":
                 L.lgh_agg_add_cube(self.h, idx, _d3(item[1]), item[2], *self._mat(item[3]))
             elif k == "box":

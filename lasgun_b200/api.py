@@ -25,10 +25,10 @@ def _v3(v):
 class Material:
     """material/mod.rs:4-46.  Value type, copied into each primitive."""
 
-    __slots__ = ("kind", "kd", "ks", "roughness")
+    __slots__ = ("kind", "kd", "ks", "roughness", "roughness2")
 
-    def __init__(self, kind, kd, ks, roughness):
-        self.kind, self.kd, self.ks, self.roughness = kind, _v3(kd), _v3(ks), float(roughness)
+    def __init__(self, kind, kd, ks, roughness, roughness2=0.0):
+        self.kind, self.kd, self.ks, self.roughness, self.roughness2 = kind, _v3(kd), _v3(ks), float(roughness), float(roughness2)
 
     @staticmethod
     def default():                       # mod.rs:15-17
@@ -42,18 +42,18 @@ class Material:
     def plastic(kd, ks, roughness):      # mod.rs:24-28
         return Material(MAT_PLASTIC, kd, ks, roughness)
 
-    # metal / glass / mirror need Whitted recursion and sampling BxDFs: outside the
-    # device hot path.  Constructing them is allowed; capture rejects them.
+    # One record for the five variants: metal keeps eta in kd, k in ks and the two roughnesses (metal.rs:13-15); glass keeps
+    # kr in kd, kt in ks and eta in roughness (mod.rs:36-41: its microfacet roughness is always 0); mirror keeps kr in kd.
     @staticmethod
-    def metal(eta, k, u_roughness, v_roughness):
-        return Material(MAT_METAL, eta, k, u_roughness)
+    def metal(eta, k, u_roughness, v_roughness):      # mod.rs:30-34
+        return Material(MAT_METAL, eta, k, u_roughness, v_roughness)
 
     @staticmethod
-    def glass(kr, kt, eta):
+    def glass(kr, kt, eta):                           # mod.rs:36-41
         return Material(MAT_GLASS, kr, kt, eta)
 
     @staticmethod
-    def mirror(kr):
+    def mirror(kr):                                   # mod.rs:43-46
         return Material(MAT_MIRROR, kr, [0, 0, 0], 0.0)
 
 

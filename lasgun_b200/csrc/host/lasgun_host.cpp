@@ -31,6 +31,21 @@ Material Material::plastic(const double kd[3], const double ks[3], double roughn
     return m;
 }
 
+Material Material::metal(const double eta[3], const double k[3], double u_roughness, double v_roughness) {   // mod.rs:30-34
+    Material m; m.kind = Metal; for (int i = 0; i < 3; i++) { m.kd[i] = eta[i]; m.ks[i] = k[i]; }
+    m.roughness = u_roughness; m.roughness_v = v_roughness;
+    return m;
+}
+Material Material::glass(const double kr[3], const double kt[3], double eta) {                                // mod.rs:36-41
+    Material m; m.kind = Glass; for (int i = 0; i < 3; i++) { m.kd[i] = kr[i]; m.ks[i] = kt[i]; }
+    m.roughness = eta;
+    return m;
+}
+Material Material::mirror(const double kr[3]) {                                                              // mod.rs:43-46
+    Material m; m.kind = Mirror; for (int i = 0; i < 3; i++) { m.kd[i] = kr[i]; m.ks[i] = 0.0; }
+    return m;
+}
+
 double Camera::plane_height(double focal) const {              // camera.rs:158-164
     return is_perspective ? focal * std::tan(param * kPi / 360.0) * 2.0 : param;
 }
@@ -394,15 +409,12 @@ struct Flattener {
     uint32_t next_id = 0;
 
     uint32_t material_index(const Material& m) {
-        if (m.kind != Material::Matte && m.kind != Material::Plastic)
-            throw Error(LGB_ERR_UNSUPPORTED, "material outside the device hot path (metal/glass/mirror need Whitted recursion and sampling BxDFs)");
-        if (m.kind == Material::Matte && m.roughness != 0.0)
-            throw Error(LGB_ERR_UNSUPPORTED, "matte with sigma != 0 (Oren-Nayar) is outside the device hot path");
+        if (m.kind < Material::Matte || m.kind > Material::Mirror) throw Error(LGB_ERR_INVALID, "unknown material kind");
         for (size_t i = 0; i < out.materials.size(); i++) {
             const lgb_material& q = out.materials[i];
-            if ((int)q.kind == m.kind && q.roughness == m.roughness && !std::memcmp(q.kd, m.kd, 24) && !std::memcmp(q.ks, m.ks, 24)) return (uint32_t)i;
+            if ((int)q.kind == m.kind && q.roughness == m.roughness && q.roughness_v == m.roughness_v && !std::memcmp(q.kd, m.kd, 24) && !std::memcmp(q.ks, m.ks, 24)) return (uint32_t)i;
         }
-        lgb_material q{}; std::memcpy(q.kd, m.kd, 24); std::memcpy(q.ks, m.ks, 24); q.roughness = m.roughness; q.kind = (uint32_t)m.kind;
+        lgb_material q{}; std::memcpy(q.kd, m.kd, 24); std::memcpy(q.ks, m.ks, 24); q.roughness = m.roughness; q.roughness_v = m.roughness_v; q.kind = (uint32_t)m.kind;
         out.materials.push_back(q);
         return (uint32_t)out.materials.size() - 1;
     }
@@ -514,7 +526,7 @@ struct Flattener {
             std::vector<Cached> cache;
             auto intern = [&](const Material& m) -> uint32_t {
                 for (const Cached& c : cache)
-                    if (c.m.kind == m.kind && c.m.roughness == m.roughness && !std::memcmp(c.m.kd, m.kd, 24) && !std::memcmp(c.m.ks, m.ks, 24)) return c.index;
+                    if (c.m.kind == m.kind && c.m.roughness == m.roughness && c.m.roughness_v == m.roughness_v && !std::memcmp(c.m.kd, m.kd, 24) && !std::memcmp(c.m.ks, m.ks, 24)) return c.index;
                 std::lock_guard<std::mutex> lock(mat_mutex);
                 const uint32_t idx = material_index(m);
                 if (cache.size() < 64) cache.push_back({m, idx});
@@ -652,7 +664,7 @@ FlatScene flatten(const Scene& scene, const BuildOptions& opt) {
     out.camera.image_plane_height = c.image_plane_height; out.camera.pixel_separation = c.pixel_separation;
     out.camera.sample_distance = c.distance; out.camera.supersampling_root = (uint32_t)c.root;
     std::memcpy(out.ambient, scene.ambient, 24); std::memcpy(out.bg_inner, scene.bg_inner, 24); std::memcpy(out.bg_outer, scene.bg_outer, 24);
-    out.bg_scale = scene.bg_scale;
+    out.bg_scale = scene.bg_scale; out.recursion = scene.recursion;
     out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return out;
 }
@@ -699,7 +711,7 @@ void FlatScene::describe(lgb_scene_desc* d) const {
     d->lights = lights.data(); d->n_lights = lights.size();
     d->camera = camera;
     std::memcpy(d->ambient, ambient, 24); std::memcpy(d->bg_inner, bg_inner, 24); std::memcpy(d->bg_outer, bg_outer, 24);
-    d->bg_scale = bg_scale;
+    d->bg_scale = bg_scale; d->recursion = recursion;
 }
 
 // ------------------------------------------------------------------ Accel / capture
@@ -753,8 +765,8 @@ struct HostScene {
     Aggregate& agg(int h) { return h == 0 ? scene.root : *pending[(size_t)h - 1]; }
 };
 thread_local std::string g_host_error;
-Material mk(int kind, const double* kd, const double* ks, double rough) {
-    Material m; m.kind = kind; std::memcpy(m.kd, kd, 24); std::memcpy(m.ks, ks, 24); m.roughness = rough; return m;
+Material mk(int kind, const double* kd, const double* ks, double rough, double rough_v) {
+    Material m; m.kind = kind; std::memcpy(m.kd, kd, 24); std::memcpy(m.ks, ks, 24); m.roughness = rough; m.roughness_v = rough_v; return m;
 }
 template <class F> int guarded(F&& f) {
     try { f(); return LGB_OK; }
@@ -773,6 +785,7 @@ void lgh_look_at(void* s, const double* o, const double* l, const double* u) { (
 int lgh_set_supersampling(void* s, int base) { return guarded([&] { ((HostScene*)s)->scene.camera.set_supersampling((uint8_t)base); }); }
 void lgh_set_ambient_light(void* s, const double* c) { ((HostScene*)s)->scene.set_ambient_light(c); }
 void lgh_set_radial_background(void* s, const double* in, const double* out, double scale) { ((HostScene*)s)->scene.set_radial_background(in, out, scale); }
+void lgh_set_max_recursion_depth(void* s, uint32_t depth) { ((HostScene*)s)->scene.set_max_recursion_depth(depth); }
 void lgh_set_mesh_smoothing(void* s, int on) { ((HostScene*)s)->scene.set_mesh_smoothing(on != 0); }
 void lgh_add_point_light(void* s, const double* p, const double* i, const double* f) { ((HostScene*)s)->scene.add_point_light(p, i, f); }
 int lgh_add_mesh(void* s, const float* pos, uint64_t nv, const uint32_t* vi, uint64_t ntri, const float* nrm, uint64_t nn, const uint32_t* ni, int64_t* ref_out) {
@@ -783,23 +796,23 @@ int lgh_add_mesh(void* s, const float* pos, uint64_t nv, const uint32_t* vi, uin
     });
 }
 int lgh_agg_new(void* s) { HostScene* h = (HostScene*)s; h->pending.emplace_back(new Aggregate()); return (int)h->pending.size(); }
-void lgh_agg_add_sphere(void* s, int ag, const double* c, double r, int kind, const double* kd, const double* ks, double rough) {
-    ((HostScene*)s)->agg(ag).add_sphere(c, r, mk(kind, kd, ks, rough));
+void lgh_agg_add_sphere(void* s, int ag, const double* c, double r, int kind, const double* kd, const double* ks, double rough, double rough_v) {
+    ((HostScene*)s)->agg(ag).add_sphere(c, r, mk(kind, kd, ks, rough, rough_v));
 }
 void lgh_agg_add_spheres(void* s, int ag, uint64_t n, const double* c, const double* r, int nmat, const int* kinds, const double* kd,
-                         const double* ks, const double* rough, const int* mat_index) {
+                         const double* ks, const double* rough, const double* rough_v, const int* mat_index) {
     Aggregate& a = ((HostScene*)s)->agg(ag); (void)nmat;
     a.contents.reserve(a.contents.size() + n);
-    for (uint64_t i = 0; i < n; i++) { int m = mat_index[i]; a.add_sphere(c + 3 * i, r[i], mk(kinds[m], kd + 3 * m, ks + 3 * m, rough[m])); }
+    for (uint64_t i = 0; i < n; i++) { int m = mat_index[i]; a.add_sphere(c + 3 * i, r[i], mk(kinds[m], kd + 3 * m, ks + 3 * m, rough[m], rough_v[m])); }
 }
-void lgh_agg_add_cube(void* s, int ag, const double* o, double dim, int kind, const double* kd, const double* ks, double rough) {
-    ((HostScene*)s)->agg(ag).add_cube(o, dim, mk(kind, kd, ks, rough));
+void lgh_agg_add_cube(void* s, int ag, const double* o, double dim, int kind, const double* kd, const double* ks, double rough, double rough_v) {
+    ((HostScene*)s)->agg(ag).add_cube(o, dim, mk(kind, kd, ks, rough, rough_v));
 }
-void lgh_agg_add_box(void* s, int ag, const double* a, const double* b, int kind, const double* kd, const double* ks, double rough) {
-    ((HostScene*)s)->agg(ag).add_box(a, b, mk(kind, kd, ks, rough));
+void lgh_agg_add_box(void* s, int ag, const double* a, const double* b, int kind, const double* kd, const double* ks, double rough, double rough_v) {
+    ((HostScene*)s)->agg(ag).add_box(a, b, mk(kind, kd, ks, rough, rough_v));
 }
-void lgh_agg_add_mesh(void* s, int ag, int64_t mesh, int has_mat, int kind, const double* kd, const double* ks, double rough) {
-    if (has_mat) ((HostScene*)s)->agg(ag).add_obj_of(ObjRef{(size_t)mesh}, mk(kind, kd, ks, rough));
+void lgh_agg_add_mesh(void* s, int ag, int64_t mesh, int has_mat, int kind, const double* kd, const double* ks, double rough, double rough_v) {
+    if (has_mat) ((HostScene*)s)->agg(ag).add_obj_of(ObjRef{(size_t)mesh}, mk(kind, kd, ks, rough, rough_v));
     else ((HostScene*)s)->agg(ag).add_obj(ObjRef{(size_t)mesh});
 }
 void lgh_agg_add_group(void* s, int parent, int child) {

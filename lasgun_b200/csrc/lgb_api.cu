@@ -481,20 +481,32 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
 
     auto tc0 = std::chrono::steady_clock::now();
     auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
-    // ---- validate materials (only the plastic / Lambertian lobes are on the device path)
-    std::vector<double> mats(8 * d->n_materials);
+    // ---- materials: the device record (lgb_types.cuh) of every `Material::scattering` (material/*.rs)
+    std::vector<double> mats(kMatStride * d->n_materials);
+    bool any_general = false, any_specular = false;
     for (uint64_t i = 0; i < d->n_materials; i++) {
         const lgb_material& m = d->materials[i];
-        if (m.kind == 0) { if (m.roughness != 0.0) return fail(ctx, LGB_ERR_UNSUPPORTED, "material: matte with sigma != 0 (Oren-Nayar) is outside the device path"); }
-        else if (m.kind != 1) return fail(ctx, LGB_ERR_UNSUPPORTED, "material: only plastic and matte(sigma=0) are on the device path (metal/glass/mirror need Whitted recursion)");
-        bool diffuse = m.kind == 0 ? true : !(m.kd[0] == 0.0 && m.kd[1] == 0.0 && m.kd[2] == 0.0);   // plastic.rs:24, matte.rs:18-26
-        bool glossy = m.kind == 1 && !(m.ks[0] == 0.0 && m.ks[1] == 0.0 && m.ks[2] == 0.0);          // plastic.rs:29
-        double* o = &mats[8 * i];
+        if (m.kind > LGB_MAT_MIRROR) return fail(ctx, LGB_ERR_INVALID, "material: unknown kind");
+        const bool plain = m.kind == LGB_MAT_PLASTIC || (m.kind == LGB_MAT_MATTE && m.roughness == 0.0);     // the lobes of the fast path
+        const bool specular = m.kind == LGB_MAT_GLASS || m.kind == LGB_MAT_MIRROR;
+        bool diffuse = m.kind == LGB_MAT_MATTE ? true : !(m.kd[0] == 0.0 && m.kd[1] == 0.0 && m.kd[2] == 0.0);   // plastic.rs:24, matte.rs:18-26
+        bool glossy = m.kind == LGB_MAT_PLASTIC && !(m.ks[0] == 0.0 && m.ks[1] == 0.0 && m.ks[2] == 0.0);        // plastic.rs:29
+        if (!plain) { diffuse = glossy = false; any_general = true; }
+        any_specular |= specular;
+        double* o = &mats[kMatStride * i];
         o[0] = m.kd[0]; o[1] = m.kd[1]; o[2] = m.kd[2]; o[3] = m.roughness;
         o[4] = m.ks[0]; o[5] = m.ks[1]; o[6] = m.ks[2];
-        long long fl = (diffuse ? 1 : 0) | (glossy ? 2 : 0);
+        long long fl = (diffuse ? kMatDiffuse : 0) | (glossy ? kMatGlossy : 0) | (plain ? 0 : kMatGeneral) | (specular ? kMatSpecular : 0) | ((long long)m.kind << 8);
         std::memcpy(&o[7], &fl, 8);
+        o[8] = m.roughness_v; o[9] = 0.0; o[10] = o[11] = 0.0;
+        if (m.kind == LGB_MAT_MATTE && m.roughness != 0.0) {               // OrenNayar::new, diffuse.rs:28-34 (cgmath Deg -> Rad: deg * pi / 180)
+            const double sigma = m.roughness * 3.14159265358979323846264338327950288 / 180.0;
+            const double sigma2 = sigma * sigma;
+            o[8] = 1.0 - (sigma2 / 2.0 * (sigma2 + 0.33));
+            o[9] = 0.45 * sigma2 / (sigma2 + 0.09);
+        }
     }
+    if (any_specular && d->recursion > kMaxRecursion) return fail(ctx, LGB_ERR_UNSUPPORTED, "lgb_scene_create: recursion deeper than 12 with glass or mirror materials");
     auto mat_ok = [&](const uint32_t* arr, uint64_t n) { for (uint64_t i = 0; i < n; i++) if (arr[i] >= d->n_materials) return false; return true; };
     if ((d->n_spheres && (!d->spheres || !d->sphere_material || !d->sphere_id)) || (d->n_cuboids && (!d->cuboids || !d->cuboid_material || !d->cuboid_id)) ||
         (d->n_triangles && (!d->triangles || !d->triangle_material || !d->triangle_id)) || (d->n_instances && !d->instances) ||
@@ -507,7 +519,8 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     lgb_scene_desc eager;                                    // lazy desc of a scene the device-side builder does not take: fetch the tree now
     const uint32_t prim_total = (uint32_t)(d->n_spheres + d->n_cuboids + d->n_triangles);
     bool lazy = !d->nodes && d->reference_tree;
-    if (lazy && !(prim_total >= 32768u && prim_total <= kLeafFirstMask && !std::getenv("LGB_HOST_BUILD"))) {
+    // (rays below specular hits break exact-t ties through resident rank tables: no lazy tree for scenes with glass or mirrors)
+    if (lazy && (any_specular || !(prim_total >= 32768u && prim_total <= kLeafFirstMask && !std::getenv("LGB_HOST_BUILD")))) {
         lgb_reference_tree tree{};
         if (d->reference_tree(d->reference_tree_user, &tree) != 0 || !tree.nodes || !tree.n_nodes) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: reference_tree callback failed");
         eager = *d;
@@ -666,6 +679,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         if (nt) { s->dev.tri = la.tri; s->dev.tri_nrm = la.tri_nrm; }
         s->dev.materials = (const double*)(D + o_mat);
         s->dev.lights = (const double*)(D + o_lights); s->dev.n_lights = (uint32_t)d->n_lights;
+        s->dev.general = any_general; s->dev.specular = any_specular; s->dev.recursion = d->recursion;
         s->gpu_built = true;
         (void)tg0;
     } else {
@@ -803,6 +817,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
             for (int k = 0; k < 3; k++) { l[9 * i + k] = d->lights[i].position[k]; l[9 * i + 3 + k] = d->lights[i].intensity[k]; l[9 * i + 6 + k] = d->lights[i].falloff[k]; }
         s->dev.lights = (const double*)(D + o_lights);
         s->dev.n_lights = (uint32_t)d->n_lights;
+        s->dev.general = any_general; s->dev.specular = any_specular; s->dev.recursion = d->recursion;
     }
     {
         cudaError_t e = cudaMemcpyAsync(D, H, arena_bytes, cudaMemcpyHostToDevice, ctx->stream);
@@ -885,7 +900,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     if (s->cam.pixel_separation != 0.0 && W.aspect > 4.0)
         return fail(c, LGB_ERR_UNSUPPORTED, "orthographic capture with aspect > 4: the scene's coordinate bound assumed aspect <= 4");
     const DevScene& S = s->dev;
-    if (!render_fused(W.spp)) CU(c, c->radiance.reserve(std::max<uint64_t>(total, 1) * 3 * sizeof(double)));      // spp > 256 only
+    if (!render_fused(W.spp) || S.general) CU(c, c->radiance.reserve(std::max<uint64_t>(total, 1) * 3 * sizeof(double)));      // spp > 256 only
     CU(c, c->counters.reserve(sizeof(DevCounters)));
     // wavefront buffers: hit_t 8 + ps 24 + hit_ref 4 + occl 4 + 3 queues x 4 x lights bytes per sample slot,
     // + occluder 4 x lights bytes per pixel slot
@@ -906,6 +921,8 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         V.queue_fetch = V.queue_count + LGB_MAX_LIGHTS * 3;
         V.tie_count = V.queue_fetch + LGB_MAX_LIGHTS * 3;
         V.fallback_count = V.tie_count + 1;
+        V.sec_count = V.fallback_count + 1;
+        V.sec_list = V.queue;                            // the shadow queues are drained before k_shade lists the specular slots
         V.fallback_list = V.queue;                       // the shadow queues are written only after the primary phase
         // automatic: where a bundle of >= 8 rays shares a traversal that is long enough to be worth sharing (measured: a loss on
         // scenes of a few dozen primitives, a gain on large ones)
@@ -974,8 +991,8 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         if (total) for (int k = 0; k < 6; k++) { float pm = 0.f; CU(c, cudaEventElapsedTime(&pm, c->phase[k], c->phase[k + 1])); stats->kernel_ms[k] = pm; }
         for (int k = 0; k < 3; k++) { stats->filter_tests[k] = hc.filter[k]; stats->exact_tests[k] = hc.exact[k]; }
         stats->stack_overflow = hc.stack_overflow;
-        stats->beams = W.beams; stats->tie_retraces = tie_slots;
-        stats->kernel_launches = total ? (render_fused(W.spp) ? 3 : 4) + (W.beams ? 2 : 0) + s->dev.n_lights * (W.spp > 1 ? 3 : 1) : 0;
+        stats->beams = W.beams; stats->tie_retraces = tie_slots; stats->secondary_rays = hc.secondary_rays;
+        stats->kernel_launches = total ? (S.general ? (S.specular && S.recursion ? 5 : 4) : render_fused(W.spp) ? 3 : 4) + (W.beams ? 2 : 0) + s->dev.n_lights * (W.spp > 1 ? 3 : 1) : 0;
         float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         stats->render_ms = ms; stats->total_ms = ms;
     }

@@ -512,6 +512,8 @@ struct Bsdf {
     D3 ng, ns, ss, ts, kd_pi, ks, wo_l;
     double alpha2, wo_ng, cos_o, lambda_o;
     bool diffuse, glossy;
+    // GENERAL variants only (dead, and removed by the compiler, in the plastic fast path): the material record as stored
+    uint32_t flags; D3 c0, c1; double p0, p1, p2;
 };
 __device__ __forceinline__ void bsdf_prepare(Bsdf& B, D3 wo) {
     B.wo_ng = dot(wo, B.ng);
@@ -546,13 +548,137 @@ __device__ __forceinline__ D3 bsdf_f(const Bsdf& B, D3 wi) {
     return f;
 }
 
+// ---- the lobes outside the plastic fast path, in the reference's own operation order
+// bxdf/mod.rs:234-258 (shading-space trigonometry)
+__device__ __forceinline__ double g_sin_theta(D3 w) { return sqrt(fmax(1.0 - w.z * w.z, 0.0)); }
+__device__ __forceinline__ double g_cos_phi(D3 w) { const double s = g_sin_theta(w); return s == 0.0 ? 1.0 : fmin(fmax(w.x / s, -1.0), 1.0); }
+__device__ __forceinline__ double g_sin_phi(D3 w) { const double s = g_sin_theta(w); return s == 0.0 ? 0.0 : fmin(fmax(w.y / s, -1.0), 1.0); }
+// fresnel.rs:37-64 for any pair of indices
+__device__ __forceinline__ double dielectric_general(double cos_i, double eta_i, double eta_t) {
+    cos_i = fmin(fmax(cos_i, -1.0), 1.0);
+    if (!(cos_i > 0.0)) { const double tmp = eta_i; eta_i = eta_t; eta_t = tmp; cos_i = fabs(cos_i); }
+    const double sin_i = sqrt(fmax(1.0 - cos_i * cos_i, 0.0));
+    const double sin_t = eta_i / eta_t * sin_i;
+    if (sin_t >= 1.0) return 1.0;
+    const double cos_t = sqrt(fmax(1.0 - sin_t * sin_t, 0.0));
+    const double r_parl = ((eta_t * cos_i) - (eta_i * cos_t)) / ((eta_t * cos_i) + (eta_i * cos_t));
+    const double r_perp = ((eta_i * cos_i) - (eta_t * cos_t)) / ((eta_i * cos_i) + (eta_t * cos_t));
+    return (r_parl * r_parl + r_perp * r_perp) * 0.5;
+}
+// fresnel.rs:68-90 with eta_i = 1 (metal.rs:21: x / 1.0 is exact)
+__device__ __forceinline__ double conductor_channel(double cos_i, double eta, double k) {
+    const double cos2 = cos_i * cos_i, sin2 = 1.0 - cos2;
+    const double e2 = eta * eta, ek2 = k * k;
+    const double t0 = e2 - ek2 - sin2;
+    const double a2b2 = sqrt(t0 * t0 + 4.0 * (e2 * ek2));
+    const double t1 = a2b2 + cos2;
+    const double a = sqrt(0.5 * (a2b2 + t0));
+    const double t2 = 2.0 * cos_i * a;
+    const double rs = (t1 - t2) / (t1 + t2);
+    const double t3 = cos2 * a2b2 + sin2 * sin2;
+    const double t4 = t2 * sin2;
+    const double rp = rs * (t3 - t4) / (t3 + t4);
+    return 0.5 * (rp + rs);
+}
+// microfacet.rs:31-66, anisotropic
+__device__ __forceinline__ double tr_d_aniso(double ax, double ay, D3 wh) {
+    const double c2 = wh.z * wh.z;
+    const double t2 = fmax(1.0 - c2, 0.0) / c2;
+    if (isinf(t2)) return 0.0;
+    const double PI = 3.14159265358979323846264338327950288;
+    const double cp = g_cos_phi(wh), sp = g_sin_phi(wh);
+    const double e = ((cp * cp) / (ax * ax) + (sp * sp) / (ay * ay)) * t2;
+    return 1.0 / (PI * ax * ay * (c2 * c2) * (1.0 + e) * (1.0 + e));
+}
+__device__ __forceinline__ double tr_lambda_aniso(double ax, double ay, D3 w) {
+    const double att = fabs(g_sin_theta(w) / w.z);
+    if (isinf(att)) return 0.0;
+    const double cp = g_cos_phi(w), sp = g_sin_phi(w);
+    const double alpha = sqrt((cp * cp) * ax * ax + (sp * sp) * ay * ay);
+    const double a2t2 = (alpha * att) * (alpha * att);
+    return (sqrt(1.0 + a2t2) - 1.0) / 2.0;
+}
+// BSDF::f (bsdf.rs:73-92) for matte(sigma > 0) and metal; the lobes of glass and mirror scatter only through sample_f (mod.rs:172)
+__device__ __noinline__ D3 bsdf_f_general(const Bsdf& B, D3 wi) {
+    const D3 zero = d3(0, 0, 0);
+    const bool reflect = dot(wi, B.ng) * B.wo_ng > 0.0;
+    if (B.wo_l.z == 0.0 || !reflect) return zero;        // both lobes are REFLECTION
+    const D3 wo = B.wo_l, wl = d3(dot(wi, B.ss), dot(wi, B.ts), dot(wi, B.ns));
+    const uint32_t kind = B.flags >> 8;
+    const double FRAC_1_PI = 0.318309886183790671537767526745028724;
+    if (kind == LGB_MAT_MATTE) {                          // diffuse.rs:36-56 (Oren-Nayar, A = p1, B = p2)
+        const double sin_i = g_sin_theta(wl), sin_o = g_sin_theta(wo);
+        double max_cos = 0.0;
+        if (sin_i > 1e-4 && sin_o > 1e-4) max_cos = fmax(g_cos_phi(wl) * g_cos_phi(wo) + g_sin_phi(wl) * g_sin_phi(wo), 0.0);
+        double sin_alpha, tan_beta;
+        if (fabs(wl.z) > fabs(wo.z)) { sin_alpha = sin_o; tan_beta = sin_i / fabs(wl.z); }
+        else { sin_alpha = sin_i; tan_beta = sin_o / fabs(wo.z); }
+        return B.c0 * FRAC_1_PI * (B.p1 + B.p2 * max_cos * sin_alpha * tan_beta);
+    }
+    if (kind == LGB_MAT_METAL) {                          // microfacet.rs:101-115 with Substance::Conductor (metal.rs:17-26)
+        const double cos_o = fabs(wo.z), cos_i = fabs(wl.z);
+        D3 wh = wl + wo;
+        if (cos_i == 0.0 || cos_o == 0.0) return zero;
+        if (wh.x == 0.0 && wh.y == 0.0 && wh.z == 0.0) return zero;
+        wh = normalize(wh);
+        const double ci = fmin(fmax(dot(wl, wh), -1.0), 1.0);
+        const D3 F = d3(conductor_channel(ci, B.c0.x, B.c1.x), conductor_channel(ci, B.c0.y, B.c1.y), conductor_channel(ci, B.c0.z, B.c1.z));
+        const double D = tr_d_aniso(B.p0, B.p1, wh);
+        const double G = 1.0 / (1.0 + tr_lambda_aniso(B.p0, B.p1, wo) + tr_lambda_aniso(B.p0, B.p1, wl));
+        return F * (D * G) / (4.0 * cos_i * cos_o);
+    }
+    return zero;
+}
+// BSDF::sample_f (bsdf.rs:94-140) for the two flag sets of integrate.rs:85,110 at sample (0.5, 0.5): a material has at most one lobe
+// matching either, so comp = 0 and the pdf is the lobe's own (1 for both specular lobes).  Returns false where the sample is void.
+// specular.rs:17-25 (reflection) and :44-66 (transmission); spectrum clamped to [0, 1] (bsdf.rs:122).
+__device__ __forceinline__ double clamp01(double v) { return fmin(fmax(v, 0.0), 1.0); }
+__device__ __forceinline__ bool sample_specular_reflection(const Bsdf& B, D3& spectrum, D3& wi_world) {
+    const uint32_t kind = B.flags >> 8;
+    if (kind == LGB_MAT_GLASS) { if (B.c0.x == 0.0 && B.c0.y == 0.0 && B.c0.z == 0.0) return false; }   // glass.rs:36: no reflection lobe
+    else if (kind != LGB_MAT_MIRROR) return false;
+    if (B.wo_l.z == 0.0) return false;
+    const D3 wi = d3(-B.wo_l.x, -B.wo_l.y, B.wo_l.z);
+    const double F = kind == LGB_MAT_GLASS ? dielectric_general(wi.z, 1.0, B.p0) : 1.0;
+    const double ac = fabs(wi.z);
+    spectrum = d3(clamp01(F * B.c0.x / ac), clamp01(F * B.c0.y / ac), clamp01(F * B.c0.z / ac));
+    wi_world = d3(B.ss.x * wi.x + B.ts.x * wi.y + B.ns.x * wi.z, B.ss.y * wi.x + B.ts.y * wi.y + B.ns.y * wi.z, B.ss.z * wi.x + B.ts.z * wi.y + B.ns.z * wi.z);
+    return true;
+}
+__device__ __forceinline__ bool sample_specular_transmission(const Bsdf& B, D3& spectrum, D3& wi_world) {
+    if ((B.flags >> 8) != LGB_MAT_GLASS || (B.c1.x == 0.0 && B.c1.y == 0.0 && B.c1.z == 0.0)) return false;      // glass.rs:46
+    if (B.wo_l.z == 0.0) return false;
+    const bool entering = B.wo_l.z > 0.0;
+    const double eta_i = entering ? 1.0 : B.p0, eta_t = entering ? B.p0 : 1.0;
+    const double eta = eta_i / eta_t;
+    // refract(wo, (0, 0, 1), eta), bxdf/mod.rs:164-174
+    const double cos_i = 0.0 * B.wo_l.x + 0.0 * B.wo_l.y + 1.0 * B.wo_l.z;
+    const double sin2_i = fmax(1.0 - cos_i * cos_i, 0.0);
+    const double sin2_t = eta * eta * sin2_i;
+    if (sin2_t >= 1.0) return false;
+    const double cos_t = sqrt(1.0 - sin2_t);
+    const double k = eta * cos_i - cos_t;
+    const D3 wi = d3((eta * -1.0) * B.wo_l.x + k * 0.0, (eta * -1.0) * B.wo_l.y + k * 0.0, (eta * -1.0) * B.wo_l.z + k * 1.0);
+    const double T = 1.0 - dielectric_general(wi.z, 1.0, B.p0);
+    const double ac = fabs(wi.z);
+    spectrum = d3(clamp01(B.c1.x * T / ac), clamp01(B.c1.y * T / ac), clamp01(B.c1.z * T / ac));
+    wi_world = d3(B.ss.x * wi.x + B.ts.x * wi.y + B.ns.x * wi.z, B.ss.y * wi.x + B.ts.y * wi.y + B.ns.y * wi.z, B.ss.z * wi.x + B.ts.z * wi.y + B.ns.z * wi.z);
+    return true;
+}
+
 __device__ __forceinline__ double lerp64(double t, double a, double b) { return a * (1.0 - t) + b * t; }
+__device__ __forceinline__ D3 background_of(const DevShade& sh, D3 d) {                  // background.rs:25-34
+    const D3 dn = normalize(d);
+    const double dz = fabs(0.0 * dn.x + 0.0 * dn.y + 1.0 * dn.z);
+    const double t = fmin(sqrt(1.0 - dz * dz) / sh.bg_scale, 1.0);
+    return d3(lerp64(t, sh.bg_inner[0], sh.bg_outer[0]), lerp64(t, sh.bg_inner[1], sh.bg_outer[1]), lerp64(t, sh.bg_inner[2], sh.bg_outer[2]));
+}
 
 // Everything the lighting loop needs about the closest hit (SurfaceInteraction::from, surface.rs:158-183,
 // + Material::scattering, plastic.rs:20-37 / matte.rs:18-26).
-struct ShadePoint { D3 wo, ng, ns, ps; Bsdf B; };
+struct ShadePoint { D3 wo, ng, ns, ps, pt; Bsdf B; };
 
-template <bool WITH_BSDF, bool INST>
+template <bool WITH_BSDF, bool INST, bool GENERAL = false>
 __device__ __forceinline__ void shade_point(const DevScene& S, const Ray64& ray, double t, uint32_t ref, ShadePoint& P, uint32_t& id) {
     Surf sf; double t_again = t;
     if (INST) {                      // the record is formed in the primitive's own space, then brought back (bvh.rs:508-518)
@@ -569,12 +695,14 @@ __device__ __forceinline__ void shade_point(const DevScene& S, const Ray64& ray,
     D3 p = ray.o + ray.d * t;
     D3 p_err = P.ng * err;
     P.ps = p + p_err;                                          // integrate.rs:40
+    if (GENERAL) P.pt = p - p_err;                             // origin of a transmitted ray, integrate.rs:126
     if (!WITH_BSDF) return;
     P.B.ng = P.ng; P.B.ns = P.ns; P.B.ss = normalize(sf.s_dpdu); P.B.ts = cross(P.ns, P.B.ss);
-    const double* M = S.materials + 8 * (size_t)sf.material;
+    const double* M = S.materials + kMatStride * (size_t)sf.material;
     P.B.kd_pi = d3(M[0], M[1], M[2]) * 0.318309886183790671537767526745028724; P.B.alpha2 = M[3] * M[3]; P.B.ks = d3(M[4], M[5], M[6]);
     const uint32_t flags = (uint32_t)__double_as_longlong(M[7]);
-    P.B.diffuse = flags & 1u; P.B.glossy = flags & 2u;
+    P.B.diffuse = flags & kMatDiffuse; P.B.glossy = flags & kMatGlossy;
+    if (GENERAL) { P.B.flags = flags; P.B.c0 = d3(M[0], M[1], M[2]); P.B.c1 = d3(M[4], M[5], M[6]); P.B.p0 = M[3]; P.B.p1 = M[8]; P.B.p2 = M[9]; }
     bsdf_prepare(P.B, P.wo);
 }
 
@@ -1171,8 +1299,10 @@ __device__ __forceinline__ uchar4 quantise(D3 c) {                     // img.rs
 // Radiance of every sample slot (integrate.rs:23-80) and, FUSED (spp <= 256: a block holds whole pixels), the film:
 // the samples of a pixel meet in shared memory and are summed in sample order (integrate.rs:16-20), so the
 // 24 B/sample radiance buffer and k_resolve drop out.  Thread t of a block: pixel t / spp of the block, sample t % spp.
-template <bool INST, bool FUSED>
-__global__ void __launch_bounds__(256, LGB_SHADE_MIN_BLOCKS) k_shade(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
+// GENERAL (scenes with Oren-Nayar, metal, glass or mirror; never FUSED): every material's BSDF::f, and the slots whose closest hit
+// carries specular lobes are listed for k_secondary.
+template <bool INST, bool FUSED, bool GENERAL = false>
+__global__ void __launch_bounds__(256, GENERAL ? 2 : LGB_SHADE_MIN_BLOCKS) k_shade(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
     const double PI = 3.14159265358979323846264338327950288;
     const uint64_t total = W.n_pixels * W.spp;
     __shared__ double rad[FUSED ? 256 * 3 : 3];
@@ -1197,13 +1327,19 @@ __global__ void __launch_bounds__(256, LGB_SHADE_MIN_BLOCKS) k_shade(DevScene S,
         if (ref != kSlotUnused && slot_ray(C, W, g, ray, x, y, s)) {
             have = true;
             if (ref == LGB_MISS) {                                       // background.rs:25-34
-                D3 dn = normalize(ray.d);
-                double dz = fabs(0.0 * dn.x + 0.0 * dn.y + 1.0 * dn.z);
-                double t = fmin(sqrt(1.0 - dz * dz) / sh.bg_scale, 1.0);
-                output = d3(lerp64(t, sh.bg_inner[0], sh.bg_outer[0]), lerp64(t, sh.bg_inner[1], sh.bg_outer[1]), lerp64(t, sh.bg_inner[2], sh.bg_outer[2]));
+                output = background_of(sh, ray.d);
             } else {
                 ShadePoint P; uint32_t id;
-                shade_point<true, INST>(S, ray, V.hit_t[g], ref, P, id);
+                shade_point<true, INST, GENERAL>(S, ray, V.hit_t[g], ref, P, id);
+                const bool general = GENERAL && (P.B.flags & kMatGeneral);
+                if (GENERAL && (P.B.flags & kMatSpecular) && S.recursion > 0) {          // integrate.rs:69: followed by k_secondary
+                    const unsigned peers = __activemask();
+                    const unsigned lane = threadIdx.x & 31u, leader = __ffs(peers) - 1;
+                    uint32_t base = 0;
+                    if (lane == leader) base = atomicAdd(V.sec_count, (uint32_t)__popc(peers));
+                    base = __shfl_sync(peers, base, leader);
+                    V.sec_list[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)g;
+                }
                 const uint32_t occl = V.occl[g];
                 if (O.aov_occl) O.aov_occl[((uint64_t)y * W.w + x) * W.spp + s] = occl;
                 for (uint32_t l = 0; l < S.n_lights; l++) {              // integrate.rs:47-66
@@ -1215,10 +1351,10 @@ __global__ void __launch_bounds__(256, LGB_SHADE_MIN_BLOCKS) k_shade(DevScene S,
                     if (f_att == 0.0) continue;
                     wi = wi * (1.0 / dist);
                     double wi_dot_n = dot(wi, P.ns);
-                    D3 f = bsdf_f(P.B, wi);                              // zero when the shadow ray was skipped
+                    D3 f = general ? bsdf_f_general(P.B, wi) : bsdf_f(P.B, wi);     // zero when the shadow ray was skipped
                     output = output + mul_el(PI * d3(L[3], L[4], L[5]), f) * (wi_dot_n / f_att);
                 }
-                output = output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), bsdf_f(P.B, P.ns));   // integrate.rs:67
+                output = output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), general ? bsdf_f_general(P.B, P.ns) : bsdf_f(P.B, P.ns));   // integrate.rs:67
                 D3 zero = d3(0, 0, 0);
                 output = output + zero + zero;          // integrate.rs:79 (reflected + refracted are zero for plastic)
             }
@@ -1238,6 +1374,85 @@ __global__ void __launch_bounds__(256, LGB_SHADE_MIN_BLOCKS) k_shade(DevScene S,
         const uint64_t p = (uint32_t)g / W.spp;
         reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)y * W.w + x] = quantise(c);
     }
+}
+
+// Whitted recursion (integrate.rs:69-132) below the closest hits that carry specular lobes (glass, mirror), one thread per listed
+// slot: a depth-first walk of the slot's ray tree on a per-thread stack of (ray, throughput, depth).  A node of the tree is shaded
+// exactly as a primary hit is — closest hit, one shadow ray per light that can contribute, BSDF::f, ambient — and its radiance,
+// scaled by the throughput of the path that reached it, is added to the slot's entry of the radiance buffer.
+// The reference nests the products (spectrum x li(child)); the throughput form multiplies the same factors in another order, which
+// moves the last bits of an f64 sum and nothing a byte of the film can see.
+struct SecRay { Ray64 ray; D3 w; uint32_t depth; };
+template <bool INST>
+__device__ __forceinline__ void push_specular(const DevScene& S, const ShadePoint& P, D3 w, uint32_t depth, SecRay* stack, int& sp) {
+    if (!(P.B.flags & kMatSpecular) || depth >= S.recursion) return;
+    D3 spec, wi;
+    if (sample_specular_reflection(P.B, spec, wi)) {                                  // specular_reflect, integrate.rs:82-106
+        if (!(spec.x == 0.0 && spec.y == 0.0 && spec.z == 0.0) && !(dot(wi, P.ns) <= 0.0)) {
+            SecRay& r = stack[sp++];
+            r.ray.o = P.ps;
+            r.ray.d = -1.0 * P.wo + 2.0 * dot(P.wo, P.ns) * P.ns;                     // bxdf::util::reflect, mod.rs:160-162
+            r.w = mul_el(w, spec); r.depth = depth + 1;
+        }
+    }
+    if (sample_specular_transmission(P.B, spec, wi)) {                                // specular_transmit, integrate.rs:108-132
+        const double c = fabs(dot(wi, P.ns));
+        if (!(spec.x == 0.0 && spec.y == 0.0 && spec.z == 0.0) && c != 0.0) {
+            SecRay& r = stack[sp++];
+            r.ray.o = P.pt; r.ray.d = wi;
+            r.w = mul_el(w, spec) * c; r.depth = depth + 1;                             // pdf = 1
+        }
+    }
+}
+template <bool INST>
+__global__ void __launch_bounds__(128) k_secondary(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
+    const double PI = 3.14159265358979323846264338327950288;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *V.sec_count) return;
+    const uint32_t g = V.sec_list[i];
+    SecRay stack[kMaxRecursion + 1];
+    int sp = 0;
+    LocalCounters lc = {};
+    unsigned long long traced = 0;
+    {
+        Ray64 ray; uint32_t x, y, s, id; ShadePoint P;
+        slot_ray(C, W, g, ray, x, y, s);
+        shade_point<true, INST, true>(S, ray, V.hit_t[g], V.hit_ref[g], P, id);
+        push_specular<INST>(S, P, d3(1.0, 1.0, 1.0), 0, stack, sp);
+    }
+    D3 rad = d3(0, 0, 0);
+    while (sp > 0) {
+        const SecRay cur = stack[--sp];
+        traced++;
+        const Hit h = traverse<false, false, INST>(S, cur.ray, CUDART_INF, lc);
+        if (h.ref == LGB_MISS) { rad = rad + mul_el(cur.w, background_of(sh, cur.ray.d)); continue; }
+        ShadePoint P; uint32_t id;
+        shade_point<true, INST, true>(S, cur.ray, h.t, h.ref, P, id);
+        const bool general = P.B.flags & kMatGeneral;
+        D3 output = d3(0, 0, 0);
+        if (!(P.B.flags & kMatSpecular)) {                                  // specular lobes: BSDF::f is zero, no light can contribute
+            for (uint32_t l = 0; l < S.n_lights; l++) {                      // integrate.rs:47-66
+                const double* L = S.lights + 9 * (size_t)l;
+                D3 wi = d3(L[0], L[1], L[2]) - P.ps;
+                if (!(dot(wi, P.ng) * P.B.wo_ng > 0.0) || P.B.wo_l.z == 0.0) continue;     // every remaining lobe is REFLECTION: f = 0
+                Ray64 sray; sray.o = P.ps; sray.d = wi;                      // light/point.rs:42-54: occluded iff the closest t < 1
+                traced++;
+                if (traverse<true, false, INST>(S, sray, 1.0, lc).ref != LGB_MISS) continue;
+                const double dist = sqrt(dot(wi, wi));
+                const double f_att = L[6] + L[7] * dist + L[8] * dist * dist;
+                if (f_att == 0.0) continue;
+                wi = wi * (1.0 / dist);
+                const double wi_dot_n = dot(wi, P.ns);
+                const D3 f = general ? bsdf_f_general(P.B, wi) : bsdf_f(P.B, wi);
+                output = output + mul_el(PI * d3(L[3], L[4], L[5]), f) * (wi_dot_n / f_att);
+            }
+            output = output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), general ? bsdf_f_general(P.B, P.ns) : bsdf_f(P.B, P.ns));
+        }
+        rad = rad + mul_el(cur.w, output);
+        push_specular<INST>(S, P, cur.w, cur.depth, stack, sp);
+    }
+    O.radiance[3 * (size_t)g + 0] += rad.x; O.radiance[3 * (size_t)g + 1] += rad.y; O.radiance[3 * (size_t)g + 2] += rad.z;
+    if (O.counters) atomicAdd(&O.counters->secondary_rays, traced);
 }
 
 // integrate.rs:16-20 + img.rs:56-67: in-order sum of the samples, weight, quantise, store.
@@ -1313,7 +1528,7 @@ __global__ void k_fp64_peak(int iters, double* sink) {
 }
 
 // ------------------------------------------------------------------ launch wrappers (called from lgb_api.cu)
-bool render_fused(uint32_t spp) { return spp >= 1 && spp <= 256; }
+bool render_fused(uint32_t spp) { return spp >= 1 && spp <= 256; }      // and !S.general: see launch_render
 
 // `ev` (optional): kRenderEvents events recorded around the phases: start | primary | setup | anchor shadow rays |
 // pretest + remaining shadow rays | shade | resolve.
@@ -1370,7 +1585,16 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
         if (which == kQueueA) mark(3);
     }
     mark(4);
-    if (render_fused(W.spp)) {          // whole pixels per block: shade and resolve in one kernel, no radiance buffer
+    if (S.general) {                    // materials beyond plastic: every BSDF in k_shade, then the specular ray trees, then the film
+        if (inst) k_shade<true, false, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, false, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+        if (S.specular && S.recursion > 0) {
+            const unsigned sb = (unsigned)((total + 127) / 128);
+            if (inst) k_secondary<true><<<sb, 128, 0, stream>>>(S, C, sh, W, O, V); else k_secondary<false><<<sb, 128, 0, stream>>>(S, C, sh, W, O, V);
+        }
+        mark(5);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
+    } else if (render_fused(W.spp)) {   // whole pixels per block: shade and resolve in one kernel, no radiance buffer
         const unsigned fb = (unsigned)((W.n_pixels + (256u / W.spp) - 1) / (256u / W.spp));
         if (inst) k_shade<true, true><<<fb, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, true><<<fb, 256, 0, stream>>>(S, C, sh, W, O, V);
         mark(5);

@@ -37,7 +37,10 @@ struct DevSpace {
 //   tri        3 x float4 {p0, id} {p1, material} {p2, normals_index|kNoNormals}
 //   tri_nrm    9 floats per entry (indexed by the value stored in tri[3i+2].w)
 //   rank       8 x prim_count u32: reference traversal position per direction octant (exact-t ties only)
-//   materials  8 doubles {kd.xyz, roughness, ks.xyz, flags(bit0 diffuse lobe, bit1 glossy lobe)}
+//   materials  kMatStride doubles {c0.xyz, p0, c1.xyz, flags, p1, p2, -, -}: the record of include/lasgun_b200.h (c0 = kd | eta | kr,
+//              c1 = ks | k | kt, p0 = roughness | sigma | u_roughness | eta) with flags = bit0 diffuse lobe, bit1 glossy lobe,
+//              bit2 a material the plastic fast path does not evaluate (Oren-Nayar, metal, glass, mirror), bit3 specular lobes
+//              (glass, mirror: Whitted recursion), kind << 8; p1 = v_roughness (metal) | Oren-Nayar A, p2 = Oren-Nayar B
 //   lights     9 doubles {pos, intensity, falloff}
 struct DevScene {
     const float4* nodes;
@@ -63,6 +66,9 @@ struct DevScene {
     uint32_t instanced;
     uint32_t n_lights;
     uint32_t n_nodes;
+    uint32_t general;     // some material carries flag bit2: the GENERAL shade variant runs
+    uint32_t specular;    // some material carries flag bit3: k_secondary follows the specular rays
+    uint32_t recursion;   // scene.recursion (scene.rs:60), depth limit of integrate.rs:69
     float err_abs;        // absolute coordinate error bound of an f32 ray against this scene (see lgb_api.cu)
 };
 
@@ -106,6 +112,7 @@ struct DevCounters {
     unsigned long long exact[3];     // f64 reference-arithmetic tests by primitive type
     unsigned long long p_node_tests, p_filter[3], p_exact[3];   // the share of the primary-ray kernels in the three counters above
     unsigned long long beam_node_tests;                         // of those: node fetches of the pixel beams (k_beam)
+    unsigned long long secondary_rays;                          // rays k_secondary traced
     unsigned int stack_overflow;
     unsigned int pad;
 };
@@ -136,9 +143,14 @@ struct DevWave {
     float* beam_bound;               // per pixel slot: the list is complete for rays whose closest hit is not beyond it
     uint32_t* fallback_list;         // sample slots of such pixels (aliases the shadow queues, which are not yet in use)
     uint32_t* fallback_count;
+    uint32_t* sec_list;              // sample slots whose closest hit has specular lobes (aliases the shadow queues, drained by then)
+    uint32_t* sec_count;
 };
 constexpr int kQueueA = 0, kQueueB = 1, kQueueC = 2;
-constexpr size_t kWaveCtrBytes = 8 + 4 * (size_t)LGB_MAX_LIGHTS * 3 * 2 + 8;      // + tie_count, fallback_count
+constexpr size_t kWaveCtrBytes = 8 + 4 * (size_t)LGB_MAX_LIGHTS * 3 * 2 + 16;     // + tie_count, fallback_count, sec_count, pad
+constexpr int kMatStride = 12;
+constexpr uint32_t kMatDiffuse = 1u, kMatGlossy = 2u, kMatGeneral = 4u, kMatSpecular = 8u;
+constexpr uint32_t kMaxRecursion = 12;         // depth of the per-ray stack k_secondary keeps (lgb_scene_create rejects deeper scenes)
 constexpr uint32_t kTieCap = 1u << 20;
 constexpr int kBeamList = 48;                  // leaves a pixel beam may reach before the pixel falls back to per-ray traversal
 constexpr uint32_t kBeamOverflow = 0xFFFFFFFFu;

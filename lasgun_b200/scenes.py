@@ -26,8 +26,9 @@ def splitmix64_uniform(seed: int, count: int) -> np.ndarray:
     return (z >> np.uint64(11)).astype(np.float64) * (2.0 ** -53)
 
 
-def mesh_grid(n: int, s: float) -> ObjData:
-    """MESH(N, S) of SURVEY §8d: bumpy sphere, (N+1)^2 vertices (seam duplicated), 2*N^2 triangles."""
+def mesh_grid(n: int, s: float, smooth: bool = False) -> ObjData:
+    """MESH(N, S) of SURVEY §8d: bumpy sphere, (N+1)^2 vertices (seam duplicated), 2*N^2 triangles.
+    smooth: also one vertex normal per vertex (the radial direction, f32), as an OBJ with `vn` records would carry."""
     i = np.arange(n + 1, dtype=np.float64)
     u = 2.0 * math.pi * i / n
     v = math.pi * i / n
@@ -43,6 +44,9 @@ def mesh_grid(n: int, s: float) -> ObjData:
     faces = np.empty((2 * n * n, 3), np.uint32)
     faces[0::2] = np.stack([a, b, c], axis=-1)
     faces[1::2] = np.stack([a, c, d], axis=-1)
+    if smooth:
+        nrm = pos.reshape(-1, 3) / np.linalg.norm(pos.reshape(-1, 3), axis=1, keepdims=True)
+        return ObjData(pos32, faces, nrm.astype(np.float32), faces.copy())
     return ObjData(pos32, faces)
 
 
@@ -271,6 +275,74 @@ def nested_groups(res=(320, 240), supersampling=1, transformed_root=False, mesh_
     return scene, tuple(res)
 
 
+def simplereflect(supersampling=2, res=512, recursion=4):
+    """The reference's src/examples/simplereflect.rs: the `simple` layout in glass and mirror, Whitted depth 4
+    (star_mesh() stands in for the Git-LFS-only smstdodeca.obj, as in `simple`)."""
+    scene = Scene()
+    scene.set_ambient_light([0.2, 0.2, 0.2])
+    scene.set_radial_background([0.93, 0.87, 0.36], [0.94, 0.6, 0.1], 0.5)
+    scene.set_max_recursion_depth(recursion)
+    camera = scene.set_perspective_camera(45.0)
+    camera.look_at([25.0, 0.0, 800.0], [25.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+    camera.set_supersampling(supersampling)
+    mat0 = Material.glass([0.7, 1.0, 0.7], [0.5, 0.7, 0.5], 1.333)
+    mat1 = Material.mirror([0.5, 0.5, 0.5])
+    mat2 = Material.glass([1.0, 0.6, 0.1], [0.7, 0.7, 1.0], 1.75)
+    mat3 = Material.glass([0.7, 0.6, 1.0], [0.5, 0.4, 0.8], 1.5)
+    mesh = scene.add_obj(star_mesh())
+    scene.add_point_light([-100.0, 150.0, 400.0], [0.9, 0.9, 0.9], [1.0, 0.0, 0.0])
+    scene.add_point_light([400.0, 100.0, 150.0], [0.7, 0.0, 0.7], [1.0, 0.0, 0.0])
+    scene.root.add_sphere([0.0, 0.0, -400.0], 100.0, mat0)
+    scene.root.add_sphere([200.0, 50.0, -100.0], 150.0, mat0)
+    scene.root.add_sphere([0.0, -1200.0, -500.0], 1000.0, mat1)
+    scene.root.add_sphere([-100.0, 25.0, -300.0], 50.0, mat2)
+    scene.root.add_sphere([0.0, 100.0, -250.0], 25.0, mat0)
+    scene.root.add_cube([-200.0, -125.0, 0.0], 100.0, mat3)
+    scene.root.add_obj_of(mesh, mat2)
+    return scene, (res, res)
+
+
+def materials(res=(384, 288), supersampling=1, recursion=3, grouped=False):
+    """Every `Material` variant (material/mod.rs:19-46) on every shape: Oren-Nayar matte, isotropic and anisotropic metal (the
+    parameters of src/examples/playground.rs:15 and simplecows.rs:18 among them), glass, mirror, plastic; a smooth mesh (vertex
+    normals: the shading frame of bsdf.rs:33-36 is not orthonormal there) in metal and in glass.  grouped: the specular objects sit
+    in a rotated, scaled group, so the rays below them cross instance transforms."""
+    scene = Scene()
+    scene.set_ambient_light([0.15, 0.15, 0.15])
+    scene.set_radial_background([0.35, 0.5, 0.8], [0.9, 0.85, 0.7], 0.7)
+    scene.set_max_recursion_depth(recursion)
+    camera = scene.set_perspective_camera(48.0)
+    camera.look_at([0.5, 3.2, 11.0], [0.0, 0.6, 0.0], [0.0, 1.0, 0.0])
+    camera.set_supersampling(supersampling)
+    scene.add_point_light([6.0, 9.0, 8.0], [0.8, 0.8, 0.8], [1.0, 0.0, 0.0])
+    scene.add_point_light([-7.0, 6.0, 4.0], [0.5, 0.45, 0.4], [1.0, 0.02, 0.0])
+    smooth = scene.add_obj(mesh_grid(20, 1.0, smooth=True))
+    flat = scene.add_obj(star_mesh(0.7, 1.0))
+    r = scene.root
+    r.add_box([-9.0, -1.2, -9.0], [9.0, -1.0, 9.0], Material.matte([0.7, 0.65, 0.6], 25.0))                 # Oren-Nayar floor
+    r.add_box([-9.0, -1.0, -9.2], [9.0, 6.0, -9.0], Material.mirror([0.85, 0.85, 0.9]))                      # mirror back wall
+    r.add_sphere([-4.0, 0.0, 0.5], 1.0, Material.metal([0.9, 0.1, 0.9], [0.7, 1.0, 0.7], 0.25, 0.25))        # playground.rs:15
+    r.add_sphere([-1.6, 0.0, 1.5], 1.0, Material.metal([0.2, 0.9, 1.1], [3.9, 2.4, 2.2], 0.08, 0.45))        # anisotropic
+    r.add_cube([3.2, -1.0, -1.5], 1.6, Material.metal([0.0, 0.0, 0.0], [0.7, 0.7, 0.7], 0.5, 0.5))           # simplecows.rs:18
+    r.add_sphere([4.2, 0.1, 2.6], 0.9, Material.matte([0.9, 0.3, 0.2], 60.0))
+    r.add_sphere([-3.0, -0.5, 3.8], 0.5, Material.plastic([0.2, 0.7, 0.3], [0.5, 0.5, 0.5], 0.2))
+    g = Aggregate() if grouped else r
+    if grouped:
+        g.scale(1.0, 1.15, 0.9); g.rotate_y(25.0); g.translate([0.2, 0.15, 0.3])
+    g.add_sphere([1.0, 0.2, 2.2], 1.2, Material.glass([1.0, 0.7, 1.0], [0.7, 1.0, 0.7], 1.25))               # cornell.rs:22
+    g.add_cube([-0.6, -1.0, 3.6], 0.9, Material.glass([0.7, 0.6, 1.0], [0.8, 0.8, 0.8], 1.333))              # spooky.rs:22
+    g.add_sphere([2.6, -0.4, 4.4], 0.6, Material.mirror([0.5, 0.5, 0.5]))
+    g.add_sphere([-2.2, 2.2, -2.0], 0.9, Material.glass([0.0, 0.0, 0.0], [0.9, 0.9, 0.9], 1.5))              # kr = 0: transmission lobe only
+    g.add_sphere([0.2, 2.6, -3.0], 0.8, Material.glass([0.9, 0.9, 0.9], [0.0, 0.0, 0.0], 1.5))               # kt = 0: reflection lobe only
+    m1 = Aggregate(); m1.translate([2.3, 2.3, -1.0]); m1.add_obj_of(smooth, Material.metal([0.3, 0.5, 0.9], [2.5, 2.0, 1.6], 0.3, 0.12))
+    m2 = Aggregate(); m2.scale(0.9, 0.9, 0.9); m2.translate([-0.4, 1.9, 0.6]); m2.add_obj_of(smooth, Material.glass([0.8, 0.8, 0.8], [0.9, 0.9, 0.9], 1.4))
+    m3 = Aggregate(); m3.translate([-4.6, 1.9, -1.5]); m3.add_obj_of(flat, Material.matte([0.4, 0.5, 0.9], 35.0))
+    g.add_group(m1); g.add_group(m2); g.add_group(m3)
+    if grouped:
+        r.add_group(g)
+    return scene, tuple(res)
+
+
 CONFIGS = {
     "simple": lambda: simple("b", 2),
     "simple_nomesh": lambda: simple("a", 2),
@@ -279,4 +351,6 @@ CONFIGS = {
     "cornell": cornell,
     "spheres1m": spheres1m,
     "mixed4k": mixed4k,
+    "simplereflect": simplereflect,
+    "materials": materials,
 }

@@ -213,9 +213,14 @@ static Bounds transform_bounds(const Transform& t, const Bounds& b) {
 }
 
 // ---------------------------------------------------------------- material
-// material/mod.rs:4-46.  Only matte(sigma == 0) and plastic are on the path.
-enum MatKind { MAT_MATTE = 0, MAT_PLASTIC = 1 };
-struct Material { int kind; V3 kd, ks; double roughness; /* matte: roughness = sigma */ };
+// material/mod.rs:4-46.  One record for the five variants:
+//   matte   kd, roughness = sigma (degrees, clamped to [0, 90] by matte.rs:15)
+//   plastic kd, ks, roughness
+//   metal   kd = eta, ks = k, roughness = u_roughness, roughness2 = v_roughness (metal.rs:13-15)
+//   glass   kd = kr, ks = kt, roughness = eta (mod.rs:36-41: the two glass roughnesses are always 0)
+//   mirror  kd = kr
+enum MatKind { MAT_MATTE = 0, MAT_PLASTIC = 1, MAT_METAL = 2, MAT_GLASS = 3, MAT_MIRROR = 4 };
+struct Material { int kind; V3 kd, ks; double roughness; double roughness2 = 0.0; };
 static Material mat_default() { return Material{MAT_MATTE, v3(0.5, 0.5, 0.5), v3(0, 0, 0), 0.0}; }   // mod.rs:15-17
 
 // ---------------------------------------------------------------- intersection record
@@ -283,7 +288,7 @@ static RayIsect inverse_transform_isect(const Transform& t, const RayIsect& i) {
 // ---------------------------------------------------------------- counters
 struct Counters {
     uint64_t node_tests = 0, sphere_tests = 0, cuboid_tests = 0, tri_tests = 0;
-    uint64_t primary = 0, primary_hits = 0, shadow = 0, shadow_occluded = 0, exact_ties = 0;
+    uint64_t primary = 0, primary_hits = 0, shadow = 0, shadow_occluded = 0, exact_ties = 0, secondary = 0;
     void add(const Counters& o) {
         node_tests += o.node_tests; sphere_tests += o.sphere_tests; cuboid_tests += o.cuboid_tests;
         tri_tests += o.tri_tests; primary += o.primary; primary_hits += o.primary_hits;
@@ -892,15 +897,46 @@ struct Distribution {
     }
     double g(V3 wo, V3 wi) const { return 1.0 / (1.0 + lambda(wo) + lambda(wi)); }
 };
+// core/bxdf/fresnel.rs:68-90
+static V3 conductor(double cos_theta_i, V3 eta_i, V3 eta_t, V3 k) {
+    cos_theta_i = rmin(rmax(cos_theta_i, -1.0), 1.0);
+    V3 eta = v3(eta_t.x / eta_i.x, eta_t.y / eta_i.y, eta_t.z / eta_i.z);
+    V3 etak = v3(k.x / eta_i.x, k.y / eta_i.y, k.z / eta_i.z);
+    double cos2 = cos_theta_i * cos_theta_i;
+    double sin2 = 1.0 - cos2;
+    V3 eta2 = mul_el(eta, eta), etak2 = mul_el(etak, etak);
+    auto chan = [&](double e2, double ek2) {
+        double t0 = e2 - ek2 - sin2;
+        double a2plusb2 = std::sqrt(t0 * t0 + 4.0 * (e2 * ek2));
+        double t1 = a2plusb2 + cos2;
+        double a = std::sqrt(0.5 * (a2plusb2 + t0));
+        double t2 = 2.0 * cos_theta_i * a;
+        double rs = (t1 - t2) / (t1 + t2);
+        double t3 = cos2 * a2plusb2 + sin2 * sin2;
+        double t4 = t2 * sin2;
+        double rp = rs * (t3 - t4) / (t3 + t4);
+        return 0.5 * (rp + rs);
+    };
+    return v3(chan(eta2.x, etak2.x), chan(eta2.y, etak2.y), chan(eta2.z, etak2.z));
+}
+// core/bxdf/fresnel.rs:7-33
+enum SubstKind { SUB_DIELECTRIC = 0, SUB_CONDUCTOR = 1, SUB_NOOP = 2 };
+struct Substance {
+    int kind = SUB_NOOP; double eta_i = 1.0, eta_t = 1.0; V3 c_eta_i, c_eta_t, c_k;
+    V3 evaluate(double cos_theta_i) const {
+        if (kind == SUB_DIELECTRIC) { double F = dielectric(cos_theta_i, eta_i, eta_t); return v3(F, F, F); }
+        if (kind == SUB_CONDUCTOR) return conductor(cos_theta_i, c_eta_i, c_eta_t, c_k);
+        return v3(1.0, 1.0, 1.0);
+    }
+};
 // microfacet.rs:101-115
-static V3 microfacet_f(V3 r, const Distribution& dist, V3 wo, V3 wi) {
+static V3 microfacet_f(V3 r, const Substance& sub, const Distribution& dist, V3 wo, V3 wi) {
     double cos_o = std::fabs(wo.z), cos_i = std::fabs(wi.z);
     V3 wh = wi + wo;
     if (cos_i == 0.0 || cos_o == 0.0) return v3(0, 0, 0);
     if (wh.x == 0.0 && wh.y == 0.0 && wh.z == 0.0) return v3(0, 0, 0);
     wh = normalize(wh);
-    double F = dielectric(dot(wi, wh), 1.0, 1.5);
-    V3 spectrum = v3(F, F, F);
+    V3 spectrum = sub.evaluate(dot(wi, wh));
     return mul_el(r * dist.d(wh) * dist.g(wo, wi), spectrum) / (4.0 * cos_i * cos_o);
 }
 
@@ -918,35 +954,141 @@ static SurfaceInteraction surface_from(const Ray& ray, const RayIsect& isect) {
     si.s_dpdu = normalize(isect.s_dpdu); si.s_dpdv = normalize(isect.s_dpdv);
     return si;
 }
-// interaction/bsdf.rs:29-46, 73-92, 155-161 + material/{plastic.rs:20-37, matte.rs:18-26}
-struct BSDF {
-    V3 ng, ns, ss, ts;
-    bool has_diffuse = false, has_glossy = false;
-    V3 kd, ks; Distribution dist;
-    V3 f(V3 wo, V3 wi) const {
-        bool reflect = dot(wi, ng) * dot(wo, ng) > 0.0;
-        V3 wo_l = v3(dot(wo, ss), dot(wo, ts), dot(wo, ns));
-        V3 wi_l = v3(dot(wi, ss), dot(wi, ts), dot(wi, ns));
-        if (wo_l.z == 0.0) return v3(0, 0, 0);
-        V3 f = v3(0, 0, 0);
-        if (has_diffuse && reflect) f = f + kd * FRAC_1_PI;             // diffuse.rs:14
-        if (has_glossy && reflect) f = f + microfacet_f(ks, dist, wo_l, wi_l);
-        return f;
+// bxdf/mod.rs:18-31
+enum : uint32_t { BX_REFLECTION = 1, BX_TRANSMISSION = 2, BX_DIFFUSE = 4, BX_GLOSSY = 8, BX_SPECULAR = 16 };
+enum BxKind { BX_QUICK_DIFFUSE, BX_OREN_NAYAR, BX_MICROFACET_REFLECTION, BX_SPECULAR_REFLECTION, BX_SPECULAR_TRANSMISSION };
+struct LightSample { V3 spectrum, wi; double pdf; };
+// bxdf/mod.rs:164-174: refract in shading coordinates
+static bool refract(V3 wi, V3 n, double eta, V3& out) {
+    double cos_i = dot(n, wi);
+    double sin2_i = rmax(1.0 - cos_i * cos_i, 0.0);
+    double sin2_t = eta * eta * sin2_i;
+    if (sin2_t >= 1.0) return false;
+    double cos_t = std::sqrt(1.0 - sin2_t);
+    out = (eta * -1.0) * wi + (eta * cos_i - cos_t) * n;
+    return true;
+}
+struct BxDF {
+    int kind; V3 r; double a = 0, b = 0; Substance sub; Distribution dist{1, 1}; double eta_a = 1, eta_b = 1;
+    uint32_t t() const {                                                  // mod.rs:141-152
+        switch (kind) {
+            case BX_QUICK_DIFFUSE: case BX_OREN_NAYAR: return BX_REFLECTION | BX_DIFFUSE;
+            case BX_MICROFACET_REFLECTION: return BX_REFLECTION | BX_GLOSSY;
+            case BX_SPECULAR_REFLECTION: return BX_REFLECTION | BX_SPECULAR;
+            default: return BX_TRANSMISSION | BX_SPECULAR;
+        }
+    }
+    bool matches(uint32_t flags) const { return (t() & flags) == t(); }  // mod.rs:154-157
+    bool has_t(uint32_t flags) const { return (t() & flags) != 0; }      // mod.rs:159-161
+    V3 f(V3 wo, V3 wi) const {                                            // mod.rs:165-175
+        switch (kind) {
+            case BX_QUICK_DIFFUSE: return r * FRAC_1_PI;                  // diffuse.rs:14
+            case BX_OREN_NAYAR: {                                         // diffuse.rs:36-56
+                double sin_i = sin_theta(wi), sin_o = sin_theta(wo);
+                double max_cos = 0.0;
+                if (sin_i > 1e-4 && sin_o > 1e-4) {
+                    double d_cos = cos_phi(wi) * cos_phi(wo) + sin_phi(wi) * sin_phi(wo);
+                    max_cos = rmax(d_cos, 0.0);
+                }
+                double sin_alpha, tan_beta;
+                if (std::fabs(wi.z) > std::fabs(wo.z)) { sin_alpha = sin_o; tan_beta = sin_i / std::fabs(wi.z); }
+                else { sin_alpha = sin_i; tan_beta = sin_o / std::fabs(wo.z); }
+                return r * FRAC_1_PI * (a + b * max_cos * sin_alpha * tan_beta);
+            }
+            case BX_MICROFACET_REFLECTION: return microfacet_f(r, sub, dist, wo, wi);
+            default: return v3(0, 0, 0);                                  // specular lobes scatter only through sample_f
+        }
+    }
+    // specular.rs:17-25, 44-66 (the only sample_f variants a Whitted path reaches: integrate.rs:85,110)
+    LightSample sample_f(V3 wo) const {
+        if (kind == BX_SPECULAR_REFLECTION) {
+            V3 wi = v3(-wo.x, -wo.y, wo.z);
+            V3 spectrum = mul_el(sub.evaluate(wi.z), r) / std::fabs(wi.z);
+            return LightSample{spectrum, wi, 1.0};
+        }
+        bool entering = wo.z > 0.0;
+        double eta_i = entering ? eta_a : eta_b, eta_t = entering ? eta_b : eta_a;
+        V3 wi;
+        if (!refract(wo, v3(0.0, 0.0, 1.0), eta_i / eta_t, wi)) return LightSample{v3(0, 0, 0), v3(0, 0, 0), 0.0};
+        V3 spectrum = mul_el(r, v3(1.0, 1.0, 1.0) - sub.evaluate(wi.z)) / std::fabs(wi.z);
+        return LightSample{spectrum, wi, 1.0};
     }
 };
+static BxDF oren_nayar(V3 r, double sigma_deg) {                          // diffuse.rs:28-34
+    double sigma = deg2rad(sigma_deg);
+    double sigma2 = sigma * sigma;
+    BxDF b; b.kind = BX_OREN_NAYAR; b.r = r;
+    b.a = 1.0 - (sigma2 / 2.0 * (sigma2 + 0.33));
+    b.b = 0.45 * sigma2 / (sigma2 + 0.09);
+    return b;
+}
+// interaction/bsdf.rs:29-46, 73-92, 94-140, 155-175 + material/{matte,plastic,metal,glass,mirror}.rs
+struct BSDF {
+    V3 ng, ns, ss, ts;
+    BxDF bx[2]; int n = 0;
+    void add(const BxDF& b) { bx[n++] = b; }
+    V3 to_local(V3 v) const { return v3(dot(v, ss), dot(v, ts), dot(v, ns)); }
+    V3 to_world(V3 v) const {
+        return v3(ss.x * v.x + ts.x * v.y + ns.x * v.z, ss.y * v.x + ts.y * v.y + ns.y * v.z, ss.z * v.x + ts.z * v.y + ns.z * v.z);
+    }
+    V3 f(V3 wo, V3 wi) const {
+        bool reflect = dot(wi, ng) * dot(wo, ng) > 0.0;
+        V3 wo_l = to_local(wo), wi_l = to_local(wi);
+        if (wo_l.z == 0.0) return v3(0, 0, 0);
+        V3 f = v3(0, 0, 0);
+        for (int i = 0; i < n; i++)
+            if ((reflect && bx[i].has_t(BX_REFLECTION)) || (!reflect && bx[i].has_t(BX_TRANSMISSION))) f = f + bx[i].f(wo_l, wi_l);
+        return f;
+    }
+    // bsdf.rs:94-140 with sample = (0.5, 0.5) and SPECULAR flags: at most one lobe of a material matches either flag set
+    // (glass: one reflection + one transmission lobe), so comp = 0 and pdf = f_sample.pdf / 1.
+    LightSample sample_f(V3 wo, uint32_t flags) const {
+        int matching = 0; const BxDF* pick = nullptr;
+        for (int i = 0; i < n; i++) if (bx[i].matches(flags)) { if (!pick) pick = &bx[i]; matching++; }
+        if (matching == 0) return LightSample{v3(0, 0, 0), v3(0, 0, 0), 0.0};
+        V3 wo_l = to_local(wo);
+        if (wo_l.z == 0.0) return LightSample{v3(0, 0, 0), v3(0, 0, 0), 0.0};
+        LightSample fs = pick->sample_f(wo_l);
+        if (fs.pdf == 0.0) return fs;
+        V3 wi = to_world(fs.wi);
+        auto clamp01 = [](double v) { return rmin(rmax(v, 0.0), 1.0); };
+        V3 spectrum = v3(clamp01(fs.spectrum.x), clamp01(fs.spectrum.y), clamp01(fs.spectrum.z));
+        return LightSample{spectrum, wi, fs.pdf / (double)matching};
+    }
+};
+static inline bool is_zero(V3 c) { return c.x == 0.0 && c.y == 0.0 && c.z == 0.0; }
 static bool scattering(const Material& m, const SurfaceInteraction& si, BSDF& b) {
-    b.ng = si.ng; b.ns = si.ns; b.ss = si.s_dpdu; b.ts = cross(si.ns, b.ss);
-    if (m.kind == MAT_PLASTIC) {
-        b.has_diffuse = !(m.kd.x == 0.0 && m.kd.y == 0.0 && m.kd.z == 0.0);
-        b.has_glossy = !(m.ks.x == 0.0 && m.ks.y == 0.0 && m.ks.z == 0.0);
-        b.kd = m.kd; b.ks = m.ks; b.dist = Distribution{m.roughness, m.roughness};
+    b.ng = si.ng; b.ns = si.ns; b.ss = si.s_dpdu; b.ts = cross(si.ns, b.ss); b.n = 0;
+    BxDF x;
+    switch (m.kind) {
+    case MAT_PLASTIC:                                                      // plastic.rs:20-37
+        if (!is_zero(m.kd)) { x.kind = BX_QUICK_DIFFUSE; x.r = m.kd; b.add(x); }
+        if (!is_zero(m.ks)) {
+            x = BxDF(); x.kind = BX_MICROFACET_REFLECTION; x.r = m.ks; x.sub.kind = SUB_DIELECTRIC; x.sub.eta_i = 1.0; x.sub.eta_t = 1.5;
+            x.dist = Distribution{m.roughness, m.roughness}; b.add(x);
+        }
+        return true;
+    case MAT_MATTE:                                                        // matte.rs:18-26
+        if (m.roughness == 0.0) { x.kind = BX_QUICK_DIFFUSE; x.r = m.kd; b.add(x); }
+        else b.add(oren_nayar(m.kd, m.roughness));
+        return true;
+    case MAT_METAL:                                                        // metal.rs:17-26
+        x.kind = BX_MICROFACET_REFLECTION; x.r = v3(1.0, 1.0, 1.0);
+        x.sub.kind = SUB_CONDUCTOR; x.sub.c_eta_i = v3(1.0, 1.0, 1.0); x.sub.c_eta_t = m.kd; x.sub.c_k = m.ks;
+        x.dist = Distribution{m.roughness, m.roughness2}; b.add(x);
+        return true;
+    case MAT_GLASS:                                                        // glass.rs:33-56 (distribution = None)
+        if (!is_zero(m.kd)) { x.kind = BX_SPECULAR_REFLECTION; x.r = m.kd; x.sub.kind = SUB_DIELECTRIC; x.sub.eta_i = 1.0; x.sub.eta_t = m.roughness; b.add(x); }
+        if (!is_zero(m.ks)) {
+            x = BxDF(); x.kind = BX_SPECULAR_TRANSMISSION; x.r = m.ks; x.eta_a = 1.0; x.eta_b = m.roughness;
+            x.sub.kind = SUB_DIELECTRIC; x.sub.eta_i = 1.0; x.sub.eta_t = m.roughness; b.add(x);
+        }
+        return true;
+    case MAT_MIRROR:                                                       // mirror.rs:14-16
+        x.kind = BX_SPECULAR_REFLECTION; x.r = m.kd; x.sub.kind = SUB_NOOP; b.add(x);
         return true;
     }
-    if (m.kind == MAT_MATTE && m.roughness == 0.0) {   // quick_diffuse is added unconditionally
-        b.has_diffuse = true; b.has_glossy = false; b.kd = m.kd; b.ks = v3(0, 0, 0); b.dist = Distribution{1, 1};
-        return true;
-    }
-    return false;   // Oren-Nayar / metal / glass / mirror: outside the hot path
+    return false;
 }
 static inline double lerp(double t, double a, double b) { return a * (1.0 - t) + b * t; }    // space/mod.rs:28-30
 // material/background.rs:25-34  (powf(2.) folded to x*x, as LLVM does)
@@ -958,15 +1100,15 @@ static V3 background_bg(const Background& bg, V3 d) {
 
 struct SampleAOV { uint32_t prim_id; double t; uint32_t occl_mask; bool unsupported; };
 
-// integrate/integrate.rs:23-80 (depth recursion returns zero for matte/plastic: bsdf.rs:94-96)
-static V3 li(const Accel& acc, const Ray& ray, SampleAOV* aov) {
+// integrate/integrate.rs:23-132
+static V3 li(const Accel& acc, const Ray& ray, uint32_t depth, SampleAOV* aov) {
     const Scene& sc = *acc.scene;
-    if (g_cnt) g_cnt->primary++;
+    if (g_cnt) { if (depth == 0) g_cnt->primary++; else g_cnt->secondary++; }
     RayIsect isect = isect_default();
     const Primitive* shape = acc.root->intersect(ray, isect);
     if (aov) { aov->prim_id = 0xFFFFFFFFu; aov->t = INF; aov->occl_mask = 0; aov->unsupported = false; }
     if (!shape) return background_bg(sc.background, normalize(ray.d));
-    if (g_cnt) g_cnt->primary_hits++;
+    if (g_cnt && depth == 0) g_cnt->primary_hits++;
     Material material;
     if (!shape->material(material)) material = isect.material;
     if (aov) { aov->prim_id = isect.prim_id; aov->t = isect.t; }
@@ -994,9 +1136,27 @@ static V3 li(const Accel& acc, const Ray& ray, SampleAOV* aov) {
         output = output + (mul_el(PI * light.intensity, f) * wi_dot_n / f_att);
     }
     output = output + mul_el(sc.ambient, bsdf.f(wo, n));
-    // integrate.rs:69-79: specular_reflect/transmit -> BSDF::sample_f -> zero matching components -> zero.
-    V3 zero = v3(0, 0, 0);
-    return output + zero + zero;
+    V3 refracted = v3(0, 0, 0), reflected = v3(0, 0, 0);
+    if (depth < sc.recursion) {                                           // integrate.rs:69-77
+        {   // specular_transmit, integrate.rs:108-132
+            LightSample s = bsdf.sample_f(wo, BX_TRANSMISSION | BX_SPECULAR);
+            if (!(s.pdf <= 0.0 || is_zero(s.spectrum) || std::fabs(dot(s.wi, n)) == 0.0)) {
+                Ray r = ray_new(si.p - si.p_err, s.wi);
+                V3 l = li(acc, r, depth + 1, nullptr);
+                refracted = mul_el(s.spectrum, l) * std::fabs(dot(s.wi, n)) / s.pdf;
+            }
+        }
+        {   // specular_reflect, integrate.rs:82-106
+            LightSample s = bsdf.sample_f(wo, BX_REFLECTION | BX_SPECULAR);
+            if (!(s.pdf <= 0.0 || is_zero(s.spectrum) || dot(s.wi, n) <= 0.0)) {
+                V3 wr = -1.0 * wo + 2.0 * dot(wo, n) * n;                 // bxdf::util::reflect, mod.rs:160-162
+                Ray r = ray_new(si.p + si.p_err, wr);
+                V3 l = li(acc, r, depth + 1, nullptr);
+                reflected = mul_el(s.spectrum, l);
+            }
+        }
+    }
+    return output + reflected + refracted;                                // integrate.rs:79
 }
 
 // img.rs:65-67
@@ -1047,7 +1207,7 @@ static void capture_subset(const Accel& acc, size_t k, size_t n, uint32_t w, uin
         for (size_t s = 0; s < spp; s++) {     // integrate.rs:16-20
             SampleAOV aov;
             bool want = aov_id || aov_t || aov_occl || unsupported;
-            V3 c = li(acc, rays[s], want ? &aov : nullptr);
+            V3 c = li(acc, rays[s], 0, want ? &aov : nullptr);
             if (want && aov.unsupported && unsupported) unsupported->store(1);
             if (aov_id) aov_id[off * spp + s] = aov.prim_id;
             if (aov_t) aov_t[off * spp + s] = aov.t;
@@ -1074,9 +1234,10 @@ struct orc_counters {
 
 void* orc_scene_new() { return new Scene(); }
 void orc_scene_free(void* s) { delete (Scene*)s; }
-static Material mk_mat(int kind, const double* kd, const double* ks, double rough) {
-    return Material{kind, v3(kd[0], kd[1], kd[2]), v3(ks[0], ks[1], ks[2]), rough};
+static Material mk_mat(int kind, const double* kd, const double* ks, double rough, double rough2) {
+    return Material{kind, v3(kd[0], kd[1], kd[2]), v3(ks[0], ks[1], ks[2]), rough, rough2};
 }
+void orc_set_max_recursion_depth(void* s, uint32_t depth) { ((Scene*)s)->recursion = depth; }          // scene.rs
 void orc_set_perspective_camera(void* s, double fov) { ((Scene*)s)->camera.reset(true, fov); }
 void orc_set_orthographic_camera(void* s, double height) { ((Scene*)s)->camera.reset(false, height); }
 void orc_look_at(void* s, const double* o, const double* l, const double* u) {
@@ -1101,27 +1262,27 @@ int orc_add_mesh(void* s, const float* pos, uint64_t nv, const uint32_t* vi, uin
     return (int)sc->meshes.size() - 1;
 }
 int orc_agg_new(void* s) { Scene* sc = (Scene*)s; sc->aggs.emplace_back(); return (int)sc->aggs.size() - 1; }
-void orc_agg_add_sphere(void* s, int ag, const double* c, double r, int kind, const double* kd, const double* ks, double rough) {
-    ((Scene*)s)->aggs[ag].contents.push_back(SceneNode{N_SPHERE, v3(c[0], c[1], c[2]), v3(0, 0, 0), r, mk_mat(kind, kd, ks, rough), true, -1});
+void orc_agg_add_sphere(void* s, int ag, const double* c, double r, int kind, const double* kd, const double* ks, double rough, double rough2) {
+    ((Scene*)s)->aggs[ag].contents.push_back(SceneNode{N_SPHERE, v3(c[0], c[1], c[2]), v3(0, 0, 0), r, mk_mat(kind, kd, ks, rough, rough2), true, -1});
 }
 void orc_agg_add_spheres(void* s, int ag, uint64_t n, const double* c, const double* r, int nmat, const int* kinds,
-                         const double* kd, const double* ks, const double* rough, const int* mat_index) {
+                         const double* kd, const double* ks, const double* rough, const double* rough2, const int* mat_index) {
     Aggregate& a = ((Scene*)s)->aggs[ag];
     a.contents.reserve(a.contents.size() + n);
     for (uint64_t i = 0; i < n; i++) {
         int m = mat_index[i]; (void)nmat;
         a.contents.push_back(SceneNode{N_SPHERE, v3(c[3 * i], c[3 * i + 1], c[3 * i + 2]), v3(0, 0, 0), r[i],
-                                       mk_mat(kinds[m], kd + 3 * m, ks + 3 * m, rough[m]), true, -1});
+                                       mk_mat(kinds[m], kd + 3 * m, ks + 3 * m, rough[m], rough2[m]), true, -1});
     }
 }
-void orc_agg_add_cube(void* s, int ag, const double* o, double dim, int kind, const double* kd, const double* ks, double rough) {
-    ((Scene*)s)->aggs[ag].contents.push_back(SceneNode{N_CUBE, v3(o[0], o[1], o[2]), v3(0, 0, 0), dim, mk_mat(kind, kd, ks, rough), true, -1});
+void orc_agg_add_cube(void* s, int ag, const double* o, double dim, int kind, const double* kd, const double* ks, double rough, double rough2) {
+    ((Scene*)s)->aggs[ag].contents.push_back(SceneNode{N_CUBE, v3(o[0], o[1], o[2]), v3(0, 0, 0), dim, mk_mat(kind, kd, ks, rough, rough2), true, -1});
 }
-void orc_agg_add_box(void* s, int ag, const double* a, const double* b, int kind, const double* kd, const double* ks, double rough) {
-    ((Scene*)s)->aggs[ag].contents.push_back(SceneNode{N_CUBOID, v3(a[0], a[1], a[2]), v3(b[0], b[1], b[2]), 0.0, mk_mat(kind, kd, ks, rough), true, -1});
+void orc_agg_add_box(void* s, int ag, const double* a, const double* b, int kind, const double* kd, const double* ks, double rough, double rough2) {
+    ((Scene*)s)->aggs[ag].contents.push_back(SceneNode{N_CUBOID, v3(a[0], a[1], a[2]), v3(b[0], b[1], b[2]), 0.0, mk_mat(kind, kd, ks, rough, rough2), true, -1});
 }
-void orc_agg_add_mesh(void* s, int ag, int mesh, int has_mat, int kind, const double* kd, const double* ks, double rough) {
-    ((Scene*)s)->aggs[ag].contents.push_back(SceneNode{N_MESH, v3(0, 0, 0), v3(0, 0, 0), 0.0, mk_mat(kind, kd, ks, rough), has_mat != 0, mesh});
+void orc_agg_add_mesh(void* s, int ag, int mesh, int has_mat, int kind, const double* kd, const double* ks, double rough, double rough2) {
+    ((Scene*)s)->aggs[ag].contents.push_back(SceneNode{N_MESH, v3(0, 0, 0), v3(0, 0, 0), 0.0, mk_mat(kind, kd, ks, rough, rough2), has_mat != 0, mesh});
 }
 void orc_agg_add_group(void* s, int ag, int child) {
     ((Scene*)s)->aggs[ag].contents.push_back(SceneNode{N_GROUP, v3(0, 0, 0), v3(0, 0, 0), 0.0, mat_default(), false, child});
@@ -1257,6 +1418,30 @@ void orc_test_surface(double t, const double* dpdu, const double* dpdv, const do
     RayIsect is = isect_new(t, v3(dpdu[0], dpdu[1], dpdu[2]), v3(dpdv[0], dpdv[1], dpdv[2]));
     SurfaceInteraction si = surface_from(ray_new(v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2])), is);
     out[0] = si.ng.x; out[1] = si.ng.y; out[2] = si.ng.z;
+}
+// Substance::evaluate (fresnel.rs:22-33).  kind 0 dielectric (p = eta_i, eta_t), 1 conductor (p = eta_i[3], eta_t[3], k[3]), 2 no-op.
+void orc_test_fresnel(int kind, double cos_i, const double* p, double* out) {
+    Substance s; s.kind = kind;
+    if (kind == SUB_DIELECTRIC) { s.eta_i = p[0]; s.eta_t = p[1]; }
+    if (kind == SUB_CONDUCTOR) { s.c_eta_i = v3(p[0], p[1], p[2]); s.c_eta_t = v3(p[3], p[4], p[5]); s.c_k = v3(p[6], p[7], p[8]); }
+    V3 f = s.evaluate(cos_i); out[0] = f.x; out[1] = f.y; out[2] = f.z;
+}
+// Material::scattering on a hand-made interaction (ng, ns, normalised dpdu), then BSDF::f(wo, wi) and the two Whitted samples
+// (bsdf.rs:73-140): out_f[3]; out_refl = spectrum[3], wi[3], pdf; out_trans likewise.
+void orc_test_bsdf(int kind, const double* kd, const double* ks, double rough, double rough2, const double* frame,
+                   const double* wo, const double* wi, double* out_f, double* out_refl, double* out_trans) {
+    SurfaceInteraction si;
+    si.ng = v3(frame[0], frame[1], frame[2]); si.ns = v3(frame[3], frame[4], frame[5]); si.s_dpdu = v3(frame[6], frame[7], frame[8]);
+    BSDF b;
+    scattering(mk_mat(kind, kd, ks, rough, rough2), si, b);
+    V3 o = v3(wo[0], wo[1], wo[2]), i = v3(wi[0], wi[1], wi[2]);
+    V3 f = b.f(o, i); out_f[0] = f.x; out_f[1] = f.y; out_f[2] = f.z;
+    LightSample r = b.sample_f(o, BX_REFLECTION | BX_SPECULAR), t = b.sample_f(o, BX_TRANSMISSION | BX_SPECULAR);
+    double* dst[2] = {out_refl, out_trans}; const LightSample* src[2] = {&r, &t};
+    for (int k = 0; k < 2; k++) {
+        dst[k][0] = src[k]->spectrum.x; dst[k][1] = src[k]->spectrum.y; dst[k][2] = src[k]->spectrum.z;
+        dst[k][3] = src[k]->wi.x; dst[k][4] = src[k]->wi.y; dst[k][5] = src[k]->wi.z; dst[k][6] = src[k]->pdf;
+    }
 }
 // Exact f64 re-test of ONE canonical primitive against one ray:
 // returns t or +inf.  The primitive is located by canonical id through the accel.

@@ -51,11 +51,13 @@ def lib():
         "orc_add_point_light": (None, [vp, dp, dp, dp]),
         "orc_add_mesh": (C.c_int, [vp, fp, C.c_uint64, u32p, C.c_uint64, fp, C.c_uint64, u32p]),
         "orc_agg_new": (C.c_int, [vp]),
-        "orc_agg_add_sphere": (None, [vp, C.c_int, dp, C.c_double, C.c_int, dp, dp, C.c_double]),
-        "orc_agg_add_spheres": (None, [vp, C.c_int, C.c_uint64, dp, dp, C.c_int, ip, dp, dp, dp, ip]),
-        "orc_agg_add_cube": (None, [vp, C.c_int, dp, C.c_double, C.c_int, dp, dp, C.c_double]),
-        "orc_agg_add_box": (None, [vp, C.c_int, dp, dp, C.c_int, dp, dp, C.c_double]),
-        "orc_agg_add_mesh": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_double]),
+        "orc_agg_add_sphere": (None, [vp, C.c_int, dp, C.c_double, C.c_int, dp, dp, C.c_double, C.c_double]),
+        "orc_agg_add_spheres": (None, [vp, C.c_int, C.c_uint64, dp, dp, C.c_int, ip, dp, dp, dp, dp, ip]),
+        "orc_agg_add_cube": (None, [vp, C.c_int, dp, C.c_double, C.c_int, dp, dp, C.c_double, C.c_double]),
+        "orc_agg_add_box": (None, [vp, C.c_int, dp, dp, C.c_int, dp, dp, C.c_double, C.c_double]),
+        "orc_agg_add_mesh": (None, [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double]),
+        "orc_set_max_recursion_depth": (None, [vp, C.c_uint32]),
+        "orc_test_fresnel": (None, [C.c_int, C.c_double, dp, dp]), "orc_test_bsdf": (None, [C.c_int, dp, dp, C.c_double, C.c_double, dp, dp, dp, dp, dp, dp]),
         "orc_agg_add_group": (None, [vp, C.c_int, C.c_int]), "orc_agg_swap_backface": (None, [vp, C.c_int]),
         "orc_agg_translate": (None, [vp, C.c_int, dp]), "orc_agg_scale": (None, [vp, C.c_int, C.c_double, C.c_double, C.c_double]),
         "orc_agg_rotate_axis": (None, [vp, C.c_int, C.c_int, C.c_double]), "orc_agg_rotate": (None, [vp, C.c_int, C.c_double, dp]),
@@ -101,6 +103,7 @@ class OracleScene:
             L.orc_look_at(self.h, _d3(cam.look[0]), _d3(cam.look[1]), _d3(cam.look[2]))
         L.orc_set_supersampling(self.h, cam.supersampling)
         L.orc_set_ambient_light(self.h, _d3(scene.ambient))
+        L.orc_set_max_recursion_depth(self.h, int(scene.recursion))
         L.orc_set_radial_background(self.h, _d3(scene.background[0]), _d3(scene.background[1]), scene.background[2])
         for p, i, f in scene.lights:
             L.orc_add_point_light(self.h, _d3(p), _d3(i), _d3(f))
@@ -116,7 +119,7 @@ class OracleScene:
         self.spp = cam.num_samples()
 
     def _mat(self, m):
-        return (m.kind, _d3(m.kd), _d3(m.ks), m.roughness)
+        return (m.kind, _d3(m.kd), _d3(m.ks), m.roughness, m.roughness2)
 
     def _fill(self, idx, agg):
         L = lib()
@@ -140,9 +143,10 @@ class OracleScene:
                 kinds = np.array([m.kind for m in mats], np.int32)
                 kd = np.array([m.kd for m in mats], np.float64); ks = np.array([m.ks for m in mats], np.float64)
                 rough = np.array([m.roughness for m in mats], np.float64)
+                rough2 = np.array([m.roughness2 for m in mats], np.float64)
                 L.orc_agg_add_spheres(self.h, idx, len(rad), _ptr(cen, C.c_double), _ptr(rad, C.c_double), len(mats),
                                       _ptr(kinds, C.c_int), _ptr(kd, C.c_double), _ptr(ks, C.c_double),
-                                      _ptr(rough, C.c_double), _ptr(midx, C.c_int))
+                                      _ptr(rough, C.c_double), _ptr(rough2, C.c_double), _ptr(midx, C.c_int))
             elif k == "cube":
                 L.orc_agg_add_cube(self.h, idx, _d3(item[1]), item[2], *self._mat(item[3]))
             elif k == "box":
@@ -191,7 +195,7 @@ class OracleScene:
                            _ptr(ts, C.c_double) if aov else None, _ptr(occl, C.c_uint32) if aov else None,
                            _ptr(lis, C.c_double) if li else None, C.byref(cnt) if counters else None, C.byref(ms))
         if rc == 1:
-            raise RuntimeError("oracle: a material outside the hot path (Oren-Nayar/metal/glass/mirror) was hit")
+            raise RuntimeError("oracle: unknown material kind")
         if rc == 2:
             raise RuntimeError("oracle: traversal stack overflow (the reference would panic, bvh.rs:469)")
         out.update(render_ms=ms.value, prim_id=ids, t=ts, occl=occl, li=lis, counters=cnt.as_dict() if counters else None)

@@ -71,13 +71,14 @@ def test_flat_scene_structure(native):
 
 
 def test_reference_hazards_are_errors(native):
-    """Q9: empty aggregate; materials outside the path -> loud errors."""
+    """Q9: empty aggregates -> loud errors.  Every material variant flattens."""
     sc = Scene()
     with pytest.raises(native.LasgunError):
         native.FlatScene(sc)
     sc = Scene(); sc.root.add_sphere([0, 0, 0], 1.0, Material.glass([1, 1, 1], [1, 1, 1], 1.5))
-    with pytest.raises(native.LasgunError):
-        native.FlatScene(sc)
+    sc.root.add_sphere([3, 0, 0], 1.0, Material.metal([0.2, 0.9, 1.1], [3.9, 2.4, 2.2], 0.08, 0.45)); sc.set_max_recursion_depth(5)
+    flat = native.FlatScene(sc)
+    assert flat.desc.n_materials == 2 and flat.desc.recursion == 5
     sc = Scene(); g = Aggregate(); g.translate([1, 0, 0]); sc.root.add_group(g)      # empty nested aggregate
     with pytest.raises(native.LasgunError):
         native.FlatScene(sc)

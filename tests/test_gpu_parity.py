@@ -101,6 +101,42 @@ def test_small_config_parity(native, oracle, gpu_ctx, name):
     assert st["shadow_rays"] == len(sc.lights) * st["primary_hits"]
 
 
+# matte(sigma > 0), metal, glass, mirror and the Whitted recursion of integrate.rs:69-132
+WHITTED = {
+    "simplereflect_9spp": lambda: scenes.simplereflect(2, 160),                 # src/examples/simplereflect.rs, depth 4
+    "simplereflect_depth1": lambda: scenes.simplereflect(0, 160, recursion=1),
+    "simplereflect_depth0": lambda: scenes.simplereflect(0, 96, recursion=0),
+    "materials_4spp": lambda: scenes.materials((256, 192), 1),
+    "materials_grouped": lambda: scenes.materials((256, 192), 0, grouped=True),
+    "materials_depth8": lambda: scenes.materials((160, 120), 0, recursion=8),
+}
+
+
+@pytest.mark.parametrize("name", sorted(WHITTED))
+def test_materials_and_whitted_parity(native, oracle, gpu_ctx, name):
+    sc, (w, h) = WHITTED[name]()
+    o = oracle.OracleScene(sc)
+    ref = o.capture(w, h, aov=True)
+    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+    out = dev.capture_aov(w, h)
+    rgba, st = dev.capture(w, h)
+    dev.destroy()
+    spp = sc.camera.num_samples()
+
+    def retest(pid, i):
+        rays = o.camera_sample((i // spp) % w, (i // spp) // w, w, h)
+        return o.retest(pid, rays[i % spp, :3], rays[i % spp, 3:])
+
+    a = parity.aov_report(out, ref, retest)                      # the primary hits, as for every other scene
+    assert a["mismatches"] == 0 and a["hit_miss_flips"] == 0 and a["near_ties"] <= 1e-4 * a["samples"], a
+    assert a["t_bit_equal"] == a["t_compared"] and a["occl_diff"] == 0, a
+    f = parity.film_report(rgba, ref["rgba"])                    # ... and the film, which carries every ray below them
+    assert f["alpha_equal"] and f["within_1_frac"] >= 0.999, f
+    assert f["identical_frac"] >= 0.999, f
+    assert np.array_equal(rgba, out["rgba"])
+    assert (st["secondary_rays"] > 0) == (sc.recursion > 0), st
+
+
 def test_reference_cornell_grazing_rays(native, oracle, gpu_ctx):
     """src/examples/cornell.rs as shipped (on-axis eye): the rays of the image diagonals run exactly along the edges where
     two transformed walls meet.  There the reference's own f64 node test (cuboid.rs:104-121) can reject, by one rounding, a
@@ -381,13 +417,15 @@ def test_abi_rejects_what_the_path_does_not_cover(native, gpu_ctx):
     flat.desc.abi_version = 99
     assert L.lgb_scene_create(gpu_ctx.h, C.byref(flat.desc), C.byref(h)) == native.LGB_ERR_INVALID
     flat.desc.abi_version = abi
-    mats = (C.c_double * 8).from_address(flat.desc.materials)
-    kind_addr = flat.desc.materials + 7 * 8
+    kind_addr = flat.desc.materials + 8 * 8               # lgb_material.kind
     old = C.c_uint32.from_address(kind_addr).value
-    C.c_uint32.from_address(kind_addr).value = 3          # glass
+    C.c_uint32.from_address(kind_addr).value = 7          # no such Material variant
+    assert L.lgb_scene_create(gpu_ctx.h, C.byref(flat.desc), C.byref(h)) == native.LGB_ERR_INVALID
+    assert b"material" in L.lgb_last_error(gpu_ctx.h)
+    C.c_uint32.from_address(kind_addr).value = 3          # glass, deeper than the per-ray stack of k_secondary
+    flat.desc.recursion = 13
     assert L.lgb_scene_create(gpu_ctx.h, C.byref(flat.desc), C.byref(h)) == native.LGB_ERR_UNSUPPORTED
-    assert b"plastic" in L.lgb_last_error(gpu_ctx.h)
+    flat.desc.recursion = 3
     C.c_uint32.from_address(kind_addr).value = old
     assert L.lgb_scene_create(gpu_ctx.h, C.byref(flat.desc), C.byref(h)) == 0
     L.lgb_scene_destroy(h)
-    del mats
