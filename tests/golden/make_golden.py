@@ -23,13 +23,18 @@ CASES = {
     "C5_mixed_16spp": lambda: scenes.mixed4k(mesh_n=40, nspheres=4000, res=(64, 36), supersampling=3),
     "F1_nested_groups": lambda: scenes.nested_groups((80, 60), 1),
     "F1_cornell_groups_offaxis_9spp": lambda: scenes.cornell_groups((48, 48), 2, eye=(0.21, 0.13, 5.0)),
+    "F4_simplereflect_depth4_4spp": lambda: scenes.simplereflect(1, 64),
+    "F4_materials": lambda: scenes.materials((96, 72), 0),
+    "F4_materials_grouped_4spp": lambda: scenes.materials((64, 48), 1, grouped=True),
 }
 
 if __name__ == "__main__":
     from oracle import pyoracle as po
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "films.npz")
+    old = dict(np.load(path)) if os.path.exists(path) else {}
     out = {}
     for name, mk in CASES.items():
         sc, (w, h) = mk()
         out[name] = po.OracleScene(sc).capture(w, h)["rgba"]
-        print(name, out[name].shape, int(out[name].astype(np.uint64).sum()))
-    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "films.npz"), **out)
+        print(name, out[name].shape, int(out[name].astype(np.uint64).sum()), "unchanged" if name in old and np.array_equal(old[name], out[name]) else "NEW/CHANGED")
+    np.savez_compressed(path, **out)
