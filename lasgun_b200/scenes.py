@@ -353,4 +353,6 @@ CONFIGS = {
     "mixed4k": mixed4k,
     "simplereflect": simplereflect,
     "materials": materials,
+    "simplereflect2k": lambda: simplereflect(2, 2048),                     # 4.2 Mpixel, 9 spp, depth 4: 37.7 M ray trees
+    "materials2k": lambda: materials((2560, 1920), 1),                     # 4.9 Mpixel, 4 spp
 }
