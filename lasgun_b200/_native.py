@@ -339,6 +339,10 @@ class Context:
         """LGB_OPT_BEAMS: 1 on (whenever spp >= 4), 0 off, -1 automatic (the default)."""
         self.check(lib().lgb_set_option(self.h, 2, int(mode)))
 
+    def set_whitted(self, wavefront: bool):
+        """LGB_OPT_WHITTED: the specular ray trees level by level (default) or one thread per tree."""
+        self.check(lib().lgb_set_option(self.h, 3, 1 if wavefront else 0))
+
     def measure(self):
         L = lib()
         out = {}

@@ -20,6 +20,9 @@ namespace lgb {
 constexpr int kRenderEvents = 7;
 cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev, int part);
 bool render_fused(uint32_t spp);
+cudaError_t launch_level(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, int sms, cudaStream_t);
+cudaError_t launch_gather(const SpawnRec* recs, const uint32_t* nspec, double* rad_parent, const double* rad_child, uint64_t n_upper, cudaStream_t);
+cudaError_t launch_resolve(const DevWork&, const DevOut&, cudaStream_t);
 cudaError_t launch_trace(const DevScene&, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns, cudaStream_t);
 cudaError_t launch_l2_read(const void* buf, uint64_t bytes, int iters, float* sink, int sms, cudaStream_t);
 cudaError_t launch_fp32_peak(int iters, float* sink, int sms, cudaStream_t);
@@ -51,6 +54,10 @@ struct lgb_ctx {
     cudaEvent_t phase[kRenderEvents] = {};
     std::string error;
     DevBuf radiance, film, counters, tiles, aov_id, aov_t, aov_occl, scratch, wave, wave_ctr, ties, beam;
+    // levels of the specular ray trees (Whitted recursion): radiance and spawn records of every level (kept until the fold back up),
+    // the rays of the current and the next level, the wavefront buffers of the current level, per-level counters
+    DevBuf lvl_rad[kMaxRecursion + 1], lvl_recs[kMaxRecursion + 1], raybuf[2], wave2, wave2_ctr, lvl_ctr;
+    int whitted_wavefront = 1;             // LGB_OPT_WHITTED: 1 level-by-level wavefront, 0 one thread per ray tree (k_secondary)
     int beams = -1;                        // LGB_OPT_BEAMS: 0 off, 1 on, -1 automatic
     std::vector<uint32_t> tile_host;
     uint32_t tile_key[4] = {0, 0, 0, 0};   // w, h, rank, ranks of the cached tile list
@@ -177,6 +184,7 @@ int lgb_set_option(lgb_ctx* c, int option, int value) {
     if (!c) return LGB_ERR_INVALID;
     if (option == LGB_OPT_COUNT_WORK) { c->count_work = value != 0; return LGB_OK; }
     if (option == LGB_OPT_BEAMS) { c->beams = value < 0 ? -1 : (value != 0); return LGB_OK; }
+    if (option == LGB_OPT_WHITTED) { c->whitted_wavefront = value != 0; return LGB_OK; }
     return fail(c, LGB_ERR_INVALID, "lgb_set_option: unknown option");
 }
 
@@ -184,7 +192,9 @@ void lgb_shutdown(lgb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties, &c->beam}) b->release();
+    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties, &c->beam, &c->raybuf[0], &c->raybuf[1], &c->wave2, &c->wave2_ctr, &c->lvl_ctr}) b->release();
+    for (DevBuf& b : c->lvl_rad) b.release();
+    for (DevBuf& b : c->lvl_recs) b.release();
     if (c->staging) cudaFreeHost(c->staging);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
     for (auto& e : c->phase) cudaEventDestroy(e);
@@ -865,6 +875,82 @@ struct CaptureArgs {
     cudaStream_t stream;
 };
 
+// Wavefront buffers of `nslots` sample slots carved out of one allocation (layout: DevWave, lgb_types.cuh).
+static size_t wave_bytes(uint64_t nslots, uint32_t nl, uint64_t npix) { return nslots * (8 + 24 + 4 + 4 + 12 * (size_t)nl) + npix * 4 * nl; }
+static DevWave carve_wave(void* wave, void* ctr, uint64_t nslots, uint32_t nl) {
+    DevWave V{};
+    char* base = (char*)wave;
+    V.hit_t = (double*)base; base += nslots * 8;
+    V.ps = (double*)base; base += nslots * 24;
+    V.hit_ref = (uint32_t*)base; base += nslots * 4;
+    V.occl = (uint32_t*)base; base += nslots * 4;
+    V.queue = (uint32_t*)base; V.queue_stride = nslots; base += nslots * 12 * nl;
+    V.occluder = (uint32_t*)base;
+    V.work_counter = (unsigned long long*)ctr;
+    V.queue_count = (uint32_t*)((char*)ctr + 8);
+    V.queue_fetch = V.queue_count + LGB_MAX_LIGHTS * 3;
+    V.tie_count = V.queue_fetch + LGB_MAX_LIGHTS * 3;
+    V.fallback_count = V.tie_count + 1;
+    V.sec_count = V.fallback_count + 1;
+    V.fallback_list = V.queue;                       // the shadow queues are written only after the primary phase ...
+    V.sec_list = V.queue;                            // ... and drained before k_shade lists the specular slots
+    return V;
+}
+
+// Whitted recursion below the specular hits of the camera wave (integrate.rs:69-132), level by level.  k_shade of a wave has
+// already turned its specular hits into the rays of the next level (spawn_children); here each level is traced and shaded with the
+// RAYBUF variants of the frame's own kernels, and when a level spawns nothing (or scene.recursion is reached) the radiance is
+// folded back up (k_gather).  One small device-to-host read per level sizes the next buffers and launches.
+// prepare_spawn points wave `level` (slots sample slots) at the buffers of level + 1; false: not enough memory, use k_secondary.
+static bool prepare_spawn(lgb_ctx* c, DevWave& V, uint32_t level, uint64_t slots) {
+    if (c->lvl_recs[level].reserve((size_t)slots * sizeof(SpawnRec)) != cudaSuccess || c->raybuf[(level + 1) & 1].reserve(2 * (size_t)slots * 48) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    V.recs = (SpawnRec*)c->lvl_recs[level].p; V.next_rays = (double*)c->raybuf[(level + 1) & 1].p;
+    V.spawn_ctr = (uint32_t*)c->lvl_ctr.p + 4 * level; V.next_t_base = (uint32_t)slots;
+    return true;
+}
+static int run_whitted_levels(lgb_ctx* c, lgb_scene* s, const DevOut& O0, uint64_t slots0, cudaStream_t st, bool count, uint64_t* rays_traced, uint32_t* launches) {
+    const DevScene& S = s->dev;
+    const uint32_t nl = std::max<uint32_t>(S.n_lights, 1);
+    const uint32_t* d_ctr = (const uint32_t*)c->lvl_ctr.p;
+    uint64_t slots[kMaxRecursion + 2] = {slots0};    // sample slots of every level (holes included)
+    int traced = 0;                                  // levels 1 .. traced exist
+    std::vector<unsigned char> hctr(kWaveCtrBytes);
+    for (uint32_t l = 0; l < S.recursion; l++) {
+        uint32_t sc[4];                              // what wave l spawned: records, reflected rays, transmitted rays
+        CU(c, cudaMemcpyAsync(sc, d_ctr + 4 * l, 16, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+        const uint64_t n_r = sc[1], n_t = sc[2];
+        if (n_r + n_t == 0) break;
+        const uint64_t n = n_t ? slots[l] + n_t : n_r;               // reflected rays from slot 0, transmitted ones from slots[l]
+        if (n >= (1ull << 32) - 64) return fail(c, LGB_ERR_UNSUPPORTED, "capture: more than 2^32 rays in one level of the specular ray trees");
+        slots[l + 1] = n; traced = (int)l + 1;
+        CU(c, c->lvl_rad[l + 1].reserve((size_t)n * 24));
+        CU(c, c->wave2.reserve(wave_bytes(n, nl, 1)));
+        CU(c, c->wave2_ctr.reserve(kWaveCtrBytes));
+        DevWork Wl{};
+        Wl.mode = 3; Wl.w = (uint32_t)n; Wl.h = 1; Wl.n_pixels = n; Wl.spp = 1; Wl.rays = (const double*)c->raybuf[(l + 1) & 1].p; Wl.depth = l + 1;
+        Wl.hole_lo = (uint32_t)n_r; Wl.hole_hi = n_t ? (uint32_t)slots[l] : (uint32_t)n_r;
+        DevWave Vl = carve_wave(c->wave2.p, c->wave2_ctr.p, n, nl);
+        if (l + 1 < S.recursion && !prepare_spawn(c, Vl, l + 1, n)) return fail(c, LGB_ERR_CUDA, "capture: out of device memory for a level of the specular ray trees");
+        DevOut Ol{}; Ol.radiance = (double*)c->lvl_rad[l + 1].p;
+        CU(c, launch_level(S, s->cam, s->shade, Wl, Ol, Vl, c->sm_count, st));
+        *launches += 4 + S.n_lights;                                 // k_primary, k_setup, k_shadow x lights, k_shade; k_gather on the way back
+        *rays_traced += n_r + n_t;
+        if (count) {                                                 // + the shadow rays of this level (lgb_stats.secondary_rays)
+            CU(c, cudaMemcpyAsync(hctr.data(), c->wave2_ctr.p, kWaveCtrBytes, cudaMemcpyDeviceToHost, st));
+            CU(c, cudaStreamSynchronize(st));
+            const uint32_t* qc = (const uint32_t*)(hctr.data() + 8);
+            for (uint32_t k = 0; k < S.n_lights; k++) *rays_traced += qc[k * 3 + kQueueA];
+        }
+    }
+    for (int l = traced - 1; l >= 0; l--)
+        CU(c, launch_gather((const SpawnRec*)c->lvl_recs[l].p, d_ctr + 4 * l, l == 0 ? O0.radiance : (double*)c->lvl_rad[l].p, (const double*)c->lvl_rad[l + 1].p, slots[l], st));
+    return LGB_OK;
+}
+
 static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats* stats, bool sync_stats) {
     if (!c || !s || s->ctx != c) return fail(c, LGB_ERR_INVALID, "capture: scene does not belong to this context");
     if (a.w == 0 || a.h == 0 || (uint64_t)a.w * a.h >= (1ull << 32)) return fail(c, LGB_ERR_INVALID, "capture: bad film size");
@@ -958,6 +1044,12 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     cudaEvent_t* pev = (stats && sync_stats && total) ? c->phase : nullptr;
     uint32_t tie_slots = 0;
     const bool st_on = a.aov || c->count_work;
+    int wf = (S.general && c->whitted_wavefront) ? 4 : 0;           // launch_render stops after k_shade; the levels and the resolve follow here
+    if (wf && S.specular && S.recursion > 0 && total) {             // k_shade of the camera wave spawns level 1
+        CU(c, c->lvl_ctr.reserve(4 * (kMaxRecursion + 2) * 4));
+        CU(c, cudaMemsetAsync(c->lvl_ctr.p, 0, 4 * (kMaxRecursion + 2) * 4, st));
+        if (!prepare_spawn(c, V, 0, total)) wf = 0;                 // not enough memory for the level buffers: one thread per ray tree instead
+    }
     if (s->lazy_fn && !s->dev.rank && total) {
         // no rank tables yet: trace the primary rays, and only if one met two primitives at bit-identical t fetch the
         // caller's reference tree, build the tables and re-trace those slots (lasgun_b200.h, "Lazy reference tree")
@@ -973,9 +1065,16 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
             else CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));          // too many to list: the whole frame again
             CU(c, launch_render(s->dev, s->cam, s->shade, W2, O, V, st_on, a.aov, c->sm_count, st, ties <= V.tie_cap ? nullptr : pev, 1));
         }
-        CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 2));
+        CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 2 | wf));
     } else {
-        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 3));
+        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 3 | wf));
+    }
+    uint64_t level_rays = 0; uint32_t level_launches = 0;
+    if (wf && total) {                     // materials beyond plastic: the levels of the specular ray trees, then the film
+        if (S.specular && S.recursion > 0) if (int rc = run_whitted_levels(c, s, O, total, st, stats != nullptr, &level_rays, &level_launches)) return rc;
+        if (pev) CU(c, cudaEventRecord(pev[5], st));
+        CU(c, launch_resolve(W, O, st));
+        if (pev) CU(c, cudaEventRecord(pev[6], st));
     }
     CU(c, cudaEventRecord(c->ev1, st));
     if (stats && sync_stats) {
@@ -991,8 +1090,8 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         if (total) for (int k = 0; k < 6; k++) { float pm = 0.f; CU(c, cudaEventElapsedTime(&pm, c->phase[k], c->phase[k + 1])); stats->kernel_ms[k] = pm; }
         for (int k = 0; k < 3; k++) { stats->filter_tests[k] = hc.filter[k]; stats->exact_tests[k] = hc.exact[k]; }
         stats->stack_overflow = hc.stack_overflow;
-        stats->beams = W.beams; stats->tie_retraces = tie_slots; stats->secondary_rays = hc.secondary_rays;
-        stats->kernel_launches = total ? (S.general ? (S.specular && S.recursion ? 5 : 4) : render_fused(W.spp) ? 3 : 4) + (W.beams ? 2 : 0) + s->dev.n_lights * (W.spp > 1 ? 3 : 1) : 0;
+        stats->beams = W.beams; stats->tie_retraces = tie_slots; stats->secondary_rays = hc.secondary_rays + level_rays;
+        stats->kernel_launches = total ? level_launches + (S.general ? (S.specular && S.recursion && !wf ? 5 : 4) : render_fused(W.spp) ? 3 : 4) + (W.beams ? 2 : 0) + s->dev.n_lights * (W.spp > 1 ? 3 : 1) : 0;
         float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         stats->render_ms = ms; stats->total_ms = ms;
     }

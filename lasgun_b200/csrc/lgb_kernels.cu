@@ -674,9 +674,16 @@ __device__ __forceinline__ D3 background_of(const DevShade& sh, D3 d) {         
     return d3(lerp64(t, sh.bg_inner[0], sh.bg_outer[0]), lerp64(t, sh.bg_inner[1], sh.bg_outer[1]), lerp64(t, sh.bg_inner[2], sh.bg_outer[2]));
 }
 
+// Flags of the material of a closest hit (lgb_types.cuh) without forming its surface record.
+__device__ __forceinline__ uint32_t material_flags(const DevScene& S, uint32_t ref) {
+    const uint32_t type = ref >> 30, i = ref & 0x3FFFFFFFu;
+    const uint32_t m = type == LGB_PRIM_SPHERE ? S.sph_mat[i] : type == LGB_PRIM_CUBOID ? S.cub_mat[i] : __float_as_uint(S.tri[3 * (size_t)i + 1].w);
+    return (uint32_t)__double_as_longlong(S.materials[kMatStride * (size_t)m + 7]);
+}
+
 // Everything the lighting loop needs about the closest hit (SurfaceInteraction::from, surface.rs:158-183,
 // + Material::scattering, plastic.rs:20-37 / matte.rs:18-26).
-struct ShadePoint { D3 wo, ng, ns, ps, pt; Bsdf B; };
+struct ShadePoint { D3 wo, ng, ns, ps, pt; Bsdf B; uint32_t mat; };
 
 template <bool WITH_BSDF, bool INST, bool GENERAL = false>
 __device__ __forceinline__ void shade_point(const DevScene& S, const Ray64& ray, double t, uint32_t ref, ShadePoint& P, uint32_t& id) {
@@ -688,6 +695,7 @@ __device__ __forceinline__ void shade_point(const DevScene& S, const Ray64& ray,
         record_to_world(S, space, sf);
     } else surface_of(S, ray, ref, t_again, sf);
     id = sf.id;
+    P.mat = sf.material;
     P.wo = -normalize(ray.d);
     P.ng = face_forward(normalize(cross(sf.g_dpdu, sf.g_dpdv)), P.wo);
     P.ns = sf.has_n ? normalize(sf.n) : normalize(cross(sf.s_dpdu, sf.s_dpdv));
@@ -772,7 +780,15 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 // k_shade    per slot: BSDF evaluation for the unoccluded lights + ambient -> radiance (integrate.rs:47-67)
 // k_resolve  per pixel: in-order sample sum, weight, quantise, uchar4 store (integrate.rs:16-20, img.rs:56-67)
 
+template <bool RAYBUF = false>
 __device__ __forceinline__ bool slot_ray(const DevCamera& C, const DevWork& W, uint64_t g, Ray64& ray, uint32_t& x, uint32_t& y, uint32_t& s) {
+    if (RAYBUF) {                                                  // a level of the specular ray trees: the rays are stored
+        if (g >= W.hole_lo && g < W.hole_hi) return false;
+        const double* r = W.rays + 6 * g;
+        ray.o = d3(r[0], r[1], r[2]); ray.d = d3(r[3], r[4], r[5]);
+        x = (uint32_t)g; y = 0; s = 0;
+        return true;
+    }
     const uint32_t g32 = (uint32_t)g, p = g32 / W.spp;
     s = g32 - p * W.spp;
     if (!slot_to_pixel(W, p, x, y)) return false;
@@ -855,7 +871,7 @@ __device__ __forceinline__ void block_append_multi(MultiAppendScratch& sc, uint3
     }
 }
 
-template <bool STATS, bool INST>
+template <bool STATS, bool INST, bool RAYBUF = false>
 __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_primary(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
     const uint64_t total = W.slot_list ? (W.n_list_dev ? (uint64_t)*W.n_list_dev : W.n_list) : W.n_pixels * W.spp;   // every sample slot, or the listed ones
     const unsigned lane = threadIdx.x & 31u;
@@ -879,7 +895,7 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_primary(De
                         else {
                             uint32_t x, y, s;
                             const uint64_t slot = W.slot_list ? W.slot_list[idx] : idx;
-                            if (slot_ray(C, W, slot, world, x, y, s)) {
+                            if (slot_ray<RAYBUF>(C, W, slot, world, x, y, s)) {
                                 g = slot; enter_root<INST>(S, world, ray, f, T, CUDART_INF); active = true; need = false; primary++;
                             } else {
                                 V.hit_t[slot] = CUDART_INF; V.hit_ref[slot] = kSlotUnused;     // pixel outside the film: take another
@@ -1122,7 +1138,7 @@ __global__ void __launch_bounds__(256, 4) k_leafp(DevScene S, DevCamera C, DevWo
     }
 }
 
-template <bool ALL_SHADOWS, bool INST>
+template <bool ALL_SHADOWS, bool INST, bool RAYBUF = false>
 __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
     const uint64_t total = W.n_pixels * W.spp;
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1131,13 +1147,18 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
     if (g < total) {
         const uint32_t ref = V.hit_ref[g];
         Ray64 ray; uint32_t x, y, s;
-        if (ref != kSlotUnused && slot_ray(C, W, g, ray, x, y, s)) {
+        bool ref_done = false;
+        if (ref != kSlotUnused && slot_ray<RAYBUF>(C, W, g, ray, x, y, s)) {
             const uint64_t gi = ((uint64_t)y * W.w + x) * W.spp + s;
             if (ref == LGB_MISS) {                                   // the background is evaluated by k_shade
                 if (O.aov_id) O.aov_id[gi] = LGB_MISS;
                 if (O.aov_t) O.aov_t[gi] = CUDART_INF;
                 if (O.aov_occl) O.aov_occl[gi] = 0;
             } else {
+                // glass and mirror: BSDF::f is zero whatever the light does (bxdf/mod.rs:172) -- no shadow ray, no shadow origin
+                if (!ALL_SHADOWS && S.specular && (material_flags(S, ref) & kMatSpecular)) { V.occl[g] = 0; ref_done = true; }
+            }
+            if (ref != LGB_MISS && !ref_done) {
                 live = true;
                 const double t = V.hit_t[g];
                 ShadePoint P; uint32_t id;
@@ -1288,6 +1309,9 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_shadow(Dev
 #ifndef LGB_SHADE_MIN_BLOCKS
 #define LGB_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef LGB_GSHADE_MIN_BLOCKS
+#define LGB_GSHADE_MIN_BLOCKS 2      // the GENERAL variants (every material, spawn of the specular rays)
+#endif
 __device__ __forceinline__ uchar4 quantise(D3 c) {                     // img.rs:56-67
     uchar4 px;
     px.x = (unsigned char)round(fmin(fmax(c.x, 0.0), 1.0) * 255.0);
@@ -1299,10 +1323,50 @@ __device__ __forceinline__ uchar4 quantise(D3 c) {                     // img.rs
 // Radiance of every sample slot (integrate.rs:23-80) and, FUSED (spp <= 256: a block holds whole pixels), the film:
 // the samples of a pixel meet in shared memory and are summed in sample order (integrate.rs:16-20), so the
 // 24 B/sample radiance buffer and k_resolve drop out.  Thread t of a block: pixel t / spp of the block, sample t % spp.
+// The rays below one specular hit (specular_reflect / specular_transmit, integrate.rs:82-132) appended to the next level of the
+// wavefront: reflected rays fill the level's slots from 0, transmitted ones from V.next_t_base, so each kind stays with its own
+// (neighbouring rays of a warp then point the same way); one record per hit tells k_gather where the children are.
+__device__ __forceinline__ void spawn_children(const ShadePoint& P, const DevWave& V, uint32_t g) {
+    SpawnRec rec; rec.slot = g; rec.child_r = rec.child_t = kNoChild; rec.pad = 0;
+    rec.spec_r[0] = rec.spec_r[1] = rec.spec_r[2] = rec.spec_t[0] = rec.spec_t[1] = rec.spec_t[2] = rec.c = 0.0;
+    Ray64 rr, rt; D3 spec, wi;
+    bool has_r = false, has_t = false;
+    if (sample_specular_reflection(P.B, spec, wi) && !(spec.x == 0.0 && spec.y == 0.0 && spec.z == 0.0) && !(dot(wi, P.ns) <= 0.0)) {
+        has_r = true; rr.o = P.ps; rr.d = -1.0 * P.wo + 2.0 * dot(P.wo, P.ns) * P.ns;      // bxdf::util::reflect, mod.rs:160-162
+        rec.spec_r[0] = spec.x; rec.spec_r[1] = spec.y; rec.spec_r[2] = spec.z;
+    }
+    if (sample_specular_transmission(P.B, spec, wi)) {
+        const double c = fabs(dot(wi, P.ns));
+        if (!(spec.x == 0.0 && spec.y == 0.0 && spec.z == 0.0) && c != 0.0) {
+            has_t = true; rt.o = P.pt; rt.d = wi; rec.c = c;
+            rec.spec_t[0] = spec.x; rec.spec_t[1] = spec.y; rec.spec_t[2] = spec.z;
+        }
+    }
+    const unsigned peers = __activemask(), lane = threadIdx.x & 31u, leader = __ffs(peers) - 1;
+    const unsigned mr = __ballot_sync(peers, has_r), mt = __ballot_sync(peers, has_t);
+    uint32_t b_rec = 0, b_r = 0, b_t = 0;
+    if (lane == leader) {
+        b_rec = atomicAdd(V.spawn_ctr, (uint32_t)__popc(peers));
+        if (mr) b_r = atomicAdd(V.spawn_ctr + 1, (uint32_t)__popc(mr));
+        if (mt) b_t = atomicAdd(V.spawn_ctr + 2, (uint32_t)__popc(mt));
+    }
+    b_rec = __shfl_sync(peers, b_rec, leader); b_r = __shfl_sync(peers, b_r, leader); b_t = __shfl_sync(peers, b_t, leader);
+    const unsigned below = (1u << lane) - 1u;
+    if (has_r) {
+        rec.child_r = b_r + __popc(mr & below);
+        double* o = V.next_rays + 6 * (size_t)rec.child_r; o[0] = rr.o.x; o[1] = rr.o.y; o[2] = rr.o.z; o[3] = rr.d.x; o[4] = rr.d.y; o[5] = rr.d.z;
+    }
+    if (has_t) {
+        rec.child_t = V.next_t_base + b_t + __popc(mt & below);
+        double* o = V.next_rays + 6 * (size_t)rec.child_t; o[0] = rt.o.x; o[1] = rt.o.y; o[2] = rt.o.z; o[3] = rt.d.x; o[4] = rt.d.y; o[5] = rt.d.z;
+    }
+    V.recs[b_rec + __popc(peers & below)] = rec;
+}
+
 // GENERAL (scenes with Oren-Nayar, metal, glass or mirror; never FUSED): every material's BSDF::f, and the slots whose closest hit
 // carries specular lobes are listed for k_secondary.
-template <bool INST, bool FUSED, bool GENERAL = false>
-__global__ void __launch_bounds__(256, GENERAL ? 2 : LGB_SHADE_MIN_BLOCKS) k_shade(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
+template <bool INST, bool FUSED, bool GENERAL = false, bool RAYBUF = false>
+__global__ void __launch_bounds__(256, GENERAL ? LGB_GSHADE_MIN_BLOCKS : LGB_SHADE_MIN_BLOCKS) k_shade(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
     const double PI = 3.14159265358979323846264338327950288;
     const uint64_t total = W.n_pixels * W.spp;
     __shared__ double rad[FUSED ? 256 * 3 : 3];
@@ -1324,7 +1388,7 @@ __global__ void __launch_bounds__(256, GENERAL ? 2 : LGB_SHADE_MIN_BLOCKS) k_sha
     if (mine) {
         const uint32_t ref = V.hit_ref[g];
         Ray64 ray;
-        if (ref != kSlotUnused && slot_ray(C, W, g, ray, x, y, s)) {
+        if (ref != kSlotUnused && slot_ray<RAYBUF>(C, W, g, ray, x, y, s)) {
             have = true;
             if (ref == LGB_MISS) {                                       // background.rs:25-34
                 output = background_of(sh, ray.d);
@@ -1332,7 +1396,8 @@ __global__ void __launch_bounds__(256, GENERAL ? 2 : LGB_SHADE_MIN_BLOCKS) k_sha
                 ShadePoint P; uint32_t id;
                 shade_point<true, INST, GENERAL>(S, ray, V.hit_t[g], ref, P, id);
                 const bool general = GENERAL && (P.B.flags & kMatGeneral);
-                if (GENERAL && (P.B.flags & kMatSpecular) && S.recursion > 0) {          // integrate.rs:69: followed by k_secondary
+                if (GENERAL && (P.B.flags & kMatSpecular) && W.depth < S.recursion && V.recs) spawn_children(P, V, (uint32_t)g);   // integrate.rs:69
+                else if (GENERAL && (P.B.flags & kMatSpecular) && W.depth < S.recursion) {                                      // ... or k_secondary follows
                     const unsigned peers = __activemask();
                     const unsigned lane = threadIdx.x & 31u, leader = __ffs(peers) - 1;
                     uint32_t base = 0;
@@ -1404,8 +1469,14 @@ __device__ __forceinline__ void push_specular(const DevScene& S, const ShadePoin
         }
     }
 }
+#ifndef LGB_SEC_THREADS
+#define LGB_SEC_THREADS 128
+#endif
+#ifndef LGB_SEC_MIN_BLOCKS
+#define LGB_SEC_MIN_BLOCKS 2
+#endif
 template <bool INST>
-__global__ void __launch_bounds__(128) k_secondary(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
+__global__ void __launch_bounds__(LGB_SEC_THREADS, LGB_SEC_MIN_BLOCKS) k_secondary(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
     const double PI = 3.14159265358979323846264338327950288;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *V.sec_count) return;
@@ -1453,6 +1524,30 @@ __global__ void __launch_bounds__(128) k_secondary(DevScene S, DevCamera C, DevS
     }
     O.radiance[3 * (size_t)g + 0] += rad.x; O.radiance[3 * (size_t)g + 1] += rad.y; O.radiance[3 * (size_t)g + 2] += rad.z;
     if (O.counters) atomicAdd(&O.counters->secondary_rays, traced);
+}
+
+// ---- the same recursion as a wavefront, one level of the ray trees at a time (the default; k_secondary is kept as a cross-check):
+// the rays of a level are traced and shaded by the SAME lean kernels as the camera rays (k_primary / k_setup / k_shadow / k_shade
+// in their RAYBUF variants: a slot's ray is read from a buffer instead of being generated by the camera), k_shade turns the specular
+// hits of a level into the rays of the next one while it has their shading point in registers (spawn_children), and after the
+// deepest level k_gather folds the radiance back up, parent by parent, in the reference's own order: output + reflected +
+// refracted (integrate.rs:79).
+__global__ void __launch_bounds__(256) k_gather(const SpawnRec* recs, const uint32_t* nspec, double* rad_parent, const double* rad_child) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *nspec) return;
+    const SpawnRec r = recs[i];
+    D3 output = d3(rad_parent[3 * (size_t)r.slot], rad_parent[3 * (size_t)r.slot + 1], rad_parent[3 * (size_t)r.slot + 2]);
+    D3 reflected = d3(0, 0, 0), refracted = d3(0, 0, 0);
+    if (r.child_r != kNoChild) {
+        const double* l = rad_child + 3 * (size_t)r.child_r;
+        reflected = mul_el(d3(r.spec_r[0], r.spec_r[1], r.spec_r[2]), d3(l[0], l[1], l[2]));
+    }
+    if (r.child_t != kNoChild) {
+        const double* l = rad_child + 3 * (size_t)r.child_t;
+        refracted = mul_el(d3(r.spec_t[0], r.spec_t[1], r.spec_t[2]), d3(l[0], l[1], l[2])) * r.c;        // / pdf, which is 1
+    }
+    output = output + reflected + refracted;
+    rad_parent[3 * (size_t)r.slot] = output.x; rad_parent[3 * (size_t)r.slot + 1] = output.y; rad_parent[3 * (size_t)r.slot + 2] = output.z;
 }
 
 // integrate.rs:16-20 + img.rs:56-67: in-order sum of the samples, weight, quantise, store.
@@ -1587,9 +1682,10 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     mark(4);
     if (S.general) {                    // materials beyond plastic: every BSDF in k_shade, then the specular ray trees, then the film
         if (inst) k_shade<true, false, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, false, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+        if (part & 4) return cudaGetLastError();      // the caller runs the levels of the ray trees (launch_level / launch_spawn / launch_gather) and the resolve
         if (S.specular && S.recursion > 0) {
-            const unsigned sb = (unsigned)((total + 127) / 128);
-            if (inst) k_secondary<true><<<sb, 128, 0, stream>>>(S, C, sh, W, O, V); else k_secondary<false><<<sb, 128, 0, stream>>>(S, C, sh, W, O, V);
+            const unsigned sb = (unsigned)((total + LGB_SEC_THREADS - 1) / LGB_SEC_THREADS);
+            if (inst) k_secondary<true><<<sb, LGB_SEC_THREADS, 0, stream>>>(S, C, sh, W, O, V); else k_secondary<false><<<sb, LGB_SEC_THREADS, 0, stream>>>(S, C, sh, W, O, V);
         }
         mark(5);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -1606,6 +1702,37 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
         k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
     }
     mark(6);
+    return cudaGetLastError();
+}
+// One level of the specular ray trees: W.mode == 3, the rays in W.rays; radiance of every ray into O.radiance, specular hits into V.sec_list.
+cudaError_t launch_level(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O, const DevWave& V, int sms, cudaStream_t stream) {
+    const uint64_t total = W.n_pixels;
+    if (total == 0) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(V.work_counter, 0, kWaveCtrBytes, stream)) != cudaSuccess) return e;
+    const unsigned pb = (unsigned)std::min<uint64_t>((total + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, (uint64_t)sms * LGB_MIN_BLOCKS);
+    const unsigned blocks = (unsigned)((total + 255) / 256), ablocks = (unsigned)((total + kAppendThreads - 1) / kAppendThreads);
+    if (S.instanced) {
+        k_primary<false, true, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V);
+        k_setup<false, true, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
+        for (uint32_t l = 0; l < S.n_lights; l++) k_shadow<false, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, kQueueA);
+        k_shade<true, false, true, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+    } else {
+        k_primary<false, false, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V);
+        k_setup<false, false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
+        for (uint32_t l = 0; l < S.n_lights; l++) k_shadow<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, kQueueA);
+        k_shade<false, false, true, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_gather(const SpawnRec* recs, const uint32_t* nspec, double* rad_parent, const double* rad_child, uint64_t n_upper, cudaStream_t stream) {
+    if (n_upper == 0) return cudaSuccess;
+    k_gather<<<(unsigned)((n_upper + 255) / 256), 256, 0, stream>>>(recs, nspec, rad_parent, rad_child);
+    return cudaGetLastError();
+}
+cudaError_t launch_resolve(const DevWork& W, const DevOut& O, cudaStream_t stream) {
+    if (W.n_pixels == 0) return cudaSuccess;
+    k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
     return cudaGetLastError();
 }
 cudaError_t launch_trace(const DevScene& S, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns, cudaStream_t stream) {

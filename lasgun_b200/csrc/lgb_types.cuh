@@ -87,6 +87,7 @@ struct DevShade {
 //   mode 0: macro tiles listed in tile_list (tile index = my * n_macro_x + mx)
 //   mode 1: capture_subset — pixels k, k+n, ... of the row-major film (lib.rs:152)
 //   mode 2: caller-supplied rays (lgb_trace_rays)
+//   mode 3: one level of the specular ray trees (Whitted recursion): slot i is ray i of `rays`, spp = 1
 struct DevWork {
     uint32_t mode;
     uint32_t w, h;
@@ -103,7 +104,21 @@ struct DevWork {
     const uint32_t* n_list_dev;      // ... or as many as this device counter says (beam fallback)
     uint32_t compact_out;            // resolve writes film[slot] instead of film[y*w + x]
     uint32_t beams;                  // primary rays through pixel beams (k_beam / k_leafp) when spp >= 4
+    const double* rays;              // mode 3: origin + direction, 6 doubles per slot
+    uint32_t depth;                  // mode 3: depth of these rays in integrate.rs:23's recursion (camera rays: 0)
+    uint32_t hole_lo, hole_hi;       // mode 3: slots [hole_lo, hole_hi) hold no ray (reflected rays fill the level's slots from 0, transmitted ones from hole_hi)
 };
+
+
+// One specular hit and the rays it spawned (k_spawn); k_gather folds the children's radiance back into the parent's:
+// output + reflected + refracted, integrate.rs:79, with reflected = spectrum x li (:103) and refracted = spectrum x li * |wi.ns| / pdf (:129)
+struct SpawnRec {
+    uint32_t slot;                   // the parent's slot in its own level
+    uint32_t child_r, child_t;       // ray indices in the next level, or kNoChild
+    uint32_t pad;
+    double spec_r[3], spec_t[3], c;  // c = |wi . ns| of the transmitted direction (pdf = 1)
+};
+constexpr uint32_t kNoChild = 0xFFFFFFFFu;
 
 struct DevCounters {
     unsigned long long primary_rays, primary_hits, shadow_traced, shadow_occluded, shadow_cached;
@@ -145,6 +160,11 @@ struct DevWave {
     uint32_t* fallback_count;
     uint32_t* sec_list;              // sample slots whose closest hit has specular lobes (aliases the shadow queues, drained by then)
     uint32_t* sec_count;
+    // wavefront Whitted recursion: k_shade turns the specular hits of this wave into the rays of the next level
+    SpawnRec* recs;                  // NULL: list the slots in sec_list instead (k_secondary follows)
+    double* next_rays;               // 6 doubles per ray of the next level
+    uint32_t* spawn_ctr;             // {records written, reflected rays, transmitted rays, -}
+    uint32_t next_t_base;            // first slot of the transmitted rays in the next level (= slots of this wave)
 };
 constexpr int kQueueA = 0, kQueueB = 1, kQueueC = 2;
 constexpr size_t kWaveCtrBytes = 8 + 4 * (size_t)LGB_MAX_LIGHTS * 3 * 2 + 16;     // + tie_count, fallback_count, sec_count, pad

@@ -119,8 +119,18 @@ def test_materials_and_whitted_parity(native, oracle, gpu_ctx, name):
     ref = o.capture(w, h, aov=True)
     dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
     out = dev.capture_aov(w, h)
-    rgba, st = dev.capture(w, h)
+    rgba, st = dev.capture(w, h)                                 # the ray trees level by level (default) ...
+    gpu_ctx.set_whitted(False)
+    try:
+        rgba_t, st_t = dev.capture(w, h)                         # ... and one thread per tree (k_secondary): same rays, same film
+    finally:
+        gpu_ctx.set_whitted(True)
     dev.destroy()
+    ft = parity.film_report(rgba_t, rgba)
+    assert ft["within_1_frac"] >= 0.999 and ft["identical_frac"] >= 0.999, ft
+    assert st_t["secondary_rays"] == st["secondary_rays"], (st_t["secondary_rays"], st["secondary_rays"])
+    ft = parity.film_report(rgba_t, ref["rgba"])
+    assert ft["alpha_equal"] and ft["within_1_frac"] >= 0.999 and ft["identical_frac"] >= 0.999, ft
     spp = sc.camera.num_samples()
 
     def retest(pid, i):
@@ -135,6 +145,57 @@ def test_materials_and_whitted_parity(native, oracle, gpu_ctx, name):
     assert f["identical_frac"] >= 0.999, f
     assert np.array_equal(rgba, out["rgba"])
     assert (st["secondary_rays"] > 0) == (sc.recursion > 0), st
+
+
+def test_whitted_through_every_entry_point(native, oracle, gpu_ctx):
+    """The specular ray trees behind the other ways into the path: capture_subset (compact output), tile ranks, forced pixel beams,
+    the lazy reference tree of `capture(scene, film)` (taken eagerly for such scenes), the C++ mirror, a scene without lights."""
+    import ctypes as C
+
+    import torch
+
+    import lasgun_b200
+    sc, (w, h) = scenes.materials((200, 150), 1, grouped=False)
+    ref = oracle.OracleScene(sc).capture(w, h)["rgba"]
+    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+    try:
+        full, st = dev.capture(w, h)
+        f = parity.film_report(full, ref)
+        assert f["alpha_equal"] and f["within_1_frac"] >= 0.999 and f["identical_frac"] >= 0.999, f
+        sub = np.zeros((h, w, 4), np.uint8); dev.capture_subset(2, 5, w, h, sub)
+        assert np.array_equal(sub.reshape(-1, 4)[2::5], full.reshape(-1, 4)[2::5]) and not sub.reshape(-1, 4)[0::5].any()
+        acc = torch.zeros((h, w, 4), dtype=torch.int32, device="cuda")
+        for r in range(3):
+            film = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+            dev.capture_device(w, h, film.data_ptr(), rank=r, ranks=3, want_stats=True)      # with stats the call waits for the frame
+            acc += film.to(torch.int32)
+        assert np.array_equal(acc.cpu().numpy().astype(np.uint8), full)
+    finally:
+        dev.destroy()
+    sc2, (w2, h2) = scenes.simplereflect(1, 96)                          # no transformed group: the primary rays can go through beams
+    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc2))
+    try:
+        plain, st_p = dev.capture(w2, h2)
+        gpu_ctx.set_beams(1)
+        beamed, st_b = dev.capture(w2, h2)
+        assert st_b["beams"] == 1 and st_p["beams"] == 0 and np.array_equal(beamed, plain) and st_b["secondary_rays"] == st_p["secondary_rays"]
+    finally:
+        gpu_ctx.set_beams(-1)
+        dev.destroy()
+    film = Film(w, h)
+    lasgun_b200.capture(sc, film, ctx=gpu_ctx)                           # flattens lazily; glass and mirrors make the device ask for the tree at once
+    assert np.array_equal(film.pixels(), full)
+    host = native.HostScene(sc)
+    rgba = np.zeros((h, w, 4), np.uint8)
+    assert native.lib().lgh_capture(host.h, w, h, rgba.ctypes.data_as(C.POINTER(C.c_uint8))) == 0, native.lib().lgh_last_error()
+    assert np.array_equal(rgba, full)
+    sc.lights.clear()                                                    # no light: ambient, background and the ray trees only
+    ref = oracle.OracleScene(sc).capture(w, h)["rgba"]
+    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+    dark, st = dev.capture(w, h)
+    dev.destroy()
+    f = parity.film_report(dark, ref)
+    assert f["alpha_equal"] and f["within_1_frac"] >= 0.999 and f["identical_frac"] >= 0.999 and st["secondary_rays"] > 0, (f, st)
 
 
 def test_reference_cornell_grazing_rays(native, oracle, gpu_ctx):
