@@ -248,9 +248,10 @@ int lgb_capture_subset(lgb_ctx* ctx, lgb_scene* scene, uint32_t k, uint32_t n, u
 
 /* Debug / parity: full-frame capture that also returns, per sample (index (y*w + x)*spp + s, sample
  * order of camera.rs:137-145), the canonical id of the closest-hit primitive (LGB_MISS if none), its
- * f64 ray parameter t (+inf if none) and a bit mask of occluded lights.  Any pointer may be NULL. */
+ * f64 ray parameter t (+inf if none), a bit mask of occluded lights and the sample's radiance (3 doubles: `li`,
+ * integrate.rs:23, before the weighted sum of integrate.rs:16-20).  Any pointer may be NULL. */
 int lgb_capture_aov(lgb_ctx* ctx, lgb_scene* scene, uint32_t w, uint32_t h, uint8_t* rgba_out,
-                    uint32_t* prim_id, double* t, uint32_t* occluded, lgb_stats* stats);
+                    uint32_t* prim_id, double* t, uint32_t* occluded, double* li, lgb_stats* stats);
 
 /* Device-resident capture for benchmarks and multi-GPU: renders the macro-tiles owned by
  * `tile_rank` of `tile_ranks` (all tiles when tile_ranks == 1) into `d_film`, a DEVICE pointer to a

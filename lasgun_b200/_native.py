@@ -113,7 +113,7 @@ def lib():
         "lgb_scene_node_count": (C.c_uint32, [vp]),
         "lgb_capture": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u8p, C.POINTER(Stats)]),
         "lgb_capture_subset": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u8p, C.POINTER(Stats)]),
-        "lgb_capture_aov": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u8p, u32p, dp, u32p, C.POINTER(Stats)]),
+        "lgb_capture_aov": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u8p, u32p, dp, u32p, dp, C.POINTER(Stats)]),
         "lgb_capture_device": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.POINTER(Stats)]),
         "lgb_trace_rays": (C.c_int, [vp, vp, dp, C.c_uint64, u32p, dp, dp, dp]),
         "lgb_measure_l2_read_gbs": (C.c_int, [vp, C.c_uint64, C.c_int, dp]),
@@ -425,14 +425,15 @@ class DeviceScene:
         self.ctx.check(lib().lgb_capture_subset(self.ctx.h, self.h, k, n, w, h, _ptr(rgba, C.c_uint8), C.byref(st)))
         return st.as_dict()
 
-    def capture_aov(self, w, h):
+    def capture_aov(self, w, h, li=False):
         ns = w * h * self.spp
         rgba = np.zeros((h, w, 4), np.uint8)
         ids = np.zeros((ns,), np.uint32); t = np.zeros((ns,), np.float64); occl = np.zeros((ns,), np.uint32)
+        rad = np.zeros((ns, 3), np.float64) if li else None
         st = Stats()
         self.ctx.check(lib().lgb_capture_aov(self.ctx.h, self.h, w, h, _ptr(rgba, C.c_uint8), _ptr(ids, C.c_uint32),
-                                             _ptr(t, C.c_double), _ptr(occl, C.c_uint32), C.byref(st)))
-        return {"rgba": rgba, "prim_id": ids, "t": t, "occl": occl, "stats": st.as_dict()}
+                                             _ptr(t, C.c_double), _ptr(occl, C.c_uint32), _ptr(rad, C.c_double) if li else None, C.byref(st)))
+        return {"rgba": rgba, "prim_id": ids, "t": t, "occl": occl, "li": rad, "stats": st.as_dict()}
 
     def capture_device(self, w, h, d_film_ptr, rank=0, ranks=1, stream=0, want_stats=False):
         st = Stats() if want_stats else None

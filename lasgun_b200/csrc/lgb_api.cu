@@ -23,6 +23,7 @@ bool render_fused(uint32_t spp);
 cudaError_t launch_level(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, int sms, cudaStream_t);
 cudaError_t launch_gather(const SpawnRec* recs, const uint32_t* nspec, double* rad_parent, const double* rad_child, uint64_t n_upper, cudaStream_t);
 cudaError_t launch_resolve(const DevWork&, const DevOut&, cudaStream_t);
+cudaError_t launch_export_li(const DevWork&, const DevOut&, const DevWave&, cudaStream_t);
 cudaError_t launch_trace(const DevScene&, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns, cudaStream_t);
 cudaError_t launch_l2_read(const void* buf, uint64_t bytes, int iters, float* sink, int sms, cudaStream_t);
 cudaError_t launch_fp32_peak(int iters, float* sink, int sms, cudaStream_t);
@@ -53,6 +54,7 @@ struct lgb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaEvent_t phase[kRenderEvents] = {};
     std::string error;
+    DevBuf aov_li;
     DevBuf radiance, film, counters, tiles, aov_id, aov_t, aov_occl, scratch, wave, wave_ctr, ties, beam;
     // levels of the specular ray trees (Whitted recursion): radiance and spawn records of every level (kept until the fold back up),
     // the rays of the current and the next level, the wavefront buffers of the current level, per-level counters
@@ -192,7 +194,7 @@ void lgb_shutdown(lgb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties, &c->beam, &c->raybuf[0], &c->raybuf[1], &c->wave2, &c->wave2_ctr, &c->lvl_ctr}) b->release();
+    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties, &c->beam, &c->raybuf[0], &c->raybuf[1], &c->wave2, &c->wave2_ctr, &c->lvl_ctr, &c->aov_li}) b->release();
     for (DevBuf& b : c->lvl_rad) b.release();
     for (DevBuf& b : c->lvl_recs) b.release();
     if (c->staging) cudaFreeHost(c->staging);
@@ -873,6 +875,7 @@ struct CaptureArgs {
     bool aov;
     void* d_film;                // device film or NULL (context film)
     cudaStream_t stream;
+    bool want_li = false;        // aov: also the radiance of every sample
 };
 
 // Wavefront buffers of `nslots` sample slots carved out of one allocation (layout: DevWave, lgb_types.cuh).
@@ -986,7 +989,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     if (s->cam.pixel_separation != 0.0 && W.aspect > 4.0)
         return fail(c, LGB_ERR_UNSUPPORTED, "orthographic capture with aspect > 4: the scene's coordinate bound assumed aspect <= 4");
     const DevScene& S = s->dev;
-    if (!render_fused(W.spp) || S.general) CU(c, c->radiance.reserve(std::max<uint64_t>(total, 1) * 3 * sizeof(double)));      // spp > 256 only
+    if (!render_fused(W.spp) || S.general || a.want_li) CU(c, c->radiance.reserve(std::max<uint64_t>(total, 1) * 3 * sizeof(double)));      // spp > 256 only
     CU(c, c->counters.reserve(sizeof(DevCounters)));
     // wavefront buffers: hit_t 8 + ps 24 + hit_ref 4 + occl 4 + 3 queues x 4 x lights bytes per sample slot,
     // + occluder 4 x lights bytes per pixel slot
@@ -1038,6 +1041,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     if (a.aov) {
         CU(c, c->aov_id.reserve(area * W.spp * 4)); CU(c, c->aov_t.reserve(area * W.spp * 8)); CU(c, c->aov_occl.reserve(area * W.spp * 4));
         O.aov_id = (uint32_t*)c->aov_id.p; O.aov_t = (double*)c->aov_t.p; O.aov_occl = (uint32_t*)c->aov_occl.p;
+        if (a.want_li) { CU(c, c->aov_li.reserve(std::max<uint64_t>(area * W.spp, 1) * 24)); O.aov_li = (double*)c->aov_li.p; }
     }
     CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));
     CU(c, cudaEventRecord(c->ev0, st));
@@ -1076,6 +1080,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         CU(c, launch_resolve(W, O, st));
         if (pev) CU(c, cudaEventRecord(pev[6], st));
     }
+    if (O.aov_li) CU(c, launch_export_li(W, O, V, st));
     CU(c, cudaEventRecord(c->ev1, st));
     if (stats && sync_stats) {
         DevCounters hc;
@@ -1122,15 +1127,17 @@ int lgb_capture(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint8_t* rgba,
     return finish_host(c, c->film.p, rgba, (size_t)w * h * 4, stp);
 }
 
-int lgb_capture_aov(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint8_t* rgba, uint32_t* prim_id, double* t, uint32_t* occl, lgb_stats* stats) {
+int lgb_capture_aov(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint8_t* rgba, uint32_t* prim_id, double* t, uint32_t* occl, double* li, lgb_stats* stats) {
     lgb_stats local; lgb_stats* stp = stats ? stats : &local;
     CaptureArgs a{w, h, 0, 0, 1, 0, 0, true, nullptr, nullptr};
+    a.want_li = li != nullptr;
     int rc = run_capture(c, s, a, stp, true);
     if (rc) return rc;
     const uint64_t ns = (uint64_t)w * h * s->cam.root * s->cam.root;
     if (prim_id) CU(c, cudaMemcpyAsync(prim_id, c->aov_id.p, ns * 4, cudaMemcpyDeviceToHost, c->stream));
     if (t) CU(c, cudaMemcpyAsync(t, c->aov_t.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
     if (occl) CU(c, cudaMemcpyAsync(occl, c->aov_occl.p, ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (li) CU(c, cudaMemcpyAsync(li, c->aov_li.p, ns * 24, cudaMemcpyDeviceToHost, c->stream));
     if (rgba) return finish_host(c, c->film.p, rgba, (size_t)w * h * 4, stp);
     CU(c, cudaStreamSynchronize(c->stream));
     return LGB_OK;

@@ -1564,6 +1564,17 @@ __global__ void __launch_bounds__(256) k_resolve(DevWork W, DevOut O) {
     reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)y * W.w + x] = quantise(c);
 }
 
+// Per-sample radiance for lgb_capture_aov: radiance buffer (slot order) -> caller's order ((y * w + x) * spp + s).
+__global__ void __launch_bounds__(256) k_export_li(DevWork W, DevOut O, DevWave V) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= W.n_pixels * W.spp || V.hit_ref[g] == kSlotUnused) return;
+    uint32_t x, y;
+    const uint32_t p = (uint32_t)g / W.spp, s = (uint32_t)g - p * W.spp;
+    if (!slot_to_pixel(W, p, x, y)) return;
+    const uint64_t gi = ((uint64_t)y * W.w + x) * W.spp + s;
+    O.aov_li[3 * gi] = O.radiance[3 * g]; O.aov_li[3 * gi + 1] = O.radiance[3 * g + 1]; O.aov_li[3 * gi + 2] = O.radiance[3 * g + 2];
+}
+
 // Caller-supplied rays (lgb_trace_rays): closest hit id, t, RayIntersection::ng()/ns() (surface.rs:107-118)
 template <bool INST>
 __global__ void __launch_bounds__(128) k_trace(DevScene S, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ngs, double* nss) {
@@ -1690,7 +1701,7 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
         mark(5);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
-    } else if (render_fused(W.spp)) {   // whole pixels per block: shade and resolve in one kernel, no radiance buffer
+    } else if (render_fused(W.spp) && !O.aov_li) {   // whole pixels per block: shade and resolve in one kernel, no radiance buffer
         const unsigned fb = (unsigned)((W.n_pixels + (256u / W.spp) - 1) / (256u / W.spp));
         if (inst) k_shade<true, true><<<fb, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, true><<<fb, 256, 0, stream>>>(S, C, sh, W, O, V);
         mark(5);
@@ -1728,6 +1739,12 @@ cudaError_t launch_level(const DevScene& S, const DevCamera& C, const DevShade& 
 cudaError_t launch_gather(const SpawnRec* recs, const uint32_t* nspec, double* rad_parent, const double* rad_child, uint64_t n_upper, cudaStream_t stream) {
     if (n_upper == 0) return cudaSuccess;
     k_gather<<<(unsigned)((n_upper + 255) / 256), 256, 0, stream>>>(recs, nspec, rad_parent, rad_child);
+    return cudaGetLastError();
+}
+cudaError_t launch_export_li(const DevWork& W, const DevOut& O, const DevWave& V, cudaStream_t stream) {
+    const uint64_t total = W.n_pixels * W.spp;
+    if (total == 0) return cudaSuccess;
+    k_export_li<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(W, O, V);
     return cudaGetLastError();
 }
 cudaError_t launch_resolve(const DevWork& W, const DevOut& O, cudaStream_t stream) {

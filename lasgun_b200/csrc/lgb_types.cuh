@@ -181,6 +181,7 @@ struct DevOut {
     uint32_t* aov_id;                // optional, global sample index
     double* aov_t;
     uint32_t* aov_occl;
+    double* aov_li;                  // optional: the radiance of every sample (li, integrate.rs:23), global sample index
     DevCounters* counters;           // optional
     uint8_t* film;                   // row-major RGBA8 (may be a peer pointer)
 };

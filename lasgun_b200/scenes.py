@@ -161,8 +161,10 @@ def spheres1m(count=1_000_000, res=2048):
     return scene, (res, res)
 
 
-def mixed4k(mesh_n=500, nspheres=100_000, res=(3840, 2160), supersampling=3):
-    """C5: MESH(500, 100) + 100k spheres on a shell + ground box, 2 lights, 16 spp."""
+def mixed4k(mesh_n=500, nspheres=100_000, res=(3840, 2160), supersampling=3, whitted=False):
+    """C5: MESH(500, 100) + 100k spheres on a shell + ground box, 2 lights, 16 spp.
+    whitted: the same geometry with a quarter of the spheres in glass, an eighth mirrors, a metal mesh and a mirror ground
+    (a large scene for the recursion of integrate.rs:69-132; not one of the five configs)."""
     scene = Scene()
     scene.set_ambient_light([0.1, 0.1, 0.1])
     camera = scene.set_perspective_camera(50.0)
@@ -171,15 +173,24 @@ def mixed4k(mesh_n=500, nspheres=100_000, res=(3840, 2160), supersampling=3):
     mesh = scene.add_obj(mesh_grid(mesh_n, 100.0))
     scene.add_point_light([-400.0, 500.0, 600.0], [0.8, 0.8, 0.8], [1.0, 0.0, 0.0])
     scene.add_point_light([500.0, 300.0, 200.0], [0.5, 0.45, 0.4], [1.0, 0.0, 0.0])
-    scene.root.add_obj_of(mesh, Material.plastic([0.7, 0.6, 0.5], [0.4, 0.4, 0.4], 0.25))
+    on = (lambda k: True) if whitted is True else (lambda k: bool(whitted) and k in whitted)      # (a subset, by name, for experiments)
+    scene.root.add_obj_of(mesh, Material.metal([0.2, 0.9, 1.1], [3.9, 2.4, 2.2], 0.3, 0.3) if on("metal") else Material.plastic([0.7, 0.6, 0.5], [0.4, 0.4, 0.4], 0.25))
     u = splitmix64_uniform(0x5EED0005, 4 * nspheres).reshape(nspheres, 4)
     theta = np.arccos(1.0 - 2.0 * u[:, 0])
     phi = 2.0 * math.pi * u[:, 1]
     R = 150.0 + 250.0 * u[:, 2]
     rad = 0.5 + 2.5 * u[:, 3]
     centers = np.stack([R * np.sin(theta) * np.cos(phi), R * np.cos(theta), R * np.sin(theta) * np.sin(phi)], axis=-1)
-    scene.root.add_spheres(centers, rad, _cube_palette(), np.arange(nspheres) % 8)
-    scene.root.add_box([-600.0, -130.0, -600.0], [600.0, -120.0, 600.0], Material.plastic([0.6, 0.6, 0.6], [0.0, 0.0, 0.0], 0.25))
+    pal = _cube_palette()
+    if on("glass"):
+        pal[0] = Material.glass([0.9, 0.9, 0.9], [0.9, 0.95, 0.9], 1.5); pal[4] = Material.glass([1.0, 0.7, 1.0], [0.7, 1.0, 0.7], 1.25)
+    if on("mirror"):
+        pal[2] = Material.mirror([0.8, 0.8, 0.85])
+    if on("matte"):
+        pal[6] = Material.matte([0.8, 0.5, 0.3], 30.0)
+    scene.root.add_spheres(centers, rad, pal, np.arange(nspheres) % 8)
+    scene.root.add_box([-600.0, -130.0, -600.0], [600.0, -120.0, 600.0],
+                       Material.mirror([0.6, 0.6, 0.6]) if on("ground") else Material.plastic([0.6, 0.6, 0.6], [0.0, 0.0, 0.0], 0.25))
     return scene, tuple(res)
 
 
@@ -355,4 +366,5 @@ CONFIGS = {
     "materials": materials,
     "simplereflect2k": lambda: simplereflect(2, 2048),                     # 4.2 Mpixel, 9 spp, depth 4: 37.7 M ray trees
     "materials2k": lambda: materials((2560, 1920), 1),                     # 4.9 Mpixel, 4 spp
+    "mixed4k_whitted": lambda: mixed4k(whitted=True),                      # the C5 geometry in glass / mirror / metal, 16 spp, depth 3
 }

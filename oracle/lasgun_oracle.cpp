@@ -1100,6 +1100,14 @@ static V3 background_bg(const Background& bg, V3 d) {
 
 struct SampleAOV { uint32_t prim_id; double t; uint32_t occl_mask; bool unsupported; };
 
+// Optional trace of one call tree of li() (orc_debug_li): every ray it casts, in order, as 8 doubles
+// {kind (0 path ray, 1 shadow ray), depth, o.xyz, d.xyz} followed by {prim id or -1, t}.
+static thread_local std::vector<double>* g_trace = nullptr;
+static void trace_ray(int kind, uint32_t depth, const Ray& r, double prim, double t) {
+    if (!g_trace) return;
+    const double v[10] = {(double)kind, (double)depth, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, prim, t};
+    g_trace->insert(g_trace->end(), v, v + 10);
+}
 // integrate/integrate.rs:23-132
 static V3 li(const Accel& acc, const Ray& ray, uint32_t depth, SampleAOV* aov) {
     const Scene& sc = *acc.scene;
@@ -1107,6 +1115,7 @@ static V3 li(const Accel& acc, const Ray& ray, uint32_t depth, SampleAOV* aov) {
     RayIsect isect = isect_default();
     const Primitive* shape = acc.root->intersect(ray, isect);
     if (aov) { aov->prim_id = 0xFFFFFFFFu; aov->t = INF; aov->occl_mask = 0; aov->unsupported = false; }
+    trace_ray(0, depth, ray, shape ? (double)isect.prim_id : -1.0, isect.t);
     if (!shape) return background_bg(sc.background, normalize(ray.d));
     if (g_cnt && depth == 0) g_cnt->primary_hits++;
     Material material;
@@ -1124,7 +1133,8 @@ static V3 li(const Accel& acc, const Ray& ray, uint32_t depth, SampleAOV* aov) {
         Ray sray = ray_new(p, light.position - p);
         if (g_cnt) g_cnt->shadow++;
         RayIsect si2 = isect_default();
-        acc.root->intersect(sray, si2);
+        const Primitive* blocker = acc.root->intersect(sray, si2);
+        trace_ray(1, depth, sray, blocker ? (double)si2.prim_id : -1.0, si2.t);
         if (si2.t < 1.0) { if (g_cnt) g_cnt->shadow_occluded++; if (aov) aov->occl_mask |= (1u << li_); continue; }
         V3 wi = light.position - p;
         double d = magnitude(wi);
@@ -1466,6 +1476,29 @@ double orc_retest_prim(void* accel, uint32_t prim_id, const double* o, const dou
         }
     }
     return INF;
+}
+// Closest hit of caller-supplied rays (Accel::intersect, bvh.rs:461-522): ids = canonical primitive id or 0xFFFFFFFF, t = isect.t.
+void orc_trace_rays(void* accel, const double* rays, uint64_t n, uint32_t* ids, double* ts) {
+    Accel* acc = (Accel*)accel;
+    for (uint64_t i = 0; i < n; i++) {
+        Ray r = ray_new(v3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]));
+        RayIsect is = isect_default();
+        const Primitive* shape = acc->root->intersect(r, is);
+        ids[i] = shape ? is.prim_id : 0xFFFFFFFFu;
+        ts[i] = shape ? is.t : INF;
+    }
+}
+// li() of one ray with a trace of every ray cast below it (10 doubles each, see trace_ray); returns the number of rays, out_li = radiance.
+uint64_t orc_debug_li(void* accel, const double* ray, double* out_li, double* out_trace, uint64_t cap) {
+    Accel* acc = (Accel*)accel;
+    std::vector<double> tr;
+    g_trace = &tr;
+    V3 c = li(*acc, ray_new(v3(ray[0], ray[1], ray[2]), v3(ray[3], ray[4], ray[5])), 0, nullptr);
+    g_trace = nullptr;
+    out_li[0] = c.x; out_li[1] = c.y; out_li[2] = c.z;
+    const uint64_t n = tr.size() / 10;
+    for (uint64_t i = 0; i < n && i < cap; i++) for (int k = 0; k < 10; k++) out_trace[10 * i + k] = tr[10 * i + k];
+    return n;
 }
 // Camera rays for one pixel (camera.rs:113-146): out = spp * 6 doubles (origin, d)
 void orc_camera_sample(void* s, uint32_t x, uint32_t y, uint32_t w, uint32_t h, double* out) {

@@ -73,6 +73,8 @@ def lib():
         "orc_retest_prim": (C.c_double, [vp, C.c_uint32, dp, dp]),
         "orc_camera_sample": (None, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, dp]),
         "orc_hardware_threads": (C.c_int, []),
+        "orc_trace_rays": (None, [vp, dp, C.c_uint64, u32p, dp]),
+        "orc_debug_li": (C.c_uint64, [vp, dp, dp, dp, C.c_uint64]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -200,6 +202,19 @@ class OracleScene:
             raise RuntimeError("oracle: traversal stack overflow (the reference would panic, bvh.rs:469)")
         out.update(render_ms=ms.value, prim_id=ids, t=ts, occl=occl, li=lis, counters=cnt.as_dict() if counters else None)
         return out
+
+    def debug_li(self, ray, cap=4096):
+        """li() of one ray and every ray cast below it: (radiance, array of {kind, depth, o, d, prim id or -1, t})."""
+        r = np.ascontiguousarray(ray, np.float64); out = np.zeros(3); tr = np.zeros((cap, 10))
+        n = lib().orc_debug_li(self.accel, _ptr(r, C.c_double), _ptr(out, C.c_double), _ptr(tr, C.c_double), cap)
+        return out, tr[:min(n, cap)]
+
+    def trace_rays(self, rays_od):
+        """Closest hit (canonical id, t) of rays given as (n, 6) origin + direction."""
+        rays = np.ascontiguousarray(rays_od, np.float64).reshape(-1, 6)
+        ids = np.zeros((len(rays),), np.uint32); t = np.zeros((len(rays),), np.float64)
+        lib().orc_trace_rays(self.accel, _ptr(rays, C.c_double), len(rays), _ptr(ids, C.c_uint32), _ptr(t, C.c_double))
+        return ids, t
 
     def camera_sample(self, x, y, w, h):
         out = np.zeros((self.spp, 6), np.float64)
