@@ -203,6 +203,7 @@ int lgb_device_count(void);
 int lgb_init(int device, lgb_ctx** out);
 void lgb_shutdown(lgb_ctx* ctx);
 #define LGB_OPT_COUNT_WORK 1        /* value != 0: captures also fill the work counters of lgb_stats */
+#define LGB_OPT_SIDE_STREAMS 4      /* 1 (default): the shadow-ray kernels of different lights overlap on a side stream; 0: one stream */
 #define LGB_OPT_WHITTED 3           /* glass / mirror ray trees: 1 (default) level-by-level wavefront on the frame's own kernels, 0 one thread per tree */
 #define LGB_OPT_BEAMS 2             /* pixel beams: at >= 4 samples per pixel the primary rays of a pixel share ONE bundle traversal
                                      * (k_beam) and then walk its leaf list; same results.  1 on, 0 off, -1 (default) automatic:

@@ -339,6 +339,10 @@ class Context:
         """LGB_OPT_BEAMS: 1 on (whenever spp >= 4), 0 off, -1 automatic (the default)."""
         self.check(lib().lgb_set_option(self.h, 2, int(mode)))
 
+    def set_side_streams(self, on: bool):
+        """LGB_OPT_SIDE_STREAMS: overlap the shadow chains of different lights (default on)."""
+        self.check(lib().lgb_set_option(self.h, 4, 1 if on else 0))
+
     def set_whitted(self, wavefront: bool):
         """LGB_OPT_WHITTED: the specular ray trees level by level (default) or one thread per tree."""
         self.check(lib().lgb_set_option(self.h, 3, 1 if wavefront else 0))

@@ -18,7 +18,7 @@
 
 namespace lgb {
 constexpr int kRenderEvents = 7;
-cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev, int part);
+cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev, int part, const SideStreams* side);
 bool render_fused(uint32_t spp);
 cudaError_t launch_level(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, int sms, cudaStream_t);
 cudaError_t launch_gather(const SpawnRec* recs, const uint32_t* nspec, double* rad_parent, const double* rad_child, uint64_t n_upper, cudaStream_t);
@@ -59,6 +59,8 @@ struct lgb_ctx {
     // levels of the specular ray trees (Whitted recursion): radiance and spawn records of every level (kept until the fold back up),
     // the rays of the current and the next level, the wavefront buffers of the current level, per-level counters
     DevBuf lvl_rad[kMaxRecursion + 1], lvl_recs[kMaxRecursion + 1], raybuf[2], wave2, wave2_ctr, lvl_ctr;
+    SideStreams side{};                    // streams the shadow chains of different lights are spread over (LGB_OPT_SIDE_STREAMS)
+    int side_streams = 1;
     int whitted_wavefront = 1;             // LGB_OPT_WHITTED: 1 level-by-level wavefront, 0 one thread per ray tree (k_secondary)
     int beams = -1;                        // LGB_OPT_BEAMS: 0 off, 1 on, -1 automatic
     std::vector<uint32_t> tile_host;
@@ -143,6 +145,12 @@ int lgb_init(int device, lgb_ctx** out) {
     CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(nullptr, cudaEventCreate(&c->ev0)); CU(nullptr, cudaEventCreate(&c->ev1)); CU(nullptr, cudaEventCreate(&c->ev2));
     for (auto& e : c->phase) CU(nullptr, cudaEventCreate(&e));
+    c->side.n = 1;                         // one side stream: two lights' chains at a time (a third stream measured no further gain)
+    for (int k = 0; k < c->side.n; k++) {
+        CU(nullptr, cudaStreamCreateWithFlags(&c->side.s[k], cudaStreamNonBlocking));
+        CU(nullptr, cudaEventCreateWithFlags(&c->side.join[k], cudaEventDisableTiming));
+    }
+    CU(nullptr, cudaEventCreateWithFlags(&c->side.fork, cudaEventDisableTiming));
     {   // scene arenas come from the stream-ordered pool and are kept cached between scenes (cudaMalloc/cudaFree cost ms)
         cudaMemPool_t mp;
         if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
@@ -187,6 +195,7 @@ int lgb_set_option(lgb_ctx* c, int option, int value) {
     if (option == LGB_OPT_COUNT_WORK) { c->count_work = value != 0; return LGB_OK; }
     if (option == LGB_OPT_BEAMS) { c->beams = value < 0 ? -1 : (value != 0); return LGB_OK; }
     if (option == LGB_OPT_WHITTED) { c->whitted_wavefront = value != 0; return LGB_OK; }
+    if (option == LGB_OPT_SIDE_STREAMS) { c->side_streams = value != 0; return LGB_OK; }
     return fail(c, LGB_ERR_INVALID, "lgb_set_option: unknown option");
 }
 
@@ -200,6 +209,8 @@ void lgb_shutdown(lgb_ctx* c) {
     if (c->staging) cudaFreeHost(c->staging);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
     for (auto& e : c->phase) cudaEventDestroy(e);
+    for (int k = 0; k < c->side.n; k++) { cudaStreamDestroy(c->side.s[k]); cudaEventDestroy(c->side.join[k]); }
+    cudaEventDestroy(c->side.fork);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1048,6 +1059,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     cudaEvent_t* pev = (stats && sync_stats && total) ? c->phase : nullptr;
     uint32_t tie_slots = 0;
     const bool st_on = a.aov || c->count_work;
+    const SideStreams* side = (c->side_streams && c->side.n) ? &c->side : nullptr;
     int wf = (S.general && c->whitted_wavefront) ? 4 : 0;           // launch_render stops after k_shade; the levels and the resolve follow here
     if (wf && S.specular && S.recursion > 0 && total) {             // k_shade of the camera wave spawns level 1
         CU(c, c->lvl_ctr.reserve(4 * (kMaxRecursion + 2) * 4));
@@ -1057,7 +1069,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     if (s->lazy_fn && !s->dev.rank && total) {
         // no rank tables yet: trace the primary rays, and only if one met two primitives at bit-identical t fetch the
         // caller's reference tree, build the tables and re-trace those slots (lasgun_b200.h, "Lazy reference tree")
-        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 1));
+        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 1, side));
         uint32_t ties = 0;
         CU(c, cudaMemcpyAsync(&ties, V.tie_count, 4, cudaMemcpyDeviceToHost, st));
         CU(c, cudaStreamSynchronize(st));
@@ -1067,11 +1079,11 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
             DevWork W2 = W;
             if (ties <= V.tie_cap) { W2.slot_list = V.tie_list; W2.n_list = ties; }
             else CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));          // too many to list: the whole frame again
-            CU(c, launch_render(s->dev, s->cam, s->shade, W2, O, V, st_on, a.aov, c->sm_count, st, ties <= V.tie_cap ? nullptr : pev, 1));
+            CU(c, launch_render(s->dev, s->cam, s->shade, W2, O, V, st_on, a.aov, c->sm_count, st, ties <= V.tie_cap ? nullptr : pev, 1, side));
         }
-        CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 2 | wf));
+        CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 2 | wf, side));
     } else {
-        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 3 | wf));
+        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 3 | wf, side));
     }
     uint64_t level_rays = 0; uint32_t level_launches = 0;
     if (wf && total) {                     // materials beyond plastic: the levels of the specular ray trees, then the film

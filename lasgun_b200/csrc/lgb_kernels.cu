@@ -1238,7 +1238,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork 
                 Ray64 ray;
                 ray.o = d3(V.ps[3 * (size_t)g], V.ps[3 * (size_t)g + 1], V.ps[3 * (size_t)g + 2]);
                 ray.d = lp - ray.o;                                                  // light/point.rs:43-44
-                if (occludes<INST>(S, oc, ray)) { V.occl[g] |= 1u << light; to_c = false; ncached++; }   // sole writer of occl[g] in this launch
+                if (occludes<INST>(S, oc, ray)) { atomicOr(&V.occl[g], 1u << light); to_c = false; ncached++; }   // (another light's chain may be running on a side stream)
             }
         }
         block_append(sc, to_c, g, V.queue + (size_t)(light * 3 + kQueueC) * V.queue_stride, &V.queue_count[light * 3 + kQueueC]);
@@ -1639,8 +1639,11 @@ bool render_fused(uint32_t spp) { return spp >= 1 && spp <= 256; }      // and !
 // `ev` (optional): kRenderEvents events recorded around the phases: start | primary | setup | anchor shadow rays |
 // pretest + remaining shadow rays | shade | resolve.
 // part 1 = k_primary (every slot, or W.slot_list: the re-trace of tied slots), 2 = everything after it, 3 = both.
+// `side` (optional): the shadow chains of the lights are independent of each other (own queues, own fetch counters, own occluder
+// table, one bit each in `occl`), so they are dealt round-robin over the launch stream and the side streams: the blocks of one
+// light's persistent kernel fill the SMs that the tail of another's has left idle.
 cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O,
-                          const DevWave& V, bool stats, bool all_shadows, int sms, cudaStream_t stream, cudaEvent_t* ev, int part) {
+                          const DevWave& V, bool stats, bool all_shadows, int sms, cudaStream_t stream, cudaEvent_t* ev, int part, const SideStreams* side) {
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], stream); };
     const uint64_t total = W.n_pixels * W.spp;
     const bool cache = W.spp > 1;
@@ -1677,19 +1680,24 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     if (inst) { if (all_shadows) k_setup<true, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); }
     else { if (all_shadows) k_setup<true, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); }
     mark(2);
-    // anchor rays (queue A), then the cached-occluder test of the rest (B -> C), then the survivors (queue C)
+    // per light: anchor rays (queue A), then the cached-occluder test of the rest (B -> C), then the survivors (queue C)
+    const int nside = (side && S.n_lights > 1) ? std::min<int>(side->n, (int)S.n_lights - 1) : 0;
+    for (int k = 0; k < nside; k++) { cudaEventRecord(side->fork, stream); cudaStreamWaitEvent(side->s[k], side->fork, 0); }
     for (int which = kQueueA; which <= (cache ? kQueueC : kQueueA); which += 2) {
         const unsigned sb = which == kQueueA ? (unsigned)std::min<uint64_t>((W.n_pixels + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, pblocks) : pblocks;
         for (uint32_t l = 0; l < S.n_lights; l++) {
+            const int lane = nside ? (int)(l % (uint32_t)(nside + 1)) : 0;
+            cudaStream_t ls = lane ? side->s[lane - 1] : stream;
             if (which == kQueueC) {
                 const unsigned tb = (unsigned)std::min<uint64_t>(ablocks, (uint64_t)sms * 4);
-                if (inst) k_pretest<true><<<tb, kAppendThreads, 0, stream>>>(S, W, O, V, l); else k_pretest<false><<<tb, kAppendThreads, 0, stream>>>(S, W, O, V, l);
+                if (inst) k_pretest<true><<<tb, kAppendThreads, 0, ls>>>(S, W, O, V, l); else k_pretest<false><<<tb, kAppendThreads, 0, ls>>>(S, W, O, V, l);
             }
-            if (inst) { if (stats) k_shadow<true, true><<<sb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, which); else k_shadow<false, true><<<sb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, which); }
-            else { if (stats) k_shadow<true, false><<<sb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, which); else k_shadow<false, false><<<sb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, which); }
+            if (inst) { if (stats) k_shadow<true, true><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); else k_shadow<false, true><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); }
+            else { if (stats) k_shadow<true, false><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); else k_shadow<false, false><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); }
         }
-        if (which == kQueueA) mark(3);
+        if (which == kQueueA) mark(3);      // (with side streams the anchor / rest split of the launch stream's own lights only)
     }
+    for (int k = 0; k < nside; k++) { cudaEventRecord(side->join[k], side->s[k]); cudaStreamWaitEvent(stream, side->join[k], 0); }
     mark(4);
     if (S.general) {                    // materials beyond plastic: every BSDF in k_shade, then the specular ray trees, then the film
         if (inst) k_shade<true, false, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, false, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);

@@ -132,6 +132,9 @@ struct DevCounters {
     unsigned int pad;
 };
 
+// Side streams for the per-light shadow chains (launch_render); host-side only.
+struct SideStreams { cudaStream_t s[3]; cudaEvent_t fork, join[3]; int n; };
+
 // Wavefront buffers, one entry per sample slot g = pixel_slot * spp + s.
 struct DevWave {
     double* hit_t;                   // closest-hit parameter (f64, reference arithmetic)

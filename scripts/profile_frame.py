@@ -12,6 +12,8 @@ else:
     sc, (w, h) = scenes.CONFIGS[name]()
 import os
 ctx = N.Context(0)
+if os.environ.get("LGB_SIDE") == "0":
+    ctx.set_side_streams(False)
 if os.environ.get("LGB_WHITTED") == "0":
     ctx.set_whitted(False)       # one thread per specular ray tree (k_secondary) instead of the level-by-level wavefront
 dev = N.DeviceScene(ctx, N.FlatScene(sc))
