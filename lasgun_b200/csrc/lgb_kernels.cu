@@ -996,8 +996,11 @@ __device__ __forceinline__ bool beam_slab(float lx, float ly, float lz, float hx
 // complete for every ray of the pixel whose own closest hit is not farther than B; k_leafp sends the others (depth
 // discontinuities inside the pixel) and the pixels with more than kBeamList leaves to the per-ray traversal.
 constexpr float kBeamMargin = 1.03125f;
+#ifndef LGB_BEAM_THREADS
+#define LGB_BEAM_THREADS 64          // as for k_leafp: 256 -> 64 threads per block, 54.02 -> 53.59 ms/frame
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(256, 4) k_beam(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
+__global__ void __launch_bounds__(LGB_BEAM_THREADS, 1024 / LGB_BEAM_THREADS) k_beam(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     LocalCounters lc = {};
@@ -1087,8 +1090,14 @@ __global__ void __launch_bounds__(256, 4) k_beam(DevScene S, DevCamera C, DevWor
 }
 
 // One thread per sample slot (the centre sample is already done): the leaves of its pixel's beam, nearest first.
+#ifndef LGB_LEAFP_PREFETCH
+#define LGB_LEAFP_PREFETCH 0
+#endif
+#ifndef LGB_LEAFP_THREADS
+#define LGB_LEAFP_THREADS 64         // a block waits for its slowest ray before it frees its slots: 256 -> 64 threads, 55.15 -> 53.97 ms/frame
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(256, 4) k_leafp(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
+__global__ void __launch_bounds__(LGB_LEAFP_THREADS, 1024 / LGB_LEAFP_THREADS) k_leafp(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
     __shared__ AppendScratch sc;
     const uint64_t total = W.n_pixels * W.spp;
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1106,8 +1115,15 @@ __global__ void __launch_bounds__(256, 4) k_leafp(DevScene S, DevCamera C, DevWo
             const float bound = V.beam_bound[p];
             Ray64 ray; RayF f; Trav T;
             enter_root<false>(S, world, ray, f, T, CUDART_INF);
+#if LGB_LEAFP_PREFETCH
+            uint2 e_next = n ? __ldg(&V.beam_list[p]) : make_uint2(0u, 0u);
+            for (uint32_t i = 0; i < n; i++) {
+                const uint2 e = e_next;
+                if (i + 1 < n) e_next = __ldg(&V.beam_list[(size_t)(i + 1) * W.n_pixels + p]);       // in flight while this leaf is tested
+#else
             for (uint32_t i = 0; i < n; i++) {
                 const uint2 e = __ldg(&V.beam_list[(size_t)i * W.n_pixels + p]);
+#endif
                 if (__uint_as_float(e.y) > T.best_up) continue;            // starts beyond the best hit (the list is only nearly sorted)
                 leaf_prims<false, STATS, false>(S, world, ray, f, T, (e.x >> 29) & 3u, ((e.x >> 24) & 31u) + 1u, e.x & kLeafFirstMask, CUDART_INF, lc);
             }
@@ -1314,6 +1330,9 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_shadow(Dev
 #ifndef LGB_SHADE_MIN_BLOCKS
 #define LGB_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef LGB_FUSED_THREADS
+#define LGB_FUSED_THREADS 256u
+#endif
 #ifndef LGB_WARP_RESOLVE
 #define LGB_WARP_RESOLVE 0           // 1: fused resolve through warp shuffles instead of shared memory + barrier (measured 0.4 ms slower)
 #endif
@@ -1382,7 +1401,7 @@ __global__ void __launch_bounds__(256, GENERAL ? LGB_GSHADE_MIN_BLOCKS : LGB_SHA
     uint64_t g;
     bool mine;
     if (FUSED) {
-        const uint32_t ppb = 256u / W.spp;                              // pixels per block
+        const uint32_t ppb = blockDim.x / W.spp;                        // pixels per block
         const uint64_t p = (uint64_t)blockIdx.x * ppb + threadIdx.x / W.spp;
         mine = threadIdx.x < ppb * W.spp && p < W.n_pixels;
         g = p * W.spp + threadIdx.x % W.spp;
@@ -1684,9 +1703,9 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
         if (W.beams && W.spp >= 4 && !inst && !W.slot_list) {
             // one bundle traversal per pixel, then every sample ray walks its pixel's leaf list; pixels whose bundle
             // reaches too many leaves go through the per-ray traversal (their slots are listed by k_leafp)
-            const unsigned bb = (unsigned)((W.n_pixels + 255) / 256), lb = (unsigned)((total + 255) / 256);
-            if (stats) { k_beam<true><<<bb, 256, 0, stream>>>(S, C, W, O, V); k_leafp<true><<<lb, 256, 0, stream>>>(S, C, W, O, V); }
-            else { k_beam<false><<<bb, 256, 0, stream>>>(S, C, W, O, V); k_leafp<false><<<lb, 256, 0, stream>>>(S, C, W, O, V); }
+            const unsigned bb = (unsigned)((W.n_pixels + LGB_BEAM_THREADS - 1) / LGB_BEAM_THREADS), lb = (unsigned)((total + LGB_LEAFP_THREADS - 1) / LGB_LEAFP_THREADS);
+            if (stats) { k_beam<true><<<bb, LGB_BEAM_THREADS, 0, stream>>>(S, C, W, O, V); k_leafp<true><<<lb, LGB_LEAFP_THREADS, 0, stream>>>(S, C, W, O, V); }
+            else { k_beam<false><<<bb, LGB_BEAM_THREADS, 0, stream>>>(S, C, W, O, V); k_leafp<false><<<lb, LGB_LEAFP_THREADS, 0, stream>>>(S, C, W, O, V); }
             DevWork Wf = W; Wf.slot_list = V.fallback_list; Wf.n_list = 0; Wf.n_list_dev = V.fallback_count;
             if (stats) k_primary<true, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, Wf, O, V); else k_primary<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, Wf, O, V);
         } else if (pb) {
@@ -1732,8 +1751,9 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
     } else if (render_fused(W.spp) && !O.aov_li) {   // whole pixels per block: shade and resolve in one kernel, no radiance buffer
-        const unsigned fb = (unsigned)((W.n_pixels + (256u / W.spp) - 1) / (256u / W.spp));
-        if (inst) k_shade<true, true><<<fb, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, true><<<fb, 256, 0, stream>>>(S, C, sh, W, O, V);
+        const unsigned ft = W.spp <= LGB_FUSED_THREADS ? LGB_FUSED_THREADS : 256u;        // threads per block: whole pixels, as few of them as the option allows
+        const unsigned fb = (unsigned)((W.n_pixels + (ft / W.spp) - 1) / (ft / W.spp));
+        if (inst) k_shade<true, true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V);
         mark(5);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     } else {
