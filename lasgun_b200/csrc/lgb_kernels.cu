@@ -843,6 +843,34 @@ __device__ __forceinline__ void block_append(AppendScratch& sc, bool mine, uint3
     __syncthreads();          // scratch is reused by the next call
 }
 
+// The same for N consecutive items per thread (thread t holds items N t .. N t + N - 1 of the block's range): one scan and one atomic
+// for N times the items, queue order = item order.
+template <int N>
+__device__ __forceinline__ void block_append_n(AppendScratch& sc, unsigned mine, const uint32_t* values, uint32_t* queue, uint32_t* count) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, below = (1u << lane) - 1u;
+    unsigned before = 0, wtot = 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) { const unsigned m = __ballot_sync(0xFFFFFFFFu, (mine >> k) & 1u); before += __popc(m & below); wtot += __popc(m); }
+    if (lane == 0) sc.warp_off[warp] = wtot;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const unsigned nw = blockDim.x >> 5;
+        const uint32_t c = lane < nw ? sc.warp_off[lane] : 0u;
+        uint32_t incl = c;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += v; }
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0 && tot) base = atomicAdd(count, tot);
+        if (lane == 0) sc.base = base;
+        if (lane < nw) sc.warp_off[lane] = incl - c;
+    }
+    __syncthreads();
+    uint32_t at = sc.base + sc.warp_off[warp] + before;
+#pragma unroll
+    for (int k = 0; k < N; k++) if ((mine >> k) & 1u) queue[at++] = values[k];
+    __syncthreads();          // scratch is reused by the next call
+}
+
 // The same for up to 2 x LGB_MAX_LIGHTS queues at once (k_setup: one pass over the block instead of one per queue).
 // flags: bit q set <=> this thread appends `value` to queue q (queue words: V.queue / V.queue_count index q' = map[q]).
 struct MultiAppendScratch { uint32_t warp_off[2 * LGB_MAX_LIGHTS][kAppendThreads / 32]; uint32_t base[2 * LGB_MAX_LIGHTS]; };
@@ -1239,6 +1267,10 @@ __device__ __forceinline__ bool occludes(const DevScene& S, uint32_t ref, const 
 }
 
 // Queue B -> occl bit (blocked by the occluder the pixel's anchor ray found) or queue C (needs a traversal).
+#ifndef LGB_PRETEST_ITEMS
+#define LGB_PRETEST_ITEMS 2          // 1 / 2 / 4 / 8 entries per thread and round: 53.60 / 52.54 / 53.20 / 53.12 ms/frame
+#endif
+constexpr int kPretestItems = LGB_PRETEST_ITEMS;
 template <bool INST>
 __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light) {
     __shared__ AppendScratch sc;
@@ -1247,22 +1279,31 @@ __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork 
     const double* L = S.lights + 9 * (size_t)light;
     const D3 lp = d3(L[0], L[1], L[2]);
     unsigned ncached = 0;
-    for (unsigned i0 = blockIdx.x * blockDim.x; i0 < total; i0 += gridDim.x * blockDim.x) {      // block-uniform trip count
-        const unsigned i = i0 + threadIdx.x;
-        bool to_c = false;
-        uint32_t g = 0;
-        if (i < total) {
-            g = V.queue[(size_t)(light * 3 + kQueueB) * V.queue_stride + i];
-            const uint32_t oc = V.occluder[(size_t)light * W.n_pixels + g / W.spp];
-            to_c = true;
-            if (oc != LGB_MISS) {
-                Ray64 ray;
-                ray.o = d3(V.ps[3 * (size_t)g], V.ps[3 * (size_t)g + 1], V.ps[3 * (size_t)g + 2]);
-                ray.d = lp - ray.o;                                                  // light/point.rs:43-44
-                if (occludes<INST>(S, oc, ray)) { atomicOr(&V.occl[g], 1u << light); to_c = false; ncached++; }   // (another light's chain may be running on a side stream)
+    // kPretestItems consecutive queue entries per thread and round: their loads are in flight together and one block-ordered
+    // append (three barriers) serves them all
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x * kPretestItems; i0 < total; i0 += (uint64_t)gridDim.x * blockDim.x * kPretestItems) {      // block-uniform trip count
+        const uint64_t first = i0 + threadIdx.x * kPretestItems;
+        uint32_t g[kPretestItems], oc[kPretestItems];
+        unsigned to_c = 0;
+#pragma unroll
+        for (int k = 0; k < kPretestItems; k++) {
+            g[k] = 0; oc[k] = LGB_MISS;
+            if (first + k < total) {
+                g[k] = V.queue[(size_t)(light * 3 + kQueueB) * V.queue_stride + first + k];
+                oc[k] = V.occluder[(size_t)light * W.n_pixels + g[k] / W.spp];
+                to_c |= 1u << k;
             }
         }
-        block_append(sc, to_c, g, V.queue + (size_t)(light * 3 + kQueueC) * V.queue_stride, &V.queue_count[light * 3 + kQueueC]);
+#pragma unroll
+        for (int k = 0; k < kPretestItems; k++) {
+            if (oc[k] != LGB_MISS) {
+                Ray64 ray;
+                ray.o = d3(V.ps[3 * (size_t)g[k]], V.ps[3 * (size_t)g[k] + 1], V.ps[3 * (size_t)g[k] + 2]);
+                ray.d = lp - ray.o;                                                  // light/point.rs:43-44
+                if (occludes<INST>(S, oc[k], ray)) { atomicOr(&V.occl[g[k]], 1u << light); to_c &= ~(1u << k); ncached++; }   // (another light's chain may be running on a side stream)
+            }
+        }
+        block_append_n<kPretestItems>(sc, to_c, g, V.queue + (size_t)(light * 3 + kQueueC) * V.queue_stride, &V.queue_count[light * 3 + kQueueC]);
     }
     if (O.counters) {
         const unsigned long long n = warp_sum(ncached);
