@@ -1024,6 +1024,9 @@ __device__ __forceinline__ bool beam_slab(float lx, float ly, float lz, float hx
 // complete for every ray of the pixel whose own closest hit is not farther than B; k_leafp sends the others (depth
 // discontinuities inside the pixel) and the pixels with more than kBeamList leaves to the per-ray traversal.
 constexpr float kBeamMargin = 1.03125f;
+#ifndef LGB_BEAM_PRIMS
+#define LGB_BEAM_PRIMS 1             // the bundle lists primitives, not leaves: 52.56 -> 48.44 ms/frame (k_leafp 10.8 -> 6.5, k_beam 4.4 -> 5.2 ms)
+#endif
 #ifndef LGB_BEAM_THREADS
 #define LGB_BEAM_THREADS 64          // as for k_leafp: 256 -> 64 threads per block, 54.02 -> 53.59 ms/frame
 #endif
@@ -1051,12 +1054,48 @@ __global__ void __launch_bounds__(LGB_BEAM_THREADS, 1024 / LGB_BEAM_THREADS) k_b
             bool over = false;
             while (cur != kDone && !over) {
                 if (cur & kLeafBit) {                  // a leaf the bundle enters before the bound: list it, test the centre ray
+#if LGB_BEAM_PRIMS
+                    // ... primitive by primitive: the bundle against the primitive's own (padded) box, so that the sample rays of
+                    // the pixel are handed only the primitives their bundle can reach -- a quarter of a leaf on average
+                    const uint32_t type = (cur >> 29) & 3u, count = ((cur >> 24) & 31u) + 1u, first = cur & kLeafFirstMask;
+                    for (uint32_t i = 0; i < count; i++) {
+                        const uint32_t idx = first + i;
+                        float lx, ly, lz, hx, hy, hz;
+                        if (type == LGB_PRIM_TRIANGLE) {
+                            const float4* tp = S.tri + 3 * (size_t)idx;
+                            const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+                            lx = fminf(q0.x, fminf(q1.x, q2.x)); hx = fmaxf(q0.x, fmaxf(q1.x, q2.x));
+                            ly = fminf(q0.y, fminf(q1.y, q2.y)); hy = fmaxf(q0.y, fmaxf(q1.y, q2.y));
+                            lz = fminf(q0.z, fminf(q1.z, q2.z)); hz = fmaxf(q0.z, fmaxf(q1.z, q2.z));
+                        } else if (type == LGB_PRIM_SPHERE) {
+                            const float4 sp4 = __ldg(&S.sph32[idx]);
+                            const float rr = __fadd_ru(sp4.w, f.err);
+                            lx = __fsub_rd(sp4.x, rr); hx = __fadd_ru(sp4.x, rr); ly = __fsub_rd(sp4.y, rr); hy = __fadd_ru(sp4.y, rr); lz = __fsub_rd(sp4.z, rr); hz = __fadd_ru(sp4.z, rr);
+                        } else {
+                            const float4 lo = __ldg(&S.cub32[2 * idx]), hi = __ldg(&S.cub32[2 * idx + 1]);      // padded already
+                            lx = lo.x; ly = lo.y; lz = lo.z; hx = hi.x; hy = hi.y; hz = hi.z;
+                        }
+                        if (type != LGB_PRIM_CUBOID) {                                 // the padding of the node boxes (k_make_items)
+                            lx = __fsub_rd(lx, f.err); ly = __fsub_rd(ly, f.err); lz = __fsub_rd(lz, f.err);
+                            hx = __fadd_ru(hx, f.err); hy = __fadd_ru(hy, f.err); hz = __fadd_ru(hz, f.err);
+                        }
+                        float tn;
+                        if (!beam_slab<8>(lx, ly, lz, hx, hy, hz, f, B, tn) || tn > bound) continue;
+                        if (n == (uint32_t)kBeamList) { over = true; break; }
+                        list[n++] = make_uint2(kLeafBit | (type << 29) | idx, __float_as_uint(tn));
+                        leaf_prims<false, STATS, false>(S, world, ray, f, T, type, 1u, idx, CUDART_INF, lc);
+                        bound = T.best_up * kBeamMargin;
+                    }
+                    if (over) break;
+                    cur = kDone;
+#else
                     const float t = cur_t;
                     if (n == (uint32_t)kBeamList) { over = true; break; }
                     list[n++] = make_uint2(cur, __float_as_uint(t));
                     leaf_prims<false, STATS, false>(S, world, ray, f, T, (cur >> 29) & 3u, ((cur >> 24) & 31u) + 1u, cur & kLeafFirstMask, CUDART_INF, lc);
                     bound = T.best_up * kBeamMargin;
                     cur = kDone;
+#endif
                 } else {
                     const float4* np = S.nodes + 4 * (size_t)cur;
                     const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);

@@ -175,7 +175,10 @@ constexpr int kMatStride = 12;
 constexpr uint32_t kMatDiffuse = 1u, kMatGlossy = 2u, kMatGeneral = 4u, kMatSpecular = 8u;
 constexpr uint32_t kMaxRecursion = 12;         // depth of the per-ray stack k_secondary keeps (lgb_scene_create rejects deeper scenes)
 constexpr uint32_t kTieCap = 1u << 20;
-constexpr int kBeamList = 48;                  // leaves a pixel beam may reach before the pixel falls back to per-ray traversal
+#ifndef LGB_BEAM_LIST
+#define LGB_BEAM_LIST 48
+#endif
+constexpr int kBeamList = LGB_BEAM_LIST;                  // leaves a pixel beam may reach before the pixel falls back to per-ray traversal
 constexpr uint32_t kBeamOverflow = 0xFFFFFFFFu;
 constexpr uint32_t kSlotUnused = 0xFFFFFFFEu;
 
