@@ -54,7 +54,7 @@ struct lgb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaEvent_t phase[kRenderEvents] = {};
     std::string error;
-    DevBuf aov_li;
+    DevBuf aov_li, beam2;
     DevBuf radiance, film, counters, tiles, aov_id, aov_t, aov_occl, scratch, wave, wave_ctr, ties, beam;
     // levels of the specular ray trees (Whitted recursion): radiance and spawn records of every level (kept until the fold back up),
     // the rays of the current and the next level, the wavefront buffers of the current level, per-level counters
@@ -203,7 +203,7 @@ void lgb_shutdown(lgb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties, &c->beam, &c->raybuf[0], &c->raybuf[1], &c->wave2, &c->wave2_ctr, &c->lvl_ctr, &c->aov_li}) b->release();
+    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties, &c->beam, &c->raybuf[0], &c->raybuf[1], &c->wave2, &c->wave2_ctr, &c->lvl_ctr, &c->aov_li, &c->beam2}) b->release();
     for (DevBuf& b : c->lvl_rad) b.release();
     for (DevBuf& b : c->lvl_recs) b.release();
     if (c->staging) cudaFreeHost(c->staging);
@@ -906,6 +906,7 @@ static DevWave carve_wave(void* wave, void* ctr, uint64_t nslots, uint32_t nl) {
     V.tie_count = V.queue_fetch + LGB_MAX_LIGHTS * 3;
     V.fallback_count = V.tie_count + 1;
     V.sec_count = V.fallback_count + 1;
+    V.free_count = V.sec_count + 2;
     V.fallback_list = V.queue;                       // the shadow queues are written only after the primary phase ...
     V.sec_list = V.queue;                            // ... and drained before k_shade lists the specular slots
     return V;
@@ -1022,6 +1023,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         V.tie_count = V.queue_fetch + LGB_MAX_LIGHTS * 3;
         V.fallback_count = V.tie_count + 1;
         V.sec_count = V.fallback_count + 1;
+        V.free_count = V.sec_count + 2;
         V.sec_list = V.queue;                            // the shadow queues are drained before k_shade lists the specular slots
         V.fallback_list = V.queue;                       // the shadow queues are written only after the primary phase
         // automatic: where a bundle of >= 8 rays shares a traversal that is long enough to be worth sharing (measured: a loss on
@@ -1032,6 +1034,10 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
             CU(c, c->beam.reserve(npx * kBeamList * sizeof(uint2) + npx * 8));
             V.beam_list = (uint2*)c->beam.p; V.beam_count = (uint32_t*)((char*)c->beam.p + npx * kBeamList * sizeof(uint2));
             V.beam_bound = (float*)(V.beam_count + npx);
+            if (S.n_lights > 1 && c->side_streams && c->side.n) {       // shadow beams of the light on the side stream
+                CU(c, c->beam2.reserve(npx * kBeamList * sizeof(uint2) + npx * 4));
+                V.beam_list2 = (uint2*)c->beam2.p; V.beam_count2 = (uint32_t*)((char*)c->beam2.p + npx * kBeamList * sizeof(uint2));
+            }
         }
         V.tie_list = nullptr; V.tie_cap = 0;
         if (s->lazy_fn && !s->dev.rank) {

@@ -1023,7 +1023,10 @@ __device__ __forceinline__ bool beam_slab(float lx, float ly, float lz, float hx
 // the walk -- a node or leaf whose bundle entry distance exceeds B = t_c (1 + 1/32) is not visited.  The list is then
 // complete for every ray of the pixel whose own closest hit is not farther than B; k_leafp sends the others (depth
 // discontinuities inside the pixel) and the pixels with more than kBeamList leaves to the per-ray traversal.
-constexpr float kBeamMargin = 1.03125f;
+#ifndef LGB_BEAM_MARGIN
+#define LGB_BEAM_MARGIN 1.03125f
+#endif
+constexpr float kBeamMargin = LGB_BEAM_MARGIN;
 #ifndef LGB_BEAM_PRIMS
 #define LGB_BEAM_PRIMS 1             // the bundle lists primitives, not leaves: 52.56 -> 48.44 ms/frame (k_leafp 10.8 -> 6.5, k_beam 4.4 -> 5.2 ms)
 #endif
@@ -1329,8 +1332,10 @@ __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork 
             g[k] = 0; oc[k] = LGB_MISS;
             if (first + k < total) {
                 g[k] = V.queue[(size_t)(light * 3 + kQueueB) * V.queue_stride + first + k];
-                oc[k] = V.occluder[(size_t)light * W.n_pixels + g[k] / W.spp];
-                to_c |= 1u << k;
+                if (g[k] != kEntryDone) {                                          // (k_swalk has resolved it from the pixel's shadow beam)
+                    oc[k] = V.occluder[(size_t)light * W.n_pixels + g[k] / W.spp];
+                    to_c |= 1u << k;
+                }
             }
         }
 #pragma unroll
@@ -1348,6 +1353,164 @@ __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork 
         const unsigned long long n = warp_sum(ncached);
         if (lane == 0 && n) { atomicAdd(&O.counters->shadow_cached, n); atomicAdd(&O.counters->shadow_occluded, n); }
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&O.counters->shadow_traced, (unsigned long long)total);
+    }
+}
+
+// ================================================================== shadow beams
+// The shadow rays of a pixel towards one light are a bundle too: seen from the light they share their origin, and their
+// directions (light -> shadow origin of every sample) differ by the footprint of one pixel on the surface.  k_sbeam, one thread per
+// ANCHOR ray (queue A: the centre sample of a pixel) that k_shadow found FREE, walks the BVH once with that bundle over the segment
+// light .. surface (parameter s in [0, 1], the reference's t = 1 - s) and lists the primitives whose own boxes the bundle meets
+// (f32 only: pure culling).  Where the list is complete the other samples of the pixel need no traversal at all: k_swalk tests
+// them against the listed primitives only (f32 filter + exact f64 test) and removes them from queue B.  Whatever is left (pixels
+// whose anchor is blocked -- k_pretest tries its occluder on the other samples first, as before --, overflowing lists, pixels
+// without an anchor ray) goes the old way: k_pretest, then k_shadow over queue C.
+#ifndef LGB_SHADOW_BEAMS
+#define LGB_SHADOW_BEAMS 1           // 48.45 -> 45.50 ms/frame on mixed4k (bundles only for pixels whose anchor ray is free; with every anchor as a bundle: 54.3)
+#endif
+template <bool STATS>
+__global__ void __launch_bounds__(LGB_BEAM_THREADS, 1024 / LGB_BEAM_THREADS) k_sbeam(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light,
+                                                                                     uint2* list_out, uint32_t* count_out) {
+    const unsigned total = V.free_count[light];                           // the anchor rays k_shadow found free (listed in queue C's space)
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    LocalCounters lc = {};
+    if (i < total) {
+        const uint32_t ga = V.queue[(size_t)(light * 3 + kQueueC) * V.queue_stride + i];
+        const uint32_t p = ga / W.spp;
+        {
+        const double* Lp = S.lights + 9 * (size_t)light;
+        const D3 lp = d3(Lp[0], Lp[1], Lp[2]);
+        Ray64 centre; centre.o = lp;                                      // the bundle runs from the common point towards the surface
+        centre.d = d3(V.ps[3 * (size_t)ga], V.ps[3 * (size_t)ga + 1], V.ps[3 * (size_t)ga + 2]) - lp;
+        // per-axis interval of the directions over the samples of the pixel that have a shadow origin
+        double dmin[3] = {centre.d.x, centre.d.y, centre.d.z}, dmax[3] = {centre.d.x, centre.d.y, centre.d.z};
+        for (uint32_t k = 0; k < W.spp; k++) {
+            const size_t g = (size_t)p * W.spp + k;
+            const uint32_t ref = V.hit_ref[g];
+            if (ref == LGB_MISS || ref == kSlotUnused) continue;
+            const double dx = V.ps[3 * g] - lp.x, dy = V.ps[3 * g + 1] - lp.y, dz = V.ps[3 * g + 2] - lp.z;
+            dmin[0] = fmin(dmin[0], dx); dmax[0] = fmax(dmax[0], dx); dmin[1] = fmin(dmin[1], dy); dmax[1] = fmax(dmax[1], dy);
+            dmin[2] = fmin(dmin[2], dz); dmax[2] = fmax(dmax[2], dz);
+        }
+        const double dc[3] = {centre.d.x, centre.d.y, centre.d.z};
+        float sp[3];
+        for (int a = 0; a < 3; a++) {                                     // as make_beam: |1/d| over the bundle relative to the centre's
+            if (!(dmin[a] > 0.0) && !(dmax[a] < 0.0)) { sp[a] = 1e30f; continue; }
+            const double lo = fmin(fabs(dmin[a]), fabs(dmax[a])), hi = fmax(fabs(dmin[a]), fabs(dmax[a])), c = fabs(dc[a]);
+            const double up = c / lo - 1.0, dn = 1.0 - c / hi;
+            sp[a] = __double2float_ru(fmax(fmax(up, dn), 0.0) * 1.0000001 + 4e-7);
+        }
+        BeamF B; B.sx = sp[0]; B.sy = sp[1]; B.sz = sp[2];
+        const RayF f = make_rayf(centre, S.err_abs);
+        const float smax = 1.0f + 1e-5f;                                  // occluders lie at s in (0, 1]; the slack covers the f32 slab arithmetic
+        uint32_t stack[kStackDepth]; int sp_ = 0;
+        uint2 list[kBeamList];
+        uint32_t n = 0, cur = 0;
+        bool over = false;
+        while (cur != kDone && !over) {
+            if (cur & kLeafBit) {
+                const uint32_t type = (cur >> 29) & 3u, count = ((cur >> 24) & 31u) + 1u, first = cur & kLeafFirstMask;
+                for (uint32_t k = 0; k < count; k++) {
+                    const uint32_t idx = first + k;
+                    float lx, ly, lz, hx, hy, hz;
+                    if (type == LGB_PRIM_TRIANGLE) {
+                        const float4* tp = S.tri + 3 * (size_t)idx;
+                        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+                        lx = fminf(q0.x, fminf(q1.x, q2.x)); hx = fmaxf(q0.x, fmaxf(q1.x, q2.x));
+                        ly = fminf(q0.y, fminf(q1.y, q2.y)); hy = fmaxf(q0.y, fmaxf(q1.y, q2.y));
+                        lz = fminf(q0.z, fminf(q1.z, q2.z)); hz = fmaxf(q0.z, fmaxf(q1.z, q2.z));
+                    } else if (type == LGB_PRIM_SPHERE) {
+                        const float4 s4 = __ldg(&S.sph32[idx]);
+                        const float rr = __fadd_ru(s4.w, f.err);
+                        lx = __fsub_rd(s4.x, rr); hx = __fadd_ru(s4.x, rr); ly = __fsub_rd(s4.y, rr); hy = __fadd_ru(s4.y, rr); lz = __fsub_rd(s4.z, rr); hz = __fadd_ru(s4.z, rr);
+                    } else {
+                        const float4 lo = __ldg(&S.cub32[2 * idx]), hi = __ldg(&S.cub32[2 * idx + 1]);
+                        lx = lo.x; ly = lo.y; lz = lo.z; hx = hi.x; hy = hi.y; hz = hi.z;
+                    }
+                    if (type != LGB_PRIM_CUBOID) {
+                        lx = __fsub_rd(lx, f.err); ly = __fsub_rd(ly, f.err); lz = __fsub_rd(lz, f.err);
+                        hx = __fadd_ru(hx, f.err); hy = __fadd_ru(hy, f.err); hz = __fadd_ru(hz, f.err);
+                    }
+                    float tn;
+                    if (!beam_slab<8>(lx, ly, lz, hx, hy, hz, f, B, tn) || tn > smax) continue;
+                    if (n == (uint32_t)kBeamList) { over = true; break; }
+                    list[n++] = make_uint2(kLeafBit | (type << 29) | idx, __float_as_uint(tn));
+                }
+                cur = kDone;
+            } else {
+                const float4* np = S.nodes + 4 * (size_t)cur;
+                const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+                const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+                if (STATS) lc.node_tests++;
+                float t0, t1;
+                bool h0, h1;
+                switch (f.oct) {
+#define LGB_BEAM_CASE(o) case o: h0 = beam_slab<o>(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, f, B, t0); h1 = beam_slab<o>(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, f, B, t1); break;
+                LGB_BEAM_CASE(0) LGB_BEAM_CASE(1) LGB_BEAM_CASE(2) LGB_BEAM_CASE(3) LGB_BEAM_CASE(4) LGB_BEAM_CASE(5) LGB_BEAM_CASE(6)
+                default: h0 = beam_slab<7>(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, f, B, t0); h1 = beam_slab<7>(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, f, B, t1); break;
+#undef LGB_BEAM_CASE
+                }
+                h0 = h0 && t0 <= smax; h1 = h1 && t1 <= smax;
+                const uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+                if (h0 && h1) { cur = c0; stack[sp_++] = c1; }
+                else if (h0) cur = c0;
+                else if (h1) cur = c1;
+                else cur = kDone;
+            }
+            if (cur == kDone && sp_ && !over) cur = stack[--sp_];
+        }
+        if (!over) {
+            for (uint32_t k = 0; k < n; k++) list_out[(size_t)k * W.n_pixels + p] = list[k];
+            count_out[p] = n;                                             // complete: k_swalk serves the other samples from it
+        }
+        }
+    }
+    if (O.counters && STATS) {
+        unsigned long long nt = warp_sum(lc.node_tests);
+        if (lane == 0) atomicAdd(&O.counters->node_tests, nt);
+    }
+}
+// One thread per queue-B entry (the non-anchor samples): where the pixel's bundle left a complete list, the ray is tested against
+// the listed primitives alone, any hit with t < 1 (light/point.rs:48-49), and the entry is taken out of the queue.
+template <bool STATS>
+__global__ void __launch_bounds__(LGB_LEAFP_THREADS, 1024 / LGB_LEAFP_THREADS) k_swalk(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light,
+                                                                                       const uint2* list_in, const uint32_t* count_in) {
+    const unsigned total = V.queue_count[light * 3 + kQueueB];
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    LocalCounters lc = {};
+    unsigned occluded = 0;
+    if (i < total) {
+        uint32_t* slot = V.queue + (size_t)(light * 3 + kQueueB) * V.queue_stride + i;
+        const uint32_t g = *slot;
+        const uint32_t p = g / W.spp;
+        const uint32_t n = count_in[p];
+        if (n != kBeamOverflow) {
+            const double* Lp = S.lights + 9 * (size_t)light;
+            Ray64 world;
+            world.o = d3(V.ps[3 * (size_t)g], V.ps[3 * (size_t)g + 1], V.ps[3 * (size_t)g + 2]);
+            world.d = d3(Lp[0], Lp[1], Lp[2]) - world.o;
+            Ray64 ray; RayF f; Trav T;
+            enter_root<false>(S, world, ray, f, T, 1.0);
+            bool hit = false;
+            for (uint32_t k = 0; k < n && !hit; k++) {
+                const uint2 e = __ldg(&list_in[(size_t)k * W.n_pixels + p]);
+                hit = leaf_prims<true, STATS, false>(S, world, ray, f, T, (e.x >> 29) & 3u, 1u, e.x & kLeafFirstMask, 1.0, lc);
+            }
+            if (hit) { atomicOr(&V.occl[g], 1u << light); occluded++; }
+            *slot = kEntryDone;
+        }
+    }
+    if (O.counters) {
+        unsigned long long v = warp_sum(occluded);
+        if (lane == 0 && v) atomicAdd(&O.counters->shadow_occluded, v);
+        if (STATS) {
+            for (int k = 0; k < 3; k++) {
+                unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
+                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); }
+            }
+        }
     }
 }
 
@@ -1388,6 +1551,13 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_shadow(Dev
             if (done) {
                 if (T.best.ref != LGB_MISS) { atomicOr(&V.occl[g], 1u << light); occluded++; }
                 if (record) V.occluder[(size_t)light * W.n_pixels + g / W.spp] = T.best.ref;
+                if (record && W.beams && T.best.ref == LGB_MISS) {       // a free anchor: its pixel gets a shadow beam (k_sbeam); listed in queue C's space
+                    const unsigned peers = __activemask(), leader = __ffs(peers) - 1;
+                    uint32_t base = 0;
+                    if (lane == leader) base = atomicAdd(V.free_count + light, (uint32_t)__popc(peers));
+                    base = __shfl_sync(peers, base, leader);
+                    V.queue[(size_t)(light * 3 + kQueueC) * V.queue_stride + base + __popc(peers & ((1u << lane) - 1u))] = g;
+                }
                 active = false;
             }
         }
@@ -1804,20 +1974,31 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     // per light: anchor rays (queue A), then the cached-occluder test of the rest (B -> C), then the survivors (queue C)
     const int nside = (side && S.n_lights > 1) ? std::min<int>(side->n, (int)S.n_lights - 1) : 0;
     for (int k = 0; k < nside; k++) { cudaEventRecord(side->fork, stream); cudaStreamWaitEvent(side->s[k], side->fork, 0); }
-    for (int which = kQueueA; which <= (cache ? kQueueC : kQueueA); which += 2) {
-        const unsigned sb = which == kQueueA ? (unsigned)std::min<uint64_t>((W.n_pixels + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, pblocks) : pblocks;
-        for (uint32_t l = 0; l < S.n_lights; l++) {
-            const int lane = nside ? (int)(l % (uint32_t)(nside + 1)) : 0;
-            cudaStream_t ls = lane ? side->s[lane - 1] : stream;
+    // (light by light on its lane: the shadow-beam lists of a lane are reused by its next light)
+    for (uint32_t l = 0; l < S.n_lights; l++) {
+        const int lane = nside ? (int)(l % (uint32_t)(nside + 1)) : 0;
+        cudaStream_t ls = lane ? side->s[lane - 1] : stream;
+        uint2* blist = lane ? V.beam_list2 : V.beam_list; uint32_t* bcount = lane ? V.beam_count2 : V.beam_count;
+        const bool sbeams = LGB_SHADOW_BEAMS && W.beams && cache && !inst && blist && lane < 2;
+        for (int which = kQueueA; which <= (cache ? kQueueC : kQueueA); which += 2) {
+            const unsigned sb = which == kQueueA ? (unsigned)std::min<uint64_t>((W.n_pixels + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, pblocks) : pblocks;
             if (which == kQueueC) {
+                if (sbeams) {                       // pixels whose anchor ray is free: one bundle walk, then the other samples from its list, no traversal
+                    if ((e = cudaMemsetAsync(bcount, 0xFF, (size_t)W.n_pixels * 4, ls)) != cudaSuccess) return e;
+                    const unsigned bb = (unsigned)((W.n_pixels + LGB_BEAM_THREADS - 1) / LGB_BEAM_THREADS);
+                    if (stats) k_sbeam<true><<<bb, LGB_BEAM_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount); else k_sbeam<false><<<bb, LGB_BEAM_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount);
+                    const unsigned wb = (unsigned)((total + LGB_LEAFP_THREADS - 1) / LGB_LEAFP_THREADS);
+                    if (stats) k_swalk<true><<<wb, LGB_LEAFP_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount); else k_swalk<false><<<wb, LGB_LEAFP_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount);
+                }
                 const unsigned tb = (unsigned)std::min<uint64_t>(ablocks, (uint64_t)sms * 4);
                 if (inst) k_pretest<true><<<tb, kAppendThreads, 0, ls>>>(S, W, O, V, l); else k_pretest<false><<<tb, kAppendThreads, 0, ls>>>(S, W, O, V, l);
             }
             if (inst) { if (stats) k_shadow<true, true><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); else k_shadow<false, true><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); }
             else { if (stats) k_shadow<true, false><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); else k_shadow<false, false><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); }
+            if (which == kQueueA && l == 0) mark(3);      // (the anchor / rest split of the first light only)
         }
-        if (which == kQueueA) mark(3);      // (with side streams the anchor / rest split of the launch stream's own lights only)
     }
+    if (S.n_lights == 0) mark(3);
     for (int k = 0; k < nside; k++) { cudaEventRecord(side->join[k], side->s[k]); cudaStreamWaitEvent(stream, side->join[k], 0); }
     mark(4);
     if (S.general) {                    // materials beyond plastic: every BSDF in k_shade, then the specular ray trees, then the film

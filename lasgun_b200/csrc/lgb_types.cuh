@@ -159,6 +159,9 @@ struct DevWave {
     uint2* beam_list;                // [i * n_pixels + pixel_slot] = (leaf word, entry distance bits)
     uint32_t* beam_count;            // per pixel slot; kBeamOverflow: fall back to the per-ray traversal
     float* beam_bound;               // per pixel slot: the list is complete for rays whose closest hit is not beyond it
+    uint32_t* free_count;            // per light: anchor rays k_shadow found free, listed (in that light's still empty queue C) for k_sbeam
+    uint2* beam_list2;               // the same pair once more: shadow beams of the light whose chain runs on the side stream
+    uint32_t* beam_count2;
     uint32_t* fallback_list;         // sample slots of such pixels (aliases the shadow queues, which are not yet in use)
     uint32_t* fallback_count;
     uint32_t* sec_list;              // sample slots whose closest hit has specular lobes (aliases the shadow queues, drained by then)
@@ -170,7 +173,7 @@ struct DevWave {
     uint32_t next_t_base;            // first slot of the transmitted rays in the next level (= slots of this wave)
 };
 constexpr int kQueueA = 0, kQueueB = 1, kQueueC = 2;
-constexpr size_t kWaveCtrBytes = 8 + 4 * (size_t)LGB_MAX_LIGHTS * 3 * 2 + 16;     // + tie_count, fallback_count, sec_count, pad
+constexpr size_t kWaveCtrBytes = 8 + 4 * (size_t)LGB_MAX_LIGHTS * 3 * 2 + 16 + 4 * (size_t)LGB_MAX_LIGHTS;     // + tie_count, fallback_count, sec_count, pad, free_count[lights]
 constexpr int kMatStride = 12;
 constexpr uint32_t kMatDiffuse = 1u, kMatGlossy = 2u, kMatGeneral = 4u, kMatSpecular = 8u;
 constexpr uint32_t kMaxRecursion = 12;         // depth of the per-ray stack k_secondary keeps (lgb_scene_create rejects deeper scenes)
@@ -180,6 +183,7 @@ constexpr uint32_t kTieCap = 1u << 20;
 #endif
 constexpr int kBeamList = LGB_BEAM_LIST;                  // leaves a pixel beam may reach before the pixel falls back to per-ray traversal
 constexpr uint32_t kBeamOverflow = 0xFFFFFFFFu;
+constexpr uint32_t kEntryDone = 0xFFFFFFFFu;       // a queue-B entry k_swalk has resolved from the pixel's shadow beam
 constexpr uint32_t kSlotUnused = 0xFFFFFFFEu;
 
 struct DevOut {

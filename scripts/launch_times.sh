@@ -1,7 +1,7 @@
 #!/bin/bash
 # per-kernel launch list of one frame: ./scripts/launch_times.sh <workload> <tag>
 w=${1:-mixed4k}; tag=${2:-tmp}
-ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -k "regex:k_primary|k_setup|k_shadow|k_pretest|k_shade|k_resolve|k_beam|k_leafp|k_secondary|k_spawn|k_gather" -c 80 --csv --log-file gpurun_out/launches_$tag.csv python scripts/profile_frame.py $w 1 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -k "regex:k_primary|k_setup|k_shadow|k_pretest|k_shade|k_resolve|k_beam|k_leafp|k_secondary|k_spawn|k_gather|k_sbeam|k_swalk" -c 80 --csv --log-file gpurun_out/launches_$tag.csv python scripts/profile_frame.py $w 1 > /dev/null 2>&1
 python - <<PY
 import csv, collections
 rows=[r for r in csv.reader(open("gpurun_out/launches_$tag.csv")) if len(r)>10 and r[0].isdigit()]
