@@ -1356,6 +1356,11 @@ __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork 
     }
 }
 
+#ifndef LGB_SBEAM_THREADS
+#define LGB_SBEAM_THREADS_ 64
+#else
+#define LGB_SBEAM_THREADS_ LGB_SBEAM_THREADS
+#endif
 // ================================================================== shadow beams
 // The shadow rays of a pixel towards one light are a bundle too: seen from the light they share their origin, and their
 // directions (light -> shadow origin of every sample) differ by the footprint of one pixel on the surface.  k_sbeam, one thread per
@@ -1369,7 +1374,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork 
 #define LGB_SHADOW_BEAMS 1           // 48.45 -> 45.50 ms/frame on mixed4k (bundles only for pixels whose anchor ray is free; with every anchor as a bundle: 54.3)
 #endif
 template <bool STATS>
-__global__ void __launch_bounds__(LGB_BEAM_THREADS, 1024 / LGB_BEAM_THREADS) k_sbeam(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light,
+__global__ void __launch_bounds__(LGB_SBEAM_THREADS_, 1024 / LGB_SBEAM_THREADS_) k_sbeam(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light,
                                                                                      uint2* list_out, uint32_t* count_out) {
     const unsigned total = V.free_count[light];                           // the anchor rays k_shadow found free (listed in queue C's space)
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1473,8 +1478,14 @@ __global__ void __launch_bounds__(LGB_BEAM_THREADS, 1024 / LGB_BEAM_THREADS) k_s
 }
 // One thread per queue-B entry (the non-anchor samples): where the pixel's bundle left a complete list, the ray is tested against
 // the listed primitives alone, any hit with t < 1 (light/point.rs:48-49), and the entry is taken out of the queue.
+#ifndef LGB_SWALK_THREADS
+#define LGB_SWALK_THREADS 128        // 32 / 64 / 128 / 256 threads: 46.5 / 45.5 / 45.1 / 45.4 ms/frame
+#endif
+#ifndef LGB_SBEAM_THREADS
+#define LGB_SBEAM_THREADS 64
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(LGB_LEAFP_THREADS, 1024 / LGB_LEAFP_THREADS) k_swalk(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light,
+__global__ void __launch_bounds__(LGB_SWALK_THREADS, 1024 / LGB_SWALK_THREADS) k_swalk(DevScene S, DevWork W, DevOut O, DevWave V, uint32_t light,
                                                                                        const uint2* list_in, const uint32_t* count_in) {
     const unsigned total = V.queue_count[light * 3 + kQueueB];
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1985,10 +1996,10 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
             if (which == kQueueC) {
                 if (sbeams) {                       // pixels whose anchor ray is free: one bundle walk, then the other samples from its list, no traversal
                     if ((e = cudaMemsetAsync(bcount, 0xFF, (size_t)W.n_pixels * 4, ls)) != cudaSuccess) return e;
-                    const unsigned bb = (unsigned)((W.n_pixels + LGB_BEAM_THREADS - 1) / LGB_BEAM_THREADS);
-                    if (stats) k_sbeam<true><<<bb, LGB_BEAM_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount); else k_sbeam<false><<<bb, LGB_BEAM_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount);
-                    const unsigned wb = (unsigned)((total + LGB_LEAFP_THREADS - 1) / LGB_LEAFP_THREADS);
-                    if (stats) k_swalk<true><<<wb, LGB_LEAFP_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount); else k_swalk<false><<<wb, LGB_LEAFP_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount);
+                    const unsigned bb = (unsigned)((W.n_pixels + LGB_SBEAM_THREADS_ - 1) / LGB_SBEAM_THREADS_);
+                    if (stats) k_sbeam<true><<<bb, LGB_SBEAM_THREADS_, 0, ls>>>(S, W, O, V, l, blist, bcount); else k_sbeam<false><<<bb, LGB_SBEAM_THREADS_, 0, ls>>>(S, W, O, V, l, blist, bcount);
+                    const unsigned wb = (unsigned)((total + LGB_SWALK_THREADS - 1) / LGB_SWALK_THREADS);
+                    if (stats) k_swalk<true><<<wb, LGB_SWALK_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount); else k_swalk<false><<<wb, LGB_SWALK_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount);
                 }
                 const unsigned tb = (unsigned)std::min<uint64_t>(ablocks, (uint64_t)sms * 4);
                 if (inst) k_pretest<true><<<tb, kAppendThreads, 0, ls>>>(S, W, O, V, l); else k_pretest<false><<<tb, kAppendThreads, 0, ls>>>(S, W, O, V, l);
