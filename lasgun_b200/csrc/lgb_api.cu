@@ -1114,7 +1114,8 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         for (int k = 0; k < 3; k++) { stats->filter_tests[k] = hc.filter[k]; stats->exact_tests[k] = hc.exact[k]; }
         stats->stack_overflow = hc.stack_overflow;
         stats->beams = W.beams; stats->tie_retraces = tie_slots; stats->secondary_rays = hc.secondary_rays + level_rays;
-        stats->kernel_launches = total ? level_launches + (S.general ? (S.specular && S.recursion && !wf ? 5 : 4) : render_fused(W.spp) ? 3 : 4) + (W.beams ? 2 : 0) + s->dev.n_lights * (W.spp > 1 ? 3 : 1) : 0;
+        stats->kernel_launches = total ? level_launches + (S.general ? (S.specular && S.recursion && !wf ? 5 : 4) : render_fused(W.spp) ? 3 : 4) + (W.beams ? 2 : 0) + s->dev.n_lights * (W.spp > 1 ? 3 : 1)
+                                         + ((W.beams && W.spp > 1 && !S.instanced) ? 2 * s->dev.n_lights : 0) : 0;      // k_sbeam + k_swalk per light
         float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         stats->render_ms = ms; stats->total_ms = ms;
     }
