@@ -184,7 +184,7 @@ typedef struct lgb_stats {
     float total_ms;                  /* device time incl. film copy back to the host */
     uint32_t kernel_launches;
     uint32_t stack_overflow;         /* 1 if a ray exceeded the 64-entry stack (bvh.rs:469) */
-    uint32_t beams;                  /* 1 if the primary rays went through pixel beams (LGB_OPT_BEAMS) */
+    uint32_t beams;                  /* 1 if the primary (and shadow) rays went through pixel beams (LGB_OPT_BEAMS) */
     uint32_t tie_retraces;           /* lazy reference tree: sample slots re-traced because of an exact-t tie (this call) */
     uint64_t secondary_rays;         /* rays below specular hits (reflected, transmitted and their shadow rays), integrate.rs:69-132 */
 } lgb_stats;
@@ -206,8 +206,10 @@ void lgb_shutdown(lgb_ctx* ctx);
 #define LGB_OPT_SIDE_STREAMS 4      /* 1 (default): the shadow-ray kernels of different lights overlap on a side stream; 0: one stream */
 #define LGB_OPT_WHITTED 3           /* glass / mirror ray trees: 1 (default) level-by-level wavefront on the frame's own kernels, 0 one thread per tree */
 #define LGB_OPT_BEAMS 2             /* pixel beams: at >= 4 samples per pixel the primary rays of a pixel share ONE bundle traversal
-                                     * (k_beam) and then walk its leaf list; same results.  1 on, 0 off, -1 (default) automatic:
-                                     * on for >= 8 samples per pixel and a BVH of >= 4096 nodes.  env LGB_BEAMS presets it. */
+                                     * (k_beam) and then test only the primitives it listed; likewise the shadow rays of a pixel
+                                     * whose centre sample is unoccluded (k_sbeam, from the light).  Same results.  1 on, 0 off,
+                                     * -1 (default) automatic: on for >= 8 samples per pixel and a BVH of >= 4096 nodes.
+                                     * env LGB_BEAMS presets it. */
 int lgb_set_option(lgb_ctx* ctx, int option, int value);
 const char* lgb_last_error(lgb_ctx* ctx);          /* ctx may be NULL: last error of lgb_init */
 const char* lgb_status_string(int status);
