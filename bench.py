@@ -192,6 +192,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = N.Context(local)
+    if os.environ.get("LGB_SIDE") == "0":              # experiments: the shadow chains of the lights on one stream
+        ctx.set_side_streams(False)
     sc, (w, h) = workload(args.workload, args)
     spp, nl = sc.camera.num_samples(), len(sc.lights)
     hscene_host = N.HostScene(sc)                      # the built `Scene` (scene construction is not part of capture)
