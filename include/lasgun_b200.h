@@ -208,7 +208,7 @@ void lgb_shutdown(lgb_ctx* ctx);
 #define LGB_OPT_BEAMS 2             /* pixel beams: at >= 4 samples per pixel the primary rays of a pixel share ONE bundle traversal
                                      * (k_beam) and then test only the primitives it listed; likewise the shadow rays of a pixel
                                      * whose centre sample is unoccluded (k_sbeam, from the light).  Same results.  1 on, 0 off,
-                                     * -1 (default) automatic: on for >= 8 samples per pixel and a BVH of >= 4096 nodes.
+                                     * -1 (default) automatic: on for >= 8 samples per pixel and a BVH of >= 1024 nodes.
                                      * env LGB_BEAMS presets it. */
 int lgb_set_option(lgb_ctx* ctx, int option, int value);
 const char* lgb_last_error(lgb_ctx* ctx);          /* ctx may be NULL: last error of lgb_init */

@@ -1028,7 +1028,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         V.fallback_list = V.queue;                       // the shadow queues are written only after the primary phase
         // automatic: where a bundle of >= 8 rays shares a traversal that is long enough to be worth sharing (measured: a loss on
         // scenes of a few dozen primitives, a gain on large ones)
-        W.beams = (W.spp >= 4 && !S.instanced && (c->beams == 1 || (c->beams < 0 && W.spp >= 8 && S.n_nodes >= 4096u))) ? 1u : 0u;
+        W.beams = (W.spp >= 4 && !S.instanced && (c->beams == 1 || (c->beams < 0 && W.spp >= 8 && S.n_nodes >= 1024u))) ? 1u : 0u;
         if (W.beams) {
             const uint64_t npx = std::max<uint64_t>(W.n_pixels, 1);
             CU(c, c->beam.reserve(npx * kBeamList * sizeof(uint2) + npx * 8));
