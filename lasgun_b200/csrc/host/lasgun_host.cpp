@@ -474,19 +474,38 @@ struct Flattener {
     std::unique_ptr<Level> level_from_aggregate(const Aggregate& ag, bool is_root) {
         (void)is_root;
         auto lv = std::make_unique<Level>();
-        // Pass 1 (sequential, construction order): canonical ids, array slots, nested levels.
+        // Pass 1: canonical ids (construction order, nested levels included) and array slots.  The nodes are 150-byte
+        // records, so even reading their kinds is a 150 MB sweep for a million spheres: the chunks count their spheres / cuboids and
+        // note their mesh / group nodes in parallel (1a), a short sequential walk over the chunks hands out the bases and builds the
+        // nested levels in order (1b), and the chunks write ids and slots in parallel (1c).
         const size_t nn = ag.contents.size();
         raw_vector<uint32_t> slot(nn), ids(nn);
-        size_t n_s = 0, n_c = 0;       // slot[] holds the ordinal among this level's own spheres / cuboids until pass 1 is over
         lv->boxes.resize(nn); lv->refs.resize(nn);
-        for (size_t i = 0; i < nn; i++) {
-            const Aggregate::Node& n = ag.contents[i];
-            switch (n.kind) {
-            case Aggregate::Node::Sphere: slot[i] = (uint32_t)n_s++; ids[i] = next_id++; break;
-            case Aggregate::Node::Cube:
-            case Aggregate::Node::Cuboid: slot[i] = (uint32_t)n_c++; ids[i] = next_id++; break;
-            case Aggregate::Node::Mesh:
-            case Aggregate::Node::Group: {
+        constexpr size_t kGrain = 1 << 13;
+        const size_t n_chunks = lgb::Pool::get().chunks_of(nn, kGrain);                    // the partition for_range makes of [0, nn)
+        const size_t per_chunk = n_chunks ? (nn + n_chunks - 1) / n_chunks : 0;
+        struct ChunkInfo { uint32_t n_s = 0, n_c = 0; std::vector<uint32_t> nested; uint32_t id_base = 0, s_ord = 0, c_ord = 0; std::vector<uint32_t> nested_ids; };
+        std::vector<ChunkInfo> chunks(n_chunks);
+        lgb::Pool::get().for_range(nn, kGrain, [&](size_t b0, size_t e0, size_t c) {
+            ChunkInfo& ci = chunks[c];
+            for (size_t i = b0; i < e0; i++) {
+                const Aggregate::Node::Kind k = ag.contents[i].kind;
+                if (k == Aggregate::Node::Sphere) ci.n_s++;
+                else if (k == Aggregate::Node::Cube || k == Aggregate::Node::Cuboid) ci.n_c++;
+                else ci.nested.push_back((uint32_t)i);
+            }
+        });
+        size_t n_s = 0, n_c = 0;       // ordinals among this level's own spheres / cuboids
+        for (size_t c = 0; c < n_chunks; c++) {
+            ChunkInfo& ci = chunks[c];
+            ci.id_base = next_id; ci.s_ord = (uint32_t)n_s; ci.c_ord = (uint32_t)n_c;
+            n_s += ci.n_s; n_c += ci.n_c;
+            // ids inside the chunk: primitives before a nested node come first, then the nested level's own primitives
+            size_t prev = c * per_chunk;
+            for (uint32_t at : ci.nested) {
+                const Aggregate::Node& n = ag.contents[at];
+                next_id += (uint32_t)(at - prev);                  // the own primitives in [prev, at)
+                ci.nested_ids.push_back(next_id);                  // id the next own primitive after `at` would have had before the nested level took its ids
                 std::unique_ptr<Level> child = n.kind == Aggregate::Node::Mesh ? level_from_mesh(n.ref, n.has_mat, n.mat)
                                                                                 : level_from_aggregate(ag.groups[n.ref], false);
                 lgb_instance inst{};
@@ -499,21 +518,29 @@ struct Flattener {
                     inst.swap_backface = g.swap_backface_flag ? 1u : 0u;
                     std::memcpy(inst.m, g.transform.m, sizeof inst.m); std::memcpy(inst.minv, g.transform.minv, sizeof inst.minv);
                 }
-                lv->boxes[i] = transform_bounds(inst.m, cb);                   // BVHAccel::bound, bvh.rs:457-459
+                lv->boxes[at] = transform_bounds(inst.m, cb);                  // BVHAccel::bound, bvh.rs:457-459
                 out.instances.push_back(inst);
-                lv->refs[i] = LGB_PRIM_REF(LGB_PRIM_INSTANCE, out.instances.size() - 1);
+                lv->refs[at] = LGB_PRIM_REF(LGB_PRIM_INSTANCE, out.instances.size() - 1);
                 lv->child_instance.push_back((uint32_t)out.instances.size() - 1);
                 lv->children.push_back(std::move(child));
-                break;
+                ci.nested_ids.back() = next_id;                    // first id after the nested level
+                prev = at + 1;
             }
-            }
+            const size_t end = std::min(nn, (c + 1) * per_chunk);
+            next_id += (uint32_t)(end - prev);
         }
         const size_t s_base = out.spheres.size(), c_base = out.cuboids.size();      // after the nested levels took theirs
-        for (size_t i = 0; i < nn; i++) {
-            const Aggregate::Node::Kind k = ag.contents[i].kind;
-            if (k == Aggregate::Node::Sphere) slot[i] += (uint32_t)s_base;
-            else if (k == Aggregate::Node::Cube || k == Aggregate::Node::Cuboid) slot[i] += (uint32_t)c_base;
-        }
+        lgb::Pool::get().for_range(nn, kGrain, [&](size_t b0, size_t e0, size_t c) {
+            const ChunkInfo& ci = chunks[c];
+            uint32_t id = ci.id_base, so = ci.s_ord + (uint32_t)s_base, co = ci.c_ord + (uint32_t)c_base;
+            size_t ni = 0;
+            for (size_t i = b0; i < e0; i++) {
+                const Aggregate::Node::Kind k = ag.contents[i].kind;
+                if (k == Aggregate::Node::Sphere) { slot[i] = so++; ids[i] = id++; }
+                else if (k == Aggregate::Node::Cube || k == Aggregate::Node::Cuboid) { slot[i] = co++; ids[i] = id++; }
+                else id = ci.nested_ids[ni++];                    // the nested level's primitives took the ids in between
+            }
+        });
         out.spheres.resize(s_base + n_s); out.sphere_material.resize(s_base + n_s); out.sphere_id.resize(s_base + n_s);
         out.cuboids.resize(c_base + n_c); out.cuboid_material.resize(c_base + n_c); out.cuboid_id.resize(c_base + n_c);
         // Pass 2 (all threads): primitive records and bounds.  Materials are interned through a small per-chunk

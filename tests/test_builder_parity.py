@@ -82,3 +82,76 @@ def test_reference_hazards_are_errors(native):
     sc = Scene(); g = Aggregate(); g.translate([1, 0, 0]); sc.root.add_group(g)      # empty nested aggregate
     with pytest.raises(native.LasgunError):
         native.FlatScene(sc)
+
+
+def expected_ids(sc):
+    """Canonical primitive ids: a running counter in construction order -- `from_aggregate` visits `contents` in order,
+    a mesh contributes its triangles in file order, a nested group its own contents at the place it was added."""
+    spheres, boxes, tri_first = {}, {}, {}
+    nxt = [0]
+
+    def walk(agg):
+        for item in agg.contents:
+            k = item[0]
+            if k == "sphere":
+                spheres.setdefault((tuple(np.asarray(item[1], float)), float(item[2])), []).append(nxt[0]); nxt[0] += 1
+            elif k == "spheres":
+                for c, r in zip(np.asarray(item[1], float), np.asarray(item[2], float)):
+                    spheres.setdefault((tuple(c), float(r)), []).append(nxt[0]); nxt[0] += 1
+            elif k == "cube":
+                o = np.asarray(item[1], float)
+                boxes.setdefault((tuple(o), tuple(o + item[2])), []).append(nxt[0]); nxt[0] += 1
+            elif k == "box":
+                a, b = np.asarray(item[1], float), np.asarray(item[2], float)
+                boxes.setdefault((tuple(np.minimum(a, b)), tuple(np.maximum(a, b))), []).append(nxt[0]); nxt[0] += 1
+            elif k == "mesh":
+                tri_first.setdefault(id(item), []).append(nxt[0]); nxt[0] += len(sc.meshes[item[1].index].faces)
+            elif k == "group":
+                walk(item[1])
+    walk(sc.root)
+    return spheres, boxes, sorted(v for vs in tri_first.values() for v in vs), nxt[0]
+
+
+def many_chunks_scene():
+    """More contents than one flatten chunk holds (8192), with groups and a mesh in between: the parallel id / slot assignment
+    must hand the nested levels their id ranges at the right places."""
+    sc = Scene()
+    sc.set_perspective_camera(45.0).look_at([0, 0, 60], [0, 0, 0], [0, 1, 0])
+    rng = np.random.default_rng(5)
+    mat = Material.plastic([0.5, 0.5, 0.5], [0.2, 0.2, 0.2], 0.3)
+    mesh = sc.add_obj(scenes.mesh_grid(6, 1.0))
+    for i in range(30000):
+        c = rng.uniform(-20, 20, 3)
+        if i % 7 == 3:
+            sc.root.add_cube(list(c), 0.3 + (i % 5) * 0.01, mat)
+        else:
+            sc.root.add_sphere(list(c), 0.1 + (i % 11) * 0.01, mat)
+        if i in (5, 8191, 8192, 12000, 24575, 29999):
+            g = Aggregate(); g.translate([float(i % 13), 0.0, 0.0])
+            g.add_sphere([0.0, 0.0, float(i)], 0.5, mat); g.add_obj_of(mesh, mat); g.add_cube([1.0, 2.0, float(i)], 0.25, mat)
+            sc.root.add_group(g)
+    return sc
+
+
+@pytest.mark.parametrize("name", ["nested_groups", "mixed", "many_chunks"])
+def test_canonical_ids_follow_construction_order(native, name):
+    import ctypes as C
+    sc = many_chunks_scene() if name == "many_chunks" else CASES[name]()
+    flat = native.FlatScene(sc, lazy=(name != "nested_groups"))
+    d = flat.desc
+    spheres, boxes, tri_first, total = expected_ids(sc)
+    assert flat.prim_count == total
+
+    def arr(ptr, n, ty, width=1):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ty)), shape=(n * width,)).reshape(n, width) if n else np.zeros((0, width))
+    sp = arr(d.spheres, d.n_spheres, C.c_double, 4); sid = arr(d.sphere_id, d.n_spheres, C.c_uint32)[:, 0]
+    for row, i in zip(sp, sid):
+        assert int(i) in spheres[(tuple(row[:3]), float(row[3]))]          # (the same sphere may be added twice: a list of ids)
+    cb = arr(d.cuboids, d.n_cuboids, C.c_double, 6); cid = arr(d.cuboid_id, d.n_cuboids, C.c_uint32)[:, 0]
+    for row, i in zip(cb, cid):
+        assert int(i) in boxes[(tuple(row[:3]), tuple(row[3:]))]
+    tid = arr(d.triangle_id, d.n_triangles, C.c_uint32)[:, 0]
+    used = set(sid.tolist()) | set(cid.tolist()) | set(tid.tolist())
+    assert len(used) == total and used == set(range(total))                 # every id exactly once
+    for first in tri_first:                                                   # a mesh's triangles take consecutive ids from its place in the order
+        assert first in set(tid.tolist())
