@@ -437,11 +437,11 @@ struct Flattener {
             std::fill(out.tri_has_normals.begin() + had, out.tri_has_normals.begin() + base, (uint8_t)0);   // earlier meshes without normals
         }
         const uint32_t id0 = next_id; next_id += (uint32_t)ntri;
-        for (size_t t = 0; t < ntri; t++)
-            for (int v = 0; v < 3; v++)
-                if ((size_t)m.faces[3 * t + v] * 3 + 2 >= m.positions.size()) throw Error(LGB_ERR_INVALID, "mesh face references a vertex out of range");
+        std::atomic<bool> bad_index{false};
         lgb::Pool::get().for_range(ntri, 1 << 14, [&](size_t t0, size_t t1, size_t) {
           for (size_t t = t0; t < t1; t++) {
+            if ((size_t)m.faces[3 * t] * 3 + 2 >= m.positions.size() || (size_t)m.faces[3 * t + 1] * 3 + 2 >= m.positions.size() ||
+                (size_t)m.faces[3 * t + 2] * 3 + 2 >= m.positions.size()) { bad_index.store(true); continue; }
             lgb_triangle& tr = out.triangles[base + t];
             const float* p0 = &m.positions[3 * (size_t)m.faces[3 * t]], *p1 = &m.positions[3 * (size_t)m.faces[3 * t + 1]], *p2 = &m.positions[3 * (size_t)m.faces[3 * t + 2]];
             Box b;
@@ -452,6 +452,8 @@ struct Flattener {
                 b.mn[k] = lo < e ? lo : e; b.mx[k] = hi < e ? e : hi;
             }
             if (has_n) {
+                if ((size_t)m.normal_faces[3 * t] * 3 + 2 >= m.normals.size() || (size_t)m.normal_faces[3 * t + 1] * 3 + 2 >= m.normals.size() ||
+                    (size_t)m.normal_faces[3 * t + 2] * 3 + 2 >= m.normals.size()) { bad_index.store(true); continue; }
                 lgb_tri_normals& q = out.tri_normals[base + t];
                 for (int k = 0; k < 3; k++) {
                     q.n0[k] = m.normals[3 * (size_t)m.normal_faces[3 * t] + k];
@@ -466,6 +468,7 @@ struct Flattener {
             lv->refs[t] = LGB_PRIM_REF(LGB_PRIM_TRIANGLE, base + t);
           }
         });
+        if (bad_index.load()) throw Error(LGB_ERR_INVALID, "mesh face references a vertex or normal out of range");
         lv->per_node = ntri;
         return lv;
     }

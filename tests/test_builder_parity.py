@@ -155,3 +155,18 @@ def test_canonical_ids_follow_construction_order(native, name):
     assert len(used) == total and used == set(range(total))                 # every id exactly once
     for first in tri_first:                                                   # a mesh's triangles take consecutive ids from its place in the order
         assert first in set(tid.tolist())
+
+
+def test_mesh_index_out_of_range_is_an_error(native):
+    """api.ObjData refuses bad indices; arrays that went bad afterwards are caught by the C++ flatten (in its parallel loop)."""
+    from lasgun_b200.api import ObjData
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    with pytest.raises(ValueError):
+        ObjData(pos, np.array([[0, 1, 5]], np.uint32))
+    for what in ("face", "normal"):
+        sc = Scene()
+        m = ObjData(pos, np.array([[0, 1, 2]], np.uint32), np.array([[0, 0, 1]], np.float32), np.array([[0, 0, 0]], np.uint32))
+        sc.root.add_obj_of(sc.add_obj(m), Material.default())
+        (m.faces if what == "face" else m.normal_faces)[0, 2] = 7
+        with pytest.raises(native.LasgunError):
+            native.FlatScene(sc)
