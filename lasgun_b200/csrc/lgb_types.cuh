@@ -179,7 +179,7 @@ constexpr uint32_t kMatDiffuse = 1u, kMatGlossy = 2u, kMatGeneral = 4u, kMatSpec
 constexpr uint32_t kMaxRecursion = 12;         // depth of the per-ray stack k_secondary keeps (lgb_scene_create rejects deeper scenes)
 constexpr uint32_t kTieCap = 1u << 20;
 #ifndef LGB_BEAM_LIST
-#define LGB_BEAM_LIST 48
+#define LGB_BEAM_LIST 24             // entries a bundle may list before the pixel goes the per-ray way; 16 / 24 / 32 / 48 / 64: 44.4 / 44.6 / 44.7 / 45.1 / 45.2 ms/frame on mixed4k
 #endif
 constexpr int kBeamList = LGB_BEAM_LIST;                  // leaves a pixel beam may reach before the pixel falls back to per-ray traversal
 constexpr uint32_t kBeamOverflow = 0xFFFFFFFFu;
