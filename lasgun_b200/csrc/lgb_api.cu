@@ -32,6 +32,12 @@ cudaError_t launch_fp64_peak(int iters, double* sink, int sms, cudaStream_t);
 
 using namespace lgb;
 
+// The layouts the bindings mirror by hand (lasgun_b200/_native.py, tests/test_abi.py).
+static_assert(sizeof(lgb_material) == 72 && offsetof(lgb_material, kind) == 64, "lgb_material layout (ABI v4)");
+static_assert(sizeof(lgb_node) == 32 && sizeof(lgb_instance) == 16 + 2 * 16 * 8, "lgb_node / lgb_instance layout");
+static_assert(sizeof(lgb_stats) == 21 * 8 + 12 * 4, "lgb_stats layout");
+static_assert(sizeof(SpawnRec) == 72, "SpawnRec layout");
+
 static thread_local std::string g_init_error;
 
 struct DevBuf {
