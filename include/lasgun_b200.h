@@ -268,6 +268,11 @@ int lgb_capture_device(lgb_ctx* ctx, lgb_scene* scene, uint32_t w, uint32_t h, u
 int lgb_trace_rays(lgb_ctx* ctx, lgb_scene* scene, const double* rays_od, uint64_t n_rays,
                    uint32_t* prim_id, double* t, double* ng, double* ns);
 
+/* Debug / parity: the reciprocal and reciprocal square root the shading kernel uses in place of IEEE division / sqrt
+ * (MUFU seed + one third-order refinement, csrc/lgb_math.cuh) evaluated on caller-supplied positive normal doubles;
+ * the tests bound their relative error (a few 1e-16).  They only colour: no hit, shadow or sign decision goes through them. */
+int lgb_debug_fastmath(lgb_ctx* ctx, const double* x, uint64_t n, double* rcp_out, double* rsqrt_out);
+
 /* Measured device ceilings used for roofline reporting (bench only). */
 int lgb_measure_l2_read_gbs(lgb_ctx* ctx, uint64_t bytes, int iters, double* gbs_out);
 int lgb_measure_fp32_gops(lgb_ctx* ctx, int iters, double* glaneops_out);

@@ -22,7 +22,7 @@ LGB_LEAF_FLAG = 0x80000000
 ABI_SYMBOLS = [
     "lgb_build_probe", "lgb_device_count", "lgb_init", "lgb_set_option", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
     "lgb_film_alloc_shared", "lgb_film_open_shared", "lgb_film_release_shared", "lgb_scene_destroy", "lgb_scene_layout_bytes", "lgb_scene_export", "lgb_scene_import", "lgb_scene_verify", "lgb_scene_device_bytes", "lgb_scene_build_ms", "lgb_scene_node_count", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
-    "lgb_capture_device", "lgb_trace_rays", "lgb_measure_l2_read_gbs", "lgb_measure_fp32_gops", "lgb_measure_fp64_gops",
+    "lgb_capture_device", "lgb_trace_rays", "lgb_debug_fastmath", "lgb_measure_l2_read_gbs", "lgb_measure_fp32_gops", "lgb_measure_fp64_gops",
 ]
 
 
@@ -116,6 +116,7 @@ def lib():
         "lgb_capture_aov": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u8p, u32p, dp, u32p, dp, C.POINTER(Stats)]),
         "lgb_capture_device": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.POINTER(Stats)]),
         "lgb_trace_rays": (C.c_int, [vp, vp, dp, C.c_uint64, u32p, dp, dp, dp]),
+        "lgb_debug_fastmath": (C.c_int, [vp, dp, C.c_uint64, dp, dp]),
         "lgb_measure_l2_read_gbs": (C.c_int, [vp, C.c_uint64, C.c_int, dp]),
         "lgb_measure_fp32_gops": (C.c_int, [vp, C.c_int, dp]), "lgb_measure_fp64_gops": (C.c_int, [vp, C.c_int, dp]),
         # host mirror
@@ -346,6 +347,14 @@ class Context:
     def set_whitted(self, wavefront: bool):
         """LGB_OPT_WHITTED: the specular ray trees level by level (default) or one thread per tree."""
         self.check(lib().lgb_set_option(self.h, 3, 1 if wavefront else 0))
+
+    def fastmath(self, x):
+        """lgb_debug_fastmath: the shading kernel's reciprocal and reciprocal square root of every x (positive, normal f64)."""
+        import numpy as np
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        r, q = np.empty_like(x), np.empty_like(x)
+        self.check(lib().lgb_debug_fastmath(self.h, _ptr(x, C.c_double), x.size, _ptr(r, C.c_double), _ptr(q, C.c_double)))
+        return r, q
 
     def measure(self):
         L = lib()

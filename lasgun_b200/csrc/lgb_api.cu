@@ -28,6 +28,7 @@ cudaError_t launch_trace(const DevScene&, const double* rays, uint64_t n, uint32
 cudaError_t launch_l2_read(const void* buf, uint64_t bytes, int iters, float* sink, int sms, cudaStream_t);
 cudaError_t launch_fp32_peak(int iters, float* sink, int sms, cudaStream_t);
 cudaError_t launch_fp64_peak(int iters, double* sink, int sms, cudaStream_t);
+cudaError_t launch_fastmath(const double* x, uint64_t n, double* rcp, double* rsq, cudaStream_t);
 }  // namespace lgb
 
 using namespace lgb;
@@ -95,6 +96,7 @@ struct lgb_scene {
     void* rank_buf = nullptr;                        // rank tables uploaded later live outside the arena
     uint64_t tie_retraces = 0;
     uint64_t bytes = 0;
+    cudaEvent_t last_use = nullptr;   // recorded behind every capture on the stream it ran on: lgb_scene_destroy frees the arena behind it
     DevScene dev{};
     DevCamera cam{};
     DevShade shade{};
@@ -108,6 +110,7 @@ static int fail(lgb_ctx* ctx, int code, const std::string& msg) {
     return code;
 }
 static int cuda_fail(lgb_ctx* ctx, cudaError_t e, const char* what) {
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(ctx, LGB_ERR_NOMEM, std::string(what) + ": out of device memory"); }
     return fail(ctx, LGB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 #define CU(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); } while (0)
@@ -148,15 +151,25 @@ int lgb_init(int device, lgb_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (const char* e = std::getenv("LGB_BEAMS")) { const int v = std::atoi(e); c->beams = v < 0 ? -1 : (v != 0); }
-    CU(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(nullptr, cudaEventCreate(&c->ev0)); CU(nullptr, cudaEventCreate(&c->ev1)); CU(nullptr, cudaEventCreate(&c->ev2));
-    for (auto& e : c->phase) CU(nullptr, cudaEventCreate(&e));
     c->side.n = 1;                         // one side stream: two lights' chains at a time (a third stream measured no further gain)
+    cudaError_t ie = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (ie == cudaSuccess) ie = cudaEventCreate(&c->ev0);
+    if (ie == cudaSuccess) ie = cudaEventCreate(&c->ev1);
+    if (ie == cudaSuccess) ie = cudaEventCreate(&c->ev2);
+    for (auto& e : c->phase) if (ie == cudaSuccess) ie = cudaEventCreate(&e);
     for (int k = 0; k < c->side.n; k++) {
-        CU(nullptr, cudaStreamCreateWithFlags(&c->side.s[k], cudaStreamNonBlocking));
-        CU(nullptr, cudaEventCreateWithFlags(&c->side.join[k], cudaEventDisableTiming));
+        if (ie == cudaSuccess) ie = cudaStreamCreateWithFlags(&c->side.s[k], cudaStreamNonBlocking);
+        if (ie == cudaSuccess) ie = cudaEventCreateWithFlags(&c->side.join[k], cudaEventDisableTiming);
     }
-    CU(nullptr, cudaEventCreateWithFlags(&c->side.fork, cudaEventDisableTiming));
+    if (ie == cudaSuccess) ie = cudaEventCreateWithFlags(&c->side.fork, cudaEventDisableTiming);
+    if (ie != cudaSuccess) {               // nothing of a half-made context survives (every handle below is NULL-safe to skip)
+        if (c->stream) cudaStreamDestroy(c->stream);
+        for (cudaEvent_t e : {c->ev0, c->ev1, c->ev2, c->side.fork}) if (e) cudaEventDestroy(e);
+        for (auto& e : c->phase) if (e) cudaEventDestroy(e);
+        for (int k = 0; k < c->side.n; k++) { if (c->side.s[k]) cudaStreamDestroy(c->side.s[k]); if (c->side.join[k]) cudaEventDestroy(c->side.join[k]); }
+        delete c;
+        return cuda_fail(nullptr, ie, "lgb_init: stream / event creation");
+    }
     {   // scene arenas come from the stream-ordered pool and are kept cached between scenes (cudaMalloc/cudaFree cost ms)
         cudaMemPool_t mp;
         if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
@@ -456,6 +469,10 @@ int lgb_scene_verify(lgb_ctx* ctx, const lgb_scene* s, lgb_build_info* out) {
 void lgb_scene_destroy(lgb_scene* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
+    if (s->last_use) {                 // a capture may still be running on a caller-supplied stream (lgb_capture_device is asynchronous)
+        cudaStreamWaitEvent(s->ctx->stream, s->last_use, 0);
+        cudaEventDestroy(s->last_use);
+    }
     if (s->rank_buf) cudaFreeAsync(s->rank_buf, s->ctx->stream);
     if (s->arena && s->owns_arena) cudaFreeAsync(s->arena, s->ctx->stream);      // stream-ordered: later work of this context is behind it
     else if (s->arena) cudaStreamSynchronize(s->ctx->stream);                    // borrowed arena: the caller may free it right after
@@ -484,11 +501,23 @@ int lgb_scene_import(lgb_ctx* ctx, const void* layout, uint64_t layout_bytes, vo
     s->dev = L.dev; s->cam = L.cam; s->shade = L.shade; s->max_abs = L.max_abs;
     const char* base = (const char*)arena_dev;
     bool ok = true;
+    // every array must lie inside the arena with its whole extent (counts recomputed from the leaf words would need the nodes:
+    // the per-type counts are bounded by prim_count, which is what the kernels can index)
+    const DevScene& Ld = L.dev;
+    const uint64_t P = Ld.prim_count, nsp = Ld.n_spaces;
+    auto within = [&](const void* p, uint64_t bytes) {
+        const uint64_t off = (uint64_t)p;
+        if (off == kNullOffset) return true;
+        return off <= L.arena_bytes && bytes <= L.arena_bytes - off;
+    };
+    ok = ok && Ld.nodes != (const float4*)kNullOffset && within(Ld.nodes, (uint64_t)Ld.n_nodes * 64) && within(Ld.rank, (uint64_t)8 * Ld.rank_items * 4);
+    ok = ok && within(Ld.materials, 0) && within(Ld.lights, (uint64_t)Ld.n_lights * 72) && within(Ld.spaces, Ld.instanced ? nsp * sizeof(DevSpace) : 0);
+    ok = ok && Ld.n_lights <= LGB_MAX_LIGHTS && Ld.rank_items >= P;
     for_each_pointer(s->dev, [&](const void*& p) {
         const uint64_t off = (uint64_t)p;
-        if (off == kNullOffset) p = nullptr; else if (off >= L.arena_bytes) ok = false; else p = base + off;
+        if (off == kNullOffset) p = nullptr; else if (off > L.arena_bytes) ok = false; else p = base + off;
     });
-    if (!ok) { delete s; return fail(ctx, LGB_ERR_INVALID, "lgb_scene_import: offset outside the arena"); }
+    if (!ok) { delete s; return fail(ctx, LGB_ERR_INVALID, "lgb_scene_import: an array of the layout does not lie inside the arena"); }
     *out = s;
     return LGB_OK;
 }
@@ -707,7 +736,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         if (ncb) { s->dev.cub32 = la.cub32; s->dev.cub64 = la.cub64; s->dev.cub_mat = la.cub_mat; s->dev.cub_id = la.cub_id; }
         if (nt) { s->dev.tri = la.tri; s->dev.tri_nrm = la.tri_nrm; }
         s->dev.materials = (const double*)(D + o_mat);
-        s->dev.lights = (const double*)(D + o_lights); s->dev.n_lights = (uint32_t)d->n_lights;
+        s->dev.lights = d->n_lights ? (const double*)(D + o_lights) : nullptr; s->dev.n_lights = (uint32_t)d->n_lights;
         s->dev.general = any_general; s->dev.specular = any_specular; s->dev.recursion = d->recursion;
         s->gpu_built = true;
         (void)tg0;
@@ -844,7 +873,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         double* l = (double*)(H + o_lights);
         for (uint64_t i = 0; i < d->n_lights; i++)
             for (int k = 0; k < 3; k++) { l[9 * i + k] = d->lights[i].position[k]; l[9 * i + 3 + k] = d->lights[i].intensity[k]; l[9 * i + 6 + k] = d->lights[i].falloff[k]; }
-        s->dev.lights = (const double*)(D + o_lights);
+        s->dev.lights = d->n_lights ? (const double*)(D + o_lights) : nullptr;      // (an empty array at the very end of the arena has no valid offset)
         s->dev.n_lights = (uint32_t)d->n_lights;
         s->dev.general = any_general; s->dev.specular = any_specular; s->dev.recursion = d->recursion;
     }
@@ -896,16 +925,18 @@ struct CaptureArgs {
 };
 
 // Wavefront buffers of `nslots` sample slots carved out of one allocation (layout: DevWave, lgb_types.cuh).
-static size_t wave_bytes(uint64_t nslots, uint32_t nl, uint64_t npix) { return nslots * (8 + 24 + 4 + 4 + 12 * (size_t)nl) + npix * 4 * nl; }
-static DevWave carve_wave(void* wave, void* ctr, uint64_t nslots, uint32_t nl) {
+static size_t wave_bytes(uint64_t nslots, uint32_t nl, uint64_t npix) { return nslots * (8 + 24 + 4 + 4 + 4 + 12 * (size_t)nl) + npix * 4 * nl + ((nslots + 15) & ~(uint64_t)15); }
+static DevWave carve_wave(void* wave, void* ctr, uint64_t nslots, uint32_t nl, uint64_t npix = 1) {
     DevWave V{};
     char* base = (char*)wave;
     V.hit_t = (double*)base; base += nslots * 8;
     V.ps = (double*)base; base += nslots * 24;
     V.hit_ref = (uint32_t*)base; base += nslots * 4;
     V.occl = (uint32_t*)base; base += nslots * 4;
+    V.gate = (uint32_t*)base; base += nslots * 4;
     V.queue = (uint32_t*)base; V.queue_stride = nslots; base += nslots * 12 * nl;
-    V.occluder = (uint32_t*)base;
+    V.occluder = (uint32_t*)base; base += npix * 4 * nl;
+    V.sflags = (unsigned char*)base;
     V.work_counter = (unsigned long long*)ctr;
     V.queue_count = (uint32_t*)((char*)ctr + 8);
     V.queue_fetch = V.queue_count + LGB_MAX_LIGHTS * 3;
@@ -1012,26 +1043,10 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     // wavefront buffers: hit_t 8 + ps 24 + hit_ref 4 + occl 4 + 3 queues x 4 x lights bytes per sample slot,
     // + occluder 4 x lights bytes per pixel slot
     const uint64_t nslots = std::max<uint64_t>(total, 1), nl = std::max<uint32_t>(S.n_lights, 1), npix = std::max<uint64_t>(W.n_pixels, 1);
-    CU(c, c->wave.reserve(nslots * (8 + 24 + 4 + 4 + 12 * nl) + npix * 4 * nl));
+    CU(c, c->wave.reserve(wave_bytes(nslots, (uint32_t)nl, npix)));
     CU(c, c->wave_ctr.reserve(kWaveCtrBytes));
-    DevWave V{};
+    DevWave V = carve_wave(c->wave.p, c->wave_ctr.p, nslots, (uint32_t)nl, npix);
     {
-        char* base = (char*)c->wave.p;
-        V.hit_t = (double*)base; base += nslots * 8;
-        V.ps = (double*)base; base += nslots * 24;
-        V.hit_ref = (uint32_t*)base; base += nslots * 4;
-        V.occl = (uint32_t*)base; base += nslots * 4;
-        V.queue = (uint32_t*)base; V.queue_stride = nslots; base += nslots * 12 * nl;
-        V.occluder = (uint32_t*)base;
-        V.work_counter = (unsigned long long*)c->wave_ctr.p;
-        V.queue_count = (uint32_t*)((char*)c->wave_ctr.p + 8);
-        V.queue_fetch = V.queue_count + LGB_MAX_LIGHTS * 3;
-        V.tie_count = V.queue_fetch + LGB_MAX_LIGHTS * 3;
-        V.fallback_count = V.tie_count + 1;
-        V.sec_count = V.fallback_count + 1;
-        V.free_count = V.sec_count + 2;
-        V.sec_list = V.queue;                            // the shadow queues are drained before k_shade lists the specular slots
-        V.fallback_list = V.queue;                       // the shadow queues are written only after the primary phase
         // automatic: where a bundle of >= 8 rays shares a traversal that is long enough to be worth sharing (measured: a loss on
         // scenes of a few dozen primitives, a gain on large ones)
         W.beams = (W.spp >= 4 && !S.instanced && (c->beams == 1 || (c->beams < 0 && W.spp >= 8 && S.n_nodes >= 1024u))) ? 1u : 0u;
@@ -1106,6 +1121,8 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     }
     if (O.aov_li) CU(c, launch_export_li(W, O, V, st));
     CU(c, cudaEventRecord(c->ev1, st));
+    if (!s->last_use) CU(c, cudaEventCreateWithFlags(&s->last_use, cudaEventDisableTiming));
+    CU(c, cudaEventRecord(s->last_use, st));
     if (stats && sync_stats) {
         DevCounters hc;
         CU(c, cudaMemcpyAsync(&hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
@@ -1197,6 +1214,20 @@ int lgb_trace_rays(lgb_ctx* c, lgb_scene* s, const double* rays, uint64_t n, uin
     if (ts) CU(c, cudaMemcpyAsync(ts, d_t, n * 8, cudaMemcpyDeviceToHost, c->stream));
     if (ng) CU(c, cudaMemcpyAsync(ng, d_ng, n * 24, cudaMemcpyDeviceToHost, c->stream));
     if (ns) CU(c, cudaMemcpyAsync(ns, d_ns, n * 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LGB_OK;
+}
+
+int lgb_debug_fastmath(lgb_ctx* c, const double* x, uint64_t n, double* rcp_out, double* rsqrt_out) {
+    if (!c || (n && (!x || !rcp_out || !rsqrt_out))) return fail(c, LGB_ERR_INVALID, "lgb_debug_fastmath: NULL argument");
+    CU(c, cudaSetDevice(c->device));
+    if (n == 0) return LGB_OK;
+    CU(c, c->scratch.reserve(n * 24));
+    double* d = (double*)c->scratch.p;
+    CU(c, cudaMemcpyAsync(d, x, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, launch_fastmath(d, n, d + n, d + 2 * n, c->stream));
+    CU(c, cudaMemcpyAsync(rcp_out, d + n, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(rsqrt_out, d + 2 * n, n * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return LGB_OK;
 }

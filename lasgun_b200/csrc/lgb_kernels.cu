@@ -713,6 +713,78 @@ __device__ __forceinline__ void shade_point(const DevScene& S, const Ray64& ray,
     bsdf_prepare(P.B, P.wo);
 }
 
+// ------------------------------------------------------------------ lean surface record (scenes without transformed aggregates)
+// For spheres, cuboids and triangles without vertex normals the reference's ng and ns (surface.rs:158-183 on the differentials of
+// sphere.rs:88-120, cuboid.rs:97-99, triangle.rs:257-304) are both +-n, n the unit vector along
+//   sphere    p - c            cross(dpdu, dpdv) = -+2 pi^2 rho (p - c), swapped for hits from outside (sphere.rs:117-119)
+//   cuboid    e_k              the axis not among (u_axis, v_axis)
+//   triangle  cross(p0 - p2, p1 - p2)
+// and the signs are two of the reference's own decisions: ns = -n for a sphere hit from inside, ns = ff(n, -d) for cuboids and
+// triangles (cuboid.rs:98, triangle.rs:303), ng = ff(n, wo) always (surface.rs:165).  k_setup takes those decisions (in the reference's
+// arithmetic where a sign could hinge on rounding: anything within 1e-9 of a tie goes the long way through shade_point) and hands
+// them to k_shade in one byte per slot, so neither kernel forms the differentials, and the unit normal costs one reciprocal
+// square root instead of three normalisations.  n agrees with the reference's vectors to rounding (1e-16; 1e-11 for spheres, whose
+// hit point is that far off the surface): the shadow origin p + ng 2^-36 (surface.rs:168, integrate.rs:40) needs ng to 1e-4 to come
+// out bit-identical, which the occlusion-bit parity of every test confirms.
+constexpr uint32_t kSfNsFlip = 1u, kSfNgFlip = 2u, kSfAxisShift = 2u, kSfGeneric = 0x80u;
+struct LeanSurf { D3 n; uint32_t material, flags; };
+
+// Unit n of the hit primitive.  EXACT_SIGNS (k_setup): also the flip bits, or kSfGeneric where the lean form does not apply.
+template <bool EXACT_SIGNS>
+__device__ __forceinline__ void lean_surface(const DevScene& S, const Ray64& ray, double t, uint32_t ref, uint32_t flags_in, LeanSurf& L) {
+    const uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
+    uint32_t flags = flags_in;
+    if (type == LGB_PRIM_SPHERE) {
+        const double2 c01 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx));
+        const double2 c23 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx + 2));
+        const D3 c = d3(c01.x, c01.y, c23.x);
+        D3 pl = ray.o + ray.d * t - c;                                  // sphere.rs:88-91
+        if (pl.x == 0.0 && pl.y == 0.0) pl.x = 1e-5 * c23.y;            // sphere.rs:95
+        L.material = __ldg(&S.sph_mat[idx]);
+        if (EXACT_SIGNS) {
+            // inside <=> the smaller root is negative (sphere.rs:57-63) <=> c = |o - c|^2 - r^2 < 0 for an accepted hit: the roots are
+            // q / a and c / q (math.rs:21-27), of opposite sign iff c < 0; c == 0 is left to the reference's own sequence
+            const D3 l = ray.o - c;
+            const double cc = dot(l, l) - c23.y * c23.y;
+            const double side = -dot(pl, ray.d);                        // ng = ff(+-n, wo): sign of n . (-d)
+            const double tie = 1e-9 * (fabs(pl.x) + fabs(pl.y) + fabs(pl.z)) * (fabs(ray.d.x) + fabs(ray.d.y) + fabs(ray.d.z));
+            if (cc == 0.0 || !(fabs(side) > tie)) flags = kSfGeneric;
+            else flags = (cc < 0.0 ? kSfNsFlip : 0u) | (side < 0.0 ? kSfNgFlip : 0u);
+        }
+        L.n = pl * fast_rsqrt(fdot(pl, pl));
+    } else if (type == LGB_PRIM_CUBOID) {
+        L.material = __ldg(&S.cub_mat[idx]);
+        if (EXACT_SIGNS) {
+            double mn[3], mx[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { mn[k] = __ldg(&S.cub64[6 * (size_t)idx + k]); mx[k] = __ldg(&S.cub64[6 * (size_t)idx + 3 + k]); }
+            int ua = 1, va = 2; double tt = t;
+            cuboid_exact(mn, mx, ray, tt, ua, va);                      // which face: the reference's own bookkeeping (cuboid.rs:63-93)
+            const int k = 3 - ua - va;
+            const double dk = comp(ray.d, k);
+            // cross(e_u, e_v) = +-e_k; face-forwarded to -d (cuboid.rs:98) and to wo (surface.rs:165) it is -sign(d_k) e_k either way
+            if (dk == 0.0) flags = kSfGeneric;
+            else flags = (dk > 0.0 ? (kSfNsFlip | kSfNgFlip) : 0u) | ((uint32_t)k << kSfAxisShift);
+        }
+        L.n = axis_vec((int)((flags >> kSfAxisShift) & 3u));
+    } else {
+        const float4* tp = S.tri + 3 * (size_t)idx;
+        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+        L.material = __float_as_uint(q1.w);
+        const D3 p2 = d3(q2.x, q2.y, q2.z);
+        const D3 dp02 = d3(q0.x, q0.y, q0.z) - p2, dp12 = d3(q1.x, q1.y, q1.z) - p2;
+        const D3 c = fcross(dp02, dp12);
+        if (EXACT_SIGNS) {
+            const double side = -dot(c, ray.d);                         // n = ff(c, -d) (triangle.rs:303); ng = ff(-c^, wo): the same sign
+            const double tie = 1e-9 * (fabs(c.x) + fabs(c.y) + fabs(c.z)) * (fabs(ray.d.x) + fabs(ray.d.y) + fabs(ray.d.z));
+            if (__float_as_uint(q2.w) != kNoNormals || !(fabs(side) > tie)) flags = kSfGeneric;
+            else flags = side < 0.0 ? (kSfNsFlip | kSfNgFlip) : 0u;
+        }
+        L.n = c * fast_rsqrt(fdot(c, c));
+    }
+    L.flags = flags;
+}
+
 // ------------------------------------------------------------------ work mapping
 // Slot indices fit 32 bits (run_capture rejects launches of 2^32 samples or more): no 64-bit divisions on this path.
 __device__ __forceinline__ bool slot_to_pixel(const DevWork& W, uint64_t p64, uint32_t& x, uint32_t& y) {
@@ -1225,6 +1297,7 @@ __global__ void __launch_bounds__(LGB_LEAFP_THREADS, 1024 / LGB_LEAFP_THREADS) k
 
 template <bool ALL_SHADOWS, bool INST, bool RAYBUF = false>
 __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
+    constexpr bool LEAN = !INST && !RAYBUF;          // camera rays of scenes without transformed aggregates: lean_surface
     const uint64_t total = W.n_pixels * W.spp;
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t need = 0;
@@ -1246,26 +1319,42 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
             if (ref != LGB_MISS && !ref_done) {
                 live = true;
                 const double t = V.hit_t[g];
-                ShadePoint P; uint32_t id;
-                shade_point<false, INST>(S, ray, t, ref, P, id);
-                V.ps[3 * g + 0] = P.ps.x; V.ps[3 * g + 1] = P.ps.y; V.ps[3 * g + 2] = P.ps.z;
-                if (O.aov_id) O.aov_id[gi] = id;
+                D3 ng, ps; double wo_ng; uint32_t sflags = kSfGeneric;
+                if (LEAN) {                          // ng = +-n and the reference's sign decisions, no differentials (lean_surface)
+                    LeanSurf Ls;
+                    lean_surface<true>(S, ray, t, ref, 0u, Ls);
+                    sflags = Ls.flags;
+                    if (!(sflags & kSfGeneric)) {
+                        ng = (sflags & kSfNgFlip) ? -Ls.n : Ls.n;
+                        ps = ray.o + ray.d * t + ng * (2.220446049250313e-16 * 65536.0);       // surface.rs:168, integrate.rs:40
+                        wo_ng = 1.0;                 // ng faces wo by construction (clear of rounding, else kSfGeneric)
+                    }
+                }
+                if (sflags & kSfGeneric) {
+                    ShadePoint P; uint32_t id;
+                    shade_point<false, INST>(S, ray, t, ref, P, id);
+                    ng = P.ng; ps = P.ps; wo_ng = dot(P.wo, P.ng);
+                }
+                V.ps[3 * g + 0] = ps.x; V.ps[3 * g + 1] = ps.y; V.ps[3 * g + 2] = ps.z;
+                if (O.aov_id) O.aov_id[gi] = canonical_id(S, ref);
                 if (O.aov_t) O.aov_t[gi] = t;
-                const double wo_ng = dot(P.wo, P.ng);
+                uint32_t gate = 0;
                 for (uint32_t l = 0; l < S.n_lights; l++) {
                     const double* L = S.lights + 9 * (size_t)l;
                     // bsdf.f is zero unless wi and wo are on the same side of ng (bsdf.rs:75,85-86): the light then
                     // adds exactly zero whether or not it is occluded, so no shadow ray is traced.
                     // The test is the reference's own product with the normalised wi; its sign is that of the unnormalised
                     // dot product whenever that is clear of rounding (1e-6 of |v|_1), which spares the sqrt and the division.
-                    const D3 v = d3(L[0], L[1], L[2]) - P.ps;
-                    const double dv = dot(v, P.ng);
+                    const D3 v = d3(L[0], L[1], L[2]) - ps;
+                    const double dv = dot(v, ng);
                     bool same;
                     if (fabs(dv) > 1e-6 * (fabs(v.x) + fabs(v.y) + fabs(v.z)) && fabs(wo_ng) > 1e-100) same = (dv > 0.0) == (wo_ng > 0.0);
-                    else same = dot(normalize(v), P.ng) * wo_ng > 0.0;
-                    if (ALL_SHADOWS || same) need |= 1u << l;
+                    else same = dot(normalize(v), ng) * ((sflags & kSfGeneric) ? wo_ng : dot(-normalize(ray.d), ng)) > 0.0;
+                    if (same) gate |= 1u << l;
                 }
+                need = ALL_SHADOWS ? (S.n_lights >= 32u ? 0xFFFFFFFFu : (1u << S.n_lights) - 1u) : gate;
                 V.occl[g] = 0;
+                if (LEAN) { V.gate[g] = gate; V.sflags[g] = (unsigned char)sflags; }
             }
         }
     }
@@ -1705,7 +1794,7 @@ __global__ void __launch_bounds__(256, GENERAL ? LGB_GSHADE_MIN_BLOCKS : LGB_SHA
                     wi = wi * (1.0 / dist);
                     double wi_dot_n = dot(wi, P.ns);
                     D3 f = general ? bsdf_f_general(P.B, wi) : bsdf_f(P.B, wi);     // zero when the shadow ray was skipped
-                    output = output + mul_el(PI * d3(L[3], L[4], L[5]), f) * (wi_dot_n / f_att);
+                    output = output + mul_el(PI * d3(L[3], L[4], L[5]), f) * wi_dot_n / f_att;        // integrate.rs:65: (.. * wi_dot_n) / f_att
                 }
                 output = output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), general ? bsdf_f_general(P.B, P.ns) : bsdf_f(P.B, P.ns));   // integrate.rs:67
                 D3 zero = d3(0, 0, 0);
@@ -1731,6 +1820,169 @@ __global__ void __launch_bounds__(256, GENERAL ? LGB_GSHADE_MIN_BLOCKS : LGB_SHA
         return;
     }
 #endif
+    rad[3 * threadIdx.x] = output.x; rad[3 * threadIdx.x + 1] = output.y; rad[3 * threadIdx.x + 2] = output.z;
+    valid[threadIdx.x] = have ? 1 : 0;
+    __syncthreads();
+    if (mine && threadIdx.x % W.spp == 0 && valid[threadIdx.x]) {        // sample 0 of a pixel inside the film: resolve it
+        D3 c = d3(0, 0, 0);
+        for (uint32_t k = 0; k < W.spp; k++) c = c + d3(rad[3 * (threadIdx.x + k)], rad[3 * (threadIdx.x + k) + 1], rad[3 * (threadIdx.x + k) + 2]);
+        c = c * (1.0 / (double)W.spp);
+        const uint64_t p = (uint32_t)g / W.spp;
+        reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)y * W.w + x] = quantise(c);
+    }
+}
+
+// ------------------------------------------------------------------ lean shading (plastic / matte(0) scenes without transformed aggregates)
+// The same radiance as k_shade's plain variant, arranged for the FP64 pipe: the surface record comes from lean_surface + k_setup's
+// sign byte; the shading frame never appears (the lobes are isotropic and (ss, ts, ns) is orthonormal, so wo_l.z = wo.ns,
+// wi_l.z = wi.ns, wh = wi + wo with |wh|^2 = 2u, wi_l.wh = u, u = 1 + wi.wo); and all quotients of one BSDF evaluation share one
+// reciprocal:
+//   cos(theta_h)^2 = z^2 / 2u, z = wi.ns + wo.ns        q = alpha^2 c2 + s2 = Q / 2u, Q = alpha^2 z^2 + max(2u - z^2, 0)
+//   Fresnel at cos = sqrt(u / 2) (fresnel.rs:37-64, eta 1 -> 1.5):  F = Fnum / Fden, Fnum = (ad)^2 + (cb)^2, Fden = 2 (bd)^2
+//   4 cos_i cos_o (1 + Lambda_o + Lambda_i) = 2 (A_o cos_i + A_i cos_o), A(w) = sqrt(cos^2 + alpha^2 sin^2)   (microfacet.rs:55-66)
+//   f_glossy wi.ns / f_att = ks alpha^2 Fnum (2u)^2 wi.ns / (pi Q^2 2 (A_o cos_i + A_i cos_o) Fden f_att)
+// Four square roots and one reciprocal per evaluation, each a MUFU seed plus one refinement (lgb_math.cuh), against 9 IEEE
+// divisions / square roots in bsdf_f.  The result differs from the reference's by f64 rounding, as bsdf_f's does.
+struct LeanHit { D3 wo, ns; double woz, cos_o, Ao, alpha2; bool glossy; };
+__device__ __forceinline__ void lean_eval(const LeanHit& H, D3 wi, double wn, double f_att, double& a, double& g) {
+    const double PI = 3.14159265358979323846264338327950288;
+    g = 0.0;
+    const double cos_i = fabs(wn);
+    if (H.glossy && cos_i != 0.0) {                                      // (cos_o != 0: the caller returns black for wo_l.z == 0)
+        const double u = 1.0 + fdot(wi, H.wo);
+        const double z = wn + H.woz, z2 = z * z;
+        if (u > 0.0 && z2 != 0.0) {
+            const double twou = u + u;
+            const double Q = fma(H.alpha2, z2, fmax(twou - z2, 0.0));
+            const double c = fmin(fast_sqrt(0.5 * u), 1.0);
+            const double cos_t = fast_sqrt(fmax(fma(fma(c, c, -1.0), 4.0 / 9.0, 1.0), 0.0));    // 1 - (1 - c^2) / 1.5^2
+            const double ta = fma(1.5, c, -cos_t), tb = fma(1.5, c, cos_t), tc = fma(-1.5, cos_t, c), td = fma(1.5, cos_t, c);
+            const double ad = ta * td, cb = tc * tb, bd = tb * td;
+            const double fnum = fma(ad, ad, cb * cb), fden = 2.0 * (bd * bd);
+            const double Ai = fast_sqrt(fma(H.alpha2, fmax(fma(-cos_i, cos_i, 1.0), 0.0), cos_i * cos_i));
+            const double K = PI * (Q * Q) * (2.0 * fma(H.Ao, cos_i, Ai * H.cos_o)) * fden;      // everything under the bar but f_att
+            if (K > 0.0) {
+                const double R = fast_rcp(K * f_att);
+                g = H.alpha2 * fnum * (twou * twou) * R * wn;
+                a = wn * K * R;
+                return;
+            }
+        }
+    }
+    a = wn * fast_rcp(f_att);
+}
+
+// The slots lean_surface leaves to the reference's own sequence (vertex normals, sign decisions within rounding of a tie).
+__device__ __forceinline__ D3 shade_generic_plastic(const DevScene& S, const DevShade& sh, const Ray64& ray, double t, uint32_t ref, uint32_t occl) {
+    const double PI = 3.14159265358979323846264338327950288;
+    ShadePoint P; uint32_t id;
+    shade_point<true, false, false>(S, ray, t, ref, P, id);
+    D3 output = d3(0, 0, 0);
+    for (uint32_t l = 0; l < S.n_lights; l++) {              // integrate.rs:47-66
+        if ((occl >> l) & 1u) continue;
+        const double* L = S.lights + 9 * (size_t)l;
+        D3 wi = d3(L[0], L[1], L[2]) - P.ps;
+        const double dist = sqrt(dot(wi, wi));
+        const double f_att = L[6] + L[7] * dist + L[8] * dist * dist;
+        if (f_att == 0.0) continue;
+        wi = wi * (1.0 / dist);
+        const double wi_dot_n = dot(wi, P.ns);
+        output = output + mul_el(PI * d3(L[3], L[4], L[5]), bsdf_f(P.B, wi)) * wi_dot_n / f_att;
+    }
+    return output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), bsdf_f(P.B, P.ns));   // integrate.rs:67
+}
+
+#ifndef LGB_LEAN_MIN_BLOCKS
+#define LGB_LEAN_MIN_BLOCKS 4
+#endif
+template <bool FUSED>
+__global__ void __launch_bounds__(256, LGB_LEAN_MIN_BLOCKS) k_shade_lean(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
+    const double PI = 3.14159265358979323846264338327950288;
+    const uint64_t total = W.n_pixels * W.spp;
+    __shared__ double rad[FUSED ? 256 * 3 : 3];
+    __shared__ unsigned char valid[FUSED ? 256 : 1];
+    uint64_t g;
+    bool mine;
+    if (FUSED) {
+        const uint32_t ppb = blockDim.x / W.spp;                        // pixels per block
+        const uint64_t p = (uint64_t)blockIdx.x * ppb + threadIdx.x / W.spp;
+        mine = threadIdx.x < ppb * W.spp && p < W.n_pixels;
+        g = p * W.spp + threadIdx.x % W.spp;
+    } else {
+        g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        mine = g < total;
+    }
+    D3 output = d3(0, 0, 0);
+    bool have = false, generic = false;
+    uint32_t x = 0, y = 0, s = 0;
+    if (mine) {
+        const uint32_t ref = V.hit_ref[g];
+        Ray64 ray;
+        if (ref != kSlotUnused && slot_ray<false>(C, W, g, ray, x, y, s)) {
+            have = true;
+            if (ref == LGB_MISS) {                                       // background.rs:25-34
+                output = background_of(sh, ray.d);
+            } else {
+                const uint32_t occl = V.occl[g], sflags = V.sflags[g];
+                const double t = V.hit_t[g];
+                if (O.aov_occl) O.aov_occl[((uint64_t)y * W.w + x) * W.spp + s] = occl;
+                if (sflags & kSfGeneric) generic = true;             // (rare: shaded after the lean code so that their registers do not add up)
+                else {
+                    const uint32_t lit = V.gate[g] & ~occl;              // lights that are neither occluded nor on the far side of ng
+                    LeanSurf Ls;
+                    lean_surface<false>(S, ray, t, ref, sflags, Ls);
+                    LeanHit H;
+                    H.ns = (sflags & kSfNsFlip) ? -Ls.n : Ls.n;
+                    const D3 ng = (sflags & kSfNgFlip) ? -Ls.n : Ls.n;
+                    const D3 ps = fmadd(ng, 2.220446049250313e-16 * 65536.0, fmadd(ray.d, t, ray.o));
+                    H.wo = ray.d * -fast_rsqrt(fdot(ray.d, ray.d));
+                    H.woz = fdot(H.wo, H.ns); H.cos_o = fabs(H.woz);
+                    const double* M = S.materials + kMatStride * (size_t)Ls.material;
+                    const uint32_t mflags = (uint32_t)__double_as_longlong(M[7]);
+                    H.glossy = mflags & kMatGlossy; H.alpha2 = M[3] * M[3];
+                    H.Ao = H.glossy ? fast_sqrt(fma(H.alpha2, fmax(fma(-H.cos_o, H.cos_o, 1.0), 0.0), H.cos_o * H.cos_o)) : 0.0;
+                    if (H.woz != 0.0) {                                  // bsdf.rs:82: every lobe is zero at wo_l.z == 0
+                        D3 dsum = d3(0, 0, 0), gsum = d3(0, 0, 0);       // sum of (pi I | ambient) x weight of the diffuse and of the glossy lobe
+                        for (uint32_t l = 0; l < S.n_lights; l++) {      // integrate.rs:47-66
+                            if (!((lit >> l) & 1u)) continue;
+                            const double* L = S.lights + 9 * (size_t)l;
+                            const D3 v = d3(L[0], L[1], L[2]) - ps;
+                            const double d2 = fdot(v, v);
+                            if (!(d2 > 0.0)) continue;
+                            const double inv = fast_rsqrt(d2), dist = d2 * inv;
+                            const double f_att = fma(L[8] * dist, dist, fma(L[7], dist, L[6]));
+                            if (f_att == 0.0) continue;
+                            const D3 wi = v * inv;
+                            double a, gl;
+                            lean_eval(H, wi, fdot(wi, H.ns), f_att, a, gl);
+                            const D3 I = PI * d3(L[3], L[4], L[5]);
+                            dsum = fmadd(I, a, dsum); gsum = fmadd(I, gl, gsum);
+                        }
+                        if (((sflags & kSfNsFlip) != 0) == ((sflags & kSfNgFlip) != 0)) {       // integrate.rs:67: wi = ns passes bsdf.rs:75 iff ns = ng
+                            double a, gl;
+                            lean_eval(H, H.ns, 1.0, 1.0, a, gl);
+                            const D3 amb = d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]);
+                            dsum = fmadd(amb, a, dsum); gsum = fmadd(amb, gl, gsum);
+                        }
+                        const double inv_pi = 0.318309886183790671537767526745028724;
+                        const D3 kd = (mflags & kMatDiffuse) ? d3(M[0], M[1], M[2]) * inv_pi : d3(0, 0, 0);
+                        output = d3(fma(kd.x, dsum.x, M[4] * gsum.x), fma(kd.y, dsum.y, M[5] * gsum.y), fma(kd.z, dsum.z, M[6] * gsum.z));
+                    }
+                }
+            }
+        }
+    }
+#ifndef LGB_LEAN_NO_GENERIC       // (experiments: the register need of the lean code alone)
+    if (generic) {
+        Ray64 ray; uint32_t x2, y2, s2;
+        slot_ray<false>(C, W, g, ray, x2, y2, s2);
+        output = shade_generic_plastic(S, sh, ray, V.hit_t[g], V.hit_ref[g], V.occl[g]);
+    }
+#endif
+    if (!FUSED) {
+        if (have) { O.radiance[3 * g + 0] = output.x; O.radiance[3 * g + 1] = output.y; O.radiance[3 * g + 2] = output.z; }
+        return;
+    }
     rad[3 * threadIdx.x] = output.x; rad[3 * threadIdx.x + 1] = output.y; rad[3 * threadIdx.x + 2] = output.z;
     valid[threadIdx.x] = have ? 1 : 0;
     __syncthreads();
@@ -1817,7 +2069,7 @@ __global__ void __launch_bounds__(LGB_SEC_THREADS, LGB_SEC_MIN_BLOCKS) k_seconda
                 wi = wi * (1.0 / dist);
                 const double wi_dot_n = dot(wi, P.ns);
                 const D3 f = general ? bsdf_f_general(P.B, wi) : bsdf_f(P.B, wi);
-                output = output + mul_el(PI * d3(L[3], L[4], L[5]), f) * (wi_dot_n / f_att);
+                output = output + mul_el(PI * d3(L[3], L[4], L[5]), f) * wi_dot_n / f_att;        // integrate.rs:65: (.. * wi_dot_n) / f_att
             }
             output = output + mul_el(d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]), general ? bsdf_f_general(P.B, P.ns) : bsdf_f(P.B, P.ns));
         }
@@ -1935,6 +2187,16 @@ __global__ void k_fp64_peak(int iters, double* sink) {
     if (s == 123456.789) *sink = s;
 }
 
+// The shading path's reciprocal / reciprocal square root (lgb_math.cuh) on caller-supplied values: tests pin their accuracy.
+__global__ void k_fastmath(const double* x, uint64_t n, double* rcp, double* rsq) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { rcp[i] = fast_rcp(x[i]); rsq[i] = fast_rsqrt(x[i]); }
+}
+cudaError_t launch_fastmath(const double* x, uint64_t n, double* rcp, double* rsq, cudaStream_t stream) {
+    if (n) k_fastmath<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, n, rcp, rsq);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ launch wrappers (called from lgb_api.cu)
 bool render_fused(uint32_t spp) { return spp >= 1 && spp <= 256; }      // and !S.general: see launch_render
 
@@ -2025,11 +2287,11 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     } else if (render_fused(W.spp) && !O.aov_li) {   // whole pixels per block: shade and resolve in one kernel, no radiance buffer
         const unsigned ft = W.spp <= LGB_FUSED_THREADS ? LGB_FUSED_THREADS : 256u;        // threads per block: whole pixels, as few of them as the option allows
         const unsigned fb = (unsigned)((W.n_pixels + (ft / W.spp) - 1) / (ft / W.spp));
-        if (inst) k_shade<true, true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V);
+        if (inst) k_shade<true, true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V); else k_shade_lean<true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V);
         mark(5);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     } else {
-        if (inst) k_shade<true, false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+        if (inst) k_shade<true, false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade_lean<false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
         mark(5);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);

@@ -141,6 +141,8 @@ struct DevWave {
     uint32_t* hit_ref;               // type << 30 | index, LGB_MISS, or kSlotUnused (pixel outside the film)
     double* ps;                      // shadow-ray origin p + p_err (3 per slot)
     uint32_t* occl;                  // bit l set: light l occluded
+    uint32_t* gate;                  // bit l set: wi of light l and wo lie on the same side of ng (bsdf.rs:75,85-86); k_setup -> k_shade (lean path)
+    unsigned char* sflags;           // the reference's sign decisions about the surface record (kSf*, lgb_kernels.cu); k_setup -> k_shade
     // Shadow-ray queues of slot indices, three per light (kQueueA/B/C), each queue_stride entries:
     //   A  anchor rays: the centre sample of every pixel (every ray at 1 spp); traced first, their occluder
     //      is remembered per (light, pixel) in `occluder`

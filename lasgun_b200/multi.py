@@ -91,19 +91,38 @@ class SharedFilm:
             self.ptr = None
 
 
-def capture_distributed(dev_scene, w: int, h: int, film, rank: int, ranks: int, stream: int = 0, shared: SharedFilm | None = None):
+def capture_distributed(dev_scene, w: int, h: int, film, rank: int, ranks: int, stream: int | None = None, shared: SharedFilm | None = None):
     """One frame across `ranks` GPUs.  With `shared`: every rank's kernels store their tiles into rank 0's film over NVLink
     and a stream-ordered barrier completes the frame (no collective moves pixels).  Otherwise: render this rank's tiles into
-    `film` (CUDA uint8 tensor) and SUM-reduce to rank 0."""
+    `film` (CUDA uint8 tensor) and SUM-reduce to rank 0.
+
+    `stream` is the cudaStream_t the kernels are queued on; it must be the stream torch's collectives and `film.zero_()` run on
+    (default: torch's current stream), otherwise the zeroing, the reduce or the end-of-frame barrier are not ordered against
+    the stores.  With `shared`, the barrier at the end of frame k also orders rank 0's readers of frame k before any rank's
+    stores of frame k + 1 only if the reader runs on this same stream before the next call (the bench and the tests do)."""
+    import torch
+    cur = torch.cuda.current_stream().cuda_stream
+    if stream is None:
+        stream = cur
+    # the legacy default stream (0) cannot be handed to the library (NULL means its private stream), and a stream other than torch's
+    # current one is not ordered against the collectives: in both cases fence on the host instead (slower, never wrong)
+    fenced = ranks > 1 and (stream == 0 or stream != cur)
+
+    def render(ptr):
+        if fenced:
+            torch.cuda.current_stream().synchronize()           # film.zero_() / the previous frame's readers are done
+            dev_scene.capture_device(w, h, ptr, rank=rank, ranks=ranks, stream=stream, want_stats=True)      # synchronises
+        else:
+            dev_scene.capture_device(w, h, ptr, rank=rank, ranks=ranks, stream=stream)
     if shared is not None:
         import torch.distributed as dist
-        dev_scene.capture_device(w, h, shared.ptr, rank=rank, ranks=ranks, stream=stream)
+        render(shared.ptr)
         if ranks > 1:
             dist.all_reduce(shared._sync)            # on the current stream, i.e. after this rank's stores: the frame is whole on return
         return shared.tensor
     if ranks > 1:
         film.zero_()
-    dev_scene.capture_device(w, h, film.data_ptr(), rank=rank, ranks=ranks, stream=stream)
+    render(film.data_ptr())
     if ranks > 1:
         gather_film(film)
     return film

@@ -81,6 +81,17 @@ SMALL = {
 }
 
 
+def test_shading_fast_reciprocals(native, gpu_ctx):
+    """The shading kernel replaces IEEE 1/x and 1/sqrt(x) by a MUFU seed + one third-order step (csrc/lgb_math.cuh): within a few
+    ulp over the whole range shading meets (they only colour: no hit, shadow or sign decision goes through them)."""
+    rng = np.random.default_rng(7)
+    x = np.concatenate([np.exp(rng.uniform(np.log(1e-30), np.log(1e30), 200000)), rng.uniform(0.5, 2.0, 200000),
+                        np.array([1.0, 2.0, 4.0, 0.25, 3.0, 1e-300, 1e300, 2.0 - 2.0 ** -52])])
+    r, q = gpu_ctx.fastmath(x)
+    assert np.max(np.abs(r * x - 1.0)) <= 6 * 2.0 ** -53
+    assert np.max(np.abs(q * q * x - 1.0)) <= 12 * 2.0 ** -53
+
+
 @pytest.mark.parametrize("name", sorted(SMALL))
 def test_small_config_parity(native, oracle, gpu_ctx, name):
     sc, (w, h) = SMALL[name]()

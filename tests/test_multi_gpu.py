@@ -27,7 +27,15 @@ torch.cuda.synchronize()
 film = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
 multi.capture_distributed(dev, w, h, film, rank, world, st.cuda_stream)      # NCCL gather of the same frame
 torch.cuda.synchronize()
+film2 = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+multi.capture_distributed(dev, w, h, film2, rank, world)                      # no stream given: torch's current stream
+torch.cuda.synchronize()
+film3 = torch.ones((h, w, 4), dtype=torch.uint8, device="cuda")
+with torch.cuda.stream(torch.cuda.default_stream()):                          # the legacy default stream: host-fenced, still whole
+    multi.capture_distributed(dev, w, h, film3, rank, world)
+torch.cuda.synchronize()
 if rank == 0:
+    assert torch.equal(film2, film) and torch.equal(film3, film), "capture_distributed without an explicit stream lost pixels"
     one = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
     dev.capture_device(w, h, one.data_ptr(), rank=0, ranks=1, stream=st.cuda_stream)
     torch.cuda.synchronize()
@@ -51,7 +59,7 @@ def test_two_gpu_shared_film(tmp_path):
         pytest.skip("needs two GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, LGB_ROOT=ROOT, NCCL_DEBUG="WARN")
+    env = dict(os.environ, LGB_ROOT=ROOT)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29631", str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
