@@ -263,6 +263,21 @@ int lgb_capture_aov(lgb_ctx* ctx, lgb_scene* scene, uint32_t w, uint32_t h, uint
 int lgb_capture_device(lgb_ctx* ctx, lgb_scene* scene, uint32_t w, uint32_t h, uint32_t tile_rank,
                        uint32_t tile_ranks, void* d_film, void* stream, lgb_stats* stats);
 
+/* Per-kernel timing of one frame (bench / roofline): the frame of lgb_capture_device (all tiles) with a pair of CUDA events around
+ * EVERY kernel launch, all launches on one stream (the shadow chains of different lights do not overlap in this call), and, with
+ * LGB_OPT_COUNT_WORK set, each launch's share of the work counters.  Entries come in launch order; *n_out is the number of
+ * launches (entries beyond `cap` are dropped).  d_film: device film or NULL (the context's own).  Synchronises. */
+typedef struct lgb_kernel_time {
+    char name[40];                   /* kernel, "[light l]" appended for the per-light launches */
+    float ms;
+    uint32_t reserved;
+    uint64_t node_tests;             /* work counters of this launch alone (zero unless LGB_OPT_COUNT_WORK): see lgb_stats */
+    uint64_t filter_tests[3], exact_tests[3];
+    uint64_t primary_rays, primary_hits, shadow_rays, shadow_occluded;
+} lgb_kernel_time;
+int lgb_capture_profile(lgb_ctx* ctx, lgb_scene* scene, uint32_t w, uint32_t h, void* d_film,
+                        lgb_kernel_time* out, uint32_t cap, uint32_t* n_out, lgb_stats* stats);
+
 /* Trace caller-supplied rays (o[3], d[3] f64 each) through the scene: closest-hit id and t.
  * Used by the known-answer and random-ray parity tests. */
 int lgb_trace_rays(lgb_ctx* ctx, lgb_scene* scene, const double* rays_od, uint64_t n_rays,

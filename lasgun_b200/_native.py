@@ -22,7 +22,7 @@ LGB_LEAF_FLAG = 0x80000000
 ABI_SYMBOLS = [
     "lgb_build_probe", "lgb_device_count", "lgb_init", "lgb_set_option", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
     "lgb_film_alloc_shared", "lgb_film_open_shared", "lgb_film_release_shared", "lgb_scene_destroy", "lgb_scene_layout_bytes", "lgb_scene_export", "lgb_scene_import", "lgb_scene_verify", "lgb_scene_device_bytes", "lgb_scene_build_ms", "lgb_scene_node_count", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
-    "lgb_capture_device", "lgb_trace_rays", "lgb_debug_fastmath", "lgb_measure_l2_read_gbs", "lgb_measure_fp32_gops", "lgb_measure_fp64_gops",
+    "lgb_capture_device", "lgb_capture_profile", "lgb_trace_rays", "lgb_debug_fastmath", "lgb_measure_l2_read_gbs", "lgb_measure_fp32_gops", "lgb_measure_fp64_gops",
 ]
 
 
@@ -75,6 +75,12 @@ class BuildInfo(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 40), ("ms", C.c_float), ("reserved", C.c_uint32), ("node_tests", C.c_uint64),
+                ("filter_tests", C.c_uint64 * 3), ("exact_tests", C.c_uint64 * 3), ("primary_rays", C.c_uint64), ("primary_hits", C.c_uint64),
+                ("shadow_rays", C.c_uint64), ("shadow_occluded", C.c_uint64)]
+
+
 class Stats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("primary_hits", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("shadow_rays_traced", C.c_uint64), ("shadow_occluded", C.c_uint64), ("shadow_cache_hits", C.c_uint64), ("exact_tests", C.c_uint64 * 3),
@@ -115,6 +121,7 @@ def lib():
         "lgb_capture_subset": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u8p, C.POINTER(Stats)]),
         "lgb_capture_aov": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, u8p, u32p, dp, u32p, dp, C.POINTER(Stats)]),
         "lgb_capture_device": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.POINTER(Stats)]),
+        "lgb_capture_profile": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, C.POINTER(KernelTime), C.c_uint32, u32p, C.POINTER(Stats)]),
         "lgb_trace_rays": (C.c_int, [vp, vp, dp, C.c_uint64, u32p, dp, dp, dp]),
         "lgb_debug_fastmath": (C.c_int, [vp, dp, C.c_uint64, dp, dp]),
         "lgb_measure_l2_read_gbs": (C.c_int, [vp, C.c_uint64, C.c_int, dp]),
@@ -453,6 +460,19 @@ class DeviceScene:
         self.ctx.check(lib().lgb_capture_device(self.ctx.h, self.h, w, h, rank, ranks, C.c_void_p(d_film_ptr),
                                                 C.c_void_p(stream) if stream else None, C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
+
+    def capture_profile(self, w, h, d_film_ptr=0):
+        """lgb_capture_profile: (list of per-launch dicts in launch order, frame stats)."""
+        arr = (KernelTime * 64)()
+        n = C.c_uint32()
+        st = Stats()
+        self.ctx.check(lib().lgb_capture_profile(self.ctx.h, self.h, w, h, C.c_void_p(d_film_ptr) if d_film_ptr else None, arr, 64, C.byref(n), C.byref(st)))
+        out = []
+        for k in arr[:min(n.value, 64)]:
+            out.append({"name": k.name.decode(), "ms": float(k.ms), "node_tests": int(k.node_tests), "filter_tests": list(k.filter_tests),
+                        "exact_tests": list(k.exact_tests), "primary_rays": int(k.primary_rays), "primary_hits": int(k.primary_hits),
+                        "shadow_rays": int(k.shadow_rays), "shadow_occluded": int(k.shadow_occluded)})
+        return out, st.as_dict()
 
     def trace_rays(self, rays_od):
         rays = np.ascontiguousarray(rays_od, np.float64).reshape(-1, 6)

@@ -18,7 +18,7 @@
 
 namespace lgb {
 constexpr int kRenderEvents = 7;
-cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev, int part, const SideStreams* side);
+cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev, int part, const SideStreams* side, KernelLog* klog);
 bool render_fused(uint32_t spp);
 cudaError_t launch_level(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, int sms, cudaStream_t);
 cudaError_t launch_gather(const SpawnRec* recs, const uint32_t* nspec, double* rad_parent, const double* rad_child, uint64_t n_upper, cudaStream_t);
@@ -38,6 +38,7 @@ static_assert(sizeof(lgb_material) == 72 && offsetof(lgb_material, kind) == 64, 
 static_assert(sizeof(lgb_node) == 32 && sizeof(lgb_instance) == 16 + 2 * 16 * 8, "lgb_node / lgb_instance layout");
 static_assert(sizeof(lgb_stats) == 21 * 8 + 12 * 4, "lgb_stats layout");
 static_assert(sizeof(SpawnRec) == 72, "SpawnRec layout");
+static_assert(sizeof(lgb_kernel_time) == 40 + 8 + 11 * 8, "lgb_kernel_time layout");
 
 static thread_local std::string g_init_error;
 
@@ -66,6 +67,7 @@ struct lgb_ctx {
     // levels of the specular ray trees (Whitted recursion): radiance and spawn records of every level (kept until the fold back up),
     // the rays of the current and the next level, the wavefront buffers of the current level, per-level counters
     DevBuf lvl_rad[kMaxRecursion + 1], lvl_recs[kMaxRecursion + 1], raybuf[2], wave2, wave2_ctr, lvl_ctr;
+    KernelLog klog{}; DevBuf klog_snaps;   // lgb_capture_profile
     SideStreams side{};                    // streams the shadow chains of different lights are spread over (LGB_OPT_SIDE_STREAMS)
     int side_streams = 1;
     int whitted_wavefront = 1;             // LGB_OPT_WHITTED: 1 level-by-level wavefront, 0 one thread per ray tree (k_secondary)
@@ -223,6 +225,8 @@ void lgb_shutdown(lgb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties, &c->beam, &c->raybuf[0], &c->raybuf[1], &c->wave2, &c->wave2_ctr, &c->lvl_ctr, &c->aov_li, &c->beam2}) b->release();
+    c->klog_snaps.release();
+    for (int k = 0; k < c->klog.made; k++) { cudaEventDestroy(c->klog.ev0[k]); cudaEventDestroy(c->klog.ev1[k]); }
     for (DevBuf& b : c->lvl_rad) b.release();
     for (DevBuf& b : c->lvl_recs) b.release();
     if (c->staging) cudaFreeHost(c->staging);
@@ -922,9 +926,12 @@ struct CaptureArgs {
     void* d_film;                // device film or NULL (context film)
     cudaStream_t stream;
     bool want_li = false;        // aov: also the radiance of every sample
+    KernelLog* klog = nullptr;   // lgb_capture_profile: events and counter snapshots around every launch (one stream)
 };
 
 // Wavefront buffers of `nslots` sample slots carved out of one allocation (layout: DevWave, lgb_types.cuh).
+static uint64_t fastdiv_magic(uint64_t d) { return d <= 1 ? 0ull : (~0ull) / d + 1ull; }      // fdiv(), lgb_kernels.cu
+static void set_divisors(DevWork& W, uint32_t root) { W.fd_spp = fastdiv_magic(W.spp); W.fd_root = fastdiv_magic(root); W.fd_nmx = fastdiv_magic(W.n_macro_x); }
 static size_t wave_bytes(uint64_t nslots, uint32_t nl, uint64_t npix) { return nslots * (8 + 24 + 4 + 4 + 4 + 12 * (size_t)nl) + npix * 4 * nl + ((nslots + 15) & ~(uint64_t)15); }
 static DevWave carve_wave(void* wave, void* ctr, uint64_t nslots, uint32_t nl, uint64_t npix = 1) {
     DevWave V{};
@@ -985,6 +992,7 @@ static int run_whitted_levels(lgb_ctx* c, lgb_scene* s, const DevOut& O0, uint64
         DevWork Wl{};
         Wl.mode = 3; Wl.w = (uint32_t)n; Wl.h = 1; Wl.n_pixels = n; Wl.spp = 1; Wl.rays = (const double*)c->raybuf[(l + 1) & 1].p; Wl.depth = l + 1;
         Wl.hole_lo = (uint32_t)n_r; Wl.hole_hi = n_t ? (uint32_t)slots[l] : (uint32_t)n_r;
+        set_divisors(Wl, 1);
         DevWave Vl = carve_wave(c->wave2.p, c->wave2_ctr.p, n, nl);
         if (l + 1 < S.recursion && !prepare_spawn(c, Vl, l + 1, n)) return fail(c, LGB_ERR_CUDA, "capture: out of device memory for a level of the specular ray trees");
         DevOut Ol{}; Ol.radiance = (double*)c->lvl_rad[l + 1].p;
@@ -1033,6 +1041,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         W.n_pixels = area > a.k ? (area - a.k + a.n - 1) / a.n : 0;
         W.compact_out = 1;
     }
+    set_divisors(W, s->cam.root);
     const uint64_t total = W.n_pixels * W.spp;
     if (total >= (1ull << 32) - 64) return fail(c, LGB_ERR_INVALID, "capture: more than 2^32 samples in one launch");
     if (s->cam.pixel_separation != 0.0 && W.aspect > 4.0)
@@ -1086,7 +1095,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     cudaEvent_t* pev = (stats && sync_stats && total) ? c->phase : nullptr;
     uint32_t tie_slots = 0;
     const bool st_on = a.aov || c->count_work;
-    const SideStreams* side = (c->side_streams && c->side.n) ? &c->side : nullptr;
+    const SideStreams* side = (c->side_streams && c->side.n && !a.klog) ? &c->side : nullptr;
     int wf = (S.general && c->whitted_wavefront) ? 4 : 0;           // launch_render stops after k_shade; the levels and the resolve follow here
     if (wf && S.specular && S.recursion > 0 && total) {             // k_shade of the camera wave spawns level 1
         CU(c, c->lvl_ctr.reserve(4 * (kMaxRecursion + 2) * 4));
@@ -1096,7 +1105,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     if (s->lazy_fn && !s->dev.rank && total) {
         // no rank tables yet: trace the primary rays, and only if one met two primitives at bit-identical t fetch the
         // caller's reference tree, build the tables and re-trace those slots (lasgun_b200.h, "Lazy reference tree")
-        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 1, side));
+        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 1, side, a.klog));
         uint32_t ties = 0;
         CU(c, cudaMemcpyAsync(&ties, V.tie_count, 4, cudaMemcpyDeviceToHost, st));
         CU(c, cudaStreamSynchronize(st));
@@ -1106,11 +1115,11 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
             DevWork W2 = W;
             if (ties <= V.tie_cap) { W2.slot_list = V.tie_list; W2.n_list = ties; }
             else CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));          // too many to list: the whole frame again
-            CU(c, launch_render(s->dev, s->cam, s->shade, W2, O, V, st_on, a.aov, c->sm_count, st, ties <= V.tie_cap ? nullptr : pev, 1, side));
+            CU(c, launch_render(s->dev, s->cam, s->shade, W2, O, V, st_on, a.aov, c->sm_count, st, ties <= V.tie_cap ? nullptr : pev, 1, side, a.klog));
         }
-        CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 2 | wf, side));
+        CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 2 | wf, side, a.klog));
     } else {
-        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 3 | wf, side));
+        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 3 | wf, side, a.klog));
     }
     uint64_t level_rays = 0; uint32_t level_launches = 0;
     if (wf && total) {                     // materials beyond plastic: the levels of the specular ray trees, then the film
@@ -1196,6 +1205,35 @@ int lgb_capture_subset(lgb_ctx* c, lgb_scene* s, uint32_t k, uint32_t n, uint32_
     std::vector<uint8_t> compact(np * 4);
     if (np) { rc = finish_host(c, c->film.p, compact.data(), np * 4, stp); if (rc) return rc; }
     for (uint64_t p = 0; p < np; p++) std::memcpy(rgba + (k + p * (uint64_t)n) * 4, &compact[4 * p], 4);   // lib.rs:152-161
+    return LGB_OK;
+}
+
+int lgb_capture_profile(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, void* d_film, lgb_kernel_time* out, uint32_t cap, uint32_t* n_out, lgb_stats* stats) {
+    if (!c || !out || !n_out) return fail(c, LGB_ERR_INVALID, "lgb_capture_profile: NULL argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, c->klog_snaps.reserve(sizeof(DevCounters) * KernelLog::kMax));
+    c->klog.n = 0; c->klog.snaps = (DevCounters*)c->klog_snaps.p;
+    lgb_stats local; lgb_stats* stp = stats ? stats : &local;
+    CaptureArgs a{w, h, 0, 0, 1, 0, 0, false, d_film, nullptr};
+    a.klog = &c->klog;
+    if (int rc = run_capture(c, s, a, stp, true)) return rc;             // synchronises
+    const int n = c->klog.n;
+    std::vector<DevCounters> snap((size_t)std::max(n, 1));
+    if (n) CU(c, cudaMemcpy(snap.data(), c->klog.snaps, sizeof(DevCounters) * n, cudaMemcpyDeviceToHost));
+    DevCounters prev{};
+    for (int i = 0; i < n && (uint32_t)i < cap; i++) {
+        lgb_kernel_time& o = out[i];
+        std::memset(&o, 0, sizeof o);
+        std::snprintf(o.name, sizeof o.name, "%s", c->klog.name[i]);
+        CU(c, cudaEventElapsedTime(&o.ms, c->klog.ev0[i], c->klog.ev1[i]));
+        const DevCounters& k = snap[i];
+        o.node_tests = k.node_tests - prev.node_tests;
+        for (int t = 0; t < 3; t++) { o.filter_tests[t] = k.filter[t] - prev.filter[t]; o.exact_tests[t] = k.exact[t] - prev.exact[t]; }
+        o.primary_rays = k.primary_rays - prev.primary_rays; o.primary_hits = k.primary_hits - prev.primary_hits;
+        o.shadow_rays = k.shadow_traced - prev.shadow_traced; o.shadow_occluded = k.shadow_occluded - prev.shadow_occluded;
+        prev = k;
+    }
+    *n_out = (uint32_t)n;
     return LGB_OK;
 }
 

@@ -748,22 +748,39 @@ __device__ __forceinline__ void lean_surface(const DevScene& S, const Ray64& ray
             const double cc = dot(l, l) - c23.y * c23.y;
             const double side = -dot(pl, ray.d);                        // ng = ff(+-n, wo): sign of n . (-d)
             const double tie = 1e-9 * (fabs(pl.x) + fabs(pl.y) + fabs(pl.z)) * (fabs(ray.d.x) + fabs(ray.d.y) + fabs(ray.d.z));
-            if (cc == 0.0 || !(fabs(side) > tie)) flags = kSfGeneric;
+            if (cc == 0.0 || !(fabs(side) > tie) || !(c23.y > 0.0)) flags = kSfGeneric;
             else flags = (cc < 0.0 ? kSfNsFlip : 0u) | (side < 0.0 ? kSfNgFlip : 0u);
         }
-        L.n = pl * fast_rsqrt(fdot(pl, pl));
+        // the reference's normal is cross(dpdu, dpdv) of sphere.rs:97-116 = -+2 pi^2 (x s, y s, z rho), s = r sin(theta) = sqrt(r^2 - z^2) as the
+        // clamped acos / sin pair gives it, rho = |(x, y)|: NOT the radial direction when the hit point sits 1e-10 r off the surface (a ray
+        // from far away: math.rs:7-30 cancels ten digits).  Its length is rho r, so n = (x s / (rho r), y s / (rho r), z / r).
+        const double A = fmax(fma(c23.y, c23.y, -(pl.z * pl.z)), 0.0), B = fma(pl.x, pl.x, pl.y * pl.y);
+        const double inv_r = fast_rcp(fabs(c23.y));
+        if (A > 0.0 && B > 0.0) {
+            const double k = A * fast_rsqrt(A * B) * inv_r;             // s / (rho r)
+            L.n = d3(pl.x * k, pl.y * k, fmin(fmax(pl.z * inv_r, -1.0), 1.0));
+        } else L.n = d3(0.0, 0.0, pl.z < 0.0 ? -1.0 : 1.0);
     } else if (type == LGB_PRIM_CUBOID) {
         L.material = __ldg(&S.cub_mat[idx]);
         if (EXACT_SIGNS) {
             double mn[3], mx[3];
 #pragma unroll
             for (int k = 0; k < 3; k++) { mn[k] = __ldg(&S.cub64[6 * (size_t)idx + k]); mx[k] = __ldg(&S.cub64[6 * (size_t)idx + 3 + k]); }
-            int ua = 1, va = 2; double tt = t;
-            cuboid_exact(mn, mx, ray, tt, ua, va);                      // which face: the reference's own bookkeeping (cuboid.rs:63-93)
-            const int k = 3 - ua - va;
+            // which face (cuboid.rs:63-93 keeps the axis of the winning slab): the one the hit point lies on.  The distance to the nearest
+            // face plane is rounding-sized along that axis only, unless the point sits on an edge -- those go the long way.
+            const D3 p = ray.o + ray.d * t;
+            double e[3], scale = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double pk = comp(p, k);
+                e[k] = fmin(fabs(pk - mn[k]), fabs(pk - mx[k]));
+                scale = fmax(scale, fmax(fabs(mn[k]), fabs(mx[k])));
+            }
+            const int k = e[0] <= e[1] ? (e[0] <= e[2] ? 0 : 2) : (e[1] <= e[2] ? 1 : 2);
+            const double second = k == 0 ? fmin(e[1], e[2]) : k == 1 ? fmin(e[0], e[2]) : fmin(e[0], e[1]);
             const double dk = comp(ray.d, k);
             // cross(e_u, e_v) = +-e_k; face-forwarded to -d (cuboid.rs:98) and to wo (surface.rs:165) it is -sign(d_k) e_k either way
-            if (dk == 0.0) flags = kSfGeneric;
+            if (dk == 0.0 || !(second > 1e-6 * (1.0 + scale)) || !(e[k] < 1e-9 * (1.0 + scale))) flags = kSfGeneric;
             else flags = (dk > 0.0 ? (kSfNsFlip | kSfNgFlip) : 0u) | ((uint32_t)k << kSfAxisShift);
         }
         L.n = axis_vec((int)((flags >> kSfAxisShift) & 3u));
@@ -786,6 +803,10 @@ __device__ __forceinline__ void lean_surface(const DevScene& S, const Ray64& ray
 }
 
 // ------------------------------------------------------------------ work mapping
+// n / d for the per-launch divisors (samples per pixel, supersampling root, macro tiles per row) as one 64 x 64 -> high 64 multiply:
+// m = ceil(2^64 / d) (DevWork, host side) is exact for every 32-bit n (the error term n (m d - 2^64) / (d 2^64) < 2^-32 <= 1 / d);
+// m == 0 stands for d == 1.  A hardware-less u32 division is ~20 instructions, and these kernels did six to eight per thread.
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, uint64_t m) { return m ? (uint32_t)__umul64hi((uint64_t)n, m) : n; }
 // Slot indices fit 32 bits (run_capture rejects launches of 2^32 samples or more): no 64-bit divisions on this path.
 __device__ __forceinline__ bool slot_to_pixel(const DevWork& W, uint64_t p64, uint32_t& x, uint32_t& y) {
     const uint32_t p = (uint32_t)p64;
@@ -796,8 +817,9 @@ __device__ __forceinline__ bool slot_to_pixel(const DevWork& W, uint64_t p64, ui
         uint32_t micro = q / 32, in = q % 32;
         uint32_t px = (micro % (kMacroTile / kMicroW)) * kMicroW + in % kMicroW;
         uint32_t py = (micro / (kMacroTile / kMicroW)) * kMicroH + in / kMicroW;
-        x = (tile % W.n_macro_x) * kMacroTile + px;
-        y = (tile / W.n_macro_x) * kMacroTile + py;
+        const uint32_t ty = fdiv(tile, W.fd_nmx);
+        x = (tile - ty * W.n_macro_x) * kMacroTile + px;
+        y = ty * kMacroTile + py;
         return x < W.w && y < W.h;
     } else {
         const uint64_t off64 = (uint64_t)W.sub_k + (uint64_t)p * (uint64_t)W.sub_n;   // lib.rs:152-154
@@ -823,7 +845,8 @@ __device__ __forceinline__ Ray64 camera_ray(const DevCamera& C, const DevWork& W
     D3 d = d3(C.view[0], C.view[1], C.view[2]) + (soy * up) + (sox * aux);
     D3 updiff = up * sep, auxdiff = aux * sep;
     D3 halfdiff = updiff * 0.5 + auxdiff * 0.5;
-    double fi = (double)(s / C.root), fj = (double)(s % C.root);
+    const uint32_t si = fdiv(s, W.fd_root);
+    double fi = (double)si, fj = (double)(s - si * C.root);
     r.d = d + (fj * updiff) + (fi * auxdiff) + halfdiff;
     return r;
 }
@@ -860,7 +883,7 @@ __device__ __forceinline__ bool slot_ray(const DevCamera& C, const DevWork& W, u
         x = (uint32_t)g; y = 0; s = 0;
         return true;
     }
-    const uint32_t g32 = (uint32_t)g, p = g32 / W.spp;
+    const uint32_t g32 = (uint32_t)g, p = fdiv(g32, W.fd_spp);
     s = g32 - p * W.spp;
     if (!slot_to_pixel(W, p, x, y)) return false;
     ray = camera_ray(C, W, x, y, s);
@@ -1247,8 +1270,9 @@ __global__ void __launch_bounds__(LGB_LEAFP_THREADS, 1024 / LGB_LEAFP_THREADS) k
     LocalCounters lc = {};
     unsigned int hits = 0, primary = 0;
     bool fallback = false;
-    if (g < total && (uint32_t)g % W.spp != W.anchor) {
-        const uint64_t p = (uint32_t)g / W.spp;
+    const uint32_t pix = fdiv((uint32_t)g, W.fd_spp);
+    if (g < total && (uint32_t)g - pix * W.spp != W.anchor) {
+        const uint64_t p = pix;
         const uint32_t n = V.beam_count[p];
         Ray64 world; uint32_t x, y, s;
         if (!slot_ray(C, W, g, world, x, y, s)) { V.hit_t[g] = CUDART_INF; V.hit_ref[g] = kSlotUnused; }
@@ -1279,8 +1303,8 @@ __global__ void __launch_bounds__(LGB_LEAFP_THREADS, 1024 / LGB_LEAFP_THREADS) k
         }
     } else if (g < total) {                        // centre sample: done by k_beam, unless ...
         uint32_t x, y;
-        if (!slot_to_pixel(W, (uint32_t)g / W.spp, x, y)) { V.hit_t[g] = CUDART_INF; V.hit_ref[g] = kSlotUnused; }      // ... the pixel is outside the film
-        else if (V.beam_count[(uint32_t)g / W.spp] == kBeamOverflow) fallback = true;                                      // ... or its walk was cut short
+        if (!slot_to_pixel(W, pix, x, y)) { V.hit_t[g] = CUDART_INF; V.hit_ref[g] = kSlotUnused; }      // ... the pixel is outside the film
+        else if (V.beam_count[pix] == kBeamOverflow) fallback = true;                                      // ... or its walk was cut short
     }
     block_append(sc, fallback, (uint32_t)g, V.fallback_list, V.fallback_count);
     if (O.counters) {
@@ -1304,6 +1328,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
     bool live = false;
     if (g < total) {
         const uint32_t ref = V.hit_ref[g];
+        const double t_hit = V.hit_t[g];             // (requested together with ref: one round trip to memory instead of two)
         Ray64 ray; uint32_t x, y, s;
         bool ref_done = false;
         if (ref != kSlotUnused && slot_ray<RAYBUF>(C, W, g, ray, x, y, s)) {
@@ -1318,7 +1343,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
             }
             if (ref != LGB_MISS && !ref_done) {
                 live = true;
-                const double t = V.hit_t[g];
+                const double t = t_hit;
                 D3 ng, ps; double wo_ng; uint32_t sflags = kSfGeneric;
                 if (LEAN) {                          // ng = +-n and the reference's sign decisions, no differentials (lean_surface)
                     LeanSurf Ls;
@@ -1364,7 +1389,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
     __shared__ uint32_t qmap[2 * LGB_MAX_LIGHTS];
     if (threadIdx.x < 2 * S.n_lights) qmap[threadIdx.x] = (threadIdx.x >> 1) * 3 + ((threadIdx.x & 1) ? kQueueB : kQueueA);
     __syncthreads();
-    const bool anchor = W.spp == 1 || (uint32_t)g % W.spp == W.anchor;
+    const bool anchor = W.spp == 1 || (uint32_t)g - fdiv((uint32_t)g, W.fd_spp) * W.spp == W.anchor;
     unsigned long long flags = 0;
     if (live) for (uint32_t l = 0; l < S.n_lights; l++) if ((need >> l) & 1u) flags |= 1ull << (2 * l + (anchor ? 0 : 1));
     block_append_multi(sc, 2 * S.n_lights, flags, (uint32_t)g, V.queue, V.queue_stride, V.queue_count, qmap);
@@ -1422,7 +1447,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork 
             if (first + k < total) {
                 g[k] = V.queue[(size_t)(light * 3 + kQueueB) * V.queue_stride + first + k];
                 if (g[k] != kEntryDone) {                                          // (k_swalk has resolved it from the pixel's shadow beam)
-                    oc[k] = V.occluder[(size_t)light * W.n_pixels + g[k] / W.spp];
+                    oc[k] = V.occluder[(size_t)light * W.n_pixels + fdiv(g[k], W.fd_spp)];
                     to_c |= 1u << k;
                 }
             }
@@ -1471,7 +1496,7 @@ __global__ void __launch_bounds__(LGB_SBEAM_THREADS_, 1024 / LGB_SBEAM_THREADS_)
     LocalCounters lc = {};
     if (i < total) {
         const uint32_t ga = V.queue[(size_t)(light * 3 + kQueueC) * V.queue_stride + i];
-        const uint32_t p = ga / W.spp;
+        const uint32_t p = fdiv(ga, W.fd_spp);
         {
         const double* Lp = S.lights + 9 * (size_t)light;
         const D3 lp = d3(Lp[0], Lp[1], Lp[2]);
@@ -1584,7 +1609,7 @@ __global__ void __launch_bounds__(LGB_SWALK_THREADS, 1024 / LGB_SWALK_THREADS) k
     if (i < total) {
         uint32_t* slot = V.queue + (size_t)(light * 3 + kQueueB) * V.queue_stride + i;
         const uint32_t g = *slot;
-        const uint32_t p = g / W.spp;
+        const uint32_t p = fdiv(g, W.fd_spp);
         const uint32_t n = count_in[p];
         if (n != kBeamOverflow) {
             const double* Lp = S.lights + 9 * (size_t)light;
@@ -1650,7 +1675,7 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_shadow(Dev
             const bool done = trav_run<true, STATS, true, INST>(S, world, ray, f, T, stack, nullptr, 1.0, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
             if (done) {
                 if (T.best.ref != LGB_MISS) { atomicOr(&V.occl[g], 1u << light); occluded++; }
-                if (record) V.occluder[(size_t)light * W.n_pixels + g / W.spp] = T.best.ref;
+                if (record) V.occluder[(size_t)light * W.n_pixels + fdiv(g, W.fd_spp)] = T.best.ref;
                 if (record && W.beams && T.best.ref == LGB_MISS) {       // a free anchor: its pixel gets a shadow beam (k_sbeam); listed in queue C's space
                     const unsigned peers = __activemask(), leader = __ffs(peers) - 1;
                     uint32_t base = 0;
@@ -1895,40 +1920,51 @@ __device__ __forceinline__ D3 shade_generic_plastic(const DevScene& S, const Dev
 #ifndef LGB_LEAN_MIN_BLOCKS
 #define LGB_LEAN_MIN_BLOCKS 4
 #endif
+// FUSED (spp <= 256): a block holds whole pixels (thread t: pixel t / spp of the block, sample t % spp); the samples meet in shared
+// memory, one thread per (pixel, channel) sums them in sample order (integrate.rs:16-20) and quantises (img.rs:56-67), one thread per
+// pixel stores the uchar4.
+constexpr int kRadStride = 256 + 16 + 1;           // per channel; index t + t / 16 keeps the per-pixel runs on different banks
 template <bool FUSED>
 __global__ void __launch_bounds__(256, LGB_LEAN_MIN_BLOCKS) k_shade_lean(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
     const double PI = 3.14159265358979323846264338327950288;
-    const uint64_t total = W.n_pixels * W.spp;
-    __shared__ double rad[FUSED ? 256 * 3 : 3];
+    __shared__ double rad[FUSED ? 3 * kRadStride : 3];
     __shared__ unsigned char valid[FUSED ? 256 : 1];
+    __shared__ unsigned char bytes[FUSED ? 256 * 3 : 1];
     uint64_t g;
+    uint32_t p32, s;
     bool mine;
-    if (FUSED) {
-        const uint32_t ppb = blockDim.x / W.spp;                        // pixels per block
-        const uint64_t p = (uint64_t)blockIdx.x * ppb + threadIdx.x / W.spp;
-        mine = threadIdx.x < ppb * W.spp && p < W.n_pixels;
-        g = p * W.spp + threadIdx.x % W.spp;
+    const uint32_t ppb = FUSED ? fdiv(blockDim.x, W.fd_spp) : 0u;   // pixels per block
+    if constexpr (FUSED) {
+        const uint32_t tp = fdiv(threadIdx.x, W.fd_spp);
+        s = threadIdx.x - tp * W.spp;
+        const uint64_t p = (uint64_t)blockIdx.x * ppb + tp;
+        mine = tp < ppb && p < W.n_pixels;
+        p32 = (uint32_t)p;
+        g = p * W.spp + s;
     } else {
         g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        mine = g < total;
+        mine = g < W.n_pixels * W.spp;
+        p32 = fdiv((uint32_t)g, W.fd_spp);
+        s = (uint32_t)g - p32 * W.spp;
     }
     D3 output = d3(0, 0, 0);
     bool have = false, generic = false;
-    uint32_t x = 0, y = 0, s = 0;
+    uint32_t x = 0, y = 0;
     if (mine) {
+        // everything the slot needs from the wave, requested at once (the loads are independent; their latency is this kernel's main stall)
         const uint32_t ref = V.hit_ref[g];
-        Ray64 ray;
-        if (ref != kSlotUnused && slot_ray<false>(C, W, g, ray, x, y, s)) {
+        const double t = V.hit_t[g];
+        const uint32_t occl = V.occl[g], gate = V.gate[g], sflags = V.sflags[g];
+        if (ref != kSlotUnused && slot_to_pixel(W, p32, x, y)) {
+            const Ray64 ray = camera_ray(C, W, x, y, s);
             have = true;
             if (ref == LGB_MISS) {                                       // background.rs:25-34
                 output = background_of(sh, ray.d);
             } else {
-                const uint32_t occl = V.occl[g], sflags = V.sflags[g];
-                const double t = V.hit_t[g];
                 if (O.aov_occl) O.aov_occl[((uint64_t)y * W.w + x) * W.spp + s] = occl;
                 if (sflags & kSfGeneric) generic = true;             // (rare: shaded after the lean code so that their registers do not add up)
                 else {
-                    const uint32_t lit = V.gate[g] & ~occl;              // lights that are neither occluded nor on the far side of ng
+                    const uint32_t lit = gate & ~occl;                   // lights that are neither occluded nor on the far side of ng
                     LeanSurf Ls;
                     lean_surface<false>(S, ray, t, ref, sflags, Ls);
                     LeanHit H;
@@ -1974,24 +2010,36 @@ __global__ void __launch_bounds__(256, LGB_LEAN_MIN_BLOCKS) k_shade_lean(DevScen
     }
 #ifndef LGB_LEAN_NO_GENERIC       // (experiments: the register need of the lean code alone)
     if (generic) {
-        Ray64 ray; uint32_t x2, y2, s2;
-        slot_ray<false>(C, W, g, ray, x2, y2, s2);
+        const Ray64 ray = camera_ray(C, W, x, y, s);
         output = shade_generic_plastic(S, sh, ray, V.hit_t[g], V.hit_ref[g], V.occl[g]);
     }
 #endif
-    if (!FUSED) {
+    if constexpr (!FUSED) {
         if (have) { O.radiance[3 * g + 0] = output.x; O.radiance[3 * g + 1] = output.y; O.radiance[3 * g + 2] = output.z; }
-        return;
+    } else {
+    {
+        const uint32_t at = threadIdx.x + (threadIdx.x >> 4);
+        rad[at] = output.x; rad[kRadStride + at] = output.y; rad[2 * kRadStride + at] = output.z;
+        valid[threadIdx.x] = have ? 1 : 0;
     }
-    rad[3 * threadIdx.x] = output.x; rad[3 * threadIdx.x + 1] = output.y; rad[3 * threadIdx.x + 2] = output.z;
-    valid[threadIdx.x] = have ? 1 : 0;
     __syncthreads();
-    if (mine && threadIdx.x % W.spp == 0 && valid[threadIdx.x]) {        // sample 0 of a pixel inside the film: resolve it
-        D3 c = d3(0, 0, 0);
-        for (uint32_t k = 0; k < W.spp; k++) c = c + d3(rad[3 * (threadIdx.x + k)], rad[3 * (threadIdx.x + k) + 1], rad[3 * (threadIdx.x + k) + 2]);
+    for (uint32_t j = threadIdx.x; j < 3u * ppb; j += blockDim.x) {        // item j: channel j / ppb of pixel j % ppb
+        const uint32_t ch = j >= 2u * ppb ? 2u : (j >= ppb ? 1u : 0u), q = j - ch * ppb, t0 = q * W.spp;
+        if (!valid[t0]) continue;
+        const double* r = rad + ch * kRadStride;
+        double c = 0.0;
+        for (uint32_t k = 0; k < W.spp; k++) c = c + r[t0 + k + ((t0 + k) >> 4)];
         c = c * (1.0 / (double)W.spp);
-        const uint64_t p = (uint32_t)g / W.spp;
-        reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)y * W.w + x] = quantise(c);
+        bytes[3 * q + ch] = (unsigned char)round(fmin(fmax(c, 0.0), 1.0) * 255.0);      // img.rs:56-67
+    }
+    __syncthreads();
+    if (threadIdx.x < ppb && valid[threadIdx.x * W.spp]) {
+        const uint64_t p = (uint64_t)blockIdx.x * ppb + threadIdx.x;
+        uint32_t px, py;
+        slot_to_pixel(W, p, px, py);
+        uchar4 o; o.x = bytes[3 * threadIdx.x]; o.y = bytes[3 * threadIdx.x + 1]; o.z = bytes[3 * threadIdx.x + 2]; o.w = 255;
+        reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)py * W.w + px] = o;
+    }
     }
 }
 
@@ -2123,7 +2171,7 @@ __global__ void __launch_bounds__(256) k_export_li(DevWork W, DevOut O, DevWave 
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= W.n_pixels * W.spp || V.hit_ref[g] == kSlotUnused) return;
     uint32_t x, y;
-    const uint32_t p = (uint32_t)g / W.spp, s = (uint32_t)g - p * W.spp;
+    const uint32_t p = fdiv((uint32_t)g, W.fd_spp), s = (uint32_t)g - p * W.spp;
     if (!slot_to_pixel(W, p, x, y)) return;
     const uint64_t gi = ((uint64_t)y * W.w + x) * W.spp + s;
     O.aov_li[3 * gi] = O.radiance[3 * g]; O.aov_li[3 * gi + 1] = O.radiance[3 * g + 1]; O.aov_li[3 * gi + 2] = O.radiance[3 * g + 2];
@@ -2206,8 +2254,10 @@ bool render_fused(uint32_t spp) { return spp >= 1 && spp <= 256; }      // and !
 // `side` (optional): the shadow chains of the lights are independent of each other (own queues, own fetch counters, own occluder
 // table, one bit each in `occl`), so they are dealt round-robin over the launch stream and the side streams: the blocks of one
 // light's persistent kernel fill the SMs that the tail of another's has left idle.
+#define KL(nm, light, st, ...) do { if (klog) klog->begin(nm, light, st); __VA_ARGS__; if (klog) klog->end(st, O.counters); } while (0)
 cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O,
-                          const DevWave& V, bool stats, bool all_shadows, int sms, cudaStream_t stream, cudaEvent_t* ev, int part, const SideStreams* side) {
+                          const DevWave& V, bool stats, bool all_shadows, int sms, cudaStream_t stream, cudaEvent_t* ev, int part, const SideStreams* side,
+                          KernelLog* klog) {
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], stream); };
     const uint64_t total = W.n_pixels * W.spp;
     const bool cache = W.spp > 1;
@@ -2227,13 +2277,13 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
             // one bundle traversal per pixel, then every sample ray walks its pixel's leaf list; pixels whose bundle
             // reaches too many leaves go through the per-ray traversal (their slots are listed by k_leafp)
             const unsigned bb = (unsigned)((W.n_pixels + LGB_BEAM_THREADS - 1) / LGB_BEAM_THREADS), lb = (unsigned)((total + LGB_LEAFP_THREADS - 1) / LGB_LEAFP_THREADS);
-            if (stats) { k_beam<true><<<bb, LGB_BEAM_THREADS, 0, stream>>>(S, C, W, O, V); k_leafp<true><<<lb, LGB_LEAFP_THREADS, 0, stream>>>(S, C, W, O, V); }
-            else { k_beam<false><<<bb, LGB_BEAM_THREADS, 0, stream>>>(S, C, W, O, V); k_leafp<false><<<lb, LGB_LEAFP_THREADS, 0, stream>>>(S, C, W, O, V); }
+            KL("k_beam", -1, stream, if (stats) k_beam<true><<<bb, LGB_BEAM_THREADS, 0, stream>>>(S, C, W, O, V); else k_beam<false><<<bb, LGB_BEAM_THREADS, 0, stream>>>(S, C, W, O, V));
+            KL("k_leafp", -1, stream, if (stats) k_leafp<true><<<lb, LGB_LEAFP_THREADS, 0, stream>>>(S, C, W, O, V); else k_leafp<false><<<lb, LGB_LEAFP_THREADS, 0, stream>>>(S, C, W, O, V));
             DevWork Wf = W; Wf.slot_list = V.fallback_list; Wf.n_list = 0; Wf.n_list_dev = V.fallback_count;
-            if (stats) k_primary<true, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, Wf, O, V); else k_primary<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, Wf, O, V);
+            KL("k_primary(fallback)", -1, stream, if (stats) k_primary<true, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, Wf, O, V); else k_primary<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, Wf, O, V));
         } else if (pb) {
-            if (inst) { if (stats) k_primary<true, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); }
-            else { if (stats) k_primary<true, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); }
+            if (inst) KL("k_primary", -1, stream, if (stats) k_primary<true, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V));
+            else KL("k_primary", -1, stream, if (stats) k_primary<true, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V));
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -2241,8 +2291,8 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     if (total == 0) return cudaSuccess;
     mark(1);
     const unsigned blocks = (unsigned)((total + 255) / 256), ablocks = (unsigned)((total + kAppendThreads - 1) / kAppendThreads);
-    if (inst) { if (all_shadows) k_setup<true, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); }
-    else { if (all_shadows) k_setup<true, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); }
+    if (inst) KL("k_setup", -1, stream, if (all_shadows) k_setup<true, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V));
+    else KL("k_setup", -1, stream, if (all_shadows) k_setup<true, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V));
     mark(2);
     // per light: anchor rays (queue A), then the cached-occluder test of the rest (B -> C), then the survivors (queue C)
     const int nside = (side && S.n_lights > 1) ? std::min<int>(side->n, (int)S.n_lights - 1) : 0;
@@ -2259,15 +2309,16 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
                 if (sbeams) {                       // pixels whose anchor ray is free: one bundle walk, then the other samples from its list, no traversal
                     if ((e = cudaMemsetAsync(bcount, 0xFF, (size_t)W.n_pixels * 4, ls)) != cudaSuccess) return e;
                     const unsigned bb = (unsigned)((W.n_pixels + LGB_SBEAM_THREADS_ - 1) / LGB_SBEAM_THREADS_);
-                    if (stats) k_sbeam<true><<<bb, LGB_SBEAM_THREADS_, 0, ls>>>(S, W, O, V, l, blist, bcount); else k_sbeam<false><<<bb, LGB_SBEAM_THREADS_, 0, ls>>>(S, W, O, V, l, blist, bcount);
+                    KL("k_sbeam", (int)l, ls, if (stats) k_sbeam<true><<<bb, LGB_SBEAM_THREADS_, 0, ls>>>(S, W, O, V, l, blist, bcount); else k_sbeam<false><<<bb, LGB_SBEAM_THREADS_, 0, ls>>>(S, W, O, V, l, blist, bcount));
                     const unsigned wb = (unsigned)((total + LGB_SWALK_THREADS - 1) / LGB_SWALK_THREADS);
-                    if (stats) k_swalk<true><<<wb, LGB_SWALK_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount); else k_swalk<false><<<wb, LGB_SWALK_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount);
+                    KL("k_swalk", (int)l, ls, if (stats) k_swalk<true><<<wb, LGB_SWALK_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount); else k_swalk<false><<<wb, LGB_SWALK_THREADS, 0, ls>>>(S, W, O, V, l, blist, bcount));
                 }
                 const unsigned tb = (unsigned)std::min<uint64_t>(ablocks, (uint64_t)sms * 4);
-                if (inst) k_pretest<true><<<tb, kAppendThreads, 0, ls>>>(S, W, O, V, l); else k_pretest<false><<<tb, kAppendThreads, 0, ls>>>(S, W, O, V, l);
+                KL("k_pretest", (int)l, ls, if (inst) k_pretest<true><<<tb, kAppendThreads, 0, ls>>>(S, W, O, V, l); else k_pretest<false><<<tb, kAppendThreads, 0, ls>>>(S, W, O, V, l));
             }
-            if (inst) { if (stats) k_shadow<true, true><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); else k_shadow<false, true><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); }
-            else { if (stats) k_shadow<true, false><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); else k_shadow<false, false><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); }
+            const char* sname = which == kQueueA ? "k_shadow(anchors)" : "k_shadow(rest)";
+            if (inst) KL(sname, (int)l, ls, if (stats) k_shadow<true, true><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); else k_shadow<false, true><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which));
+            else KL(sname, (int)l, ls, if (stats) k_shadow<true, false><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); else k_shadow<false, false><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which));
             if (which == kQueueA && l == 0) mark(3);      // (the anchor / rest split of the first light only)
         }
     }
@@ -2275,30 +2326,31 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     for (int k = 0; k < nside; k++) { cudaEventRecord(side->join[k], side->s[k]); cudaStreamWaitEvent(stream, side->join[k], 0); }
     mark(4);
     if (S.general) {                    // materials beyond plastic: every BSDF in k_shade, then the specular ray trees, then the film
-        if (inst) k_shade<true, false, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, false, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+        KL("k_shade(general)", -1, stream, if (inst) k_shade<true, false, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade<false, false, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V));
         if (part & 4) return cudaGetLastError();      // the caller runs the levels of the ray trees (launch_level / launch_spawn / launch_gather) and the resolve
         if (S.specular && S.recursion > 0) {
             const unsigned sb = (unsigned)((total + LGB_SEC_THREADS - 1) / LGB_SEC_THREADS);
-            if (inst) k_secondary<true><<<sb, LGB_SEC_THREADS, 0, stream>>>(S, C, sh, W, O, V); else k_secondary<false><<<sb, LGB_SEC_THREADS, 0, stream>>>(S, C, sh, W, O, V);
+            KL("k_secondary", -1, stream, if (inst) k_secondary<true><<<sb, LGB_SEC_THREADS, 0, stream>>>(S, C, sh, W, O, V); else k_secondary<false><<<sb, LGB_SEC_THREADS, 0, stream>>>(S, C, sh, W, O, V));
         }
         mark(5);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
+        KL("k_resolve", -1, stream, k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O));
     } else if (render_fused(W.spp) && !O.aov_li) {   // whole pixels per block: shade and resolve in one kernel, no radiance buffer
         const unsigned ft = W.spp <= LGB_FUSED_THREADS ? LGB_FUSED_THREADS : 256u;        // threads per block: whole pixels, as few of them as the option allows
         const unsigned fb = (unsigned)((W.n_pixels + (ft / W.spp) - 1) / (ft / W.spp));
-        if (inst) k_shade<true, true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V); else k_shade_lean<true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V);
+        KL(inst ? "k_shade(+film)" : "k_shade_lean(+film)", -1, stream, if (inst) k_shade<true, true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V); else k_shade_lean<true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V));
         mark(5);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     } else {
-        if (inst) k_shade<true, false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade_lean<false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
+        KL(inst ? "k_shade" : "k_shade_lean", -1, stream, if (inst) k_shade<true, false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V); else k_shade_lean<false><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V));
         mark(5);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O);
+        KL("k_resolve", -1, stream, k_resolve<<<(unsigned)((W.n_pixels + 255) / 256), 256, 0, stream>>>(W, O));
     }
     mark(6);
     return cudaGetLastError();
 }
+#undef KL
 // One level of the specular ray trees: W.mode == 3, the rays in W.rays; radiance of every ray into O.radiance, specular hits into V.sec_list.
 cudaError_t launch_level(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O, const DevWave& V, int sms, cudaStream_t stream) {
     const uint64_t total = W.n_pixels;

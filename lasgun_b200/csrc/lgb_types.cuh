@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "../../include/lasgun_b200.h"
 
@@ -98,6 +99,7 @@ struct DevWork {
     uint32_t sub_k, sub_n;
     uint64_t n_pixels;               // pixel slots in this launch
     uint32_t spp;
+    uint64_t fd_spp, fd_root, fd_nmx; // ceil(2^64 / d) for d = spp, the supersampling root, n_macro_x (0: d == 1): fdiv(), lgb_kernels.cu
     uint32_t anchor;                 // sample index of the pixel's anchor shadow ray (centre of the sample grid)
     const uint32_t* slot_list;       // k_primary: trace only these sample slots (re-trace of unresolved exact-t ties) ...
     uint64_t n_list;                 // ... this many of them ...
@@ -130,6 +132,28 @@ struct DevCounters {
     unsigned long long secondary_rays;                          // rays k_secondary traced
     unsigned int stack_overflow;
     unsigned int pad;
+};
+
+// lgb_capture_profile: CUDA events around every kernel launch of one frame (all on ONE stream for that call, so a launch's
+// duration is its own) and a snapshot of the work counters behind each, so that every launch's share of them is known.  Host-side only.
+struct KernelLog {
+    static constexpr int kMax = 64;
+    char name[kMax][40];
+    cudaEvent_t ev0[kMax], ev1[kMax];
+    int n = 0, made = 0;
+    DevCounters* snaps = nullptr;        // device, kMax entries: the counters as they stand after launch i
+    void begin(const char* nm, int light, cudaStream_t s) {
+        if (n >= kMax) return;
+        if (n >= made) { cudaEventCreate(&ev0[n]); cudaEventCreate(&ev1[n]); made = n + 1; }
+        if (light >= 0) snprintf(name[n], sizeof name[n], "%s[light %d]", nm, light); else snprintf(name[n], sizeof name[n], "%s", nm);
+        cudaEventRecord(ev0[n], s);
+    }
+    void end(cudaStream_t s, const DevCounters* ctr) {
+        if (n >= kMax) return;
+        cudaEventRecord(ev1[n], s);
+        if (snaps && ctr) cudaMemcpyAsync(snaps + n, ctr, sizeof(DevCounters), cudaMemcpyDeviceToDevice, s);
+        n++;
+    }
 };
 
 // Side streams for the per-light shadow chains (launch_render); host-side only.
