@@ -6,11 +6,16 @@
 A step is one full frame of the workload (default: BASELINE.json's config 5, `mixed4k`, 3840x2160 at
 16 spp — the config the 1/2/4/8-GPU metric is quoted on; it fits one GPU).  Rays are counted with the
 reference's semantics: primary = w*h*spp, shadow = lights * primary hits (integrate.rs:47-50).
-  value  scene + BVH resident in HBM, frame rendered into a device film (rank 0 after the NVLink gather)
-  e2e    `capture(scene, film)` as the reference defines it (lib.rs:55-104), with HOST buffers, every step:
-         flatten of the host scene (the reference's own HLBVH build is deferred: the device asks for it only when
-         a ray meets two primitives at bit-identical t, which this workload never does), lgb_scene_create (device
-         BVH build, H2D of the scene), lgb_capture (render + D2H of the film), lgb_scene_destroy
+  value  scene, BVH, light grids and camera grid resident in HBM, frame rendered into a device film (rank 0's after the NVLink
+         stores of the other ranks); CUDA events around exactly K frames, max over ranks
+  e2e    `capture(scene, film)` as the reference defines it (lib.rs:55-104), with HOST buffers, every step: flatten of the host
+         scene (the reference's own HLBVH build is deferred: the device asks for it only when a ray meets two primitives at
+         bit-identical t), lgb_scene_create (device BVH + light grids, H2D of the scene), lgb_capture (camera grid, render, D2H of
+         the film into PAGEABLE memory, as a reference-side `Film` is), lgb_scene_destroy
+  roofline  per kernel, largest first, from lgb_capture_profile (CUDA events around every launch, live, in this process):
+         ops = the launch's own unit counts (node / primitive tests, rays, hits, light evaluations: the library's work counters)
+         x SURVEY 8d's constants of record; peak = SM count x observed SM clock x lanes x 2 (128 lanes for the FP32 kernels, 64
+         for the FP64 shading kernels); no microbenchmark in any denominator.
 --impl reference times the CPU oracle (C++ restatement of the reference algorithm — the Rust build
 cannot be compiled here) on all host threads over a bounded sample of the same frame.
 """
@@ -18,6 +23,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import statistics
@@ -37,6 +43,8 @@ METRIC = "Mrays/s (primary+shadow)"
 OPS = {"node": 26, "sphere": (26, 39), "tri": (47, 68), "cuboid": 31, "camera": 30, "hit": 110, "light": 25 + 120, "ambient": 120,
        "background": 15, "film": 12}
 BYTES = {"node": 32, "sphere": 16, "tri": 48, "cuboid": 32, "ref": 4, "film": 4}
+FP64_KERNELS = ("k_setup", "k_shade")          # f64 reference arithmetic end to end: measured against the DFMA issue rate
+OTHER_CONFIGS = ("simple", "mesh1m", "cornell", "spheres1m")
 
 
 def load_peaks():
@@ -46,6 +54,16 @@ def load_peaks():
         return {"hbm_gbs": float(p["hbm_gbs"]), "sm_max_mhz": float(p.get("sm_max_mhz", 1965.0)), "source": "measured (MEASURED_PEAKS.json)"}
     except Exception:
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def kernel_source_hash():
+    """Hash of the CUDA sources the shipped library is built from: an ncu capture is only quoted if it was taken from the same code."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "lasgun_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -97,7 +115,7 @@ def workload(name, args):
 def reference_sample(osc, w, h, threads, target_s, spp, n_lights):
     """Bounded sample of the frame on the CPU oracle: capture_subset(k, n) for k < threads."""
     probe_n = max(threads, (w * h) // (threads * 64))
-    t0 = time.time(); r = osc.capture(w, h, threads=threads, counters=True, subset=(probe_n, 0, threads)); dt = max(time.time() - t0, 1e-4)
+    t0 = time.time(); osc.capture(w, h, threads=threads, counters=True, subset=(probe_n, 0, threads)); dt = max(time.time() - t0, 1e-4)
     pixels = threads * ((w * h + probe_n - 1) // probe_n)
     rate = pixels / dt
     want_pixels = min(w * h, max(pixels, int(rate * target_s)))
@@ -138,43 +156,97 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def traversal_work(node_fetches, f, e):
-    """Algorithmic FP32 ops and bytes of BVH traversal (SURVEY §8d): one node fetch = two slab tests of 26 ops / 32 B each;
-    f / e = primitive tests started / carried to the hit path, per type (sphere, cuboid, triangle)."""
-    ops = 2 * node_fetches * OPS["node"]
+def traversal_ops(k):
+    """FP32 ops of the node and primitive tests one launch executed: a node fetch tests two child boxes (26 ops each); a
+    primitive test that stops at the filter counts the reject path, one that runs the exact test the hit path."""
+    f, e = k["filter_tests"], k["exact_tests"]
+    ops = 2 * k["node_tests"] * OPS["node"]
     ops += (f[0] - e[0]) * OPS["sphere"][0] + e[0] * OPS["sphere"][1]
     ops += f[1] * OPS["cuboid"]
     ops += (f[2] - e[2]) * OPS["tri"][0] + e[2] * OPS["tri"][1]
-    byts = 2 * node_fetches * BYTES["node"] + f[0] * BYTES["sphere"] + f[1] * BYTES["cuboid"] + f[2] * BYTES["tri"]
+    byts = 2 * k["node_tests"] * BYTES["node"] + f[0] * BYTES["sphere"] + f[1] * BYTES["cuboid"] + f[2] * BYTES["tri"]
     return ops, byts
 
 
-def algorithmic_work(st, w, h, spp, n_lights):
-    """Algorithmic FP32 ops and bytes of one frame from the device's own work counters."""
-    ops, byts = traversal_work(st["node_tests"], st["filter_tests"], st["exact_tests"])
-    hits, prim = st["primary_hits"], st["primary_rays"]
-    ops += prim * OPS["camera"] + hits * OPS["hit"] + st["shadow_rays_traced"] * OPS["light"] + hits * OPS["ambient"]
-    ops += (prim - hits) * OPS["background"] + w * h * OPS["film"]
-    byts += w * h * BYTES["film"]
-    return ops, byts
+def kernel_table(timed, counted, frame, w, h, nl, sm_count, clock_mhz, traffic):
+    """One row per launch of the frame: its own duration (events around it) and the SURVEY-8d ops of the units it processed."""
+    fp32_peak = sm_count * clock_mhz * 1e6 * 128 * 2 / 1e9       # Gop/s, FMA = 2
+    fp64_peak = sm_count * clock_mhz * 1e6 * 64 * 2 / 1e9
+    hits, prim = frame["primary_hits"], frame["primary_rays"]
+    rows = []
+    for t, c in zip(timed, counted):
+        name = t["name"]
+        ops, byts = traversal_ops(c)
+        units = {}
+        if name.startswith(("k_primary", "k_leafp", "k_beam", "k_cprimary")):
+            ops += c["primary_rays"] * OPS["camera"]; units["camera_rays"] = c["primary_rays"]
+        if name.startswith("k_setup"):
+            ops += hits * OPS["hit"]; units["hits"] = hits
+        if name.startswith("k_shade"):
+            # one light evaluation (setup 25 + plastic BSDF 120) per unoccluded light that can contribute, the ambient evaluation per
+            # hit, the background per miss, quantise + store per pixel
+            evals = frame["shadow_rays_traced"] - frame["shadow_occluded"]
+            ops += evals * OPS["light"] + hits * OPS["ambient"] + (prim - hits) * OPS["background"] + w * h * OPS["film"]
+            byts += w * h * BYTES["film"]
+            units.update(light_evaluations=evals, hits=hits, pixels=w * h)
+        fp64 = name.startswith(FP64_KERNELS)
+        peak = fp64_peak if fp64 else fp32_peak
+        ach = ops / (t["ms"] * 1e-3) / 1e9 if t["ms"] > 0 else 0.0
+        row = {"kernel": name, "launch_ms": t["ms"], "ops_per_launch": ops, "bytes_per_launch": byts, "achieved_gops": ach,
+               "bound": "fp64_issue" if fp64 else "fp32_issue", "peak_gops": peak, "frac": ach / peak,
+               "node_tests": c["node_tests"], "filter_tests": c["filter_tests"], "exact_tests": c["exact_tests"], **units}
+        key = name.split("[")[0].split("(")[0]
+        if traffic and key in traffic:
+            row["traffic"] = traffic[key]
+        rows.append(row)
+    return rows, fp32_peak, fp64_peak
 
 
-def primary_kernel_work(st):
-    """The dominant kernel (k_primary: camera ray + closest-hit traversal of every sample)."""
-    ops, byts = traversal_work(st["primary_node_tests"], st["primary_filter_tests"], st["primary_exact_tests"])
-    return ops + st["primary_rays"] * OPS["camera"], byts
-
-
-def ncu_traffic(workload, world):
-    """dram read + write bytes of the primary-ray phase of one frame (k_beam + k_leafp + k_primary fallback) from the committed
-    `ncu --set full` capture (or None)."""
+def ncu_traffic(workload):
+    """dram read + write bytes per launch, per kernel, from the committed `ncu --set full` capture of THIS source (else None)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)
-        e = t.get(workload)
-        return (e["primary_phase_dram_bytes"] / world) if e and world == 1 else None
+        if t.get("source_hash") != kernel_source_hash():
+            return None, "profiles/ncu_traffic.json was captured from other kernel sources (hash %s, built %s): not quoted" % (t.get("source_hash"), kernel_source_hash())
+        return t.get(workload), "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/%s)" % t.get("capture", "?")
     except Exception:
-        return None
+        return None, "no profiles/ncu_traffic.json"
+
+
+def quick_config(N, ctx, name, args, film_cache):
+    """A short measurement of one of the other BASELINE configs: kernel-only ms/frame (median of a few frames), e2e of one capture
+    through the C ABI with host buffers, and the dominant kernel's roofline fraction."""
+    import torch
+    sc, (w, h) = scenes.CONFIGS[name]()
+    spp, nl = sc.camera.num_samples(), len(sc.lights)
+    host = N.HostScene(sc)
+    dev = N.DeviceScene(ctx, N.FlatScene(host))
+    film = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        st = dev.capture_device(w, h, film.data_ptr(), want_stats=True)
+    ms = statistics.median(dev.capture_device(w, h, film.data_ptr(), want_stats=True)["render_ms"] for _ in range(7))
+    rays = st["primary_rays"] + nl * st["primary_hits"]
+    timed, _ = dev.capture_profile(w, h, film.data_ptr())
+    ctx.set_count_work(True)
+    counted, stc = dev.capture_profile(w, h, film.data_ptr())
+    ctx.set_count_work(False)
+    dev.destroy()
+    L = N.lib()
+    host_film = np.zeros((h, w, 4), dtype=np.uint8)
+    e2e = []
+    for i in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        flat = N.FlatScene(host, lazy=True)
+        hs = C.c_void_p()
+        ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat.desc), C.byref(hs)))
+        ctx.check(L.lgb_capture(ctx.h, hs, w, h, host_film.ctypes.data_as(C.POINTER(C.c_uint8)), None))
+        L.lgb_scene_destroy(hs)
+        e2e.append((time.perf_counter() - t0) * 1e3)
+    return {"film": [w, h], "spp": spp, "lights": nl, "rays_per_frame": rays, "kernel_ms_per_frame": ms, "value": rays / (ms * 1e-3) / 1e6,
+            "e2e_ms_per_frame": statistics.median(e2e[1:]), "e2e_value": rays / (statistics.median(e2e[1:]) * 1e-3) / 1e6,
+            "timed": timed, "counted": counted, "frame": stc}
 
 
 def run_gpu(args):
@@ -188,9 +260,8 @@ def run_gpu(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))      # (NCCL_DEBUG is left as the driver set it; its log goes to stderr)
     ctx = N.Context(local)
     if os.environ.get("LGB_SIDE") == "0":              # experiments: the shadow chains of the lights on one stream
         ctx.set_side_streams(False)
@@ -216,29 +287,13 @@ def run_gpu(args):
     def step():
         multi.capture_distributed(dev, w, h, film, rank, world, stream, shared=shared)
 
-    # one counted frame: ray counts + work counters (not timed).  The algorithmic work of SURVEY 8d is the PER-RAY walk of the
-    # device BVH, so it is counted with the pixel beams off; the timed frames (beams automatic) share the interior-node tests
-    # of a pixel's rays and execute fewer (roofline.executed_ops_per_launch).
-    ctx.set_count_work(True)
-    ctx.set_beams(0)
+    # one counted frame (not timed): ray counts of the frame, summed over ranks
     st = dev.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream, want_stats=True)
-    ctx.set_beams(-1)
-    st_exec = dev.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream, want_stats=True)
-    ctx.set_count_work(False)
-    cnt_e = torch.tensor([st_exec["primary_rays"], st_exec["primary_node_tests"]] + st_exec["primary_filter_tests"] + st_exec["primary_exact_tests"], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(cnt_e)
-    te = cnt_e.tolist()
-    frame_exec = {"primary_rays": te[0], "primary_node_tests": te[1], "primary_filter_tests": te[2:5], "primary_exact_tests": te[5:8]}
-    cnt = torch.tensor([st["primary_rays"], st["primary_hits"], st["shadow_rays_traced"], st["node_tests"]] + st["filter_tests"] + st["exact_tests"]
-                       + [st["primary_node_tests"]] + st["primary_filter_tests"] + st["primary_exact_tests"] + [st["shadow_cache_hits"]],
-                       dtype=torch.int64, device="cuda")
+    cnt = torch.tensor([st["primary_rays"], st["primary_hits"], st["shadow_rays_traced"], st["shadow_occluded"]], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(cnt)
     tot = cnt.tolist()
-    frame = {"primary_rays": tot[0], "primary_hits": tot[1], "shadow_rays_traced": tot[2], "node_tests": tot[3],
-             "filter_tests": tot[4:7], "exact_tests": tot[7:10], "primary_node_tests": tot[10], "primary_filter_tests": tot[11:14],
-             "primary_exact_tests": tot[14:17], "shadow_cache_hits": tot[17]}
+    frame = {"primary_rays": tot[0], "primary_hits": tot[1], "shadow_rays_traced": tot[2], "shadow_occluded": tot[3]}
     rays_frame = frame["primary_rays"] + nl * frame["primary_hits"]
 
     for _ in range(args.warmup):
@@ -248,7 +303,6 @@ def run_gpu(args):
         dist.barrier()
     sampler = ClockSampler(local); sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    kern_ms = []
     torch.cuda.synchronize()
     ev[0].record()
     for _ in range(args.steps):
@@ -264,83 +318,96 @@ def run_gpu(args):
     ms_per_step = float(total_ms.item()) / args.steps
     value = rays_frame / (ms_per_step * 1e-3) / 1e6
 
-    gather_same = None
-    if shared is not None:                       # not timed: the peer-stored film against the NCCL-gathered one, every byte
-        multi.capture_distributed(dev, w, h, film, rank, world, stream)
-        torch.cuda.synchronize()
+    gather_same, same_as_one_gpu = None, None
+    if world > 1:
+        # not timed: the film of this N-GPU frame against (a) the NCCL-gathered film of the same ranks and (b) the film ONE GPU renders
+        out = multi.capture_distributed(dev, w, h, film, rank, world, stream, shared=shared)
+        frame_n = out.clone() if rank == 0 else None
+        if shared is not None:
+            multi.capture_distributed(dev, w, h, film, rank, world, stream)
+            torch.cuda.synchronize()
+            if rank == 0:
+                gather_same = bool(torch.equal(film, frame_n))
         if rank == 0:
-            gather_same = bool(torch.equal(film, shared.tensor))
+            one = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+            dev.capture_device(w, h, one.data_ptr(), rank=0, ranks=1, stream=stream)
+            torch.cuda.synchronize()
+            same_as_one_gpu = bool(torch.equal(one, frame_n))
+        dist.barrier()
 
-    # render-kernel time alone (CUDA events inside the library, on its launch stream), a few frames
-    phase_ms = []
-    for _ in range(max(3, args.steps)):
-        s2 = dev.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream, want_stats=True)
-        kern_ms.append(s2["render_ms"]); phase_ms.append(s2["kernel_ms"])
-    kms = torch.tensor([statistics.median(kern_ms)] + [sum(p[i] for p in phase_ms) / len(phase_ms) for i in range(6)], device="cuda")
+    # per-kernel: events around every launch of this rank's share of the frame (one stream), best of a few frames; a second
+    # pass with the work counters on gives every launch's unit counts
+    timed = None
+    for _ in range(3):
+        k, stp = dev.capture_profile(w, h, film.data_ptr()) if world == 1 else (None, None)
+        if k is not None and (timed is None or sum(x["ms"] for x in k) < sum(x["ms"] for x in timed)):
+            timed = k
+    counted = None
+    if world == 1:
+        ctx.set_count_work(True)
+        counted, _ = dev.capture_profile(w, h, film.data_ptr())
+        ctx.set_count_work(False)
+    kern_ms = [dev.capture_device(w, h, film.data_ptr(), rank=rank, ranks=world, stream=stream, want_stats=True) for _ in range(max(3, args.steps))]
+    kms = torch.tensor([statistics.median(s["render_ms"] for s in kern_ms)], device="cuda")
     if world > 1:
         dist.all_reduce(kms, op=dist.ReduceOp.MAX)
     kernel_ms = float(kms[0].item())
-    phases = [float(v) for v in kms[1:].tolist()]      # average launch duration per phase, CUDA events on the launch stream
+    s2 = kern_ms[-1]
 
-    # e2e through the C ABI with host buffers (rank-local frame share; film gathered on the host side of rank 0)
-    host_film_t = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()       # the caller's film: pinned host memory
-    host_film = host_film_t.numpy()
-    e2e_ms, e2e_parts = [], []
+    # e2e through the C ABI with host buffers (rank-local frame share; film gathered on the host side of rank 0).
+    # The caller's film is PAGEABLE host memory, as the reference's Film (a Vec<[u8; 4]>) is; the pinned variant is reported beside it.
+    host_film = np.zeros((h, w, 4), dtype=np.uint8)
+    host_film_pinned_t = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
+    e2e_ms, e2e_parts, e2e_pinned = [], [], []
     L = N.lib()
-    for i in range(args.e2e_steps + 1):
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        if world == 1:
-            flat_i = N.FlatScene(hscene_host, lazy=True)   # Accel::from minus the reference BVH build: that runs (callback) only if a ray meets an exact-t tie
-            t1 = time.perf_counter()
-            hscene = C.c_void_p()
-            ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat_i.desc), C.byref(hscene)))
-            t2 = time.perf_counter()
-            ctx.check(L.lgb_capture(ctx.h, hscene, w, h, host_film.ctypes.data_as(C.POINTER(C.c_uint8)), None))
-            L.lgb_scene_destroy(hscene)
-        else:
-            # the BVHs are built once, on rank 0, and the device arena is broadcast over NVLink (multi.replicate_scene)
-            tf = [t0]
-            def build_flat():
-                f = N.FlatScene(hscene_host); tf[0] = time.perf_counter(); return f
-            dev_i = multi.replicate_scene(ctx, build_flat, rank, world, N)
-            t1 = tf[0]; t2 = time.perf_counter()
-            out = multi.capture_distributed(dev_i, w, h, film, rank, world, stream, shared=shared)
-            if rank == 0:
-                host_film_t.copy_(out, non_blocking=True)
+    flat_i = None
+    for variant in ("pageable", "pinned"):
+        target = host_film if variant == "pageable" else host_film_pinned_t.numpy()
+        for i in range(args.e2e_steps + 1):
             torch.cuda.synchronize()
-            dev_i.destroy()
-        t3 = time.perf_counter()
-        e2e_parts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
-        dt = torch.tensor([(t3 - t0) * 1e3], device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        if i > 0:
-            e2e_ms.append(float(dt.item()))
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            if world == 1:
+                flat_i = N.FlatScene(hscene_host, lazy=True)   # Accel::from minus the reference BVH build: that runs (callback) only if a ray meets an exact-t tie
+                t1 = time.perf_counter()
+                hscene = C.c_void_p()
+                ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat_i.desc), C.byref(hscene)))
+                t2 = time.perf_counter()
+                ctx.check(L.lgb_capture(ctx.h, hscene, w, h, target.ctypes.data_as(C.POINTER(C.c_uint8)), None))
+                L.lgb_scene_destroy(hscene)
+            else:
+                # the BVHs are built once, on rank 0, and the device arena is broadcast over NVLink (multi.replicate_scene)
+                tf = [t0]
+
+                def build_flat():
+                    f = N.FlatScene(hscene_host); tf[0] = time.perf_counter(); return f
+                dev_i = multi.replicate_scene(ctx, build_flat, rank, world, N)
+                t1 = tf[0]; t2 = time.perf_counter()
+                out = multi.capture_distributed(dev_i, w, h, film, rank, world, stream, shared=shared)
+                if rank == 0:
+                    torch.from_numpy(target).copy_(out, non_blocking=(variant == "pinned"))
+                torch.cuda.synchronize()
+                dev_i.destroy()
+            t3 = time.perf_counter()
+            dt = torch.tensor([(t3 - t0) * 1e3], device="cuda")
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            if i > 0:
+                (e2e_ms if variant == "pageable" else e2e_pinned).append(float(dt.item()))
+                if variant == "pageable":
+                    e2e_parts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
     e2e = statistics.median(e2e_ms)
     scene_bytes = int(dev.device_bytes)
-    d_ = flat.desc                                   # what lgb_scene_create copies to the device: the caller's arrays + rank tables
-    h2d_bytes = int(d_.n_spheres * 40 + d_.n_cuboids * 56 + d_.n_triangles * (44 + (36 if d_.tri_normals else 0))
-                    + 8 * 4 * (d_.n_spheres + d_.n_cuboids + d_.n_triangles + 1))
+    d_ = flat.desc                                   # what lgb_scene_create copies to the device: the caller's arrays (+ rank tables when the tree is given)
+    h2d_bytes = int(d_.n_spheres * 40 + d_.n_cuboids * 56 + d_.n_triangles * (44 + (36 if d_.tri_normals else 0)))
+    if world > 1:
+        h2d_bytes += 8 * 4 * int(d_.n_spheres + d_.n_cuboids + d_.n_triangles + 1)
 
     if rank == 0:
         peaks = load_peaks()
-        ceil = ctx.measure()
-        ops, byts = algorithmic_work(frame, w, h, spp, nl)
-        fp32_peak = 2.0 * ceil["fp32_ffma_glanes"]                 # Gop/s with FMA = 2, measured live on this GPU
-        ach = ops / (kernel_ms * 1e-3) / 1e9 / world                # per GPU, whole frame
-        p_ops, p_bytes = primary_kernel_work(frame)
-        e_ops, e_bytes = primary_kernel_work(frame_exec)
-        sh_ops, sh_bytes = traversal_work(frame["node_tests"] - frame["primary_node_tests"],
-                                          [a - b for a, b in zip(frame["filter_tests"], frame["primary_filter_tests"])],
-                                          [a - b for a, b in zip(frame["exact_tests"], frame["primary_exact_tests"])])
-        sh_ms = phases[2] + phases[3]
-        l1_peak = 128.0 * torch.cuda.get_device_properties(local).multi_processor_count * float(clocks["sm_mhz"] or peaks["sm_max_mhz"]) * 1e6 / 1e9
-        p_ach = p_ops / (phases[0] * 1e-3) / 1e9 / world           # dominant kernel alone
-        l2_ach = byts / (kernel_ms * 1e-3) / 1e9 / world
-        hbm_bytes = scene_bytes + frame["primary_rays"] * 48 / world + w * h * 4
+        sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+        clock = float(clocks["sm_mhz"] or peaks["sm_max_mhz"])
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -348,40 +415,43 @@ def run_gpu(args):
             "config": {"workload": args.workload, "film": [w, h], "spp": spp, "lights": nl, "triangles": int(flat.desc.n_triangles),
                        "spheres": int(flat.desc.n_spheres), "cuboids": int(flat.desc.n_cuboids), "bvh_nodes": int(flat.desc.n_nodes),
                        "device_bvh_nodes": int(dev.node_count) if hasattr(dev, "node_count") else None, "parallelism": f"tiles{world}",
-                       "film_gather": None if world == 1 else ("peer stores into rank 0's film (CUDA IPC over NVLink), identical to the NCCL-reduced film: %s" % gather_same
-                                                               if shared is not None else "NCCL reduce(SUM) of disjoint tiles"),
-                       "l2_policy": "per-frame working set (radiance buffer %.0f MB + scene %.0f MB) exceeds the 126 MB L2" % (frame["primary_rays"] * 24 / 1e6 / world, scene_bytes / 1e6)},
+                       "film_gather": None if world == 1 else {
+                           "how": "peer stores into rank 0's film (CUDA IPC over NVLink)" if shared is not None else "NCCL reduce(SUM) of disjoint tiles",
+                           "identical_to_nccl_gather": gather_same, "identical_to_one_gpu": same_as_one_gpu},
+                       "l2_policy": "per-frame working set (wavefront buffers %.0f MB + scene %.0f MB) exceeds the 126 MB L2" % (frame["primary_rays"] * 57 / 1e6 / world, scene_bytes / 1e6)},
             "ms_per_frame": ms_per_step, "kernel_ms_per_frame": kernel_ms, "rays_per_frame": rays_frame,
             "rays_traced_per_frame": frame["primary_rays"] + frame["shadow_rays_traced"],
             "e2e": {"value": rays_frame / (e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": w * h * 4,
-                    "reference_tree_built": bool(world > 1 or flat_i.tree_built),
-                    "parts_ms": dict(zip(("flatten", "scene_create_device_bvh_upload", "render_readback_destroy"),
-                                         [statistics.median(p[i] for p in e2e_parts[1:]) for i in range(3)]))},
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": w * h * 4, "film_memory": "pageable",
+                    "ms_per_frame_pinned_film": statistics.median(e2e_pinned),
+                    "reference_tree_built": bool(world > 1 or (flat_i is not None and flat_i.tree_built)),
+                    "parts_ms": dict(zip(("flatten", "scene_create_device_bvh_grids_upload", "camera_grid_render_readback_destroy"),
+                                         [statistics.median(p[i] for p in e2e_parts) for i in range(3)]))},
             "gpu_launches": int(s2["kernel_launches"]) * args.steps,
-            "roofline": {"kernel": ("primary-ray phase (k_beam bundle traversal + k_leafp leaf walk + k_primary fallback)" if s2["beams"] else
-                                    "k_primary (camera rays + closest-hit traversal)") + ", %.1f%% of the frame" % (100.0 * phases[0] / max(sum(phases), 1e-9)),
-                         "bound": "fp32_issue", "achieved": p_ach, "peak": fp32_peak, "unit": "Gop/s (FMA=2)", "frac": p_ach / fp32_peak,
-                         "traffic": ncu_traffic(args.workload, world), "peak_source": "lgb_measure_fp32_gops, live on this GPU",
-                         "algorithmic_ops_per_launch": p_ops, "algorithmic_bytes_per_launch": p_bytes, "launch_ms": phases[0],
-                         "algorithmic_definition": "per-ray walk of the device BVH (SURVEY 8d), counted on a frame with LGB_OPT_BEAMS=0",
-                         "executed_ops_per_launch": e_ops, "executed_bytes_per_launch": e_bytes,
-                         "shadow_phase": {"kernels": "k_shadow (anchor rays) + k_pretest + k_shadow (rest)", "launch_ms": sh_ms,
-                                          "algorithmic_ops": sh_ops, "achieved": sh_ops / (sh_ms * 1e-3) / 1e9 / world,
-                                          "frac": sh_ops / (sh_ms * 1e-3) / 1e9 / world / fp32_peak},
-                         # node / primitive fetches are L1 hits (96 %): the ceiling that binds is the L1 data pipe, 128 B/clk/SM
-                         "l1_fetch": {"achieved_gbs": p_bytes / (phases[0] * 1e-3) / 1e9 / world, "peak_gbs": l1_peak,
-                                      "frac": p_bytes / (phases[0] * 1e-3) / 1e9 / world / l1_peak,
-                                      "peak_source": "128 B/clk/SM x SM count x SM clock under load"},
-                         "frame": {"achieved": ach, "frac": ach / fp32_peak, "algorithmic_ops_per_frame": ops, "algorithmic_bytes_per_frame": byts},
-                         "phase_ms": dict(zip(("primary", "setup", "shadow_anchor", "pretest_shadow_rest", "shade", "resolve"), phases)),
-                         "l2": {"achieved_gbs": l2_ach, "peak_gbs": ceil["l2_read_gbs"], "frac": l2_ach / ceil["l2_read_gbs"]},
-                         "hbm": {"achieved_gbs": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
-                                 "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"]},
-                         "fp64_dfma_glanes_peak": ceil["fp64_dfma_glanes"]},
             "work_per_frame": frame,
             "clocks": clocks,
         }
+        if world == 1 and timed and counted:
+            traffic, traffic_note = ncu_traffic(args.workload)
+            rows, fp32_peak, fp64_peak = kernel_table(timed, counted, frame, w, h, nl, sm_count, clock, traffic)
+            rows.sort(key=lambda r: -r["launch_ms"])
+            top = rows[0]
+            tsum = sum(r["launch_ms"] for r in rows)
+            ceil = ctx.measure()
+            line["roofline"] = {
+                "kernel": top["kernel"], "share_of_frame": top["launch_ms"] / tsum,
+                "bound": "hbm" if False else top["bound"], "achieved": top["achieved_gops"], "peak": top["peak_gops"], "unit": "Gop/s (FMA=2)",
+                "frac": top["frac"], "traffic": top.get("traffic"), "traffic_source": traffic_note,
+                "launch_ms": top["launch_ms"], "ops_per_launch": top["ops_per_launch"],
+                "peak_source": "%d SMs x %.0f MHz (median SM clock sampled during the timed region) x %d lanes x 2" % (sm_count, clock, 64 if top["bound"] == "fp64_issue" else 128),
+                "ops_definition": "the launch's own unit counts (work counters of an untimed frame of the same kernels) x SURVEY 8d constants of record",
+                "kernels": [{k: v for k, v in r.items() if k not in ("filter_tests", "exact_tests")} for r in rows],
+                "frame": {"ops": sum(r["ops_per_launch"] for r in rows), "sum_of_launch_ms": tsum,
+                          "frac_fp32_issue": sum(r["ops_per_launch"] for r in rows) / (tsum * 1e-3) / 1e9 / fp32_peak},
+                "hbm": {"compulsory_bytes": scene_bytes + w * h * 4, "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["source"],
+                        "traffic_per_frame": sum(r["traffic"] for r in rows if "traffic" in r) if traffic else None},
+                "microbenchmarks_not_used_as_peaks": {"fp32_ffma_glanes": ceil["fp32_ffma_glanes"], "fp64_dfma_glanes": ceil["fp64_dfma_glanes"], "l2_read_gbs": ceil["l2_read_gbs"]},
+            }
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle as po
             threads = po.hardware_threads()
@@ -396,6 +466,21 @@ def run_gpu(args):
                                     "sample": f"capture_subset(k, n={n}) for k in 0..{threads} of the {w}x{h} frame ({rays} rays, {r['render_ms']:.0f} ms); "
                                               "C++ restatement of the reference algorithm, not the Rust build",
                                     "bvh_build_ms": osc.build_ms, "device_film_identical_frac_at_sample": float(same)}
+        if world == 1 and not args.no_other_configs and not args.small and args.workload == "mixed4k":
+            # the other four BASELINE configs, briefly (kernel-only, e2e, dominant kernel): extra keys of the same line
+            others = {}
+            for name in OTHER_CONFIGS:
+                try:
+                    q = quick_config(N, ctx, name, args, None)
+                    qw, qh = q["film"]
+                    rows, _, _ = kernel_table(q.pop("timed"), q.pop("counted"), q.pop("frame"), qw, qh, q["lights"], sm_count, clock, None)
+                    rows.sort(key=lambda r: -r["launch_ms"])
+                    q["dominant_kernel"] = {k: rows[0][k] for k in ("kernel", "launch_ms", "ops_per_launch", "achieved_gops", "peak_gops", "bound", "frac")}
+                    q["kernels_ms"] = {r["kernel"]: r["launch_ms"] for r in rows}
+                    others[name] = q
+                except Exception as e:      # a failing side measurement must not take the headline line down with it
+                    others[name] = {"error": repr(e)}
+            line["other_configs"] = others
         print(json.dumps(line))
     dev.destroy()
     if shared is not None:
@@ -418,10 +503,11 @@ def main():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N>1 film gather: peer stores into rank 0's film, or NCCL reduce")
     ap.add_argument("--workload", default="mixed4k", choices=sorted(scenes.CONFIGS))
     ap.add_argument("--small", action="store_true", help="tiny variant of mixed4k (CPU smoke of the bench logic)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds", type=float, default=60.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

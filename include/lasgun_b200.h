@@ -201,6 +201,14 @@ int lgb_film_release_shared(lgb_ctx* ctx, void* d_film, int owner);   /* owner !
 /* Device / context --------------------------------------------------------------------- */
 int lgb_device_count(void);
 int lgb_init(int device, lgb_ctx** out);
+/* A device group in ONE process: the analogue of the reference's worker threads (src/lib.rs:55-104 spawns num_cpus of them
+ * inside one blocking `capture`).  devices[0] leads: scenes are built there and their arena is copied to the others over
+ * NVLink (not rebuilt); lgb_capture and lgb_capture_device(tile_ranks = 1) then split the macro tiles over all listed
+ * devices, each one's kernels store their pixels straight into the leader's film (peer access is required and checked here),
+ * and the call returns when every device is done.  Every other entry point runs on the leader alone.  The returned context
+ * is used exactly like a single-device one; lgb_shutdown closes the whole group. */
+int lgb_init_devices(int n_devices, const int* devices, lgb_ctx** out);
+int lgb_context_devices(const lgb_ctx* ctx);       /* devices a context renders on (1 for lgb_init) */
 void lgb_shutdown(lgb_ctx* ctx);
 #define LGB_OPT_COUNT_WORK 1        /* value != 0: captures also fill the work counters of lgb_stats */
 #define LGB_OPT_SIDE_STREAMS 4      /* 1 (default): the shadow-ray kernels of different lights overlap on a side stream; 0: one stream */
@@ -210,6 +218,14 @@ void lgb_shutdown(lgb_ctx* ctx);
                                      * whose centre sample is unoccluded (k_sbeam, from the light).  Same results.  1 on, 0 off,
                                      * -1 (default) automatic: on for >= 8 samples per pixel and a BVH of >= 1024 nodes.
                                      * env LGB_BEAMS presets it. */
+#define LGB_OPT_LIGHT_GRIDS 5       /* shadow rays through per-light cube-map grids of primitive lists instead of the BVH (csrc/lgb_grid.cu;
+                                     * scenes without transformed aggregates).  Same occlusion bits.  1 on, 0 off, -1 (default)
+                                     * automatic: device BVH of >= 1024 nodes and at most 8 lights.  Read at lgb_scene_create.
+                                     * env LGB_LIGHT_GRIDS presets it. */
+#define LGB_OPT_CAMERA_GRID 6       /* primary rays of a perspective camera through a grid of pixel tiles, each listing the primitives its
+                                     * samples can see (csrc/lgb_grid.cu), instead of the BVH / pixel beams.  Same hits.  1 on, 0 off,
+                                     * -1 (default) automatic.  Built at the first capture of a film size and kept with the scene.
+                                     * env LGB_CAMERA_GRID presets it. */
 int lgb_set_option(lgb_ctx* ctx, int option, int value);
 const char* lgb_last_error(lgb_ctx* ctx);          /* ctx may be NULL: last error of lgb_init */
 const char* lgb_status_string(int status);

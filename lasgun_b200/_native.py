@@ -20,7 +20,7 @@ LGB_LEAF_FLAG = 0x80000000
 
 # Every symbol include/lasgun_b200.h declares (checked by tests/test_abi.py without a GPU).
 ABI_SYMBOLS = [
-    "lgb_build_probe", "lgb_device_count", "lgb_init", "lgb_set_option", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
+    "lgb_build_probe", "lgb_device_count", "lgb_init", "lgb_init_devices", "lgb_context_devices", "lgb_set_option", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
     "lgb_film_alloc_shared", "lgb_film_open_shared", "lgb_film_release_shared", "lgb_scene_destroy", "lgb_scene_layout_bytes", "lgb_scene_export", "lgb_scene_import", "lgb_scene_verify", "lgb_scene_device_bytes", "lgb_scene_build_ms", "lgb_scene_node_count", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
     "lgb_capture_device", "lgb_capture_profile", "lgb_trace_rays", "lgb_debug_fastmath", "lgb_measure_l2_read_gbs", "lgb_measure_fp32_gops", "lgb_measure_fp64_gops",
 ]
@@ -103,7 +103,8 @@ def lib():
     vp, dp, fp, u32p, u64p, u8p, ip = (C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_uint32),
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_int))
     sig = {
-        "lgb_device_count": (C.c_int, []), "lgb_init": (C.c_int, [C.c_int, C.POINTER(vp)]), "lgb_shutdown": (None, [vp]),
+        "lgb_device_count": (C.c_int, []), "lgb_init": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "lgb_init_devices": (C.c_int, [C.c_int, ip, C.POINTER(vp)]), "lgb_context_devices": (C.c_int, [vp]), "lgb_shutdown": (None, [vp]),
         "lgb_set_option": (C.c_int, [vp, C.c_int, C.c_int]),
         "lgb_build_probe": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(BuildInfo)]),
         "lgb_last_error": (C.c_char_p, [vp]), "lgb_status_string": (C.c_char_p, [C.c_int]),
@@ -322,14 +323,21 @@ class FlatScene:
 class Context:
     """lgb_ctx: one GPU."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """One GPU (`device`), or a device group in this process (`devices`: the first one leads, lgb_init_devices)."""
         L = lib()
         h = C.c_void_p()
-        rc = L.lgb_init(device, C.byref(h))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = L.lgb_init_devices(len(devices), arr, C.byref(h))
+            device = devices[0] if len(devices) else 0
+        else:
+            rc = L.lgb_init(device, C.byref(h))
         if rc:
             raise LasgunError(rc, L.lgb_last_error(None).decode())
         self.h = h
         self.device = device
+        self.n_devices = int(L.lgb_context_devices(h))
 
     def check(self, rc):
         if rc:
@@ -346,6 +354,14 @@ class Context:
     def set_beams(self, mode: int):
         """LGB_OPT_BEAMS: 1 on (whenever spp >= 4), 0 off, -1 automatic (the default)."""
         self.check(lib().lgb_set_option(self.h, 2, int(mode)))
+
+    def set_light_grids(self, mode: int):
+        """LGB_OPT_LIGHT_GRIDS (read at scene creation): 1 on, 0 off, -1 automatic (the default)."""
+        self.check(lib().lgb_set_option(self.h, 5, int(mode)))
+
+    def set_camera_grid(self, mode: int):
+        """LGB_OPT_CAMERA_GRID: 1 on, 0 off, -1 automatic (the default)."""
+        self.check(lib().lgb_set_option(self.h, 6, int(mode)))
 
     def set_side_streams(self, on: bool):
         """LGB_OPT_SIDE_STREAMS: overlap the shadow chains of different lights (default on)."""
@@ -484,7 +500,8 @@ class DeviceScene:
 
     def destroy(self):
         if self.h:
-            lib().lgb_scene_destroy(self.h)
+            if self.ctx.h:                       # (a scene outliving its context is leaked, not freed through a dead context)
+                lib().lgb_scene_destroy(self.h)
             self.h = None
             self._keep = None
 

@@ -7,8 +7,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "liblasgun_b200.so")
-SOURCES = ["csrc/lgb_kernels.cu", "csrc/lgb_gpubuild.cu", "csrc/lgb_api.cu", "csrc/lgb_build.cpp", "csrc/lgb_parallel.cpp", "csrc/host/lasgun_host.cpp"]
-HEADERS = ["csrc/lgb_types.cuh", "csrc/lgb_gpubuild.cuh", "csrc/lgb_math.cuh", "csrc/lgb_build.hpp", "csrc/lgb_parallel.hpp", "../include/lasgun_b200.h", "../include/lasgun_host.hpp"]
+SOURCES = ["csrc/lgb_kernels.cu", "csrc/lgb_gpubuild.cu", "csrc/lgb_grid.cu", "csrc/lgb_api.cu", "csrc/lgb_build.cpp", "csrc/lgb_parallel.cpp", "csrc/host/lasgun_host.cpp"]
+HEADERS = ["csrc/lgb_types.cuh", "csrc/lgb_gpubuild.cuh", "csrc/lgb_grid.cuh", "csrc/lgb_math.cuh", "csrc/lgb_build.hpp", "csrc/lgb_parallel.hpp", "../include/lasgun_b200.h", "../include/lasgun_host.hpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

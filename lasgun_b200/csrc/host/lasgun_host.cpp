@@ -750,7 +750,14 @@ static lgb_ctx* g_ctx = nullptr;
 lgb_ctx* default_context() {
     std::lock_guard<std::mutex> lock(g_ctx_mutex);
     if (!g_ctx) {
-        int rc = lgb_init(0, &g_ctx);
+        // LASGUN_DEVICES: "all" = every visible GPU as one device group (the reference takes every core, lib.rs:165), a comma
+        // separated list = those, unset = device 0 alone (a process launched once per GPU must not grab its neighbours')
+        std::vector<int> devs;
+        if (const char* e = std::getenv("LASGUN_DEVICES")) {
+            if (std::string(e) == "all") { for (int i = 0; i < lgb_device_count(); i++) devs.push_back(i); }
+            else for (const char* q = e; *q;) { char* end = nullptr; const long v = std::strtol(q, &end, 10); if (end == q) break; devs.push_back((int)v); q = *end ? end + 1 : end; }
+        }
+        int rc = devs.size() > 1 ? lgb_init_devices((int)devs.size(), devs.data(), &g_ctx) : lgb_init(devs.empty() ? 0 : devs[0], &g_ctx);
         if (rc) throw Error(rc, std::string("lasgun: cannot open the GPU: ") + lgb_last_error(nullptr));
     }
     return g_ctx;

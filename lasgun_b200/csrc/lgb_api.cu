@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -13,6 +14,7 @@
 
 #include "lgb_build.hpp"
 #include "lgb_gpubuild.cuh"
+#include "lgb_grid.cuh"
 #include "lgb_parallel.hpp"
 #include "lgb_types.cuh"
 
@@ -20,7 +22,7 @@ namespace lgb {
 constexpr int kRenderEvents = 7;
 cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev, int part, const SideStreams* side, KernelLog* klog);
 bool render_fused(uint32_t spp);
-cudaError_t launch_level(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, int sms, cudaStream_t);
+cudaError_t launch_level(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, int sms, cudaStream_t, DevCounters* shadow_counters);
 cudaError_t launch_gather(const SpawnRec* recs, const uint32_t* nspec, double* rad_parent, const double* rad_child, uint64_t n_upper, cudaStream_t);
 cudaError_t launch_resolve(const DevWork&, const DevOut&, cudaStream_t);
 cudaError_t launch_export_li(const DevWork&, const DevOut&, const DevWave&, cudaStream_t);
@@ -68,10 +70,16 @@ struct lgb_ctx {
     // the rays of the current and the next level, the wavefront buffers of the current level, per-level counters
     DevBuf lvl_rad[kMaxRecursion + 1], lvl_recs[kMaxRecursion + 1], raybuf[2], wave2, wave2_ctr, lvl_ctr;
     KernelLog klog{}; DevBuf klog_snaps;   // lgb_capture_profile
+    // device group (lgb_init_devices): this context leads, `peers` render their share of the tiles into its film over NVLink
+    std::vector<lgb_ctx*> peers;
+    lgb_ctx* leader = nullptr;
+    std::mutex lazy_mu;                    // the caller's reference_tree callback is entered by one device at a time
     SideStreams side{};                    // streams the shadow chains of different lights are spread over (LGB_OPT_SIDE_STREAMS)
     int side_streams = 1;
     int whitted_wavefront = 1;             // LGB_OPT_WHITTED: 1 level-by-level wavefront, 0 one thread per ray tree (k_secondary)
     int beams = -1;                        // LGB_OPT_BEAMS: 0 off, 1 on, -1 automatic
+    int camera_grid = -1;                  // LGB_OPT_CAMERA_GRID: 0 off, 1 on, -1 automatic
+    int light_grids = -1;                  // LGB_OPT_LIGHT_GRIDS: 0 off, 1 on, -1 automatic (scenes of >= 1024 BVH nodes, <= 8 lights)
     std::vector<uint32_t> tile_host;
     uint32_t tile_key[4] = {0, 0, 0, 0};   // w, h, rank, ranks of the cached tile list
     uint32_t tile_count = 0;
@@ -98,6 +106,13 @@ struct lgb_scene {
     void* rank_buf = nullptr;                        // rank tables uploaded later live outside the arena
     uint64_t tie_retraces = 0;
     uint64_t bytes = 0;
+    // camera grid (lgb_grid.cu) of the film size it was last built for; rebuilt when the film changes
+    struct CamGrid { uint32_t w = 0, h = 0, shift = 0, nx = 0, n_large = 0; bool valid = false, refused = false; void* starts = nullptr; void* entries = nullptr; void* large = nullptr; uint64_t bytes = 0; double build_ms = 0; } camgrid;
+    CamGrid& cam_grid() { return camgrid; }
+    std::vector<void*> grid_allocs;    // light grids (lgb_grid.cu): table + per-light cell starts / entries / large lists, outside the arena
+    double t_grids = 0;                // ms
+    uint64_t grid_bytes = 0;
+    std::vector<lgb_scene*> replicas;  // device group: the same scene on every peer, in peer order (arena copied over NVLink, not rebuilt)
     cudaEvent_t last_use = nullptr;   // recorded behind every capture on the stream it ran on: lgb_scene_destroy frees the arena behind it
     DevScene dev{};
     DevCamera cam{};
@@ -153,6 +168,8 @@ int lgb_init(int device, lgb_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (const char* e = std::getenv("LGB_BEAMS")) { const int v = std::atoi(e); c->beams = v < 0 ? -1 : (v != 0); }
+    if (const char* e = std::getenv("LGB_LIGHT_GRIDS")) { const int v = std::atoi(e); c->light_grids = v < 0 ? -1 : (v != 0); }
+    if (const char* e = std::getenv("LGB_CAMERA_GRID")) { const int v = std::atoi(e); c->camera_grid = v < 0 ? -1 : (v != 0); }
     c->side.n = 1;                         // one side stream: two lights' chains at a time (a third stream measured no further gain)
     cudaError_t ie = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (ie == cudaSuccess) ie = cudaEventCreate(&c->ev0);
@@ -182,6 +199,37 @@ int lgb_init(int device, lgb_ctx** out) {
     *out = c;
     return LGB_OK;
 }
+
+int lgb_init_devices(int ndev, const int* devices, lgb_ctx** out) {
+    if (!out) return fail(nullptr, LGB_ERR_INVALID, "lgb_init_devices: out is NULL");
+    *out = nullptr;
+    if (ndev < 1 || !devices) return fail(nullptr, LGB_ERR_INVALID, "lgb_init_devices: empty device list");
+    for (int i = 0; i < ndev; i++) for (int j = 0; j < i; j++) if (devices[i] == devices[j]) return fail(nullptr, LGB_ERR_INVALID, "lgb_init_devices: device listed twice");
+    lgb_ctx* lead = nullptr;
+    if (int rc = lgb_init(devices[0], &lead)) return rc;
+    for (int i = 1; i < ndev; i++) {
+        lgb_ctx* p = nullptr;
+        int rc = lgb_init(devices[i], &p);
+        if (!rc) {
+            // the peer's kernels store their pixels into the leader's film: that needs direct peer access (NVLink / NVSwitch)
+            int can = 0;
+            cudaError_t e = cudaDeviceCanAccessPeer(&can, devices[i], devices[0]);
+            if (e == cudaSuccess && can) {
+                cudaSetDevice(devices[i]);
+                e = cudaDeviceEnablePeerAccess(devices[0], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            }
+            if (e != cudaSuccess) rc = cuda_fail(nullptr, e, "lgb_init_devices: peer access");
+            else if (!can) rc = fail(nullptr, LGB_ERR_UNSUPPORTED, "lgb_init_devices: a listed device cannot access the first one's memory (no NVLink / P2P path)");
+        }
+        if (rc) { const std::string msg = g_init_error; if (p) lgb_shutdown(p); lgb_shutdown(lead); g_init_error = msg; return rc; }
+        p->leader = lead; p->beams = lead->beams; p->light_grids = lead->light_grids; p->camera_grid = lead->camera_grid;
+        lead->peers.push_back(p);
+    }
+    *out = lead;
+    return LGB_OK;
+}
+int lgb_context_devices(const lgb_ctx* c) { return c ? 1 + (int)c->peers.size() : 0; }
 
 int lgb_film_alloc_shared(lgb_ctx* c, uint64_t bytes, void** d_film, uint8_t handle_out[LGB_IPC_HANDLE_BYTES]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == LGB_IPC_HANDLE_BYTES, "IPC handle size");
@@ -213,15 +261,20 @@ int lgb_film_release_shared(lgb_ctx* c, void* d_film, int owner) {
 
 int lgb_set_option(lgb_ctx* c, int option, int value) {
     if (!c) return LGB_ERR_INVALID;
+    for (lgb_ctx* p : c->peers) lgb_set_option(p, option, value);
     if (option == LGB_OPT_COUNT_WORK) { c->count_work = value != 0; return LGB_OK; }
     if (option == LGB_OPT_BEAMS) { c->beams = value < 0 ? -1 : (value != 0); return LGB_OK; }
     if (option == LGB_OPT_WHITTED) { c->whitted_wavefront = value != 0; return LGB_OK; }
     if (option == LGB_OPT_SIDE_STREAMS) { c->side_streams = value != 0; return LGB_OK; }
+    if (option == LGB_OPT_LIGHT_GRIDS) { c->light_grids = value < 0 ? -1 : (value != 0); return LGB_OK; }
+    if (option == LGB_OPT_CAMERA_GRID) { c->camera_grid = value < 0 ? -1 : (value != 0); return LGB_OK; }
     return fail(c, LGB_ERR_INVALID, "lgb_set_option: unknown option");
 }
 
 void lgb_shutdown(lgb_ctx* c) {
     if (!c) return;
+    for (lgb_ctx* p : c->peers) { p->leader = nullptr; lgb_shutdown(p); }
+    c->peers.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties, &c->beam, &c->raybuf[0], &c->raybuf[1], &c->wave2, &c->wave2_ctr, &c->lvl_ctr, &c->aov_li, &c->beam2}) b->release();
@@ -304,6 +357,7 @@ static int validate_reference_tree(const lgb_scene_desc* d, std::string& msg) {
 // Lazy scenes: fetch the reference tree from the caller, build the rank tables and make them resident.
 static int ensure_rank_tables(lgb_ctx* ctx, lgb_scene* s) {
     if (s->dev.rank || !s->lazy_fn) return LGB_OK;
+    std::lock_guard<std::mutex> lock((ctx->leader ? ctx->leader : ctx)->lazy_mu);      // device group: one caller of the callback at a time
     lgb_reference_tree tree{};
     if (s->lazy_fn(s->lazy_user, &tree) != 0 || !tree.nodes || !tree.n_nodes) return fail(ctx, LGB_ERR_INVALID, "reference_tree callback failed");
     lgb_scene_desc d = s->lazy_desc;
@@ -330,7 +384,7 @@ static int ensure_rank_tables(lgb_ctx* ctx, lgb_scene* s) {
 // ---- export / import: the arena is position independent once DevScene's pointers are written as offsets
 namespace {
 struct SceneLayout { uint64_t magic, arena_bytes; DevScene dev; DevCamera cam; DevShade shade; double max_abs; };
-constexpr uint64_t kLayoutMagic = 0x4C47423253434E32ull;       // "LGB2SCN2"
+constexpr uint64_t kLayoutMagic = 0x4C47423253434E33ull;       // "LGB2SCN3"
 constexpr uint64_t kNullOffset = ~0ull;
 template <class F> void for_each_pointer(DevScene& d, F f) {
     f((const void*&)d.nodes); f((const void*&)d.sph32); f((const void*&)d.sph64); f((const void*&)d.sph_mat); f((const void*&)d.sph_id);
@@ -472,17 +526,21 @@ int lgb_scene_verify(lgb_ctx* ctx, const lgb_scene* s, lgb_build_info* out) {
 
 void lgb_scene_destroy(lgb_scene* s) {
     if (!s) return;
+    for (lgb_scene* r : s->replicas) lgb_scene_destroy(r);
+    s->replicas.clear();
     cudaSetDevice(s->ctx->device);
     if (s->last_use) {                 // a capture may still be running on a caller-supplied stream (lgb_capture_device is asynchronous)
         cudaStreamWaitEvent(s->ctx->stream, s->last_use, 0);
         cudaEventDestroy(s->last_use);
     }
+    for (void* g : s->grid_allocs) cudaFreeAsync(g, s->ctx->stream);
+    for (void* g : {s->camgrid.starts, s->camgrid.entries, s->camgrid.large}) if (g) cudaFreeAsync(g, s->ctx->stream);
     if (s->rank_buf) cudaFreeAsync(s->rank_buf, s->ctx->stream);
     if (s->arena && s->owns_arena) cudaFreeAsync(s->arena, s->ctx->stream);      // stream-ordered: later work of this context is behind it
     else if (s->arena) cudaStreamSynchronize(s->ctx->stream);                    // borrowed arena: the caller may free it right after
     delete s;
 }
-uint64_t lgb_scene_device_bytes(const lgb_scene* s) { return s ? s->bytes : 0; }
+uint64_t lgb_scene_device_bytes(const lgb_scene* s) { return s ? s->bytes + s->grid_bytes : 0; }
 
 uint64_t lgb_scene_layout_bytes(void) { return sizeof(SceneLayout); }
 int lgb_scene_export(const lgb_scene* s, void* layout_out, uint64_t layout_bytes, void** arena_dev, uint64_t* arena_bytes) {
@@ -491,11 +549,13 @@ int lgb_scene_export(const lgb_scene* s, void* layout_out, uint64_t layout_bytes
     SceneLayout L{};
     L.magic = kLayoutMagic; L.arena_bytes = s->bytes; L.dev = s->dev; L.cam = s->cam; L.shade = s->shade; L.max_abs = s->max_abs;
     const char* base = (const char*)s->arena;
+    L.dev.grids = nullptr;                             // light grids live outside the arena: the importer builds its own
     for_each_pointer(L.dev, [&](const void*& p) { p = (const void*)(p ? (uint64_t)((const char*)p - base) : kNullOffset); });
     std::memcpy(layout_out, &L, sizeof L);
     *arena_dev = s->arena; *arena_bytes = s->bytes;
     return LGB_OK;
 }
+static int build_light_grids(lgb_ctx* ctx, lgb_scene* s);
 int lgb_scene_import(lgb_ctx* ctx, const void* layout, uint64_t layout_bytes, void* arena_dev, lgb_scene** out) {
     if (!ctx || !layout || layout_bytes < sizeof(SceneLayout) || !arena_dev || !out) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_import: bad argument");
     SceneLayout L; std::memcpy(&L, layout, sizeof L);
@@ -522,11 +582,101 @@ int lgb_scene_import(lgb_ctx* ctx, const void* layout, uint64_t layout_bytes, vo
         if (off == kNullOffset) p = nullptr; else if (off > L.arena_bytes) ok = false; else p = base + off;
     });
     if (!ok) { delete s; return fail(ctx, LGB_ERR_INVALID, "lgb_scene_import: an array of the layout does not lie inside the arena"); }
+    s->dev.grids = nullptr;
+    if (int rc = build_light_grids(ctx, s)) { lgb_scene_destroy(s); return rc; }
     *out = s;
     return LGB_OK;
 }
 double lgb_scene_build_ms(const lgb_scene* s) { return s ? s->build_ms : 0.0; }
 uint32_t lgb_scene_node_count(const lgb_scene* s) { return s ? s->dev.n_nodes : 0; }
+
+// Light grids (lgb_grid.cu) of a resident single-space scene, on the scene's own device and the context's stream.  A scene the
+// grids do not suit (transformed aggregates, a tiny BVH, many lights, many huge primitives) simply keeps dev.grids == NULL and its
+// shadow rays traverse the BVH.
+static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
+    DevScene& S = s->dev;
+    S.grids = nullptr;
+    const bool want = ctx->light_grids == 1 || (ctx->light_grids < 0 && S.n_nodes >= 1024u && S.n_lights <= 8u);
+    if (!want || S.instanced || S.n_lights == 0 || S.n_sph + S.n_cub + S.n_tri == 0) return LGB_OK;
+    auto t0 = std::chrono::steady_clock::now();
+    CU(ctx, cudaSetDevice(ctx->device));
+    uint32_t res = 1024;
+    if (const char* e = std::getenv("LGB_GRID_RES")) res = std::min(4096u, std::max(16u, (uint32_t)std::atoi(e)));
+    const size_t nc = grid_cells(res), scan_bytes = grid_scan_bytes(res);
+    cudaStream_t st = ctx->stream;
+    uint32_t* counts = nullptr; void* scan_tmp = nullptr; uint2* large_tmp = nullptr; uint32_t* n_large_dev = nullptr;
+    std::vector<void*> mine;                 // what the scene keeps
+    std::vector<DevGrid> table(S.n_lights);
+    auto cleanup = [&](bool keep) {
+        if (counts) cudaFreeAsync(counts, st);
+        if (scan_tmp) cudaFreeAsync(scan_tmp, st);
+        if (large_tmp) cudaFreeAsync(large_tmp, st);
+        if (n_large_dev) cudaFreeAsync(n_large_dev, st);
+        if (!keep) for (void* p : mine) cudaFreeAsync(p, st);
+    };
+#define GR(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(false); return cuda_fail(ctx, e__, #call); } } while (0)
+    GR(cudaMallocAsync((void**)&counts, (nc + 1) * 4, st));
+    GR(cudaMallocAsync(&scan_tmp, std::max<size_t>(scan_bytes, 16), st));
+    GR(cudaMallocAsync((void**)&large_tmp, sizeof(uint2) * kGridLargeCap, st));
+    GR(cudaMallocAsync((void**)&n_large_dev, 4, st));
+    bool ok = true;
+    for (uint32_t l = 0; l < S.n_lights && ok; l++) {
+        uint32_t* starts = nullptr;
+        GR(cudaMallocAsync((void**)&starts, (nc + 1) * 4, st));
+        mine.push_back(starts);
+        uint32_t total = 0, n_large = 0;
+        GR(grid_count(S, l, res, counts, starts, scan_tmp, scan_bytes, large_tmp, n_large_dev, st, &total, &n_large));
+        if (n_large > kGridLargeCap) { ok = false; break; }
+        uint2* entries = nullptr; uint2* large = nullptr;
+        GR(cudaMallocAsync((void**)&entries, sizeof(uint2) * std::max<size_t>(total, 1), st));
+        mine.push_back(entries);
+        GR(cudaMallocAsync((void**)&large, sizeof(uint2) * std::max<uint32_t>(n_large, 1), st));
+        mine.push_back(large);
+        GR(grid_fill(S, l, res, counts, starts, entries, large_tmp, n_large, st));
+        if (n_large) GR(cudaMemcpyAsync(large, large_tmp, sizeof(uint2) * n_large, cudaMemcpyDeviceToDevice, st));
+        table[l].cell_start = starts; table[l].entries = entries; table[l].large = large; table[l].res = res; table[l].n_large = n_large;
+        s->grid_bytes += (nc + 1) * 4 + sizeof(uint2) * ((size_t)total + n_large);
+    }
+    if (ok) {
+        DevGrid* dtab = nullptr;
+        GR(cudaMallocAsync((void**)&dtab, sizeof(DevGrid) * S.n_lights, st));
+        mine.push_back(dtab);
+        GR(cudaMemcpyAsync(dtab, table.data(), sizeof(DevGrid) * S.n_lights, cudaMemcpyHostToDevice, st));
+        GR(cudaStreamSynchronize(st));       // `table` is on this stack frame
+        S.grids = dtab;
+        s->grid_allocs = mine;
+    }
+    cleanup(ok);
+#undef GR
+    s->t_grids = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return LGB_OK;
+}
+
+// Device group: the finished arena is copied to every peer over NVLink (one 61 MB peer copy each for `mixed4k`, not a rebuild) and
+// the peer's scene points into its own copy.  A lazy scene stays lazy on every device (same callback, entered under one mutex).
+static int replicate_to_peers(lgb_ctx* ctx, lgb_scene* s) {
+    const char* base = (const char*)s->arena;
+    for (lgb_ctx* p : ctx->peers) {
+        CU(ctx, cudaSetDevice(p->device));
+        void* arena = nullptr;
+        CU(ctx, cudaMallocAsync(&arena, s->bytes, p->stream));
+        lgb_scene* r = new lgb_scene();
+        r->ctx = p; r->arena = arena; r->owns_arena = true; r->bytes = s->bytes; r->gpu_built = s->gpu_built;
+        r->dev = s->dev; r->cam = s->cam; r->shade = s->shade; r->max_abs = s->max_abs;
+        r->lazy_fn = s->lazy_fn; r->lazy_user = s->lazy_user; r->lazy_desc = s->lazy_desc;
+        for_each_pointer(r->dev, [&](const void*& q) { if (q) q = (const char*)arena + ((const char*)q - base); });
+        s->replicas.push_back(r);
+        CU(ctx, cudaMemcpyPeerAsync(arena, p->device, s->arena, ctx->device, s->bytes, p->stream));
+    }
+    for (size_t k = 0; k < ctx->peers.size(); k++) {
+        lgb_ctx* p = ctx->peers[k];
+        CU(ctx, cudaSetDevice(p->device)); CU(ctx, cudaStreamSynchronize(p->stream));
+        s->replicas[k]->dev.grids = nullptr;
+        if (int rc = build_light_grids(p, s->replicas[k])) return fail(ctx, rc, "light grids on device " + std::to_string(p->device) + ": " + p->error);
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    return LGB_OK;
+}
 
 int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     if (!ctx || !d || !out) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_create: NULL argument");
@@ -734,6 +884,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         s->bytes = o_nodes + (size_t)info.n_nodes * 64;
         s->dev.nodes = (const float4*)(D + o_nodes); s->dev.n_nodes = info.n_nodes;
         s->dev.rank = lazy ? nullptr : (const uint32_t*)(D + o_rank); s->dev.prim_count = prim_count; s->dev.rank_items = (uint32_t)n_items;
+        s->dev.n_sph = (uint32_t)ns; s->dev.n_cub = (uint32_t)ncb; s->dev.n_tri = (uint32_t)nt;
         s->dev.n_spaces = 1; s->dev.instanced = 0;
         if (lazy) { s->lazy_fn = d->reference_tree; s->lazy_user = d->reference_tree_user; s->lazy_desc = *d; }
         if (ns) { s->dev.sph32 = la.sph32; s->dev.sph64 = la.sph64; s->dev.sph_mat = la.sph_mat; s->dev.sph_id = la.sph_id; }
@@ -799,6 +950,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     pool.for_range(nnodes, 1 << 14, [&](size_t b, size_t e, size_t) { std::memcpy(H + o_nodes + b * 64, bvh.nodes.data() + b, (e - b) * 64); });
     s->dev.nodes = (const float4*)(D + o_nodes); s->dev.n_nodes = (uint32_t)nnodes;
     s->dev.rank = (const uint32_t*)(D + o_rank); s->dev.prim_count = prim_count; s->dev.rank_items = (uint32_t)n_items;
+    s->dev.n_sph = (uint32_t)ns; s->dev.n_cub = (uint32_t)ncb; s->dev.n_tri = (uint32_t)nt;
     s->dev.n_spaces = (uint32_t)nsp; s->dev.instanced = instanced ? 1u : 0u;
     if (instanced) {
         DevSpace* ds = (DevSpace*)(H + o_spaces);
@@ -901,6 +1053,8 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     s->t_total = ms_since(tc0);
     if (getenv("LGB_TIMING")) fprintf(stderr, "[lgb_scene_create] %s build: validate%s %.1f rank %.1f build %.1f (sah %.1f) convert+upload %.1f total %.1f ms, %u threads\n",
                                       s->gpu_built ? "device" : "host", s->gpu_built ? "+stage" : "", s->t_validate, s->t_rank, s->t_build, s->build_ms, s->t_convert_upload, s->t_total, (unsigned)threads);
+    if (int rc = build_light_grids(ctx, s)) return bail(rc);
+    if (!ctx->peers.empty()) if (int rc = replicate_to_peers(ctx, s)) return bail(rc);
     *out = s;
     return LGB_OK;
 }
@@ -918,6 +1072,63 @@ static void build_tile_list(lgb_ctx* c, uint32_t w, uint32_t h, uint32_t rank, u
     c->tile_count = 0;   // uploaded lazily
 }
 
+// Camera grid of `s` for a w x h film (lgb_grid.cu), built on first use and kept with the scene; fills W.cg_* or leaves them NULL
+// (orthographic camera, transformed aggregates, a scene too small to pay for the binning, too many primitives across the eye's plane).
+static int ensure_camgrid(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint64_t samples, DevWork& W, cudaStream_t st) {
+    const DevScene& S = s->dev;
+    const uint32_t prims = S.n_sph + S.n_cub + S.n_tri;
+    // automatic: where the frame holds enough samples to pay for binning every primitive (measured)
+    const bool want = c->camera_grid == 1 || (c->camera_grid < 0 && S.n_nodes >= 1024u && samples >= 4ull * prims);
+    if (!want || S.instanced || s->cam.pixel_separation != 0.0 || prims == 0) return LGB_OK;
+    lgb_scene::CamGrid& G = s->cam_grid();
+    if (G.refused && G.w == w && G.h == h) return LGB_OK;
+    if (!(G.valid && G.w == w && G.h == h)) {
+        auto t0 = std::chrono::steady_clock::now();
+        for (void** q : {&G.starts, &G.entries, &G.large}) if (*q) { cudaFreeAsync(*q, st); *q = nullptr; }
+        G.valid = false; G.refused = false; G.w = w; G.h = h;
+        CamGridParams P{};
+        const DevCamera& cam = s->cam;
+        // (a w, b w, w) = [aux | up | view]^-1 (X - origin)
+        const double m[9] = {cam.aux[0], cam.up[0], cam.view[0], cam.aux[1], cam.up[1], cam.view[1], cam.aux[2], cam.up[2], cam.view[2]};
+        const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+        if (!(std::fabs(det) > 1e-300) || !std::isfinite(det)) { G.refused = true; return LGB_OK; }
+        const double id = 1.0 / det;
+        P.minv[0] = (m[4] * m[8] - m[5] * m[7]) * id; P.minv[1] = (m[2] * m[7] - m[1] * m[8]) * id; P.minv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+        P.minv[3] = (m[5] * m[6] - m[3] * m[8]) * id; P.minv[4] = (m[0] * m[8] - m[2] * m[6]) * id; P.minv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+        P.minv[6] = (m[3] * m[7] - m[4] * m[6]) * id; P.minv[7] = (m[1] * m[6] - m[0] * m[7]) * id; P.minv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+        for (int k = 0; k < 3; k++) P.origin[k] = cam.origin[k];
+        P.iph = cam.image_plane_height; P.ipw = cam.image_plane_height * ((double)w / (double)h); P.w = (double)w; P.h = (double)h;
+        if (!(P.iph != 0.0) || !std::isfinite(P.iph)) { G.refused = true; return LGB_OK; }
+        P.delta0 = std::min(0.5 * cam.sample_distance, (cam.root - 0.5) * cam.sample_distance);
+        P.delta1 = std::max(0.5 * cam.sample_distance, (cam.root - 0.5) * cam.sample_distance);
+        P.w_eps = 1e-6;
+        P.shift = 2;
+        if (const char* e = std::getenv("LGB_CAM_SHIFT")) P.shift = std::min(6, std::max(0, std::atoi(e)));
+        P.nx = ((w - 1) >> P.shift) + 1; P.ny = ((h - 1) >> P.shift) + 1;
+        P.large_cells = kGridLargeCells; P.large_cap = kGridLargeCap;
+        const size_t nc = (size_t)P.nx * P.ny, scan_bytes = scan_bytes_for(nc);
+        uint32_t* counts = nullptr; void* scan_tmp = nullptr; uint32_t* n_large_dev = nullptr;
+        CU(c, cudaMallocAsync((void**)&counts, (nc + 1) * 4, st));
+        CU(c, cudaMallocAsync(&scan_tmp, std::max<size_t>(scan_bytes, 16), st));
+        CU(c, cudaMallocAsync((void**)&n_large_dev, 4, st));
+        CU(c, cudaMallocAsync(&G.starts, (nc + 1) * 4, st));
+        CU(c, cudaMallocAsync(&G.large, sizeof(uint2) * kGridLargeCap, st));
+        uint32_t total = 0, n_large = 0;
+        CU(c, camgrid_count(S, P, counts, (uint32_t*)G.starts, scan_tmp, scan_bytes, (uint2*)G.large, n_large_dev, st, &total, &n_large));
+        if (n_large > kGridLargeCap) G.refused = true;
+        else {
+            CU(c, cudaMallocAsync(&G.entries, sizeof(uint2) * std::max<size_t>(total, 1), st));
+            CU(c, camgrid_fill(S, P, counts, (const uint32_t*)G.starts, (uint2*)G.entries, (uint2*)G.large, n_large, st));
+            G.valid = true; G.shift = P.shift; G.nx = P.nx; G.n_large = n_large; G.bytes = (nc + 1) * 4 + sizeof(uint2) * ((size_t)total + n_large);
+        }
+        cudaFreeAsync(counts, st); cudaFreeAsync(scan_tmp, st); cudaFreeAsync(n_large_dev, st);
+        G.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (getenv("LGB_TIMING")) fprintf(stderr, "[camera grid] %ux%u tiles of %u px: %u entries, %u large, %.2f ms (host clock, incl. one sync)%s\n", P.nx, P.ny, 1u << P.shift, total, n_large, G.build_ms, G.refused ? " REFUSED" : "");
+    }
+    if (G.valid) { W.cg_start = (const uint32_t*)G.starts; W.cg_entries = (const uint2*)G.entries; W.cg_large = (const uint2*)G.large; W.cg_n_large = G.n_large; W.cg_shift = G.shift; W.cg_nx = G.nx; }
+    return LGB_OK;
+}
+
 struct CaptureArgs {
     uint32_t w, h;
     uint32_t mode;               // 0 tiles, 1 stride subset
@@ -926,6 +1137,7 @@ struct CaptureArgs {
     void* d_film;                // device film or NULL (context film)
     cudaStream_t stream;
     bool want_li = false;        // aov: also the radiance of every sample
+    bool klog_no_camgrid = false;
     KernelLog* klog = nullptr;   // lgb_capture_profile: events and counter snapshots around every launch (one stream)
 };
 
@@ -996,8 +1208,8 @@ static int run_whitted_levels(lgb_ctx* c, lgb_scene* s, const DevOut& O0, uint64
         DevWave Vl = carve_wave(c->wave2.p, c->wave2_ctr.p, n, nl);
         if (l + 1 < S.recursion && !prepare_spawn(c, Vl, l + 1, n)) return fail(c, LGB_ERR_CUDA, "capture: out of device memory for a level of the specular ray trees");
         DevOut Ol{}; Ol.radiance = (double*)c->lvl_rad[l + 1].p;
-        CU(c, launch_level(S, s->cam, s->shade, Wl, Ol, Vl, c->sm_count, st));
-        *launches += 4 + S.n_lights;                                 // k_primary, k_setup, k_shadow x lights, k_shade; k_gather on the way back
+        CU(c, launch_level(S, s->cam, s->shade, Wl, Ol, Vl, c->sm_count, st, count ? (DevCounters*)c->counters.p : nullptr));
+        *launches += 4 + (S.grids ? 1 : S.n_lights);                 // k_primary, k_setup, k_shadow x lights (or k_gshadow), k_shade; k_gather on the way back
         *rays_traced += n_r + n_t;
         if (count) {                                                 // + the shadow rays of this level (lgb_stats.secondary_rays)
             CU(c, cudaMemcpyAsync(hctr.data(), c->wave2_ctr.p, kWaveCtrBytes, cudaMemcpyDeviceToHost, st));
@@ -1059,6 +1271,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         // automatic: where a bundle of >= 8 rays shares a traversal that is long enough to be worth sharing (measured: a loss on
         // scenes of a few dozen primitives, a gain on large ones)
         W.beams = (W.spp >= 4 && !S.instanced && (c->beams == 1 || (c->beams < 0 && W.spp >= 8 && S.n_nodes >= 1024u))) ? 1u : 0u;
+        if (!a.klog_no_camgrid) if (int rc = ensure_camgrid(c, s, a.w, a.h, total, W, st)) return rc;
         if (W.beams) {
             const uint64_t npx = std::max<uint64_t>(W.n_pixels, 1);
             CU(c, c->beam.reserve(npx * kBeamList * sizeof(uint2) + npx * 8));
@@ -1146,16 +1359,64 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         for (int k = 0; k < 3; k++) { stats->filter_tests[k] = hc.filter[k]; stats->exact_tests[k] = hc.exact[k]; }
         stats->stack_overflow = hc.stack_overflow;
         stats->beams = W.beams; stats->tie_retraces = tie_slots; stats->secondary_rays = hc.secondary_rays + level_rays;
-        stats->kernel_launches = total ? level_launches + (S.general ? (S.specular && S.recursion && !wf ? 5 : 4) : render_fused(W.spp) ? 3 : 4) + (W.beams ? 2 : 0) + s->dev.n_lights * (W.spp > 1 ? 3 : 1)
-                                         + ((W.beams && W.spp > 1 && !S.instanced) ? 2 * s->dev.n_lights : 0) : 0;      // k_sbeam + k_swalk per light
+        const uint32_t shadow_launches = (S.grids && !S.instanced) ? 1u                                                 // k_gshadow
+                                         : s->dev.n_lights * (W.spp > 1 ? 3 : 1) + ((W.beams && W.spp > 1 && !S.instanced) ? 2 * s->dev.n_lights : 0);      // + k_sbeam + k_swalk per light
+        stats->kernel_launches = total ? level_launches + (S.general ? (S.specular && S.recursion && !wf ? 5 : 4) : render_fused(W.spp) ? 3 : 4) + (W.beams ? 2 : 0) + shadow_launches - (S.n_lights ? 0 : 0) : 0;
         float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         stats->render_ms = ms; stats->total_ms = ms;
     }
     return LGB_OK;
 }
 
+// capture over a device group (lib.rs:55-104: one blocking call, every worker): device k of n renders the macro tiles of rank k
+// into the leader's film -- the peers' uchar4 stores cross NVLink while their other tiles are still being shaded, no collective
+// and no gather pass -- each on its own host thread (a capture holds short synchronisation points: tile-list upload, the
+// lazy-tree tie count, the statistics), and the call returns when every device's stream is drained.
+static int group_capture(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, void* film, lgb_stats* stats) {
+    const uint32_t n = 1 + (uint32_t)c->peers.size();
+    if (s->replicas.size() != c->peers.size()) return fail(c, LGB_ERR_INVALID, "capture: the scene was not created on this device group");
+    std::vector<int> rc(n, LGB_OK);
+    std::vector<lgb_stats> st(n);
+    std::vector<std::thread> workers;
+    for (uint32_t k = 1; k < n; k++)
+        workers.emplace_back([&, k] {
+            CaptureArgs a{w, h, 0, k, n, 0, 0, false, film, nullptr};
+            rc[k] = run_capture(c->peers[k - 1], s->replicas[k - 1], a, &st[k], true);
+        });
+    {
+        CaptureArgs a{w, h, 0, 0, n, 0, 0, false, film, nullptr};
+        rc[0] = run_capture(c, s, a, &st[0], true);
+    }
+    for (std::thread& t : workers) t.join();
+    cudaSetDevice(c->device);
+    for (uint32_t k = 1; k < n; k++) if (rc[k]) return fail(c, rc[k], "device " + std::to_string(c->peers[k - 1]->device) + ": " + c->peers[k - 1]->error);
+    if (rc[0]) return rc[0];
+    if (stats) {
+        *stats = st[0];
+        for (uint32_t k = 1; k < n; k++) {
+            const lgb_stats& o = st[k];
+            stats->primary_rays += o.primary_rays; stats->primary_hits += o.primary_hits; stats->shadow_rays += o.shadow_rays;
+            stats->shadow_rays_traced += o.shadow_rays_traced; stats->shadow_occluded += o.shadow_occluded; stats->shadow_cache_hits += o.shadow_cache_hits;
+            stats->node_tests += o.node_tests; stats->primary_node_tests += o.primary_node_tests; stats->secondary_rays += o.secondary_rays;
+            for (int t = 0; t < 3; t++) {
+                stats->exact_tests[t] += o.exact_tests[t]; stats->filter_tests[t] += o.filter_tests[t];
+                stats->primary_exact_tests[t] += o.primary_exact_tests[t]; stats->primary_filter_tests[t] += o.primary_filter_tests[t];
+            }
+            for (int t = 0; t < 6; t++) stats->kernel_ms[t] = std::max(stats->kernel_ms[t], o.kernel_ms[t]);
+            stats->render_ms = std::max(stats->render_ms, o.render_ms); stats->total_ms = std::max(stats->total_ms, o.total_ms);
+            stats->kernel_launches += o.kernel_launches; stats->stack_overflow |= o.stack_overflow; stats->tie_retraces += o.tie_retraces;
+        }
+    }
+    return LGB_OK;
+}
+
 int lgb_capture_device(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint32_t rank, uint32_t ranks, void* d_film, void* stream, lgb_stats* stats) {
     if (!d_film) return fail(c, LGB_ERR_INVALID, "lgb_capture_device: d_film is NULL");
+    if (c && !c->peers.empty() && ranks == 1) {              // device group: the whole frame, split over the group; blocking
+        if (stream) CU(c, cudaStreamSynchronize((cudaStream_t)stream));        // the caller's earlier work on the film (a clear) is done
+        lgb_stats local;
+        return group_capture(c, s, w, h, d_film, stats ? stats : &local);
+    }
     CaptureArgs a{w, h, 0, rank, ranks, 0, 0, false, d_film, (cudaStream_t)stream};
     return run_capture(c, s, a, stats, stats != nullptr);
 }
@@ -1171,8 +1432,17 @@ static int finish_host(lgb_ctx* c, const void* dev, void* host, size_t bytes, lg
 int lgb_capture(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint8_t* rgba, lgb_stats* stats) {
     if (!rgba) return fail(c, LGB_ERR_INVALID, "lgb_capture: rgba_out is NULL");
     lgb_stats local; lgb_stats* stp = stats ? stats : &local;
-    CaptureArgs a{w, h, 0, 0, 1, 0, 0, false, nullptr, nullptr};
-    int rc = run_capture(c, s, a, stp, true);
+    int rc;
+    if (c && !c->peers.empty()) {
+        if (w == 0 || h == 0 || (uint64_t)w * h >= (1ull << 32)) return fail(c, LGB_ERR_INVALID, "capture: bad film size");
+        CU(c, cudaSetDevice(c->device));
+        CU(c, c->film.reserve((size_t)w * h * 4));
+        CU(c, cudaEventRecord(c->ev0, c->stream));
+        rc = group_capture(c, s, w, h, c->film.p, stp);
+    } else {
+        CaptureArgs a{w, h, 0, 0, 1, 0, 0, false, nullptr, nullptr};
+        rc = run_capture(c, s, a, stp, true);
+    }
     if (rc) return rc;
     if (stp->stack_overflow) return fail(c, LGB_ERR_UNSUPPORTED, "traversal stack overflow");
     return finish_host(c, c->film.p, rgba, (size_t)w * h * 4, stp);

@@ -1319,6 +1319,60 @@ __global__ void __launch_bounds__(LGB_LEAFP_THREADS, 1024 / LGB_LEAFP_THREADS) k
     }
 }
 
+// ================================================================== primary rays through the camera grid (lgb_grid.cu)
+// One thread per sample slot: the pixel's tile lists every primitive one of its samples can see, nearest first; each gets the f32
+// filter + the reference's exact test (closest hit, reference-order ties as everywhere), and the walk stops at the first entry that
+// starts beyond the best hit.  No traversal, no per-ray stack, no fallback: the list is complete for every ray of the tile.
+#ifndef LGB_CPRIMARY_THREADS
+#define LGB_CPRIMARY_THREADS 128
+#endif
+template <bool STATS>
+__global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, 1024 / LGB_CPRIMARY_THREADS) k_cprimary(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
+    const uint64_t total = W.n_pixels * W.spp;
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    LocalCounters lc = {};
+    unsigned int hits = 0, primary = 0;
+    if (g < total) {
+        const uint32_t p = fdiv((uint32_t)g, W.fd_spp), s = (uint32_t)g - p * W.spp;
+        uint32_t x, y;
+        if (!slot_to_pixel(W, p, x, y)) { V.hit_t[g] = CUDART_INF; V.hit_ref[g] = kSlotUnused; }
+        else {
+            const Ray64 world = camera_ray(C, W, x, y, s);
+            Ray64 ray; RayF f; Trav T;
+            enter_root<false>(S, world, ray, f, T, CUDART_INF);
+            primary++;
+            const size_t cell = (size_t)(y >> W.cg_shift) * W.cg_nx + (size_t)(x >> W.cg_shift);
+            const uint32_t b = __ldg(W.cg_start + cell), e = __ldg(W.cg_start + cell + 1);
+            const float to_t = f.inv_len * (1.0f - 2e-6f);                   // an entry's distance from the eye -> a lower bound of its ray parameter
+            for (uint32_t i = b; i < e; i++) {
+                const uint2 r = __ldg(W.cg_entries + i);
+                if (__uint_as_float(r.y) * to_t > T.best_up) break;          // nearest first: nothing behind the best hit can beat it
+                leaf_prims<false, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, CUDART_INF, lc);
+            }
+            for (uint32_t i = 0; i < W.cg_n_large; i++) {
+                const uint2 r = __ldg(W.cg_large + i);
+                if (__uint_as_float(r.y) * to_t > T.best_up) break;
+                leaf_prims<false, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, CUDART_INF, lc);
+            }
+            const bool hit = T.best.ref != LGB_MISS;
+            V.hit_t[g] = hit ? T.best.t : CUDART_INF; V.hit_ref[g] = T.best.ref;
+            hits += hit ? 1u : 0u;
+            if (T.tied) { const uint32_t k = atomicAdd(V.tie_count, 1u); if (k < V.tie_cap) V.tie_list[k] = (uint32_t)g; }
+        }
+    }
+    if (O.counters) {
+        unsigned long long v0 = warp_sum(primary), v1 = warp_sum(hits);
+        if (lane == 0) { atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1); }
+        if (STATS) {
+            for (int k = 0; k < 3; k++) {
+                unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
+                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); atomicAdd(&O.counters->p_filter[k], a); atomicAdd(&O.counters->p_exact[k], b); }
+            }
+        }
+    }
+}
+
 template <bool ALL_SHADOWS, bool INST, bool RAYBUF = false>
 __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
     constexpr bool LEAN = !INST && !RAYBUF;          // camera rays of scenes without transformed aggregates: lean_surface
@@ -1339,7 +1393,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
                 if (O.aov_occl) O.aov_occl[gi] = 0;
             } else {
                 // glass and mirror: BSDF::f is zero whatever the light does (bxdf/mod.rs:172) -- no shadow ray, no shadow origin
-                if (!ALL_SHADOWS && S.specular && (material_flags(S, ref) & kMatSpecular)) { V.occl[g] = 0; ref_done = true; }
+                if (!ALL_SHADOWS && S.specular && (material_flags(S, ref) & kMatSpecular)) { V.occl[g] = 0; V.gate[g] = 0; ref_done = true; }
             }
             if (ref != LGB_MISS && !ref_done) {
                 live = true;
@@ -1379,10 +1433,12 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
                 }
                 need = ALL_SHADOWS ? (S.n_lights >= 32u ? 0xFFFFFFFFu : (1u << S.n_lights) - 1u) : gate;
                 V.occl[g] = 0;
-                if (LEAN) { V.gate[g] = gate; V.sflags[g] = (unsigned char)sflags; }
+                V.gate[g] = gate;
+                if (LEAN) V.sflags[g] = (unsigned char)sflags;
             }
         }
     }
+    if (S.grids) return;         // light grids (k_gshadow) read ps / gate by slot: no queues
     // compacted per-light shadow queues (A: anchor sample of the pixel, B: the others), block-ordered, all at once:
     // flag bit 2l = queue A of light l, bit 2l + 1 = queue B
     __shared__ MultiAppendScratch sc;
@@ -1630,6 +1686,84 @@ __global__ void __launch_bounds__(LGB_SWALK_THREADS, 1024 / LGB_SWALK_THREADS) k
     if (O.counters) {
         unsigned long long v = warp_sum(occluded);
         if (lane == 0 && v) atomicAdd(&O.counters->shadow_occluded, v);
+        if (STATS) {
+            for (int k = 0; k < 3; k++) {
+                unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
+                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); }
+            }
+        }
+    }
+}
+
+// ================================================================== shadow rays through the light grids (lgb_grid.cu)
+// One thread per sample slot, every light in turn: the ray's direction seen from the light selects ONE cell of that light's cube
+// map; its entries (nearest to the light first) and the light's few large primitives get the f32 filter + the reference's exact
+// test, any hit with t < 1 (light/point.rs:48-49), up to the first entry that starts beyond the ray's own length.
+#ifndef LGB_GSHADOW_MIN_BLOCKS
+#define LGB_GSHADOW_MIN_BLOCKS 4
+#endif
+template <bool STATS, bool ALL_SHADOWS>
+__global__ void __launch_bounds__(256, LGB_GSHADOW_MIN_BLOCKS) k_gshadow(DevScene S, DevWork W, DevOut O, DevWave V) {
+    const uint64_t total = W.n_pixels * W.spp;
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    LocalCounters lc = {};
+    unsigned traced = 0, occluded = 0;
+    if (g < total) {
+        const uint32_t ref = V.hit_ref[g];
+        uint32_t mask = 0;
+        if (ref != LGB_MISS && ref != kSlotUnused) mask = ALL_SHADOWS ? (S.n_lights >= 32u ? 0xFFFFFFFFu : (1u << S.n_lights) - 1u) : V.gate[g];
+        if (mask) {
+            Ray64 world;
+            world.o = d3(V.ps[3 * g], V.ps[3 * g + 1], V.ps[3 * g + 2]);
+            uint32_t occl = 0;
+            for (uint32_t l = 0; l < S.n_lights; l++) {
+                if (!((mask >> l) & 1u)) continue;
+                traced++;
+                const double* Lp = S.lights + 9 * (size_t)l;
+                world.d = d3(Lp[0], Lp[1], Lp[2]) - world.o;                      // light/point.rs:43-44
+                // the cell of the direction light -> surface: major axis a, u = d_b / |d_a|, v = d_c / |d_a| (as face_rect, lgb_grid.cu)
+                const double ax = fabs(world.d.x), ay = fabs(world.d.y), az = fabs(world.d.z);
+                const int a = ax >= ay ? (ax >= az ? 0 : 2) : (ay >= az ? 1 : 2);
+                const double da = -(a == 0 ? world.d.x : a == 1 ? world.d.y : world.d.z);
+                const double db = -(a == 0 ? world.d.y : a == 1 ? world.d.z : world.d.x), dc = -(a == 0 ? world.d.z : a == 1 ? world.d.x : world.d.y);
+                if (da == 0.0) continue;                                           // the light sits on the shadow origin: nothing lies between
+                const DevGrid* G = S.grids + l;
+                const uint32_t res = __ldg(&G->res), n_large = __ldg(&G->n_large);
+                const double inv = fast_rcp(fabs(da)), half = 0.5 * (double)res;
+                const int cu = min(max((int)floor(fma(db * inv, half, half)), 0), (int)res - 1);
+                const int cv = min(max((int)floor(fma(dc * inv, half, half)), 0), (int)res - 1);
+                const size_t cell = ((size_t)(2 * a + (da < 0.0 ? 1 : 0)) * res + (size_t)cv) * res + (size_t)cu;
+                const uint32_t* cs = G->cell_start;
+                const uint32_t b = __ldg(cs + cell), e = __ldg(cs + cell + 1);
+                Ray64 ray; RayF f; Trav T;
+                enter_root<false>(S, world, ray, f, T, 1.0);
+                const float dd = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
+                const float len_up = dd * f.inv_len * (1.0f + 1e-5f) + f.err;     // an entry that starts farther from the light than the ray does cannot block it
+                bool hit = false;
+                const uint2* en = G->entries;
+                for (uint32_t i = b; i < e && !hit; i++) {
+                    const uint2 r = __ldg(en + i);
+                    if (__uint_as_float(r.y) > len_up) break;
+                    hit = leaf_prims<true, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, 1.0, lc);
+                }
+                const uint2* lg = G->large;
+                for (uint32_t i = 0; i < n_large && !hit; i++) {
+                    const uint2 r = __ldg(lg + i);
+                    if (__uint_as_float(r.y) > len_up) break;
+                    hit = leaf_prims<true, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, 1.0, lc);
+                }
+                if (hit) { occl |= 1u << l; occluded++; }
+            }
+            V.occl[g] = occl;
+        }
+    }
+    if (O.counters) {
+        const unsigned long long v0 = warp_sum(traced), v1 = warp_sum(occluded);
+        if (lane == 0 && v0) {
+            if (W.mode == 3) atomicAdd(&O.counters->secondary_rays, v0);      // a level of the specular ray trees: lgb_stats.secondary_rays
+            else { atomicAdd(&O.counters->shadow_traced, v0); atomicAdd(&O.counters->shadow_occluded, v1); }
+        }
         if (STATS) {
             for (int k = 0; k < 3; k++) {
                 unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
@@ -2273,7 +2407,10 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
         } else if ((e = cudaMemsetAsync(V.work_counter, 0, 8, stream)) != cudaSuccess) return e;      // the fetch counter restarts for the listed slots
         const uint64_t work = W.slot_list ? W.n_list : total;
         const unsigned pb = (unsigned)std::min<uint64_t>((work + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, (uint64_t)sms * LGB_MIN_BLOCKS);
-        if (W.beams && W.spp >= 4 && !inst && !W.slot_list) {
+        if (W.cg_start && !inst && !W.slot_list) {
+            const unsigned cb = (unsigned)((total + LGB_CPRIMARY_THREADS - 1) / LGB_CPRIMARY_THREADS);
+            KL("k_cprimary", -1, stream, if (stats) k_cprimary<true><<<cb, LGB_CPRIMARY_THREADS, 0, stream>>>(S, C, W, O, V); else k_cprimary<false><<<cb, LGB_CPRIMARY_THREADS, 0, stream>>>(S, C, W, O, V));
+        } else if (W.beams && W.spp >= 4 && !inst && !W.slot_list) {
             // one bundle traversal per pixel, then every sample ray walks its pixel's leaf list; pixels whose bundle
             // reaches too many leaves go through the per-ray traversal (their slots are listed by k_leafp)
             const unsigned bb = (unsigned)((W.n_pixels + LGB_BEAM_THREADS - 1) / LGB_BEAM_THREADS), lb = (unsigned)((total + LGB_LEAFP_THREADS - 1) / LGB_LEAFP_THREADS);
@@ -2294,11 +2431,16 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     if (inst) KL("k_setup", -1, stream, if (all_shadows) k_setup<true, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V));
     else KL("k_setup", -1, stream, if (all_shadows) k_setup<true, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V));
     mark(2);
+    if (S.grids && !inst) {             // light grids: every shadow ray of the frame in one launch, no traversal (lgb_grid.cu)
+        if (stats) KL("k_gshadow", -1, stream, if (all_shadows) k_gshadow<true, true><<<blocks, 256, 0, stream>>>(S, W, O, V); else k_gshadow<true, false><<<blocks, 256, 0, stream>>>(S, W, O, V));
+        else KL("k_gshadow", -1, stream, if (all_shadows) k_gshadow<false, true><<<blocks, 256, 0, stream>>>(S, W, O, V); else k_gshadow<false, false><<<blocks, 256, 0, stream>>>(S, W, O, V));
+        mark(3);
+    }
     // per light: anchor rays (queue A), then the cached-occluder test of the rest (B -> C), then the survivors (queue C)
-    const int nside = (side && S.n_lights > 1) ? std::min<int>(side->n, (int)S.n_lights - 1) : 0;
+    const int nside = (side && S.n_lights > 1 && !S.grids) ? std::min<int>(side->n, (int)S.n_lights - 1) : 0;
     for (int k = 0; k < nside; k++) { cudaEventRecord(side->fork, stream); cudaStreamWaitEvent(side->s[k], side->fork, 0); }
     // (light by light on its lane: the shadow-beam lists of a lane are reused by its next light)
-    for (uint32_t l = 0; l < S.n_lights; l++) {
+    for (uint32_t l = 0; l < (S.grids && !inst ? 0u : S.n_lights); l++) {
         const int lane = nside ? (int)(l % (uint32_t)(nside + 1)) : 0;
         cudaStream_t ls = lane ? side->s[lane - 1] : stream;
         uint2* blist = lane ? V.beam_list2 : V.beam_list; uint32_t* bcount = lane ? V.beam_count2 : V.beam_count;
@@ -2352,7 +2494,7 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
 }
 #undef KL
 // One level of the specular ray trees: W.mode == 3, the rays in W.rays; radiance of every ray into O.radiance, specular hits into V.sec_list.
-cudaError_t launch_level(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O, const DevWave& V, int sms, cudaStream_t stream) {
+cudaError_t launch_level(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O, const DevWave& V, int sms, cudaStream_t stream, DevCounters* shadow_counters) {
     const uint64_t total = W.n_pixels;
     if (total == 0) return cudaSuccess;
     cudaError_t e;
@@ -2367,7 +2509,8 @@ cudaError_t launch_level(const DevScene& S, const DevCamera& C, const DevShade& 
     } else {
         k_primary<false, false, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V);
         k_setup<false, false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
-        for (uint32_t l = 0; l < S.n_lights; l++) k_shadow<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, kQueueA);
+        if (S.grids) { DevOut Os = O; Os.counters = shadow_counters; k_gshadow<false, false><<<blocks, 256, 0, stream>>>(S, W, Os, V); }
+        else for (uint32_t l = 0; l < S.n_lights; l++) k_shadow<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, kQueueA);
         k_shade<false, false, true, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
     }
     return cudaGetLastError();

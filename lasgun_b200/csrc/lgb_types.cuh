@@ -29,6 +29,16 @@ struct DevSpace {
     float err_abs; uint32_t pad[3];
 };
 
+// Light grid (lgb_grid.cu): cube map around a point light, 6 faces x res^2 cells; cell (face, v, u) lists the primitives whose
+// direction footprint seen from the light touches it as (type << 30 | index, lower bound of the distance from the light as float
+// bits), nearest first; `large`: the primitives with footprints of more than kGridLargeCells cells, tested by every ray.
+struct DevGrid {
+    const uint32_t* cell_start;   // 6 res^2 + 1
+    const uint2* entries;
+    const uint2* large;
+    uint32_t res, n_large;
+};
+
 // All pointers are device pointers.  Layout:
 //   nodes      4 x float4 per node: child0 {lo.xyz, hi.xyz}, child1 {lo.xyz, hi.xyz}, {child0, child1, -, -};
 //              boxes padded (conservative for f32 rays); child word = node index, or
@@ -61,6 +71,8 @@ struct DevScene {
     const DevSpace* spaces;       // instanced scenes only (n_spaces > 1 or a transformed root)
     const uint32_t* inst_space;   // leaf-ordered child-space ids (leaf type LGB_PRIM_INSTANCE)
     const uint32_t* sph_space; const uint32_t* cub_space; const uint32_t* tri_space;   // space of every primitive, leaf order
+    const DevGrid* grids;         // one per light, or NULL: shadow rays traverse the BVH (instanced or small scenes)
+    uint32_t n_sph, n_cub, n_tri; // primitives per type (the leaf-ordered arrays above)
     uint32_t prim_count;
     uint32_t rank_items;          // prim_count + n_spaces: stride of one octant's rank table
     uint32_t n_spaces;
@@ -106,6 +118,11 @@ struct DevWork {
     const uint32_t* n_list_dev;      // ... or as many as this device counter says (beam fallback)
     uint32_t compact_out;            // resolve writes film[slot] instead of film[y*w + x]
     uint32_t beams;                  // primary rays through pixel beams (k_beam / k_leafp) when spp >= 4
+    // camera grid (lgb_grid.cu): the primary rays of a perspective camera walk the primitive list of their pixel tile (k_cprimary)
+    const uint32_t* cg_start;        // NULL: no camera grid for this launch
+    const uint2* cg_entries;
+    const uint2* cg_large;
+    uint32_t cg_n_large, cg_shift, cg_nx;
     const double* rays;              // mode 3: origin + direction, 6 doubles per slot
     uint32_t depth;                  // mode 3: depth of these rays in integrate.rs:23's recursion (camera rays: 0)
     uint32_t hole_lo, hole_hi;       // mode 3: slots [hole_lo, hole_hi) hold no ray (reflected rays fill the level's slots from 0, transmitted ones from hole_hi)

@@ -63,3 +63,36 @@ def test_two_gpu_shared_film(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29631", str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.gpu
+def test_device_group_in_one_process():
+    """lgb_init_devices: one process, one blocking capture over every GPU of the box (the reference's own shape, lib.rs:55-104);
+    the film must equal the one-GPU film byte for byte, also for a lazy scene and through the host-pointer entry."""
+    import numpy as np
+    import torch
+    from lasgun_b200 import _native as N, scenes
+    n = torch.cuda.device_count()
+    single = N.Context(0)
+    group = N.Context(devices=list(range(n)))            # n == 1: a group of one must behave like lgb_init
+    assert group.n_devices == n and single.n_devices == 1
+    try:
+        for mk, lazy in ((lambda: scenes.mixed4k(mesh_n=80, nspheres=8000, res=(480, 270), supersampling=1), False),
+                         (lambda: scenes.mixed4k(mesh_n=200, nspheres=40000, res=(640, 360), supersampling=3), True),
+                         (lambda: scenes.simple("b", 2, 200), False)):
+            sc, (w, h) = mk()
+            host = N.HostScene(sc)
+            one = N.DeviceScene(single, N.FlatScene(host))
+            ref, st1 = one.capture(w, h)
+            one.destroy()
+            dev = N.DeviceScene(group, N.FlatScene(host, lazy=lazy))
+            for _ in range(2):
+                out, stn = dev.capture(w, h)
+                assert np.array_equal(out, ref)
+                assert stn["primary_rays"] == st1["primary_rays"] and stn["primary_hits"] == st1["primary_hits"]
+            film = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda:0")
+            dev.capture_device(w, h, film.data_ptr(), want_stats=True)
+            assert np.array_equal(film.cpu().numpy(), ref)
+            dev.destroy()
+    finally:
+        group.close(); single.close()
