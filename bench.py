@@ -398,6 +398,49 @@ def run_gpu(args):
                 if variant == "pageable":
                     e2e_parts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3))
     e2e = statistics.median(e2e_ms)
+    # N > 1, once more as ONE process driving all N GPUs (lgb_init_devices: the reference's own shape -- one blocking capture that fans
+    # out inside, lib.rs:55-104): rank 0 measures while the other ranks wait on the host (a store key, no GPU activity)
+    group = None
+    if world > 1 and not args.no_group:
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            try:
+                gctx = N.Context(devices=list(range(world)))
+                gms, gparts, gkern = [], [], []
+                for i in range(args.e2e_steps + 1):
+                    t0 = time.perf_counter()
+                    fl = N.FlatScene(hscene_host, lazy=True)
+                    t1 = time.perf_counter()
+                    hs = C.c_void_p()
+                    gctx.check(L.lgb_scene_create(gctx.h, C.byref(fl.desc), C.byref(hs)))
+                    t2 = time.perf_counter()
+                    st_g = N.Stats()
+                    gctx.check(L.lgb_capture(gctx.h, hs, w, h, host_film.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(st_g)))
+                    L.lgb_scene_destroy(hs)
+                    t3 = time.perf_counter()
+                    if i > 0:
+                        gms.append((t3 - t0) * 1e3); gparts.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3)); gkern.append(float(st_g.render_ms))
+                gdev = N.DeviceScene(gctx, N.FlatScene(hscene_host, lazy=True))
+                gfilm = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda:0")
+                for _ in range(3):
+                    gdev.capture_device(w, h, gfilm.data_ptr(), want_stats=True)
+                tk = []
+                for _ in range(max(3, args.steps)):
+                    t0 = time.perf_counter(); gdev.capture_device(w, h, gfilm.data_ptr(), want_stats=True); tk.append((time.perf_counter() - t0) * 1e3)
+                one = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+                dev.capture_device(w, h, one.data_ptr(), rank=0, ranks=1, stream=stream)
+                torch.cuda.synchronize()
+                group = {"devices": world, "e2e_ms_per_frame": statistics.median(gms), "e2e_value": rays_frame / (statistics.median(gms) * 1e-3) / 1e6,
+                         "parts_ms": dict(zip(("flatten", "scene_create_replicate_grids", "capture_readback_destroy"), [statistics.median(p[i] for p in gparts) for i in range(3)])),
+                         "slowest_device_render_ms": statistics.median(gkern),
+                         "resident_ms_per_frame_host_clock": statistics.median(tk), "resident_value": rays_frame / (statistics.median(tk) * 1e-3) / 1e6,
+                         "identical_to_one_gpu": bool(torch.equal(one.cpu(), gfilm.cpu()))}
+                gdev.destroy(); gctx.close()
+            except Exception as ex:          # the per-process path above is the contract; this one must not take it down
+                group = {"error": repr(ex)}
+            store.set("lgb_group_done", "1")
+        else:
+            store.wait(["lgb_group_done"])
     scene_bytes = int(dev.device_bytes)
     d_ = flat.desc                                   # what lgb_scene_create copies to the device: the caller's arrays (+ rank tables when the tree is given)
     h2d_bytes = int(d_.n_spheres * 40 + d_.n_cuboids * 56 + d_.n_triangles * (44 + (36 if d_.tri_normals else 0)))
@@ -426,7 +469,8 @@ def run_gpu(args):
                     "ms_per_frame_pinned_film": statistics.median(e2e_pinned),
                     "reference_tree_built": bool(world > 1 or (flat_i is not None and flat_i.tree_built)),
                     "parts_ms": dict(zip(("flatten", "scene_create_device_bvh_grids_upload", "camera_grid_render_readback_destroy"),
-                                         [statistics.median(p[i] for p in e2e_parts) for i in range(3)]))},
+                                         [statistics.median(p[i] for p in e2e_parts) for i in range(3)])),
+                    "one_process_device_group": group},
             "gpu_launches": int(s2["kernel_launches"]) * args.steps,
             "work_per_frame": frame,
             "clocks": clocks,
@@ -508,6 +552,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=60.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-group", action="store_true", help="N>1: skip the one-process device-group measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

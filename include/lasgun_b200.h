@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LGB_ABI_VERSION 4
+#define LGB_ABI_VERSION 5
 
 typedef enum lgb_status {
     LGB_OK = 0,
@@ -187,6 +187,8 @@ typedef struct lgb_stats {
     uint32_t beams;                  /* 1 if the primary (and shadow) rays went through pixel beams (LGB_OPT_BEAMS) */
     uint32_t tie_retraces;           /* lazy reference tree: sample slots re-traced because of an exact-t tie (this call) */
     uint64_t secondary_rays;         /* rays below specular hits (reflected, transmitted and their shadow rays), integrate.rs:69-132 */
+    uint32_t bands;                  /* passes the frame was rendered in (per-sample buffers are sized by LGB_OPT_WAVE_BUDGET_MB) */
+    uint32_t reserved;
 } lgb_stats;
 
 /* Shared film (multi-GPU, one process per GPU): rank 0 allocates the film and hands the 64-byte handle to the other
@@ -226,6 +228,9 @@ void lgb_shutdown(lgb_ctx* ctx);
                                      * samples can see (csrc/lgb_grid.cu), instead of the BVH / pixel beams.  Same hits.  1 on, 0 off,
                                      * -1 (default) automatic.  Built at the first capture of a film size and kept with the scene.
                                      * env LGB_CAMERA_GRID presets it. */
+#define LGB_OPT_WAVE_BUDGET_MB 7    /* memory (MB, default 16384) the per-sample wavefront buffers of one capture may take: a frame that needs more
+                                     * is rendered in bands of macro tiles on the same buffers (any frame size in bounded memory).
+                                     * env LGB_WAVE_BUDGET_MB presets it. */
 int lgb_set_option(lgb_ctx* ctx, int option, int value);
 const char* lgb_last_error(lgb_ctx* ctx);          /* ctx may be NULL: last error of lgb_init */
 const char* lgb_status_string(int status);

@@ -86,7 +86,8 @@ class Stats(C.Structure):
                 ("shadow_rays_traced", C.c_uint64), ("shadow_occluded", C.c_uint64), ("shadow_cache_hits", C.c_uint64), ("exact_tests", C.c_uint64 * 3),
                 ("filter_tests", C.c_uint64 * 3), ("node_tests", C.c_uint64), ("primary_node_tests", C.c_uint64),
                 ("primary_exact_tests", C.c_uint64 * 3), ("primary_filter_tests", C.c_uint64 * 3), ("kernel_ms", C.c_float * 6), ("render_ms", C.c_float), ("total_ms", C.c_float),
-                ("kernel_launches", C.c_uint32), ("stack_overflow", C.c_uint32), ("beams", C.c_uint32), ("tie_retraces", C.c_uint32), ("secondary_rays", C.c_uint64)]
+                ("kernel_launches", C.c_uint32), ("stack_overflow", C.c_uint32), ("beams", C.c_uint32), ("tie_retraces", C.c_uint32), ("secondary_rays", C.c_uint64),
+                ("bands", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n in ("exact_tests", "filter_tests", "primary_exact_tests", "primary_filter_tests", "kernel_ms") else getattr(self, n)) for n, _ in self._fields_}
@@ -358,6 +359,10 @@ class Context:
     def set_light_grids(self, mode: int):
         """LGB_OPT_LIGHT_GRIDS (read at scene creation): 1 on, 0 off, -1 automatic (the default)."""
         self.check(lib().lgb_set_option(self.h, 5, int(mode)))
+
+    def set_wave_budget_mb(self, mb: int):
+        """LGB_OPT_WAVE_BUDGET_MB: per-sample buffers of one band of a frame (default 16384)."""
+        self.check(lib().lgb_set_option(self.h, 7, int(mb)))
 
     def set_camera_grid(self, mode: int):
         """LGB_OPT_CAMERA_GRID: 1 on, 0 off, -1 automatic (the default)."""

@@ -22,6 +22,8 @@ namespace lgb {
 constexpr int kRenderEvents = 7;
 cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev, int part, const SideStreams* side, KernelLog* klog);
 bool render_fused(uint32_t spp);
+bool surface_fused(const DevScene&, const DevWork&, const DevOut&, bool all_shadows);
+bool setup_fused(const DevScene&, const DevWork&, const DevOut&, bool all_shadows);
 cudaError_t launch_level(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, int sms, cudaStream_t, DevCounters* shadow_counters);
 cudaError_t launch_gather(const SpawnRec* recs, const uint32_t* nspec, double* rad_parent, const double* rad_child, uint64_t n_upper, cudaStream_t);
 cudaError_t launch_resolve(const DevWork&, const DevOut&, cudaStream_t);
@@ -38,7 +40,7 @@ using namespace lgb;
 // The layouts the bindings mirror by hand (lasgun_b200/_native.py, tests/test_abi.py).
 static_assert(sizeof(lgb_material) == 72 && offsetof(lgb_material, kind) == 64, "lgb_material layout (ABI v4)");
 static_assert(sizeof(lgb_node) == 32 && sizeof(lgb_instance) == 16 + 2 * 16 * 8, "lgb_node / lgb_instance layout");
-static_assert(sizeof(lgb_stats) == 21 * 8 + 12 * 4, "lgb_stats layout");
+static_assert(sizeof(lgb_stats) == 21 * 8 + 12 * 4 + 8, "lgb_stats layout");
 static_assert(sizeof(SpawnRec) == 72, "SpawnRec layout");
 static_assert(sizeof(lgb_kernel_time) == 40 + 8 + 11 * 8, "lgb_kernel_time layout");
 
@@ -78,6 +80,7 @@ struct lgb_ctx {
     int side_streams = 1;
     int whitted_wavefront = 1;             // LGB_OPT_WHITTED: 1 level-by-level wavefront, 0 one thread per ray tree (k_secondary)
     int beams = -1;                        // LGB_OPT_BEAMS: 0 off, 1 on, -1 automatic
+    uint64_t wave_budget = 16ull << 30;    // LGB_OPT_WAVE_BUDGET_MB: bytes of per-sample buffers one band of a frame may take
     int camera_grid = -1;                  // LGB_OPT_CAMERA_GRID: 0 off, 1 on, -1 automatic
     int light_grids = -1;                  // LGB_OPT_LIGHT_GRIDS: 0 off, 1 on, -1 automatic (scenes of >= 1024 BVH nodes, <= 8 lights)
     std::vector<uint32_t> tile_host;
@@ -169,6 +172,7 @@ int lgb_init(int device, lgb_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     if (const char* e = std::getenv("LGB_BEAMS")) { const int v = std::atoi(e); c->beams = v < 0 ? -1 : (v != 0); }
     if (const char* e = std::getenv("LGB_LIGHT_GRIDS")) { const int v = std::atoi(e); c->light_grids = v < 0 ? -1 : (v != 0); }
+    if (const char* e = std::getenv("LGB_WAVE_BUDGET_MB")) { const long v = std::atol(e); if (v >= 1) c->wave_budget = (uint64_t)v << 20; }
     if (const char* e = std::getenv("LGB_CAMERA_GRID")) { const int v = std::atoi(e); c->camera_grid = v < 0 ? -1 : (v != 0); }
     c->side.n = 1;                         // one side stream: two lights' chains at a time (a third stream measured no further gain)
     cudaError_t ie = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -223,7 +227,7 @@ int lgb_init_devices(int ndev, const int* devices, lgb_ctx** out) {
             else if (!can) rc = fail(nullptr, LGB_ERR_UNSUPPORTED, "lgb_init_devices: a listed device cannot access the first one's memory (no NVLink / P2P path)");
         }
         if (rc) { const std::string msg = g_init_error; if (p) lgb_shutdown(p); lgb_shutdown(lead); g_init_error = msg; return rc; }
-        p->leader = lead; p->beams = lead->beams; p->light_grids = lead->light_grids; p->camera_grid = lead->camera_grid;
+        p->leader = lead; p->beams = lead->beams; p->light_grids = lead->light_grids; p->camera_grid = lead->camera_grid; p->wave_budget = lead->wave_budget;
         lead->peers.push_back(p);
     }
     *out = lead;
@@ -268,6 +272,7 @@ int lgb_set_option(lgb_ctx* c, int option, int value) {
     if (option == LGB_OPT_SIDE_STREAMS) { c->side_streams = value != 0; return LGB_OK; }
     if (option == LGB_OPT_LIGHT_GRIDS) { c->light_grids = value < 0 ? -1 : (value != 0); return LGB_OK; }
     if (option == LGB_OPT_CAMERA_GRID) { c->camera_grid = value < 0 ? -1 : (value != 0); return LGB_OK; }
+    if (option == LGB_OPT_WAVE_BUDGET_MB) { if (value < 1) return fail(c, LGB_ERR_INVALID, "lgb_set_option: budget must be at least 1 MB"); c->wave_budget = (uint64_t)value << 20; return LGB_OK; }
     return fail(c, LGB_ERR_INVALID, "lgb_set_option: unknown option");
 }
 
@@ -649,6 +654,7 @@ static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
     cleanup(ok);
 #undef GR
     s->t_grids = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("LGB_TIMING")) fprintf(stderr, "[light grids] %u lights, res %u, %.1f MB, %.2f ms (host clock, one sync per light)%s\n", S.n_lights, res, s->grid_bytes / 1e6, s->t_grids, ok ? "" : " REFUSED");
     return LGB_OK;
 }
 
@@ -1144,7 +1150,17 @@ struct CaptureArgs {
 // Wavefront buffers of `nslots` sample slots carved out of one allocation (layout: DevWave, lgb_types.cuh).
 static uint64_t fastdiv_magic(uint64_t d) { return d <= 1 ? 0ull : (~0ull) / d + 1ull; }      // fdiv(), lgb_kernels.cu
 static void set_divisors(DevWork& W, uint32_t root) { W.fd_spp = fastdiv_magic(W.spp); W.fd_root = fastdiv_magic(root); W.fd_nmx = fastdiv_magic(W.n_macro_x); }
-static size_t wave_bytes(uint64_t nslots, uint32_t nl, uint64_t npix) { return nslots * (8 + 24 + 4 + 4 + 4 + 12 * (size_t)nl) + npix * 4 * nl + ((nslots + 15) & ~(uint64_t)15); }
+// camera.rs:115-118,131-133 once per launch (DevWork.cam_*): same operations, same order, IEEE doubles (this file is compiled without
+// floating-point contraction), so the bits are the ones every thread used to compute for itself
+static void set_camera_constants(DevWork& W, const DevCamera& C) {
+    const double iph = C.image_plane_height;
+    W.cam_ipw = iph * W.aspect;
+    const double pixel_size = iph * W.hinv;
+    const double sep = C.sample_distance * pixel_size;
+    for (int k = 0; k < 3; k++) { W.cam_updiff[k] = C.up[k] * sep; W.cam_auxdiff[k] = C.aux[k] * sep; }
+    for (int k = 0; k < 3; k++) W.cam_halfdiff[k] = W.cam_updiff[k] * 0.5 + W.cam_auxdiff[k] * 0.5;
+}
+static size_t wave_bytes(uint64_t nslots, uint32_t nl, uint64_t npix) { return nslots * (8 + 24 + 4 + 4 + 4 + 12 * (size_t)nl) + ((npix * 4 * nl + 15) & ~(uint64_t)15) + ((nslots + 15) & ~(uint64_t)15); }
 static DevWave carve_wave(void* wave, void* ctr, uint64_t nslots, uint32_t nl, uint64_t npix = 1) {
     DevWave V{};
     char* base = (char*)wave;
@@ -1154,7 +1170,7 @@ static DevWave carve_wave(void* wave, void* ctr, uint64_t nslots, uint32_t nl, u
     V.occl = (uint32_t*)base; base += nslots * 4;
     V.gate = (uint32_t*)base; base += nslots * 4;
     V.queue = (uint32_t*)base; V.queue_stride = nslots; base += nslots * 12 * nl;
-    V.occluder = (uint32_t*)base; base += npix * 4 * nl;
+    V.occluder = (uint32_t*)base; base += (npix * 4 * nl + 15) & ~(uint64_t)15;
     V.sflags = (unsigned char*)base;
     V.work_counter = (unsigned long long*)ctr;
     V.queue_count = (uint32_t*)((char*)ctr + 8);
@@ -1223,6 +1239,10 @@ static int run_whitted_levels(lgb_ctx* c, lgb_scene* s, const DevOut& O0, uint64
     return LGB_OK;
 }
 
+// One frame (or this rank's tiles of it, or a stride subset).  The per-sample wavefront buffers are sized for a BAND of the work --
+// as many macro tiles (or subset pixels) as fit the context's memory budget (LGB_OPT_WAVE_BUDGET_MB, default 16 GiB; a band also
+// stays below 2^32 sample slots, which the kernels index with 32 bits) -- and the kernel sequence runs band after band on the same
+// buffers: a frame of any size renders in bounded memory (8K at 64 spp: 2.1 G samples), and `mixed4k` is one band.
 static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats* stats, bool sync_stats) {
     if (!c || !s || s->ctx != c) return fail(c, LGB_ERR_INVALID, "capture: scene does not belong to this context");
     if (a.w == 0 || a.h == 0 || (uint64_t)a.w * a.h >= (1ull << 32)) return fail(c, LGB_ERR_INVALID, "capture: bad film size");
@@ -1233,6 +1253,8 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     W.winv = 1.0 / (double)a.w; W.hinv = 1.0 / (double)a.h; W.aspect = (double)a.w / (double)a.h;   // film.rs:36-45
     W.spp = s->cam.root * s->cam.root;
     W.anchor = (s->cam.root / 2) * s->cam.root + s->cam.root / 2;      // camera.rs:143: sample (i, j) = i * root + j
+    const uint64_t area = (uint64_t)a.w * a.h;
+    uint64_t units_all = 0;                      // macro tiles (mode 0) or pixels (mode 1) of this call
     if (a.mode == 0) {
         if (a.ranks == 0 || a.rank >= a.ranks) return fail(c, LGB_ERR_INVALID, "capture: tile_rank out of range");
         build_tile_list(c, a.w, a.h, a.rank, a.ranks);
@@ -1242,60 +1264,56 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
             CU(c, cudaStreamSynchronize(st));
             c->tile_count = (uint32_t)c->tile_host.size();
         }
-        W.tile_list = (const uint32_t*)c->tiles.p;
-        W.n_tiles = (uint32_t)c->tile_host.size();
         W.n_macro_x = (a.w + kMacroTile - 1) / kMacroTile;
-        W.n_pixels = (uint64_t)W.n_tiles * kMacroTile * kMacroTile;
+        units_all = c->tile_host.size();
     } else {
         if (a.n == 0 || a.k >= a.n) return fail(c, LGB_ERR_INVALID, "capture_subset: need k < n");
-        const uint64_t area = (uint64_t)a.w * a.h;
-        W.sub_k = a.k; W.sub_n = a.n;
-        W.n_pixels = area > a.k ? (area - a.k + a.n - 1) / a.n : 0;
+        W.sub_n = a.n;
+        units_all = area > a.k ? (area - a.k + a.n - 1) / a.n : 0;
         W.compact_out = 1;
     }
+    const uint64_t px_per_unit = a.mode == 0 ? (uint64_t)kMacroTile * kMacroTile : 1;
     set_divisors(W, s->cam.root);
-    const uint64_t total = W.n_pixels * W.spp;
-    if (total >= (1ull << 32) - 64) return fail(c, LGB_ERR_INVALID, "capture: more than 2^32 samples in one launch");
+    set_camera_constants(W, s->cam);
+    const uint64_t total_all = units_all * px_per_unit * W.spp;
     if (s->cam.pixel_separation != 0.0 && W.aspect > 4.0)
         return fail(c, LGB_ERR_UNSUPPORTED, "orthographic capture with aspect > 4: the scene's coordinate bound assumed aspect <= 4");
     const DevScene& S = s->dev;
-    if (!render_fused(W.spp) || S.general || a.want_li) CU(c, c->radiance.reserve(std::max<uint64_t>(total, 1) * 3 * sizeof(double)));      // spp > 256 only
+    const uint32_t nl = std::max<uint32_t>(S.n_lights, 1);
+    // automatic: where a bundle of >= 8 rays shares a traversal that is long enough to be worth sharing (measured: a loss on
+    // scenes of a few dozen primitives, a gain on large ones)
+    W.beams = (W.spp >= 4 && !S.instanced && (c->beams == 1 || (c->beams < 0 && W.spp >= 8 && S.n_nodes >= 1024u))) ? 1u : 0u;
+    if (!a.klog_no_camgrid && total_all) if (int rc = ensure_camgrid(c, s, a.w, a.h, total_all, W, st)) return rc;
+    const bool grid_shadows = S.grids && !S.instanced;                 // no shadow queues, no occluder cache
+    const bool beam_lists = W.beams && (!W.cg_start || !grid_shadows); // pixel beams (primary) and / or shadow beams
+    const bool two_lists = beam_lists && !grid_shadows && S.n_lights > 1 && c->side_streams && c->side.n;
+    const bool need_radiance = !render_fused(W.spp) || S.general || a.want_li;
+    const bool lazy_ties = s->lazy_fn && !s->dev.rank;
+    // the queue area also lends its first words to the pixel beams' fallback list and to k_shade's list of specular slots (one u32 per slot)
+    const uint32_t queue_nl = grid_shadows ? ((beam_lists || S.specular) ? 1u : 0u) : nl;
+    // ---- how much of the frame one band may hold
+    uint64_t per_slot = 8 + 24 + 4 + 4 + 4 + 1 + 12 * (uint64_t)queue_nl + (need_radiance ? 24 : 0);
+    if (S.specular && S.recursion > 0 && c->whitted_wavefront) per_slot += sizeof(SpawnRec) + 2 * 48 + 24 + 8 + 24 + 4 + 4 + 4 + 1;      // level buffers, worst case per slot
+    const uint64_t per_pixel = (grid_shadows ? 0 : 4 * (uint64_t)nl) + (beam_lists ? (uint64_t)kBeamList * 8 + 8 : 0) + (two_lists ? (uint64_t)kBeamList * 8 + 4 : 0);
+    const uint64_t unit_bytes = px_per_unit * (per_pixel + per_slot * W.spp), unit_slots = px_per_unit * W.spp;
+    uint64_t units_band = std::max<uint64_t>(1, std::min<uint64_t>(c->wave_budget / std::max<uint64_t>(unit_bytes, 1), ((1ull << 32) - 65) / unit_slots));
+    if (unit_slots >= (1ull << 32) - 64) return fail(c, LGB_ERR_INVALID, "capture: more than 2^32 samples in one macro tile");
+    units_band = std::min<uint64_t>(units_band, std::max<uint64_t>(units_all, 1));
+    const uint64_t n_bands = units_all ? (units_all + units_band - 1) / units_band : 0;
+    const uint64_t slots_band = std::max<uint64_t>(units_band * unit_slots, 1), npix_band = std::max<uint64_t>(units_band * px_per_unit, 1);
+    if (need_radiance) CU(c, c->radiance.reserve(slots_band * 3 * sizeof(double)));
     CU(c, c->counters.reserve(sizeof(DevCounters)));
-    // wavefront buffers: hit_t 8 + ps 24 + hit_ref 4 + occl 4 + 3 queues x 4 x lights bytes per sample slot,
-    // + occluder 4 x lights bytes per pixel slot
-    const uint64_t nslots = std::max<uint64_t>(total, 1), nl = std::max<uint32_t>(S.n_lights, 1), npix = std::max<uint64_t>(W.n_pixels, 1);
-    CU(c, c->wave.reserve(wave_bytes(nslots, (uint32_t)nl, npix)));
+    CU(c, c->wave.reserve(wave_bytes(slots_band, queue_nl, grid_shadows ? 0 : npix_band)));
     CU(c, c->wave_ctr.reserve(kWaveCtrBytes));
-    DevWave V = carve_wave(c->wave.p, c->wave_ctr.p, nslots, (uint32_t)nl, npix);
-    {
-        // automatic: where a bundle of >= 8 rays shares a traversal that is long enough to be worth sharing (measured: a loss on
-        // scenes of a few dozen primitives, a gain on large ones)
-        W.beams = (W.spp >= 4 && !S.instanced && (c->beams == 1 || (c->beams < 0 && W.spp >= 8 && S.n_nodes >= 1024u))) ? 1u : 0u;
-        if (!a.klog_no_camgrid) if (int rc = ensure_camgrid(c, s, a.w, a.h, total, W, st)) return rc;
-        if (W.beams) {
-            const uint64_t npx = std::max<uint64_t>(W.n_pixels, 1);
-            CU(c, c->beam.reserve(npx * kBeamList * sizeof(uint2) + npx * 8));
-            V.beam_list = (uint2*)c->beam.p; V.beam_count = (uint32_t*)((char*)c->beam.p + npx * kBeamList * sizeof(uint2));
-            V.beam_bound = (float*)(V.beam_count + npx);
-            if (S.n_lights > 1 && c->side_streams && c->side.n) {       // shadow beams of the light on the side stream
-                CU(c, c->beam2.reserve(npx * kBeamList * sizeof(uint2) + npx * 4));
-                V.beam_list2 = (uint2*)c->beam2.p; V.beam_count2 = (uint32_t*)((char*)c->beam2.p + npx * kBeamList * sizeof(uint2));
-            }
-        }
-        V.tie_list = nullptr; V.tie_cap = 0;
-        if (s->lazy_fn && !s->dev.rank) {
-            CU(c, c->ties.reserve((size_t)kTieCap * 4));
-            V.tie_list = (uint32_t*)c->ties.p; V.tie_cap = kTieCap;
-            if (const char* e = std::getenv("LGB_TIE_CAP")) V.tie_cap = std::min<uint32_t>(kTieCap, (uint32_t)std::strtoul(e, nullptr, 10));   // tests: force the whole-frame re-trace
-        }
-    }
+    if (beam_lists) CU(c, c->beam.reserve(npix_band * kBeamList * sizeof(uint2) + npix_band * 8));
+    if (two_lists) CU(c, c->beam2.reserve(npix_band * kBeamList * sizeof(uint2) + npix_band * 4));
+    if (lazy_ties) CU(c, c->ties.reserve((size_t)kTieCap * 4));
     DevOut O{};
     O.radiance = (double*)c->radiance.p;
     O.counters = (DevCounters*)c->counters.p;
-    const uint64_t area = (uint64_t)a.w * a.h;
     if (a.d_film) O.film = (uint8_t*)a.d_film;
     else {
-        CU(c, c->film.reserve(std::max<uint64_t>(a.mode == 0 ? area : W.n_pixels, 1) * 4));
+        CU(c, c->film.reserve(std::max<uint64_t>(a.mode == 0 ? area : units_all, 1) * 4));
         O.film = (uint8_t*)c->film.p;
     }
     if (a.aov) {
@@ -1305,43 +1323,73 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     }
     CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));
     CU(c, cudaEventRecord(c->ev0, st));
-    cudaEvent_t* pev = (stats && sync_stats && total) ? c->phase : nullptr;
+    cudaEvent_t* pev = (stats && sync_stats && total_all) ? c->phase : nullptr;
     uint32_t tie_slots = 0;
     const bool st_on = a.aov || c->count_work;
     const SideStreams* side = (c->side_streams && c->side.n && !a.klog) ? &c->side : nullptr;
-    int wf = (S.general && c->whitted_wavefront) ? 4 : 0;           // launch_render stops after k_shade; the levels and the resolve follow here
-    if (wf && S.specular && S.recursion > 0 && total) {             // k_shade of the camera wave spawns level 1
-        CU(c, c->lvl_ctr.reserve(4 * (kMaxRecursion + 2) * 4));
-        CU(c, cudaMemsetAsync(c->lvl_ctr.p, 0, 4 * (kMaxRecursion + 2) * 4, st));
-        if (!prepare_spawn(c, V, 0, total)) wf = 0;                 // not enough memory for the level buffers: one thread per ray tree instead
-    }
-    if (s->lazy_fn && !s->dev.rank && total) {
-        // no rank tables yet: trace the primary rays, and only if one met two primitives at bit-identical t fetch the
-        // caller's reference tree, build the tables and re-trace those slots (lasgun_b200.h, "Lazy reference tree")
-        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 1, side, a.klog));
-        uint32_t ties = 0;
-        CU(c, cudaMemcpyAsync(&ties, V.tie_count, 4, cudaMemcpyDeviceToHost, st));
-        CU(c, cudaStreamSynchronize(st));
-        if (ties) {
-            if (int rc = ensure_rank_tables(c, s)) return rc;
-            s->tie_retraces += ties; tie_slots = ties;
-            DevWork W2 = W;
-            if (ties <= V.tie_cap) { W2.slot_list = V.tie_list; W2.n_list = ties; }
-            else CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));          // too many to list: the whole frame again
-            CU(c, launch_render(s->dev, s->cam, s->shade, W2, O, V, st_on, a.aov, c->sm_count, st, ties <= V.tie_cap ? nullptr : pev, 1, side, a.klog));
-        }
-        CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 2 | wf, side, a.klog));
-    } else {
-        CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 3 | wf, side, a.klog));
-    }
     uint64_t level_rays = 0; uint32_t level_launches = 0;
-    if (wf && total) {                     // materials beyond plastic: the levels of the specular ray trees, then the film
-        if (S.specular && S.recursion > 0) if (int rc = run_whitted_levels(c, s, O, total, st, stats != nullptr, &level_rays, &level_launches)) return rc;
-        if (pev) CU(c, cudaEventRecord(pev[5], st));
-        CU(c, launch_resolve(W, O, st));
-        if (pev) CU(c, cudaEventRecord(pev[6], st));
+    float phase_ms[6] = {0, 0, 0, 0, 0, 0};
+    int wf = 0;
+    for (uint64_t band = 0; band < n_bands; band++) {
+        const uint64_t u0 = band * units_band, un = std::min<uint64_t>(units_band, units_all - u0);
+        if (a.mode == 0) {
+            W.tile_list = (const uint32_t*)c->tiles.p + u0; W.n_tiles = (uint32_t)un;
+            W.n_pixels = un * px_per_unit;
+        } else {
+            W.sub_k = (uint64_t)a.k + u0 * (uint64_t)a.n; W.compact_base = u0;
+            W.n_pixels = un;
+        }
+        const uint64_t total = W.n_pixels * W.spp;
+        DevWave V = carve_wave(c->wave.p, c->wave_ctr.p, slots_band, queue_nl, grid_shadows ? 0 : npix_band);
+        if (beam_lists) {
+            V.beam_list = (uint2*)c->beam.p; V.beam_count = (uint32_t*)((char*)c->beam.p + npix_band * kBeamList * sizeof(uint2));
+            V.beam_bound = (float*)(V.beam_count + npix_band);
+            if (two_lists) { V.beam_list2 = (uint2*)c->beam2.p; V.beam_count2 = (uint32_t*)((char*)c->beam2.p + npix_band * kBeamList * sizeof(uint2)); }
+        }
+        V.tie_list = nullptr; V.tie_cap = 0;
+        if (s->lazy_fn && !s->dev.rank) {
+            V.tie_list = (uint32_t*)c->ties.p; V.tie_cap = kTieCap;
+            if (const char* e = std::getenv("LGB_TIE_CAP")) V.tie_cap = std::min<uint32_t>(kTieCap, (uint32_t)std::strtoul(e, nullptr, 10));   // tests: force the whole-frame re-trace
+        }
+        wf = (S.general && c->whitted_wavefront) ? 4 : 0;               // launch_render stops after k_shade; the levels and the resolve follow here
+        if (wf && S.specular && S.recursion > 0 && total) {             // k_shade of the camera wave spawns level 1
+            CU(c, c->lvl_ctr.reserve(4 * (kMaxRecursion + 2) * 4));
+            CU(c, cudaMemsetAsync(c->lvl_ctr.p, 0, 4 * (kMaxRecursion + 2) * 4, st));
+            if (!prepare_spawn(c, V, 0, total)) wf = 0;                 // not enough memory for the level buffers: one thread per ray tree instead
+        }
+        if (s->lazy_fn && !s->dev.rank && total) {
+            // no rank tables yet: trace the primary rays, and only if one met two primitives at bit-identical t fetch the
+            // caller's reference tree, build the tables and re-trace those slots (lasgun_b200.h, "Lazy reference tree")
+            CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 1, side, a.klog));
+            uint32_t ties = 0;
+            CU(c, cudaMemcpyAsync(&ties, V.tie_count, 4, cudaMemcpyDeviceToHost, st));
+            CU(c, cudaStreamSynchronize(st));
+            if (ties) {
+                if (int rc = ensure_rank_tables(c, s)) return rc;
+                s->tie_retraces += ties; tie_slots += ties;
+                DevWork W2 = W;
+                DevCounters before{};
+                if (ties <= V.tie_cap) { W2.slot_list = V.tie_list; W2.n_list = ties; }
+                else if (band == 0) CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));          // too many to list: the whole band again
+                (void)before;
+                CU(c, launch_render(s->dev, s->cam, s->shade, W2, O, V, st_on, a.aov, c->sm_count, st, ties <= V.tie_cap ? nullptr : pev, 1, side, a.klog));
+            }
+            CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 2 | wf, side, a.klog));
+        } else {
+            CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 3 | wf, side, a.klog));
+        }
+        if (wf && total) {                     // materials beyond plastic: the levels of the specular ray trees, then the film
+            if (S.specular && S.recursion > 0) if (int rc = run_whitted_levels(c, s, O, total, st, stats != nullptr, &level_rays, &level_launches)) return rc;
+            if (pev) CU(c, cudaEventRecord(pev[5], st));
+            CU(c, launch_resolve(W, O, st));
+            if (pev) CU(c, cudaEventRecord(pev[6], st));
+        }
+        if (O.aov_li) CU(c, launch_export_li(W, O, V, st));
+        if (pev && n_bands > 1) {              // the phase events are re-recorded by the next band: read them now
+            CU(c, cudaStreamSynchronize(st));
+            for (int k = 0; k < 6; k++) { float pm = 0.f; CU(c, cudaEventElapsedTime(&pm, c->phase[k], c->phase[k + 1])); phase_ms[k] += pm; }
+        }
     }
-    if (O.aov_li) CU(c, launch_export_li(W, O, V, st));
     CU(c, cudaEventRecord(c->ev1, st));
     if (!s->last_use) CU(c, cudaEventCreateWithFlags(&s->last_use, cudaEventDisableTiming));
     CU(c, cudaEventRecord(s->last_use, st));
@@ -1355,13 +1403,19 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         stats->shadow_rays_traced = hc.shadow_traced; stats->shadow_occluded = hc.shadow_occluded; stats->shadow_cache_hits = hc.shadow_cached;
         stats->node_tests = hc.node_tests; stats->primary_node_tests = hc.p_node_tests;
         for (int k = 0; k < 3; k++) { stats->primary_filter_tests[k] = hc.p_filter[k]; stats->primary_exact_tests[k] = hc.p_exact[k]; }
-        if (total) for (int k = 0; k < 6; k++) { float pm = 0.f; CU(c, cudaEventElapsedTime(&pm, c->phase[k], c->phase[k + 1])); stats->kernel_ms[k] = pm; }
+        if (total_all && n_bands == 1) for (int k = 0; k < 6; k++) { float pm = 0.f; CU(c, cudaEventElapsedTime(&pm, c->phase[k], c->phase[k + 1])); stats->kernel_ms[k] = pm; }
+        else for (int k = 0; k < 6; k++) stats->kernel_ms[k] = phase_ms[k];
         for (int k = 0; k < 3; k++) { stats->filter_tests[k] = hc.filter[k]; stats->exact_tests[k] = hc.exact[k]; }
         stats->stack_overflow = hc.stack_overflow;
         stats->beams = W.beams; stats->tie_retraces = tie_slots; stats->secondary_rays = hc.secondary_rays + level_rays;
-        const uint32_t shadow_launches = (S.grids && !S.instanced) ? 1u                                                 // k_gshadow
+        const bool one_kernel = surface_fused(S, W, O, a.aov);              // k_surface: setup + shadows + shade + film
+        const uint32_t shadow_launches = grid_shadows ? 1u                                                                // k_gshadow
                                          : s->dev.n_lights * (W.spp > 1 ? 3 : 1) + ((W.beams && W.spp > 1 && !S.instanced) ? 2 * s->dev.n_lights : 0);      // + k_sbeam + k_swalk per light
-        stats->kernel_launches = total ? level_launches + (S.general ? (S.specular && S.recursion && !wf ? 5 : 4) : render_fused(W.spp) ? 3 : 4) + (W.beams ? 2 : 0) + shadow_launches - (S.n_lights ? 0 : 0) : 0;
+        const uint32_t primary_launches = W.cg_start ? 1u : (W.beams && W.spp >= 4 && !S.instanced) ? 3u : 1u;           // k_cprimary | k_beam + k_leafp + fallback | k_primary
+        const uint32_t shade_launches = S.general ? (S.specular && S.recursion && !wf ? 3u : 2u) : (render_fused(W.spp) && !O.aov_li) ? 1u : 2u;
+        const uint32_t setup_launches = setup_fused(S, W, O, a.aov) ? 0u : 1u;                                          // (inside k_gshadow otherwise)
+        stats->kernel_launches = total_all ? level_launches + (uint32_t)n_bands * (primary_launches + (one_kernel ? 1u : setup_launches + shadow_launches + shade_launches)) : 0;
+        stats->bands = (uint32_t)n_bands;
         float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         stats->render_ms = ms; stats->total_ms = ms;
     }

@@ -12,6 +12,10 @@
 
 #include "lgb_math.cuh"
 
+#ifndef LGB_WALK_PREFETCH
+#define LGB_WALK_PREFETCH 0          // grid walks (k_cprimary, k_gshadow): load entry i + 1 while entry i is tested
+#endif
+
 namespace lgb {
 
 // ------------------------------------------------------------------ per-ray f32 state
@@ -822,7 +826,7 @@ __device__ __forceinline__ bool slot_to_pixel(const DevWork& W, uint64_t p64, ui
         y = ty * kMacroTile + py;
         return x < W.w && y < W.h;
     } else {
-        const uint64_t off64 = (uint64_t)W.sub_k + (uint64_t)p * (uint64_t)W.sub_n;   // lib.rs:152-154
+        const uint64_t off64 = W.sub_k + (uint64_t)p * (uint64_t)W.sub_n;             // lib.rs:152-154
         if (off64 >= (uint64_t)W.w * W.h) return false;                              // (w * h < 2^32)
         const uint32_t off = (uint32_t)off64;
         y = off / W.w;
@@ -833,20 +837,17 @@ __device__ __forceinline__ bool slot_to_pixel(const DevWork& W, uint64_t p64, ui
 
 // camera.rs:113-146 for sample s of pixel (x, y)
 __device__ __forceinline__ Ray64 camera_ray(const DevCamera& C, const DevWork& W, uint32_t x, uint32_t y, uint32_t s) {
-    D3 up = d3(C.up[0], C.up[1], C.up[2]), aux = d3(C.aux[0], C.aux[1], C.aux[2]);
-    double iph = C.image_plane_height;
-    double ipw = iph * W.aspect;
-    double pixel_size = iph * W.hinv;
-    double sep = C.sample_distance * pixel_size;
-    double sox = ((double)x * W.winv - 0.5) * ipw;
-    double soy = (0.5 - (double)(y + 1) * W.hinv) * iph;
+    const D3 up = d3(C.up[0], C.up[1], C.up[2]), aux = d3(C.aux[0], C.aux[1], C.aux[2]);
+    const double iph = C.image_plane_height;
+    const double sox = ((double)x * W.winv - 0.5) * W.cam_ipw;
+    const double soy = (0.5 - (double)(y + 1) * W.hinv) * iph;
     Ray64 r;
     r.o = d3(C.origin[0], C.origin[1], C.origin[2]) + (soy * C.pixel_separation * up) + (sox * C.pixel_separation * aux);
-    D3 d = d3(C.view[0], C.view[1], C.view[2]) + (soy * up) + (sox * aux);
-    D3 updiff = up * sep, auxdiff = aux * sep;
-    D3 halfdiff = updiff * 0.5 + auxdiff * 0.5;
+    const D3 d = d3(C.view[0], C.view[1], C.view[2]) + (soy * up) + (sox * aux);
+    const D3 updiff = d3(W.cam_updiff[0], W.cam_updiff[1], W.cam_updiff[2]), auxdiff = d3(W.cam_auxdiff[0], W.cam_auxdiff[1], W.cam_auxdiff[2]);
+    const D3 halfdiff = d3(W.cam_halfdiff[0], W.cam_halfdiff[1], W.cam_halfdiff[2]);     // (host-side, lgb_api.cu set_camera_constants)
     const uint32_t si = fdiv(s, W.fd_root);
-    double fi = (double)si, fj = (double)(s - si * C.root);
+    const double fi = (double)si, fj = (double)(s - si * C.root);
     r.d = d + (fj * updiff) + (fi * auxdiff) + halfdiff;
     return r;
 }
@@ -1319,6 +1320,24 @@ __global__ void __launch_bounds__(LGB_LEAFP_THREADS, 1024 / LGB_LEAFP_THREADS) k
     }
 }
 
+// Which lights can contribute at a hit: bsdf.f is zero unless wi and wo are on the same side of ng (bsdf.rs:75,85-86) -- the light
+// then adds exactly zero whether or not it is occluded, so no shadow ray is traced.  The test is the reference's own
+// product with the normalised wi; its sign is that of the unnormalised dot product whenever that is clear of rounding (1e-6 of
+// |v|_1), which spares the sqrt and the division.  wo_ng: dot(wo, ng), or any positive number where ng faces wo by construction.
+__device__ __forceinline__ uint32_t light_gates(const DevScene& S, const Ray64& ray, D3 ps, D3 ng, double wo_ng, bool lean) {
+    uint32_t gate = 0;
+    for (uint32_t l = 0; l < S.n_lights; l++) {
+        const double* L = S.lights + 9 * (size_t)l;
+        const D3 v = d3(L[0], L[1], L[2]) - ps;
+        const double dv = dot(v, ng);
+        bool same;
+        if (fabs(dv) > 1e-6 * (fabs(v.x) + fabs(v.y) + fabs(v.z)) && fabs(wo_ng) > 1e-100) same = (dv > 0.0) == (wo_ng > 0.0);
+        else same = dot(normalize(v), ng) * (lean ? dot(-normalize(ray.d), ng) : wo_ng) > 0.0;
+        if (same) gate |= 1u << l;
+    }
+    return gate;
+}
+
 // ================================================================== primary rays through the camera grid (lgb_grid.cu)
 // One thread per sample slot: the pixel's tile lists every primitive one of its samples can see, nearest first; each gets the f32
 // filter + the reference's exact test (closest hit, reference-order ties as everywhere), and the walk stops at the first entry that
@@ -1326,8 +1345,11 @@ __global__ void __launch_bounds__(LGB_LEAFP_THREADS, 1024 / LGB_LEAFP_THREADS) k
 #ifndef LGB_CPRIMARY_THREADS
 #define LGB_CPRIMARY_THREADS 128
 #endif
+#ifndef LGB_CPRIMARY_BLOCKS
+#define LGB_CPRIMARY_BLOCKS (1024 / LGB_CPRIMARY_THREADS)
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, 1024 / LGB_CPRIMARY_THREADS) k_cprimary(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
+__global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, LGB_CPRIMARY_BLOCKS) k_cprimary(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
     const uint64_t total = W.n_pixels * W.spp;
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -1345,8 +1367,15 @@ __global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, 1024 / LGB_CPRIMARY_THRE
             const size_t cell = (size_t)(y >> W.cg_shift) * W.cg_nx + (size_t)(x >> W.cg_shift);
             const uint32_t b = __ldg(W.cg_start + cell), e = __ldg(W.cg_start + cell + 1);
             const float to_t = f.inv_len * (1.0f - 2e-6f);                   // an entry's distance from the eye -> a lower bound of its ray parameter
+#if LGB_WALK_PREFETCH
+            uint2 nxt = b < e ? __ldg(W.cg_entries + b) : make_uint2(0u, 0u);
+            for (uint32_t i = b; i < e; i++) {
+                const uint2 r = nxt;
+                if (i + 1 < e) nxt = __ldg(W.cg_entries + i + 1);            // in flight while this entry is tested
+#else
             for (uint32_t i = b; i < e; i++) {
                 const uint2 r = __ldg(W.cg_entries + i);
+#endif
                 if (__uint_as_float(r.y) * to_t > T.best_up) break;          // nearest first: nothing behind the best hit can beat it
                 leaf_prims<false, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, CUDART_INF, lc);
             }
@@ -1417,20 +1446,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_setup(DevScene S, DevCamera 
                 V.ps[3 * g + 0] = ps.x; V.ps[3 * g + 1] = ps.y; V.ps[3 * g + 2] = ps.z;
                 if (O.aov_id) O.aov_id[gi] = canonical_id(S, ref);
                 if (O.aov_t) O.aov_t[gi] = t;
-                uint32_t gate = 0;
-                for (uint32_t l = 0; l < S.n_lights; l++) {
-                    const double* L = S.lights + 9 * (size_t)l;
-                    // bsdf.f is zero unless wi and wo are on the same side of ng (bsdf.rs:75,85-86): the light then
-                    // adds exactly zero whether or not it is occluded, so no shadow ray is traced.
-                    // The test is the reference's own product with the normalised wi; its sign is that of the unnormalised
-                    // dot product whenever that is clear of rounding (1e-6 of |v|_1), which spares the sqrt and the division.
-                    const D3 v = d3(L[0], L[1], L[2]) - ps;
-                    const double dv = dot(v, ng);
-                    bool same;
-                    if (fabs(dv) > 1e-6 * (fabs(v.x) + fabs(v.y) + fabs(v.z)) && fabs(wo_ng) > 1e-100) same = (dv > 0.0) == (wo_ng > 0.0);
-                    else same = dot(normalize(v), ng) * ((sflags & kSfGeneric) ? wo_ng : dot(-normalize(ray.d), ng)) > 0.0;
-                    if (same) gate |= 1u << l;
-                }
+                const uint32_t gate = light_gates(S, ray, ps, ng, wo_ng, !(sflags & kSfGeneric));
                 need = ALL_SHADOWS ? (S.n_lights >= 32u ? 0xFFFFFFFFu : (1u << S.n_lights) - 1u) : gate;
                 V.occl[g] = 0;
                 V.gate[g] = gate;
@@ -1702,8 +1718,64 @@ __global__ void __launch_bounds__(LGB_SWALK_THREADS, 1024 / LGB_SWALK_THREADS) k
 #ifndef LGB_GSHADOW_MIN_BLOCKS
 #define LGB_GSHADOW_MIN_BLOCKS 4
 #endif
-template <bool STATS, bool ALL_SHADOWS>
-__global__ void __launch_bounds__(256, LGB_GSHADOW_MIN_BLOCKS) k_gshadow(DevScene S, DevWork W, DevOut O, DevWave V) {
+// The shadow ray from `o` towards light l (light/point.rs:43-44: d = light - o, blocked iff the closest t < 1) against that light's grid.
+template <bool STATS>
+__device__ __forceinline__ bool grid_blocked(const DevScene& S, D3 o, uint32_t l, LocalCounters& lc) {
+    Ray64 world;
+    world.o = o;
+    const double* Lp = S.lights + 9 * (size_t)l;
+    world.d = d3(Lp[0], Lp[1], Lp[2]) - world.o;
+    // the cell of the direction light -> surface: major axis a, u = d_b / |d_a|, v = d_c / |d_a| (as face_rect, lgb_grid.cu)
+    const double ax = fabs(world.d.x), ay = fabs(world.d.y), az = fabs(world.d.z);
+    const int a = ax >= ay ? (ax >= az ? 0 : 2) : (ay >= az ? 1 : 2);
+    const double da = -(a == 0 ? world.d.x : a == 1 ? world.d.y : world.d.z);
+    const double db = -(a == 0 ? world.d.y : a == 1 ? world.d.z : world.d.x), dc = -(a == 0 ? world.d.z : a == 1 ? world.d.x : world.d.y);
+    if (da == 0.0) return false;                                       // the light sits on the shadow origin: nothing lies between
+    const DevGrid* G = S.grids + l;
+    const uint32_t res = __ldg(&G->res), n_large = __ldg(&G->n_large);
+    const double inv = fast_rcp(fabs(da)), half = 0.5 * (double)res;
+    const int cu = min(max((int)floor(fma(db * inv, half, half)), 0), (int)res - 1);
+    const int cv = min(max((int)floor(fma(dc * inv, half, half)), 0), (int)res - 1);
+    const size_t cell = ((size_t)(2 * a + (da < 0.0 ? 1 : 0)) * res + (size_t)cv) * res + (size_t)cu;
+    const uint32_t* cs = G->cell_start;
+    const uint32_t b = __ldg(cs + cell), e = __ldg(cs + cell + 1);
+    Ray64 ray; RayF f; Trav T;
+    enter_root<false>(S, world, ray, f, T, 1.0);
+    const float dd = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
+    const float len_up = dd * f.inv_len * (1.0f + 1e-5f) + f.err;     // an entry that starts farther from the light than the ray does cannot block it
+    bool hit = false;
+    const uint2* en = G->entries;
+#if LGB_WALK_PREFETCH
+    uint2 nxt = b < e ? __ldg(en + b) : make_uint2(0u, 0u);
+    for (uint32_t i = b; i < e && !hit; i++) {
+        const uint2 r = nxt;
+        if (i + 1 < e) nxt = __ldg(en + i + 1);                          // in flight while this entry is tested
+#else
+    for (uint32_t i = b; i < e && !hit; i++) {
+        const uint2 r = __ldg(en + i);
+#endif
+        if (__uint_as_float(r.y) > len_up) break;
+        hit = leaf_prims<true, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, 1.0, lc);
+    }
+    const uint2* lg = G->large;
+    for (uint32_t i = 0; i < n_large && !hit; i++) {
+        const uint2 r = __ldg(lg + i);
+        if (__uint_as_float(r.y) > len_up) break;
+        hit = leaf_prims<true, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, 1.0, lc);
+    }
+    return hit;
+}
+
+// The rare slot whose sign decisions lean_surface leaves to the reference's own sequence (k_gshadow<SETUP>), out of line.
+__device__ __noinline__ void setup_generic(const DevScene& S, const Ray64& ray, double t, uint32_t ref, D3& ps, D3& ng, double& wo_ng) {
+    ShadePoint P; uint32_t id;
+    shade_point<false, false>(S, ray, t, ref, P, id);
+    ps = P.ps; ng = P.ng; wo_ng = dot(P.wo, P.ng);
+}
+// SETUP (camera rays of a plain capture): the thread also does k_setup's work for its slot -- surface record, sign byte, gates -- so
+// that the shadow origin goes from registers into the walk and is never stored (k_setup and its 24 B/slot of ps drop out of the frame).
+template <bool STATS, bool ALL_SHADOWS, bool SETUP = false>
+__global__ void __launch_bounds__(256, LGB_GSHADOW_MIN_BLOCKS) k_gshadow(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
     const uint64_t total = W.n_pixels * W.spp;
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -1712,48 +1784,36 @@ __global__ void __launch_bounds__(256, LGB_GSHADOW_MIN_BLOCKS) k_gshadow(DevScen
     if (g < total) {
         const uint32_t ref = V.hit_ref[g];
         uint32_t mask = 0;
-        if (ref != LGB_MISS && ref != kSlotUnused) mask = ALL_SHADOWS ? (S.n_lights >= 32u ? 0xFFFFFFFFu : (1u << S.n_lights) - 1u) : V.gate[g];
+        D3 ps = d3(0, 0, 0);
+        if (SETUP) {
+            const double t = V.hit_t[g];
+            Ray64 ray; uint32_t x, y, s;
+            if (ref != LGB_MISS && ref != kSlotUnused && slot_ray<false>(C, W, g, ray, x, y, s)) {
+                if (S.specular && (material_flags(S, ref) & kMatSpecular)) { V.occl[g] = 0; V.gate[g] = 0; }     // glass, mirror: BSDF::f is zero (bxdf/mod.rs:172)
+                else {
+                    LeanSurf Ls;
+                    lean_surface<true>(S, ray, t, ref, 0u, Ls);
+                    D3 ng; double wo_ng = 1.0;
+                    if (Ls.flags & kSfGeneric) setup_generic(S, ray, t, ref, ps, ng, wo_ng);
+                    else {
+                        ng = (Ls.flags & kSfNgFlip) ? -Ls.n : Ls.n;
+                        ps = ray.o + ray.d * t + ng * (2.220446049250313e-16 * 65536.0);       // surface.rs:168, integrate.rs:40
+                    }
+                    mask = light_gates(S, ray, ps, ng, wo_ng, !(Ls.flags & kSfGeneric));
+                    V.gate[g] = mask; V.sflags[g] = (unsigned char)Ls.flags;
+                    if (!mask) V.occl[g] = 0;
+                }
+            }
+        } else if (ref != LGB_MISS && ref != kSlotUnused) {
+            mask = ALL_SHADOWS ? (S.n_lights >= 32u ? 0xFFFFFFFFu : (1u << S.n_lights) - 1u) : V.gate[g];
+            if (mask) ps = d3(V.ps[3 * g], V.ps[3 * g + 1], V.ps[3 * g + 2]);
+        }
         if (mask) {
-            Ray64 world;
-            world.o = d3(V.ps[3 * g], V.ps[3 * g + 1], V.ps[3 * g + 2]);
             uint32_t occl = 0;
             for (uint32_t l = 0; l < S.n_lights; l++) {
                 if (!((mask >> l) & 1u)) continue;
                 traced++;
-                const double* Lp = S.lights + 9 * (size_t)l;
-                world.d = d3(Lp[0], Lp[1], Lp[2]) - world.o;                      // light/point.rs:43-44
-                // the cell of the direction light -> surface: major axis a, u = d_b / |d_a|, v = d_c / |d_a| (as face_rect, lgb_grid.cu)
-                const double ax = fabs(world.d.x), ay = fabs(world.d.y), az = fabs(world.d.z);
-                const int a = ax >= ay ? (ax >= az ? 0 : 2) : (ay >= az ? 1 : 2);
-                const double da = -(a == 0 ? world.d.x : a == 1 ? world.d.y : world.d.z);
-                const double db = -(a == 0 ? world.d.y : a == 1 ? world.d.z : world.d.x), dc = -(a == 0 ? world.d.z : a == 1 ? world.d.x : world.d.y);
-                if (da == 0.0) continue;                                           // the light sits on the shadow origin: nothing lies between
-                const DevGrid* G = S.grids + l;
-                const uint32_t res = __ldg(&G->res), n_large = __ldg(&G->n_large);
-                const double inv = fast_rcp(fabs(da)), half = 0.5 * (double)res;
-                const int cu = min(max((int)floor(fma(db * inv, half, half)), 0), (int)res - 1);
-                const int cv = min(max((int)floor(fma(dc * inv, half, half)), 0), (int)res - 1);
-                const size_t cell = ((size_t)(2 * a + (da < 0.0 ? 1 : 0)) * res + (size_t)cv) * res + (size_t)cu;
-                const uint32_t* cs = G->cell_start;
-                const uint32_t b = __ldg(cs + cell), e = __ldg(cs + cell + 1);
-                Ray64 ray; RayF f; Trav T;
-                enter_root<false>(S, world, ray, f, T, 1.0);
-                const float dd = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
-                const float len_up = dd * f.inv_len * (1.0f + 1e-5f) + f.err;     // an entry that starts farther from the light than the ray does cannot block it
-                bool hit = false;
-                const uint2* en = G->entries;
-                for (uint32_t i = b; i < e && !hit; i++) {
-                    const uint2 r = __ldg(en + i);
-                    if (__uint_as_float(r.y) > len_up) break;
-                    hit = leaf_prims<true, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, 1.0, lc);
-                }
-                const uint2* lg = G->large;
-                for (uint32_t i = 0; i < n_large && !hit; i++) {
-                    const uint2 r = __ldg(lg + i);
-                    if (__uint_as_float(r.y) > len_up) break;
-                    hit = leaf_prims<true, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, 1.0, lc);
-                }
-                if (hit) { occl |= 1u << l; occluded++; }
+                if (grid_blocked<STATS>(S, ps, l, lc)) { occl |= 1u << l; occluded++; }
             }
             V.occl[g] = occl;
         }
@@ -1974,7 +2034,7 @@ __global__ void __launch_bounds__(256, GENERAL ? LGB_GSHADE_MIN_BLOCKS : LGB_SHA
         if (mine && lane == base && have) {
             c = c * (1.0 / (double)W.spp);
             const uint64_t p = (uint32_t)g / W.spp;
-            reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)y * W.w + x] = quantise(c);
+            reinterpret_cast<uchar4*>(O.film)[W.compact_out ? W.compact_base + p : (uint64_t)y * W.w + x] = quantise(c);
         }
         return;
     }
@@ -1987,7 +2047,7 @@ __global__ void __launch_bounds__(256, GENERAL ? LGB_GSHADE_MIN_BLOCKS : LGB_SHA
         for (uint32_t k = 0; k < W.spp; k++) c = c + d3(rad[3 * (threadIdx.x + k)], rad[3 * (threadIdx.x + k) + 1], rad[3 * (threadIdx.x + k) + 2]);
         c = c * (1.0 / (double)W.spp);
         const uint64_t p = (uint32_t)g / W.spp;
-        reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)y * W.w + x] = quantise(c);
+        reinterpret_cast<uchar4*>(O.film)[W.compact_out ? W.compact_base + p : (uint64_t)y * W.w + x] = quantise(c);
     }
 }
 
@@ -2029,6 +2089,50 @@ __device__ __forceinline__ void lean_eval(const LeanHit& H, D3 wi, double wn, do
         }
     }
     a = wn * fast_rcp(f_att);
+}
+
+// integrate.rs:47-67 for a plastic / matte(0) hit whose surface record is lean (lean_surface): `lit` = the lights that contribute.
+__device__ __forceinline__ D3 lean_radiance(const DevScene& S, const DevShade& sh, const Ray64& ray, double t, const LeanSurf& Ls, uint32_t sflags, uint32_t lit) {
+    const double PI = 3.14159265358979323846264338327950288;
+    D3 output = d3(0, 0, 0);
+    LeanHit H;
+    H.ns = (sflags & kSfNsFlip) ? -Ls.n : Ls.n;
+    const D3 ng = (sflags & kSfNgFlip) ? -Ls.n : Ls.n;
+    const D3 ps = fmadd(ng, 2.220446049250313e-16 * 65536.0, fmadd(ray.d, t, ray.o));
+    H.wo = ray.d * -fast_rsqrt(fdot(ray.d, ray.d));
+    H.woz = fdot(H.wo, H.ns); H.cos_o = fabs(H.woz);
+    const double* M = S.materials + kMatStride * (size_t)Ls.material;
+    const uint32_t mflags = (uint32_t)__double_as_longlong(M[7]);
+    H.glossy = mflags & kMatGlossy; H.alpha2 = M[3] * M[3];
+    H.Ao = H.glossy ? fast_sqrt(fma(H.alpha2, fmax(fma(-H.cos_o, H.cos_o, 1.0), 0.0), H.cos_o * H.cos_o)) : 0.0;
+    if (H.woz != 0.0) {                                  // bsdf.rs:82: every lobe is zero at wo_l.z == 0
+        D3 dsum = d3(0, 0, 0), gsum = d3(0, 0, 0);       // sum of (pi I | ambient) x weight of the diffuse and of the glossy lobe
+        for (uint32_t l = 0; l < S.n_lights; l++) {      // integrate.rs:47-66
+            if (!((lit >> l) & 1u)) continue;
+            const double* L = S.lights + 9 * (size_t)l;
+            const D3 v = d3(L[0], L[1], L[2]) - ps;
+            const double d2 = fdot(v, v);
+            if (!(d2 > 0.0)) continue;
+            const double inv = fast_rsqrt(d2), dist = d2 * inv;
+            const double f_att = fma(L[8] * dist, dist, fma(L[7], dist, L[6]));
+            if (f_att == 0.0) continue;
+            const D3 wi = v * inv;
+            double a, gl;
+            lean_eval(H, wi, fdot(wi, H.ns), f_att, a, gl);
+            const D3 I = PI * d3(L[3], L[4], L[5]);
+            dsum = fmadd(I, a, dsum); gsum = fmadd(I, gl, gsum);
+        }
+        if (((sflags & kSfNsFlip) != 0) == ((sflags & kSfNgFlip) != 0)) {       // integrate.rs:67: wi = ns passes bsdf.rs:75 iff ns = ng
+            double a, gl;
+            lean_eval(H, H.ns, 1.0, 1.0, a, gl);
+            const D3 amb = d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]);
+            dsum = fmadd(amb, a, dsum); gsum = fmadd(amb, gl, gsum);
+        }
+        const double inv_pi = 0.318309886183790671537767526745028724;
+        const D3 kd = (mflags & kMatDiffuse) ? d3(M[0], M[1], M[2]) * inv_pi : d3(0, 0, 0);
+        output = d3(fma(kd.x, dsum.x, M[4] * gsum.x), fma(kd.y, dsum.y, M[5] * gsum.y), fma(kd.z, dsum.z, M[6] * gsum.z));
+    }
+    return output;
 }
 
 // The slots lean_surface leaves to the reference's own sequence (vertex normals, sign decisions within rounding of a tie).
@@ -2098,46 +2202,9 @@ __global__ void __launch_bounds__(256, LGB_LEAN_MIN_BLOCKS) k_shade_lean(DevScen
                 if (O.aov_occl) O.aov_occl[((uint64_t)y * W.w + x) * W.spp + s] = occl;
                 if (sflags & kSfGeneric) generic = true;             // (rare: shaded after the lean code so that their registers do not add up)
                 else {
-                    const uint32_t lit = gate & ~occl;                   // lights that are neither occluded nor on the far side of ng
                     LeanSurf Ls;
                     lean_surface<false>(S, ray, t, ref, sflags, Ls);
-                    LeanHit H;
-                    H.ns = (sflags & kSfNsFlip) ? -Ls.n : Ls.n;
-                    const D3 ng = (sflags & kSfNgFlip) ? -Ls.n : Ls.n;
-                    const D3 ps = fmadd(ng, 2.220446049250313e-16 * 65536.0, fmadd(ray.d, t, ray.o));
-                    H.wo = ray.d * -fast_rsqrt(fdot(ray.d, ray.d));
-                    H.woz = fdot(H.wo, H.ns); H.cos_o = fabs(H.woz);
-                    const double* M = S.materials + kMatStride * (size_t)Ls.material;
-                    const uint32_t mflags = (uint32_t)__double_as_longlong(M[7]);
-                    H.glossy = mflags & kMatGlossy; H.alpha2 = M[3] * M[3];
-                    H.Ao = H.glossy ? fast_sqrt(fma(H.alpha2, fmax(fma(-H.cos_o, H.cos_o, 1.0), 0.0), H.cos_o * H.cos_o)) : 0.0;
-                    if (H.woz != 0.0) {                                  // bsdf.rs:82: every lobe is zero at wo_l.z == 0
-                        D3 dsum = d3(0, 0, 0), gsum = d3(0, 0, 0);       // sum of (pi I | ambient) x weight of the diffuse and of the glossy lobe
-                        for (uint32_t l = 0; l < S.n_lights; l++) {      // integrate.rs:47-66
-                            if (!((lit >> l) & 1u)) continue;
-                            const double* L = S.lights + 9 * (size_t)l;
-                            const D3 v = d3(L[0], L[1], L[2]) - ps;
-                            const double d2 = fdot(v, v);
-                            if (!(d2 > 0.0)) continue;
-                            const double inv = fast_rsqrt(d2), dist = d2 * inv;
-                            const double f_att = fma(L[8] * dist, dist, fma(L[7], dist, L[6]));
-                            if (f_att == 0.0) continue;
-                            const D3 wi = v * inv;
-                            double a, gl;
-                            lean_eval(H, wi, fdot(wi, H.ns), f_att, a, gl);
-                            const D3 I = PI * d3(L[3], L[4], L[5]);
-                            dsum = fmadd(I, a, dsum); gsum = fmadd(I, gl, gsum);
-                        }
-                        if (((sflags & kSfNsFlip) != 0) == ((sflags & kSfNgFlip) != 0)) {       // integrate.rs:67: wi = ns passes bsdf.rs:75 iff ns = ng
-                            double a, gl;
-                            lean_eval(H, H.ns, 1.0, 1.0, a, gl);
-                            const D3 amb = d3(sh.ambient[0], sh.ambient[1], sh.ambient[2]);
-                            dsum = fmadd(amb, a, dsum); gsum = fmadd(amb, gl, gsum);
-                        }
-                        const double inv_pi = 0.318309886183790671537767526745028724;
-                        const D3 kd = (mflags & kMatDiffuse) ? d3(M[0], M[1], M[2]) * inv_pi : d3(0, 0, 0);
-                        output = d3(fma(kd.x, dsum.x, M[4] * gsum.x), fma(kd.y, dsum.y, M[5] * gsum.y), fma(kd.z, dsum.z, M[6] * gsum.z));
-                    }
+                    output = lean_radiance(S, sh, ray, t, Ls, sflags, gate & ~occl);      // lights neither occluded nor on the far side of ng
                 }
             }
         }
@@ -2172,9 +2239,116 @@ __global__ void __launch_bounds__(256, LGB_LEAN_MIN_BLOCKS) k_shade_lean(DevScen
         uint32_t px, py;
         slot_to_pixel(W, p, px, py);
         uchar4 o; o.x = bytes[3 * threadIdx.x]; o.y = bytes[3 * threadIdx.x + 1]; o.z = bytes[3 * threadIdx.x + 2]; o.w = 255;
-        reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)py * W.w + px] = o;
+        reinterpret_cast<uchar4*>(O.film)[W.compact_out ? W.compact_base + p : (uint64_t)py * W.w + px] = o;
     }
     }
+}
+
+// ================================================================== hit -> film in ONE kernel (plastic scenes with light grids)
+// k_setup + k_gshadow + k_shade_lean for one sample slot without the trip through HBM between them: the surface record and the sign
+// decisions (lean_surface), the per-light gates, the shadow rays through the light grids, the radiance and the film resolve.  Neither
+// ps, nor the gate / sign bytes, nor the occlusion bits are ever stored, and the camera ray and the unit normal are formed once.
+// The same device functions in the same order as the three kernels, so the film is theirs byte for byte (the AOV captures, which need
+// the per-sample buffers, keep the three-kernel form and the tests compare the two).
+#ifndef LGB_SURFACE_MIN_BLOCKS
+#define LGB_SURFACE_MIN_BLOCKS 4
+#endif
+template <bool STATS>
+__device__ __noinline__ D3 surface_generic(const DevScene& S, const DevShade& sh, const Ray64& ray, double t, uint32_t ref, LocalCounters& lc, unsigned& traced, unsigned& occluded) {
+    ShadePoint P; uint32_t id;
+    shade_point<false, false>(S, ray, t, ref, P, id);
+    const uint32_t gate = light_gates(S, ray, P.ps, P.ng, dot(P.wo, P.ng), false);
+    uint32_t occl = ~gate;
+    for (uint32_t l = 0; l < S.n_lights; l++) {
+        if (!((gate >> l) & 1u)) continue;
+        traced++;
+        if (grid_blocked<STATS>(S, P.ps, l, lc)) { occl |= 1u << l; occluded++; }
+    }
+    return shade_generic_plastic(S, sh, ray, t, ref, occl);
+}
+#ifndef LGB_SURFACE_THREADS
+#define LGB_SURFACE_THREADS 256u     // whole pixels per block (spp <= this, else 256)
+#endif
+template <bool STATS>
+__global__ void __launch_bounds__(256, LGB_SURFACE_MIN_BLOCKS) k_surface(DevScene S, DevCamera C, DevShade sh, DevWork W, DevOut O, DevWave V) {
+    const double PI = 3.14159265358979323846264338327950288;
+    __shared__ double rad[3 * kRadStride];
+    __shared__ unsigned char valid[256];
+    __shared__ unsigned char bytes[256 * 3];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t ppb = fdiv(blockDim.x, W.fd_spp);                 // pixels per block
+    const uint32_t tp = fdiv(threadIdx.x, W.fd_spp), s = threadIdx.x - tp * W.spp;
+    const uint64_t p = (uint64_t)blockIdx.x * ppb + tp;
+    const bool mine = tp < ppb && p < W.n_pixels;
+    const uint64_t g = p * W.spp + s;
+    LocalCounters lc = {};
+    unsigned traced = 0, occluded = 0;
+    D3 output = d3(0, 0, 0);
+    bool have = false, generic = false;
+    uint32_t x = 0, y = 0;
+    if (mine) {
+        const uint32_t ref = V.hit_ref[g];
+        const double t = V.hit_t[g];
+        if (ref != kSlotUnused && slot_to_pixel(W, (uint32_t)p, x, y)) {
+            const Ray64 ray = camera_ray(C, W, x, y, s);
+            have = true;
+            if (ref == LGB_MISS) output = background_of(sh, ray.d);                          // background.rs:25-34
+            else {
+                LeanSurf Ls;
+                lean_surface<true>(S, ray, t, ref, 0u, Ls);
+                if (Ls.flags & kSfGeneric) generic = true;
+                else {
+                    const D3 ng = (Ls.flags & kSfNgFlip) ? -Ls.n : Ls.n;
+                    const D3 ps = ray.o + ray.d * t + ng * (2.220446049250313e-16 * 65536.0);   // surface.rs:168, integrate.rs:40 (k_setup's own expression)
+                    uint32_t lit = light_gates(S, ray, ps, ng, 1.0, true);
+                    for (uint32_t l = 0; l < S.n_lights; l++) {
+                        if (!((lit >> l) & 1u)) continue;
+                        traced++;
+                        if (grid_blocked<STATS>(S, ps, l, lc)) { lit &= ~(1u << l); occluded++; }
+                    }
+                    output = lean_radiance(S, sh, ray, t, Ls, Ls.flags, lit);
+                }
+            }
+        }
+    }
+    if (generic) {               // (rare: a sign decision within rounding of a tie -- the reference's own sequence, out of line)
+        const Ray64 ray = camera_ray(C, W, x, y, s);
+        output = surface_generic<STATS>(S, sh, ray, V.hit_t[g], V.hit_ref[g], lc, traced, occluded);
+    }
+    {
+        const uint32_t at = threadIdx.x + (threadIdx.x >> 4);
+        rad[at] = output.x; rad[kRadStride + at] = output.y; rad[2 * kRadStride + at] = output.z;
+        valid[threadIdx.x] = have ? 1 : 0;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < 3u * ppb; j += blockDim.x) {        // item j: channel j / ppb of pixel j % ppb
+        const uint32_t ch = j >= 2u * ppb ? 2u : (j >= ppb ? 1u : 0u), q = j - ch * ppb, t0 = q * W.spp;
+        if (!valid[t0]) continue;
+        const double* r = rad + ch * kRadStride;
+        double c = 0.0;
+        for (uint32_t k = 0; k < W.spp; k++) c = c + r[t0 + k + ((t0 + k) >> 4)];
+        c = c * (1.0 / (double)W.spp);
+        bytes[3 * q + ch] = (unsigned char)round(fmin(fmax(c, 0.0), 1.0) * 255.0);      // img.rs:56-67
+    }
+    __syncthreads();
+    if (threadIdx.x < ppb && valid[threadIdx.x * W.spp]) {
+        const uint64_t pp = (uint64_t)blockIdx.x * ppb + threadIdx.x;
+        uint32_t px, py;
+        slot_to_pixel(W, pp, px, py);
+        uchar4 o; o.x = bytes[3 * threadIdx.x]; o.y = bytes[3 * threadIdx.x + 1]; o.z = bytes[3 * threadIdx.x + 2]; o.w = 255;
+        reinterpret_cast<uchar4*>(O.film)[W.compact_out ? W.compact_base + pp : (uint64_t)py * W.w + px] = o;
+    }
+    if (O.counters) {
+        const unsigned long long v0 = warp_sum(traced), v1 = warp_sum(occluded);
+        if (lane == 0 && v0) { atomicAdd(&O.counters->shadow_traced, v0); atomicAdd(&O.counters->shadow_occluded, v1); }
+        if (STATS) {
+            for (int k = 0; k < 3; k++) {
+                unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
+                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); }
+            }
+        }
+    }
+    (void)PI;
 }
 
 // Whitted recursion (integrate.rs:69-132) below the closest hits that carry specular lobes (glass, mirror), one thread per listed
@@ -2297,7 +2471,7 @@ __global__ void __launch_bounds__(256) k_resolve(DevWork W, DevOut O) {
     const double* r = O.radiance + 3 * p * W.spp;
     for (uint32_t s = 0; s < W.spp; s++) c = c + d3(r[3 * s], r[3 * s + 1], r[3 * s + 2]);
     c = c * weight;
-    reinterpret_cast<uchar4*>(O.film)[W.compact_out ? p : (uint64_t)y * W.w + x] = quantise(c);
+    reinterpret_cast<uchar4*>(O.film)[W.compact_out ? W.compact_base + p : (uint64_t)y * W.w + x] = quantise(c);
 }
 
 // Per-sample radiance for lgb_capture_aov: radiance buffer (slot order) -> caller's order ((y * w + x) * spp + s).
@@ -2381,6 +2555,21 @@ cudaError_t launch_fastmath(const double* x, uint64_t n, double* rcp, double* rs
 
 // ------------------------------------------------------------------ launch wrappers (called from lgb_api.cu)
 bool render_fused(uint32_t spp) { return spp >= 1 && spp <= 256; }      // and !S.general: see launch_render
+#ifndef LGB_SURFACE_FUSED
+#define LGB_SURFACE_FUSED 0          // measured (mixed4k): k_surface 16.0 ms against 2.7 + 7.4 + 4.0 ms for k_setup + k_gshadow + k_shade_lean -- the walk's
+#endif                               // spills on top of the shading state leave L1 (29.6 GB of DRAM writes per frame, profiles/r2_v8_ncu_k_surface.txt)
+#ifndef LGB_SETUP_FUSED
+#define LGB_SETUP_FUSED 1
+#endif
+// k_gshadow<SETUP> does the hit setup itself for camera rays of scenes with light grids, unless a per-sample buffer is asked for
+bool setup_fused(const DevScene& S, const DevWork& W, const DevOut& O, bool all_shadows) {
+    return LGB_SETUP_FUSED && S.grids && !S.instanced && !all_shadows && !O.aov_id && !O.aov_t && !O.aov_occl && W.mode != 3;
+}
+// k_surface serves plastic scenes with light grids and flat-shaded meshes whenever no per-sample buffer is asked for
+bool surface_fused(const DevScene& S, const DevWork& W, const DevOut& O, bool all_shadows) {
+    return LGB_SURFACE_FUSED && S.grids && !S.instanced && !S.general && !S.tri_nrm && !all_shadows && render_fused(W.spp) &&
+           !O.aov_li && !O.aov_id && !O.aov_t && !O.aov_occl && W.mode != 3;
+}
 
 // `ev` (optional): kRenderEvents events recorded around the phases: start | primary | setup | anchor shadow rays |
 // pretest + remaining shadow rays | shade | resolve.
@@ -2403,7 +2592,7 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
         if (total == 0) return cudaSuccess;
         if (!W.slot_list) {
             if ((e = cudaMemsetAsync(V.work_counter, 0, kWaveCtrBytes, stream)) != cudaSuccess) return e;
-            if (cache && S.n_lights && (e = cudaMemsetAsync(V.occluder, 0xFF, (size_t)S.n_lights * W.n_pixels * 4, stream)) != cudaSuccess) return e;
+            if (cache && S.n_lights && !(S.grids && !inst) && (e = cudaMemsetAsync(V.occluder, 0xFF, (size_t)S.n_lights * W.n_pixels * 4, stream)) != cudaSuccess) return e;      // (light grids keep no occluder cache)
         } else if ((e = cudaMemsetAsync(V.work_counter, 0, 8, stream)) != cudaSuccess) return e;      // the fetch counter restarts for the listed slots
         const uint64_t work = W.slot_list ? W.n_list : total;
         const unsigned pb = (unsigned)std::min<uint64_t>((work + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, (uint64_t)sms * LGB_MIN_BLOCKS);
@@ -2428,13 +2617,28 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     if (total == 0) return cudaSuccess;
     mark(1);
     const unsigned blocks = (unsigned)((total + 255) / 256), ablocks = (unsigned)((total + kAppendThreads - 1) / kAppendThreads);
+    if (surface_fused(S, W, O, all_shadows)) {      // hit -> film in one kernel (k_surface)
+        const unsigned ft = W.spp <= LGB_SURFACE_THREADS ? LGB_SURFACE_THREADS : 256u;
+        const unsigned fb = (unsigned)((W.n_pixels + (ft / W.spp) - 1) / (ft / W.spp));
+        mark(2); mark(3); mark(4);
+        KL("k_surface(+film)", -1, stream, if (stats) k_surface<true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V); else k_surface<false><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V));
+        mark(5); mark(6);
+        return cudaGetLastError();
+    }
+    const bool setup_in_gshadow = setup_fused(S, W, O, all_shadows);
+    if (setup_in_gshadow) {             // hit setup inside the shadow kernel: ps never leaves the registers
+        mark(2);
+        KL("k_gshadow(+setup)", -1, stream, if (stats) k_gshadow<true, false, true><<<blocks, 256, 0, stream>>>(S, C, W, O, V); else k_gshadow<false, false, true><<<blocks, 256, 0, stream>>>(S, C, W, O, V));
+        mark(3);
+    } else {
     if (inst) KL("k_setup", -1, stream, if (all_shadows) k_setup<true, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V));
     else KL("k_setup", -1, stream, if (all_shadows) k_setup<true, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V));
     mark(2);
     if (S.grids && !inst) {             // light grids: every shadow ray of the frame in one launch, no traversal (lgb_grid.cu)
-        if (stats) KL("k_gshadow", -1, stream, if (all_shadows) k_gshadow<true, true><<<blocks, 256, 0, stream>>>(S, W, O, V); else k_gshadow<true, false><<<blocks, 256, 0, stream>>>(S, W, O, V));
-        else KL("k_gshadow", -1, stream, if (all_shadows) k_gshadow<false, true><<<blocks, 256, 0, stream>>>(S, W, O, V); else k_gshadow<false, false><<<blocks, 256, 0, stream>>>(S, W, O, V));
+        if (stats) KL("k_gshadow", -1, stream, if (all_shadows) k_gshadow<true, true><<<blocks, 256, 0, stream>>>(S, C, W, O, V); else k_gshadow<true, false><<<blocks, 256, 0, stream>>>(S, C, W, O, V));
+        else KL("k_gshadow", -1, stream, if (all_shadows) k_gshadow<false, true><<<blocks, 256, 0, stream>>>(S, C, W, O, V); else k_gshadow<false, false><<<blocks, 256, 0, stream>>>(S, C, W, O, V));
         mark(3);
+    }
     }
     // per light: anchor rays (queue A), then the cached-occluder test of the rest (B -> C), then the survivors (queue C)
     const int nside = (side && S.n_lights > 1 && !S.grids) ? std::min<int>(side->n, (int)S.n_lights - 1) : 0;
@@ -2509,7 +2713,7 @@ cudaError_t launch_level(const DevScene& S, const DevCamera& C, const DevShade& 
     } else {
         k_primary<false, false, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V);
         k_setup<false, false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
-        if (S.grids) { DevOut Os = O; Os.counters = shadow_counters; k_gshadow<false, false><<<blocks, 256, 0, stream>>>(S, W, Os, V); }
+        if (S.grids) { DevOut Os = O; Os.counters = shadow_counters; k_gshadow<false, false><<<blocks, 256, 0, stream>>>(S, C, W, Os, V); }
         else for (uint32_t l = 0; l < S.n_lights; l++) k_shadow<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, kQueueA);
         k_shade<false, false, true, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
     }

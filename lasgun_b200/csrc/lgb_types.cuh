@@ -108,9 +108,14 @@ struct DevWork {
     const uint32_t* tile_list;
     uint32_t n_tiles;
     uint32_t n_macro_x;
-    uint32_t sub_k, sub_n;
+    uint64_t sub_k; uint32_t sub_n;  // (sub_k: k plus the pixels of the bands before this one)
+    uint64_t compact_base;           // mode 1: film index of this band's first pixel
     uint64_t n_pixels;               // pixel slots in this launch
     uint32_t spp;
+    // the per-launch constants of camera.rs:115-118,131-133, formed once on the host with the reference's own operations (IEEE doubles,
+    // no contraction: the same bits every thread would compute): ipw = iph * aspect, updiff = up * sep, auxdiff = aux * sep,
+    // halfdiff = updiff * 0.5 + auxdiff * 0.5 with sep = sample_distance * (iph * hinv)
+    double cam_ipw, cam_updiff[3], cam_auxdiff[3], cam_halfdiff[3];
     uint64_t fd_spp, fd_root, fd_nmx; // ceil(2^64 / d) for d = spp, the supersampling root, n_macro_x (0: d == 1): fdiv(), lgb_kernels.cu
     uint32_t anchor;                 // sample index of the pixel's anchor shadow ray (centre of the sample grid)
     const uint32_t* slot_list;       // k_primary: trace only these sample slots (re-trace of unresolved exact-t ties) ...

@@ -9,7 +9,7 @@ ctx = N.Context(0); L = N.lib()
 t = time.perf_counter(); hs = N.HostScene(sc); t_replay = time.perf_counter() - t
 film = np.zeros((h, w, 4), np.uint8)
 for it in range(4):
-    t = time.perf_counter(); flat = N.FlatScene(hs); t_flat = time.perf_counter() - t
+    t = time.perf_counter(); flat = N.FlatScene(hs, lazy=True); t_flat = time.perf_counter() - t
     hsc = C.c_void_p()
     t0 = time.perf_counter(); ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat.desc), C.byref(hsc))); t1 = time.perf_counter()
     st = N.Stats()

@@ -26,7 +26,8 @@ def test_header_symbols_exported(native):
 def test_struct_sizes_match_header(native):
     assert ctypes.sizeof(native.Node) == 32
     assert ctypes.sizeof(native.CameraDesc) == 12 * 8 + 3 * 8 + 8
-    assert ctypes.sizeof(native.Stats) == 21 * 8 + 12 * 4
+    assert ctypes.sizeof(native.Stats) == 21 * 8 + 12 * 4 + 8
+    assert ctypes.sizeof(native.KernelTime) == 40 + 8 + 11 * 8
     assert ctypes.sizeof(native.SceneDesc) % 8 == 0
 
 

@@ -183,6 +183,33 @@ def test_camera_grid(native, oracle, gpu_ctx, name):
     assert np.array_equal(films[1], films[0])
 
 
+@pytest.mark.parametrize("name", ["simple_b_9spp", "mixed_4spp", "nested_groups", "whitted"])
+def test_frames_in_bands(native, gpu_ctx, name):
+    """A memory budget far below what the frame's per-sample buffers need (LGB_OPT_WAVE_BUDGET_MB): the frame is rendered band after
+    band on the same buffers and must be the film of the single pass, through capture, capture_subset and the AOV entry."""
+    sc, (w, h) = WHITTED["materials_4spp"]() if name == "whitted" else SMALL[name]()
+    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+    try:
+        ref, st1 = dev.capture(w, h)
+        aov1 = dev.capture_aov(w, h)
+        gpu_ctx.set_wave_budget_mb(1)
+        out, stn = dev.capture(w, h)
+        assert stn["bands"] > 1 and st1["bands"] == 1
+        assert np.array_equal(out, ref)
+        for k in ("primary_rays", "primary_hits", "shadow_rays_traced", "shadow_occluded", "secondary_rays"):
+            assert stn[k] == st1[k], k
+        aovn = dev.capture_aov(w, h)
+        for k in ("rgba", "prim_id", "t", "occl"):
+            assert np.array_equal(aovn[k], aov1[k]), k
+        sub = np.zeros((h, w, 4), np.uint8)
+        for k in range(2):
+            dev.capture_subset(k, 2, w, h, sub)
+        assert np.array_equal(sub, ref)
+    finally:
+        gpu_ctx.set_wave_budget_mb(16384)
+        dev.destroy()
+
+
 # SURVEY 8f item 4: matte(sigma > 0), metal, glass, mirror and the Whitted recursion of integrate.rs:69-132
 WHITTED = {
     "simplereflect_9spp": lambda: scenes.simplereflect(2, 160),                 # src/examples/simplereflect.rs, depth 4
@@ -320,6 +347,7 @@ FULL = {
     "C2_mesh1m": (scenes.mesh1m, 211),
     "C3_cornell": (scenes.cornell, 389),
     "C4_spheres1m": (scenes.spheres1m, 1999),
+    "C5_mixed4k": (scenes.mixed4k, 7919),          # 3840x2160 at 16 spp: the oracle renders ~1000 pixels of it (a few seconds per thread)
 }
 
 
