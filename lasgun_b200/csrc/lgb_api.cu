@@ -607,54 +607,65 @@ static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
     CU(ctx, cudaSetDevice(ctx->device));
     uint32_t res = 1024;
     if (const char* e = std::getenv("LGB_GRID_RES")) res = std::min(4096u, std::max(16u, (uint32_t)std::atoi(e)));
+    const uint32_t nl = S.n_lights;
     const size_t nc = grid_cells(res), scan_bytes = grid_scan_bytes(res);
     cudaStream_t st = ctx->stream;
-    uint32_t* counts = nullptr; void* scan_tmp = nullptr; uint2* large_tmp = nullptr; uint32_t* n_large_dev = nullptr;
-    std::vector<void*> mine;                 // what the scene keeps
-    std::vector<DevGrid> table(S.n_lights);
+    std::vector<void*> temp, mine;               // freed at the end | kept by the scene
     auto cleanup = [&](bool keep) {
-        if (counts) cudaFreeAsync(counts, st);
-        if (scan_tmp) cudaFreeAsync(scan_tmp, st);
-        if (large_tmp) cudaFreeAsync(large_tmp, st);
-        if (n_large_dev) cudaFreeAsync(n_large_dev, st);
+        for (void* p : temp) cudaFreeAsync(p, st);
         if (!keep) for (void* p : mine) cudaFreeAsync(p, st);
     };
 #define GR(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(false); return cuda_fail(ctx, e__, #call); } } while (0)
-    GR(cudaMallocAsync((void**)&counts, (nc + 1) * 4, st));
-    GR(cudaMallocAsync(&scan_tmp, std::max<size_t>(scan_bytes, 16), st));
-    GR(cudaMallocAsync((void**)&large_tmp, sizeof(uint2) * kGridLargeCap, st));
-    GR(cudaMallocAsync((void**)&n_large_dev, 4, st));
-    bool ok = true;
-    for (uint32_t l = 0; l < S.n_lights && ok; l++) {
-        uint32_t* starts = nullptr;
-        GR(cudaMallocAsync((void**)&starts, (nc + 1) * 4, st));
-        mine.push_back(starts);
-        uint32_t total = 0, n_large = 0;
-        GR(grid_count(S, l, res, counts, starts, scan_tmp, scan_bytes, large_tmp, n_large_dev, st, &total, &n_large));
-        if (n_large > kGridLargeCap) { ok = false; break; }
-        uint2* entries = nullptr; uint2* large = nullptr;
-        GR(cudaMallocAsync((void**)&entries, sizeof(uint2) * std::max<size_t>(total, 1), st));
-        mine.push_back(entries);
-        GR(cudaMallocAsync((void**)&large, sizeof(uint2) * std::max<uint32_t>(n_large, 1), st));
-        mine.push_back(large);
-        GR(grid_fill(S, l, res, counts, starts, entries, large_tmp, n_large, st));
-        if (n_large) GR(cudaMemcpyAsync(large, large_tmp, sizeof(uint2) * n_large, cudaMemcpyDeviceToDevice, st));
-        table[l].cell_start = starts; table[l].entries = entries; table[l].large = large; table[l].res = res; table[l].n_large = n_large;
-        s->grid_bytes += (nc + 1) * 4 + sizeof(uint2) * ((size_t)total + n_large);
+    auto alloc = [&](std::vector<void*>& owner, size_t bytes, void** out) { cudaError_t e = cudaMallocAsync(out, std::max<size_t>(bytes, 16), st); if (e == cudaSuccess) owner.push_back(*out); return e; };
+    uint32_t* counts = nullptr; void* scan_tmp = nullptr; unsigned long long* bounds = nullptr; uint32_t* totals = nullptr; uint2* large_tmp = nullptr; DevGrid* dtab = nullptr;
+    GR(alloc(temp, (nc + 1) * 4, (void**)&counts));
+    GR(alloc(temp, scan_bytes, &scan_tmp));
+    GR(alloc(temp, 64 * 8 * (size_t)nl, (void**)&bounds));
+    GR(alloc(temp, 8 * (size_t)nl, (void**)&totals));
+    GR(alloc(temp, sizeof(uint2) * kGridLargeCap * (size_t)nl, (void**)&large_tmp));
+    GR(alloc(mine, sizeof(DevGrid) * (size_t)nl, (void**)&dtab));
+    GR(cudaMemsetAsync(dtab, 0, sizeof(DevGrid) * (size_t)nl, st));
+    const bool timing = getenv("LGB_TIMING") != nullptr;
+    auto lap = [&](const char* what) { if (!timing) return; cudaStreamSynchronize(st); fprintf(stderr, "[light grids]   %-28s %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); };
+    lap("temporaries allocated");
+    std::vector<uint32_t*> starts(nl, nullptr);
+    for (uint32_t l = 0; l < nl; l++) {          // face mappings, counts, scans of every light, then ONE synchronisation for the totals
+        GR(alloc(mine, (nc + 1) * 4, (void**)&starts[l]));
+        GR(grid_count(S, l, res, dtab + l, bounds + 64 * (size_t)l, counts, starts[l], scan_tmp, scan_bytes, large_tmp + (size_t)kGridLargeCap * l, totals + 2 * (size_t)l, st));
     }
+    lap("bounds + counts + scans");
+    std::vector<uint32_t> h_tot(2 * (size_t)nl);
+    GR(cudaMemcpyAsync(h_tot.data(), totals, 8 * (size_t)nl, cudaMemcpyDeviceToHost, st));
+    GR(cudaStreamSynchronize(st));
+    bool ok = true;
+    for (uint32_t l = 0; l < nl; l++) ok = ok && h_tot[2 * l + 1] <= kGridLargeCap;
+    uint64_t bytes = 0, entries_all = 0;
     if (ok) {
-        DevGrid* dtab = nullptr;
-        GR(cudaMallocAsync((void**)&dtab, sizeof(DevGrid) * S.n_lights, st));
-        mine.push_back(dtab);
-        GR(cudaMemcpyAsync(dtab, table.data(), sizeof(DevGrid) * S.n_lights, cudaMemcpyHostToDevice, st));
-        GR(cudaStreamSynchronize(st));       // `table` is on this stack frame
+        struct Head { const uint32_t* cell_start; const uint2* entries; const uint2* large; uint32_t res, n_large; };
+        static_assert(offsetof(DevGrid, map) == sizeof(Head), "DevGrid head");
+        std::vector<Head> heads(nl);
+        for (uint32_t l = 0; l < nl; l++) {
+            const uint32_t total = h_tot[2 * l], n_large = h_tot[2 * l + 1];
+            uint2* entries = nullptr; uint2* large = nullptr;
+            GR(alloc(mine, sizeof(uint2) * (size_t)total, (void**)&entries));
+            GR(alloc(mine, sizeof(uint2) * (size_t)n_large, (void**)&large));
+            GR(grid_fill(S, l, res, dtab + l, counts, starts[l], entries, large_tmp + (size_t)kGridLargeCap * l, n_large, st));
+            if (n_large) GR(cudaMemcpyAsync(large, large_tmp + (size_t)kGridLargeCap * l, sizeof(uint2) * n_large, cudaMemcpyDeviceToDevice, st));
+            heads[l] = Head{starts[l], entries, large, res, n_large};
+            bytes += (nc + 1) * 4 + sizeof(uint2) * ((size_t)total + n_large); entries_all += total;
+        }
+        lap("entries allocated, filled, sorted");
+        for (uint32_t l = 0; l < nl; l++) GR(cudaMemcpyAsync((char*)(dtab + l), &heads[l], sizeof(Head), cudaMemcpyHostToDevice, st));
+        GR(cudaStreamSynchronize(st));           // `heads` is on this stack frame; captures may run on other streams
         S.grids = dtab;
         s->grid_allocs = mine;
+        s->grid_bytes = bytes + sizeof(DevGrid) * nl;
     }
     cleanup(ok);
 #undef GR
     s->t_grids = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (getenv("LGB_TIMING")) fprintf(stderr, "[light grids] %u lights, res %u, %.1f MB, %.2f ms (host clock, one sync per light)%s\n", S.n_lights, res, s->grid_bytes / 1e6, s->t_grids, ok ? "" : " REFUSED");
+    if (getenv("LGB_TIMING")) fprintf(stderr, "[light grids] %u lights, res %u, %llu entries, %.1f MB, %.2f ms (host clock, two synchronisations)%s\n", nl, res,
+                                      (unsigned long long)entries_all, s->grid_bytes / 1e6, s->t_grids, ok ? "" : " REFUSED");
     return LGB_OK;
 }
 
@@ -674,13 +685,21 @@ static int replicate_to_peers(lgb_ctx* ctx, lgb_scene* s) {
         s->replicas.push_back(r);
         CU(ctx, cudaMemcpyPeerAsync(arena, p->device, s->arena, ctx->device, s->bytes, p->stream));
     }
-    for (size_t k = 0; k < ctx->peers.size(); k++) {
-        lgb_ctx* p = ctx->peers[k];
-        CU(ctx, cudaSetDevice(p->device)); CU(ctx, cudaStreamSynchronize(p->stream));
-        s->replicas[k]->dev.grids = nullptr;
-        if (int rc = build_light_grids(p, s->replicas[k])) return fail(ctx, rc, "light grids on device " + std::to_string(p->device) + ": " + p->error);
-    }
+    // every peer finishes its copy and builds its own light grids, all at once (a build holds two host synchronisations)
+    std::vector<int> rcs(ctx->peers.size(), LGB_OK);
+    std::vector<std::thread> workers;
+    for (size_t k = 0; k < ctx->peers.size(); k++)
+        workers.emplace_back([&, k] {
+            lgb_ctx* p = ctx->peers[k];
+            if (cudaSetDevice(p->device) != cudaSuccess || cudaStreamSynchronize(p->stream) != cudaSuccess) { rcs[k] = fail(p, LGB_ERR_CUDA, "scene replication: peer copy failed"); return; }
+            s->replicas[k]->dev.grids = nullptr;
+            rcs[k] = build_light_grids(p, s->replicas[k]);
+        });
+    const int rc0 = build_light_grids(ctx, s);           // the leader's own, meanwhile
+    for (std::thread& t : workers) t.join();
     CU(ctx, cudaSetDevice(ctx->device));
+    if (rc0) return rc0;
+    for (size_t k = 0; k < rcs.size(); k++) if (rcs[k]) return fail(ctx, rcs[k], "scene replication on device " + std::to_string(ctx->peers[k]->device) + ": " + ctx->peers[k]->error);
     return LGB_OK;
 }
 
@@ -1059,8 +1078,8 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     s->t_total = ms_since(tc0);
     if (getenv("LGB_TIMING")) fprintf(stderr, "[lgb_scene_create] %s build: validate%s %.1f rank %.1f build %.1f (sah %.1f) convert+upload %.1f total %.1f ms, %u threads\n",
                                       s->gpu_built ? "device" : "host", s->gpu_built ? "+stage" : "", s->t_validate, s->t_rank, s->t_build, s->build_ms, s->t_convert_upload, s->t_total, (unsigned)threads);
-    if (int rc = build_light_grids(ctx, s)) return bail(rc);
-    if (!ctx->peers.empty()) if (int rc = replicate_to_peers(ctx, s)) return bail(rc);
+    if (ctx->peers.empty()) { if (int rc = build_light_grids(ctx, s)) return bail(rc); }
+    else if (int rc = replicate_to_peers(ctx, s)) return bail(rc);       // (builds the leader's grids too, while the peers copy)
     *out = s;
     return LGB_OK;
 }

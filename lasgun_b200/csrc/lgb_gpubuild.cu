@@ -46,7 +46,14 @@ struct Work {                      // one node of the current level
 // per node with more than kMaxLeaf items: [axis][bin] box lo (3 keys), box hi (3 keys), count
 constexpr int kBinWords = 3 * NB * 7;
 
-struct Ctl { uint32_t next_count, node_count, max_depth, bin_slots; };
+struct Ctl { uint32_t next_count, node_count, max_depth, bin_slots, count, levels; };      // count: nodes of the level being split (k_advance)
+// Start of a level: the nodes the previous level produced become the current ones.  The host does not read the count back every
+// level (28 round trips for 600 k primitives): the kernels of a level take it from here, are launched for the largest level there can
+// be, and a level past the last one does nothing.
+__global__ void k_advance(Ctl* ctl) {
+    ctl->count = ctl->next_count; ctl->next_count = 0; ctl->bin_slots = 0;
+    if (ctl->count) ctl->levels++;
+}
 
 __device__ __forceinline__ int bin_of(float c, float cmin, float scale) {
     const float x = fminf(fmaxf((c - cmin) * scale, 0.0f), (float)(NB - 1));
@@ -66,9 +73,9 @@ __global__ void k_root(const GItem* items, uint32_t n, Work* work, Ctl* ctl) {
     (void)ctl;
 }
 
-__global__ void k_prep(Work* work, uint32_t count, uint32_t* bins, Ctl* ctl) {
+__global__ void k_prep(Work* work, uint32_t* bins, Ctl* ctl) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= count) return;
+    if (w >= ctl->count) return;
     Work& W = work[w];
     for (int a = 0; a < 3; a++) {
         const float lo = kfloat(W.cb_lo[a]), hi = kfloat(W.cb_hi[a]);
@@ -89,11 +96,13 @@ __global__ void k_prep(Work* work, uint32_t count, uint32_t* bins, Ctl* ctl) {
     }
 }
 
+constexpr int kTopNodesDecl = 32;
 // one atomic per distinct target among the lanes of a warp
 __device__ __forceinline__ void agg_min(uint32_t* addr, uint32_t v, unsigned peers, bool leader) { v = __reduce_min_sync(peers, v); if (leader) atomicMin(addr, v); }
 __device__ __forceinline__ void agg_max(uint32_t* addr, uint32_t v, unsigned peers, bool leader) { v = __reduce_max_sync(peers, v); if (leader) atomicMax(addr, v); }
 
-__global__ void k_bin(const GItem* items, const uint32_t* node_of, uint32_t n, const Work* work, uint32_t* bins) {
+__global__ void k_bin(const GItem* items, const uint32_t* node_of, uint32_t n, const Work* work, uint32_t* bins, const Ctl* ctl) {
+    if (ctl->count <= (uint32_t)kTopNodesDecl || ctl->count == 0) return;      // the top of the tree is k_bin_top's
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     uint32_t slot = kInvalid;
@@ -119,7 +128,9 @@ __global__ void k_bin(const GItem* items, const uint32_t* node_of, uint32_t n, c
 // Top of the tree: a handful of nodes own all the items, so k_bin's global atomics all land on the same few hundred words.
 // Here every block bins into a private copy in shared memory (slots 0 .. kTopNodes-1 of the bin pool) and merges it once.
 constexpr int kTopNodes = 32;            // 32 x 336 words = 42 KB of shared memory
-__global__ void __launch_bounds__(256) k_bin_top(const GItem* items, const uint32_t* node_of, uint32_t n, const Work* work, uint32_t* bins) {
+static_assert(kTopNodes == kTopNodesDecl, "kTopNodes");
+__global__ void __launch_bounds__(256) k_bin_top(const GItem* items, const uint32_t* node_of, uint32_t n, const Work* work, uint32_t* bins, const Ctl* ctl) {
+    if (ctl->count > (uint32_t)kTopNodes || ctl->count == 0) return;           // every bin slot < count <= kTopNodes
     __shared__ uint32_t sb[kTopNodes * kBinWords];
     for (int i = threadIdx.x; i < kTopNodes * kBinWords; i += blockDim.x) sb[i] = (i % 7) < 3 ? kKeyMax : 0u;
     __syncthreads();
@@ -168,9 +179,9 @@ __device__ __forceinline__ void set_child_word(HostNode* nodes, uint32_t parent,
     if (which) nodes[parent].c1 = word; else nodes[parent].c0 = word;
 }
 
-__global__ void k_split(Work* work, uint32_t count, const uint32_t* bins, const GItem* items, HostNode* nodes, Work* next, Ctl* ctl, uint32_t next_cap) {
+__global__ void k_split(Work* work, const uint32_t* bins, const GItem* items, HostNode* nodes, Work* next, Ctl* ctl, uint32_t next_cap) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= count) return;
+    if (w >= ctl->count) return;
     Work& W = work[w];
     const uint32_t n = W.end - W.begin;
     W.child[0] = W.child[1] = kInvalid;
@@ -432,40 +443,43 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
     root.begin = 0; root.end = n; root.parent = kInvalid; root.which = 0; root.depth = 0;
     for (int a = 0; a < 3; a++) { root.cb_lo[a] = kKeyMax; root.cb_hi[a] = 0; }
     if ((e = cudaMemcpyAsync(work[0], &root, sizeof root, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
-    Ctl c0{0, 1, 0, 0};                                    // node 0 is the root
+    Ctl c0{1, 1, 0, 0, 0, 0};                              // node 0 is the root; one node (the root) enters the first level
     if ((e = cudaMemcpyAsync(ctl, &c0, sizeof c0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(buf[0], items_in, (size_t)n * sizeof(GItem), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
     k_fill<<<ib, 256, 0, st>>>(nof[0], n, 0u);
     k_root<<<256, 256, 0, st>>>(buf[0], n, work[0], ctl);
     if ((e = check("k_root", 0)) != cudaSuccess) return e;
-    uint32_t count = 1, levels = 0, node_count = 1, max_depth = 0;
+    uint32_t levels = 0, node_count = 1, max_depth = 0, launched = 0;
     int cur = 0;
     const bool timing = std::getenv("LGB_TIMING") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto t_start = now();
-    std::vector<double> level_ms; std::vector<uint32_t> level_nodes;
-    while (count) {
-        auto t_level = now();
-        const unsigned wb = (count + 127) / 128;
-        if ((e = cudaMemsetAsync(&ctl->next_count, 0, 4, st)) != cudaSuccess) return e;
-        if ((e = cudaMemsetAsync(&ctl->bin_slots, 0, 4, st)) != cudaSuccess) return e;
-        k_prep<<<wb, 128, 0, st>>>(work[cur], count, bins, ctl);
-        if ((e = check("k_prep", levels)) != cudaSuccess) return e;
-        if (count <= (uint32_t)kTopNodes) k_bin_top<<<296, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], bins);     // every bin slot < count <= kTopNodes
-        else k_bin<<<ib, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], bins);
-        if ((e = check("k_bin", levels)) != cudaSuccess) return e;
-        k_split<<<wb, 128, 0, st>>>(work[cur], count, bins, buf[cur], nodes_out, work[cur ^ 1], ctl, n + 2);
-        if ((e = check("k_split", levels)) != cudaSuccess) return e;
-        k_scatter<<<ib, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], work[cur ^ 1], buf[cur ^ 1], nof[cur ^ 1], final_items);
-        if ((e = check("k_scatter", levels)) != cudaSuccess) return e;
-        if (dbg) std::fprintf(stderr, "[gpu_build_sah] level %u: %u nodes\n", levels, count);
+    std::vector<double> chunk_ms;
+    // a level never holds more nodes than there are items above leaf size ... bounded by the item count
+    const unsigned wb = (unsigned)(((size_t)n + 2 + 127) / 128);
+    constexpr uint32_t kChunk = 8;                         // levels queued between two looks at the control block
+    for (;;) {
+        auto t_chunk = now();
+        for (uint32_t k = 0; k < kChunk; k++) {
+            k_advance<<<1, 1, 0, st>>>(ctl);
+            k_prep<<<wb, 128, 0, st>>>(work[cur], bins, ctl);
+            if ((e = check("k_prep", launched)) != cudaSuccess) return e;
+            k_bin_top<<<296, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], bins, ctl);
+            k_bin<<<ib, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], bins, ctl);
+            if ((e = check("k_bin", launched)) != cudaSuccess) return e;
+            k_split<<<wb, 128, 0, st>>>(work[cur], bins, buf[cur], nodes_out, work[cur ^ 1], ctl, n + 2);
+            if ((e = check("k_split", launched)) != cudaSuccess) return e;
+            k_scatter<<<ib, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], work[cur ^ 1], buf[cur ^ 1], nof[cur ^ 1], final_items);
+            if ((e = check("k_scatter", launched)) != cudaSuccess) return e;
+            cur ^= 1; launched++;
+        }
         Ctl h;
         if ((e = cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-        if (timing) { level_ms.push_back(std::chrono::duration<double, std::milli>(now() - t_level).count()); level_nodes.push_back(count); }
-        count = h.next_count; node_count = h.node_count; max_depth = h.max_depth;
-        cur ^= 1;
-        if (++levels > 96) return cudaErrorUnknown;         // depth guard (splits by position halve every node from depth 40 on)
+        if (timing) chunk_ms.push_back(std::chrono::duration<double, std::milli>(now() - t_chunk).count());
+        node_count = h.node_count; max_depth = h.max_depth; levels = h.levels;
+        if (h.next_count == 0) break;
+        if (launched > 96) return cudaErrorUnknown;         // depth guard (splits by position halve every node from depth 40 on)
     }
     // per-type positions of the items in tree order; leaf words -> first index in the type's array
     for (uint32_t t = 0; t < 3; t++) {
@@ -478,8 +492,8 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;      // h_tp is on this stack frame
     if (timing) {
-        std::fprintf(stderr, "[gpu_build_sah] %u items, %u levels, %.2f ms total; per level (nodes: ms):", n, levels, std::chrono::duration<double, std::milli>(now() - t_start).count());
-        for (size_t i = 0; i < level_ms.size(); i++) std::fprintf(stderr, " %u:%.2f", level_nodes[i], level_ms[i]);
+        std::fprintf(stderr, "[gpu_build_sah] %u items, %u levels (%u launched), %.2f ms total; per chunk of %u levels:", n, levels, launched, std::chrono::duration<double, std::milli>(now() - t_start).count(), kChunk);
+        for (size_t i = 0; i < chunk_ms.size(); i++) std::fprintf(stderr, " %.2f", chunk_ms[i]);
         std::fprintf(stderr, "\n");
     }
     for (int t = 0; t < 3; t++) typepos_out[t] = typepos[t];

@@ -13,6 +13,12 @@
 // off the frame's path) -> fill -> per-cell sort by distance.  Single-space scenes only (no transformed aggregates).
 #include <cub/device/device_scan.cuh>
 
+#include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
+
 #include "lgb_grid.cuh"
 
 namespace lgb {
@@ -43,9 +49,10 @@ __device__ __forceinline__ bool prim_box(const DevScene& S, uint32_t i, double l
     return true;
 }
 
-// Cells of cube-map face `face` (major axis a = face / 2, negative side iff face & 1) that the box [lo, hi] - o can be seen in:
-// u = x_b / w, v = x_c / w over the part of the box with w = +-x_a > 0, b = (a + 1) % 3, c = (a + 2) % 3.  Conservative.
-__device__ __forceinline__ bool face_rect(const double lo[3], const double hi[3], const double o[3], int face, uint32_t res, int rect[4]) {
+// Direction footprint of the box [lo, hi] - o on cube-map face `face` (major axis a = face / 2, negative side iff face & 1):
+// u = x_b / w, v = x_c / w over the part of the box with w = +-x_a > 0, b = (a + 1) % 3, c = (a + 2) % 3, clipped to the face
+// [-1, 1]^2 and widened by 1e-9.  false: not seen on this face.  Conservative.
+__device__ __forceinline__ bool face_uv(const double lo[3], const double hi[3], const double o[3], int face, double uv[4]) {
     const int a = face >> 1, b = (a + 1) % 3, c = (a + 2) % 3;
     double wl, wh;
     if (face & 1) { wl = -(hi[a] - o[a]); wh = -(lo[a] - o[a]); } else { wl = lo[a] - o[a]; wh = hi[a] - o[a]; }
@@ -58,13 +65,18 @@ __device__ __forceinline__ bool face_rect(const double lo[3], const double hi[3]
         if (xl < 0.0 && !(wl > 0.0)) umin = -CUDART_INF;
         if (xh > 0.0 && !(wl > 0.0)) umax = CUDART_INF;
         if (umin > 1.0 || umax < -1.0) return false;          // seen on a neighbouring face only
-        umin = fmax(umin - 1e-9, -1.0); umax = fmin(umax + 1e-9, 1.0);
-        // cell index of a direction: floor((u + 1) res / 2), clamped (k_gshadow uses the same expression)
-        int c0 = (int)floor((umin + 1.0) * 0.5 * (double)res - 1e-6), c1 = (int)floor((umax + 1.0) * 0.5 * (double)res + 1e-6);
-        c0 = max(c0, 0); c1 = min(c1, (int)res - 1);
-        rect[2 * k] = c0; rect[2 * k + 1] = c1;
+        uv[2 * k] = fmax(umin - 1e-9, -1.0); uv[2 * k + 1] = fmin(umax + 1e-9, 1.0);
     }
     return true;
+}
+// Cells of that footprint under the face's mapping {u0, su, v0, sv}: floor((u - u0) su), clamped to [0, res) -- the expression
+// grid_blocked (lgb_kernels.cu) evaluates for a ray's direction; clamping keeps the listing complete for directions outside the mapped part.
+__device__ __forceinline__ void face_cells(const double uv[4], const double* map, uint32_t res, int rect[4]) {
+    for (int k = 0; k < 2; k++) {
+        int c0 = (int)fmin(fmax(floor((uv[2 * k] - map[2 * k]) * map[2 * k + 1] - 1e-6), -1.0), (double)res);
+        int c1 = (int)fmin(fmax(floor((uv[2 * k + 1] - map[2 * k]) * map[2 * k + 1] + 1e-6), -1.0), (double)res);
+        rect[2 * k] = min(max(c0, 0), (int)res - 1); rect[2 * k + 1] = min(max(c1, 0), (int)res - 1);
+    }
 }
 
 __device__ __forceinline__ float box_dmin(const double lo[3], const double hi[3], const double o[3]) {
@@ -73,9 +85,61 @@ __device__ __forceinline__ float box_dmin(const double lo[3], const double hi[3]
     return fmaxf(__double2float_rd(sqrt(d2) * (1.0 - 1e-6)), 0.0f);
 }
 
+constexpr int kBoundWords = 7;       // per face: min u, max u, min v, max v (dkeys), sum of u extents, sum of v extents, count (doubles)
+// order-preserving integer image of a double, for atomicMin / atomicMax
+__device__ __forceinline__ unsigned long long dkey(double v) { const unsigned long long b = (unsigned long long)__double_as_longlong(v); return (b >> 63) ? ~b : (b | 0x8000000000000000ull); }
+__host__ __device__ inline double dkey_inv(unsigned long long k) { const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k; double d; memcpy(&d, &b, 8); return d; }
+
+// pass A: the part of every face that the scene's SMALL primitives cover (footprints of at most `small_frac` of the face per axis);
+// bounds[face] = {min u, max u, min v, max v} as dkeys.  The cells are then laid over that part only: a light far from a compact
+// scene spends its res^2 cells on the few degrees the scene subtends, not on the whole face.
+__global__ void __launch_bounds__(256) k_grid_bounds(DevScene S, uint32_t light, double small_span, unsigned long long* bounds) {
+    // per block in shared memory first: 42 words that every primitive of the scene would otherwise hit with global atomics (measured:
+    // 2.9 - 5.5 ms per light for 0.6 - 1 M primitives that way)
+    __shared__ unsigned long long sb[6 * kBoundWords];
+    for (int k = threadIdx.x; k < 6 * kBoundWords; k += blockDim.x) { const int w = k % kBoundWords; sb[k] = (w == 0 || w == 2) ? ~0ull : 0ull; }
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S.n_sph + S.n_cub + S.n_tri) {
+        const double* L = S.lights + 9 * (size_t)light;
+        const double o[3] = {L[0], L[1], L[2]};
+        double lo[3], hi[3]; uint32_t ref;
+        prim_box(S, i, lo, hi, ref);
+        for (int f = 0; f < 6; f++) {
+            double uv[4];
+            if (!face_uv(lo, hi, o, f, uv)) continue;
+            if (uv[1] - uv[0] > small_span || uv[3] - uv[2] > small_span) continue;
+            unsigned long long* b = sb + kBoundWords * f;
+            atomicMin(b + 0, dkey(uv[0])); atomicMax(b + 1, dkey(uv[1])); atomicMin(b + 2, dkey(uv[2])); atomicMax(b + 3, dkey(uv[3]));
+            double* sum = reinterpret_cast<double*>(b + 4);              // {sum of u extents, sum of v extents, count}
+            atomicAdd(sum + 0, uv[1] - uv[0]); atomicAdd(sum + 1, uv[3] - uv[2]); atomicAdd(sum + 2, 1.0);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 6 * kBoundWords; k += blockDim.x) {
+        const int w = k % kBoundWords;
+        if (w == 0 || w == 2) { if (sb[k] != ~0ull) atomicMin(bounds + k, sb[k]); }
+        else if (w == 1 || w == 3) { if (sb[k] != 0ull) atomicMax(bounds + k, sb[k]); }
+        else { const double v = __longlong_as_double((long long)sb[k]); if (v != 0.0) atomicAdd(reinterpret_cast<double*>(bounds + k), v); }
+    }
+}
+// A face's cells: laid over the covered part, but never finer than the average small footprint -- cells smaller than the primitives
+// only multiply the entries (every primitive is listed in each cell it touches) without shortening the lists a ray walks.
+__global__ void k_grid_map(const unsigned long long* bounds, uint32_t res, double cell_factor, DevGrid* grid) {
+    const int f = threadIdx.x;
+    if (f >= 6) return;
+    const unsigned long long* b = bounds + kBoundWords * f;
+    double u0 = dkey_inv(b[0]), u1 = dkey_inv(b[1]), v0 = dkey_inv(b[2]), v1 = dkey_inv(b[3]);
+    const double* sum = reinterpret_cast<const double*>(b + 4);
+    if (!(u0 <= u1) || !(v0 <= v1) || !(sum[2] > 0.0)) { u0 = v0 = -1.0; u1 = v1 = 1.0; }          // nothing small on this face
+    const double au = sum[2] > 0.0 ? sum[0] / sum[2] : 0.0, av = sum[2] > 0.0 ? sum[1] / sum[2] : 0.0;
+    const double cu = fmax(fmax(u1 - u0, 1e-6) / (double)res, cell_factor * au), cv = fmax(fmax(v1 - v0, 1e-6) / (double)res, cell_factor * av);
+    grid->map[f][0] = u0; grid->map[f][1] = 1.0 / cu; grid->map[f][2] = v0; grid->map[f][3] = 1.0 / cv;
+}
+
 // pass 0: counts per cell (and the large list); pass 1: the entries
 template <int PASS>
-__global__ void __launch_bounds__(256) k_grid_pass(DevScene S, uint32_t light, uint32_t res, uint32_t large_cells, uint32_t large_cap,
+__global__ void __launch_bounds__(256) k_grid_pass(DevScene S, uint32_t light, const DevGrid* grid, uint32_t res, uint32_t large_cells, uint32_t large_cap,
                                                    uint32_t* counts, const uint32_t* starts, uint2* entries, uint2* large, uint32_t* n_large) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S.n_sph + S.n_cub + S.n_tri) return;
@@ -85,8 +149,9 @@ __global__ void __launch_bounds__(256) k_grid_pass(DevScene S, uint32_t light, u
     prim_box(S, i, lo, hi, ref);
     int rect[6][4]; bool on[6]; uint64_t cells = 0;
     for (int f = 0; f < 6; f++) {
-        on[f] = face_rect(lo, hi, o, f, res, rect[f]);
-        if (on[f]) cells += (uint64_t)(rect[f][1] - rect[f][0] + 1) * (uint64_t)(rect[f][3] - rect[f][2] + 1);
+        double uv[4];
+        on[f] = face_uv(lo, hi, o, f, uv);
+        if (on[f]) { face_cells(uv, grid->map[f], res, rect[f]); cells += (uint64_t)(rect[f][1] - rect[f][0] + 1) * (uint64_t)(rect[f][3] - rect[f][2] + 1); }
     }
     if (cells == 0) return;
     const uint2 rec = make_uint2(ref, __float_as_uint(box_dmin(lo, hi, o)));
@@ -105,29 +170,46 @@ __global__ void __launch_bounds__(256) k_grid_pass(DevScene S, uint32_t light, u
     }
 }
 
-// nearest first (ties by primitive: the order of the atomics must not show), so that a ray stops at the first entry beyond its own length
+// nearest first (ties by primitive: the order of the atomics must not show), so that a ray stops at the first entry beyond its own
+// length.  Short lists by insertion, long ones by heap sort (a cell seen edge-on through a dense mesh can hold hundreds of entries).
+__device__ __forceinline__ bool entry_less(uint2 x, uint2 y) {
+    const float kx = __uint_as_float(x.y), ky = __uint_as_float(y.y);
+    return kx < ky || (kx == ky && x.x < y.x);
+}
 __global__ void __launch_bounds__(256) k_grid_sort(const uint32_t* starts, uint2* entries, size_t n_cells) {
     const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= n_cells) return;
-    const uint32_t b = starts[cell], e = starts[cell + 1];
-    for (uint32_t i = b + 1; i < e; i++) {
-        const uint2 x = entries[i];
-        const float kx = __uint_as_float(x.y);
-        uint32_t j = i;
-        while (j > b) {
-            const uint2 y = entries[j - 1];
-            const float ky = __uint_as_float(y.y);
-            if (ky < kx || (ky == kx && y.x < x.x)) break;
-            entries[j] = y; j--;
+    const uint32_t b = starts[cell], e = starts[cell + 1], n = e - b;
+    if (n < 2 || n > kGridSortMax) return;                  // (a longer list stays as the atomics left it: the walks do not stop early in it)
+    uint2* a = entries + b;
+    if (n <= 24) {
+        for (uint32_t i = 1; i < n; i++) {
+            const uint2 x = a[i];
+            uint32_t j = i;
+            while (j > 0 && entry_less(x, a[j - 1])) { a[j] = a[j - 1]; j--; }
+            a[j] = x;
         }
-        entries[j] = x;
+        return;
     }
+    auto sift = [&](uint32_t root, uint32_t end) {           // max-heap on entry_less
+        const uint2 x = a[root];
+        for (;;) {
+            uint32_t child = 2 * root + 1;
+            if (child >= end) break;
+            if (child + 1 < end && entry_less(a[child], a[child + 1])) child++;
+            if (!entry_less(x, a[child])) break;
+            a[root] = a[child]; root = child;
+        }
+        a[root] = x;
+    };
+    for (uint32_t i = n / 2; i-- > 0;) sift(i, n);
+    for (uint32_t end = n - 1; end > 0; end--) { const uint2 t = a[0]; a[0] = a[end]; a[end] = t; sift(0, end); }
 }
 __global__ void k_grid_sort_large(uint2* large, uint32_t n) {
     if (blockIdx.x || threadIdx.x) return;
     for (uint32_t i = 1; i < n; i++) {
         const uint2 x = large[i]; uint32_t j = i;
-        while (j > 0 && (__uint_as_float(large[j - 1].y) > __uint_as_float(x.y) || (large[j - 1].y == x.y && large[j - 1].x > x.x))) { large[j] = large[j - 1]; j--; }
+        while (j > 0 && entry_less(x, large[j - 1])) { large[j] = large[j - 1]; j--; }
         large[j] = x;
     }
 }
@@ -213,31 +295,50 @@ size_t scan_bytes_for(size_t n_cells) {
 
 size_t grid_cells(uint32_t res) { return (size_t)6 * res * res; }
 
-// Builds the grid of one light.  `counts` / `starts`: n_cells + 1 words each (device); `scan_tmp`: cub scratch.
-// On return *total_out = entries written (after a stream synchronisation inside).  Two calls: entries == nullptr sizes the
-// grid (pass 0 + scan, returns the total), the second call fills and sorts it.
-cudaError_t grid_count(const DevScene& S, uint32_t light, uint32_t res, uint32_t* counts, uint32_t* starts, void* scan_tmp, size_t scan_bytes,
-                       uint2* large, uint32_t* n_large_dev, cudaStream_t st, uint32_t* total_out, uint32_t* n_large_out) {
+// Light grid of light `light`, first half: the face mappings (into *grid_dev), the counts, their scan into `starts`, the large list.
+// Asynchronous: the totals land in totals_dev[0] (entries) and totals_dev[1] (large primitives).
+cudaError_t grid_count(const DevScene& S, uint32_t light, uint32_t res, DevGrid* grid_dev, unsigned long long* bounds, uint32_t* counts, uint32_t* starts,
+                       void* scan_tmp, size_t scan_bytes, uint2* large, uint32_t* totals_dev, cudaStream_t st) {
     const size_t nc = grid_cells(res);
     const uint32_t n = S.n_sph + S.n_cub + S.n_tri;
     cudaError_t e;
+    unsigned long long init[6 * kBoundWords] = {};
+    for (int f = 0; f < 6; f++) { init[kBoundWords * f] = init[kBoundWords * f + 2] = ~0ull; }      // min keys: all ones; max keys and the sums: zero
+    if ((e = cudaMemcpyAsync(bounds, init, sizeof init, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;      // (pageable source: copied before the call returns)
     if ((e = cudaMemsetAsync(counts, 0, (nc + 1) * 4, st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(n_large_dev, 0, 4, st)) != cudaSuccess) return e;
-    k_grid_pass<0><<<(n + 255) / 256, 256, 0, st>>>(S, light, res, kGridLargeCells, kGridLargeCap, counts, nullptr, nullptr, large, n_large_dev);
+    if ((e = cudaMemsetAsync(totals_dev, 0, 8, st)) != cudaSuccess) return e;
+    const bool timing = getenv("LGB_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (!timing) return; cudaStreamSynchronize(st); fprintf(stderr, "[light grids]     light %u %-14s %.2f ms\n", light, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); t0 = std::chrono::steady_clock::now(); };
+    lap("memsets");
+    k_grid_bounds<<<(n + 255) / 256, 256, 0, st>>>(S, light, kGridSmallSpan, bounds);
+    lap("k_grid_bounds");
+    double cell_factor = 1.0;                        // cells no finer than this times the average small footprint (env LGB_GRID_CELL: experiments)
+    if (const char* ev = getenv("LGB_GRID_CELL")) cell_factor = atof(ev);
+    k_grid_map<<<1, 32, 0, st>>>(bounds, res, cell_factor, grid_dev);
+    k_grid_pass<0><<<(n + 255) / 256, 256, 0, st>>>(S, light, grid_dev, res, kGridLargeCells, kGridLargeCap, counts, nullptr, nullptr, large, totals_dev + 1);
+    lap("count pass");
     if ((e = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, counts, starts, (int)(nc + 1), st)) != cudaSuccess) return e;
-    uint32_t h[2] = {0, 0};
-    if ((e = cudaMemcpyAsync(&h[0], starts + nc, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(&h[1], n_large_dev, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-    *total_out = h[0]; *n_large_out = h[1];
+    lap("scan");
+    if ((e = cudaMemcpyAsync(totals_dev, starts + nc, 4, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
-cudaError_t grid_fill(const DevScene& S, uint32_t light, uint32_t res, uint32_t* counts, const uint32_t* starts, uint2* entries,
+cudaError_t grid_fill(const DevScene& S, uint32_t light, uint32_t res, const DevGrid* grid_dev, uint32_t* counts, const uint32_t* starts, uint2* entries,
                       uint2* large, uint32_t n_large, cudaStream_t st) {
     const size_t nc = grid_cells(res);
     const uint32_t n = S.n_sph + S.n_cub + S.n_tri;
-    k_grid_pass<1><<<(n + 255) / 256, 256, 0, st>>>(S, light, res, kGridLargeCells, kGridLargeCap, counts, starts, entries, nullptr, nullptr);
+    cudaError_t e;
+    // the counts of THIS light again (the buffer is shared by the lights): pass 1 consumes them as cursors
+    if ((e = cudaMemsetAsync(counts, 0, (nc + 1) * 4, st)) != cudaSuccess) return e;
+    const bool timing = getenv("LGB_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (!timing) return; cudaStreamSynchronize(st); fprintf(stderr, "[light grids]     light %u %-14s %.2f ms\n", light, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); t0 = std::chrono::steady_clock::now(); };
+    k_grid_pass<0><<<(n + 255) / 256, 256, 0, st>>>(S, light, grid_dev, res, kGridLargeCells, 0u, counts, nullptr, nullptr, nullptr, counts + nc);
+    lap("recount");
+    k_grid_pass<1><<<(n + 255) / 256, 256, 0, st>>>(S, light, grid_dev, res, kGridLargeCells, kGridLargeCap, counts, starts, entries, nullptr, nullptr);
+    lap("fill pass");
     k_grid_sort<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(starts, entries, nc);
+    lap("sort");
     if (n_large > 1) k_grid_sort_large<<<1, 32, 0, st>>>(large, n_large);
     return cudaGetLastError();
 }

@@ -7,7 +7,7 @@
 namespace lgb {
 
 constexpr uint32_t kGridLargeCells = 4096;   // a footprint of more cells than this goes to the light's `large` list
-constexpr uint32_t kGridLargeCap = 64;       // more large primitives than this: no grid for that light (BVH shadow rays instead)
+constexpr uint32_t kGridLargeCap = 128;      // more large primitives than this: no grid for that light (BVH shadow rays instead)
 
 // Camera grid (primary rays of a perspective camera): host-computed parameters of the binning pass.
 struct CamGridParams {
@@ -26,9 +26,10 @@ size_t scan_bytes_for(size_t n_cells);
 
 size_t grid_cells(uint32_t res);
 size_t grid_scan_bytes(uint32_t res);
-cudaError_t grid_count(const DevScene& S, uint32_t light, uint32_t res, uint32_t* counts, uint32_t* starts, void* scan_tmp, size_t scan_bytes,
-                       uint2* large, uint32_t* n_large_dev, cudaStream_t st, uint32_t* total_out, uint32_t* n_large_out);
-cudaError_t grid_fill(const DevScene& S, uint32_t light, uint32_t res, uint32_t* counts, const uint32_t* starts, uint2* entries,
+constexpr double kGridSmallSpan = 0.25;      // footprints up to this much of a face's [-1, 1] per axis shape the face's mapping
+cudaError_t grid_count(const DevScene& S, uint32_t light, uint32_t res, DevGrid* grid_dev, unsigned long long* bounds, uint32_t* counts, uint32_t* starts,
+                       void* scan_tmp, size_t scan_bytes, uint2* large, uint32_t* totals_dev, cudaStream_t st);
+cudaError_t grid_fill(const DevScene& S, uint32_t light, uint32_t res, const DevGrid* grid_dev, uint32_t* counts, const uint32_t* starts, uint2* entries,
                       uint2* large, uint32_t n_large, cudaStream_t st);
 
 }  // namespace lgb

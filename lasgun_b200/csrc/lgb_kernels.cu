@@ -1367,6 +1367,7 @@ __global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, LGB_CPRIMARY_BLOCKS) k_c
             const size_t cell = (size_t)(y >> W.cg_shift) * W.cg_nx + (size_t)(x >> W.cg_shift);
             const uint32_t b = __ldg(W.cg_start + cell), e = __ldg(W.cg_start + cell + 1);
             const float to_t = f.inv_len * (1.0f - 2e-6f);                   // an entry's distance from the eye -> a lower bound of its ray parameter
+            const bool sorted = e - b <= kGridSortMax;                       // (longer lists are not sorted: lgb_grid.cu)
 #if LGB_WALK_PREFETCH
             uint2 nxt = b < e ? __ldg(W.cg_entries + b) : make_uint2(0u, 0u);
             for (uint32_t i = b; i < e; i++) {
@@ -1376,7 +1377,7 @@ __global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, LGB_CPRIMARY_BLOCKS) k_c
             for (uint32_t i = b; i < e; i++) {
                 const uint2 r = __ldg(W.cg_entries + i);
 #endif
-                if (__uint_as_float(r.y) * to_t > T.best_up) break;          // nearest first: nothing behind the best hit can beat it
+                if (__uint_as_float(r.y) * to_t > T.best_up) { if (sorted) break; else continue; }    // nearest first: nothing behind the best hit can beat it
                 leaf_prims<false, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, CUDART_INF, lc);
             }
             for (uint32_t i = 0; i < W.cg_n_large; i++) {
@@ -1733,10 +1734,12 @@ __device__ __forceinline__ bool grid_blocked(const DevScene& S, D3 o, uint32_t l
     if (da == 0.0) return false;                                       // the light sits on the shadow origin: nothing lies between
     const DevGrid* G = S.grids + l;
     const uint32_t res = __ldg(&G->res), n_large = __ldg(&G->n_large);
-    const double inv = fast_rcp(fabs(da)), half = 0.5 * (double)res;
-    const int cu = min(max((int)floor(fma(db * inv, half, half)), 0), (int)res - 1);
-    const int cv = min(max((int)floor(fma(dc * inv, half, half)), 0), (int)res - 1);
-    const size_t cell = ((size_t)(2 * a + (da < 0.0 ? 1 : 0)) * res + (size_t)cv) * res + (size_t)cu;
+    const int face = 2 * a + (da < 0.0 ? 1 : 0);
+    const double* map = G->map[face];                                   // the face's cells cover [u0, u0 + res / su] x [v0, v0 + res / sv]; outside clamps to the border
+    const double inv = fast_rcp(fabs(da));
+    const int cu = min(max((int)floor((db * inv - __ldg(map)) * __ldg(map + 1)), 0), (int)res - 1);
+    const int cv = min(max((int)floor((dc * inv - __ldg(map + 2)) * __ldg(map + 3)), 0), (int)res - 1);
+    const size_t cell = ((size_t)face * res + (size_t)cv) * res + (size_t)cu;
     const uint32_t* cs = G->cell_start;
     const uint32_t b = __ldg(cs + cell), e = __ldg(cs + cell + 1);
     Ray64 ray; RayF f; Trav T;
@@ -1744,6 +1747,7 @@ __device__ __forceinline__ bool grid_blocked(const DevScene& S, D3 o, uint32_t l
     const float dd = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
     const float len_up = dd * f.inv_len * (1.0f + 1e-5f) + f.err;     // an entry that starts farther from the light than the ray does cannot block it
     bool hit = false;
+    const bool sorted = e - b <= kGridSortMax;                         // (longer lists are not sorted: lgb_grid.cu)
     const uint2* en = G->entries;
 #if LGB_WALK_PREFETCH
     uint2 nxt = b < e ? __ldg(en + b) : make_uint2(0u, 0u);
@@ -1754,7 +1758,7 @@ __device__ __forceinline__ bool grid_blocked(const DevScene& S, D3 o, uint32_t l
     for (uint32_t i = b; i < e && !hit; i++) {
         const uint2 r = __ldg(en + i);
 #endif
-        if (__uint_as_float(r.y) > len_up) break;
+        if (__uint_as_float(r.y) > len_up) { if (sorted) break; else continue; }
         hit = leaf_prims<true, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, 1.0, lc);
     }
     const uint2* lg = G->large;
@@ -2559,8 +2563,8 @@ bool render_fused(uint32_t spp) { return spp >= 1 && spp <= 256; }      // and !
 #define LGB_SURFACE_FUSED 0          // measured (mixed4k): k_surface 16.0 ms against 2.7 + 7.4 + 4.0 ms for k_setup + k_gshadow + k_shade_lean -- the walk's
 #endif                               // spills on top of the shading state leave L1 (29.6 GB of DRAM writes per frame, profiles/r2_v8_ncu_k_surface.txt)
 #ifndef LGB_SETUP_FUSED
-#define LGB_SETUP_FUSED 1
-#endif
+#define LGB_SETUP_FUSED 0            // measured (mixed4k): k_gshadow<SETUP> 11.5 ms against k_setup 2.7 + k_gshadow 7.4 ms -- like k_surface, the walk
+#endif                               // kernel pays more for the added live state than the 48 B/slot of ps traffic it saves
 // k_gshadow<SETUP> does the hit setup itself for camera rays of scenes with light grids, unless a per-sample buffer is asked for
 bool setup_fused(const DevScene& S, const DevWork& W, const DevOut& O, bool all_shadows) {
     return LGB_SETUP_FUSED && S.grids && !S.instanced && !all_shadows && !O.aov_id && !O.aov_t && !O.aov_occl && W.mode != 3;

@@ -32,11 +32,14 @@ struct DevSpace {
 // Light grid (lgb_grid.cu): cube map around a point light, 6 faces x res^2 cells; cell (face, v, u) lists the primitives whose
 // direction footprint seen from the light touches it as (type << 30 | index, lower bound of the distance from the light as float
 // bits), nearest first; `large`: the primitives with footprints of more than kGridLargeCells cells, tested by every ray.
+constexpr uint32_t kGridSortMax = 96;   // a cell's list is sorted nearest-first iff it holds at most this many entries
 struct DevGrid {
     const uint32_t* cell_start;   // 6 res^2 + 1
     const uint2* entries;
     const uint2* large;
     uint32_t res, n_large;
+    double map[6][4];             // per face {u0, su, v0, sv}: direction (u, v) lies in cell (floor((u - u0) su), floor((v - v0) sv)), clamped to the
+                                  // face's res x res cells -- the cells are laid over the part of the face the scene's small primitives cover
 };
 
 // All pointers are device pointers.  Layout:
