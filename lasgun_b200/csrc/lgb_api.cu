@@ -646,10 +646,13 @@ static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
         std::vector<Head> heads(nl);
         for (uint32_t l = 0; l < nl; l++) {
             const uint32_t total = h_tot[2 * l], n_large = h_tot[2 * l + 1];
-            uint2* entries = nullptr; uint2* large = nullptr;
+            uint2* entries = nullptr; uint2* large = nullptr; uint2* entries_tmp = nullptr; void* sort_tmp = nullptr;
+            const size_t sort_bytes = grid_sort_bytes(total, nc);
             GR(alloc(mine, sizeof(uint2) * (size_t)total, (void**)&entries));
             GR(alloc(mine, sizeof(uint2) * (size_t)n_large, (void**)&large));
-            GR(grid_fill(S, l, res, dtab + l, counts, starts[l], entries, large_tmp + (size_t)kGridLargeCap * l, n_large, st));
+            GR(alloc(temp, sizeof(uint2) * (size_t)total, (void**)&entries_tmp));
+            GR(alloc(temp, sort_bytes, &sort_tmp));
+            GR(grid_fill(S, l, res, dtab + l, counts, starts[l], entries_tmp, entries, total, sort_tmp, sort_bytes, large_tmp + (size_t)kGridLargeCap * l, n_large, st));
             if (n_large) GR(cudaMemcpyAsync(large, large_tmp + (size_t)kGridLargeCap * l, sizeof(uint2) * n_large, cudaMemcpyDeviceToDevice, st));
             heads[l] = Head{starts[l], entries, large, res, n_large};
             bytes += (nc + 1) * 4 + sizeof(uint2) * ((size_t)total + n_large); entries_all += total;
@@ -1142,8 +1145,13 @@ static int ensure_camgrid(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint
         CU(c, camgrid_count(S, P, counts, (uint32_t*)G.starts, scan_tmp, scan_bytes, (uint2*)G.large, n_large_dev, st, &total, &n_large));
         if (n_large > kGridLargeCap) G.refused = true;
         else {
+            void* entries_tmp = nullptr; void* sort_tmp = nullptr;
+            const size_t sort_bytes = grid_sort_bytes(total, nc);
             CU(c, cudaMallocAsync(&G.entries, sizeof(uint2) * std::max<size_t>(total, 1), st));
-            CU(c, camgrid_fill(S, P, counts, (const uint32_t*)G.starts, (uint2*)G.entries, (uint2*)G.large, n_large, st));
+            CU(c, cudaMallocAsync(&entries_tmp, sizeof(uint2) * std::max<size_t>(total, 1), st));
+            CU(c, cudaMallocAsync(&sort_tmp, std::max<size_t>(sort_bytes, 16), st));
+            CU(c, camgrid_fill(S, P, counts, (const uint32_t*)G.starts, (uint2*)entries_tmp, (uint2*)G.entries, total, sort_tmp, sort_bytes, (uint2*)G.large, n_large, st));
+            cudaFreeAsync(entries_tmp, st); cudaFreeAsync(sort_tmp, st);
             G.valid = true; G.shift = P.shift; G.nx = P.nx; G.n_large = n_large; G.bytes = (nc + 1) * 4 + sizeof(uint2) * ((size_t)total + n_large);
         }
         cudaFreeAsync(counts, st); cudaFreeAsync(scan_tmp, st); cudaFreeAsync(n_large_dev, st);

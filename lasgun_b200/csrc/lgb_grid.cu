@@ -12,6 +12,7 @@
 // Built on the device at scene creation from the leaf-ordered primitive arrays: count -> exclusive scan (cub::DeviceScan,
 // off the frame's path) -> fill -> per-cell sort by distance.  Single-space scenes only (no transformed aggregates).
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_sort.cuh>
 
 #include <string.h>
 #include <stdio.h>
@@ -131,9 +132,10 @@ __global__ void k_grid_map(const unsigned long long* bounds, uint32_t res, doubl
     const unsigned long long* b = bounds + kBoundWords * f;
     double u0 = dkey_inv(b[0]), u1 = dkey_inv(b[1]), v0 = dkey_inv(b[2]), v1 = dkey_inv(b[3]);
     const double* sum = reinterpret_cast<const double*>(b + 4);
-    if (!(u0 <= u1) || !(v0 <= v1) || !(sum[2] > 0.0)) { u0 = v0 = -1.0; u1 = v1 = 1.0; }          // nothing small on this face
+    if (!(u0 <= u1) || !(v0 <= v1) || !(sum[2] > 0.0) || cell_factor < 0.0) { u0 = v0 = -1.0; u1 = v1 = 1.0; }          // nothing small on this face (cell_factor < 0: the whole face, experiments)
     const double au = sum[2] > 0.0 ? sum[0] / sum[2] : 0.0, av = sum[2] > 0.0 ? sum[1] / sum[2] : 0.0;
-    const double cu = fmax(fmax(u1 - u0, 1e-6) / (double)res, cell_factor * au), cv = fmax(fmax(v1 - v0, 1e-6) / (double)res, cell_factor * av);
+    const double cf = fmax(cell_factor, 0.0);
+    const double cu = fmax(fmax(u1 - u0, 1e-6) / (double)res, cf * au), cv = fmax(fmax(v1 - v0, 1e-6) / (double)res, cf * av);
     grid->map[f][0] = u0; grid->map[f][1] = 1.0 / cu; grid->map[f][2] = v0; grid->map[f][3] = 1.0 / cv;
 }
 
@@ -170,40 +172,9 @@ __global__ void __launch_bounds__(256) k_grid_pass(DevScene S, uint32_t light, c
     }
 }
 
-// nearest first (ties by primitive: the order of the atomics must not show), so that a ray stops at the first entry beyond its own
-// length.  Short lists by insertion, long ones by heap sort (a cell seen edge-on through a dense mesh can hold hundreds of entries).
 __device__ __forceinline__ bool entry_less(uint2 x, uint2 y) {
     const float kx = __uint_as_float(x.y), ky = __uint_as_float(y.y);
     return kx < ky || (kx == ky && x.x < y.x);
-}
-__global__ void __launch_bounds__(256) k_grid_sort(const uint32_t* starts, uint2* entries, size_t n_cells) {
-    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= n_cells) return;
-    const uint32_t b = starts[cell], e = starts[cell + 1], n = e - b;
-    if (n < 2 || n > kGridSortMax) return;                  // (a longer list stays as the atomics left it: the walks do not stop early in it)
-    uint2* a = entries + b;
-    if (n <= 24) {
-        for (uint32_t i = 1; i < n; i++) {
-            const uint2 x = a[i];
-            uint32_t j = i;
-            while (j > 0 && entry_less(x, a[j - 1])) { a[j] = a[j - 1]; j--; }
-            a[j] = x;
-        }
-        return;
-    }
-    auto sift = [&](uint32_t root, uint32_t end) {           // max-heap on entry_less
-        const uint2 x = a[root];
-        for (;;) {
-            uint32_t child = 2 * root + 1;
-            if (child >= end) break;
-            if (child + 1 < end && entry_less(a[child], a[child + 1])) child++;
-            if (!entry_less(x, a[child])) break;
-            a[root] = a[child]; root = child;
-        }
-        a[root] = x;
-    };
-    for (uint32_t i = n / 2; i-- > 0;) sift(i, n);
-    for (uint32_t end = n - 1; end > 0; end--) { const uint2 t = a[0]; a[0] = a[end]; a[end] = t; sift(0, end); }
 }
 __global__ void k_grid_sort_large(uint2* large, uint32_t n) {
     if (blockIdx.x || threadIdx.x) return;
@@ -263,6 +234,20 @@ __global__ void __launch_bounds__(256) k_cam_pass(DevScene S, CamGridParams P, u
 
 }  // namespace
 
+// Every cell's entries nearest first: the record (ref, dmin bits) read as one little-endian u64 is (dmin << 32) | ref, and the bits of
+// a non-negative float order like the float, so one segmented key sort (cub::DeviceSegmentedSort, off the frame's path like the scans)
+// over the cell ranges does it for lists of any length -- a thread per cell was held up for milliseconds by the few cells that hold
+// hundreds of entries.
+size_t grid_sort_bytes(uint32_t total, size_t n_cells) {
+    size_t b = 0;
+    cub::DeviceSegmentedSort::SortKeys(nullptr, b, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)total, (int)n_cells, (const uint32_t*)nullptr, (const uint32_t*)nullptr);
+    return b;
+}
+static cudaError_t sort_cells(const uint2* in, uint2* out, uint32_t total, const uint32_t* starts, size_t n_cells, void* tmp, size_t tmp_bytes, cudaStream_t st) {
+    if (total == 0) return cudaSuccess;
+    return cub::DeviceSegmentedSort::SortKeys(tmp, tmp_bytes, reinterpret_cast<const unsigned long long*>(in), reinterpret_cast<unsigned long long*>(out), (int)total, (int)n_cells,
+                                              starts, starts + 1, st);
+}
 cudaError_t camgrid_count(const DevScene& S, const CamGridParams& P, uint32_t* counts, uint32_t* starts, void* scan_tmp, size_t scan_bytes,
                           uint2* large, uint32_t* n_large_dev, cudaStream_t st, uint32_t* total_out, uint32_t* n_large_out) {
     const size_t nc = (size_t)P.nx * P.ny;
@@ -279,11 +264,12 @@ cudaError_t camgrid_count(const DevScene& S, const CamGridParams& P, uint32_t* c
     *total_out = h[0]; *n_large_out = h[1];
     return cudaGetLastError();
 }
-cudaError_t camgrid_fill(const DevScene& S, const CamGridParams& P, uint32_t* counts, const uint32_t* starts, uint2* entries, uint2* large, uint32_t n_large, cudaStream_t st) {
+cudaError_t camgrid_fill(const DevScene& S, const CamGridParams& P, uint32_t* counts, const uint32_t* starts, uint2* entries_tmp, uint2* entries, uint32_t total,
+                         void* sort_tmp, size_t sort_bytes, uint2* large, uint32_t n_large, cudaStream_t st) {
     const size_t nc = (size_t)P.nx * P.ny;
     const uint32_t n = S.n_sph + S.n_cub + S.n_tri;
-    k_cam_pass<1><<<(n + 255) / 256, 256, 0, st>>>(S, P, counts, starts, entries, nullptr, nullptr);
-    k_grid_sort<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(starts, entries, nc);
+    k_cam_pass<1><<<(n + 255) / 256, 256, 0, st>>>(S, P, counts, starts, entries_tmp, nullptr, nullptr);
+    if (cudaError_t e = sort_cells(entries_tmp, entries, total, starts, nc, sort_tmp, sort_bytes, st)) return e;
     if (n_large > 1) k_grid_sort_large<<<1, 32, 0, st>>>(large, n_large);
     return cudaGetLastError();
 }
@@ -323,8 +309,8 @@ cudaError_t grid_count(const DevScene& S, uint32_t light, uint32_t res, DevGrid*
     if ((e = cudaMemcpyAsync(totals_dev, starts + nc, 4, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
-cudaError_t grid_fill(const DevScene& S, uint32_t light, uint32_t res, const DevGrid* grid_dev, uint32_t* counts, const uint32_t* starts, uint2* entries,
-                      uint2* large, uint32_t n_large, cudaStream_t st) {
+cudaError_t grid_fill(const DevScene& S, uint32_t light, uint32_t res, const DevGrid* grid_dev, uint32_t* counts, const uint32_t* starts, uint2* entries_tmp, uint2* entries,
+                      uint32_t total, void* sort_tmp, size_t sort_bytes, uint2* large, uint32_t n_large, cudaStream_t st) {
     const size_t nc = grid_cells(res);
     const uint32_t n = S.n_sph + S.n_cub + S.n_tri;
     cudaError_t e;
@@ -335,9 +321,9 @@ cudaError_t grid_fill(const DevScene& S, uint32_t light, uint32_t res, const Dev
     auto lap = [&](const char* what) { if (!timing) return; cudaStreamSynchronize(st); fprintf(stderr, "[light grids]     light %u %-14s %.2f ms\n", light, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); t0 = std::chrono::steady_clock::now(); };
     k_grid_pass<0><<<(n + 255) / 256, 256, 0, st>>>(S, light, grid_dev, res, kGridLargeCells, 0u, counts, nullptr, nullptr, nullptr, counts + nc);
     lap("recount");
-    k_grid_pass<1><<<(n + 255) / 256, 256, 0, st>>>(S, light, grid_dev, res, kGridLargeCells, kGridLargeCap, counts, starts, entries, nullptr, nullptr);
+    k_grid_pass<1><<<(n + 255) / 256, 256, 0, st>>>(S, light, grid_dev, res, kGridLargeCells, kGridLargeCap, counts, starts, entries_tmp, nullptr, nullptr);
     lap("fill pass");
-    k_grid_sort<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(starts, entries, nc);
+    if ((e = sort_cells(entries_tmp, entries, total, starts, nc, sort_tmp, sort_bytes, st)) != cudaSuccess) return e;
     lap("sort");
     if (n_large > 1) k_grid_sort_large<<<1, 32, 0, st>>>(large, n_large);
     return cudaGetLastError();

@@ -21,7 +21,8 @@ struct CamGridParams {
 };
 cudaError_t camgrid_count(const DevScene& S, const CamGridParams& P, uint32_t* counts, uint32_t* starts, void* scan_tmp, size_t scan_bytes,
                           uint2* large, uint32_t* n_large_dev, cudaStream_t st, uint32_t* total_out, uint32_t* n_large_out);
-cudaError_t camgrid_fill(const DevScene& S, const CamGridParams& P, uint32_t* counts, const uint32_t* starts, uint2* entries, uint2* large, uint32_t n_large, cudaStream_t st);
+cudaError_t camgrid_fill(const DevScene& S, const CamGridParams& P, uint32_t* counts, const uint32_t* starts, uint2* entries_tmp, uint2* entries, uint32_t total,
+                         void* sort_tmp, size_t sort_bytes, uint2* large, uint32_t n_large, cudaStream_t st);
 size_t scan_bytes_for(size_t n_cells);
 
 size_t grid_cells(uint32_t res);
@@ -29,7 +30,8 @@ size_t grid_scan_bytes(uint32_t res);
 constexpr double kGridSmallSpan = 0.25;      // footprints up to this much of a face's [-1, 1] per axis shape the face's mapping
 cudaError_t grid_count(const DevScene& S, uint32_t light, uint32_t res, DevGrid* grid_dev, unsigned long long* bounds, uint32_t* counts, uint32_t* starts,
                        void* scan_tmp, size_t scan_bytes, uint2* large, uint32_t* totals_dev, cudaStream_t st);
-cudaError_t grid_fill(const DevScene& S, uint32_t light, uint32_t res, const DevGrid* grid_dev, uint32_t* counts, const uint32_t* starts, uint2* entries,
-                      uint2* large, uint32_t n_large, cudaStream_t st);
+size_t grid_sort_bytes(uint32_t total, size_t n_cells);
+cudaError_t grid_fill(const DevScene& S, uint32_t light, uint32_t res, const DevGrid* grid_dev, uint32_t* counts, const uint32_t* starts, uint2* entries_tmp, uint2* entries,
+                      uint32_t total, void* sort_tmp, size_t sort_bytes, uint2* large, uint32_t n_large, cudaStream_t st);
 
 }  // namespace lgb

@@ -32,7 +32,7 @@ struct DevSpace {
 // Light grid (lgb_grid.cu): cube map around a point light, 6 faces x res^2 cells; cell (face, v, u) lists the primitives whose
 // direction footprint seen from the light touches it as (type << 30 | index, lower bound of the distance from the light as float
 // bits), nearest first; `large`: the primitives with footprints of more than kGridLargeCells cells, tested by every ray.
-constexpr uint32_t kGridSortMax = 96;   // a cell's list is sorted nearest-first iff it holds at most this many entries
+constexpr uint32_t kGridSortMax = 0xFFFFFFFFu;   // every cell's list is sorted nearest first (cub::DeviceSegmentedSort, lgb_grid.cu)
 struct DevGrid {
     const uint32_t* cell_start;   // 6 res^2 + 1
     const uint2* entries;
