@@ -240,6 +240,7 @@ def quick_config(N, ctx, name, args, film_cache):
         t0 = time.perf_counter()
         flat = N.FlatScene(host, lazy=True)
         hs = C.c_void_p()
+        flat.desc.expected_film_pixels = w * h          # capture(scene, film) knows its film
         ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat.desc), C.byref(hs)))
         ctx.check(L.lgb_capture(ctx.h, hs, w, h, host_film.ctypes.data_as(C.POINTER(C.c_uint8)), None))
         L.lgb_scene_destroy(hs)
@@ -372,6 +373,7 @@ def run_gpu(args):
                 flat_i = N.FlatScene(hscene_host, lazy=True)   # Accel::from minus the reference BVH build: that runs (callback) only if a ray meets an exact-t tie
                 t1 = time.perf_counter()
                 hscene = C.c_void_p()
+                flat_i.desc.expected_film_pixels = w * h          # capture(scene, film) knows its film
                 ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat_i.desc), C.byref(hscene)))
                 t2 = time.perf_counter()
                 ctx.check(L.lgb_capture(ctx.h, hscene, w, h, target.ctypes.data_as(C.POINTER(C.c_uint8)), None))
@@ -412,6 +414,7 @@ def run_gpu(args):
                     fl = N.FlatScene(hscene_host, lazy=True)
                     t1 = time.perf_counter()
                     hs = C.c_void_p()
+                    fl.desc.expected_film_pixels = w * h          # capture(scene, film) knows its film
                     gctx.check(L.lgb_scene_create(gctx.h, C.byref(fl.desc), C.byref(hs)))
                     t2 = time.perf_counter()
                     st_g = N.Stats()

@@ -148,7 +148,9 @@ typedef struct lgb_scene_desc {
     double ambient[3];                                       /* scene.rs:22 */
     double bg_inner[3], bg_outer[3], bg_scale;               /* material/background.rs:6-10 */
     uint32_t recursion;                                      /* scene.recursion (scene.rs:60, default 3): Whitted depth, at most 12 */
-    uint32_t reserved;
+    uint32_t expected_film_pixels;                           /* hint, 0 = unknown: w * h of the film `capture` is about to fill (lib.rs:55 knows it).
+                                                              * With it lgb_scene_create can tell whether the frame will walk the device BVH at all
+                                                              * and leave the tree unbuilt otherwise (LGB_OPT_LAZY_BVH); results never depend on it. */
     lgb_reference_tree_fn reference_tree;                    /* lazy mode (nodes == NULL), else NULL */
     void* reference_tree_user;
     double bounds_lo[3], bounds_hi[3];                       /* lazy mode: world box of all primitives */
@@ -199,6 +201,13 @@ typedef struct lgb_stats {
 int lgb_film_alloc_shared(lgb_ctx* ctx, uint64_t bytes, void** d_film, uint8_t handle_out[LGB_IPC_HANDLE_BYTES]);
 int lgb_film_open_shared(lgb_ctx* ctx, const uint8_t handle[LGB_IPC_HANDLE_BYTES], void** d_film);
 int lgb_film_release_shared(lgb_ctx* ctx, void* d_film, int owner);   /* owner != 0: cudaFree, else cudaIpcCloseMemHandle */
+/* End-of-frame flags for a shared film: words of the SAME shared allocation (allocate a little more than w*h*4).  lgb_film_signal
+ * queues, behind the caller's kernels on `stream`, a system-fenced store of `value` into *d_flag (own or peer memory);
+ * lgb_film_wait queues a kernel that returns once the n words d_flags[(first + i) * stride_bytes / 4] have all reached `value`
+ * (values only grow; it gives up after minutes instead of hanging the GPU).  A rank signals its word when its tiles are stored,
+ * rank 0 waits for all of them: the frame barrier costs two microsecond kernels and no collective (lasgun_b200/multi.py). */
+int lgb_film_signal(lgb_ctx* ctx, void* d_flag, uint32_t value, void* stream);
+int lgb_film_wait(lgb_ctx* ctx, const void* d_flags, uint32_t first, uint32_t n, uint32_t stride_bytes, uint32_t value, void* stream);
 
 /* Device / context --------------------------------------------------------------------- */
 int lgb_device_count(void);
@@ -231,6 +240,10 @@ void lgb_shutdown(lgb_ctx* ctx);
 #define LGB_OPT_WAVE_BUDGET_MB 7    /* memory (MB, default 16384) the per-sample wavefront buffers of one capture may take: a frame that needs more
                                      * is rendered in bands of macro tiles on the same buffers (any frame size in bounded memory).
                                      * env LGB_WAVE_BUDGET_MB presets it. */
+#define LGB_OPT_LAZY_BVH 8          /* 1 / -1 (default): a plastic scene large enough for the device-side builder is created WITHOUT its BVH when light
+                                     * grids will serve its shadow rays; the tree is built (6-8 ms for 0.6-1 M primitives) only if an entry point
+                                     * walks one (a frame the camera grid does not serve, lgb_trace_rays, lgb_scene_verify, lgb_scene_export).
+                                     * 0: always at lgb_scene_create.  env LGB_LAZY_BVH presets it. */
 int lgb_set_option(lgb_ctx* ctx, int option, int value);
 const char* lgb_last_error(lgb_ctx* ctx);          /* ctx may be NULL: last error of lgb_init */
 const char* lgb_status_string(int status);

@@ -180,6 +180,7 @@ struct FlatScene {
 struct BuildOptions {
     bool keep_levels = false;          // keep per-level reference arrays (tests)
     bool lazy_tree = false;            // defer the reference BVH build until the device needs it (exact-t ties only)
+    uint32_t expected_film_pixels = 0; // lgb_scene_desc.expected_film_pixels (capture fills it in)
 };
 
 FlatScene flatten(const Scene& scene, const BuildOptions& opt);   // Accel::from + flatten (bvh.rs:135-453)

@@ -21,7 +21,7 @@ LGB_LEAF_FLAG = 0x80000000
 # Every symbol include/lasgun_b200.h declares (checked by tests/test_abi.py without a GPU).
 ABI_SYMBOLS = [
     "lgb_build_probe", "lgb_device_count", "lgb_init", "lgb_init_devices", "lgb_context_devices", "lgb_set_option", "lgb_shutdown", "lgb_last_error", "lgb_status_string", "lgb_scene_create",
-    "lgb_film_alloc_shared", "lgb_film_open_shared", "lgb_film_release_shared", "lgb_scene_destroy", "lgb_scene_layout_bytes", "lgb_scene_export", "lgb_scene_import", "lgb_scene_verify", "lgb_scene_device_bytes", "lgb_scene_build_ms", "lgb_scene_node_count", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
+    "lgb_film_alloc_shared", "lgb_film_open_shared", "lgb_film_release_shared", "lgb_film_signal", "lgb_film_wait", "lgb_scene_destroy", "lgb_scene_layout_bytes", "lgb_scene_export", "lgb_scene_import", "lgb_scene_verify", "lgb_scene_device_bytes", "lgb_scene_build_ms", "lgb_scene_node_count", "lgb_capture", "lgb_capture_subset", "lgb_capture_aov",
     "lgb_capture_device", "lgb_capture_profile", "lgb_trace_rays", "lgb_debug_fastmath", "lgb_measure_l2_read_gbs", "lgb_measure_fp32_gops", "lgb_measure_fp64_gops",
 ]
 
@@ -61,7 +61,7 @@ class SceneDesc(C.Structure):
         ("lights", C.c_void_p), ("n_lights", C.c_uint64),
         ("camera", CameraDesc),
         ("ambient", C.c_double * 3), ("bg_inner", C.c_double * 3), ("bg_outer", C.c_double * 3), ("bg_scale", C.c_double),
-        ("recursion", C.c_uint32), ("reserved", C.c_uint32),
+        ("recursion", C.c_uint32), ("expected_film_pixels", C.c_uint32),
         ("reference_tree", C.c_void_p), ("reference_tree_user", C.c_void_p), ("bounds_lo", C.c_double * 3), ("bounds_hi", C.c_double * 3),
     ]
 
@@ -113,6 +113,8 @@ def lib():
         "lgb_film_alloc_shared": (C.c_int, [vp, C.c_uint64, C.POINTER(C.c_void_p), u8p]),
         "lgb_film_open_shared": (C.c_int, [vp, u8p, C.POINTER(C.c_void_p)]),
         "lgb_film_release_shared": (C.c_int, [vp, vp, C.c_int]),
+        "lgb_film_signal": (C.c_int, [vp, vp, C.c_uint32, vp]),
+        "lgb_film_wait": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
         "lgb_scene_layout_bytes": (C.c_uint64, []),
         "lgb_scene_export": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
         "lgb_scene_import": (C.c_int, [vp, vp, C.c_uint64, vp, C.POINTER(C.c_void_p)]),
@@ -363,6 +365,10 @@ class Context:
     def set_wave_budget_mb(self, mb: int):
         """LGB_OPT_WAVE_BUDGET_MB: per-sample buffers of one band of a frame (default 16384)."""
         self.check(lib().lgb_set_option(self.h, 7, int(mb)))
+
+    def set_lazy_bvh(self, mode: int):
+        """LGB_OPT_LAZY_BVH (read at scene creation): 0 build the device BVH with the scene, 1 / -1 only when something walks it."""
+        self.check(lib().lgb_set_option(self.h, 8, int(mode)))
 
     def set_camera_grid(self, mode: int):
         """LGB_OPT_CAMERA_GRID: 1 on, 0 off, -1 automatic (the default)."""

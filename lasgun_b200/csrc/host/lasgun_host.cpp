@@ -768,6 +768,7 @@ std::unique_ptr<Accel> Accel::from(const Scene& scene, lgb_ctx* ctx, const Build
     a->ctx = ctx ? ctx : default_context();
     a->flat = flatten(scene, opt);
     lgb_scene_desc d; a->flat.describe(&d);
+    d.expected_film_pixels = opt.expected_film_pixels;
     int rc = lgb_scene_create(a->ctx, &d, &a->dev);
     if (rc) throw Error(rc, std::string("lgb_scene_create: ") + lgb_last_error(a->ctx));
     return a;
@@ -776,6 +777,7 @@ Accel::~Accel() { if (dev) lgb_scene_destroy(dev); }
 
 void capture(const Scene& scene, Film& film) {                   // lib.rs:55-104
     BuildOptions opt; opt.lazy_tree = true;                      // the reference BVH is built only if a ray meets an exact-t tie
+    opt.expected_film_pixels = (uint64_t)film.w * film.h < (1ull << 32) ? film.w * film.h : 0u;      // capture knows its film: lets the device skip a BVH no ray will walk
     std::unique_ptr<Accel> root = Accel::from(scene, nullptr, opt);
     int rc = lgb_capture(root->ctx, root->dev, film.w, film.h, film.data(), nullptr);
     if (rc) throw Error(rc, std::string("lgb_capture: ") + lgb_last_error(root->ctx));

@@ -33,6 +33,8 @@ cudaError_t launch_l2_read(const void* buf, uint64_t bytes, int iters, float* si
 cudaError_t launch_fp32_peak(int iters, float* sink, int sms, cudaStream_t);
 cudaError_t launch_fp64_peak(int iters, double* sink, int sms, cudaStream_t);
 cudaError_t launch_fastmath(const double* x, uint64_t n, double* rcp, double* rsq, cudaStream_t);
+cudaError_t launch_flag_signal(void* flag, uint32_t value, cudaStream_t);
+cudaError_t launch_flag_wait(const void* flags, uint32_t first, uint32_t n, uint32_t stride_bytes, uint32_t value, cudaStream_t);
 }  // namespace lgb
 
 using namespace lgb;
@@ -81,6 +83,7 @@ struct lgb_ctx {
     int whitted_wavefront = 1;             // LGB_OPT_WHITTED: 1 level-by-level wavefront, 0 one thread per ray tree (k_secondary)
     int beams = -1;                        // LGB_OPT_BEAMS: 0 off, 1 on, -1 automatic
     uint64_t wave_budget = 16ull << 30;    // LGB_OPT_WAVE_BUDGET_MB: bytes of per-sample buffers one band of a frame may take
+    int lazy_bvh = -1;                     // LGB_OPT_LAZY_BVH: 0 build the device BVH at scene creation, 1 / -1 only when something needs it
     int camera_grid = -1;                  // LGB_OPT_CAMERA_GRID: 0 off, 1 on, -1 automatic
     int light_grids = -1;                  // LGB_OPT_LIGHT_GRIDS: 0 off, 1 on, -1 automatic (scenes of >= 1024 BVH nodes, <= 8 lights)
     std::vector<uint32_t> tile_host;
@@ -113,6 +116,14 @@ struct lgb_scene {
     struct CamGrid { uint32_t w = 0, h = 0, shift = 0, nx = 0, n_large = 0; bool valid = false, refused = false; void* starts = nullptr; void* entries = nullptr; void* large = nullptr; uint64_t bytes = 0; double build_ms = 0; } camgrid;
     CamGrid& cam_grid() { return camgrid; }
     std::vector<void*> grid_allocs;    // light grids (lgb_grid.cu): table + per-light cell starts / entries / large lists, outside the arena
+    struct GridHost { void* starts; void* entries; void* large; size_t starts_bytes, entries_bytes, large_bytes; uint32_t res, n_large; };
+    std::vector<GridHost> grid_host;   // the same buffers with their sizes (device-group replication copies them to the peers)
+    void* grid_table = nullptr;
+    // deferred device BVH (LGB_OPT_LAZY_BVH): a plastic scene whose primary and shadow rays go through the grids never walks a tree, so
+    // lgb_scene_create stores the primitives in the caller's order, keeps the uploaded raw arrays and the item boxes, and ensure_bvh
+    // builds the tree (and re-orders the primitives, and rebuilds the grids) only if some entry point needs one
+    struct Deferred { void* scratch = nullptr; RawScene raw{}; GItem* items = nullptr; GItem* final_items = nullptr; LeafArrays la{};
+                      void* build_temp = nullptr; size_t build_bytes = 0, o_nodes = 0; uint32_t n = 0; double padd = 0; } deferred;
     double t_grids = 0;                // ms
     uint64_t grid_bytes = 0;
     std::vector<lgb_scene*> replicas;  // device group: the same scene on every peer, in peer order (arena copied over NVLink, not rebuilt)
@@ -173,6 +184,7 @@ int lgb_init(int device, lgb_ctx** out) {
     if (const char* e = std::getenv("LGB_BEAMS")) { const int v = std::atoi(e); c->beams = v < 0 ? -1 : (v != 0); }
     if (const char* e = std::getenv("LGB_LIGHT_GRIDS")) { const int v = std::atoi(e); c->light_grids = v < 0 ? -1 : (v != 0); }
     if (const char* e = std::getenv("LGB_WAVE_BUDGET_MB")) { const long v = std::atol(e); if (v >= 1) c->wave_budget = (uint64_t)v << 20; }
+    if (const char* e = std::getenv("LGB_LAZY_BVH")) { const int v = std::atoi(e); c->lazy_bvh = v < 0 ? -1 : (v != 0); }
     if (const char* e = std::getenv("LGB_CAMERA_GRID")) { const int v = std::atoi(e); c->camera_grid = v < 0 ? -1 : (v != 0); }
     c->side.n = 1;                         // one side stream: two lights' chains at a time (a third stream measured no further gain)
     cudaError_t ie = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -227,7 +239,7 @@ int lgb_init_devices(int ndev, const int* devices, lgb_ctx** out) {
             else if (!can) rc = fail(nullptr, LGB_ERR_UNSUPPORTED, "lgb_init_devices: a listed device cannot access the first one's memory (no NVLink / P2P path)");
         }
         if (rc) { const std::string msg = g_init_error; if (p) lgb_shutdown(p); lgb_shutdown(lead); g_init_error = msg; return rc; }
-        p->leader = lead; p->beams = lead->beams; p->light_grids = lead->light_grids; p->camera_grid = lead->camera_grid; p->wave_budget = lead->wave_budget;
+        p->leader = lead; p->beams = lead->beams; p->light_grids = lead->light_grids; p->camera_grid = lead->camera_grid; p->wave_budget = lead->wave_budget; p->lazy_bvh = lead->lazy_bvh;
         lead->peers.push_back(p);
     }
     *out = lead;
@@ -255,6 +267,18 @@ int lgb_film_open_shared(lgb_ctx* c, const uint8_t handle[LGB_IPC_HANDLE_BYTES],
     CU(c, cudaIpcOpenMemHandle(d_film, h, cudaIpcMemLazyEnablePeerAccess));
     return LGB_OK;
 }
+int lgb_film_signal(lgb_ctx* c, void* d_flag, uint32_t value, void* stream) {
+    if (!c || !d_flag) return fail(c, LGB_ERR_INVALID, "lgb_film_signal: NULL argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, launch_flag_signal(d_flag, value, stream ? (cudaStream_t)stream : c->stream));
+    return LGB_OK;
+}
+int lgb_film_wait(lgb_ctx* c, const void* d_flags, uint32_t first, uint32_t n, uint32_t stride_bytes, uint32_t value, void* stream) {
+    if (!c || !d_flags || n > 1024 || stride_bytes % 4) return fail(c, LGB_ERR_INVALID, "lgb_film_wait: bad argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, launch_flag_wait(d_flags, first, n, stride_bytes, value, stream ? (cudaStream_t)stream : c->stream));
+    return LGB_OK;
+}
 int lgb_film_release_shared(lgb_ctx* c, void* d_film, int owner) {
     if (!c || !d_film) return LGB_ERR_INVALID;
     CU(c, cudaSetDevice(c->device));
@@ -272,6 +296,7 @@ int lgb_set_option(lgb_ctx* c, int option, int value) {
     if (option == LGB_OPT_SIDE_STREAMS) { c->side_streams = value != 0; return LGB_OK; }
     if (option == LGB_OPT_LIGHT_GRIDS) { c->light_grids = value < 0 ? -1 : (value != 0); return LGB_OK; }
     if (option == LGB_OPT_CAMERA_GRID) { c->camera_grid = value < 0 ? -1 : (value != 0); return LGB_OK; }
+    if (option == LGB_OPT_LAZY_BVH) { c->lazy_bvh = value < 0 ? -1 : (value != 0); return LGB_OK; }
     if (option == LGB_OPT_WAVE_BUDGET_MB) { if (value < 1) return fail(c, LGB_ERR_INVALID, "lgb_set_option: budget must be at least 1 MB"); c->wave_budget = (uint64_t)value << 20; return LGB_OK; }
     return fail(c, LGB_ERR_INVALID, "lgb_set_option: unknown option");
 }
@@ -386,6 +411,7 @@ static int ensure_rank_tables(lgb_ctx* ctx, lgb_scene* s) {
     return LGB_OK;
 }
 
+extern "C" { static int ensure_bvh(lgb_ctx* ctx, lgb_scene* s); }      // (defined inside the extern "C" block below)
 // ---- export / import: the arena is position independent once DevScene's pointers are written as offsets
 namespace {
 struct SceneLayout { uint64_t magic, arena_bytes; DevScene dev; DevCamera cam; DevShade shade; double max_abs; };
@@ -462,6 +488,7 @@ int lgb_build_probe(const lgb_scene_desc* d, lgb_build_info* out) {
 int lgb_scene_verify(lgb_ctx* ctx, const lgb_scene* s, lgb_build_info* out) {
     if (!ctx || !s || !out || s->ctx != ctx) return fail(ctx, LGB_ERR_INVALID, "lgb_scene_verify: bad argument");
     if (s->dev.instanced) return fail(ctx, LGB_ERR_UNSUPPORTED, "lgb_scene_verify: single-space scenes only");
+    if (int rc = ensure_bvh(ctx, const_cast<lgb_scene*>(s))) return rc;
     std::memset(out, 0, sizeof *out);
     CU(ctx, cudaSetDevice(ctx->device));
     const DevScene& S = s->dev;
@@ -538,6 +565,7 @@ void lgb_scene_destroy(lgb_scene* s) {
         cudaStreamWaitEvent(s->ctx->stream, s->last_use, 0);
         cudaEventDestroy(s->last_use);
     }
+    if (s->deferred.scratch) cudaFreeAsync(s->deferred.scratch, s->ctx->stream);
     for (void* g : s->grid_allocs) cudaFreeAsync(g, s->ctx->stream);
     for (void* g : {s->camgrid.starts, s->camgrid.entries, s->camgrid.large}) if (g) cudaFreeAsync(g, s->ctx->stream);
     if (s->rank_buf) cudaFreeAsync(s->rank_buf, s->ctx->stream);
@@ -551,6 +579,7 @@ uint64_t lgb_scene_layout_bytes(void) { return sizeof(SceneLayout); }
 int lgb_scene_export(const lgb_scene* s, void* layout_out, uint64_t layout_bytes, void** arena_dev, uint64_t* arena_bytes) {
     if (!s || !layout_out || layout_bytes < sizeof(SceneLayout) || !arena_dev || !arena_bytes) return LGB_ERR_INVALID;
     if (s->lazy_fn) return LGB_ERR_UNSUPPORTED;       // a lazy scene's rank tables live outside the arena: create it with the tree to replicate it
+    if (int rc = ensure_bvh(s->ctx, const_cast<lgb_scene*>(s))) return rc;          // (an importer cannot build the tree: it has no item boxes)
     SceneLayout L{};
     L.magic = kLayoutMagic; L.arena_bytes = s->bytes; L.dev = s->dev; L.cam = s->cam; L.shade = s->shade; L.max_abs = s->max_abs;
     const char* base = (const char*)s->arena;
@@ -593,15 +622,20 @@ int lgb_scene_import(lgb_ctx* ctx, const void* layout, uint64_t layout_bytes, vo
     return LGB_OK;
 }
 double lgb_scene_build_ms(const lgb_scene* s) { return s ? s->build_ms : 0.0; }
-uint32_t lgb_scene_node_count(const lgb_scene* s) { return s ? s->dev.n_nodes : 0; }
+uint32_t lgb_scene_node_count(const lgb_scene* s) { if (!s) return 0; ensure_bvh(s->ctx, const_cast<lgb_scene*>(s)); return s->dev.n_nodes; }   // (builds a deferred tree)
 
 // Light grids (lgb_grid.cu) of a resident single-space scene, on the scene's own device and the context's stream.  A scene the
 // grids do not suit (transformed aggregates, a tiny BVH, many lights, many huge primitives) simply keeps dev.grids == NULL and its
 // shadow rays traverse the BVH.
+// "a BVH of >= 1024 nodes", also for a scene whose tree is deferred (leaves hold up to 4 primitives: ~n / 2 nodes)
+static bool large_scene(const DevScene& S) { return S.nodes ? S.n_nodes >= 1024u : (S.n_sph + S.n_cub + S.n_tri) / 2 >= 1024u; }
+
 static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
     DevScene& S = s->dev;
     S.grids = nullptr;
-    const bool want = ctx->light_grids == 1 || (ctx->light_grids < 0 && S.n_nodes >= 1024u && S.n_lights <= 8u);
+    for (void* g : s->grid_allocs) cudaFreeAsync(g, ctx->stream);      // (a rebuild after ensure_bvh re-ordered the primitives)
+    s->grid_allocs.clear(); s->grid_host.clear(); s->grid_table = nullptr; s->grid_bytes = 0;
+    const bool want = ctx->light_grids == 1 || (ctx->light_grids < 0 && large_scene(S) && S.n_lights <= 8u);
     if (!want || S.instanced || S.n_lights == 0 || S.n_sph + S.n_cub + S.n_tri == 0) return LGB_OK;
     auto t0 = std::chrono::steady_clock::now();
     CU(ctx, cudaSetDevice(ctx->device));
@@ -638,6 +672,7 @@ static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
     GR(cudaMemcpyAsync(h_tot.data(), totals, 8 * (size_t)nl, cudaMemcpyDeviceToHost, st));
     GR(cudaStreamSynchronize(st));
     bool ok = true;
+    s->grid_host.clear();
     for (uint32_t l = 0; l < nl; l++) ok = ok && h_tot[2 * l + 1] <= kGridLargeCap;
     uint64_t bytes = 0, entries_all = 0;
     if (ok) {
@@ -655,12 +690,14 @@ static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
             GR(grid_fill(S, l, res, dtab + l, counts, starts[l], entries_tmp, entries, total, sort_tmp, sort_bytes, large_tmp + (size_t)kGridLargeCap * l, n_large, st));
             if (n_large) GR(cudaMemcpyAsync(large, large_tmp + (size_t)kGridLargeCap * l, sizeof(uint2) * n_large, cudaMemcpyDeviceToDevice, st));
             heads[l] = Head{starts[l], entries, large, res, n_large};
+            s->grid_host.push_back(lgb_scene::GridHost{starts[l], entries, large, (nc + 1) * 4, sizeof(uint2) * (size_t)total, sizeof(uint2) * (size_t)n_large, res, n_large});
             bytes += (nc + 1) * 4 + sizeof(uint2) * ((size_t)total + n_large); entries_all += total;
         }
         lap("entries allocated, filled, sorted");
         for (uint32_t l = 0; l < nl; l++) GR(cudaMemcpyAsync((char*)(dtab + l), &heads[l], sizeof(Head), cudaMemcpyHostToDevice, st));
         GR(cudaStreamSynchronize(st));           // `heads` is on this stack frame; captures may run on other streams
         S.grids = dtab;
+        s->grid_table = dtab;
         s->grid_allocs = mine;
         s->grid_bytes = bytes + sizeof(DevGrid) * nl;
     }
@@ -669,6 +706,41 @@ static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
     s->t_grids = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (getenv("LGB_TIMING")) fprintf(stderr, "[light grids] %u lights, res %u, %llu entries, %.1f MB, %.2f ms (host clock, two synchronisations)%s\n", nl, res,
                                       (unsigned long long)entries_all, s->grid_bytes / 1e6, s->t_grids, ok ? "" : " REFUSED");
+    return LGB_OK;
+}
+
+static int replicate_to_peers(lgb_ctx* ctx, lgb_scene* s);
+// The device BVH of a scene created without one (lgb_scene::Deferred): binned-SAH build from the kept item boxes, the primitives
+// re-written in leaf order, the grids (which index the primitive arrays) rebuilt, the peers of a device group re-supplied.
+static int ensure_bvh(lgb_ctx* ctx, lgb_scene* s) {
+    if (s->dev.nodes || !s->deferred.scratch) return LGB_OK;
+    if (ctx->leader) return fail(ctx, LGB_ERR_INVALID, "internal: a device-group replica cannot build its own BVH (the leader re-supplies it)");
+    auto t0 = std::chrono::steady_clock::now();
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (s->last_use) CU(ctx, cudaStreamWaitEvent(st, s->last_use, 0));       // a capture on a caller's stream may still read the arrays
+    lgb_scene::Deferred& F = s->deferred;
+    char* D = (char*)s->arena;
+    GpuBuildInfo info{};
+    uint32_t* typepos[3] = {nullptr, nullptr, nullptr};
+    cudaError_t e = gpu_build_sah(F.items, F.n, (HostNode*)(D + F.o_nodes), F.final_items, typepos, F.build_temp, F.build_bytes, st, &info);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "gpu_build_sah");
+    if (info.max_depth + 1 > (uint32_t)kStackDepth) return fail(ctx, LGB_ERR_UNSUPPORTED, "device BVH deeper than the 64-entry traversal stack");
+    if ((e = launch_convert(F.raw, F.la, F.final_items, F.n, typepos, F.padd, st)) != cudaSuccess) return cuda_fail(ctx, e, "k_convert");
+    CU(ctx, cudaStreamSynchronize(st));
+    cudaFreeAsync(F.scratch, st);
+    F = lgb_scene::Deferred{};
+    s->dev.nodes = (const float4*)(D + s->bytes); s->dev.n_nodes = info.n_nodes;      // (bytes == o_nodes while the tree was deferred)
+    s->bytes += (size_t)info.n_nodes * 64;
+    for (void** q : {&s->camgrid.starts, &s->camgrid.entries, &s->camgrid.large}) if (*q) { cudaFreeAsync(*q, st); *q = nullptr; }
+    s->camgrid.valid = false; s->camgrid.refused = false;
+    if (!ctx->peers.empty()) {
+        for (lgb_scene* r : s->replicas) lgb_scene_destroy(r);
+        s->replicas.clear();
+        if (int rc = replicate_to_peers(ctx, s)) return rc;                 // (builds the leader's grids too)
+    } else if (int rc = build_light_grids(ctx, s)) return rc;
+    s->build_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("LGB_TIMING")) fprintf(stderr, "[ensure_bvh] deferred device BVH built on demand: %u nodes, %.2f ms\n", info.n_nodes, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     return LGB_OK;
 }
 
@@ -688,21 +760,42 @@ static int replicate_to_peers(lgb_ctx* ctx, lgb_scene* s) {
         s->replicas.push_back(r);
         CU(ctx, cudaMemcpyPeerAsync(arena, p->device, s->arena, ctx->device, s->bytes, p->stream));
     }
-    // every peer finishes its copy and builds its own light grids, all at once (a build holds two host synchronisations)
-    std::vector<int> rcs(ctx->peers.size(), LGB_OK);
-    std::vector<std::thread> workers;
-    for (size_t k = 0; k < ctx->peers.size(); k++)
-        workers.emplace_back([&, k] {
-            lgb_ctx* p = ctx->peers[k];
-            if (cudaSetDevice(p->device) != cudaSuccess || cudaStreamSynchronize(p->stream) != cudaSuccess) { rcs[k] = fail(p, LGB_ERR_CUDA, "scene replication: peer copy failed"); return; }
-            s->replicas[k]->dev.grids = nullptr;
-            rcs[k] = build_light_grids(p, s->replicas[k]);
-        });
-    const int rc0 = build_light_grids(ctx, s);           // the leader's own, meanwhile
-    for (std::thread& t : workers) t.join();
+    // the leader builds its light grids while the arenas travel; the grids then travel too (a table and three buffers per light:
+    // 98 MB for `mixed4k`) and only the pointers of the peer's table are rewritten -- rebuilding them per device cost 12 ms at 8 GPUs
+    if (int rc0 = build_light_grids(ctx, s)) return rc0;
+    struct Head { const uint32_t* cell_start; const uint2* entries; const uint2* large; uint32_t res, n_large; };
+    std::vector<std::vector<Head>> all_heads(ctx->peers.size());      // (alive until every peer's stream is drained below)
+    for (size_t k = 0; k < ctx->peers.size(); k++) {
+        lgb_ctx* p = ctx->peers[k];
+        lgb_scene* r = s->replicas[k];
+        r->dev.grids = nullptr;
+        if (!s->dev.grids) continue;
+        CU(ctx, cudaSetDevice(p->device));
+        const size_t nl = s->grid_host.size();
+        void* tab = nullptr;
+        CU(ctx, cudaMallocAsync(&tab, sizeof(DevGrid) * nl, p->stream));
+        r->grid_allocs.push_back(tab);
+        CU(ctx, cudaMemcpyPeerAsync(tab, p->device, s->grid_table, ctx->device, sizeof(DevGrid) * nl, p->stream));
+        std::vector<Head>& heads = all_heads[k];
+        heads.resize(nl);
+        for (size_t l = 0; l < nl; l++) {
+            const lgb_scene::GridHost& g = s->grid_host[l];
+            void* b[3] = {nullptr, nullptr, nullptr};
+            const void* src[3] = {g.starts, g.entries, g.large};
+            const size_t bytes[3] = {g.starts_bytes, g.entries_bytes, g.large_bytes};
+            for (int q = 0; q < 3; q++) {
+                CU(ctx, cudaMallocAsync(&b[q], std::max<size_t>(bytes[q], 16), p->stream));
+                r->grid_allocs.push_back(b[q]);
+                if (bytes[q]) CU(ctx, cudaMemcpyPeerAsync(b[q], p->device, src[q], ctx->device, bytes[q], p->stream));
+            }
+            heads[l] = Head{(const uint32_t*)b[0], (const uint2*)b[1], (const uint2*)b[2], g.res, g.n_large};
+            r->grid_host.push_back(lgb_scene::GridHost{b[0], b[1], b[2], bytes[0], bytes[1], bytes[2], g.res, g.n_large});
+        }
+        for (size_t l = 0; l < nl; l++) CU(ctx, cudaMemcpyAsync((char*)tab + sizeof(DevGrid) * l, &heads[l], sizeof(Head), cudaMemcpyHostToDevice, p->stream));
+        r->dev.grids = (const DevGrid*)tab; r->grid_table = tab; r->grid_bytes = s->grid_bytes;
+    }
+    for (lgb_ctx* p : ctx->peers) { CU(ctx, cudaSetDevice(p->device)); CU(ctx, cudaStreamSynchronize(p->stream)); }
     CU(ctx, cudaSetDevice(ctx->device));
-    if (rc0) return rc0;
-    for (size_t k = 0; k < rcs.size(); k++) if (rcs[k]) return fail(ctx, rcs[k], "scene replication on device " + std::to_string(ctx->peers[k]->device) + ": " + ctx->peers[k]->error);
     return LGB_OK;
 }
 
@@ -855,7 +948,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
             if (e != cudaSuccess) return bail(e == cudaErrorMemoryAllocation ? fail(ctx, LGB_ERR_NOMEM, "scene build: device scratch allocation failed") : cuda_fail(ctx, e, "cudaMallocAsync"));
         }
         char* H = (char*)ctx->staging; char* D = (char*)s->arena; char* T = (char*)scratch;
-        auto gfail = [&](int code) { cudaFreeAsync(scratch, ctx->stream); return bail(code); };
+        auto gfail = [&](int code) { if (!s->deferred.scratch) cudaFreeAsync(scratch, ctx->stream); return bail(code); };
         Pool& pool = Pool::get();
         auto stage = [&](size_t at, const void* src, size_t bytes) {
             if (!bytes) return;
@@ -898,19 +991,33 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         auto tb0 = std::chrono::steady_clock::now();
         GpuBuildInfo info{};
         uint32_t* typepos[3] = {nullptr, nullptr, nullptr};
-        e = gpu_build_sah(items, (uint32_t)n, (HostNode*)(D + o_nodes), final_items, typepos, T + t_build, build_bytes, ctx->stream, &info);
-        if (e != cudaSuccess) { cuda_fail(ctx, e, "gpu_build_sah"); return gfail(LGB_ERR_CUDA); }
-        if (info.max_depth + 1 > (uint32_t)kStackDepth) return gfail(fail(ctx, LGB_ERR_UNSUPPORTED, "device BVH deeper than the 64-entry traversal stack"));
         LeafArrays la{};
         la.sph32 = (float4*)(D + o_s32); la.sph64 = (double*)(D + o_s64); la.sph_mat = (uint32_t*)(D + o_smat); la.sph_id = (uint32_t*)(D + o_sid);
         la.cub32 = (float4*)(D + o_c32); la.cub64 = (double*)(D + o_c64); la.cub_mat = (uint32_t*)(D + o_cmat); la.cub_id = (uint32_t*)(D + o_cid);
         la.tri = (float4*)(D + o_tri); la.tri_nrm = any_normals ? (float*)(D + o_nrm) : nullptr;
-        if ((e = launch_convert(raw, la, final_items, (uint32_t)n, typepos, padd, ctx->stream)) != cudaSuccess) { cuda_fail(ctx, e, "k_convert"); return gfail(LGB_ERR_CUDA); }
-        cudaFreeAsync(scratch, ctx->stream);
+        // plastic scenes whose shadow rays will have light grids: no tree yet (see lgb_scene::Deferred); everything else builds it now
+        // ... and whose primary rays will have a camera grid: known only if the caller says how large the film is (the grid pays from four
+        // samples per primitive, ensure_camgrid); LGB_OPT_LAZY_BVH = 1 defers regardless
+        const uint64_t expect_samples = (uint64_t)d->expected_film_pixels * d->camera.supersampling_root * d->camera.supersampling_root;
+        const bool cam_grid_likely = d->camera.pixel_separation == 0.0 && ctx->camera_grid != 0 && (ctx->camera_grid == 1 || expect_samples >= 4ull * n);
+        const bool defer = (ctx->lazy_bvh == 1 || (ctx->lazy_bvh < 0 && cam_grid_likely)) && !any_general && d->n_lights >= 1 &&
+                           (ctx->light_grids == 1 || (ctx->light_grids < 0 && d->n_lights <= 8));
+        if (defer) {
+            if ((e = gpu_identity_positions(items, (uint32_t)n, typepos, T + t_build, build_bytes, ctx->stream)) != cudaSuccess) { cuda_fail(ctx, e, "gpu_identity_positions"); return gfail(LGB_ERR_CUDA); }
+            if ((e = launch_convert(raw, la, items, (uint32_t)n, typepos, padd, ctx->stream)) != cudaSuccess) { cuda_fail(ctx, e, "k_convert"); return gfail(LGB_ERR_CUDA); }
+            s->deferred.scratch = scratch; s->deferred.raw = raw; s->deferred.items = items; s->deferred.final_items = final_items; s->deferred.la = la;
+            s->deferred.build_temp = T + t_build; s->deferred.build_bytes = build_bytes; s->deferred.o_nodes = o_nodes; s->deferred.n = (uint32_t)n; s->deferred.padd = padd;
+        } else {
+            e = gpu_build_sah(items, (uint32_t)n, (HostNode*)(D + o_nodes), final_items, typepos, T + t_build, build_bytes, ctx->stream, &info);
+            if (e != cudaSuccess) { cuda_fail(ctx, e, "gpu_build_sah"); return gfail(LGB_ERR_CUDA); }
+            if (info.max_depth + 1 > (uint32_t)kStackDepth) return gfail(fail(ctx, LGB_ERR_UNSUPPORTED, "device BVH deeper than the 64-entry traversal stack"));
+            if ((e = launch_convert(raw, la, final_items, (uint32_t)n, typepos, padd, ctx->stream)) != cudaSuccess) { cuda_fail(ctx, e, "k_convert"); return gfail(LGB_ERR_CUDA); }
+            cudaFreeAsync(scratch, ctx->stream);
+        }
         s->build_ms = ms_since(tb0);
         s->t_build = s->build_ms;
         s->bytes = o_nodes + (size_t)info.n_nodes * 64;
-        s->dev.nodes = (const float4*)(D + o_nodes); s->dev.n_nodes = info.n_nodes;
+        s->dev.nodes = defer ? nullptr : (const float4*)(D + o_nodes); s->dev.n_nodes = info.n_nodes;
         s->dev.rank = lazy ? nullptr : (const uint32_t*)(D + o_rank); s->dev.prim_count = prim_count; s->dev.rank_items = (uint32_t)n_items;
         s->dev.n_sph = (uint32_t)ns; s->dev.n_cub = (uint32_t)ncb; s->dev.n_tri = (uint32_t)nt;
         s->dev.n_spaces = 1; s->dev.instanced = 0;
@@ -1106,7 +1213,7 @@ static int ensure_camgrid(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint
     const DevScene& S = s->dev;
     const uint32_t prims = S.n_sph + S.n_cub + S.n_tri;
     // automatic: where the frame holds enough samples to pay for binning every primitive (measured)
-    const bool want = c->camera_grid == 1 || (c->camera_grid < 0 && S.n_nodes >= 1024u && samples >= 4ull * prims);
+    const bool want = c->camera_grid == 1 || (c->camera_grid < 0 && large_scene(S) && samples >= 4ull * prims);
     if (!want || S.instanced || s->cam.pixel_separation != 0.0 || prims == 0) return LGB_OK;
     lgb_scene::CamGrid& G = s->cam_grid();
     if (G.refused && G.w == w && G.h == h) return LGB_OK;
@@ -1309,8 +1416,15 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     const uint32_t nl = std::max<uint32_t>(S.n_lights, 1);
     // automatic: where a bundle of >= 8 rays shares a traversal that is long enough to be worth sharing (measured: a loss on
     // scenes of a few dozen primitives, a gain on large ones)
-    W.beams = (W.spp >= 4 && !S.instanced && (c->beams == 1 || (c->beams < 0 && W.spp >= 8 && S.n_nodes >= 1024u))) ? 1u : 0u;
+    W.beams = (W.spp >= 4 && !S.instanced && (c->beams == 1 || (c->beams < 0 && W.spp >= 8 && large_scene(S)))) ? 1u : 0u;
     if (!a.klog_no_camgrid && total_all) if (int rc = ensure_camgrid(c, s, a.w, a.h, total_all, W, st)) return rc;
+    if (!S.nodes && total_all && (!W.cg_start || !(S.grids && !S.instanced) || S.general)) {
+        // a scene created without its BVH (lgb_scene::Deferred) meets a frame that walks one: build it now, then the grids again
+        if (int rc = ensure_bvh(c, s)) return rc;
+        W.cg_start = nullptr; W.cg_entries = nullptr; W.cg_large = nullptr;
+        W.beams = (W.spp >= 4 && !S.instanced && (c->beams == 1 || (c->beams < 0 && W.spp >= 8 && large_scene(S)))) ? 1u : 0u;
+        if (!a.klog_no_camgrid) if (int rc = ensure_camgrid(c, s, a.w, a.h, total_all, W, st)) return rc;
+    }
     const bool grid_shadows = S.grids && !S.instanced;                 // no shadow queues, no occluder cache
     const bool beam_lists = W.beams && (!W.cg_start || !grid_shadows); // pixel beams (primary) and / or shadow beams
     const bool two_lists = beam_lists && !grid_shadows && S.n_lights > 1 && c->side_streams && c->side.n;
@@ -1456,6 +1570,13 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
 static int group_capture(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, void* film, lgb_stats* stats) {
     const uint32_t n = 1 + (uint32_t)c->peers.size();
     if (s->replicas.size() != c->peers.size()) return fail(c, LGB_ERR_INVALID, "capture: the scene was not created on this device group");
+    if (!s->dev.nodes && s->deferred.scratch) {          // deferred BVH: the leader decides for the group before anybody renders
+        CU(c, cudaSetDevice(c->device));
+        DevWork Wp{};
+        const uint64_t samples = (uint64_t)w * h * s->cam.root * s->cam.root;
+        if (int rc = ensure_camgrid(c, s, w, h, samples, Wp, c->stream)) return rc;
+        if (!Wp.cg_start || !(s->dev.grids && !s->dev.instanced) || s->dev.general) if (int rc = ensure_bvh(c, s)) return rc;
+    }
     std::vector<int> rc(n, LGB_OK);
     std::vector<lgb_stats> st(n);
     std::vector<std::thread> workers;
@@ -1591,6 +1712,7 @@ int lgb_capture_profile(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, void* 
 int lgb_trace_rays(lgb_ctx* c, lgb_scene* s, const double* rays, uint64_t n, uint32_t* ids, double* ts, double* ng, double* ns) {
     if (!c || !s || (!rays && n)) return fail(c, LGB_ERR_INVALID, "lgb_trace_rays: NULL argument");
     CU(c, cudaSetDevice(c->device));
+    if (int rc = ensure_bvh(c, s)) return rc;
     if (n == 0) return LGB_OK;
     const size_t need = n * (48 + 4 + 8 + 24 + 24);
     CU(c, c->scratch.reserve(need));

@@ -409,6 +409,28 @@ size_t gpu_build_temp_bytes(uint32_t n) {
     return b;
 }
 
+// The per-type positions of the items in the order they are given (no tree: the deferred-BVH scenes of lgb_api.cu store their
+// primitives in the caller's order until a tree is asked for).  typepos_out as from gpu_build_sah; `temp` of gpu_build_temp_bytes(n).
+cudaError_t gpu_identity_positions(const GItem* items, uint32_t n, uint32_t** typepos_out, void* temp, size_t temp_bytes, cudaStream_t st) {
+    if (temp_bytes < gpu_build_temp_bytes(n)) return cudaErrorInvalidValue;
+    char* p = (char*)temp;
+    auto take = [&](size_t bytes) { char* r = p; p += align256(bytes); return r; };
+    uint32_t* typepos[3] = {(uint32_t*)take((size_t)n * 4), (uint32_t*)take((size_t)n * 4), (uint32_t*)take((size_t)n * 4)};
+    size_t scan_bytes = 0;
+    {
+        auto in = thrust::make_transform_iterator((const GItem*)nullptr, TypeIs{0});
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, in, (uint32_t*)nullptr, (int)n);
+    }
+    void* scan_tmp = take(scan_bytes);
+    cudaError_t e;
+    for (uint32_t t = 0; t < 3; t++) {
+        auto in = thrust::make_transform_iterator(items, TypeIs{t});
+        if ((e = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, in, typepos[t], (int)n, st)) != cudaSuccess) return e;
+    }
+    for (int t = 0; t < 3; t++) typepos_out[t] = typepos[t];
+    return cudaSuccess;
+}
+
 cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out, GItem* final_items, uint32_t** typepos_out, void* temp, size_t temp_bytes,
                           cudaStream_t st, GpuBuildInfo* info) {
     if (n <= (uint32_t)kMaxLeaf || temp_bytes < gpu_build_temp_bytes(n)) return cudaErrorInvalidValue;

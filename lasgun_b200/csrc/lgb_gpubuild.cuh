@@ -20,6 +20,8 @@ size_t gpu_build_temp_bytes(uint32_t n);
 cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out, GItem* final_items, uint32_t** typepos_out, void* temp, size_t temp_bytes,
                           cudaStream_t stream, GpuBuildInfo* info);
 
+cudaError_t gpu_identity_positions(const GItem* items, uint32_t n, uint32_t** typepos_out, void* temp, size_t temp_bytes, cudaStream_t st);
+
 // The caller's arrays as uploaded (device pointers, caller layout) and the leaf-ordered arrays the kernels read.
 struct RawScene {
     const lgb_sphere* spheres; const uint32_t* sphere_material; const uint32_t* sphere_id; uint32_t n_spheres;

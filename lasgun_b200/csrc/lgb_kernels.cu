@@ -2515,6 +2515,36 @@ __global__ void __launch_bounds__(128) k_trace(DevScene S, const double* rays, u
     if (nss) { nss[3 * i] = ns.x; nss[3 * i + 1] = ns.y; nss[3 * i + 2] = ns.z; }
 }
 
+// ------------------------------------------------------------------ end-of-frame flags of a shared film (multi-GPU, one process per GPU)
+// The ranks' pixels reach rank 0's film as plain peer stores; what is left of the "gather" is knowing when they have all arrived.
+// Each rank ends its frame by storing the frame number into its own word of rank 0's memory (behind a system-scope fence, so the
+// pixel stores are visible first); rank 0 ends its frame by waiting for every word -- a microsecond-scale kernel each, no collective.
+__global__ void k_flag_signal(volatile uint32_t* flag, uint32_t value) {
+    __threadfence_system();
+    *flag = value;
+    __threadfence_system();
+}
+__global__ void k_flag_wait(const volatile uint32_t* flags, uint32_t first, uint32_t n, uint32_t stride_words, uint32_t value, uint32_t* timed_out) {
+    const uint32_t i = first + threadIdx.x;
+    if (threadIdx.x < n) {
+        unsigned long long spins = 0;
+        while ((int32_t)(flags[(size_t)i * stride_words] - value) < 0) {      // (wrap-safe: frame numbers only grow)
+            if (++spins > (1ull << 31)) { if (timed_out) *timed_out = 1u; break; }      // a lost rank must not hang the GPU: give up after ~minutes
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+cudaError_t launch_flag_signal(void* flag, uint32_t value, cudaStream_t stream) {
+    k_flag_signal<<<1, 1, 0, stream>>>((volatile uint32_t*)flag, value);
+    return cudaGetLastError();
+}
+cudaError_t launch_flag_wait(const void* flags, uint32_t first, uint32_t n, uint32_t stride_bytes, uint32_t value, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_flag_wait<<<1, 32 * ((n + 31) / 32), 0, stream>>>((const volatile uint32_t*)flags, first, n, stride_bytes / 4, value, nullptr);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ ceilings for the roofline report
 __global__ void k_l2_read(const float4* __restrict__ buf, uint64_t n_vec, int iters, float* sink) {
     float acc = 0.0f;

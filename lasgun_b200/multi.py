@@ -73,8 +73,12 @@ class SharedFilm:
         L = native.lib()
         handle = (C.c_uint8 * 64)()
         ptr = C.c_void_p()
+        self.ranks = ranks
+        self.film_bytes = w * h * 4
+        self.flag_off = (self.film_bytes + 255) & ~255          # flags behind the film: word 0 = rank 0's `go`, word 16 r = rank r's `done`
+        self.frame = 0
         if rank == 0:
-            ctx.check(L.lgb_film_alloc_shared(ctx.h, w * h * 4, C.byref(ptr), handle))
+            ctx.check(L.lgb_film_alloc_shared(ctx.h, self.flag_off + 64 * (ranks + 1), C.byref(ptr), handle))
         t = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device="cuda")
         if ranks > 1:
             dist.broadcast(t, src=0)
@@ -84,6 +88,11 @@ class SharedFilm:
         self.ptr = ptr.value
         self.tensor = torch.as_tensor(_DevicePointer(self.ptr, w * h * 4), device="cuda").view(h, w, 4) if rank == 0 else None
         self._sync = torch.zeros(1, dtype=torch.int32, device="cuda")
+        if rank == 0:
+            torch.as_tensor(_DevicePointer(self.ptr + self.flag_off, 64 * (ranks + 1)), device="cuda").zero_()
+            torch.cuda.synchronize()
+        if ranks > 1:
+            dist.barrier()                                   # the flags are zero before any rank looks at them
 
     def close(self):
         if self.ptr:
@@ -115,10 +124,29 @@ def capture_distributed(dev_scene, w: int, h: int, film, rank: int, ranks: int, 
         else:
             dev_scene.capture_device(w, h, ptr, rank=rank, ranks=ranks, stream=stream)
     if shared is not None:
-        import torch.distributed as dist
-        render(shared.ptr)
-        if ranks > 1:
-            dist.all_reduce(shared._sync)            # on the current stream, i.e. after this rank's stores: the frame is whole on return
+        # The frame barrier is two flag words in rank 0's memory, not a collective: rank 0 opens frame f (`go` = f: it is done with
+        # the film of frame f - 1), every other rank waits for that word, renders, and stores f into its own `done` word behind a
+        # system fence; rank 0 renders and then waits for all `done` words.  All of it queued on `stream`: the frame is whole when
+        # rank 0's stream reaches the end of this call.
+        L, ctx = shared.native.lib(), shared.ctx
+        vp = shared.native.C.c_void_p
+        shared.frame += 1
+        f, flags = shared.frame, shared.ptr + shared.flag_off
+        st = vp(stream) if stream else None
+        if ranks > 1 and not fenced:
+            if rank == 0:
+                ctx.check(L.lgb_film_signal(ctx.h, vp(flags), f, st))
+                render(shared.ptr)
+                ctx.check(L.lgb_film_wait(ctx.h, vp(flags), 1, ranks - 1, 64, f, st))
+            else:
+                ctx.check(L.lgb_film_wait(ctx.h, vp(flags), 0, 1, 64, f, st))
+                render(shared.ptr)
+                ctx.check(L.lgb_film_signal(ctx.h, vp(flags + 64 * rank), f, st))
+        else:
+            import torch.distributed as dist
+            render(shared.ptr)
+            if ranks > 1:
+                dist.all_reduce(shared._sync)        # host-fenced variant: a collective barrier on the current stream
         return shared.tensor
     if ranks > 1:
         film.zero_()

@@ -11,6 +11,7 @@ film = np.zeros((h, w, 4), np.uint8)
 for it in range(4):
     t = time.perf_counter(); flat = N.FlatScene(hs, lazy=True); t_flat = time.perf_counter() - t
     hsc = C.c_void_p()
+    flat.desc.expected_film_pixels = w * h          # capture(scene, film) knows its film
     t0 = time.perf_counter(); ctx.check(L.lgb_scene_create(ctx.h, C.byref(flat.desc), C.byref(hsc))); t1 = time.perf_counter()
     st = N.Stats()
     ctx.check(L.lgb_capture(ctx.h, hsc, w, h, film.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(st))); t2 = time.perf_counter()

@@ -210,6 +210,44 @@ def test_frames_in_bands(native, gpu_ctx, name):
         dev.destroy()
 
 
+def test_deferred_bvh(native, oracle, gpu_ctx):
+    """LGB_OPT_LAZY_BVH: a large plastic scene is created without its device BVH (grids serve its rays) and renders the film of the
+    scene created with it; the first entry point that walks a tree (here: a frame with the camera grid off, lgb_trace_rays) builds
+    it, re-orders the primitives and rebuilds the grids -- the film, ids and t stay those of the oracle."""
+    sc, (w, h) = scenes.mixed4k(mesh_n=200, nspheres=40000, res=(320, 180), supersampling=1)
+    ref = oracle.OracleScene(sc).capture(w, h, aov=True)
+    try:
+        gpu_ctx.set_lazy_bvh(0)
+        eager = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+        film_eager, _ = eager.capture(w, h)
+        eager.destroy()
+        gpu_ctx.set_lazy_bvh(1)
+        dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+        film0, st0 = dev.capture(w, h)                       # no tree yet
+        out0 = dev.capture_aov(w, h)
+        a = parity.aov_report(out0, ref)
+        assert a["id_mismatch"] == 0 and a["t_bit_equal"] == a["t_compared"] and a["occl_diff"] == 0, a
+        assert np.array_equal(film0, film_eager) and np.array_equal(out0["rgba"], film0)
+        gpu_ctx.set_camera_grid(0)                           # this frame walks the BVH: built now
+        film1, st1 = dev.capture(w, h)
+        gpu_ctx.set_camera_grid(-1)
+        film2, _ = dev.capture(w, h)                         # and the grids were rebuilt over the re-ordered primitives
+        out2 = dev.capture_aov(w, h)
+        a = parity.aov_report(out2, ref)
+        assert a["id_mismatch"] == 0 and a["t_bit_equal"] == a["t_compared"] and a["occl_diff"] == 0, a
+        assert np.array_equal(film1, film_eager) and np.array_equal(film2, film_eager)
+        assert dev.verify()["boxes_ok"] == 1
+        dev.destroy()
+        dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+        rays = oracle.OracleScene(sc).camera_sample(w // 2, h // 2, w, h)
+        ids, ts, _, _ = dev.trace_rays(rays)                 # lgb_trace_rays on a scene without a tree
+        k = (h // 2 * w + w // 2) * sc.camera.num_samples()
+        assert np.array_equal(ids, ref["prim_id"].reshape(-1)[k:k + len(ids)])
+        dev.destroy()
+    finally:
+        gpu_ctx.set_lazy_bvh(-1); gpu_ctx.set_camera_grid(-1)
+
+
 # SURVEY 8f item 4: matte(sigma > 0), metal, glass, mirror and the Whitted recursion of integrate.rs:69-132
 WHITTED = {
     "simplereflect_9spp": lambda: scenes.simplereflect(2, 160),                 # src/examples/simplereflect.rs, depth 4
