@@ -119,6 +119,7 @@ struct lgb_scene {
     struct GridHost { void* starts; void* entries; void* large; size_t starts_bytes, entries_bytes, large_bytes; uint32_t res, n_large; };
     std::vector<GridHost> grid_host;   // the same buffers with their sizes (device-group replication copies them to the peers)
     void* grid_table = nullptr;
+    uint64_t expect_samples = 0;       // lgb_scene_desc.expected_film_pixels x spp (0: unknown, the scene may serve many frames)
     // deferred device BVH (LGB_OPT_LAZY_BVH): a plastic scene whose primary and shadow rays go through the grids never walks a tree, so
     // lgb_scene_create stores the primitives in the caller's order, keeps the uploaded raw arrays and the item boxes, and ensure_bvh
     // builds the tree (and re-orders the primitives, and rebuilds the grids) only if some entry point needs one
@@ -635,7 +636,10 @@ static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
     S.grids = nullptr;
     for (void* g : s->grid_allocs) cudaFreeAsync(g, ctx->stream);      // (a rebuild after ensure_bvh re-ordered the primitives)
     s->grid_allocs.clear(); s->grid_host.clear(); s->grid_table = nullptr; s->grid_bytes = 0;
-    const bool want = ctx->light_grids == 1 || (ctx->light_grids < 0 && large_scene(S) && S.n_lights <= 8u);
+    bool want = ctx->light_grids == 1 || (ctx->light_grids < 0 && large_scene(S) && S.n_lights <= 8u);
+    // a scene made for ONE frame of known size (capture(scene, film)) must earn its grids within that frame: they cost about as much to
+    // build as 10 shadow rays per primitive cost to trace (measured: `mesh1m`, 0.7 shadow rays per triangle, 3.8 ms of grids for 0.1 ms of render)
+    if (want && ctx->light_grids < 0 && s->expect_samples && s->expect_samples * S.n_lights < 8ull * (S.n_sph + S.n_cub + S.n_tri)) want = false;
     if (!want || S.instanced || S.n_lights == 0 || S.n_sph + S.n_cub + S.n_tri == 0) return LGB_OK;
     auto t0 = std::chrono::steady_clock::now();
     CU(ctx, cudaSetDevice(ctx->device));
@@ -869,6 +873,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
 
     lgb_scene* s = new lgb_scene();
     s->ctx = ctx;
+    s->expect_samples = (uint64_t)d->expected_film_pixels * d->camera.supersampling_root * d->camera.supersampling_root;
     auto bail = [&](int code) { lgb_scene_destroy(s); return code; };
 
     // ---- box that contains the scene and every ray origin, in world coordinates: it bounds the coordinates an f32
@@ -1000,8 +1005,8 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         // samples per primitive, ensure_camgrid); LGB_OPT_LAZY_BVH = 1 defers regardless
         const uint64_t expect_samples = (uint64_t)d->expected_film_pixels * d->camera.supersampling_root * d->camera.supersampling_root;
         const bool cam_grid_likely = d->camera.pixel_separation == 0.0 && ctx->camera_grid != 0 && (ctx->camera_grid == 1 || expect_samples >= 4ull * n);
-        const bool defer = (ctx->lazy_bvh == 1 || (ctx->lazy_bvh < 0 && cam_grid_likely)) && !any_general && d->n_lights >= 1 &&
-                           (ctx->light_grids == 1 || (ctx->light_grids < 0 && d->n_lights <= 8));
+        const bool grids_likely = ctx->light_grids == 1 || (ctx->light_grids < 0 && d->n_lights <= 8 && !(expect_samples && expect_samples * d->n_lights < 8ull * n));
+        const bool defer = (ctx->lazy_bvh == 1 || (ctx->lazy_bvh < 0 && cam_grid_likely)) && !any_general && d->n_lights >= 1 && grids_likely;
         if (defer) {
             if ((e = gpu_identity_positions(items, (uint32_t)n, typepos, T + t_build, build_bytes, ctx->stream)) != cudaSuccess) { cuda_fail(ctx, e, "gpu_identity_positions"); return gfail(LGB_ERR_CUDA); }
             if ((e = launch_convert(raw, la, items, (uint32_t)n, typepos, padd, ctx->stream)) != cudaSuccess) { cuda_fail(ctx, e, "k_convert"); return gfail(LGB_ERR_CUDA); }

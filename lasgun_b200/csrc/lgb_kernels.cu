@@ -12,6 +12,14 @@
 
 #include "lgb_math.cuh"
 
+// The two traversal prescriptions of the north star that measurements rejected, kept as build variants:
+#ifndef LGB_SMEM_STACK
+#define LGB_SMEM_STACK 0             // 1: the per-ray traversal stacks of k_primary / k_shadow in shared memory ([entry][thread], conflict-free) instead of local memory
+#endif
+#ifndef LGB_SMEM_TOP
+#define LGB_SMEM_TOP 0               // N > 0: the first N nodes of the device BVH (its top levels: nodes are numbered level by level) staged in shared memory per block
+#endif
+#define LGB_STK(i) ((i) * stride)      // entry i of a traversal stack: stride 1 in local memory, the block size in shared memory
 #ifndef LGB_WALK_PREFETCH
 #define LGB_WALK_PREFETCH 0          // grid walks (k_cprimary, k_gshadow): load entry i + 1 while entry i is tested
 #endif
@@ -206,19 +214,23 @@ struct Trav {                 // resumable traversal state of one ray
 // TSTACK (closest-hit rays): the entry distance of a deferred child is kept beside it, and a popped entry
 // that now starts beyond the best hit is dropped without fetching its node.
 template <bool TSTACK>
-__device__ __forceinline__ uint32_t stack_pop(int& sp, const uint32_t* stack, const float* tstack, float best_up) {
+__device__ __forceinline__ uint32_t stack_pop(int& sp, const uint32_t* stack, const float* tstack, float best_up, const int stride = 1) {
     while (sp) {
         --sp;
-        if (!TSTACK || tstack[sp] <= best_up) return stack[sp];
+        if (!TSTACK || tstack[LGB_STK(sp)] <= best_up) return stack[LGB_STK(sp)];
     }
     return kDone;
 }
 template <int OCT, bool STATS, bool TSTACK>
-__device__ __forceinline__ void node_loop(const DevScene& S, const RayF& f, float best_up, uint32_t& cur, int& sp, uint32_t* stack, float* tstack, LocalCounters& lc) {
+__device__ __forceinline__ void node_loop(const DevScene& S, const RayF& f, float best_up, uint32_t& cur, int& sp, uint32_t* stack, float* tstack, LocalCounters& lc, const float4* top = nullptr, const int stride = 1) {
     while (!(cur & kLeafBit) && cur != kDone) {
         const float4* np = S.nodes + 4 * (size_t)cur;
-        const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-        const float2 n3 = __ldg(reinterpret_cast<const float2*>(np + 3));
+        float4 n0, n1, n2; float2 n3;
+#if LGB_SMEM_TOP
+        if (top && cur < (uint32_t)LGB_SMEM_TOP) { const float4* tp = top + 4 * cur; n0 = tp[0]; n1 = tp[1]; n2 = tp[2]; n3 = make_float2(tp[3].x, tp[3].y); }
+        else
+#endif
+        { n0 = __ldg(np); n1 = __ldg(np + 1); n2 = __ldg(np + 2); n3 = __ldg(reinterpret_cast<const float2*>(np + 3)); }
         if (STATS) lc.node_tests++;
         float tn0, tn1;
         bool h0, h1;
@@ -233,11 +245,11 @@ __device__ __forceinline__ void node_loop(const DevScene& S, const RayF& f, floa
         if (h0 && h1) {
             const bool swap = tn1 < tn0;
             cur = swap ? c1 : c0;
-            if (TSTACK) tstack[sp] = swap ? tn0 : tn1;
-            stack[sp++] = swap ? c0 : c1;
+            if (TSTACK) tstack[LGB_STK(sp)] = swap ? tn0 : tn1;
+            stack[LGB_STK(sp)] = swap ? c0 : c1; sp++;
         } else if (h0) cur = c0;
         else if (h1) cur = c1;
-        else cur = stack_pop<TSTACK>(sp, stack, tstack, best_up);
+        else cur = stack_pop<TSTACK>(sp, stack, tstack, best_up, stride);
     }
 }
 
@@ -323,21 +335,21 @@ constexpr uint32_t kInstLeaf = kLeafBit | ((uint32_t)LGB_PRIM_INSTANCE << 29);
 constexpr uint32_t kExitMarker = kInstLeaf | (31u << 24);
 template <bool ANYHIT, bool STATS, bool REFILL, bool INST>
 __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& world, Ray64& ray, RayF& f, Trav& T, uint32_t* stack, float* tstack, double tmax,
-                                         LocalCounters& lc, int refill_below, unsigned octw) {
+                                         LocalCounters& lc, int refill_below, unsigned octw, const float4* top = nullptr, const int stride = 1) {
     Hit& best = T.best;
     float& best_tf = T.best_tf; float& best_up = T.best_up;
     uint32_t& cur = T.cur; int& sp = T.sp;
     for (;;) {
         switch (INST ? f.oct : octw) {   // octw is warp-uniform: the octant shared by every ray of the warp, or 8 (mixed)
-        case 0: node_loop<0, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 1: node_loop<1, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 2: node_loop<2, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 3: node_loop<3, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 4: node_loop<4, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 5: node_loop<5, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 6: node_loop<6, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        case 7: node_loop<7, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
-        default: node_loop<8, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc); break;
+        case 0: node_loop<0, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc, top, stride); break;
+        case 1: node_loop<1, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc, top, stride); break;
+        case 2: node_loop<2, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc, top, stride); break;
+        case 3: node_loop<3, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc, top, stride); break;
+        case 4: node_loop<4, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc, top, stride); break;
+        case 5: node_loop<5, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc, top, stride); break;
+        case 6: node_loop<6, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc, top, stride); break;
+        case 7: node_loop<7, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc, top, stride); break;
+        default: node_loop<8, STATS, (!ANYHIT && LGB_TSTACK)>(S, f, best_up, cur, sp, stack, tstack, lc, top, stride); break;
         }
         if (cur == kDone) return true;
         {
@@ -348,9 +360,9 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& world, 
                     ray = ray_to_space(S, first, world);
                     f = make_rayf(ray, S.spaces[first].err_abs);
                 } else {
-                    if (count > 1u) { if (!ANYHIT && LGB_TSTACK) tstack[sp] = -CUDART_INF_F; stack[sp++] = kInstLeaf | ((count - 2u) << 24) | (first + 1u); }
-                    if (!ANYHIT && LGB_TSTACK) tstack[sp] = -CUDART_INF_F;
-                    stack[sp++] = kExitMarker | T.space;
+                    if (count > 1u) { if (!ANYHIT && LGB_TSTACK) tstack[LGB_STK(sp)] = -CUDART_INF_F; stack[LGB_STK(sp)] = kInstLeaf | ((count - 2u) << 24) | (first + 1u); sp++; }
+                    if (!ANYHIT && LGB_TSTACK) tstack[LGB_STK(sp)] = -CUDART_INF_F;
+                    stack[LGB_STK(sp)] = kExitMarker | T.space; sp++;
                     const uint32_t child = __ldg(&S.inst_space[first]);
                     const DevSpace& c = S.spaces[child];
                     if (!(c.flags & kSpaceIdentity)) ray = ray_into(c, ray);
@@ -361,7 +373,7 @@ __device__ __forceinline__ bool trav_run(const DevScene& S, const Ray64& world, 
                 }
             } else if (leaf_prims<ANYHIT, STATS, INST>(S, world, ray, f, T, type, count, first, tmax, lc)) { cur = kDone; return true; }
         }
-        cur = stack_pop<(!ANYHIT && LGB_TSTACK)>(sp, stack, tstack, best_up);
+        cur = stack_pop<(!ANYHIT && LGB_TSTACK)>(sp, stack, tstack, best_up, stride);
         if (REFILL && __popc(__activemask()) < refill_below) return cur == kDone;
     }
 }
@@ -858,10 +870,10 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 }
 
 #ifndef LGB_MIN_BLOCKS
-#define LGB_MIN_BLOCKS 4
+#define LGB_MIN_BLOCKS 8
 #endif
 #ifndef LGB_TRAV_THREADS
-#define LGB_TRAV_THREADS 256          // threads per block of the persistent traversal kernels
+#define LGB_TRAV_THREADS 128          // threads per block of the persistent traversal kernels (256 x 4 blocks: the same on large frames, `mesh1m` 0.85 -> 0.68 ms: shorter tails)
 #endif
 
 // ================================================================== wavefront pipeline
@@ -1000,8 +1012,24 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_primary(De
     const unsigned lane = threadIdx.x & 31u;
     LocalCounters lc = {};
     unsigned int hits = 0, primary = 0;
+#if LGB_SMEM_STACK
+    extern __shared__ uint32_t dyn_smem[];                                   // [entry][thread]: stack words, then entry distances
+    uint32_t* stack = dyn_smem + threadIdx.x;
+    float* tstack = reinterpret_cast<float*>(dyn_smem + (size_t)kStackDepth * LGB_TRAV_THREADS) + threadIdx.x;
+    constexpr int kStride = LGB_TRAV_THREADS;
+#else
     uint32_t stack[kStackDepth];
     float tstack[LGB_TSTACK ? kStackDepth : 1];
+    constexpr int kStride = 1;
+#endif
+#if LGB_SMEM_TOP
+    __shared__ float4 s_top[4 * LGB_SMEM_TOP];
+    for (uint32_t i = threadIdx.x; i < 4u * min((uint32_t)LGB_SMEM_TOP, S.n_nodes); i += blockDim.x) s_top[i] = __ldg(S.nodes + i);
+    __syncthreads();
+    const float4* top = s_top;
+#else
+    const float4* top = nullptr;
+#endif
     Ray64 world, ray; RayF f; Trav T;      // INST: `ray` is the ray in the current space; otherwise it stays equal to `world`
     uint64_t g = 0;
     bool active = false, drained = false;
@@ -1034,7 +1062,7 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_primary(De
         const unsigned oct0 = __shfl_sync(0xFFFFFFFFu, f.oct, __ffs(amask) - 1);
         const unsigned octw = __all_sync(0xFFFFFFFFu, !active || f.oct == oct0) ? oct0 : 8u;
         if (active) {
-            const bool done = trav_run<false, STATS, true, INST>(S, world, ray, f, T, stack, tstack, CUDART_INF, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
+            const bool done = trav_run<false, STATS, true, INST>(S, world, ray, f, T, stack, tstack, CUDART_INF, lc, drained ? 0 : LGB_REFILL_BELOW, octw, top, kStride);
             if (done) {
                 const bool hit = T.best.ref != LGB_MISS;
                 V.hit_t[g] = hit ? T.best.t : CUDART_INF; V.hit_ref[g] = T.best.ref;
@@ -1847,7 +1875,22 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_shadow(Dev
     const unsigned lane = threadIdx.x & 31u;
     LocalCounters lc = {};
     unsigned int occluded = 0;
+#if LGB_SMEM_STACK
+    extern __shared__ uint32_t dyn_smem[];
+    uint32_t* stack = dyn_smem + threadIdx.x;
+    constexpr int kStride = LGB_TRAV_THREADS;
+#else
     uint32_t stack[kStackDepth];
+    constexpr int kStride = 1;
+#endif
+#if LGB_SMEM_TOP
+    __shared__ float4 s_top[4 * LGB_SMEM_TOP];
+    for (uint32_t i = threadIdx.x; i < 4u * min((uint32_t)LGB_SMEM_TOP, S.n_nodes); i += blockDim.x) s_top[i] = __ldg(S.nodes + i);
+    __syncthreads();
+    const float4* top = s_top;
+#else
+    const float4* top = nullptr;
+#endif
     Ray64 world, ray; RayF f; Trav T;
     uint32_t g = 0;
     bool active = false, drained = false;
@@ -1870,7 +1913,7 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_shadow(Dev
         const unsigned oct0 = __shfl_sync(0xFFFFFFFFu, f.oct, __ffs(amask) - 1);
         const unsigned octw = __all_sync(0xFFFFFFFFu, !active || f.oct == oct0) ? oct0 : 8u;
         if (active) {
-            const bool done = trav_run<true, STATS, true, INST>(S, world, ray, f, T, stack, nullptr, 1.0, lc, drained ? 0 : LGB_REFILL_BELOW, octw);
+            const bool done = trav_run<true, STATS, true, INST>(S, world, ray, f, T, stack, nullptr, 1.0, lc, drained ? 0 : LGB_REFILL_BELOW, octw, top, kStride);
             if (done) {
                 if (T.best.ref != LGB_MISS) { atomicOr(&V.occl[g], 1u << light); occluded++; }
                 if (record) V.occluder[(size_t)light * W.n_pixels + fdiv(g, W.fd_spp)] = T.best.ref;
@@ -2587,6 +2630,8 @@ cudaError_t launch_fastmath(const double* x, uint64_t n, double* rcp, double* rs
     return cudaGetLastError();
 }
 
+constexpr size_t kPrimarySmem = LGB_SMEM_STACK ? (size_t)2 * kStackDepth * LGB_TRAV_THREADS * 4 : 0;      // dynamic shared memory of the stack variants
+constexpr size_t kShadowSmem = LGB_SMEM_STACK ? (size_t)kStackDepth * LGB_TRAV_THREADS * 4 : 0;
 // ------------------------------------------------------------------ launch wrappers (called from lgb_api.cu)
 bool render_fused(uint32_t spp) { return spp >= 1 && spp <= 256; }      // and !S.general: see launch_render
 #ifndef LGB_SURFACE_FUSED
@@ -2616,6 +2661,18 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
                           const DevWave& V, bool stats, bool all_shadows, int sms, cudaStream_t stream, cudaEvent_t* ev, int part, const SideStreams* side,
                           KernelLog* klog) {
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], stream); };
+#if LGB_SMEM_STACK
+    {   // the shared-memory stack variant needs more than the default 48 KB of dynamic shared memory (per device: cheap, idempotent)
+        cudaFuncSetAttribute(k_primary<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrimarySmem);
+        cudaFuncSetAttribute(k_primary<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrimarySmem);
+        cudaFuncSetAttribute(k_primary<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrimarySmem);
+        cudaFuncSetAttribute(k_primary<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrimarySmem);
+        cudaFuncSetAttribute(k_shadow<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShadowSmem);
+        cudaFuncSetAttribute(k_shadow<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShadowSmem);
+        cudaFuncSetAttribute(k_shadow<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShadowSmem);
+        cudaFuncSetAttribute(k_shadow<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShadowSmem);
+    }
+#endif
     const uint64_t total = W.n_pixels * W.spp;
     const bool cache = W.spp > 1;
     const unsigned pblocks = (unsigned)std::min<uint64_t>((total + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, (uint64_t)sms * LGB_MIN_BLOCKS);
@@ -2640,10 +2697,10 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
             KL("k_beam", -1, stream, if (stats) k_beam<true><<<bb, LGB_BEAM_THREADS, 0, stream>>>(S, C, W, O, V); else k_beam<false><<<bb, LGB_BEAM_THREADS, 0, stream>>>(S, C, W, O, V));
             KL("k_leafp", -1, stream, if (stats) k_leafp<true><<<lb, LGB_LEAFP_THREADS, 0, stream>>>(S, C, W, O, V); else k_leafp<false><<<lb, LGB_LEAFP_THREADS, 0, stream>>>(S, C, W, O, V));
             DevWork Wf = W; Wf.slot_list = V.fallback_list; Wf.n_list = 0; Wf.n_list_dev = V.fallback_count;
-            KL("k_primary(fallback)", -1, stream, if (stats) k_primary<true, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, Wf, O, V); else k_primary<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, Wf, O, V));
+            KL("k_primary(fallback)", -1, stream, if (stats) k_primary<true, false><<<pb, LGB_TRAV_THREADS, kPrimarySmem, stream>>>(S, C, Wf, O, V); else k_primary<false, false><<<pb, LGB_TRAV_THREADS, kPrimarySmem, stream>>>(S, C, Wf, O, V));
         } else if (pb) {
-            if (inst) KL("k_primary", -1, stream, if (stats) k_primary<true, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V));
-            else KL("k_primary", -1, stream, if (stats) k_primary<true, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V); else k_primary<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V));
+            if (inst) KL("k_primary", -1, stream, if (stats) k_primary<true, true><<<pb, LGB_TRAV_THREADS, kPrimarySmem, stream>>>(S, C, W, O, V); else k_primary<false, true><<<pb, LGB_TRAV_THREADS, kPrimarySmem, stream>>>(S, C, W, O, V));
+            else KL("k_primary", -1, stream, if (stats) k_primary<true, false><<<pb, LGB_TRAV_THREADS, kPrimarySmem, stream>>>(S, C, W, O, V); else k_primary<false, false><<<pb, LGB_TRAV_THREADS, kPrimarySmem, stream>>>(S, C, W, O, V));
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -2697,8 +2754,8 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
                 KL("k_pretest", (int)l, ls, if (inst) k_pretest<true><<<tb, kAppendThreads, 0, ls>>>(S, W, O, V, l); else k_pretest<false><<<tb, kAppendThreads, 0, ls>>>(S, W, O, V, l));
             }
             const char* sname = which == kQueueA ? "k_shadow(anchors)" : "k_shadow(rest)";
-            if (inst) KL(sname, (int)l, ls, if (stats) k_shadow<true, true><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); else k_shadow<false, true><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which));
-            else KL(sname, (int)l, ls, if (stats) k_shadow<true, false><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which); else k_shadow<false, false><<<sb, LGB_TRAV_THREADS, 0, ls>>>(S, W, O, V, l, which));
+            if (inst) KL(sname, (int)l, ls, if (stats) k_shadow<true, true><<<sb, LGB_TRAV_THREADS, kShadowSmem, ls>>>(S, W, O, V, l, which); else k_shadow<false, true><<<sb, LGB_TRAV_THREADS, kShadowSmem, ls>>>(S, W, O, V, l, which));
+            else KL(sname, (int)l, ls, if (stats) k_shadow<true, false><<<sb, LGB_TRAV_THREADS, kShadowSmem, ls>>>(S, W, O, V, l, which); else k_shadow<false, false><<<sb, LGB_TRAV_THREADS, kShadowSmem, ls>>>(S, W, O, V, l, which));
             if (which == kQueueA && l == 0) mark(3);      // (the anchor / rest split of the first light only)
         }
     }
@@ -2740,15 +2797,15 @@ cudaError_t launch_level(const DevScene& S, const DevCamera& C, const DevShade& 
     const unsigned pb = (unsigned)std::min<uint64_t>((total + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, (uint64_t)sms * LGB_MIN_BLOCKS);
     const unsigned blocks = (unsigned)((total + 255) / 256), ablocks = (unsigned)((total + kAppendThreads - 1) / kAppendThreads);
     if (S.instanced) {
-        k_primary<false, true, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V);
+        k_primary<false, true, true><<<pb, LGB_TRAV_THREADS, kPrimarySmem, stream>>>(S, C, W, O, V);
         k_setup<false, true, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
-        for (uint32_t l = 0; l < S.n_lights; l++) k_shadow<false, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, kQueueA);
+        for (uint32_t l = 0; l < S.n_lights; l++) k_shadow<false, true><<<pb, LGB_TRAV_THREADS, kPrimarySmem, stream>>>(S, W, O, V, l, kQueueA);
         k_shade<true, false, true, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
     } else {
-        k_primary<false, false, true><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, C, W, O, V);
+        k_primary<false, false, true><<<pb, LGB_TRAV_THREADS, kPrimarySmem, stream>>>(S, C, W, O, V);
         k_setup<false, false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
         if (S.grids) { DevOut Os = O; Os.counters = shadow_counters; k_gshadow<false, false><<<blocks, 256, 0, stream>>>(S, C, W, Os, V); }
-        else for (uint32_t l = 0; l < S.n_lights; l++) k_shadow<false, false><<<pb, LGB_TRAV_THREADS, 0, stream>>>(S, W, O, V, l, kQueueA);
+        else for (uint32_t l = 0; l < S.n_lights; l++) k_shadow<false, false><<<pb, LGB_TRAV_THREADS, kPrimarySmem, stream>>>(S, W, O, V, l, kQueueA);
         k_shade<false, false, true, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
     }
     return cudaGetLastError();
