@@ -84,26 +84,43 @@ class ClockSampler:
     def _run(self):
         while not self.stop_flag:
             try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                t = time.perf_counter()
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
                 r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for bit, name in self.HW.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                self.samples.append((t, mhz, r))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.01)
 
     def start(self):
+        """Started BEFORE the warm-up: the thread's start-up and NVML's first queries (milliseconds, and they serialise with kernel
+        launches in the driver) must not land inside a timed region that at 8 GPUs is only a dozen milliseconds long."""
         if self.nv:
             self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
 
-    def stop(self):
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t0=None, t1=None):
         self.stop_flag = True
         if self.thread:
             self.thread.join()
-        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        inside = [x for x in self.samples if t0 is None or t0 <= x[0] <= t1]
+        note = None
+        if not inside and self.samples:           # a region shorter than the sampling period: the samples on either side of it
+            inside = sorted(self.samples, key=lambda x: min(abs(x[0] - t0), abs(x[0] - t1)))[:2]
+            note = "timed region shorter than the 10 ms sampling period: the two nearest samples"
+        reasons = set()
+        for _, _, r in inside:
+            for bit, name in self.HW.items():
+                if r & bit:
+                    reasons.add(name)
+        out = {"sm_mhz": statistics.median(x[1] for x in inside) if inside else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(reasons), "samples": len(inside)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def workload(name, args):
@@ -297,22 +314,24 @@ def run_gpu(args):
     frame = {"primary_rays": tot[0], "primary_hits": tot[1], "shadow_rays_traced": tot[2], "shadow_occluded": tot[3]}
     rays_frame = frame["primary_rays"] + nl * frame["primary_hits"]
 
+    sampler = ClockSampler(local); sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local); sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     torch.cuda.synchronize()
+    t_region0 = sampler.mark()
     ev[0].record()
     for _ in range(args.steps):
         step()
     ev[1].record()
     torch.cuda.synchronize()
+    t_region1 = sampler.mark()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_region0, t_region1)
     total_ms = torch.tensor([ev[0].elapsed_time(ev[1])], device="cuda")
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)

@@ -83,6 +83,7 @@ struct lgb_ctx {
     int whitted_wavefront = 1;             // LGB_OPT_WHITTED: 1 level-by-level wavefront, 0 one thread per ray tree (k_secondary)
     int beams = -1;                        // LGB_OPT_BEAMS: 0 off, 1 on, -1 automatic
     uint64_t wave_budget = 16ull << 30;    // LGB_OPT_WAVE_BUDGET_MB: bytes of per-sample buffers one band of a frame may take
+    int setup_in_primary = 1;              // env LGB_SETUP_IN_PRIMARY (experiments): k_cprimary<SETUP>
     int lazy_bvh = -1;                     // LGB_OPT_LAZY_BVH: 0 build the device BVH at scene creation, 1 / -1 only when something needs it
     int camera_grid = -1;                  // LGB_OPT_CAMERA_GRID: 0 off, 1 on, -1 automatic
     int light_grids = -1;                  // LGB_OPT_LIGHT_GRIDS: 0 off, 1 on, -1 automatic (scenes of >= 1024 BVH nodes, <= 8 lights)
@@ -185,6 +186,7 @@ int lgb_init(int device, lgb_ctx** out) {
     if (const char* e = std::getenv("LGB_BEAMS")) { const int v = std::atoi(e); c->beams = v < 0 ? -1 : (v != 0); }
     if (const char* e = std::getenv("LGB_LIGHT_GRIDS")) { const int v = std::atoi(e); c->light_grids = v < 0 ? -1 : (v != 0); }
     if (const char* e = std::getenv("LGB_WAVE_BUDGET_MB")) { const long v = std::atol(e); if (v >= 1) c->wave_budget = (uint64_t)v << 20; }
+    if (const char* e = std::getenv("LGB_SETUP_IN_PRIMARY")) c->setup_in_primary = std::atoi(e) != 0;
     if (const char* e = std::getenv("LGB_LAZY_BVH")) { const int v = std::atoi(e); c->lazy_bvh = v < 0 ? -1 : (v != 0); }
     if (const char* e = std::getenv("LGB_CAMERA_GRID")) { const int v = std::atoi(e); c->camera_grid = v < 0 ? -1 : (v != 0); }
     c->side.n = 1;                         // one side stream: two lights' chains at a time (a third stream measured no further gain)
@@ -239,8 +241,18 @@ int lgb_init_devices(int ndev, const int* devices, lgb_ctx** out) {
             if (e != cudaSuccess) rc = cuda_fail(nullptr, e, "lgb_init_devices: peer access");
             else if (!can) rc = fail(nullptr, LGB_ERR_UNSUPPORTED, "lgb_init_devices: a listed device cannot access the first one's memory (no NVLink / P2P path)");
         }
+        if (!rc) {
+            // scene arenas and grids come from the leader's stream-ordered pool, which cudaDeviceEnablePeerAccess does not cover: without
+            // this grant the peer copies of a scene are staged through the host (measured: 31 ms for 7 x 160 MB instead of ~2)
+            cudaMemPool_t mp;
+            cudaMemAccessDesc acc{};
+            acc.location.type = cudaMemLocationTypeDevice; acc.location.id = devices[i]; acc.flags = cudaMemAccessFlagsProtReadWrite;
+            cudaError_t e = cudaDeviceGetDefaultMemPool(&mp, devices[0]);
+            if (e == cudaSuccess) e = cudaMemPoolSetAccess(mp, &acc, 1);
+            if (e != cudaSuccess) rc = cuda_fail(nullptr, e, "lgb_init_devices: cudaMemPoolSetAccess");
+        }
         if (rc) { const std::string msg = g_init_error; if (p) lgb_shutdown(p); lgb_shutdown(lead); g_init_error = msg; return rc; }
-        p->leader = lead; p->beams = lead->beams; p->light_grids = lead->light_grids; p->camera_grid = lead->camera_grid; p->wave_budget = lead->wave_budget; p->lazy_bvh = lead->lazy_bvh;
+        p->leader = lead; p->beams = lead->beams; p->light_grids = lead->light_grids; p->camera_grid = lead->camera_grid; p->wave_budget = lead->wave_budget; p->lazy_bvh = lead->lazy_bvh; p->setup_in_primary = lead->setup_in_primary;
         lead->peers.push_back(p);
     }
     *out = lead;
@@ -1431,6 +1443,8 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         if (!a.klog_no_camgrid) if (int rc = ensure_camgrid(c, s, a.w, a.h, total_all, W, st)) return rc;
     }
     const bool grid_shadows = S.grids && !S.instanced;                 // no shadow queues, no occluder cache
+    // hit setup inside the camera-grid kernel (no k_setup launch): plain captures whose shadows go through the light grids
+    W.setup_in_primary = (c->setup_in_primary && W.cg_start && grid_shadows && !a.aov && a.mode != 3) ? 1u : 0u;
     const bool beam_lists = W.beams && (!W.cg_start || !grid_shadows); // pixel beams (primary) and / or shadow beams
     const bool two_lists = beam_lists && !grid_shadows && S.n_lights > 1 && c->side_streams && c->side.n;
     const bool need_radiance = !render_fused(W.spp) || S.general || a.want_li;
@@ -1513,6 +1527,17 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
             if (ties) {
                 if (int rc = ensure_rank_tables(c, s)) return rc;
                 s->tie_retraces += ties; tie_slots += ties;
+                if (!S.nodes && s->deferred.scratch) {
+                    // the re-trace walks the BVH, and this scene was created without one (lgb_scene::Deferred): build it -- that re-orders
+                    // the primitives, so the hits of this band are void -- and render the band again, now with resident rank tables
+                    if (c->leader) return fail(c, LGB_ERR_INVALID, "internal: a device-group replica met an exact-t tie without a BVH");
+                    if (int rc = ensure_bvh(c, s)) return rc;
+                    W.cg_start = nullptr; W.cg_entries = nullptr; W.cg_large = nullptr;
+                    if (!a.klog_no_camgrid) if (int rc = ensure_camgrid(c, s, a.w, a.h, total_all, W, st)) return rc;
+                    band--;                                      // (unsigned wrap at band 0 is undone by the loop's increment)
+                    continue;
+                }
+                W.setup_in_primary = 0;                          // the re-traced slots change their hits: k_setup runs over the band after all
                 DevWork W2 = W;
                 DevCounters before{};
                 if (ties <= V.tie_cap) { W2.slot_list = V.tie_list; W2.n_list = ties; }
@@ -1559,7 +1584,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
                                          : s->dev.n_lights * (W.spp > 1 ? 3 : 1) + ((W.beams && W.spp > 1 && !S.instanced) ? 2 * s->dev.n_lights : 0);      // + k_sbeam + k_swalk per light
         const uint32_t primary_launches = W.cg_start ? 1u : (W.beams && W.spp >= 4 && !S.instanced) ? 3u : 1u;           // k_cprimary | k_beam + k_leafp + fallback | k_primary
         const uint32_t shade_launches = S.general ? (S.specular && S.recursion && !wf ? 3u : 2u) : (render_fused(W.spp) && !O.aov_li) ? 1u : 2u;
-        const uint32_t setup_launches = setup_fused(S, W, O, a.aov) ? 0u : 1u;                                          // (inside k_gshadow otherwise)
+        const uint32_t setup_launches = (W.setup_in_primary || setup_fused(S, W, O, a.aov)) ? 0u : 1u;                                          // (inside k_gshadow otherwise)
         stats->kernel_launches = total_all ? level_launches + (uint32_t)n_bands * (primary_launches + (one_kernel ? 1u : setup_launches + shadow_launches + shade_launches)) : 0;
         stats->bands = (uint32_t)n_bands;
         float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));

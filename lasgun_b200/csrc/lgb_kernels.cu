@@ -1366,6 +1366,12 @@ __device__ __forceinline__ uint32_t light_gates(const DevScene& S, const Ray64& 
     return gate;
 }
 
+// The rare slot whose sign decisions lean_surface leaves to the reference's own sequence (k_gshadow<SETUP>), out of line.
+__device__ __noinline__ void setup_generic(const DevScene& S, const Ray64& ray, double t, uint32_t ref, D3& ps, D3& ng, double& wo_ng) {
+    ShadePoint P; uint32_t id;
+    shade_point<false, false>(S, ray, t, ref, P, id);
+    ps = P.ps; ng = P.ng; wo_ng = dot(P.wo, P.ng);
+}
 // ================================================================== primary rays through the camera grid (lgb_grid.cu)
 // One thread per sample slot: the pixel's tile lists every primitive one of its samples can see, nearest first; each gets the f32
 // filter + the reference's exact test (closest hit, reference-order ties as everywhere), and the walk stops at the first entry that
@@ -1376,7 +1382,10 @@ __device__ __forceinline__ uint32_t light_gates(const DevScene& S, const Ray64& 
 #ifndef LGB_CPRIMARY_BLOCKS
 #define LGB_CPRIMARY_BLOCKS (1024 / LGB_CPRIMARY_THREADS)
 #endif
-template <bool STATS>
+// SETUP (plain captures with light grids): once the walk is over the thread still holds the camera ray and the hit, and the hit
+// primitive is warm in L1 -- it does k_setup's work for its slot right there (surface record, sign byte, shadow origin, gates) and
+// k_setup drops out of the frame.  The walk's own state is dead by then, so nothing is added to what lives across it.
+template <bool STATS, bool SETUP = false>
 __global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, LGB_CPRIMARY_BLOCKS) k_cprimary(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
     const uint64_t total = W.n_pixels * W.spp;
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1417,6 +1426,24 @@ __global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, LGB_CPRIMARY_BLOCKS) k_c
             V.hit_t[g] = hit ? T.best.t : CUDART_INF; V.hit_ref[g] = T.best.ref;
             hits += hit ? 1u : 0u;
             if (T.tied) { const uint32_t k = atomicAdd(V.tie_count, 1u); if (k < V.tie_cap) V.tie_list[k] = (uint32_t)g; }
+            if (SETUP && hit) {
+                const uint32_t ref = T.best.ref; const double t = T.best.t;
+                if (S.specular && (material_flags(S, ref) & kMatSpecular)) { V.occl[g] = 0; V.gate[g] = 0; }     // glass, mirror: BSDF::f is zero (bxdf/mod.rs:172)
+                else {
+                    LeanSurf Ls;
+                    lean_surface<true>(S, world, t, ref, 0u, Ls);
+                    D3 ng, ps; double wo_ng = 1.0;
+                    if (Ls.flags & kSfGeneric) setup_generic(S, world, t, ref, ps, ng, wo_ng);
+                    else {
+                        ng = (Ls.flags & kSfNgFlip) ? -Ls.n : Ls.n;
+                        ps = world.o + world.d * t + ng * (2.220446049250313e-16 * 65536.0);       // surface.rs:168, integrate.rs:40
+                    }
+                    V.ps[3 * g + 0] = ps.x; V.ps[3 * g + 1] = ps.y; V.ps[3 * g + 2] = ps.z;
+                    V.gate[g] = light_gates(S, world, ps, ng, wo_ng, !(Ls.flags & kSfGeneric));
+                    V.sflags[g] = (unsigned char)Ls.flags;
+                    V.occl[g] = 0;
+                }
+            }
         }
     }
     if (O.counters) {
@@ -1798,12 +1825,6 @@ __device__ __forceinline__ bool grid_blocked(const DevScene& S, D3 o, uint32_t l
     return hit;
 }
 
-// The rare slot whose sign decisions lean_surface leaves to the reference's own sequence (k_gshadow<SETUP>), out of line.
-__device__ __noinline__ void setup_generic(const DevScene& S, const Ray64& ray, double t, uint32_t ref, D3& ps, D3& ng, double& wo_ng) {
-    ShadePoint P; uint32_t id;
-    shade_point<false, false>(S, ray, t, ref, P, id);
-    ps = P.ps; ng = P.ng; wo_ng = dot(P.wo, P.ng);
-}
 // SETUP (camera rays of a plain capture): the thread also does k_setup's work for its slot -- surface record, sign byte, gates -- so
 // that the shadow origin goes from registers into the walk and is never stored (k_setup and its 24 B/slot of ps drop out of the frame).
 template <bool STATS, bool ALL_SHADOWS, bool SETUP = false>
@@ -2692,7 +2713,8 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
         const unsigned pb = (unsigned)std::min<uint64_t>((work + LGB_TRAV_THREADS - 1) / LGB_TRAV_THREADS, (uint64_t)sms * LGB_MIN_BLOCKS);
         if (W.cg_start && !inst && !W.slot_list) {
             const unsigned cb = (unsigned)((total + LGB_CPRIMARY_THREADS - 1) / LGB_CPRIMARY_THREADS);
-            KL("k_cprimary", -1, stream, if (stats) k_cprimary<true><<<cb, LGB_CPRIMARY_THREADS, 0, stream>>>(S, C, W, O, V); else k_cprimary<false><<<cb, LGB_CPRIMARY_THREADS, 0, stream>>>(S, C, W, O, V));
+            if (W.setup_in_primary) KL("k_cprimary(+setup)", -1, stream, if (stats) k_cprimary<true, true><<<cb, LGB_CPRIMARY_THREADS, 0, stream>>>(S, C, W, O, V); else k_cprimary<false, true><<<cb, LGB_CPRIMARY_THREADS, 0, stream>>>(S, C, W, O, V));
+            else KL("k_cprimary", -1, stream, if (stats) k_cprimary<true><<<cb, LGB_CPRIMARY_THREADS, 0, stream>>>(S, C, W, O, V); else k_cprimary<false><<<cb, LGB_CPRIMARY_THREADS, 0, stream>>>(S, C, W, O, V));
         } else if (W.beams && W.spp >= 4 && !inst && !W.slot_list) {
             // one bundle traversal per pixel, then every sample ray walks its pixel's leaf list; pixels whose bundle
             // reaches too many leaves go through the per-ray traversal (their slots are listed by k_leafp)
@@ -2719,8 +2741,12 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
         mark(5); mark(6);
         return cudaGetLastError();
     }
-    const bool setup_in_gshadow = setup_fused(S, W, O, all_shadows);
-    if (setup_in_gshadow) {             // hit setup inside the shadow kernel: ps never leaves the registers
+    const bool setup_in_gshadow = !W.setup_in_primary && setup_fused(S, W, O, all_shadows);
+    if (W.setup_in_primary) {           // k_cprimary<SETUP> has written ps / gate / sign byte: straight to the shadow rays
+        mark(2);
+        KL("k_gshadow", -1, stream, if (stats) k_gshadow<true, false><<<blocks, 256, 0, stream>>>(S, C, W, O, V); else k_gshadow<false, false><<<blocks, 256, 0, stream>>>(S, C, W, O, V));
+        mark(3);
+    } else if (setup_in_gshadow) {             // hit setup inside the shadow kernel: ps never leaves the registers
         mark(2);
         KL("k_gshadow(+setup)", -1, stream, if (stats) k_gshadow<true, false, true><<<blocks, 256, 0, stream>>>(S, C, W, O, V); else k_gshadow<false, false, true><<<blocks, 256, 0, stream>>>(S, C, W, O, V));
         mark(3);

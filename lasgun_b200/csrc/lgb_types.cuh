@@ -131,6 +131,7 @@ struct DevWork {
     const uint2* cg_entries;
     const uint2* cg_large;
     uint32_t cg_n_large, cg_shift, cg_nx;
+    uint32_t setup_in_primary;       // k_cprimary<SETUP> does k_setup's work (plain captures with light grids; run_capture decides)
     const double* rays;              // mode 3: origin + direction, 6 doubles per slot
     uint32_t depth;                  // mode 3: depth of these rays in integrate.rs:23's recursion (camera rays: 0)
     uint32_t hole_lo, hole_hi;       // mode 3: slots [hole_lo, hole_hi) hold no ray (reflected rays fill the level's slots from 0, transmitted ones from hole_hi)
