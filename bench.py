@@ -14,8 +14,9 @@ reference's semantics: primary = w*h*spp, shadow = lights * primary hits (integr
          the film into PAGEABLE memory, as a reference-side `Film` is), lgb_scene_destroy
   roofline  per kernel, largest first, from lgb_capture_profile (CUDA events around every launch, live, in this process):
          ops = the launch's own unit counts (node / primitive tests, rays, hits, light evaluations: the library's work counters)
-         x SURVEY 8d's constants of record; peak = SM count x observed SM clock x lanes x 2 (128 lanes for the FP32 kernels, 64
-         for the FP64 shading kernels); no microbenchmark in any denominator.
+         x SURVEY 8d's constants of record; peak = SM count x observed SM clock x lanes x 2 (128 lanes for the f32 filter / walk
+         work, 64 for the f64 hit setup and shading; a launch that does both is held to the blend of the two by its own op mix);
+         no microbenchmark in any denominator.
 --impl reference times the CPU oracle (C++ restatement of the reference algorithm — the Rust build
 cannot be compiled here) on all host threads over a bounded sample of the same frame.
 """
@@ -43,7 +44,6 @@ METRIC = "Mrays/s (primary+shadow)"
 OPS = {"node": 26, "sphere": (26, 39), "tri": (47, 68), "cuboid": 31, "camera": 30, "hit": 110, "light": 25 + 120, "ambient": 120,
        "background": 15, "film": 12}
 BYTES = {"node": 32, "sphere": 16, "tri": 48, "cuboid": 32, "ref": 4, "film": 4}
-FP64_KERNELS = ("k_setup", "k_shade")          # f64 reference arithmetic end to end: measured against the DFMA issue rate
 OTHER_CONFIGS = ("simple", "mesh1m", "cornell", "spheres1m")
 
 
@@ -194,23 +194,28 @@ def kernel_table(timed, counted, frame, w, h, nl, sm_count, clock_mhz, traffic):
     for t, c in zip(timed, counted):
         name = t["name"]
         ops, byts = traversal_ops(c)
+        ops64 = 0                                    # the part of the launch's work that is f64 reference arithmetic end to end
         units = {}
         if name.startswith(("k_primary", "k_leafp", "k_beam", "k_cprimary")):
             ops += c["primary_rays"] * OPS["camera"]; units["camera_rays"] = c["primary_rays"]
-        if name.startswith("k_setup"):
-            ops += hits * OPS["hit"]; units["hits"] = hits
+        if name.startswith("k_setup") or "+setup" in name:          # k_cprimary(+setup), k_gshadow(+setup): hit setup at the kernel's tail
+            ops64 += hits * OPS["hit"]; units["hits"] = hits
         if name.startswith("k_shade"):
             # one light evaluation (setup 25 + plastic BSDF 120) per unoccluded light that can contribute, the ambient evaluation per
             # hit, the background per miss, quantise + store per pixel
             evals = frame["shadow_rays_traced"] - frame["shadow_occluded"]
-            ops += evals * OPS["light"] + hits * OPS["ambient"] + (prim - hits) * OPS["background"] + w * h * OPS["film"]
+            ops64 += evals * OPS["light"] + hits * OPS["ambient"] + (prim - hits) * OPS["background"] + w * h * OPS["film"]
             byts += w * h * BYTES["film"]
             units.update(light_evaluations=evals, hits=hits, pixels=w * h)
-        fp64 = name.startswith(FP64_KERNELS)
-        peak = fp64_peak if fp64 else fp32_peak
-        ach = ops / (t["ms"] * 1e-3) / 1e9 if t["ms"] > 0 else 0.0
-        row = {"kernel": name, "launch_ms": t["ms"], "ops_per_launch": ops, "bytes_per_launch": byts, "achieved_gops": ach,
-               "bound": "fp64_issue" if fp64 else "fp32_issue", "peak_gops": peak, "frac": ach / peak,
+        # a launch that mixes the two (the walk in f32 filters, its setup tail in f64) is measured against the blend of the two issue
+        # rates weighted by its own op mix: the time the launch would take at peak is ops32 / fp32_peak + ops64 / fp64_peak
+        total = ops + ops64
+        at_peak = ops / fp32_peak + ops64 / fp64_peak
+        peak = total / at_peak if at_peak > 0 else fp32_peak
+        ach = total / (t["ms"] * 1e-3) / 1e9 if t["ms"] > 0 else 0.0
+        bound = "fp64_issue" if ops == 0 else "fp32_issue" if ops64 == 0 else "fp32+fp64_issue"
+        row = {"kernel": name, "launch_ms": t["ms"], "ops_per_launch": total, "fp64_ops_per_launch": ops64, "bytes_per_launch": byts, "achieved_gops": ach,
+               "bound": bound, "peak_gops": peak, "frac": ach / peak,
                "node_tests": c["node_tests"], "filter_tests": c["filter_tests"], "exact_tests": c["exact_tests"], **units}
         key = name.split("[")[0].split("(")[0]
         if traffic and key in traffic:
@@ -509,11 +514,13 @@ def run_gpu(args):
                 "bound": "hbm" if False else top["bound"], "achieved": top["achieved_gops"], "peak": top["peak_gops"], "unit": "Gop/s (FMA=2)",
                 "frac": top["frac"], "traffic": top.get("traffic"), "traffic_source": traffic_note,
                 "launch_ms": top["launch_ms"], "ops_per_launch": top["ops_per_launch"],
-                "peak_source": "%d SMs x %.0f MHz (median SM clock sampled during the timed region) x %d lanes x 2" % (sm_count, clock, 64 if top["bound"] == "fp64_issue" else 128),
+                "peak_source": "%d SMs x %.0f MHz (median SM clock sampled during the timed region) x %s lanes x 2" % (
+                    sm_count, clock, {"fp64_issue": "64", "fp32_issue": "128"}.get(top["bound"], "128 (f32 part) / 64 (f64 part), blended by the launch's op mix")),
                 "ops_definition": "the launch's own unit counts (work counters of an untimed frame of the same kernels) x SURVEY 8d constants of record",
                 "kernels": [{k: v for k, v in r.items() if k not in ("filter_tests", "exact_tests")} for r in rows],
                 "frame": {"ops": sum(r["ops_per_launch"] for r in rows), "sum_of_launch_ms": tsum,
-                          "frac_fp32_issue": sum(r["ops_per_launch"] for r in rows) / (tsum * 1e-3) / 1e9 / fp32_peak},
+                          "frac_fp32_issue": sum(r["ops_per_launch"] for r in rows) / (tsum * 1e-3) / 1e9 / fp32_peak,
+                          "frac_blended": sum(r["ops_per_launch"] / r["peak_gops"] for r in rows) / 1e9 / (tsum * 1e-3)},
                 "hbm": {"compulsory_bytes": scene_bytes + w * h * 4, "peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["source"],
                         "traffic_per_frame": sum(r["traffic"] for r in rows if "traffic" in r) if traffic else None},
                 "microbenchmarks_not_used_as_peaks": {"fp32_ffma_glanes": ceil["fp32_ffma_glanes"], "fp64_dfma_glanes": ceil["fp64_dfma_glanes"], "l2_read_gbs": ceil["l2_read_gbs"]},
