@@ -77,6 +77,7 @@ struct lgb_ctx {
     // device group (lgb_init_devices): this context leads, `peers` render their share of the tiles into its film over NVLink
     std::vector<lgb_ctx*> peers;
     lgb_ctx* leader = nullptr;
+    cudaMemPool_t share_pool = nullptr;    // a group leader's scene arenas and grids live here: a pool of its own that the peers may read (lgb_init_devices)
     std::mutex lazy_mu;                    // the caller's reference_tree callback is entered by one device at a time
     SideStreams side{};                    // streams the shadow chains of different lights are spread over (LGB_OPT_SIDE_STREAMS)
     int side_streams = 1;
@@ -241,19 +242,28 @@ int lgb_init_devices(int ndev, const int* devices, lgb_ctx** out) {
             if (e != cudaSuccess) rc = cuda_fail(nullptr, e, "lgb_init_devices: peer access");
             else if (!can) rc = fail(nullptr, LGB_ERR_UNSUPPORTED, "lgb_init_devices: a listed device cannot access the first one's memory (no NVLink / P2P path)");
         }
-        if (!rc) {
-            // scene arenas and grids come from the leader's stream-ordered pool, which cudaDeviceEnablePeerAccess does not cover: without
-            // this grant the peer copies of a scene are staged through the host (measured: 31 ms for 7 x 160 MB instead of ~2)
-            cudaMemPool_t mp;
-            cudaMemAccessDesc acc{};
-            acc.location.type = cudaMemLocationTypeDevice; acc.location.id = devices[i]; acc.flags = cudaMemAccessFlagsProtReadWrite;
-            cudaError_t e = cudaDeviceGetDefaultMemPool(&mp, devices[0]);
-            if (e == cudaSuccess) e = cudaMemPoolSetAccess(mp, &acc, 1);
-            if (e != cudaSuccess) rc = cuda_fail(nullptr, e, "lgb_init_devices: cudaMemPoolSetAccess");
-        }
         if (rc) { const std::string msg = g_init_error; if (p) lgb_shutdown(p); lgb_shutdown(lead); g_init_error = msg; return rc; }
         p->leader = lead; p->beams = lead->beams; p->light_grids = lead->light_grids; p->camera_grid = lead->camera_grid; p->wave_budget = lead->wave_budget; p->lazy_bvh = lead->lazy_bvh; p->setup_in_primary = lead->setup_in_primary;
         lead->peers.push_back(p);
+    }
+    if (ndev > 1) {
+        // What the peers copy from the leader (scene arena, light grids) is stream-ordered pool memory, which cudaDeviceEnablePeerAccess
+        // does not cover: without a grant those peer copies are staged through the host (measured: 31 ms for 7 x 160 MB instead of ~2).
+        // The grant goes to a pool of the group's own, made here while it is empty -- granting it on the device's default pool made
+        // that pool refuse to grow afterwards whenever it already held memory of another context (scripts/diag_group_pool.py).
+        cudaSetDevice(devices[0]);
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned; props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice; props.location.id = devices[0];
+        cudaError_t e = cudaMemPoolCreate(&lead->share_pool, &props);
+        if (e == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(lead->share_pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            std::vector<cudaMemAccessDesc> acc((size_t)ndev - 1);
+            for (int i = 1; i < ndev; i++) { acc[i - 1] = cudaMemAccessDesc{}; acc[i - 1].location.type = cudaMemLocationTypeDevice; acc[i - 1].location.id = devices[i]; acc[i - 1].flags = cudaMemAccessFlagsProtReadWrite; }
+            e = cudaMemPoolSetAccess(lead->share_pool, acc.data(), acc.size());
+        }
+        if (e != cudaSuccess) { const int rc = cuda_fail(nullptr, e, "lgb_init_devices: shared memory pool"); const std::string msg = g_init_error; lgb_shutdown(lead); g_init_error = msg; return rc; }
     }
     *out = lead;
     return LGB_OK;
@@ -330,6 +340,7 @@ void lgb_shutdown(lgb_ctx* c) {
     for (auto& e : c->phase) cudaEventDestroy(e);
     for (int k = 0; k < c->side.n; k++) { cudaStreamDestroy(c->side.s[k]); cudaEventDestroy(c->side.join[k]); }
     cudaEventDestroy(c->side.fork);
+    if (c->share_pool) cudaMemPoolDestroy(c->share_pool);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -643,6 +654,10 @@ uint32_t lgb_scene_node_count(const lgb_scene* s) { if (!s) return 0; ensure_bvh
 // "a BVH of >= 1024 nodes", also for a scene whose tree is deferred (leaves hold up to 4 primitives: ~n / 2 nodes)
 static bool large_scene(const DevScene& S) { return S.nodes ? S.n_nodes >= 1024u : (S.n_sph + S.n_cub + S.n_tri) / 2 >= 1024u; }
 
+// memory a device group's peers copy from (scene arena, grids): the leader's shared pool; any other context: the device's default pool
+static cudaError_t shared_alloc(lgb_ctx* ctx, void** p, size_t bytes, cudaStream_t st) {
+    return ctx->share_pool ? cudaMallocFromPoolAsync(p, bytes, ctx->share_pool, st) : cudaMallocAsync(p, bytes, st);
+}
 static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
     DevScene& S = s->dev;
     S.grids = nullptr;
@@ -666,7 +681,11 @@ static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
         if (!keep) for (void* p : mine) cudaFreeAsync(p, st);
     };
 #define GR(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(false); return cuda_fail(ctx, e__, #call); } } while (0)
-    auto alloc = [&](std::vector<void*>& owner, size_t bytes, void** out) { cudaError_t e = cudaMallocAsync(out, std::max<size_t>(bytes, 16), st); if (e == cudaSuccess) owner.push_back(*out); return e; };
+    auto alloc = [&](std::vector<void*>& owner, size_t bytes, void** out) {
+        cudaError_t e = &owner == &mine ? shared_alloc(ctx, out, std::max<size_t>(bytes, 16), st) : cudaMallocAsync(out, std::max<size_t>(bytes, 16), st);
+        if (e == cudaSuccess) owner.push_back(*out);
+        return e;
+    };
     uint32_t* counts = nullptr; void* scan_tmp = nullptr; unsigned long long* bounds = nullptr; uint32_t* totals = nullptr; uint2* large_tmp = nullptr; DevGrid* dtab = nullptr;
     GR(alloc(temp, (nc + 1) * 4, (void**)&counts));
     GR(alloc(temp, scan_bytes, &scan_tmp));
@@ -959,10 +978,14 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         {
             cudaError_t e = ctx->reserve_staging(st_raw + raw_bytes);
             if (e != cudaSuccess) return bail(e == cudaErrorMemoryAllocation ? fail(ctx, LGB_ERR_NOMEM, "scene upload: pinned staging allocation failed") : cuda_fail(ctx, e, "cudaHostAlloc"));
-            e = cudaMallocAsync(&s->arena, arena_cap, ctx->stream);
+            e = shared_alloc(ctx, &s->arena, arena_cap, ctx->stream);
             if (e != cudaSuccess) { s->arena = nullptr; return bail(e == cudaErrorMemoryAllocation ? fail(ctx, LGB_ERR_NOMEM, "scene upload: device allocation failed") : cuda_fail(ctx, e, "cudaMallocAsync")); }
             e = cudaMallocAsync(&scratch, scratch_bytes, ctx->stream);
-            if (e != cudaSuccess) return bail(e == cudaErrorMemoryAllocation ? fail(ctx, LGB_ERR_NOMEM, "scene build: device scratch allocation failed") : cuda_fail(ctx, e, "cudaMallocAsync"));
+            if (e != cudaSuccess) {
+                size_t fr = 0, tot = 0; cudaGetLastError(); cudaMemGetInfo(&fr, &tot);
+                char msg[160]; std::snprintf(msg, sizeof msg, "scene build: device scratch allocation of %zu bytes failed (%zu of %zu bytes free on the device)", scratch_bytes, fr, tot);
+                return bail(e == cudaErrorMemoryAllocation ? fail(ctx, LGB_ERR_NOMEM, msg) : cuda_fail(ctx, e, "cudaMallocAsync"));
+            }
         }
         char* H = (char*)ctx->staging; char* D = (char*)s->arena; char* T = (char*)scratch;
         auto gfail = [&](int code) { if (!s->deferred.scratch) cudaFreeAsync(scratch, ctx->stream); return bail(code); };
@@ -1085,7 +1108,7 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
     {
         cudaError_t e = ctx->reserve_staging(arena_bytes);
         if (e != cudaSuccess) return bail(e == cudaErrorMemoryAllocation ? fail(ctx, LGB_ERR_NOMEM, "scene upload: pinned staging allocation failed") : cuda_fail(ctx, e, "cudaHostAlloc"));
-        e = cudaMallocAsync(&s->arena, arena_bytes, ctx->stream);
+        e = shared_alloc(ctx, &s->arena, arena_bytes, ctx->stream);
         if (e != cudaSuccess) { s->arena = nullptr; return bail(e == cudaErrorMemoryAllocation ? fail(ctx, LGB_ERR_NOMEM, "scene upload: device allocation failed") : cuda_fail(ctx, e, "cudaMallocAsync")); }
         s->bytes = arena_bytes;
         // the previous scene's H2D copy out of the staging buffer is complete: lgb_scene_create synchronises before returning

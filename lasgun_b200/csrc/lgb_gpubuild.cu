@@ -451,12 +451,18 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
     void* scan_tmp = take(scan_bytes);
 
     cudaError_t e;
-    const bool dbg = std::getenv("LGB_GPUBUILD_DEBUG") != nullptr;
-    auto check = [&](const char* what, uint32_t level) {      // debug: find the kernel that faults
+    const bool dbg = std::getenv("LGB_GPUBUILD_DEBUG") != nullptr;       // synchronise after every kernel: finds the one that faults, and says
+    double k_ms[2][4] = {};                                              // where the levels' time goes (top 8 levels | the rest) x (prep, bin, split, scatter)
+    auto t_k = std::chrono::steady_clock::now();
+    auto check = [&](const char* what, uint32_t level) {
         if (!dbg) return cudaSuccess;
         cudaError_t ce = cudaStreamSynchronize(st);
         if (ce == cudaSuccess) ce = cudaGetLastError();
         if (ce != cudaSuccess) std::fprintf(stderr, "[gpu_build_sah] %s failed at level %u: %s\n", what, level, cudaGetErrorString(ce));
+        const auto t = std::chrono::steady_clock::now();
+        const int which = what[2] == 'p' ? 0 : what[2] == 'b' ? 1 : what[3] == 'p' ? 2 : 3;       // k_prep, k_bin, k_split, k_scatter
+        k_ms[level < 8 ? 0 : 1][which] += std::chrono::duration<double, std::milli>(t - t_k).count();
+        t_k = t;
         return ce;
     };
     const unsigned ib = (n + 255) / 256;
@@ -517,6 +523,8 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
         std::fprintf(stderr, "[gpu_build_sah] %u items, %u levels (%u launched), %.2f ms total; per chunk of %u levels:", n, levels, launched, std::chrono::duration<double, std::milli>(now() - t_start).count(), kChunk);
         for (size_t i = 0; i < chunk_ms.size(); i++) std::fprintf(stderr, " %.2f", chunk_ms[i]);
         std::fprintf(stderr, "\n");
+        if (dbg) for (int h = 0; h < 2; h++) std::fprintf(stderr, "[gpu_build_sah]   %s: prep %.2f bin %.2f split %.2f scatter %.2f ms (synchronised after every kernel)\n", h ? "levels 8.." : "levels 0..7",
+                                                          k_ms[h][0], k_ms[h][1], k_ms[h][2], k_ms[h][3]);
     }
     for (int t = 0; t < 3; t++) typepos_out[t] = typepos[t];
     info->n_nodes = node_count; info->max_depth = max_depth; info->levels = levels;

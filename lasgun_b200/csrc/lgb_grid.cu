@@ -238,15 +238,47 @@ __global__ void __launch_bounds__(256) k_cam_pass(DevScene S, CamGridParams P, u
 // a non-negative float order like the float, so one segmented key sort (cub::DeviceSegmentedSort, off the frame's path like the scans)
 // over the cell ranges does it for lists of any length -- a thread per cell was held up for milliseconds by the few cells that hold
 // hundreds of entries.
-size_t grid_sort_bytes(uint32_t total, size_t n_cells) {
+// Short lists (almost all of them: a light-grid cell holds a handful of entries and most of the 6 M cells hold none) are sorted by ONE
+// thread each, in local memory; only the cells longer than kSortThread go to the segmented sort, as a compacted list of ranges --
+// handing it all the cells cost 2 ms per light for 4 M entries, nearly all of it per-segment bookkeeping for empty and tiny segments.
+// A cell counts as long above 32 entries, so there are at most total / 33 of them: that bound sizes the range list and is the
+// segment count the sort is launched with (unused ranges are empty), so the host need not read anything back.
+constexpr uint32_t kSortThread = 32;
+static uint32_t long_bound(uint32_t total) { return total / (kSortThread + 1) + 1; }
+static size_t long_list_bytes(uint32_t total) { return ((size_t)(2 * long_bound(total) + 1) * 4 + 255) & ~(size_t)255; }
+size_t grid_sort_bytes(uint32_t total, size_t) {
     size_t b = 0;
-    cub::DeviceSegmentedSort::SortKeys(nullptr, b, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)total, (int)n_cells, (const uint32_t*)nullptr, (const uint32_t*)nullptr);
-    return b;
+    cub::DeviceSegmentedSort::SortKeys(nullptr, b, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)total, (int)long_bound(total), (const uint32_t*)nullptr, (const uint32_t*)nullptr);
+    return b + long_list_bytes(total);
+}
+__global__ void __launch_bounds__(128) k_sort_short(const unsigned long long* in, unsigned long long* out, const uint32_t* starts, uint32_t n_cells,
+                                                    uint32_t* long_begin, uint32_t* long_end, uint32_t* n_long) {
+    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    const uint32_t b = starts[cell], n = starts[cell + 1] - b;
+    if (n == 0) return;
+    if (n == 1) { out[b] = in[b]; return; }
+    if (n > kSortThread) { const uint32_t k = atomicAdd(n_long, 1u); long_begin[k] = b; long_end[k] = b + n; return; }
+    unsigned long long v[kSortThread];
+    for (uint32_t i = 0; i < n; i++) {                      // insertion sort as the entries arrive
+        const unsigned long long x = in[b + i];
+        uint32_t j = i;
+        while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; j--; }
+        v[j] = x;
+    }
+    for (uint32_t i = 0; i < n; i++) out[b + i] = v[i];
 }
 static cudaError_t sort_cells(const uint2* in, uint2* out, uint32_t total, const uint32_t* starts, size_t n_cells, void* tmp, size_t tmp_bytes, cudaStream_t st) {
     if (total == 0) return cudaSuccess;
-    return cub::DeviceSegmentedSort::SortKeys(tmp, tmp_bytes, reinterpret_cast<const unsigned long long*>(in), reinterpret_cast<unsigned long long*>(out), (int)total, (int)n_cells,
-                                              starts, starts + 1, st);
+    const uint32_t bound = long_bound(total);
+    const size_t list_bytes = long_list_bytes(total);
+    uint32_t* long_begin = (uint32_t*)tmp; uint32_t* long_end = long_begin + bound; uint32_t* n_long = long_end + bound;
+    if (cudaError_t e = cudaMemsetAsync(tmp, 0, list_bytes, st)) return e;
+    k_sort_short<<<(unsigned)((n_cells + 127) / 128), 128, 0, st>>>(reinterpret_cast<const unsigned long long*>(in), reinterpret_cast<unsigned long long*>(out), starts, (uint32_t)n_cells,
+                                                                    long_begin, long_end, n_long);
+    size_t cub_bytes = tmp_bytes - list_bytes;
+    return cub::DeviceSegmentedSort::SortKeys((char*)tmp + list_bytes, cub_bytes, reinterpret_cast<const unsigned long long*>(in), reinterpret_cast<unsigned long long*>(out), (int)total, (int)bound,
+                                              long_begin, long_end, st);
 }
 cudaError_t camgrid_count(const DevScene& S, const CamGridParams& P, uint32_t* counts, uint32_t* starts, void* scan_tmp, size_t scan_bytes,
                           uint2* large, uint32_t* n_large_dev, cudaStream_t st, uint32_t* total_out, uint32_t* n_large_out) {
