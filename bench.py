@@ -471,9 +471,32 @@ def run_gpu(args):
     scene_bytes = int(dev.device_bytes)
     d_ = flat.desc                                   # what lgb_scene_create copies to the device: the caller's arrays (+ rank tables when the tree is given)
     h2d_bytes = int(d_.n_spheres * 40 + d_.n_cuboids * 56 + d_.n_triangles * (44 + (36 if d_.tri_normals else 0)))
+    h2d_bytes_lazy = h2d_bytes
     if world > 1:
         h2d_bytes += 8 * 4 * int(d_.n_spheres + d_.n_cuboids + d_.n_triangles + 1)
 
+    # The e2e headline is the call a user of the reference makes: ONE host process, capture(scene, film) (lib.rs:55-104), fanning out
+    # over the N GPUs inside the library (lgb_init_devices).  The one-process-per-GPU form of the same frame (scene built on rank 0,
+    # arena broadcast over NCCL, peer-stored film) is reported beside it; at N = 1 the two are the same call.
+    per_process = {"value": rays_frame / (e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e,
+                   "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": w * h * 4, "film_memory": "pageable",
+                   "ms_per_frame_pinned_film": statistics.median(e2e_pinned),
+                   "reference_tree_built": bool(world > 1 or (flat_i is not None and flat_i.tree_built)),
+                   "parts_ms": dict(zip(("flatten", "scene_create_device_bvh_grids_upload", "camera_grid_render_readback_destroy"),
+                                        [statistics.median(p[i] for p in e2e_parts) for i in range(3)]))}
+    if world > 1 and group and "error" not in group:
+        e2e_line = {"value": group["e2e_value"], "unit": "Mrays/s", "ms_per_frame": group["e2e_ms_per_frame"],
+                    "h2d_bytes_per_step": h2d_bytes_lazy, "d2h_bytes_per_step": w * h * 4, "film_memory": "pageable",
+                    "path": "one host process, %d GPUs as a device group (lgb_init_devices): FlatScene(lazy) + lgb_scene_create + lgb_capture into a pageable host film" % world,
+                    "reference_tree_built": False, "parts_ms": group["parts_ms"], "identical_to_one_gpu": group["identical_to_one_gpu"],
+                    "slowest_device_render_ms": group["slowest_device_render_ms"],
+                    "resident_ms_per_frame_host_clock": group["resident_ms_per_frame_host_clock"], "resident_value": group["resident_value"],
+                    "one_process_per_gpu": per_process}
+    else:
+        e2e_line = dict(per_process)
+        if world > 1:
+            e2e_line["path"] = "one process per GPU (scene built on rank 0, arena broadcast over NCCL, film peer-stored into rank 0)"
+            e2e_line["one_process_device_group"] = group
     if rank == 0:
         peaks = load_peaks()
         sm_count = torch.cuda.get_device_properties(local).multi_processor_count
@@ -491,13 +514,7 @@ def run_gpu(args):
                        "l2_policy": "per-frame working set (wavefront buffers %.0f MB + scene %.0f MB) exceeds the 126 MB L2" % (frame["primary_rays"] * 57 / 1e6 / world, scene_bytes / 1e6)},
             "ms_per_frame": ms_per_step, "kernel_ms_per_frame": kernel_ms, "rays_per_frame": rays_frame,
             "rays_traced_per_frame": frame["primary_rays"] + frame["shadow_rays_traced"],
-            "e2e": {"value": rays_frame / (e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": w * h * 4, "film_memory": "pageable",
-                    "ms_per_frame_pinned_film": statistics.median(e2e_pinned),
-                    "reference_tree_built": bool(world > 1 or (flat_i is not None and flat_i.tree_built)),
-                    "parts_ms": dict(zip(("flatten", "scene_create_device_bvh_grids_upload", "camera_grid_render_readback_destroy"),
-                                         [statistics.median(p[i] for p in e2e_parts) for i in range(3)])),
-                    "one_process_device_group": group},
+            "e2e": e2e_line,
             "gpu_launches": int(s2["kernel_launches"]) * args.steps,
             "work_per_frame": frame,
             "clocks": clocks,

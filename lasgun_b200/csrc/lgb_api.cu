@@ -101,6 +101,9 @@ struct lgb_ctx {
         if (e == cudaSuccess) staging_cap = bytes + bytes / 4;
         return e;
     }
+    // pinned bounce buffer of the film read-back into pageable memory (finish_host), and one event per chunk of it
+    void* film_host = nullptr; size_t film_host_cap = 0;
+    std::vector<cudaEvent_t> chunk_ev;
 };
 
 struct lgb_scene {
@@ -336,6 +339,8 @@ void lgb_shutdown(lgb_ctx* c) {
     for (DevBuf& b : c->lvl_rad) b.release();
     for (DevBuf& b : c->lvl_recs) b.release();
     if (c->staging) cudaFreeHost(c->staging);
+    if (c->film_host) cudaFreeHost(c->film_host);
+    for (cudaEvent_t e : c->chunk_ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
     for (auto& e : c->phase) cudaEventDestroy(e);
     for (int k = 0; k < c->side.n; k++) { cudaStreamDestroy(c->side.s[k]); cudaEventDestroy(c->side.join[k]); }
@@ -1676,7 +1681,40 @@ int lgb_capture_device(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint32_
     return run_capture(c, s, a, stats, stats != nullptr);
 }
 
+// The film goes to the caller's buffer.  A pageable one (the reference's Film is a Vec, film.rs:22-45) makes cudaMemcpy bounce through
+// the driver's own small pinned buffers at ~13 GB/s; instead the film crosses PCIe in chunks into a pinned buffer of the context's at
+// the link's rate, and every host thread carries a chunk on into the caller's memory while the next one is crossing.
 static int finish_host(lgb_ctx* c, const void* dev, void* host, size_t bytes, lgb_stats* stats) {
+    constexpr size_t kChunk = 4u << 20;
+    bool bounce = bytes >= 2 * kChunk && !std::getenv("LGB_NO_FILM_BOUNCE");
+    if (bounce) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); bounce = false; }
+        else bounce = at.type == cudaMemoryTypeUnregistered;
+    }
+    if (bounce && c->film_host_cap < bytes) {
+        if (c->film_host) cudaFreeHost(c->film_host);
+        c->film_host = nullptr; c->film_host_cap = 0;
+        if (cudaHostAlloc(&c->film_host, bytes, cudaHostAllocDefault) == cudaSuccess) c->film_host_cap = bytes; else { cudaGetLastError(); bounce = false; }
+    }
+    if (bounce) {
+        const size_t n = (bytes + kChunk - 1) / kChunk;
+        while (c->chunk_ev.size() < n) { cudaEvent_t e; CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->chunk_ev.push_back(e); }
+        for (size_t i = 0; i < n; i++) {
+            const size_t off = i * kChunk, len = std::min(kChunk, bytes - off);
+            CU(c, cudaMemcpyAsync((char*)c->film_host + off, (const char*)dev + off, len, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaEventRecord(c->chunk_ev[i], c->stream));
+        }
+        CU(c, cudaEventRecord(c->ev2, c->stream));
+        for (size_t i = 0; i < n; i++) {
+            const size_t off = i * kChunk, len = std::min(kChunk, bytes - off);
+            CU(c, cudaEventSynchronize(c->chunk_ev[i]));
+            const char* src = (const char*)c->film_host + off; char* dst = (char*)host + off;
+            Pool::get().for_range(len, 256u << 10, [&](size_t b, size_t e, size_t) { std::memcpy(dst + b, src + b, e - b); });
+        }
+        if (stats) { float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev2)); stats->total_ms = ms; }
+        return LGB_OK;
+    }
     CU(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaEventRecord(c->ev2, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));

@@ -23,6 +23,9 @@
 #ifndef LGB_WALK_PREFETCH
 #define LGB_WALK_PREFETCH 0          // grid walks (k_cprimary, k_gshadow): load entry i + 1 while entry i is tested
 #endif
+#ifndef LGB_WALK_SPLIT
+#define LGB_WALK_SPLIT 1             // grid walks: filters run down the list until one passes, then the warp meets for the exact test (prim_filter / prim_exact)
+#endif
 
 namespace lgb {
 
@@ -322,6 +325,70 @@ __device__ __forceinline__ bool leaf_prims(const DevScene& S, const Ray64& world
             }
         }
     }
+    return false;
+}
+
+// The two halves of leaf_prims for ONE primitive, for the grid walks (k_cprimary, k_gshadow; LGB_WALK_SPLIT): a lane first runs
+// filters down its list until one passes, then the warp meets for the exact f64 test.  In the fused form a warp ran the exact test
+// -- by far the longest stretch of the loop body -- in nearly every iteration for whichever lanes happened to pass in that one.
+template <bool STATS>
+__device__ __forceinline__ bool prim_filter(const DevScene& S, const RayF& f, float best_tf, uint32_t type, uint32_t idx, LocalCounters& lc) {
+    if (type == LGB_PRIM_SPHERE) {
+        const float4 s = __ldg(&S.sph32[idx]);
+        if (STATS) lc.filter[0]++;
+        const float lx = s.x - f.ox, ly = s.y - f.oy, lz = s.z - f.oz;
+        const float bq = lx * f.dx + ly * f.dy + lz * f.dz;
+        const float tc = bq * f.inv_dd;
+        const float wx = __fmaf_rn(-tc, f.dx, lx), wy = __fmaf_rn(-tc, f.dy, ly), wz = __fmaf_rn(-tc, f.dz, lz);
+        const float perp2 = wx * wx + wy * wy + wz * wz;
+        const float rr = s.w + 2.0f * f.err;
+        if (perp2 > rr * rr * (1.0f + 1e-6f)) return false;
+        const float half = rr * f.inv_len;
+        const float slack = fabsf(tc) * 2e-6f + 2.0f * f.err * f.inv_len;
+        if (tc - half - slack > best_tf) return false;
+        if (tc + half + slack < 0.0f) return false;
+        return true;
+    }
+    if (type == LGB_PRIM_TRIANGLE) {
+        const float4* tp = S.tri + 3 * (size_t)idx;
+        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+        if (STATS) lc.filter[2]++;
+        return f.kz == 0 ? tri_filter<0>(q0, q1, q2, f, best_tf) : f.kz == 1 ? tri_filter<1>(q0, q1, q2, f, best_tf) : tri_filter<2>(q0, q1, q2, f, best_tf);
+    }
+    const float4 lo = __ldg(&S.cub32[2 * idx]), hi = __ldg(&S.cub32[2 * idx + 1]);
+    if (STATS) lc.filter[1]++;
+    float tn;
+    return slab2(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, f, CUDART_INF_F, tn);
+}
+template <bool ANYHIT, bool STATS>
+__device__ __forceinline__ bool prim_exact(const DevScene& S, const Ray64& world, const Ray64& ray, const RayF& f, Trav& T, uint32_t type, uint32_t idx, double tmax,
+                                           LocalCounters& lc) {
+    Hit& best = T.best;
+    double t; bool ok;
+    if (type == LGB_PRIM_SPHERE) {
+        if (STATS) lc.exact[0]++;
+        const double2 c01 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx));
+        const double2 c23 = __ldg(reinterpret_cast<const double2*>(S.sph64 + 4 * (size_t)idx + 2));
+        bool inside;
+        ok = sphere_exact(d3(c01.x, c01.y, c23.x), c23.y, ray, t, inside);
+    } else if (type == LGB_PRIM_TRIANGLE) {
+        if (STATS) lc.exact[2]++;
+        const float4* tp = S.tri + 3 * (size_t)idx;
+        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+        double b0, b1, b2;
+        ok = triangle_exact(d3(q0.x, q0.y, q0.z), d3(q1.x, q1.y, q1.z), d3(q2.x, q2.y, q2.z), ray, t, b0, b1, b2);
+    } else {
+        if (STATS) lc.exact[1]++;
+        double mn[3], mx[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { mn[k] = __ldg(&S.cub64[6 * (size_t)idx + k]); mx[k] = __ldg(&S.cub64[6 * (size_t)idx + 3 + k]); }
+        int ua, va;
+        ok = cuboid_exact(mn, mx, ray, t, ua, va);
+    }
+    if (!ok) return false;
+    const uint32_t ref = LGB_PRIM_REF(type, idx);
+    if (ANYHIT) { if (t < tmax) { best.t = t; best.ref = ref; return true; } return false; }
+    if (accepts<false>(S, f, world, best, t, ref, T.tied)) { best.t = t; best.ref = ref; T.best_tf = __double2float_ru(t); T.best_up = inflate_up(t); }
     return false;
 }
 
@@ -1405,6 +1472,22 @@ __global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, LGB_CPRIMARY_BLOCKS) k_c
             const uint32_t b = __ldg(W.cg_start + cell), e = __ldg(W.cg_start + cell + 1);
             const float to_t = f.inv_len * (1.0f - 2e-6f);                   // an entry's distance from the eye -> a lower bound of its ray parameter
             const bool sorted = e - b <= kGridSortMax;                       // (longer lists are not sorted: lgb_grid.cu)
+#if LGB_WALK_SPLIT
+            // positions [b, e) are the tile's list, [e, e2) the large list (both nearest first)
+            const uint32_t e2 = e + W.cg_n_large;
+            for (uint32_t i = b;;) {
+                uint32_t cand = 0xFFFFFFFFu;
+                while (i < e2) {
+                    const bool in_cell = i < e;
+                    const uint2 r = __ldg(in_cell ? W.cg_entries + i : W.cg_large + (i - e));
+                    i++;
+                    if (__uint_as_float(r.y) * to_t > T.best_up) { if (!in_cell) i = e2; else if (sorted) i = e; continue; }    // nearest first: nothing behind the best hit can beat it
+                    if (prim_filter<STATS>(S, f, T.best_tf, r.x >> 30, r.x & 0x3FFFFFFFu, lc)) { cand = r.x; break; }
+                }
+                if (cand == 0xFFFFFFFFu) break;
+                prim_exact<false, STATS>(S, world, ray, f, T, cand >> 30, cand & 0x3FFFFFFFu, CUDART_INF, lc);
+            }
+#else
 #if LGB_WALK_PREFETCH
             uint2 nxt = b < e ? __ldg(W.cg_entries + b) : make_uint2(0u, 0u);
             for (uint32_t i = b; i < e; i++) {
@@ -1422,6 +1505,7 @@ __global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, LGB_CPRIMARY_BLOCKS) k_c
                 if (__uint_as_float(r.y) * to_t > T.best_up) break;
                 leaf_prims<false, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, CUDART_INF, lc);
             }
+#endif
             const bool hit = T.best.ref != LGB_MISS;
             V.hit_t[g] = hit ? T.best.t : CUDART_INF; V.hit_ref[g] = T.best.ref;
             hits += hit ? 1u : 0u;
@@ -1804,6 +1888,23 @@ __device__ __forceinline__ bool grid_blocked(const DevScene& S, D3 o, uint32_t l
     bool hit = false;
     const bool sorted = e - b <= kGridSortMax;                         // (longer lists are not sorted: lgb_grid.cu)
     const uint2* en = G->entries;
+    const uint2* lg = G->large;
+#if LGB_WALK_SPLIT
+    // positions [b, e) are the cell's list, [e, e2) the light's large list (both nearest first)
+    const uint32_t e2 = e + n_large;
+    for (uint32_t i = b;;) {
+        uint32_t cand = 0xFFFFFFFFu;
+        while (i < e2) {
+            const bool in_cell = i < e;
+            const uint2 r = __ldg(in_cell ? en + i : lg + (i - e));
+            i++;
+            if (__uint_as_float(r.y) > len_up) { if (!in_cell) i = e2; else if (sorted) i = e; continue; }
+            if (prim_filter<STATS>(S, f, T.best_tf, r.x >> 30, r.x & 0x3FFFFFFFu, lc)) { cand = r.x; break; }
+        }
+        if (cand == 0xFFFFFFFFu) break;
+        if (prim_exact<true, STATS>(S, world, ray, f, T, cand >> 30, cand & 0x3FFFFFFFu, 1.0, lc)) { hit = true; break; }
+    }
+#else
 #if LGB_WALK_PREFETCH
     uint2 nxt = b < e ? __ldg(en + b) : make_uint2(0u, 0u);
     for (uint32_t i = b; i < e && !hit; i++) {
@@ -1816,12 +1917,12 @@ __device__ __forceinline__ bool grid_blocked(const DevScene& S, D3 o, uint32_t l
         if (__uint_as_float(r.y) > len_up) { if (sorted) break; else continue; }
         hit = leaf_prims<true, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, 1.0, lc);
     }
-    const uint2* lg = G->large;
     for (uint32_t i = 0; i < n_large && !hit; i++) {
         const uint2 r = __ldg(lg + i);
         if (__uint_as_float(r.y) > len_up) break;
         hit = leaf_prims<true, STATS, false>(S, world, ray, f, T, r.x >> 30, 1u, r.x & 0x3FFFFFFFu, 1.0, lc);
     }
+#endif
     return hit;
 }
 
