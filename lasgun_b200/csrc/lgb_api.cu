@@ -20,7 +20,7 @@
 
 namespace lgb {
 constexpr int kRenderEvents = 7;
-cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev, int part, const SideStreams* side, KernelLog* klog);
+cudaError_t launch_render(const DevScene&, const DevCamera&, const DevShade&, const DevWork&, const DevOut&, const DevWave&, bool stats, bool all_shadows, int sms, cudaStream_t, cudaEvent_t* ev, int part, const SideStreams* side, KernelLog* klog, ShadeChunks* chunks = nullptr);
 bool render_fused(uint32_t spp);
 bool surface_fused(const DevScene&, const DevWork&, const DevOut&, bool all_shadows);
 bool setup_fused(const DevScene&, const DevWork&, const DevOut&, bool all_shadows);
@@ -70,6 +70,7 @@ struct lgb_ctx {
     std::string error;
     DevBuf aov_li, beam2;
     DevBuf radiance, film, counters, tiles, aov_id, aov_t, aov_occl, scratch, wave, wave_ctr, ties, beam;
+    DevBuf scene_copy;                     // the DevScene of the launches in flight, in global memory (DevScene::self, sync_scene_copy)
     // levels of the specular ray trees (Whitted recursion): radiance and spawn records of every level (kept until the fold back up),
     // the rays of the current and the next level, the wavefront buffers of the current level, per-level counters
     DevBuf lvl_rad[kMaxRecursion + 1], lvl_recs[kMaxRecursion + 1], raybuf[2], wave2, wave2_ctr, lvl_ctr;
@@ -104,6 +105,20 @@ struct lgb_ctx {
     // pinned bounce buffer of the film read-back into pageable memory (finish_host), and one event per chunk of it
     void* film_host = nullptr; size_t film_host_cap = 0;
     std::vector<cudaEvent_t> chunk_ev;
+    cudaStream_t copy_stream = nullptr;    // the film's slices travel here while the next slice is shaded (run_capture)
+    bool host_film_done = false;           // run_capture delivered the film to CaptureArgs::host_film itself
+    cudaError_t reserve_film_host(size_t bytes) {
+        if (film_host_cap >= bytes) return cudaSuccess;
+        if (film_host) cudaFreeHost(film_host);
+        film_host = nullptr; film_host_cap = 0;
+        cudaError_t e = cudaHostAlloc(&film_host, bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) film_host_cap = bytes;
+        return e;
+    }
+    cudaError_t reserve_chunk_events(size_t n) {
+        while (chunk_ev.size() < n) { cudaEvent_t e; if (cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) return rc; chunk_ev.push_back(e); }
+        return cudaSuccess;
+    }
 };
 
 struct lgb_scene {
@@ -187,6 +202,12 @@ int lgb_init(int device, lgb_ctx** out) {
     lgb_ctx* c = new lgb_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char* e = std::getenv("LGB_STACK_LIMIT")) {          // experiments: the per-thread local-memory size the driver lays the stacks out with
+        size_t before = 0; cudaDeviceGetLimit(&before, cudaLimitStackSize);
+        cudaDeviceSetLimit(cudaLimitStackSize, (size_t)std::atol(e));
+        size_t after = 0; cudaDeviceGetLimit(&after, cudaLimitStackSize);
+        std::fprintf(stderr, "[lgb_init] cudaLimitStackSize %zu -> %zu\n", before, after);
+    }
     if (const char* e = std::getenv("LGB_BEAMS")) { const int v = std::atoi(e); c->beams = v < 0 ? -1 : (v != 0); }
     if (const char* e = std::getenv("LGB_LIGHT_GRIDS")) { const int v = std::atoi(e); c->light_grids = v < 0 ? -1 : (v != 0); }
     if (const char* e = std::getenv("LGB_WAVE_BUDGET_MB")) { const long v = std::atol(e); if (v >= 1) c->wave_budget = (uint64_t)v << 20; }
@@ -333,7 +354,7 @@ void lgb_shutdown(lgb_ctx* c) {
     c->peers.clear();
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties, &c->beam, &c->raybuf[0], &c->raybuf[1], &c->wave2, &c->wave2_ctr, &c->lvl_ctr, &c->aov_li, &c->beam2}) b->release();
+    for (DevBuf* b : {&c->radiance, &c->film, &c->counters, &c->tiles, &c->aov_id, &c->aov_t, &c->aov_occl, &c->scratch, &c->wave, &c->wave_ctr, &c->ties, &c->beam, &c->raybuf[0], &c->raybuf[1], &c->wave2, &c->wave2_ctr, &c->lvl_ctr, &c->aov_li, &c->beam2, &c->scene_copy}) b->release();
     c->klog_snaps.release();
     for (int k = 0; k < c->klog.made; k++) { cudaEventDestroy(c->klog.ev0[k]); cudaEventDestroy(c->klog.ev1[k]); }
     for (DevBuf& b : c->lvl_rad) b.release();
@@ -341,6 +362,7 @@ void lgb_shutdown(lgb_ctx* c) {
     if (c->staging) cudaFreeHost(c->staging);
     if (c->film_host) cudaFreeHost(c->film_host);
     for (cudaEvent_t e : c->chunk_ev) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
     for (auto& e : c->phase) cudaEventDestroy(e);
     for (int k = 0; k < c->side.n; k++) { cudaStreamDestroy(c->side.s[k]); cudaEventDestroy(c->side.join[k]); }
@@ -995,15 +1017,21 @@ int lgb_scene_create(lgb_ctx* ctx, const lgb_scene_desc* d, lgb_scene** out) {
         char* H = (char*)ctx->staging; char* D = (char*)s->arena; char* T = (char*)scratch;
         auto gfail = [&](int code) { if (!s->deferred.scratch) cudaFreeAsync(scratch, ctx->stream); return bail(code); };
         Pool& pool = Pool::get();
+        // the caller's arrays go through the pinned buffer in chunks: while one chunk crosses PCIe the host threads stage the next
+        cudaError_t stage_err = cudaSuccess;
         auto stage = [&](size_t at, const void* src, size_t bytes) {
-            if (!bytes) return;
-            pool.for_range(bytes, 1 << 20, [&](size_t b, size_t e, size_t) { std::memcpy(H + st_raw + at + b, (const char*)src + b, e - b); });
+            constexpr size_t kChunk = 4u << 20;
+            for (size_t c0 = 0; c0 < bytes && stage_err == cudaSuccess; c0 += kChunk) {
+                const size_t len = std::min(kChunk, bytes - c0);
+                pool.for_range(len, 256u << 10, [&](size_t b, size_t e, size_t) { std::memcpy(H + st_raw + at + c0 + b, (const char*)src + c0 + b, e - b); });
+                stage_err = cudaMemcpyAsync(T + at + c0, H + st_raw + at + c0, len, cudaMemcpyHostToDevice, ctx->stream);
+            }
         };
         stage(r_sph, d->spheres, ns * sizeof(lgb_sphere)); stage(r_smat, d->sphere_material, ns * 4); stage(r_sid, d->sphere_id, ns * 4);
         stage(r_cub, d->cuboids, ncb * sizeof(lgb_cuboid)); stage(r_cmat, d->cuboid_material, ncb * 4); stage(r_cid, d->cuboid_id, ncb * 4);
         stage(r_tri, d->triangles, nt * sizeof(lgb_triangle)); stage(r_tmat, d->triangle_material, nt * 4); stage(r_tid, d->triangle_id, nt * 4);
         if (any_normals) { stage(r_nrm, d->tri_normals, nt * sizeof(lgb_tri_normals)); if (d->tri_has_normals) stage(r_has, d->tri_has_normals, nt); }
-        cudaError_t e = cudaMemcpyAsync(T, H + st_raw, raw_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        cudaError_t e = stage_err;
         if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaMemcpyAsync(H2D raw scene)"); return gfail(LGB_ERR_CUDA); }
         RawScene raw{};
         raw.spheres = (const lgb_sphere*)(T + r_sph); raw.sphere_material = (const uint32_t*)(T + r_smat); raw.sphere_id = (const uint32_t*)(T + r_sid); raw.n_spheres = (uint32_t)ns;
@@ -1314,6 +1342,16 @@ static int ensure_camgrid(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint
     return LGB_OK;
 }
 
+// DevScene::self: the scene record in global memory for the launches queued on `st` from here on (out-of-line device functions read
+// it there).  The source is pageable, so the record is taken before the call returns; whatever changes s->dev later -- rank tables,
+// a deferred BVH -- comes back through here before it launches anything.
+static int sync_scene_copy(lgb_ctx* c, lgb_scene* s, cudaStream_t st) {
+    CU(c, c->scene_copy.reserve(sizeof(DevScene)));
+    s->dev.self = (const DevScene*)c->scene_copy.p;
+    CU(c, cudaMemcpyAsync(c->scene_copy.p, &s->dev, sizeof(DevScene), cudaMemcpyHostToDevice, st));
+    return LGB_OK;
+}
+
 struct CaptureArgs {
     uint32_t w, h;
     uint32_t mode;               // 0 tiles, 1 stride subset
@@ -1323,6 +1361,7 @@ struct CaptureArgs {
     cudaStream_t stream;
     bool want_li = false;        // aov: also the radiance of every sample
     bool klog_no_camgrid = false;
+    void* host_film = nullptr;   // lgb_capture: the caller's film; where the frame allows it the read-back starts behind the first slice of the shade kernel
     KernelLog* klog = nullptr;   // lgb_capture_profile: events and counter snapshots around every launch (one stream)
 };
 
@@ -1518,6 +1557,17 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     uint64_t level_rays = 0; uint32_t level_launches = 0;
     float phase_ms[6] = {0, 0, 0, 0, 0, 0};
     int wf = 0;
+    // lgb_capture of a whole frame on one device, one band: the shade kernel runs in slices and the film's finished rows leave for the
+    // host behind each (the read-back of a 33 MB film costs 1.7 ms behind the frame, 0.5 ms behind its last slice)
+    c->host_film_done = false;
+    ShadeChunks chunk_rec{}; ShadeChunks* chunks = nullptr;
+    constexpr uint32_t kShadeSlices = 4;
+    if (a.host_film && a.mode == 0 && a.ranks == 1 && n_bands == 1 && !a.aov && !a.klog && !a.d_film && !S.general && area * 4 >= (8u << 20) && !std::getenv("LGB_NO_FILM_OVERLAP")) {
+        if (!c->copy_stream) CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CU(c, c->reserve_chunk_events(2 * kShadeSlices));
+        chunk_rec.want = kShadeSlices; chunk_rec.ev = c->chunk_ev.data();
+        chunks = &chunk_rec;
+    }
     for (uint64_t band = 0; band < n_bands; band++) {
         const uint64_t u0 = band * units_band, un = std::min<uint64_t>(units_band, units_all - u0);
         if (a.mode == 0) {
@@ -1548,6 +1598,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         if (s->lazy_fn && !s->dev.rank && total) {
             // no rank tables yet: trace the primary rays, and only if one met two primitives at bit-identical t fetch the
             // caller's reference tree, build the tables and re-trace those slots (lasgun_b200.h, "Lazy reference tree")
+            if (int rc = sync_scene_copy(c, s, st)) return rc;
             CU(c, launch_render(S, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 1, side, a.klog));
             uint32_t ties = 0;
             CU(c, cudaMemcpyAsync(&ties, V.tie_count, 4, cudaMemcpyDeviceToHost, st));
@@ -1571,11 +1622,14 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
                 if (ties <= V.tie_cap) { W2.slot_list = V.tie_list; W2.n_list = ties; }
                 else if (band == 0) CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));          // too many to list: the whole band again
                 (void)before;
+                if (int rc = sync_scene_copy(c, s, st)) return rc;
                 CU(c, launch_render(s->dev, s->cam, s->shade, W2, O, V, st_on, a.aov, c->sm_count, st, ties <= V.tie_cap ? nullptr : pev, 1, side, a.klog));
             }
-            CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 2 | wf, side, a.klog));
+            if (int rc = sync_scene_copy(c, s, st)) return rc;
+            CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 2 | wf, side, a.klog, chunks));
         } else {
-            CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 3 | wf, side, a.klog));
+            if (int rc = sync_scene_copy(c, s, st)) return rc;
+            CU(c, launch_render(s->dev, s->cam, s->shade, W, O, V, st_on, a.aov, c->sm_count, st, pev, 3 | wf, side, a.klog, chunks));
         }
         if (wf && total) {                     // materials beyond plastic: the levels of the specular ray trees, then the film
             if (S.specular && S.recursion > 0) if (int rc = run_whitted_levels(c, s, O, total, st, stats != nullptr, &level_rays, &level_launches)) return rc;
@@ -1592,6 +1646,25 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     CU(c, cudaEventRecord(c->ev1, st));
     if (!s->last_use) CU(c, cudaEventCreateWithFlags(&s->last_use, cudaEventDisableTiming));
     CU(c, cudaEventRecord(s->last_use, st));
+    uint32_t copy_rows[9] = {0};                 // film rows [copy_rows[k], copy_rows[k + 1]) leave behind slice k
+    bool copy_bounce = false;
+    if (chunks && chunks->launched) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, a.host_film) != cudaSuccess) { cudaGetLastError(); copy_bounce = true; }
+        else copy_bounce = at.type == cudaMemoryTypeUnregistered;
+        if (copy_bounce) CU(c, c->reserve_film_host(area * 4));
+        char* dst = copy_bounce ? (char*)c->film_host : (char*)a.host_film;
+        const uint64_t px_tile_row = (uint64_t)W.n_macro_x * kMacroTile * kMacroTile;
+        for (uint32_t k = 0; k < chunks->launched; k++) {
+            const uint64_t rows = k + 1 == chunks->launched ? a.h : std::min<uint64_t>(a.h, chunks->done_pixels[k] / px_tile_row * kMacroTile);
+            copy_rows[k + 1] = (uint32_t)std::max<uint64_t>(rows, copy_rows[k]);
+            CU(c, cudaStreamWaitEvent(c->copy_stream, chunks->ev[k], 0));
+            const size_t off = (size_t)copy_rows[k] * a.w * 4, len = (size_t)(copy_rows[k + 1] - copy_rows[k]) * a.w * 4;
+            if (len) CU(c, cudaMemcpyAsync(dst + off, (const char*)O.film + off, len, cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(c, cudaEventRecord(chunks->ev[kShadeSlices + k], c->copy_stream));
+        }
+        CU(c, cudaEventRecord(c->ev2, c->copy_stream));
+    }
     if (stats && sync_stats) {
         DevCounters hc;
         CU(c, cudaMemcpyAsync(&hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
@@ -1614,9 +1687,23 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         const uint32_t shade_launches = S.general ? (S.specular && S.recursion && !wf ? 3u : 2u) : (render_fused(W.spp) && !O.aov_li) ? 1u : 2u;
         const uint32_t setup_launches = (W.setup_in_primary || setup_fused(S, W, O, a.aov)) ? 0u : 1u;                                          // (inside k_gshadow otherwise)
         stats->kernel_launches = total_all ? level_launches + (uint32_t)n_bands * (primary_launches + (one_kernel ? 1u : setup_launches + shadow_launches + shade_launches)) : 0;
+        if (chunks && chunks->launched) stats->kernel_launches += chunks->launched - 1;
         stats->bands = (uint32_t)n_bands;
         float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         stats->render_ms = ms; stats->total_ms = ms;
+    }
+    if (chunks && chunks->launched) {
+        for (uint32_t k = 0; k < chunks->launched; k++) {
+            CU(c, cudaEventSynchronize(chunks->ev[kShadeSlices + k]));
+            const size_t off = (size_t)copy_rows[k] * a.w * 4, len = (size_t)(copy_rows[k + 1] - copy_rows[k]) * a.w * 4;
+            if (copy_bounce && len) {
+                const char* src = (const char*)c->film_host + off; char* out = (char*)a.host_film + off;
+                Pool::get().for_range(len, 256u << 10, [&](size_t b, size_t e, size_t) { std::memcpy(out + b, src + b, e - b); });
+            }
+        }
+        CU(c, cudaStreamSynchronize(st));           // (the slices' events are behind everything on st but the counters' copy)
+        if (stats && sync_stats) { float ms = 0.f; CU(c, cudaEventElapsedTime(&ms, c->ev0, c->ev2)); stats->total_ms = ms; }
+        c->host_film_done = true;
     }
     return LGB_OK;
 }
@@ -1692,14 +1779,10 @@ static int finish_host(lgb_ctx* c, const void* dev, void* host, size_t bytes, lg
         if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); bounce = false; }
         else bounce = at.type == cudaMemoryTypeUnregistered;
     }
-    if (bounce && c->film_host_cap < bytes) {
-        if (c->film_host) cudaFreeHost(c->film_host);
-        c->film_host = nullptr; c->film_host_cap = 0;
-        if (cudaHostAlloc(&c->film_host, bytes, cudaHostAllocDefault) == cudaSuccess) c->film_host_cap = bytes; else { cudaGetLastError(); bounce = false; }
-    }
+    if (bounce && c->reserve_film_host(bytes) != cudaSuccess) { cudaGetLastError(); bounce = false; }
     if (bounce) {
         const size_t n = (bytes + kChunk - 1) / kChunk;
-        while (c->chunk_ev.size() < n) { cudaEvent_t e; CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->chunk_ev.push_back(e); }
+        CU(c, c->reserve_chunk_events(n));
         for (size_t i = 0; i < n; i++) {
             const size_t off = i * kChunk, len = std::min(kChunk, bytes - off);
             CU(c, cudaMemcpyAsync((char*)c->film_host + off, (const char*)dev + off, len, cudaMemcpyDeviceToHost, c->stream));
@@ -1734,10 +1817,12 @@ int lgb_capture(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint8_t* rgba,
         rc = group_capture(c, s, w, h, c->film.p, stp);
     } else {
         CaptureArgs a{w, h, 0, 0, 1, 0, 0, false, nullptr, nullptr};
+        a.host_film = rgba;
         rc = run_capture(c, s, a, stp, true);
     }
     if (rc) return rc;
     if (stp->stack_overflow) return fail(c, LGB_ERR_UNSUPPORTED, "traversal stack overflow");
+    if (c->peers.empty() && c->host_film_done) return LGB_OK;         // the film left in slices behind the shade kernel's (run_capture)
     return finish_host(c, c->film.p, rgba, (size_t)w * h * 4, stp);
 }
 
@@ -1811,6 +1896,7 @@ int lgb_trace_rays(lgb_ctx* c, lgb_scene* s, const double* rays, uint64_t n, uin
     double* d_rays = (double*)base; double* d_t = (double*)(base + n * 48); double* d_ng = (double*)(base + n * 56); double* d_ns = (double*)(base + n * 80);
     uint32_t* d_id = (uint32_t*)(base + n * 104);
     CU(c, cudaMemcpyAsync(d_rays, rays, n * 48, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = sync_scene_copy(c, s, c->stream)) return rc;
     CU(c, launch_trace(s->dev, d_rays, n, d_id, d_t, d_ng, d_ns, c->stream));
     if (ids) CU(c, cudaMemcpyAsync(ids, d_id, n * 4, cudaMemcpyDeviceToHost, c->stream));
     if (ts) CU(c, cudaMemcpyAsync(ts, d_t, n * 8, cudaMemcpyDeviceToHost, c->stream));

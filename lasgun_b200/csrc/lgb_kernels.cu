@@ -23,11 +23,25 @@
 #ifndef LGB_WALK_PREFETCH
 #define LGB_WALK_PREFETCH 0          // grid walks (k_cprimary, k_gshadow): load entry i + 1 while entry i is tested
 #endif
+#ifndef LGB_CP_STAGE
+#define LGB_CP_STAGE 1               // k_cprimary: a warp whose lanes share a tile stages the list's first 32 entries + filter records in shared memory (needs LGB_WALK_SPLIT)
+#endif
+#ifndef LGB_WAVE_STREAM
+#define LGB_WAVE_STREAM 1            // wavefront entries (6 GB per mixed4k frame, each written once and read once) are stored / loaded with the streaming
+#endif                               // hint (st.global.cs / ld.global.cs: evict-first in L2), so they do not push the scene and the grids (~100-160 MB) out of the 126 MB L2
 #ifndef LGB_WALK_SPLIT
 #define LGB_WALK_SPLIT 1             // grid walks: filters run down the list until one passes, then the warp meets for the exact test (prim_filter / prim_exact)
 #endif
 
 namespace lgb {
+
+#if LGB_WAVE_STREAM
+template <class T> __device__ __forceinline__ void wst(T* p, T v) { __stcs(p, v); }
+template <class T> __device__ __forceinline__ T wld(const T* p) { return __ldcs(p); }
+#else
+template <class T> __device__ __forceinline__ void wst(T* p, T v) { *p = v; }
+template <class T> __device__ __forceinline__ T wld(const T* p) { return *p; }
+#endif
 
 // ------------------------------------------------------------------ per-ray f32 state
 struct RayF {
@@ -124,13 +138,15 @@ __device__ __forceinline__ Ray64 ray_into(const DevSpace& sp, const Ray64& r) {
     return o;
 }
 // The world ray taken down the chain of transforms to `space`, level by level as the reference does (bvh.rs:462).
-__device__ __noinline__ Ray64 ray_to_space(const DevScene& S, uint32_t space, const Ray64& world) {
+// (Out of line, so it takes the space table by value: see DevScene::self.)
+__device__ __noinline__ Ray64 ray_to_space(const DevSpace* spaces, uint32_t space, const Ray64& world) {
     uint32_t chain[kMaxSpaceDepth]; int n = 0;
-    for (uint32_t s = space; s != kNoParent; s = S.spaces[s].parent) chain[n++] = s;
+    for (uint32_t s = space; s != kNoParent; s = spaces[s].parent) chain[n++] = s;
     Ray64 r = world;
-    while (n--) { const DevSpace& sp = S.spaces[chain[n]]; if (!(sp.flags & kSpaceIdentity)) r = ray_into(sp, r); }
+    while (n--) { const DevSpace& sp = spaces[chain[n]]; if (!(sp.flags & kSpaceIdentity)) r = ray_into(sp, r); }
     return r;
 }
+__device__ __forceinline__ Ray64 ray_to_space(const DevScene& S, uint32_t space, const Ray64& world) { return ray_to_space(S.spaces, space, world); }
 __device__ __forceinline__ uint32_t space_of(const DevScene& S, uint32_t ref) {
     const uint32_t type = ref >> 30, idx = ref & 0x3FFFFFFFu;
     return type == LGB_PRIM_SPHERE ? S.sph_space[idx] : type == LGB_PRIM_CUBOID ? S.cub_space[idx] : S.tri_space[idx];
@@ -140,7 +156,8 @@ __device__ __forceinline__ unsigned octant_of(const Ray64& r) {                 
 }
 // Exact-t tie between two primitives of an instanced scene: both are lifted to their deepest common space (a nested
 // level stands for everything below it) and compared by that level's test order for the ray's octant THERE.
-__device__ __noinline__ bool rank_before_instanced(const DevScene& S, const Ray64& world, uint32_t ref_a, uint32_t ref_b) {
+__device__ __noinline__ bool rank_before_instanced(const DevScene* Sg, const Ray64& world, uint32_t ref_a, uint32_t ref_b) {
+    const DevScene& S = *Sg;              // the record in global memory (DevScene::self)
     uint32_t ia = canonical_id(S, ref_a), sa = space_of(S, ref_a), ib = canonical_id(S, ref_b), sb = space_of(S, ref_b);
     uint32_t da = S.spaces[sa].depth, db = S.spaces[sb].depth;
     while (da > db) { ia = S.prim_count + sa; sa = S.spaces[sa].parent; da--; }
@@ -160,7 +177,7 @@ __device__ __forceinline__ bool accepts(const DevScene& S, const RayF& f, const 
     if (t < best.t) return true;
     if (t == best.t && best.ref != LGB_MISS && best.ref != ref) {
         if (!S.rank) { tied = 1u; return false; }
-        if (INST) return rank_before_instanced(S, world, ref, best.ref);
+        if (INST) return rank_before_instanced(S.self, world, ref, best.ref);
         const uint32_t* r = S.rank + (size_t)f.oct * S.rank_items;
         return r[canonical_id(S, ref)] < r[canonical_id(S, best.ref)];
     }
@@ -331,10 +348,11 @@ __device__ __forceinline__ bool leaf_prims(const DevScene& S, const Ray64& world
 // The two halves of leaf_prims for ONE primitive, for the grid walks (k_cprimary, k_gshadow; LGB_WALK_SPLIT): a lane first runs
 // filters down its list until one passes, then the warp meets for the exact f64 test.  In the fused form a warp ran the exact test
 // -- by far the longest stretch of the loop body -- in nearly every iteration for whichever lanes happened to pass in that one.
+// the filter of one primitive given its f32 record (sphere: q0 = {c, r}; cuboid: q0, q1 = padded lo, hi; triangle: q0..q2 = vertices)
 template <bool STATS>
-__device__ __forceinline__ bool prim_filter(const DevScene& S, const RayF& f, float best_tf, uint32_t type, uint32_t idx, LocalCounters& lc) {
+__device__ __forceinline__ bool prim_filter_rec(const RayF& f, float best_tf, uint32_t type, const float4 q0, const float4 q1, const float4 q2, LocalCounters& lc) {
     if (type == LGB_PRIM_SPHERE) {
-        const float4 s = __ldg(&S.sph32[idx]);
+        const float4 s = q0;
         if (STATS) lc.filter[0]++;
         const float lx = s.x - f.ox, ly = s.y - f.oy, lz = s.z - f.oz;
         const float bq = lx * f.dx + ly * f.dy + lz * f.dz;
@@ -350,15 +368,23 @@ __device__ __forceinline__ bool prim_filter(const DevScene& S, const RayF& f, fl
         return true;
     }
     if (type == LGB_PRIM_TRIANGLE) {
-        const float4* tp = S.tri + 3 * (size_t)idx;
-        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
         if (STATS) lc.filter[2]++;
         return f.kz == 0 ? tri_filter<0>(q0, q1, q2, f, best_tf) : f.kz == 1 ? tri_filter<1>(q0, q1, q2, f, best_tf) : tri_filter<2>(q0, q1, q2, f, best_tf);
     }
-    const float4 lo = __ldg(&S.cub32[2 * idx]), hi = __ldg(&S.cub32[2 * idx + 1]);
     if (STATS) lc.filter[1]++;
     float tn;
-    return slab2(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, f, CUDART_INF_F, tn);
+    return slab2(q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, f, CUDART_INF_F, tn);
+}
+__device__ __forceinline__ void prim_record(const DevScene& S, uint32_t type, uint32_t idx, float4& q0, float4& q1, float4& q2) {
+    if (type == LGB_PRIM_SPHERE) q0 = __ldg(&S.sph32[idx]);
+    else if (type == LGB_PRIM_TRIANGLE) { const float4* tp = S.tri + 3 * (size_t)idx; q0 = __ldg(tp); q1 = __ldg(tp + 1); q2 = __ldg(tp + 2); }
+    else { q0 = __ldg(&S.cub32[2 * idx]); q1 = __ldg(&S.cub32[2 * idx + 1]); }
+}
+template <bool STATS>
+__device__ __forceinline__ bool prim_filter(const DevScene& S, const RayF& f, float best_tf, uint32_t type, uint32_t idx, LocalCounters& lc) {
+    float4 q0, q1 = make_float4(0.f, 0.f, 0.f, 0.f), q2 = q1;
+    prim_record(S, type, idx, q0, q1, q2);
+    return prim_filter_rec<STATS>(f, best_tf, type, q0, q1, q2, lc);
 }
 template <bool ANYHIT, bool STATS>
 __device__ __forceinline__ bool prim_exact(const DevScene& S, const Ray64& world, const Ray64& ray, const RayF& f, Trav& T, uint32_t type, uint32_t idx, double tmax,
@@ -539,9 +565,9 @@ __device__ void surface_of(const DevScene& S, const Ray64& ray, uint32_t ref, do
 
 // The local record taken back to world space, level by level from the innermost space outwards:
 // transform_ray_intersection (transform.rs:243-264) then swap_backface (surface.rs:88-99, bvh.rs:510-518).
-__device__ __noinline__ void record_to_world(const DevScene& S, uint32_t space, Surf& sf) {
-    for (uint32_t s = space; s != kNoParent; s = S.spaces[s].parent) {
-        const DevSpace& sp = S.spaces[s];
+__device__ __noinline__ void record_to_world(const DevSpace* spaces, uint32_t space, Surf& sf) {
+    for (uint32_t s = space; s != kNoParent; s = spaces[s].parent) {
+        const DevSpace& sp = spaces[s];
         if (!(sp.flags & kSpaceIdentity)) {
             const bool shading_differs = sf.g_dpdu.x != sf.s_dpdu.x || sf.g_dpdu.y != sf.s_dpdu.y || sf.g_dpdu.z != sf.s_dpdu.z ||
                                          sf.g_dpdv.x != sf.s_dpdv.x || sf.g_dpdv.y != sf.s_dpdv.y || sf.g_dpdv.z != sf.s_dpdv.z;
@@ -774,7 +800,7 @@ __device__ __forceinline__ void shade_point(const DevScene& S, const Ray64& ray,
         const uint32_t space = space_of(S, ref);
         const Ray64 local = ray_to_space(S, space, ray);
         surface_of(S, local, ref, t_again, sf);
-        record_to_world(S, space, sf);
+        record_to_world(S.spaces, space, sf);
     } else surface_of(S, ray, ref, t_again, sf);
     id = sf.id;
     P.mat = sf.material;
@@ -1439,6 +1465,19 @@ __device__ __noinline__ void setup_generic(const DevScene& S, const Ray64& ray, 
     shade_point<false, false>(S, ray, t, ref, P, id);
     ps = P.ps; ng = P.ng; wo_ng = dot(P.wo, P.ng);
 }
+// The same for k_cprimary<SETUP>, written so that nothing of the kernel's own state has its address taken: the scene record is read
+// from global memory (DevScene::self), the ray goes by value, the results go straight to the slot's wavefront entries.  With
+// `const DevScene& S` bound to the kernel's parameter block every thread copied the 350-byte record to its stack at entry (28 STL.64
+// per thread: 30 GB of local stores per mixed4k frame, through L1 into L2), and the ray after it -- for a call one slot in a million makes.
+__device__ __noinline__ void setup_generic_slot(const DevScene* Sg, double ox, double oy, double oz, double dx, double dy, double dz, double t, uint32_t ref,
+                                                double* ps_out, uint32_t* gate_out) {
+    const DevScene& S = *Sg;
+    Ray64 ray; ray.o = d3(ox, oy, oz); ray.d = d3(dx, dy, dz);
+    ShadePoint P; uint32_t id;
+    shade_point<false, false>(S, ray, t, ref, P, id);
+    ps_out[0] = P.ps.x; ps_out[1] = P.ps.y; ps_out[2] = P.ps.z;
+    *gate_out = light_gates(S, ray, P.ps, P.ng, dot(P.wo, P.ng), false);
+}
 // ================================================================== primary rays through the camera grid (lgb_grid.cu)
 // One thread per sample slot: the pixel's tile lists every primitive one of its samples can see, nearest first; each gets the f32
 // filter + the reference's exact test (closest hit, reference-order ties as everywhere), and the walk stops at the first entry that
@@ -1459,17 +1498,53 @@ __global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, LGB_CPRIMARY_BLOCKS) k_c
     const unsigned lane = threadIdx.x & 31u;
     LocalCounters lc = {};
     unsigned int hits = 0, primary = 0;
+    bool valid = false;
+    uint32_t x = 0, y = 0, s = 0;
     if (g < total) {
-        const uint32_t p = fdiv((uint32_t)g, W.fd_spp), s = (uint32_t)g - p * W.spp;
-        uint32_t x, y;
-        if (!slot_to_pixel(W, p, x, y)) { V.hit_t[g] = CUDART_INF; V.hit_ref[g] = kSlotUnused; }
-        else {
+        const uint32_t p = fdiv((uint32_t)g, W.fd_spp);
+        s = (uint32_t)g - p * W.spp;
+        if (!slot_to_pixel(W, p, x, y)) { wst(&V.hit_t[g], (double)(CUDART_INF)); wst(&V.hit_ref[g], (uint32_t)(kSlotUnused)); }
+        else valid = true;
+    }
+    const size_t cell = (size_t)(y >> W.cg_shift) * W.cg_nx + (size_t)(x >> W.cg_shift);
+    uint32_t b = 0, e = 0;
+    if (valid) { b = __ldg(W.cg_start + cell); e = __ldg(W.cg_start + cell + 1); }
+#if LGB_CP_STAGE
+    // A warp holds the samples of 32 / spp neighbouring pixels, so at >= 8 spp all its lanes walk the SAME tile's list.  Then the lanes
+    // fetch its first 32 entries and their f32 filter records side by side, one entry each, into the warp's slab of shared memory, and
+    // the walk reads them from there: the dependent chain list -> entry -> record (two L1 / L2 round trips per entry and lane) becomes
+    // one parallel fetch per warp.  Warps whose lanes disagree (1 spp: 32 pixels, two tiles) walk from global memory as before.
+    constexpr uint32_t kStage = 32;
+    __shared__ uint2 s_ent[LGB_CPRIMARY_THREADS / 32][kStage];
+    __shared__ float4 s_rec[LGB_CPRIMARY_THREADS / 32][kStage][3];
+    const unsigned wid = threadIdx.x >> 5;
+    uint32_t ns = 0;
+    {
+        const unsigned vmask = __ballot_sync(0xFFFFFFFFu, valid);
+        if (vmask) {
+            const int lead = __ffs(vmask) - 1;
+            const unsigned long long cell0 = __shfl_sync(0xFFFFFFFFu, (unsigned long long)cell, lead);
+            const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, b, lead), e0 = __shfl_sync(0xFFFFFFFFu, e, lead);
+            if (__all_sync(0xFFFFFFFFu, !valid || (unsigned long long)cell == cell0)) {
+                ns = min(e0 - b0, kStage);
+                if (lane < ns) {
+                    const uint2 r = __ldg(W.cg_entries + b0 + lane);
+                    float4 q0, q1 = make_float4(0.f, 0.f, 0.f, 0.f), q2 = q1;
+                    prim_record(S, r.x >> 30, r.x & 0x3FFFFFFFu, q0, q1, q2);
+                    s_ent[wid][lane] = r;
+                    s_rec[wid][lane][0] = q0; s_rec[wid][lane][1] = q1; s_rec[wid][lane][2] = q2;
+                }
+                __syncwarp();
+            }
+        }
+    }
+#endif
+    if (valid) {
+        {
             const Ray64 world = camera_ray(C, W, x, y, s);
             Ray64 ray; RayF f; Trav T;
             enter_root<false>(S, world, ray, f, T, CUDART_INF);
             primary++;
-            const size_t cell = (size_t)(y >> W.cg_shift) * W.cg_nx + (size_t)(x >> W.cg_shift);
-            const uint32_t b = __ldg(W.cg_start + cell), e = __ldg(W.cg_start + cell + 1);
             const float to_t = f.inv_len * (1.0f - 2e-6f);                   // an entry's distance from the eye -> a lower bound of its ray parameter
             const bool sorted = e - b <= kGridSortMax;                       // (longer lists are not sorted: lgb_grid.cu)
 #if LGB_WALK_SPLIT
@@ -1479,10 +1554,23 @@ __global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, LGB_CPRIMARY_BLOCKS) k_c
                 uint32_t cand = 0xFFFFFFFFu;
                 while (i < e2) {
                     const bool in_cell = i < e;
+#if LGB_CP_STAGE
+                    const uint32_t k = i - b;
+                    const bool staged = k < ns;
+                    const uint2 r = staged ? s_ent[wid][k] : __ldg(in_cell ? W.cg_entries + i : W.cg_large + (i - e));
+                    i++;
+                    if (__uint_as_float(r.y) * to_t > T.best_up) { if (!in_cell) i = e2; else if (sorted) i = e; continue; }    // nearest first: nothing behind the best hit can beat it
+                    const uint32_t type = r.x >> 30;
+                    float4 q0, q1 = make_float4(0.f, 0.f, 0.f, 0.f), q2 = q1;
+                    if (staged) { q0 = s_rec[wid][k][0]; if (type != LGB_PRIM_SPHERE) { q1 = s_rec[wid][k][1]; q2 = s_rec[wid][k][2]; } }
+                    else prim_record(S, type, r.x & 0x3FFFFFFFu, q0, q1, q2);
+                    if (prim_filter_rec<STATS>(f, T.best_tf, type, q0, q1, q2, lc)) { cand = r.x; break; }
+#else
                     const uint2 r = __ldg(in_cell ? W.cg_entries + i : W.cg_large + (i - e));
                     i++;
                     if (__uint_as_float(r.y) * to_t > T.best_up) { if (!in_cell) i = e2; else if (sorted) i = e; continue; }    // nearest first: nothing behind the best hit can beat it
                     if (prim_filter<STATS>(S, f, T.best_tf, r.x >> 30, r.x & 0x3FFFFFFFu, lc)) { cand = r.x; break; }
+#endif
                 }
                 if (cand == 0xFFFFFFFFu) break;
                 prim_exact<false, STATS>(S, world, ray, f, T, cand >> 30, cand & 0x3FFFFFFFu, CUDART_INF, lc);
@@ -1507,25 +1595,24 @@ __global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, LGB_CPRIMARY_BLOCKS) k_c
             }
 #endif
             const bool hit = T.best.ref != LGB_MISS;
-            V.hit_t[g] = hit ? T.best.t : CUDART_INF; V.hit_ref[g] = T.best.ref;
+            wst(&V.hit_t[g], (double)(hit ? T.best.t : CUDART_INF)); wst(&V.hit_ref[g], (uint32_t)(T.best.ref));
             hits += hit ? 1u : 0u;
             if (T.tied) { const uint32_t k = atomicAdd(V.tie_count, 1u); if (k < V.tie_cap) V.tie_list[k] = (uint32_t)g; }
             if (SETUP && hit) {
                 const uint32_t ref = T.best.ref; const double t = T.best.t;
-                if (S.specular && (material_flags(S, ref) & kMatSpecular)) { V.occl[g] = 0; V.gate[g] = 0; }     // glass, mirror: BSDF::f is zero (bxdf/mod.rs:172)
+                if (S.specular && (material_flags(S, ref) & kMatSpecular)) { wst(&V.occl[g], (uint32_t)(0)); wst(&V.gate[g], (uint32_t)(0)); }     // glass, mirror: BSDF::f is zero (bxdf/mod.rs:172)
                 else {
                     LeanSurf Ls;
                     lean_surface<true>(S, world, t, ref, 0u, Ls);
-                    D3 ng, ps; double wo_ng = 1.0;
-                    if (Ls.flags & kSfGeneric) setup_generic(S, world, t, ref, ps, ng, wo_ng);
+                    if (Ls.flags & kSfGeneric) setup_generic_slot(S.self, world.o.x, world.o.y, world.o.z, world.d.x, world.d.y, world.d.z, t, ref, V.ps + 3 * g, V.gate + g);
                     else {
-                        ng = (Ls.flags & kSfNgFlip) ? -Ls.n : Ls.n;
-                        ps = world.o + world.d * t + ng * (2.220446049250313e-16 * 65536.0);       // surface.rs:168, integrate.rs:40
+                        const D3 ng = (Ls.flags & kSfNgFlip) ? -Ls.n : Ls.n;
+                        const D3 ps = world.o + world.d * t + ng * (2.220446049250313e-16 * 65536.0);       // surface.rs:168, integrate.rs:40
+                        wst(&V.ps[3 * g + 0], ps.x); wst(&V.ps[3 * g + 1], ps.y); wst(&V.ps[3 * g + 2], ps.z);
+                        wst(&V.gate[g], (uint32_t)(light_gates(S, world, ps, ng, 1.0, true)));
                     }
-                    V.ps[3 * g + 0] = ps.x; V.ps[3 * g + 1] = ps.y; V.ps[3 * g + 2] = ps.z;
-                    V.gate[g] = light_gates(S, world, ps, ng, wo_ng, !(Ls.flags & kSfGeneric));
-                    V.sflags[g] = (unsigned char)Ls.flags;
-                    V.occl[g] = 0;
+                    wst(&V.sflags[g], (unsigned char)((unsigned char)Ls.flags));
+                    wst(&V.occl[g], (uint32_t)(0));
                 }
             }
         }
@@ -1936,7 +2023,7 @@ __global__ void __launch_bounds__(256, LGB_GSHADOW_MIN_BLOCKS) k_gshadow(DevScen
     LocalCounters lc = {};
     unsigned traced = 0, occluded = 0;
     if (g < total) {
-        const uint32_t ref = V.hit_ref[g];
+        const uint32_t ref = wld(&V.hit_ref[g]);
         uint32_t mask = 0;
         D3 ps = d3(0, 0, 0);
         if (SETUP) {
@@ -1961,8 +2048,8 @@ __global__ void __launch_bounds__(256, LGB_GSHADOW_MIN_BLOCKS) k_gshadow(DevScen
         } else {
             // gate and shadow origin are requested together with the hit word, not one after the other (three dependent round trips
             // were 18 % of this kernel's stall samples); for a miss they hold stale values nobody looks at
-            const uint32_t gate = ALL_SHADOWS ? (S.n_lights >= 32u ? 0xFFFFFFFFu : (1u << S.n_lights) - 1u) : V.gate[g];
-            ps = d3(V.ps[3 * g], V.ps[3 * g + 1], V.ps[3 * g + 2]);
+            const uint32_t gate = ALL_SHADOWS ? (S.n_lights >= 32u ? 0xFFFFFFFFu : (1u << S.n_lights) - 1u) : wld(&V.gate[g]);
+            ps = d3(wld(&V.ps[3 * g]), wld(&V.ps[3 * g + 1]), wld(&V.ps[3 * g + 2]));
             if (ref != LGB_MISS && ref != kSlotUnused) mask = gate;
         }
         if (mask) {
@@ -1972,7 +2059,7 @@ __global__ void __launch_bounds__(256, LGB_GSHADOW_MIN_BLOCKS) k_gshadow(DevScen
                 traced++;
                 if (grid_blocked<STATS>(S, ps, l, lc)) { occl |= 1u << l; occluded++; }
             }
-            V.occl[g] = occl;
+            wst(&V.occl[g], occl);
         }
     }
     if (O.counters) {
@@ -2347,7 +2434,7 @@ __global__ void __launch_bounds__(256, LGB_LEAN_MIN_BLOCKS) k_shade_lean(DevScen
     if constexpr (FUSED) {
         const uint32_t tp = fdiv(threadIdx.x, W.fd_spp);
         s = threadIdx.x - tp * W.spp;
-        const uint64_t p = (uint64_t)blockIdx.x * ppb + tp;
+        const uint64_t p = ((uint64_t)blockIdx.x + W.block_off) * ppb + tp;
         mine = tp < ppb && p < W.n_pixels;
         p32 = (uint32_t)p;
         g = p * W.spp + s;
@@ -2362,9 +2449,9 @@ __global__ void __launch_bounds__(256, LGB_LEAN_MIN_BLOCKS) k_shade_lean(DevScen
     uint32_t x = 0, y = 0;
     if (mine) {
         // everything the slot needs from the wave, requested at once (the loads are independent; their latency is this kernel's main stall)
-        const uint32_t ref = V.hit_ref[g];
-        const double t = V.hit_t[g];
-        const uint32_t occl = V.occl[g], gate = V.gate[g], sflags = V.sflags[g];
+        const uint32_t ref = wld(&V.hit_ref[g]);
+        const double t = wld(&V.hit_t[g]);
+        const uint32_t occl = wld(&V.occl[g]), gate = wld(&V.gate[g]), sflags = wld(&V.sflags[g]);
         if (ref != kSlotUnused && slot_to_pixel(W, p32, x, y)) {
             const Ray64 ray = camera_ray(C, W, x, y, s);
             have = true;
@@ -2407,7 +2494,7 @@ __global__ void __launch_bounds__(256, LGB_LEAN_MIN_BLOCKS) k_shade_lean(DevScen
     }
     __syncthreads();
     if (threadIdx.x < ppb && valid[threadIdx.x * W.spp]) {
-        const uint64_t p = (uint64_t)blockIdx.x * ppb + threadIdx.x;
+        const uint64_t p = ((uint64_t)blockIdx.x + W.block_off) * ppb + threadIdx.x;
         uint32_t px, py;
         slot_to_pixel(W, p, px, py);
         uchar4 o; o.x = bytes[3 * threadIdx.x]; o.y = bytes[3 * threadIdx.x + 1]; o.z = bytes[3 * threadIdx.x + 2]; o.w = 255;
@@ -2671,7 +2758,7 @@ __global__ void __launch_bounds__(128) k_trace(DevScene S, const double* rays, u
         if (INST) {
             const uint32_t space = space_of(S, h.ref);
             surface_of(S, ray_to_space(S, space, ray), h.ref, t, sf);
-            record_to_world(S, space, sf);
+            record_to_world(S.spaces, space, sf);
         } else surface_of(S, ray, h.ref, t, sf);
         id = sf.id;
         ng = normalize(cross(sf.g_dpdu, sf.g_dpdv));
@@ -2784,7 +2871,8 @@ bool surface_fused(const DevScene& S, const DevWork& W, const DevOut& O, bool al
 #define KL(nm, light, st, ...) do { if (klog) klog->begin(nm, light, st); __VA_ARGS__; if (klog) klog->end(st, O.counters); } while (0)
 cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade& sh, const DevWork& W, const DevOut& O,
                           const DevWave& V, bool stats, bool all_shadows, int sms, cudaStream_t stream, cudaEvent_t* ev, int part, const SideStreams* side,
-                          KernelLog* klog) {
+                          KernelLog* klog, ShadeChunks* chunks) {
+    if (chunks) chunks->launched = 0;
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], stream); };
 #if LGB_SMEM_STACK
     {   // the shared-memory stack variant needs more than the default 48 KB of dynamic shared memory (per device: cheap, idempotent)
@@ -2905,6 +2993,18 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     } else if (render_fused(W.spp) && !O.aov_li) {   // whole pixels per block: shade and resolve in one kernel, no radiance buffer
         const unsigned ft = W.spp <= LGB_FUSED_THREADS ? LGB_FUSED_THREADS : 256u;        // threads per block: whole pixels, as few of them as the option allows
         const unsigned fb = (unsigned)((W.n_pixels + (ft / W.spp) - 1) / (ft / W.spp));
+        if (chunks && chunks->want > 1 && !inst && !klog && fb >= 64u * chunks->want) {
+            // slices of consecutive blocks = consecutive pixel slots = (single-rank tile lists are row-major) consecutive rows of macro tiles
+            const unsigned K = std::min<unsigned>(chunks->want, 8u), ppb = ft / W.spp;
+            for (unsigned k = 0; k < K; k++) {
+                const unsigned b0 = (unsigned)((uint64_t)fb * k / K), b1 = (unsigned)((uint64_t)fb * (k + 1) / K);
+                DevWork Wk = W; Wk.block_off = b0;
+                k_shade_lean<true><<<b1 - b0, ft, 0, stream>>>(S, C, sh, Wk, O, V);
+                cudaEventRecord(chunks->ev[k], stream);
+                chunks->done_pixels[k] = std::min<uint64_t>((uint64_t)b1 * ppb, W.n_pixels);
+            }
+            chunks->launched = K;
+        } else
         KL(inst ? "k_shade(+film)" : "k_shade_lean(+film)", -1, stream, if (inst) k_shade<true, true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V); else k_shade_lean<true><<<fb, ft, 0, stream>>>(S, C, sh, W, O, V));
         mark(5);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;

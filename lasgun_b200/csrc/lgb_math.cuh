@@ -67,6 +67,11 @@ __device__ __forceinline__ bool sphere_exact(D3 c, double rad, const Ray64& ray,
         if (b == 0.0) return false;
         t = -cc / b;
     } else {
+        // Origin outside the sphere and moving away from it (cc > 0, b > 0): whatever the discriminant, q = -(b + sqrt) / 2 < 0, so
+        // r0 = q / a < 0 and r1 = cc / q < 0, t = max(r0, r1) < 0 and the reference returns None.  Decided on the reference's own b and
+        // cc, bit for bit; the bounds keep every quotient clear of underflow to -0.0 (which would pass `t < 0.0`).  This is the test every
+        // shadow ray leaving a sphere runs against its own sphere: it now ends before the square root and the two divisions.
+        if (cc > 1e-200 && b > 1e-100 && b < 1e100 && a < 1e100) return false;
         double disc = b * b - 4.0 * a * cc;
         if (disc < 0.0) return false;
         double sg = copysign(1.0, b);

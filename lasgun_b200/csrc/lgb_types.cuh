@@ -86,6 +86,10 @@ struct DevScene {
     uint32_t specular;    // some material carries flag bit3: k_secondary follows the specular rays
     uint32_t recursion;   // scene.recursion (scene.rs:60), depth limit of integrate.rs:69
     float err_abs;        // absolute coordinate error bound of an f32 ray against this scene (see lgb_api.cu)
+    // This record once more, in global memory (uploaded before every launch sequence, lgb_api.cu): what an out-of-line device function
+    // reads.  A `const DevScene&` bound to the kernel's parameter block has its address taken, and then every thread copies the whole
+    // record to its stack at entry (28 STL.64) whether or not it ever makes the call.
+    const DevScene* self;
 };
 
 struct DevCamera {
@@ -135,6 +139,7 @@ struct DevWork {
     const double* rays;              // mode 3: origin + direction, 6 doubles per slot
     uint32_t depth;                  // mode 3: depth of these rays in integrate.rs:23's recursion (camera rays: 0)
     uint32_t hole_lo, hole_hi;       // mode 3: slots [hole_lo, hole_hi) hold no ray (reflected rays fill the level's slots from 0, transmitted ones from hole_hi)
+    uint32_t block_off;              // k_shade_lean<FUSED> launched in chunks (ShadeChunks): blockIdx.x + block_off is the block's place in the whole launch
 };
 
 
@@ -182,6 +187,9 @@ struct KernelLog {
     }
 };
 
+// The fused shade + film kernel launched as `want` consecutive slices, an event behind each: lgb_capture starts the film's trip to
+// the host behind the first slice instead of behind the frame (launch_render fills launched / done_pixels; host-side only).
+struct ShadeChunks { uint32_t want; cudaEvent_t* ev; uint32_t launched; uint64_t done_pixels[8]; };
 // Side streams for the per-light shadow chains (launch_render); host-side only.
 struct SideStreams { cudaStream_t s[3]; cudaEvent_t fork, join[3]; int n; };
 

@@ -18,8 +18,18 @@ def show(tag, dev, film):
     print(f"{tag:34s}", " ".join(f"{x['name']} {x['ms']:.2f}" for x in best), flush=True)
 
 
-film = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
-if "first_on_tstream" in steps:            # the bench's first capture (camera grid build, wave buffers) runs on a torch stream
+if "scene_first" in steps:                 # as profile_kernels.py: the scene is created before torch allocates anything
+    dev = N.DeviceScene(ctx, N.FlatScene(sc))
+    film = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        dev.capture_device(w, h, film.data_ptr(), want_stats=True)
+    show("scene first, then the film", dev, film)
+    steps = [x for x in steps if x not in ("plain", "first_on_tstream")] + ["skip"]
+else:
+    film = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+if "skip" in steps:
+    pass
+elif "first_on_tstream" in steps:            # the bench's first capture (camera grid build, wave buffers) runs on a torch stream
     ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
     hs = N.HostScene(sc); flat = N.FlatScene(hs)
     dev = N.DeviceScene(ctx, flat)

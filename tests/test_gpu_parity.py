@@ -608,6 +608,37 @@ def test_tile_ranks_partition_the_film(native, gpu_ctx):
     dev.destroy()
 
 
+@pytest.mark.parametrize("spp_root", [1, 3])
+def test_capture_readback_in_slices(native, gpu_ctx, monkeypatch, spp_root):
+    """lgb_capture of a film of >= 8 MB: the shade kernel runs in slices and the finished rows travel to the host behind each
+    (run_capture), through a pinned bounce buffer when the caller's film is pageable.  The film must be the one the device holds,
+    byte for byte -- pageable and pinned destination, a height that is no multiple of the 32-row macro tiles, 1 and 9 spp (9: a
+    block's pixels do not divide a macro tile) -- and the one the unsliced read-back (LGB_NO_FILM_OVERLAP) delivers."""
+    import torch
+    w, h = 2048, 1100
+    sc, _ = scenes.mixed4k(mesh_n=48, nspheres=3000, res=(w, h), supersampling=spp_root)
+    dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+    film = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    dev.capture_device(w, h, film.data_ptr(), want_stats=True)
+    want = film.cpu().numpy()
+    pageable = np.full((h, w, 4), 7, np.uint8)
+    _, st = dev.capture(w, h, out=pageable)
+    assert np.array_equal(pageable, want)
+    assert st["kernel_launches"] >= 4            # the slices are launches of their own
+    pinned = torch.full((h, w, 4), 9, dtype=torch.uint8).pin_memory()
+    dev.capture(w, h, out=pinned.numpy())
+    assert np.array_equal(pinned.numpy(), want)
+    monkeypatch.setenv("LGB_NO_FILM_OVERLAP", "1")
+    plain = np.full((h, w, 4), 5, np.uint8)
+    dev.capture(w, h, out=plain)
+    assert np.array_equal(plain, want)
+    monkeypatch.setenv("LGB_NO_FILM_BOUNCE", "1")
+    plain2 = np.full((h, w, 4), 3, np.uint8)
+    dev.capture(w, h, out=plain2)
+    assert np.array_equal(plain2, want)
+    dev.destroy()
+
+
 def test_public_api_capture(native, oracle, gpu_ctx):
     """The call a user makes: lasgun_b200.capture(scene, film) == oracle film."""
     import lasgun_b200
