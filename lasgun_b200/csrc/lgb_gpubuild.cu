@@ -7,6 +7,9 @@
 //   k_scatter  per item: move to its side (warp-aggregated cursors), grow the child's centroid bounds; items of
 //              finished leaves go to their final position
 // Items keep nested ranges [begin, end), so the final item array is in tree order and a leaf is a contiguous run.
+// A node of at most kSub items leaves the level loop: its whole sub-tree is finished by ONE warp in shared memory (k_subtrees: same
+// bins, same sweep, same float arithmetic), so the loop runs ~log2(n / kSub) levels instead of the tree's depth and the deep levels --
+// a quarter of a million nodes, each with 1.3 KB of bins in global memory -- cost one launch.
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/transform_iterator.h>
 
@@ -46,7 +49,9 @@ struct Work {                      // one node of the current level
 // per node with more than kMaxLeaf items: [axis][bin] box lo (3 keys), box hi (3 keys), count
 constexpr int kBinWords = 3 * NB * 7;
 
-struct Ctl { uint32_t next_count, node_count, max_depth, bin_slots, count, levels; };      // count: nodes of the level being split (k_advance)
+struct Ctl { uint32_t next_count, node_count, max_depth, bin_slots, count, levels, sub_count; };      // count: nodes of the level being split (k_advance)
+constexpr uint32_t kSub = 256;         // a node of at most this many items is finished by one warp (k_subtrees)
+struct SubRoot { uint32_t begin, end, parent, which, depth; };
 // Start of a level: the nodes the previous level produced become the current ones.  The host does not read the count back every
 // level (28 round trips for 600 k primitives): the kernels of a level take it from here, are launched for the largest level there can
 // be, and a level past the last one does nothing.
@@ -85,7 +90,8 @@ __global__ void k_prep(Work* work, uint32_t* bins, Ctl* ctl) {
     }
     W.cur_l = W.cur_r = 0;
     W.bins = kInvalid;
-    if (W.end - W.begin > (uint32_t)kMaxLeaf) {
+    const uint32_t n = W.end - W.begin;
+    if (n > kSub || (W.parent == kInvalid && n > (uint32_t)kMaxLeaf)) {         // (smaller nodes go to k_subtrees; the root never does)
         const uint32_t slot = atomicAdd(&ctl->bin_slots, 1u);
         W.bins = slot;
         uint32_t* b = bins + (size_t)slot * kBinWords;
@@ -174,17 +180,79 @@ struct FBox {
 };
 __device__ __forceinline__ void bin_box(const uint32_t* b, float* lo, float* hi) { for (int k = 0; k < 3; k++) { lo[k] = kfloat(b[k]); hi[k] = kfloat(b[3 + k]); } }
 
+// SAH sweep over the bins of one axis: the best split so far is replaced only by a strictly cheaper one
+__device__ __forceinline__ void sah_axis(const uint32_t* B, int a, float& best, int& best_axis, int& best_bin) {
+    float la[NB]; uint32_t lc[NB];
+    FBox acc; acc.reset(); uint32_t c = 0;
+    for (int k = 0; k < NB; k++) {
+        const uint32_t* b = B + (a * NB + k) * 7;
+        if (b[6]) { float lo[3], hi[3]; bin_box(b, lo, hi); acc.grow(lo, hi); }
+        c += b[6]; la[k] = c ? acc.half_area() : 0.0f; lc[k] = c;
+    }
+    acc.reset(); c = 0;
+    for (int k = NB - 1; k >= 1; k--) {
+        const uint32_t* b = B + (a * NB + k) * 7;
+        if (b[6]) { float lo[3], hi[3]; bin_box(b, lo, hi); acc.grow(lo, hi); }
+        c += b[6];
+        if (!c || !lc[k - 1]) continue;
+        const float cost = la[k - 1] * (float)lc[k - 1] + acc.half_area() * (float)c;
+        if (cost < best) { best = cost; best_axis = a; best_bin = k - 1; }
+    }
+}
+
+// The same sweep by a warp: lane k (and its mirror k + 16) owns bin k of axis a, prefix and suffix boxes come from shuffle scans.  It finds
+// what sah_axis finds: min / max are exact in any order, the cost is the same expression of the same operands, and among equal costs the
+// larger bin wins, as it does in the descending loop above.
+__device__ __forceinline__ void sah_axis_warp(const uint32_t* B, int a, unsigned lane, float& best, int& best_axis, int& best_bin) {
+    const unsigned k = lane & 15u;
+    const uint32_t* b = B + (a * NB + k) * 7;
+    const uint32_t cnt = b[6];
+    FBox pre, suf; pre.reset();
+    if (cnt) bin_box(b, pre.lo, pre.hi);
+    suf = pre;
+    uint32_t pc = cnt, sc = cnt;
+    for (unsigned d = 1; d < 16; d <<= 1) {
+        for (int q = 0; q < 3; q++) {
+            const float pl = __shfl_up_sync(0xFFFFFFFFu, pre.lo[q], d, 16), ph = __shfl_up_sync(0xFFFFFFFFu, pre.hi[q], d, 16);
+            const float sl = __shfl_down_sync(0xFFFFFFFFu, suf.lo[q], d, 16), sh = __shfl_down_sync(0xFFFFFFFFu, suf.hi[q], d, 16);
+            if (k >= d) { pre.lo[q] = fminf(pre.lo[q], pl); pre.hi[q] = fmaxf(pre.hi[q], ph); }
+            if (k + d < 16u) { suf.lo[q] = fminf(suf.lo[q], sl); suf.hi[q] = fmaxf(suf.hi[q], sh); }
+        }
+        const uint32_t c0 = __shfl_up_sync(0xFFFFFFFFu, pc, d, 16), c1 = __shfl_down_sync(0xFFFFFFFFu, sc, d, 16);
+        if (k >= d) pc += c0;
+        if (k + d < 16u) sc += c1;
+    }
+    const float pa = pc ? pre.half_area() : 0.0f;
+    const float la = __shfl_up_sync(0xFFFFFFFFu, pa, 1, 16);                 // prefix over bins 0 .. k-1
+    const uint32_t lc = __shfl_up_sync(0xFFFFFFFFu, pc, 1, 16);
+    float c = INFINITY; int kk = -1;
+    if (k >= 1u && sc && lc) {
+        const float cost = la * (float)lc + suf.half_area() * (float)sc;
+        if (cost < INFINITY) { c = cost; kk = (int)k; }
+    }
+    for (unsigned d = 8; d > 0; d >>= 1) {
+        const float oc = __shfl_xor_sync(0xFFFFFFFFu, c, d); const int ok = __shfl_xor_sync(0xFFFFFFFFu, kk, d);
+        if (oc < c || (oc == c && ok > kk)) { c = oc; kk = ok; }
+    }
+    if (kk >= 0 && c < best) { best = c; best_axis = a; best_bin = kk - 1; }
+}
+
 __device__ __forceinline__ void set_child_word(HostNode* nodes, uint32_t parent, uint32_t which, uint32_t word) {
     if (parent == kInvalid) return;
     if (which) nodes[parent].c1 = word; else nodes[parent].c0 = word;
 }
 
-__global__ void k_split(Work* work, const uint32_t* bins, const GItem* items, HostNode* nodes, Work* next, Ctl* ctl, uint32_t next_cap) {
+__global__ void k_split(Work* work, const uint32_t* bins, const GItem* items, HostNode* nodes, Work* next, Ctl* ctl, uint32_t next_cap, SubRoot* subs) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= ctl->count) return;
     Work& W = work[w];
     const uint32_t n = W.end - W.begin;
     W.child[0] = W.child[1] = kInvalid;
+    if (n <= kSub && W.parent != kInvalid) {                   // its items stay where they are (k_scatter), a warp of k_subtrees builds the rest
+        W.mode = 4;
+        subs[atomicAdd(&ctl->sub_count, 1u)] = SubRoot{W.begin, W.end, W.parent, W.which, W.depth};
+        return;
+    }
     FBox lbox, rbox; lbox.reset(); rbox.reset();
     uint32_t nl = 0;
     if (n <= (uint32_t)kMaxLeaf) {
@@ -212,22 +280,7 @@ __global__ void k_split(Work* work, const uint32_t* bins, const GItem* items, Ho
         if (W.depth < 40) {
             for (int a = 0; a < 3; a++) {
                 if (W.scale[a] == 0.0f) continue;
-                float la[NB]; uint32_t lc[NB];
-                FBox acc; acc.reset(); uint32_t c = 0;
-                for (int k = 0; k < NB; k++) {
-                    const uint32_t* b = B + (a * NB + k) * 7;
-                    if (b[6]) { float lo[3], hi[3]; bin_box(b, lo, hi); acc.grow(lo, hi); }
-                    c += b[6]; la[k] = c ? acc.half_area() : 0.0f; lc[k] = c;
-                }
-                acc.reset(); c = 0;
-                for (int k = NB - 1; k >= 1; k--) {
-                    const uint32_t* b = B + (a * NB + k) * 7;
-                    if (b[6]) { float lo[3], hi[3]; bin_box(b, lo, hi); acc.grow(lo, hi); }
-                    c += b[6];
-                    if (!c || !lc[k - 1]) continue;
-                    const float cost = la[k - 1] * (float)lc[k - 1] + acc.half_area() * (float)c;
-                    if (cost < best) { best = cost; best_axis = a; best_bin = k - 1; }
-                }
+                sah_axis(B, a, best, best_axis, best_bin);
             }
         }
         if (best_axis >= 0) {
@@ -277,7 +330,7 @@ __global__ void k_scatter(const GItem* items, uint32_t* node_of, uint32_t n, Wor
     if (w == kInvalid) return;
     Work& W = work[w];
     const GItem it = items[i];
-    const bool is_leaf = W.mode == 3;
+    const bool is_leaf = W.mode >= 3;                           // a leaf, or the root of a sub-tree k_subtrees finishes in place
     const unsigned live = __ballot_sync(act, !is_leaf);
     if (is_leaf) { final_items[i] = it; node_of_out[i] = kInvalid; node_of[i] = kInvalid; return; }   // leaf: the item is where it stays; retired in BOTH buffers
     bool left;
@@ -302,6 +355,145 @@ __global__ void k_scatter(const GItem* items, uint32_t* node_of, uint32_t n, Wor
         agg_min(&C.cb_lo[a], k, peers, lead);
         agg_max(&C.cb_hi[a], k, peers, lead);
     }
+}
+
+// One warp per sub-tree root of at most kSub items: the items sit in shared memory, a permutation of 16-bit indices is partitioned
+// node by node (depth first, explicit stack), and every decision is k_split's: same centroid bounds (k_scatter grows them from the same
+// items), same bin map, same bins (min / max / count do not depend on the order), same sweep.
+constexpr int kSubWarps = 4;
+__global__ void __launch_bounds__(32 * kSubWarps) k_subtrees(const SubRoot* subs, GItem* final_items, HostNode* nodes, Ctl* ctl) {
+    __shared__ uint4 s_items[kSubWarps][kSub * 2];
+    __shared__ uint16_t s_idx[kSubWarps][2][kSub];
+    __shared__ uint32_t s_bins[kSubWarps][kBinWords];
+    __shared__ uint4 s_stack[kSubWarps][64];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    const uint32_t s = blockIdx.x * kSubWarps + warp;
+    if (s >= ctl->sub_count) return;
+    const SubRoot R = subs[s];
+    const uint32_t n0 = R.end - R.begin;
+    const GItem* items = reinterpret_cast<const GItem*>(s_items[warp]);
+    uint16_t* idx = s_idx[warp][0]; uint16_t* alt = s_idx[warp][1];
+    uint32_t* bins = s_bins[warp];
+    uint4* stack = s_stack[warp];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(final_items + R.begin);
+        for (uint32_t i = lane; i < 2 * n0; i += 32) s_items[warp][i] = src[i];
+        for (uint32_t i = lane; i < n0; i += 32) idx[i] = (uint16_t)i;
+    }
+    if (lane == 0) stack[0] = make_uint4(0u, n0, R.parent | (R.which << 31), R.depth);
+    __syncwarp();
+    uint32_t sp = 1, maxd = 0;
+    while (sp) {
+        const uint4 top = stack[--sp];
+        __syncwarp();
+        const uint32_t b = top.x, e = top.y, n = e - b, parent = top.z & 0x7FFFFFFFu, which = top.z >> 31, depth = top.w;
+        uint32_t mode = 0, nl = 0, tmin = 0; int axis = -1, bin = -1;
+        float cmin[3] = {0.f, 0.f, 0.f}, scale[3] = {0.f, 0.f, 0.f};
+        FBox lbox, rbox; lbox.reset(); rbox.reset();
+        if (n <= (uint32_t)kMaxLeaf) {
+            const uint32_t t = lane < n ? items[idx[b + lane]].type : 0xFFFFFFFFu;
+            const uint32_t t0 = __shfl_sync(0xFFFFFFFFu, t, 0);
+            const bool mixed = __any_sync(0xFFFFFFFFu, lane < n && t != t0);
+            tmin = __reduce_min_sync(0xFFFFFFFFu, t);
+            if (!mixed) {
+                if (lane == 0) set_child_word(nodes, parent, which, kLeafBit | (tmin << 29) | ((n - 1) << 24) | (R.begin + b));
+                maxd = max(maxd, depth);
+                continue;
+            }
+            mode = 1;
+            for (uint32_t i = b; i < e; i++) {                   // at most kMaxLeaf items
+                const GItem& it = items[idx[i]];
+                if (it.type == tmin) { nl++; lbox.grow(it.lo, it.hi); } else rbox.grow(it.lo, it.hi);
+            }
+        } else {
+            uint32_t clo[3] = {kKeyMax, kKeyMax, kKeyMax}, chi[3] = {0, 0, 0};
+            for (uint32_t i = b + lane; i < e; i += 32) {
+                const GItem& it = items[idx[i]];
+                for (int a = 0; a < 3; a++) { const uint32_t k = fkey(centroid(it, a)); clo[a] = min(clo[a], k); chi[a] = max(chi[a], k); }
+            }
+            for (int a = 0; a < 3; a++) {
+                const float lo = kfloat(__reduce_min_sync(0xFFFFFFFFu, clo[a])), hi = kfloat(__reduce_max_sync(0xFFFFFFFFu, chi[a]));
+                const float ext = hi - lo;
+                cmin[a] = lo;
+                scale[a] = ext > 0.0f ? (float)NB * (1.0f - 1e-6f) / ext : 0.0f;
+            }
+            for (int i = lane; i < kBinWords; i += 32) bins[i] = (i % 7) < 3 ? kKeyMax : 0u;
+            __syncwarp();
+            for (uint32_t i = b + lane; i < e; i += 32) {
+                const GItem& it = items[idx[i]];
+                for (int a = 0; a < 3; a++) {
+                    uint32_t* q = bins + (a * NB + bin_of(centroid(it, a), cmin[a], scale[a])) * 7;
+                    atomicMin(q + 0, fkey(it.lo[0])); atomicMin(q + 1, fkey(it.lo[1])); atomicMin(q + 2, fkey(it.lo[2]));
+                    atomicMax(q + 3, fkey(it.hi[0])); atomicMax(q + 4, fkey(it.hi[1])); atomicMax(q + 5, fkey(it.hi[2]));
+                    atomicAdd(q + 6, 1u);
+                }
+            }
+            __syncwarp();
+            // the axes compete in k_split's order (a later axis wins only if strictly cheaper)
+            float best = INFINITY;
+            if (depth < 40)
+                for (int a = 0; a < 3; a++) if (scale[a] != 0.0f) sah_axis_warp(bins, a, lane, best, axis, bin);
+            if (axis >= 0) {
+                mode = 0;
+                for (int k = 0; k < NB; k++) {
+                    const uint32_t* q = bins + (axis * NB + k) * 7;
+                    if (!q[6]) continue;
+                    float lo[3], hi[3]; bin_box(q, lo, hi);
+                    if (k <= bin) { lbox.grow(lo, hi); nl += q[6]; } else rbox.grow(lo, hi);
+                }
+            } else {                                             // coincident centroids or depth guard: halve by position
+                mode = 2; nl = n / 2;
+                for (int k = 0; k < NB; k++) {
+                    const uint32_t* q = bins + k * 7;
+                    if (!q[6]) continue;
+                    float lo[3], hi[3]; bin_box(q, lo, hi); lbox.grow(lo, hi);
+                }
+                rbox = lbox;
+            }
+        }
+        uint32_t me = 0;
+        if (lane == 0) {
+            me = atomicAdd(&ctl->node_count, 1u);
+            set_child_word(nodes, parent, which, me);
+            HostNode& nd = nodes[me];
+            for (int k = 0; k < 3; k++) { nd.v[k] = lbox.lo[k]; nd.v[3 + k] = lbox.hi[k]; nd.v[6 + k] = rbox.lo[k]; nd.v[9 + k] = rbox.hi[k]; }
+            nd.pad0 = nd.pad1 = 0;
+        }
+        me = __shfl_sync(0xFFFFFFFFu, me, 0);
+        // stable partition of the node's index range
+        uint32_t lc = 0, rc = 0;
+        for (uint32_t base = b; base < e; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < e;
+            const uint16_t id = valid ? idx[i] : (uint16_t)0;
+            bool left = false;
+            if (valid) {
+                const GItem& it = items[id];
+                if (mode == 0) left = bin_of(centroid(it, axis), cmin[axis], scale[axis]) <= bin;
+                else if (mode == 1) left = it.type == tmin;
+                else left = i - b < nl;
+            }
+            const unsigned lm = __ballot_sync(0xFFFFFFFFu, left), rm = __ballot_sync(0xFFFFFFFFu, valid && !left);
+            if (left) alt[b + lc + __popc(lm & lt)] = id;
+            else if (valid) alt[b + nl + rc + __popc(rm & lt)] = id;
+            lc += __popc(lm); rc += __popc(rm);
+        }
+        __syncwarp();
+        for (uint32_t i = b + lane; i < e; i += 32) idx[i] = alt[i];
+        if (sp + 2 > 64u) { maxd = 0xFFFFu; break; }            // cannot happen below the depth guard; the caller rejects the tree
+        if (lane == 0) {
+            stack[sp] = make_uint4(b + nl, e, me | (1u << 31), depth + 1);
+            stack[sp + 1] = make_uint4(b, b + nl, me, depth + 1);
+        }
+        sp += 2;
+        __syncwarp();
+    }
+    __syncwarp();
+    {
+        uint4* dst = reinterpret_cast<uint4*>(final_items + R.begin);
+        for (uint32_t i = lane; i < 2 * n0; i += 32) dst[i] = s_items[warp][2 * idx[i >> 1] + (i & 1)];
+    }
+    if (lane == 0) atomicMax(&ctl->max_depth, maxd);
 }
 
 __global__ void k_fill(uint32_t* p, uint32_t n, uint32_t v) { const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
@@ -399,6 +591,7 @@ size_t gpu_build_temp_bytes(uint32_t n) {
     b += 2 * align256((size_t)n * sizeof(GItem));            // ping / pong
     b += 2 * align256((size_t)n * 4);                        // node_of ping / pong
     b += 2 * align256((size_t)(n + 2) * sizeof(Work));       // work lists of two levels
+    b += align256((size_t)(n + 2) * sizeof(SubRoot));        // sub-tree roots (k_subtrees)
     b += align256(((size_t)n / (kMaxLeaf + 1) + 2) * kBinWords * 4);   // bin pool: nodes of more than kMaxLeaf items
     b += align256(sizeof(Ctl)) + align256(4 * sizeof(void*));
     b += 3 * align256((size_t)n * 4);                        // per-type positions
@@ -439,6 +632,7 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
     GItem* buf[2] = {(GItem*)take((size_t)n * sizeof(GItem)), (GItem*)take((size_t)n * sizeof(GItem))};
     uint32_t* nof[2] = {(uint32_t*)take((size_t)n * 4), (uint32_t*)take((size_t)n * 4)};
     Work* work[2] = {(Work*)take((size_t)(n + 2) * sizeof(Work)), (Work*)take((size_t)(n + 2) * sizeof(Work))};
+    SubRoot* subs = (SubRoot*)take((size_t)(n + 2) * sizeof(SubRoot));
     uint32_t* bins = (uint32_t*)take(((size_t)n / (kMaxLeaf + 1) + 2) * kBinWords * 4);
     Ctl* ctl = (Ctl*)take(sizeof(Ctl));
     uint32_t** d_typepos = (uint32_t**)take(4 * sizeof(void*));
@@ -471,16 +665,17 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
     root.begin = 0; root.end = n; root.parent = kInvalid; root.which = 0; root.depth = 0;
     for (int a = 0; a < 3; a++) { root.cb_lo[a] = kKeyMax; root.cb_hi[a] = 0; }
     if ((e = cudaMemcpyAsync(work[0], &root, sizeof root, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
-    Ctl c0{1, 1, 0, 0, 0, 0};                              // node 0 is the root; one node (the root) enters the first level
+    Ctl c0{1, 1, 0, 0, 0, 0, 0};                           // node 0 is the root; one node (the root) enters the first level
     if ((e = cudaMemcpyAsync(ctl, &c0, sizeof c0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(buf[0], items_in, (size_t)n * sizeof(GItem), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
     k_fill<<<ib, 256, 0, st>>>(nof[0], n, 0u);
     k_root<<<256, 256, 0, st>>>(buf[0], n, work[0], ctl);
     if ((e = check("k_root", 0)) != cudaSuccess) return e;
-    uint32_t levels = 0, node_count = 1, max_depth = 0, launched = 0;
+    uint32_t levels = 0, node_count = 1, max_depth = 0, launched = 0, sub_count = 0;
     int cur = 0;
     const bool timing = std::getenv("LGB_TIMING") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
+    if (timing) cudaStreamSynchronize(st);                 // (the caller's upload is still in flight on this stream: keep it out of the first chunk)
     auto t_start = now();
     std::vector<double> chunk_ms;
     // a level never holds more nodes than there are items above leaf size ... bounded by the item count
@@ -495,7 +690,7 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
             k_bin_top<<<296, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], bins, ctl);
             k_bin<<<ib, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], bins, ctl);
             if ((e = check("k_bin", launched)) != cudaSuccess) return e;
-            k_split<<<wb, 128, 0, st>>>(work[cur], bins, buf[cur], nodes_out, work[cur ^ 1], ctl, n + 2);
+            k_split<<<wb, 128, 0, st>>>(work[cur], bins, buf[cur], nodes_out, work[cur ^ 1], ctl, n + 2, subs);
             if ((e = check("k_split", launched)) != cudaSuccess) return e;
             k_scatter<<<ib, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], work[cur ^ 1], buf[cur ^ 1], nof[cur ^ 1], final_items);
             if ((e = check("k_scatter", launched)) != cudaSuccess) return e;
@@ -506,8 +701,18 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
         if (timing) chunk_ms.push_back(std::chrono::duration<double, std::milli>(now() - t_chunk).count());
         node_count = h.node_count; max_depth = h.max_depth; levels = h.levels;
-        if (h.next_count == 0) break;
+        if (h.next_count == 0) { sub_count = h.sub_count; break; }
         if (launched > 96) return cudaErrorUnknown;         // depth guard (splits by position halve every node from depth 40 on)
+    }
+    double sub_ms = 0.0;
+    if (sub_count) {                                        // every node the loop left at <= kSub items: one warp each, to the leaves
+        auto t_sub = now();
+        k_subtrees<<<(sub_count + kSubWarps - 1) / kSubWarps, 32 * kSubWarps, 0, st>>>(subs, final_items, nodes_out, ctl);
+        Ctl h;
+        if ((e = cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        node_count = h.node_count; max_depth = h.max_depth;
+        sub_ms = std::chrono::duration<double, std::milli>(now() - t_sub).count();
     }
     // per-type positions of the items in tree order; leaf words -> first index in the type's array
     for (uint32_t t = 0; t < 3; t++) {
@@ -522,7 +727,7 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
     if (timing) {
         std::fprintf(stderr, "[gpu_build_sah] %u items, %u levels (%u launched), %.2f ms total; per chunk of %u levels:", n, levels, launched, std::chrono::duration<double, std::milli>(now() - t_start).count(), kChunk);
         for (size_t i = 0; i < chunk_ms.size(); i++) std::fprintf(stderr, " %.2f", chunk_ms[i]);
-        std::fprintf(stderr, "\n");
+        std::fprintf(stderr, "; %u sub-trees of <= %u items %.2f ms\n", sub_count, kSub, sub_ms);
         if (dbg) for (int h = 0; h < 2; h++) std::fprintf(stderr, "[gpu_build_sah]   %s: prep %.2f bin %.2f split %.2f scatter %.2f ms (synchronised after every kernel)\n", h ? "levels 8.." : "levels 0..7",
                                                           k_ms[h][0], k_ms[h][1], k_ms[h][2], k_ms[h][3]);
     }

@@ -235,50 +235,83 @@ __global__ void __launch_bounds__(256) k_cam_pass(DevScene S, CamGridParams P, u
 }  // namespace
 
 // Every cell's entries nearest first: the record (ref, dmin bits) read as one little-endian u64 is (dmin << 32) | ref, and the bits of
-// a non-negative float order like the float, so one segmented key sort (cub::DeviceSegmentedSort, off the frame's path like the scans)
-// over the cell ranges does it for lists of any length -- a thread per cell was held up for milliseconds by the few cells that hold
-// hundreds of entries.
-// Short lists (almost all of them: a light-grid cell holds a handful of entries and most of the 6 M cells hold none) are sorted by ONE
-// thread each, in local memory; only the cells longer than kSortThread go to the segmented sort, as a compacted list of ranges --
-// handing it all the cells cost 2 ms per light for 4 M entries, nearly all of it per-segment bookkeeping for empty and tiny segments.
-// A cell counts as long above 32 entries, so there are at most total / 33 of them: that bound sizes the range list and is the
-// segment count the sort is launched with (unused ranges are empty), so the host need not read anything back.
-constexpr uint32_t kSortThread = 32;
-static uint32_t long_bound(uint32_t total) { return total / (kSortThread + 1) + 1; }
-static size_t long_list_bytes(uint32_t total) { return ((size_t)(2 * long_bound(total) + 1) * 4 + 255) & ~(size_t)255; }
+// a non-negative float order like the float, so a cell is sorted as plain u64 keys (all distinct: a primitive is listed once per cell).
+// k_sort_cells: one warp per 32 consecutive cells; a list of up to 32 entries is a bitonic network over the lanes (shuffles only), empty
+// cells and single entries cost a ballot; longer cells are listed.  k_sort_medium: one warp per listed cell of up to kSortWarp entries,
+// bitonic sort in the warp's slice of shared memory (a warp of their own each: a view along a row of primitives puts hundreds of entries
+// into each of a run of adjacent cells).  Cells above kSortWarp entries go to cub::DeviceSegmentedSort (off the frame's path, like the
+// scans) as a compacted list of ranges.  Both lists are sized by their bounds -- at most total / 33 medium and total / (kSortWarp + 1)
+// long cells -- and the launches are made for the bounds (unused ranges are empty), so the host need not read anything back.
+// Measured before: one THREAD per short cell (insertion sort in local memory) + the segmented sort for everything above 32 entries
+// took 1.8 ms per light and 4.7 ms for the camera grid on `spheres1m` (12 M entries, 45 per tile); now 0.3 / 0.5 ms.
+constexpr uint32_t kSortWarp = 1024;
+constexpr int kSortWarps = 4;            // warps per block of k_sort_medium: 4 x 8 KB of shared memory
+static uint32_t long_bound(uint32_t total) { return total / (kSortWarp + 1) + 1; }
+static uint32_t medium_bound(uint32_t total) { return total / 33 + 1; }
+static size_t long_list_bytes(uint32_t total) { return ((size_t)(2 * long_bound(total) + 2 * medium_bound(total) + 2) * 4 + 255) & ~(size_t)255; }
 size_t grid_sort_bytes(uint32_t total, size_t) {
     size_t b = 0;
     cub::DeviceSegmentedSort::SortKeys(nullptr, b, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)total, (int)long_bound(total), (const uint32_t*)nullptr, (const uint32_t*)nullptr);
     return b + long_list_bytes(total);
 }
-__global__ void __launch_bounds__(128) k_sort_short(const unsigned long long* in, unsigned long long* out, const uint32_t* starts, uint32_t n_cells,
-                                                    uint32_t* long_begin, uint32_t* long_end, uint32_t* n_long) {
-    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= n_cells) return;
-    const uint32_t b = starts[cell], n = starts[cell + 1] - b;
-    if (n == 0) return;
-    if (n == 1) { out[b] = in[b]; return; }
-    if (n > kSortThread) { const uint32_t k = atomicAdd(n_long, 1u); long_begin[k] = b; long_end[k] = b + n; return; }
-    unsigned long long v[kSortThread];
-    for (uint32_t i = 0; i < n; i++) {                      // insertion sort as the entries arrive
-        const unsigned long long x = in[b + i];
-        uint32_t j = i;
-        while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; j--; }
-        v[j] = x;
+__global__ void __launch_bounds__(128) k_sort_cells(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, const uint32_t* __restrict__ starts,
+                                                    uint32_t n_cells, uint32_t* long_begin, uint32_t* long_end, uint32_t* n_long, uint2* medium, uint32_t* n_medium) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;         // a warp's lanes hold 32 consecutive cells
+    uint32_t b = 0, n = 0;
+    if (cell < n_cells) { b = starts[cell]; n = starts[cell + 1] - b; }
+    if (n == 1) out[b] = in[b];
+    else if (n > kSortWarp) { const uint32_t k = atomicAdd(n_long, 1u); long_begin[k] = b; long_end[k] = b + n; }
+    else if (n > 32u) medium[atomicAdd(n_medium, 1u)] = make_uint2(b, n);
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, n >= 2u && n <= 32u);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t cb = __shfl_sync(0xFFFFFFFFu, b, src), cn = __shfl_sync(0xFFFFFFFFu, n, src);
+        unsigned long long v = lane < cn ? in[cb + lane] : ~0ull;          // one entry per lane, padded with the largest key
+        for (unsigned k = 2; k <= 32u; k <<= 1)
+            for (unsigned j = k >> 1; j > 0; j >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, v, j);
+                const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+                v = keep_min ? (o < v ? o : v) : (o > v ? o : v);
+            }
+        if (lane < cn) out[cb + lane] = v;
     }
-    for (uint32_t i = 0; i < n; i++) out[b + i] = v[i];
+}
+__global__ void __launch_bounds__(32 * kSortWarps) k_sort_medium(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, const uint2* __restrict__ medium,
+                                                                  const uint32_t* __restrict__ n_medium) {
+    __shared__ unsigned long long sm[kSortWarps][kSortWarp];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t m = blockIdx.x * kSortWarps + warp;
+    if (m >= *n_medium) return;
+    unsigned long long* buf = sm[warp];
+    const uint32_t cb = medium[m].x, cn = medium[m].y;
+    uint32_t P = 64; while (P < cn) P <<= 1;
+    for (uint32_t i = lane; i < P; i += 32) buf[i] = i < cn ? in[cb + i] : ~0ull;
+    __syncwarp();
+    for (uint32_t k = 2; k <= P; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = lane; t < P / 2; t += 32) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;      // the pair (i, i + j), bit j of i clear
+                const unsigned long long x = buf[i], y = buf[l];
+                if ((x > y) == ((i & k) == 0)) { buf[i] = y; buf[l] = x; }
+            }
+            __syncwarp();
+        }
+    for (uint32_t i = lane; i < cn; i += 32) out[cb + i] = buf[i];
 }
 static cudaError_t sort_cells(const uint2* in, uint2* out, uint32_t total, const uint32_t* starts, size_t n_cells, void* tmp, size_t tmp_bytes, cudaStream_t st) {
     if (total == 0) return cudaSuccess;
-    const uint32_t bound = long_bound(total);
+    const uint32_t bound = long_bound(total), mbound = medium_bound(total);
     const size_t list_bytes = long_list_bytes(total);
-    uint32_t* long_begin = (uint32_t*)tmp; uint32_t* long_end = long_begin + bound; uint32_t* n_long = long_end + bound;
+    uint32_t* long_begin = (uint32_t*)tmp; uint32_t* long_end = long_begin + bound; uint32_t* n_long = long_end + bound; uint32_t* n_medium = n_long + 1;
+    uint2* medium = (uint2*)(n_medium + 1);                                   // (8-byte aligned: 2 * bound + 2 words precede it)
     if (cudaError_t e = cudaMemsetAsync(tmp, 0, list_bytes, st)) return e;
-    k_sort_short<<<(unsigned)((n_cells + 127) / 128), 128, 0, st>>>(reinterpret_cast<const unsigned long long*>(in), reinterpret_cast<unsigned long long*>(out), starts, (uint32_t)n_cells,
-                                                                    long_begin, long_end, n_long);
+    auto keys_in = reinterpret_cast<const unsigned long long*>(in); auto keys_out = reinterpret_cast<unsigned long long*>(out);
+    k_sort_cells<<<(unsigned)((n_cells + 127) / 128), 128, 0, st>>>(keys_in, keys_out, starts, (uint32_t)n_cells, long_begin, long_end, n_long, medium, n_medium);
+    k_sort_medium<<<(mbound + kSortWarps - 1) / kSortWarps, 32 * kSortWarps, 0, st>>>(keys_in, keys_out, medium, n_medium);
     size_t cub_bytes = tmp_bytes - list_bytes;
-    return cub::DeviceSegmentedSort::SortKeys((char*)tmp + list_bytes, cub_bytes, reinterpret_cast<const unsigned long long*>(in), reinterpret_cast<unsigned long long*>(out), (int)total, (int)bound,
-                                              long_begin, long_end, st);
+    return cub::DeviceSegmentedSort::SortKeys((char*)tmp + list_bytes, cub_bytes, keys_in, keys_out, (int)total, (int)bound, long_begin, long_end, st);
 }
 cudaError_t camgrid_count(const DevScene& S, const CamGridParams& P, uint32_t* counts, uint32_t* starts, void* scan_tmp, size_t scan_bytes,
                           uint2* large, uint32_t* n_large_dev, cudaStream_t st, uint32_t* total_out, uint32_t* n_large_out) {

@@ -1,0 +1,16 @@
+#!/bin/bash
+# re-entry check of HEAD: parity, the full bench line, and where capture()'s host side goes on the geometry-heavy configs
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
+python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_n1.json").read().strip().splitlines()[-1])
+print({k:d[k] for k in ("value","ms_per_step","kernel_ms_per_frame")}); print(json.dumps(d["e2e"])[:900])
+for k,v in d.get("other_configs",{}).items(): print(k, v.get("kernel_ms_per_frame"), v.get("e2e_ms_per_frame"))
+PY
+{
+LGB_TIMING=1 python scripts/e2e_breakdown.py mesh1m
+LGB_TIMING=1 LGB_GPUBUILD_DEBUG=1 python scripts/e2e_breakdown.py mesh1m
+LGB_TIMING=1 python scripts/e2e_breakdown.py spheres1m
+} > gpurun_out/r2_v29_e2e_breakdown.txt 2>&1
+grep -v "light [0-9]" gpurun_out/r2_v29_e2e_breakdown.txt | tail -60
