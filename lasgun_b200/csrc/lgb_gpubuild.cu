@@ -140,26 +140,19 @@ __global__ void __launch_bounds__(256) k_bin_top(const GItem* items, const uint3
     __shared__ uint32_t sb[kTopNodes * kBinWords];
     for (int i = threadIdx.x; i < kTopNodes * kBinWords; i += blockDim.x) sb[i] = (i % 7) < 3 ? kKeyMax : 0u;
     __syncthreads();
-    const unsigned lane = threadIdx.x & 31u;
-    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {       // block-uniform trip count
-        const uint32_t i = i0 + threadIdx.x;
-        uint32_t slot = kInvalid;
-        GItem it; const Work* W = nullptr;
-        if (i < n) {
-            const uint32_t w = node_of[i];
-            if (w != kInvalid) { W = &work[w]; slot = W->bins; if (slot != kInvalid) it = items[i]; }
-        }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t w = node_of[i];
+        if (w == kInvalid) continue;
+        const Work& W = work[w];
+        if (W.bins == kInvalid) continue;
+        const GItem it = items[i];
+        // shared-memory atomics take the lanes' conflicts as they come: cheaper than sorting the lanes into groups first (match_any + six
+        // reductions per group, the form the global atomics of k_bin need)
         for (int a = 0; a < 3; a++) {
-            uint32_t target = kInvalid;
-            if (slot != kInvalid) target = slot * (3 * NB) + a * NB + bin_of(centroid(it, a), W->cmin[a], W->scale[a]);
-            const unsigned act = __ballot_sync(0xFFFFFFFFu, target != kInvalid);
-            if (target == kInvalid) continue;
-            const unsigned peers = __match_any_sync(act, target);
-            const bool leader = lane == (unsigned)(__ffs(peers) - 1);
-            uint32_t* b = sb + (size_t)target * 7;
-            agg_min(b + 0, fkey(it.lo[0]), peers, leader); agg_min(b + 1, fkey(it.lo[1]), peers, leader); agg_min(b + 2, fkey(it.lo[2]), peers, leader);
-            agg_max(b + 3, fkey(it.hi[0]), peers, leader); agg_max(b + 4, fkey(it.hi[1]), peers, leader); agg_max(b + 5, fkey(it.hi[2]), peers, leader);
-            if (leader) atomicAdd(b + 6, (uint32_t)__popc(peers));
+            uint32_t* b = sb + (size_t)(W.bins * (3 * NB) + a * NB + bin_of(centroid(it, a), W.cmin[a], W.scale[a])) * 7;
+            atomicMin(b + 0, fkey(it.lo[0])); atomicMin(b + 1, fkey(it.lo[1])); atomicMin(b + 2, fkey(it.lo[2]));
+            atomicMax(b + 3, fkey(it.hi[0])); atomicMax(b + 4, fkey(it.hi[1])); atomicMax(b + 5, fkey(it.hi[2]));
+            atomicAdd(b + 6, 1u);
         }
     }
     __syncthreads();
@@ -321,7 +314,66 @@ __global__ void k_split(Work* work, const uint32_t* bins, const GItem* items, Ho
     }
 }
 
-__global__ void k_scatter(const GItem* items, uint32_t* node_of, uint32_t n, Work* work, Work* next, GItem* items_out, uint32_t* node_of_out, GItem* final_items) {
+// The top of the tree once more: with a handful of nodes owning all the items, the cursors and child bounds of k_scatter are a few dozen
+// words that every warp of the grid hits with global atomics (level 0: 31 k warps x 14 atomics on 14 addresses).  Here a block of 1024
+// threads settles its items among themselves in shared memory and goes to global memory once per (node, side) it holds.
+constexpr int kScatterTopThreads = 1024;
+__global__ void __launch_bounds__(kScatterTopThreads) k_scatter_top(const GItem* items, uint32_t* node_of, uint32_t n, Work* work, Work* next, GItem* items_out,
+                                                                     uint32_t* node_of_out, GItem* final_items, const Ctl* ctl) {
+    if (ctl->count > (uint32_t)kTopNodes || ctl->count == 0) return;
+    __shared__ uint32_t s_cnt[2 * kTopNodes], s_base[2 * kTopNodes], s_lo[2 * kTopNodes][3], s_hi[2 * kTopNodes][3];
+    for (int k = threadIdx.x; k < 2 * kTopNodes; k += blockDim.x) { s_cnt[k] = 0; for (int a = 0; a < 3; a++) { s_lo[k][a] = kKeyMax; s_hi[k][a] = 0; } }
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t w = kInvalid;
+    if (i < n) w = node_of[i];
+    GItem it; bool live = false, left = false; uint32_t rank = 0, key = 0;
+    if (w != kInvalid) {
+        const Work& W = work[w];
+        it = items[i];
+        if (W.mode >= 3) { final_items[i] = it; node_of_out[i] = kInvalid; node_of[i] = kInvalid; }
+        else {
+            live = true;
+            if (W.mode == 0) left = bin_of(centroid(it, W.axis), W.cmin[W.axis], W.scale[W.axis]) <= (int)W.bin;
+            else if (W.mode == 1) left = it.type == W.tmin;
+            else left = i - W.begin < W.nl;
+            key = w * 2u + (left ? 0u : 1u);
+        }
+    }
+    const unsigned act = __ballot_sync(0xFFFFFFFFu, live);
+    if (live) {
+        const unsigned peers = __match_any_sync(act, key);
+        const int leader = __ffs(peers) - 1;
+        const bool lead = (int)lane == leader;
+        uint32_t b0 = 0;
+        if (lead) b0 = atomicAdd(&s_cnt[key], (uint32_t)__popc(peers));
+        rank = __shfl_sync(peers, b0, leader) + __popc(peers & ((1u << lane) - 1u));
+        for (int a = 0; a < 3; a++) {
+            const uint32_t k = fkey(centroid(it, a));
+            agg_min(&s_lo[key][a], k, peers, lead);
+            agg_max(&s_hi[key][a], k, peers, lead);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kTopNodes && s_cnt[threadIdx.x]) {
+        const uint32_t k = threadIdx.x;
+        Work& W = work[k >> 1];
+        s_base[k] = atomicAdd((k & 1u) ? &W.cur_r : &W.cur_l, s_cnt[k]);
+        Work& Cn = next[W.child[k & 1u]];
+        for (int a = 0; a < 3; a++) { atomicMin(&Cn.cb_lo[a], s_lo[k][a]); atomicMax(&Cn.cb_hi[a], s_hi[k][a]); }
+    }
+    __syncthreads();
+    if (live) {
+        const Work& W = work[w];
+        const uint32_t dest = (left ? W.begin : W.begin + W.nl) + s_base[key] + rank;
+        items_out[dest] = it;
+        node_of_out[dest] = W.child[left ? 0 : 1];
+    }
+}
+
+__global__ void k_scatter(const GItem* items, uint32_t* node_of, uint32_t n, Work* work, Work* next, GItem* items_out, uint32_t* node_of_out, GItem* final_items, const Ctl* ctl) {
+    if (ctl->count <= (uint32_t)kTopNodes) return;             // the top of the tree is k_scatter_top's
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     uint32_t w = kInvalid;
@@ -361,7 +413,12 @@ __global__ void k_scatter(const GItem* items, uint32_t* node_of, uint32_t n, Wor
 // node by node (depth first, explicit stack), and every decision is k_split's: same centroid bounds (k_scatter grows them from the same
 // items), same bin map, same bins (min / max / count do not depend on the order), same sweep.
 constexpr int kSubWarps = 4;
-__global__ void __launch_bounds__(32 * kSubWarps) k_subtrees(const SubRoot* subs, GItem* final_items, HostNode* nodes, Ctl* ctl) {
+// Node indices: a sub-tree writes its nodes to its own run of a scratch array under local indices (at most n - 1 interior nodes for n
+// items, so the run [begin, end) of the item range does), takes its place in the output with ONE atomic when it is complete, and copies
+// the nodes over with their child words re-based.  One atomic per node on the common counter was the kernel's bound: 570 k same-address
+// atomics for a million triangles, 1 ms when issued late, 6 ms when issued early.
+constexpr uint32_t kSubRootParent = 0x7FFFFFFFu;       // stack entry of the sub-tree's root: its parent is a node of the level loop
+__global__ void __launch_bounds__(32 * kSubWarps) k_subtrees(const SubRoot* subs, GItem* final_items, HostNode* nodes, HostNode* scratch, Ctl* ctl) {
     __shared__ uint4 s_items[kSubWarps][kSub * 2];
     __shared__ uint16_t s_idx[kSubWarps][2][kSub];
     __shared__ uint32_t s_bins[kSubWarps][kBinWords];
@@ -380,9 +437,10 @@ __global__ void __launch_bounds__(32 * kSubWarps) k_subtrees(const SubRoot* subs
         for (uint32_t i = lane; i < 2 * n0; i += 32) s_items[warp][i] = src[i];
         for (uint32_t i = lane; i < n0; i += 32) idx[i] = (uint16_t)i;
     }
-    if (lane == 0) stack[0] = make_uint4(0u, n0, R.parent | (R.which << 31), R.depth);
+    if (lane == 0) stack[0] = make_uint4(0u, n0, kSubRootParent, R.depth);
     __syncwarp();
-    uint32_t sp = 1, maxd = 0;
+    HostNode* mine = scratch + R.begin;
+    uint32_t sp = 1, maxd = 0, n_mine = 0, root_word = 0;
     while (sp) {
         const uint4 top = stack[--sp];
         __syncwarp();
@@ -396,7 +454,9 @@ __global__ void __launch_bounds__(32 * kSubWarps) k_subtrees(const SubRoot* subs
             const bool mixed = __any_sync(0xFFFFFFFFu, lane < n && t != t0);
             tmin = __reduce_min_sync(0xFFFFFFFFu, t);
             if (!mixed) {
-                if (lane == 0) set_child_word(nodes, parent, which, kLeafBit | (tmin << 29) | ((n - 1) << 24) | (R.begin + b));
+                const uint32_t word = kLeafBit | (tmin << 29) | ((n - 1) << 24) | (R.begin + b);
+                if (parent == kSubRootParent) root_word = word;
+                else if (lane == 0) set_child_word(mine, parent, which, word);
                 maxd = max(maxd, depth);
                 continue;
             }
@@ -451,15 +511,13 @@ __global__ void __launch_bounds__(32 * kSubWarps) k_subtrees(const SubRoot* subs
                 rbox = lbox;
             }
         }
-        uint32_t me = 0;
+        const uint32_t me = n_mine++;                            // local index: the sub-tree's root is 0
         if (lane == 0) {
-            me = atomicAdd(&ctl->node_count, 1u);
-            set_child_word(nodes, parent, which, me);
-            HostNode& nd = nodes[me];
+            if (parent != kSubRootParent) set_child_word(mine, parent, which, me);
+            HostNode& nd = mine[me];
             for (int k = 0; k < 3; k++) { nd.v[k] = lbox.lo[k]; nd.v[3 + k] = lbox.hi[k]; nd.v[6 + k] = rbox.lo[k]; nd.v[9 + k] = rbox.hi[k]; }
             nd.pad0 = nd.pad1 = 0;
         }
-        me = __shfl_sync(0xFFFFFFFFu, me, 0);
         // stable partition of the node's index range
         uint32_t lc = 0, rc = 0;
         for (uint32_t base = b; base < e; base += 32) {
@@ -493,7 +551,23 @@ __global__ void __launch_bounds__(32 * kSubWarps) k_subtrees(const SubRoot* subs
         uint4* dst = reinterpret_cast<uint4*>(final_items + R.begin);
         for (uint32_t i = lane; i < 2 * n0; i += 32) dst[i] = s_items[warp][2 * idx[i >> 1] + (i & 1)];
     }
-    if (lane == 0) atomicMax(&ctl->max_depth, maxd);
+    // the sub-tree's place in the output, its nodes with re-based child words, and its own word in the parent
+    uint32_t base = 0;
+    if (lane == 0 && n_mine) base = atomicAdd(&ctl->node_count, n_mine);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(mine);
+        uint4* dst = reinterpret_cast<uint4*>(nodes + base);
+        for (uint32_t i = lane; i < 4 * n_mine; i += 32) {
+            uint4 v = src[i];
+            if ((i & 3u) == 3u) { if (!(v.x & kLeafBit)) v.x += base; if (!(v.y & kLeafBit)) v.y += base; }
+            dst[i] = v;
+        }
+    }
+    if (lane == 0) {
+        set_child_word(nodes, R.parent, R.which, n_mine ? base : root_word);
+        atomicMax(&ctl->max_depth, maxd);
+    }
 }
 
 __global__ void k_fill(uint32_t* p, uint32_t n, uint32_t v) { const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
@@ -592,6 +666,7 @@ size_t gpu_build_temp_bytes(uint32_t n) {
     b += 2 * align256((size_t)n * 4);                        // node_of ping / pong
     b += 2 * align256((size_t)(n + 2) * sizeof(Work));       // work lists of two levels
     b += align256((size_t)(n + 2) * sizeof(SubRoot));        // sub-tree roots (k_subtrees)
+    b += align256((size_t)n * sizeof(HostNode));             // ... and their nodes under local indices
     b += align256(((size_t)n / (kMaxLeaf + 1) + 2) * kBinWords * 4);   // bin pool: nodes of more than kMaxLeaf items
     b += align256(sizeof(Ctl)) + align256(4 * sizeof(void*));
     b += 3 * align256((size_t)n * 4);                        // per-type positions
@@ -633,6 +708,7 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
     uint32_t* nof[2] = {(uint32_t*)take((size_t)n * 4), (uint32_t*)take((size_t)n * 4)};
     Work* work[2] = {(Work*)take((size_t)(n + 2) * sizeof(Work)), (Work*)take((size_t)(n + 2) * sizeof(Work))};
     SubRoot* subs = (SubRoot*)take((size_t)(n + 2) * sizeof(SubRoot));
+    HostNode* sub_nodes = (HostNode*)take((size_t)n * sizeof(HostNode));
     uint32_t* bins = (uint32_t*)take(((size_t)n / (kMaxLeaf + 1) + 2) * kBinWords * 4);
     Ctl* ctl = (Ctl*)take(sizeof(Ctl));
     uint32_t** d_typepos = (uint32_t**)take(4 * sizeof(void*));
@@ -692,7 +768,8 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
             if ((e = check("k_bin", launched)) != cudaSuccess) return e;
             k_split<<<wb, 128, 0, st>>>(work[cur], bins, buf[cur], nodes_out, work[cur ^ 1], ctl, n + 2, subs);
             if ((e = check("k_split", launched)) != cudaSuccess) return e;
-            k_scatter<<<ib, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], work[cur ^ 1], buf[cur ^ 1], nof[cur ^ 1], final_items);
+            k_scatter_top<<<(n + kScatterTopThreads - 1) / kScatterTopThreads, kScatterTopThreads, 0, st>>>(buf[cur], nof[cur], n, work[cur], work[cur ^ 1], buf[cur ^ 1], nof[cur ^ 1], final_items, ctl);
+            k_scatter<<<ib, 256, 0, st>>>(buf[cur], nof[cur], n, work[cur], work[cur ^ 1], buf[cur ^ 1], nof[cur ^ 1], final_items, ctl);
             if ((e = check("k_scatter", launched)) != cudaSuccess) return e;
             cur ^= 1; launched++;
         }
@@ -707,7 +784,7 @@ cudaError_t gpu_build_sah(const GItem* items_in, uint32_t n, HostNode* nodes_out
     double sub_ms = 0.0;
     if (sub_count) {                                        // every node the loop left at <= kSub items: one warp each, to the leaves
         auto t_sub = now();
-        k_subtrees<<<(sub_count + kSubWarps - 1) / kSubWarps, 32 * kSubWarps, 0, st>>>(subs, final_items, nodes_out, ctl);
+        k_subtrees<<<(sub_count + kSubWarps - 1) / kSubWarps, 32 * kSubWarps, 0, st>>>(subs, final_items, nodes_out, sub_nodes, ctl);
         Ctl h;
         if ((e = cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;

@@ -17,10 +17,17 @@ namespace lgb {
 
 // std::vector whose resize() leaves trivially-constructible elements uninitialised (the arrays are filled by
 // all threads right after sizing; a sequential zero-fill would cost more than the fill).
+// Blocks of a megabyte and more come from a process-wide cache of freed blocks (lgb_parallel.cpp): `capture(scene, film)` sizes the same
+// ~100 MB of arrays for every frame, and a fresh mapping costs its page faults on first touch and an munmap on release (measured: 2 of
+// the 6 ms of flattening a million triangles).
+void* block_alloc(size_t bytes);
+void block_free(void* p, size_t bytes) noexcept;
 template <class T>
 struct default_init_allocator : std::allocator<T> {
     template <class U> struct rebind { using other = default_init_allocator<U>; };
     using std::allocator<T>::allocator;
+    T* allocate(size_t n) { return static_cast<T*>(block_alloc(n * sizeof(T))); }
+    void deallocate(T* p, size_t n) noexcept { block_free(p, n * sizeof(T)); }
     template <class U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void*>(p)) U; }
     template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
 };
