@@ -1529,8 +1529,9 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     const uint64_t n_bands = units_all ? (units_all + units_band - 1) / units_band : 0;
     const uint64_t slots_band = std::max<uint64_t>(units_band * unit_slots, 1), npix_band = std::max<uint64_t>(units_band * px_per_unit, 1);
     if (need_radiance) CU(c, c->radiance.reserve(slots_band * 3 * sizeof(double)));
-    CU(c, c->counters.reserve(sizeof(DevCounters)));
+    CU(c, c->counters.reserve(kCtrBytes));
     CU(c, c->wave.reserve(wave_bytes(slots_band, queue_nl, grid_shadows ? 0 : npix_band)));
+    char* const wave_base = (char*)c->wave.p;
     CU(c, c->wave_ctr.reserve(kWaveCtrBytes));
     if (beam_lists) CU(c, c->beam.reserve(npix_band * kBeamList * sizeof(uint2) + npix_band * 8));
     if (two_lists) CU(c, c->beam2.reserve(npix_band * kBeamList * sizeof(uint2) + npix_band * 4));
@@ -1548,7 +1549,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
         O.aov_id = (uint32_t*)c->aov_id.p; O.aov_t = (double*)c->aov_t.p; O.aov_occl = (uint32_t*)c->aov_occl.p;
         if (a.want_li) { CU(c, c->aov_li.reserve(std::max<uint64_t>(area * W.spp, 1) * 24)); O.aov_li = (double*)c->aov_li.p; }
     }
-    CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));
+    CU(c, cudaMemsetAsync(c->counters.p, 0, kCtrBytes, st));
     CU(c, cudaEventRecord(c->ev0, st));
     cudaEvent_t* pev = (stats && sync_stats && total_all) ? c->phase : nullptr;
     uint32_t tie_slots = 0;
@@ -1578,7 +1579,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
             W.n_pixels = un;
         }
         const uint64_t total = W.n_pixels * W.spp;
-        DevWave V = carve_wave(c->wave.p, c->wave_ctr.p, slots_band, queue_nl, grid_shadows ? 0 : npix_band);
+        DevWave V = carve_wave(wave_base, c->wave_ctr.p, slots_band, queue_nl, grid_shadows ? 0 : npix_band);
         if (beam_lists) {
             V.beam_list = (uint2*)c->beam.p; V.beam_count = (uint32_t*)((char*)c->beam.p + npix_band * kBeamList * sizeof(uint2));
             V.beam_bound = (float*)(V.beam_count + npix_band);
@@ -1620,7 +1621,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
                 DevWork W2 = W;
                 DevCounters before{};
                 if (ties <= V.tie_cap) { W2.slot_list = V.tie_list; W2.n_list = ties; }
-                else if (band == 0) CU(c, cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), st));          // too many to list: the whole band again
+                else if (band == 0) CU(c, cudaMemsetAsync(c->counters.p, 0, kCtrBytes, st));          // too many to list: the whole band again
                 (void)before;
                 if (int rc = sync_scene_copy(c, s, st)) return rc;
                 CU(c, launch_render(s->dev, s->cam, s->shade, W2, O, V, st_on, a.aov, c->sm_count, st, ties <= V.tie_cap ? nullptr : pev, 1, side, a.klog));
@@ -1667,6 +1668,7 @@ static int run_capture(lgb_ctx* c, lgb_scene* s, const CaptureArgs& a, lgb_stats
     }
     if (stats && sync_stats) {
         DevCounters hc;
+        CU(c, launch_fold_counters((DevCounters*)c->counters.p, st));
         CU(c, cudaMemcpyAsync(&hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
         CU(c, cudaStreamSynchronize(st));
         std::memset(stats, 0, sizeof *stats);

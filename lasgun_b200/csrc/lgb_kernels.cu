@@ -116,6 +116,10 @@ __device__ __forceinline__ float inflate_up(double t) { return __double2float_ru
 
 struct Hit { double t; uint32_t ref; };     // ref = type << 30 | index in the leaf-ordered arrays
 
+// the counter stripe of this warp (lgb_types.cuh, kCtrStripes)
+__device__ __forceinline__ DevCounters* ctr(const DevOut& O) {
+    return reinterpret_cast<DevCounters*>(reinterpret_cast<char*>(O.counters) + (size_t)(1u + ((blockIdx.x + (threadIdx.x >> 5) * 17u) & (kCtrStripes - 1u))) * kCtrStride);
+}
 struct LocalCounters { unsigned int node_tests, filter[3], exact[3]; };
 
 __device__ __forceinline__ uint32_t canonical_id(const DevScene& S, uint32_t ref) {
@@ -1167,13 +1171,13 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_primary(De
     }
     if (O.counters && (!W.slot_list || W.n_list_dev)) {          // a re-trace of tied slots is not counted twice (beam fallback slots are new)
         unsigned long long v0 = warp_sum(primary), v1 = warp_sum(hits);
-        if (lane == 0) { atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1); }
+        if (lane == 0) { atomicAdd(&ctr(O)->primary_rays, v0); atomicAdd(&ctr(O)->primary_hits, v1); }
         if (STATS) {
             unsigned long long n = warp_sum(lc.node_tests);
-            if (lane == 0) { atomicAdd(&O.counters->node_tests, n); atomicAdd(&O.counters->p_node_tests, n); }
+            if (lane == 0) { atomicAdd(&ctr(O)->node_tests, n); atomicAdd(&ctr(O)->p_node_tests, n); }
             for (int k = 0; k < 3; k++) {
                 unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
-                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); atomicAdd(&O.counters->p_filter[k], a); atomicAdd(&O.counters->p_exact[k], b); }
+                if (lane == 0) { atomicAdd(&ctr(O)->filter[k], a); atomicAdd(&ctr(O)->exact[k], b); atomicAdd(&ctr(O)->p_filter[k], a); atomicAdd(&ctr(O)->p_exact[k], b); }
             }
         }
     }
@@ -1364,13 +1368,13 @@ __global__ void __launch_bounds__(LGB_BEAM_THREADS, 1024 / LGB_BEAM_THREADS) k_b
     }
     if (O.counters) {
         unsigned long long v0 = warp_sum(primary), v1 = warp_sum(hits);
-        if (lane == 0) { atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1); }
+        if (lane == 0) { atomicAdd(&ctr(O)->primary_rays, v0); atomicAdd(&ctr(O)->primary_hits, v1); }
         if (STATS) {
             const unsigned long long v = warp_sum(lc.node_tests);
-            if (lane == 0) { atomicAdd(&O.counters->node_tests, v); atomicAdd(&O.counters->p_node_tests, v); atomicAdd(&O.counters->beam_node_tests, v); }
+            if (lane == 0) { atomicAdd(&ctr(O)->node_tests, v); atomicAdd(&ctr(O)->p_node_tests, v); atomicAdd(&ctr(O)->beam_node_tests, v); }
             for (int k = 0; k < 3; k++) {
                 unsigned long long a = warp_sum(lc.filter[k]), b2 = warp_sum(lc.exact[k]);
-                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b2); atomicAdd(&O.counters->p_filter[k], a); atomicAdd(&O.counters->p_exact[k], b2); }
+                if (lane == 0) { atomicAdd(&ctr(O)->filter[k], a); atomicAdd(&ctr(O)->exact[k], b2); atomicAdd(&ctr(O)->p_filter[k], a); atomicAdd(&ctr(O)->p_exact[k], b2); }
             }
         }
     }
@@ -1431,11 +1435,11 @@ __global__ void __launch_bounds__(LGB_LEAFP_THREADS, 1024 / LGB_LEAFP_THREADS) k
     block_append(sc, fallback, (uint32_t)g, V.fallback_list, V.fallback_count);
     if (O.counters) {
         unsigned long long v0 = warp_sum(primary), v1 = warp_sum(hits);
-        if (lane == 0) { atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1); }
+        if (lane == 0) { atomicAdd(&ctr(O)->primary_rays, v0); atomicAdd(&ctr(O)->primary_hits, v1); }
         if (STATS) {
             for (int k = 0; k < 3; k++) {
                 unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
-                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); atomicAdd(&O.counters->p_filter[k], a); atomicAdd(&O.counters->p_exact[k], b); }
+                if (lane == 0) { atomicAdd(&ctr(O)->filter[k], a); atomicAdd(&ctr(O)->exact[k], b); atomicAdd(&ctr(O)->p_filter[k], a); atomicAdd(&ctr(O)->p_exact[k], b); }
             }
         }
     }
@@ -1619,11 +1623,11 @@ __global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, LGB_CPRIMARY_BLOCKS) k_c
     }
     if (O.counters) {
         unsigned long long v0 = warp_sum(primary), v1 = warp_sum(hits);
-        if (lane == 0) { atomicAdd(&O.counters->primary_rays, v0); atomicAdd(&O.counters->primary_hits, v1); }
+        if (lane == 0) { atomicAdd(&ctr(O)->primary_rays, v0); atomicAdd(&ctr(O)->primary_hits, v1); }
         if (STATS) {
             for (int k = 0; k < 3; k++) {
                 unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
-                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); atomicAdd(&O.counters->p_filter[k], a); atomicAdd(&O.counters->p_exact[k], b); }
+                if (lane == 0) { atomicAdd(&ctr(O)->filter[k], a); atomicAdd(&ctr(O)->exact[k], b); atomicAdd(&ctr(O)->p_filter[k], a); atomicAdd(&ctr(O)->p_exact[k], b); }
             }
         }
     }
@@ -1764,8 +1768,8 @@ __global__ void __launch_bounds__(kAppendThreads) k_pretest(DevScene S, DevWork 
     }
     if (O.counters) {
         const unsigned long long n = warp_sum(ncached);
-        if (lane == 0 && n) { atomicAdd(&O.counters->shadow_cached, n); atomicAdd(&O.counters->shadow_occluded, n); }
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&O.counters->shadow_traced, (unsigned long long)total);
+        if (lane == 0 && n) { atomicAdd(&ctr(O)->shadow_cached, n); atomicAdd(&ctr(O)->shadow_occluded, n); }
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr(O)->shadow_traced, (unsigned long long)total);
     }
 }
 
@@ -1886,7 +1890,7 @@ __global__ void __launch_bounds__(LGB_SBEAM_THREADS_, 1024 / LGB_SBEAM_THREADS_)
     }
     if (O.counters && STATS) {
         unsigned long long nt = warp_sum(lc.node_tests);
-        if (lane == 0) atomicAdd(&O.counters->node_tests, nt);
+        if (lane == 0) atomicAdd(&ctr(O)->node_tests, nt);
     }
 }
 // One thread per queue-B entry (the non-anchor samples): where the pixel's bundle left a complete list, the ray is tested against
@@ -1928,11 +1932,11 @@ __global__ void __launch_bounds__(LGB_SWALK_THREADS, 1024 / LGB_SWALK_THREADS) k
     }
     if (O.counters) {
         unsigned long long v = warp_sum(occluded);
-        if (lane == 0 && v) atomicAdd(&O.counters->shadow_occluded, v);
+        if (lane == 0 && v) atomicAdd(&ctr(O)->shadow_occluded, v);
         if (STATS) {
             for (int k = 0; k < 3; k++) {
                 unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
-                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); }
+                if (lane == 0) { atomicAdd(&ctr(O)->filter[k], a); atomicAdd(&ctr(O)->exact[k], b); }
             }
         }
     }
@@ -2065,13 +2069,13 @@ __global__ void __launch_bounds__(256, LGB_GSHADOW_MIN_BLOCKS) k_gshadow(DevScen
     if (O.counters) {
         const unsigned long long v0 = warp_sum(traced), v1 = warp_sum(occluded);
         if (lane == 0 && v0) {
-            if (W.mode == 3) atomicAdd(&O.counters->secondary_rays, v0);      // a level of the specular ray trees: lgb_stats.secondary_rays
-            else { atomicAdd(&O.counters->shadow_traced, v0); atomicAdd(&O.counters->shadow_occluded, v1); }
+            if (W.mode == 3) atomicAdd(&ctr(O)->secondary_rays, v0);      // a level of the specular ray trees: lgb_stats.secondary_rays
+            else { atomicAdd(&ctr(O)->shadow_traced, v0); atomicAdd(&ctr(O)->shadow_occluded, v1); }
         }
         if (STATS) {
             for (int k = 0; k < 3; k++) {
                 unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
-                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); }
+                if (lane == 0) { atomicAdd(&ctr(O)->filter[k], a); atomicAdd(&ctr(O)->exact[k], b); }
             }
         }
     }
@@ -2142,14 +2146,14 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_shadow(Dev
     }
     if (O.counters) {
         unsigned long long v = warp_sum(occluded);
-        if (lane == 0) atomicAdd(&O.counters->shadow_occluded, v);
-        if (which == kQueueA && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&O.counters->shadow_traced, (unsigned long long)total);
+        if (lane == 0) atomicAdd(&ctr(O)->shadow_occluded, v);
+        if (which == kQueueA && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr(O)->shadow_traced, (unsigned long long)total);
         if (STATS) {
             unsigned long long n = warp_sum(lc.node_tests);
-            if (lane == 0) atomicAdd(&O.counters->node_tests, n);
+            if (lane == 0) atomicAdd(&ctr(O)->node_tests, n);
             for (int k = 0; k < 3; k++) {
                 unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
-                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); }
+                if (lane == 0) { atomicAdd(&ctr(O)->filter[k], a); atomicAdd(&ctr(O)->exact[k], b); }
             }
         }
     }
@@ -2599,11 +2603,11 @@ __global__ void __launch_bounds__(256, LGB_SURFACE_MIN_BLOCKS) k_surface(DevScen
     }
     if (O.counters) {
         const unsigned long long v0 = warp_sum(traced), v1 = warp_sum(occluded);
-        if (lane == 0 && v0) { atomicAdd(&O.counters->shadow_traced, v0); atomicAdd(&O.counters->shadow_occluded, v1); }
+        if (lane == 0 && v0) { atomicAdd(&ctr(O)->shadow_traced, v0); atomicAdd(&ctr(O)->shadow_occluded, v1); }
         if (STATS) {
             for (int k = 0; k < 3; k++) {
                 unsigned long long a = warp_sum(lc.filter[k]), b = warp_sum(lc.exact[k]);
-                if (lane == 0) { atomicAdd(&O.counters->filter[k], a); atomicAdd(&O.counters->exact[k], b); }
+                if (lane == 0) { atomicAdd(&ctr(O)->filter[k], a); atomicAdd(&ctr(O)->exact[k], b); }
             }
         }
     }
@@ -2692,7 +2696,7 @@ __global__ void __launch_bounds__(LGB_SEC_THREADS, LGB_SEC_MIN_BLOCKS) k_seconda
         push_specular<INST>(S, P, cur.w, cur.depth, stack, sp);
     }
     O.radiance[3 * (size_t)g + 0] += rad.x; O.radiance[3 * (size_t)g + 1] += rad.y; O.radiance[3 * (size_t)g + 2] += rad.z;
-    if (O.counters) atomicAdd(&O.counters->secondary_rays, traced);
+    if (O.counters) atomicAdd(&ctr(O)->secondary_rays, traced);
 }
 
 // ---- the same recursion as a wavefront, one level of the ray trees at a time (the default; k_secondary is kept as a cross-check):
@@ -2789,6 +2793,18 @@ __global__ void k_flag_wait(const volatile uint32_t* flags, uint32_t first, uint
         }
     }
     __threadfence_system();
+}
+__global__ void k_fold_counters(DevCounters* base) {
+    constexpr unsigned kWords = sizeof(DevCounters) / 8;
+    if (threadIdx.x >= kWords) return;
+    unsigned long long sum = 0;
+    for (uint32_t k = 1; k <= kCtrStripes; k++) sum += reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(base) + (size_t)k * kCtrStride)[threadIdx.x];
+    reinterpret_cast<unsigned long long*>(base)[threadIdx.x] = sum;
+}
+cudaError_t launch_fold_counters(DevCounters* base, cudaStream_t stream) {
+    if (!base) return cudaSuccess;
+    k_fold_counters<<<1, 32, 0, stream>>>(base);
+    return cudaGetLastError();
 }
 cudaError_t launch_flag_signal(void* flag, uint32_t value, cudaStream_t stream) {
     k_flag_signal<<<1, 1, 0, stream>>>((volatile uint32_t*)flag, value);

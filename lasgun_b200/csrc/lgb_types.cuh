@@ -165,6 +165,16 @@ struct DevCounters {
     unsigned int pad;
 };
 
+// Where the kernels add: the buffer behind DevOut::counters holds the record the host reads, then kCtrStripes copies kCtrStride bytes
+// apart; a warp adds to the copy its block and warp index select (ctr(), lgb_kernels.cu) and launch_fold_counters sums the copies into
+// the record before anybody reads it.  With ONE copy the 4 M warps of k_cprimary sent 8 M atomics to two words per frame; the L2 slice
+// those words lived on was the kernel's bottleneck whenever a hot read-only line of the frame (tile list, large list, lights) happened
+// to share it -- 6.8 ms or 8.2-8.8 ms for the same launch, decided by whatever the process had allocated before (profiles/r2_v36-38).
+constexpr uint32_t kCtrStripes = 64, kCtrStride = 256;
+static_assert(sizeof(DevCounters) <= kCtrStride, "counter stripe");
+constexpr size_t kCtrBytes = (size_t)(1 + kCtrStripes) * kCtrStride;
+cudaError_t launch_fold_counters(DevCounters* base, cudaStream_t stream);
+
 // lgb_capture_profile: CUDA events around every kernel launch of one frame (all on ONE stream for that call, so a launch's
 // duration is its own) and a snapshot of the work counters behind each, so that every launch's share of them is known.  Host-side only.
 struct KernelLog {
@@ -182,7 +192,7 @@ struct KernelLog {
     void end(cudaStream_t s, const DevCounters* ctr) {
         if (n >= kMax) return;
         cudaEventRecord(ev1[n], s);
-        if (snaps && ctr) cudaMemcpyAsync(snaps + n, ctr, sizeof(DevCounters), cudaMemcpyDeviceToDevice, s);
+        if (snaps && ctr) { launch_fold_counters(const_cast<DevCounters*>(ctr), s); cudaMemcpyAsync(snaps + n, ctr, sizeof(DevCounters), cudaMemcpyDeviceToDevice, s); }
         n++;
     }
 };
