@@ -1622,7 +1622,7 @@ __global__ void __launch_bounds__(LGB_CPRIMARY_THREADS, LGB_CPRIMARY_BLOCKS) k_c
         }
     }
     if (O.counters) {
-        unsigned long long v0 = warp_sum(primary), v1 = warp_sum(hits);
+        const unsigned long long v0 = __popc(__ballot_sync(0xFFFFFFFFu, primary != 0)), v1 = __popc(__ballot_sync(0xFFFFFFFFu, hits != 0));      // (one slot per thread)
         if (lane == 0) { atomicAdd(&ctr(O)->primary_rays, v0); atomicAdd(&ctr(O)->primary_hits, v1); }
         if (STATS) {
             for (int k = 0; k < 3; k++) {
@@ -2794,16 +2794,17 @@ __global__ void k_flag_wait(const volatile uint32_t* flags, uint32_t first, uint
     }
     __threadfence_system();
 }
-__global__ void k_fold_counters(DevCounters* base) {
-    constexpr unsigned kWords = sizeof(DevCounters) / 8;
-    if (threadIdx.x >= kWords) return;
+constexpr unsigned kCtrWords = sizeof(DevCounters) / 8;
+__global__ void __launch_bounds__(32 * kCtrWords) k_fold_counters(DevCounters* base) {      // one warp per counter word
+    const unsigned word = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     unsigned long long sum = 0;
-    for (uint32_t k = 1; k <= kCtrStripes; k++) sum += reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(base) + (size_t)k * kCtrStride)[threadIdx.x];
-    reinterpret_cast<unsigned long long*>(base)[threadIdx.x] = sum;
+    for (uint32_t k = 1 + lane; k <= kCtrStripes; k += 32) sum += reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(base) + (size_t)k * kCtrStride)[word];
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if (lane == 0) reinterpret_cast<unsigned long long*>(base)[word] = sum;
 }
 cudaError_t launch_fold_counters(DevCounters* base, cudaStream_t stream) {
     if (!base) return cudaSuccess;
-    k_fold_counters<<<1, 32, 0, stream>>>(base);
+    k_fold_counters<<<1, 32 * kCtrWords, 0, stream>>>(base);
     return cudaGetLastError();
 }
 cudaError_t launch_flag_signal(void* flag, uint32_t value, cudaStream_t stream) {

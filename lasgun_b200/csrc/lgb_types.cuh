@@ -170,7 +170,7 @@ struct DevCounters {
 // the record before anybody reads it.  With ONE copy the 4 M warps of k_cprimary sent 8 M atomics to two words per frame; the L2 slice
 // those words lived on was the kernel's bottleneck whenever a hot read-only line of the frame (tile list, large list, lights) happened
 // to share it -- 6.8 ms or 8.2-8.8 ms for the same launch, decided by whatever the process had allocated before (profiles/r2_v36-38).
-constexpr uint32_t kCtrStripes = 64, kCtrStride = 256;
+constexpr uint32_t kCtrStripes = 512, kCtrStride = 256;       // (64 stripes still cost 0.2 ms per grid walk: 130 k atomics per line)
 static_assert(sizeof(DevCounters) <= kCtrStride, "counter stripe");
 constexpr size_t kCtrBytes = (size_t)(1 + kCtrStripes) * kCtrStride;
 cudaError_t launch_fold_counters(DevCounters* base, cudaStream_t stream);
