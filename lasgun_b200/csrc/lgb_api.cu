@@ -713,20 +713,26 @@ static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
         if (e == cudaSuccess) owner.push_back(*out);
         return e;
     };
-    uint32_t* counts = nullptr; void* scan_tmp = nullptr; unsigned long long* bounds = nullptr; uint32_t* totals = nullptr; uint2* large_tmp = nullptr; DevGrid* dtab = nullptr;
-    GR(alloc(temp, (nc + 1) * 4, (void**)&counts));
-    GR(alloc(temp, scan_bytes, &scan_tmp));
-    GR(alloc(temp, 64 * 8 * (size_t)nl, (void**)&bounds));
-    GR(alloc(temp, 8 * (size_t)nl, (void**)&totals));
-    GR(alloc(temp, sizeof(uint2) * kGridLargeCap * (size_t)nl, (void**)&large_tmp));
-    GR(alloc(mine, sizeof(DevGrid) * (size_t)nl, (void**)&dtab));
+    // Four allocations per scene, not twenty: the stream-ordered pool of a long-lived process is fragmented, and the per-light buffers
+    // of `spheres1m` cost 5 ms to allocate as the bench's fourth workload against 1 ms in a fresh process.  One temporary block for the
+    // count passes, one kept block for the table and every light's cell starts; after the totals are known one kept block for every
+    // light's entries and large list, and one temporary block that the lights' fill + sort passes use in turn (same stream).
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t b_counts = up((nc + 1) * 4), b_scan = up(scan_bytes), b_bounds = up(64 * 8 * (size_t)nl), b_totals = up(8 * (size_t)nl), b_large = up(sizeof(uint2) * kGridLargeCap * (size_t)nl);
+    char* tmp_a = nullptr; char* keep_a = nullptr;
+    GR(alloc(temp, b_counts + b_scan + b_bounds + b_totals + b_large, (void**)&tmp_a));
+    uint32_t* counts = (uint32_t*)tmp_a; void* scan_tmp = tmp_a + b_counts; unsigned long long* bounds = (unsigned long long*)(tmp_a + b_counts + b_scan);
+    uint32_t* totals = (uint32_t*)(tmp_a + b_counts + b_scan + b_bounds); uint2* large_tmp = (uint2*)(tmp_a + b_counts + b_scan + b_bounds + b_totals);
+    const size_t b_tab = up(sizeof(DevGrid) * (size_t)nl), b_starts = up((nc + 1) * 4);
+    GR(alloc(mine, b_tab + b_starts * nl, (void**)&keep_a));
+    DevGrid* dtab = (DevGrid*)keep_a;
     GR(cudaMemsetAsync(dtab, 0, sizeof(DevGrid) * (size_t)nl, st));
     const bool timing = getenv("LGB_TIMING") != nullptr;
     auto lap = [&](const char* what) { if (!timing) return; cudaStreamSynchronize(st); fprintf(stderr, "[light grids]   %-28s %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); };
     lap("temporaries allocated");
     std::vector<uint32_t*> starts(nl, nullptr);
     for (uint32_t l = 0; l < nl; l++) {          // face mappings, counts, scans of every light, then ONE synchronisation for the totals
-        GR(alloc(mine, (nc + 1) * 4, (void**)&starts[l]));
+        starts[l] = (uint32_t*)(keep_a + b_tab + b_starts * l);
         GR(grid_count(S, l, res, dtab + l, bounds + 64 * (size_t)l, counts, starts[l], scan_tmp, scan_bytes, large_tmp + (size_t)kGridLargeCap * l, totals + 2 * (size_t)l, st));
     }
     lap("bounds + counts + scans");
@@ -741,14 +747,23 @@ static int build_light_grids(lgb_ctx* ctx, lgb_scene* s) {
         struct Head { const uint32_t* cell_start; const uint2* entries; const uint2* large; uint32_t res, n_large; };
         static_assert(offsetof(DevGrid, map) == sizeof(Head), "DevGrid head");
         std::vector<Head> heads(nl);
+        size_t keep_b_bytes = 0, max_entries = 0, max_sort = 0;
         for (uint32_t l = 0; l < nl; l++) {
             const uint32_t total = h_tot[2 * l], n_large = h_tot[2 * l + 1];
-            uint2* entries = nullptr; uint2* large = nullptr; uint2* entries_tmp = nullptr; void* sort_tmp = nullptr;
+            keep_b_bytes += up(std::max<size_t>(sizeof(uint2) * (size_t)total, 16)) + up(std::max<size_t>(sizeof(uint2) * (size_t)n_large, 16));
+            max_entries = std::max(max_entries, up(std::max<size_t>(sizeof(uint2) * (size_t)total, 16)));
+            max_sort = std::max(max_sort, up(grid_sort_bytes(total, nc)));
+        }
+        char* keep_b = nullptr; char* tmp_b = nullptr;
+        GR(alloc(mine, keep_b_bytes, (void**)&keep_b));
+        GR(alloc(temp, max_entries + max_sort, (void**)&tmp_b));
+        size_t at = 0;
+        for (uint32_t l = 0; l < nl; l++) {
+            const uint32_t total = h_tot[2 * l], n_large = h_tot[2 * l + 1];
+            uint2* entries = (uint2*)(keep_b + at); at += up(std::max<size_t>(sizeof(uint2) * (size_t)total, 16));
+            uint2* large = (uint2*)(keep_b + at); at += up(std::max<size_t>(sizeof(uint2) * (size_t)n_large, 16));
+            uint2* entries_tmp = (uint2*)tmp_b; void* sort_tmp = tmp_b + max_entries;
             const size_t sort_bytes = grid_sort_bytes(total, nc);
-            GR(alloc(mine, sizeof(uint2) * (size_t)total, (void**)&entries));
-            GR(alloc(mine, sizeof(uint2) * (size_t)n_large, (void**)&large));
-            GR(alloc(temp, sizeof(uint2) * (size_t)total, (void**)&entries_tmp));
-            GR(alloc(temp, sort_bytes, &sort_tmp));
             GR(grid_fill(S, l, res, dtab + l, counts, starts[l], entries_tmp, entries, total, sort_tmp, sort_bytes, large_tmp + (size_t)kGridLargeCap * l, n_large, st));
             if (n_large) GR(cudaMemcpyAsync(large, large_tmp + (size_t)kGridLargeCap * l, sizeof(uint2) * n_large, cudaMemcpyDeviceToDevice, st));
             heads[l] = Head{starts[l], entries, large, res, n_large};
@@ -1315,26 +1330,26 @@ static int ensure_camgrid(lgb_ctx* c, lgb_scene* s, uint32_t w, uint32_t h, uint
         P.nx = ((w - 1) >> P.shift) + 1; P.ny = ((h - 1) >> P.shift) + 1;
         P.large_cells = kGridLargeCells; P.large_cap = kGridLargeCap;
         const size_t nc = (size_t)P.nx * P.ny, scan_bytes = scan_bytes_for(nc);
-        uint32_t* counts = nullptr; void* scan_tmp = nullptr; uint32_t* n_large_dev = nullptr;
-        CU(c, cudaMallocAsync((void**)&counts, (nc + 1) * 4, st));
-        CU(c, cudaMallocAsync(&scan_tmp, std::max<size_t>(scan_bytes, 16), st));
-        CU(c, cudaMallocAsync((void**)&n_large_dev, 4, st));
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        char* tmp_a = nullptr;                                   // counts | scan scratch | large counter: one allocation (see build_light_grids)
+        CU(c, cudaMallocAsync((void**)&tmp_a, up((nc + 1) * 4) + up(std::max<size_t>(scan_bytes, 16)) + 256, st));
+        uint32_t* counts = (uint32_t*)tmp_a; void* scan_tmp = tmp_a + up((nc + 1) * 4); uint32_t* n_large_dev = (uint32_t*)(tmp_a + up((nc + 1) * 4) + up(std::max<size_t>(scan_bytes, 16)));
         CU(c, cudaMallocAsync(&G.starts, (nc + 1) * 4, st));
         CU(c, cudaMallocAsync(&G.large, sizeof(uint2) * kGridLargeCap, st));
         uint32_t total = 0, n_large = 0;
         CU(c, camgrid_count(S, P, counts, (uint32_t*)G.starts, scan_tmp, scan_bytes, (uint2*)G.large, n_large_dev, st, &total, &n_large));
         if (n_large > kGridLargeCap) G.refused = true;
         else {
-            void* entries_tmp = nullptr; void* sort_tmp = nullptr;
-            const size_t sort_bytes = grid_sort_bytes(total, nc);
+            char* tmp_b = nullptr;                               // unsorted entries | sort scratch
+            const size_t sort_bytes = grid_sort_bytes(total, nc), b_entries = up(sizeof(uint2) * std::max<size_t>(total, 1));
             CU(c, cudaMallocAsync(&G.entries, sizeof(uint2) * std::max<size_t>(total, 1), st));
-            CU(c, cudaMallocAsync(&entries_tmp, sizeof(uint2) * std::max<size_t>(total, 1), st));
-            CU(c, cudaMallocAsync(&sort_tmp, std::max<size_t>(sort_bytes, 16), st));
+            CU(c, cudaMallocAsync((void**)&tmp_b, b_entries + std::max<size_t>(sort_bytes, 16), st));
+            void* entries_tmp = tmp_b; void* sort_tmp = tmp_b + b_entries;
             CU(c, camgrid_fill(S, P, counts, (const uint32_t*)G.starts, (uint2*)entries_tmp, (uint2*)G.entries, total, sort_tmp, sort_bytes, (uint2*)G.large, n_large, st));
-            cudaFreeAsync(entries_tmp, st); cudaFreeAsync(sort_tmp, st);
+            cudaFreeAsync(tmp_b, st);
             G.valid = true; G.shift = P.shift; G.nx = P.nx; G.n_large = n_large; G.bytes = (nc + 1) * 4 + sizeof(uint2) * ((size_t)total + n_large);
         }
-        cudaFreeAsync(counts, st); cudaFreeAsync(scan_tmp, st); cudaFreeAsync(n_large_dev, st);
+        cudaFreeAsync(tmp_a, st);
         G.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (getenv("LGB_TIMING")) fprintf(stderr, "[camera grid] %ux%u tiles of %u px: %u entries, %u large, %.2f ms (host clock, incl. one sync)%s\n", P.nx, P.ny, 1u << P.shift, total, n_large, G.build_ms, G.refused ? " REFUSED" : "");
     }
