@@ -1946,8 +1946,11 @@ __global__ void __launch_bounds__(LGB_SWALK_THREADS, 1024 / LGB_SWALK_THREADS) k
 // One thread per sample slot, every light in turn: the ray's direction seen from the light selects ONE cell of that light's cube
 // map; its entries (nearest to the light first) and the light's few large primitives get the f32 filter + the reference's exact
 // test, any hit with t < 1 (light/point.rs:48-49), up to the first entry that starts beyond the ray's own length.
+#ifndef LGB_GSHADOW_THREADS
+#define LGB_GSHADOW_THREADS 64            // 256 / 128 / 64 threads per block at 1024 per SM: 7.35 / 6.79 / 6.69 ms on mixed4k (a block keeps its registers until its slowest ray is done)
+#endif
 #ifndef LGB_GSHADOW_MIN_BLOCKS
-#define LGB_GSHADOW_MIN_BLOCKS 4
+#define LGB_GSHADOW_MIN_BLOCKS (1024 / LGB_GSHADOW_THREADS)
 #endif
 // The shadow ray from `o` towards light l (light/point.rs:43-44: d = light - o, blocked iff the closest t < 1) against that light's grid.
 template <bool STATS>
@@ -2020,7 +2023,7 @@ __device__ __forceinline__ bool grid_blocked(const DevScene& S, D3 o, uint32_t l
 // SETUP (camera rays of a plain capture): the thread also does k_setup's work for its slot -- surface record, sign byte, gates -- so
 // that the shadow origin goes from registers into the walk and is never stored (k_setup and its 24 B/slot of ps drop out of the frame).
 template <bool STATS, bool ALL_SHADOWS, bool SETUP = false>
-__global__ void __launch_bounds__(256, LGB_GSHADOW_MIN_BLOCKS) k_gshadow(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
+__global__ void __launch_bounds__(LGB_GSHADOW_THREADS, LGB_GSHADOW_MIN_BLOCKS) k_gshadow(DevScene S, DevCamera C, DevWork W, DevOut O, DevWave V) {
     const uint64_t total = W.n_pixels * W.spp;
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -2163,7 +2166,7 @@ __global__ void __launch_bounds__(LGB_TRAV_THREADS, LGB_MIN_BLOCKS) k_shadow(Dev
 #define LGB_SHADE_MIN_BLOCKS 4
 #endif
 #ifndef LGB_FUSED_THREADS
-#define LGB_FUSED_THREADS 256u
+#define LGB_FUSED_THREADS 128u          // blocks of 256 / 128 threads (whole pixels): k_shade_lean 4.05 / 3.88 ms on mixed4k
 #endif
 #ifndef LGB_WARP_RESOLVE
 #define LGB_WARP_RESOLVE 0           // 1: fused resolve through warp shuffles instead of shared memory + barrier (measured 0.4 ms slower)
@@ -2950,19 +2953,19 @@ cudaError_t launch_render(const DevScene& S, const DevCamera& C, const DevShade&
     const bool setup_in_gshadow = !W.setup_in_primary && setup_fused(S, W, O, all_shadows);
     if (W.setup_in_primary) {           // k_cprimary<SETUP> has written ps / gate / sign byte: straight to the shadow rays
         mark(2);
-        KL("k_gshadow", -1, stream, if (stats) k_gshadow<true, false><<<blocks, 256, 0, stream>>>(S, C, W, O, V); else k_gshadow<false, false><<<blocks, 256, 0, stream>>>(S, C, W, O, V));
+        KL("k_gshadow", -1, stream, if (stats) k_gshadow<true, false><<<(unsigned)((total + LGB_GSHADOW_THREADS - 1) / LGB_GSHADOW_THREADS), LGB_GSHADOW_THREADS, 0, stream>>>(S, C, W, O, V); else k_gshadow<false, false><<<(unsigned)((total + LGB_GSHADOW_THREADS - 1) / LGB_GSHADOW_THREADS), LGB_GSHADOW_THREADS, 0, stream>>>(S, C, W, O, V));
         mark(3);
     } else if (setup_in_gshadow) {             // hit setup inside the shadow kernel: ps never leaves the registers
         mark(2);
-        KL("k_gshadow(+setup)", -1, stream, if (stats) k_gshadow<true, false, true><<<blocks, 256, 0, stream>>>(S, C, W, O, V); else k_gshadow<false, false, true><<<blocks, 256, 0, stream>>>(S, C, W, O, V));
+        KL("k_gshadow(+setup)", -1, stream, if (stats) k_gshadow<true, false, true><<<(unsigned)((total + LGB_GSHADOW_THREADS - 1) / LGB_GSHADOW_THREADS), LGB_GSHADOW_THREADS, 0, stream>>>(S, C, W, O, V); else k_gshadow<false, false, true><<<(unsigned)((total + LGB_GSHADOW_THREADS - 1) / LGB_GSHADOW_THREADS), LGB_GSHADOW_THREADS, 0, stream>>>(S, C, W, O, V));
         mark(3);
     } else {
     if (inst) KL("k_setup", -1, stream, if (all_shadows) k_setup<true, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V));
     else KL("k_setup", -1, stream, if (all_shadows) k_setup<true, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V); else k_setup<false, false><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V));
     mark(2);
     if (S.grids && !inst) {             // light grids: every shadow ray of the frame in one launch, no traversal (lgb_grid.cu)
-        if (stats) KL("k_gshadow", -1, stream, if (all_shadows) k_gshadow<true, true><<<blocks, 256, 0, stream>>>(S, C, W, O, V); else k_gshadow<true, false><<<blocks, 256, 0, stream>>>(S, C, W, O, V));
-        else KL("k_gshadow", -1, stream, if (all_shadows) k_gshadow<false, true><<<blocks, 256, 0, stream>>>(S, C, W, O, V); else k_gshadow<false, false><<<blocks, 256, 0, stream>>>(S, C, W, O, V));
+        if (stats) KL("k_gshadow", -1, stream, if (all_shadows) k_gshadow<true, true><<<(unsigned)((total + LGB_GSHADOW_THREADS - 1) / LGB_GSHADOW_THREADS), LGB_GSHADOW_THREADS, 0, stream>>>(S, C, W, O, V); else k_gshadow<true, false><<<(unsigned)((total + LGB_GSHADOW_THREADS - 1) / LGB_GSHADOW_THREADS), LGB_GSHADOW_THREADS, 0, stream>>>(S, C, W, O, V));
+        else KL("k_gshadow", -1, stream, if (all_shadows) k_gshadow<false, true><<<(unsigned)((total + LGB_GSHADOW_THREADS - 1) / LGB_GSHADOW_THREADS), LGB_GSHADOW_THREADS, 0, stream>>>(S, C, W, O, V); else k_gshadow<false, false><<<(unsigned)((total + LGB_GSHADOW_THREADS - 1) / LGB_GSHADOW_THREADS), LGB_GSHADOW_THREADS, 0, stream>>>(S, C, W, O, V));
         mark(3);
     }
     }
@@ -3051,7 +3054,7 @@ cudaError_t launch_level(const DevScene& S, const DevCamera& C, const DevShade& 
     } else {
         k_primary<false, false, true><<<pb, LGB_TRAV_THREADS, kPrimarySmem, stream>>>(S, C, W, O, V);
         k_setup<false, false, true><<<ablocks, kAppendThreads, 0, stream>>>(S, C, sh, W, O, V);
-        if (S.grids) { DevOut Os = O; Os.counters = shadow_counters; k_gshadow<false, false><<<blocks, 256, 0, stream>>>(S, C, W, Os, V); }
+        if (S.grids) { DevOut Os = O; Os.counters = shadow_counters; k_gshadow<false, false><<<(unsigned)((total + LGB_GSHADOW_THREADS - 1) / LGB_GSHADOW_THREADS), LGB_GSHADOW_THREADS, 0, stream>>>(S, C, W, Os, V); }
         else for (uint32_t l = 0; l < S.n_lights; l++) k_shadow<false, false><<<pb, LGB_TRAV_THREADS, kPrimarySmem, stream>>>(S, W, O, V, l, kQueueA);
         k_shade<false, false, true, true><<<blocks, 256, 0, stream>>>(S, C, sh, W, O, V);
     }
