@@ -1490,7 +1490,7 @@ __device__ __noinline__ void setup_generic_slot(const DevScene* Sg, double ox, d
 #define LGB_CPRIMARY_THREADS 128
 #endif
 #ifndef LGB_CPRIMARY_BLOCKS
-#define LGB_CPRIMARY_BLOCKS (1024 / LGB_CPRIMARY_THREADS)
+#define LGB_CPRIMARY_BLOCKS (1280 / LGB_CPRIMARY_THREADS)     // 8 / 10 / 12 blocks of 128 (64 / 48 / 40 registers): 6.58 / 6.53 / 6.62 ms on mixed4k, 0.283 / 0.265 / 0.258 on spheres1m
 #endif
 // SETUP (plain captures with light grids): once the walk is over the thread still holds the camera ray and the hit, and the hit
 // primitive is warm in L1 -- it does k_setup's work for its slot right there (surface record, sign byte, shadow origin, gates) and
@@ -1949,8 +1949,10 @@ __global__ void __launch_bounds__(LGB_SWALK_THREADS, 1024 / LGB_SWALK_THREADS) k
 #ifndef LGB_GSHADOW_THREADS
 #define LGB_GSHADOW_THREADS 64            // 256 / 128 / 64 threads per block at 1024 per SM: 7.35 / 6.79 / 6.69 ms on mixed4k (a block keeps its registers until its slowest ray is done)
 #endif
+// Registers per thread against threads per SM (mixed4k, 64-thread blocks): 80 / 72 / 64 / 48 / 40 / 32 registers = 768 / 896 / 1024 / 1280 /
+// 1536 / 2048 threads: 7.53 / 6.93 / 6.69 / 6.06 / 6.01 / 7.21 ms.  The walk waits on loads; more rays in flight buy more than the spills cost.
 #ifndef LGB_GSHADOW_MIN_BLOCKS
-#define LGB_GSHADOW_MIN_BLOCKS (1024 / LGB_GSHADOW_THREADS)
+#define LGB_GSHADOW_MIN_BLOCKS (1536 / LGB_GSHADOW_THREADS)
 #endif
 // The shadow ray from `o` towards light l (light/point.rs:43-44: d = light - o, blocked iff the closest t < 1) against that light's grid.
 template <bool STATS>
@@ -2422,7 +2424,7 @@ __device__ __forceinline__ D3 shade_generic_plastic(const DevScene& S, const Dev
 }
 
 #ifndef LGB_LEAN_MIN_BLOCKS
-#define LGB_LEAN_MIN_BLOCKS 4
+#define LGB_LEAN_MIN_BLOCKS 5            // (of 256 threads: 64 / 48 / 40 registers = 4 / 5 / 6: 3.88 / 3.65 / 3.75 ms on mixed4k)
 #endif
 // FUSED (spp <= 256): a block holds whole pixels (thread t: pixel t / spp of the block, sample t % spp); the samples meet in shared
 // memory, one thread per (pixel, channel) sums them in sample order (integrate.rs:16-20) and quantises (img.rs:56-67), one thread per
