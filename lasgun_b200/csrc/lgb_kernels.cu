@@ -24,7 +24,9 @@
 #define LGB_WALK_PREFETCH 0          // grid walks (k_cprimary, k_gshadow): load entry i + 1 while entry i is tested
 #endif
 #ifndef LGB_CP_STAGE
-#define LGB_CP_STAGE 1               // k_cprimary: a warp whose lanes share a tile stages the list's first 32 entries + filter records in shared memory (needs LGB_WALK_SPLIT)
+#define LGB_CP_STAGE 0               // k_cprimary: a warp whose lanes share a tile stages the list's first 32 entries + filter records in shared memory (needs LGB_WALK_SPLIT).
+                                     // Worth 0.08 ms at 64 registers / 1024 threads per SM; at 48 registers / 1280 threads it COSTS 1.0 ms (6.53 vs 5.54 ms on mixed4k): the
+                                     // 70 KB of slabs per SM come out of the L1 that holds the spill frames (profiles/r2_v47_stage.txt)
 #endif
 #ifndef LGB_WAVE_STREAM
 #define LGB_WAVE_STREAM 1            // wavefront entries (6 GB per mixed4k frame, each written once and read once) are stored / loaded with the streaming
@@ -1490,7 +1492,7 @@ __device__ __noinline__ void setup_generic_slot(const DevScene* Sg, double ox, d
 #define LGB_CPRIMARY_THREADS 128
 #endif
 #ifndef LGB_CPRIMARY_BLOCKS
-#define LGB_CPRIMARY_BLOCKS (1280 / LGB_CPRIMARY_THREADS)     // 8 / 10 / 12 blocks of 128 (64 / 48 / 40 registers): 6.58 / 6.53 / 6.62 ms on mixed4k, 0.283 / 0.265 / 0.258 on spheres1m
+#define LGB_CPRIMARY_BLOCKS (1280 / LGB_CPRIMARY_THREADS)     // 8 / 10 / 12 / 14 blocks of 128 (64 / 48 / 40 / 32 registers), no staging: 5.70 / 5.54 / 5.67 / 6.10 ms on mixed4k
 #endif
 // SETUP (plain captures with light grids): once the walk is over the thread still holds the camera ray and the hit, and the hit
 // primitive is warm in L1 -- it does k_setup's work for its slot right there (surface record, sign byte, shadow origin, gates) and
