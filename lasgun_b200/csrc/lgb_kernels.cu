@@ -32,7 +32,11 @@
 #define LGB_WAVE_STREAM 1            // wavefront entries (6 GB per mixed4k frame, each written once and read once) are stored / loaded with the streaming
 #endif                               // hint (st.global.cs / ld.global.cs: evict-first in L2), so they do not push the scene and the grids (~100-160 MB) out of the 126 MB L2
 #ifndef LGB_WALK_SPLIT
-#define LGB_WALK_SPLIT 1             // grid walks: filters run down the list until one passes, then the warp meets for the exact test (prim_filter / prim_exact)
+#define LGB_WALK_SPLIT 1             // camera-grid walk: filters run down the list until one passes, then the warp meets for the exact test (prim_filter / prim_exact)
+#endif
+#ifndef LGB_WALK_SPLIT_SHADOW
+#define LGB_WALK_SPLIT_SHADOW 0      // the same for the light-grid walk.  Split / fused at 40-48 registers: k_cprimary 5.55 / 5.78 ms, k_gshadow 6.02 / 5.75 (at 64 registers
+                                     // the split won both: 19.47 vs 19.76 ms per frame); an any-hit walk ends at its first exact hit, there is less to converge for
 #endif
 
 namespace lgb {
@@ -1987,7 +1991,7 @@ __device__ __forceinline__ bool grid_blocked(const DevScene& S, D3 o, uint32_t l
     const bool sorted = e - b <= kGridSortMax;                         // (longer lists are not sorted: lgb_grid.cu)
     const uint2* en = G->entries;
     const uint2* lg = G->large;
-#if LGB_WALK_SPLIT
+#if LGB_WALK_SPLIT_SHADOW
     // positions [b, e) are the cell's list, [e, e2) the light's large list (both nearest first)
     const uint32_t e2 = e + n_large;
     for (uint32_t i = b;;) {
