@@ -53,3 +53,28 @@ def test_product_does_not_touch_oracle():
                     if re.search(r"(import|from)\s+oracle|pyoracle|lasgun_oracle|oracle/", txt) and "does not include or link anything under oracle" not in txt:
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_host_block_cache_reuses_freed_blocks(native):
+    """The host mirror's arrays (include/lasgun_host.hpp) come from lgh_block_alloc: a freed block of a megabyte or more is handed out
+    again for a request it fits (capture(scene, film) sizes the same arrays every frame), small requests bypass the cache."""
+    lib = ctypes.CDLL(native.SO_PATH)
+    lib.lgh_block_alloc.restype = ctypes.c_void_p
+    lib.lgh_block_alloc.argtypes = [ctypes.c_size_t]
+    lib.lgh_block_free.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    big = 5 << 20
+    p = lib.lgh_block_alloc(big)
+    assert p
+    ctypes.memset(p, 0x5A, big)
+    lib.lgh_block_free(p, big)
+    got = []                                         # (other tests of this process may have left fitting blocks in the cache: at most 64)
+    for _ in range(70):
+        got.append(lib.lgh_block_alloc(big - 4096))  # rounds to the same 2 MB multiple: the cached block fits
+        if got[-1] == p:
+            break
+    assert p in got and all(got)
+    for q in got:
+        lib.lgh_block_free(q, big - 4096)
+    small = lib.lgh_block_alloc(1000)
+    assert small
+    lib.lgh_block_free(small, 1000)
