@@ -482,7 +482,6 @@ struct Flattener {
         // note their mesh / group nodes in parallel (1a), a short sequential walk over the chunks hands out the bases and builds the
         // nested levels in order (1b), and the chunks write ids and slots in parallel (1c).
         const size_t nn = ag.contents.size();
-        raw_vector<uint32_t> slot(nn), ids(nn);
         lv->boxes.resize(nn); lv->refs.resize(nn);
         constexpr size_t kGrain = 1 << 13;
         const size_t n_chunks = lgb::Pool::get().chunks_of(nn, kGrain);                    // the partition for_range makes of [0, nn)
@@ -533,17 +532,8 @@ struct Flattener {
             next_id += (uint32_t)(end - prev);
         }
         const size_t s_base = out.spheres.size(), c_base = out.cuboids.size();      // after the nested levels took theirs
-        lgb::Pool::get().for_range(nn, kGrain, [&](size_t b0, size_t e0, size_t c) {
-            const ChunkInfo& ci = chunks[c];
-            uint32_t id = ci.id_base, so = ci.s_ord + (uint32_t)s_base, co = ci.c_ord + (uint32_t)c_base;
-            size_t ni = 0;
-            for (size_t i = b0; i < e0; i++) {
-                const Aggregate::Node::Kind k = ag.contents[i].kind;
-                if (k == Aggregate::Node::Sphere) { slot[i] = so++; ids[i] = id++; }
-                else if (k == Aggregate::Node::Cube || k == Aggregate::Node::Cuboid) { slot[i] = co++; ids[i] = id++; }
-                else id = ci.nested_ids[ni++];                    // the nested level's primitives took the ids in between
-            }
-        });
+        // (1c, the ids and slots of the chunk's own primitives, is a running count along the chunk: pass 2 below walks the same chunks
+        // and keeps it in registers -- a third sweep over the 150-byte nodes and two arrays of a word per node are not needed)
         out.spheres.resize(s_base + n_s); out.sphere_material.resize(s_base + n_s); out.sphere_id.resize(s_base + n_s);
         out.cuboids.resize(c_base + n_c); out.cuboid_material.resize(c_base + n_c); out.cuboid_id.resize(c_base + n_c);
         // Pass 2 (all threads): primitive records and bounds.  Materials are interned through a small per-chunk
@@ -551,7 +541,10 @@ struct Flattener {
         std::mutex mat_mutex;
         std::atomic<bool> failed{false};
         std::string fail_msg; int fail_status = LGB_ERR_INVALID;
-        lgb::Pool::get().for_range(nn, 1 << 13, [&](size_t b0, size_t e0, size_t) {
+        lgb::Pool::get().for_range(nn, kGrain, [&](size_t b0, size_t e0, size_t chunk) {
+            const ChunkInfo& ci = chunks[chunk];
+            uint32_t id = ci.id_base, so = ci.s_ord + (uint32_t)s_base, co = ci.c_ord + (uint32_t)c_base;
+            size_t ni = 0;
             struct Cached { Material m; uint32_t index; };
             std::vector<Cached> cache;
             auto intern = [&](const Material& m) -> uint32_t {
@@ -569,8 +562,9 @@ struct Flattener {
                     if (n.kind == Aggregate::Node::Sphere) {
                         lgb_sphere s; for (int k = 0; k < 3; k++) { s.center[k] = n.a[k]; double lo = n.a[k] - n.r, hi = n.a[k] + n.r; b.mn[k] = lo < hi ? lo : hi; b.mx[k] = lo < hi ? hi : lo; }   // sphere.rs:73-77
                         s.radius = n.r;
-                        out.spheres[slot[i]] = s; out.sphere_material[slot[i]] = intern(n.mat); out.sphere_id[slot[i]] = ids[i];
-                        lv->refs[i] = LGB_PRIM_REF(LGB_PRIM_SPHERE, slot[i]);
+                        const uint32_t at = so++;
+                        out.spheres[at] = s; out.sphere_material[at] = intern(n.mat); out.sphere_id[at] = id++;
+                        lv->refs[i] = LGB_PRIM_REF(LGB_PRIM_SPHERE, at);
                     } else if (n.kind == Aggregate::Node::Cube || n.kind == Aggregate::Node::Cuboid) {
                         lgb_cuboid c;
                         for (int k = 0; k < 3; k++) {
@@ -578,9 +572,10 @@ struct Flattener {
                             c.min[k] = p0 < p1 ? p0 : p1; c.max[k] = p0 < p1 ? p1 : p0;                          // Bounds::new, bounds.rs:37-42
                             b.mn[k] = c.min[k]; b.mx[k] = c.max[k];
                         }
-                        out.cuboids[slot[i]] = c; out.cuboid_material[slot[i]] = intern(n.mat); out.cuboid_id[slot[i]] = ids[i];
-                        lv->refs[i] = LGB_PRIM_REF(LGB_PRIM_CUBOID, slot[i]);
-                    } else continue;
+                        const uint32_t at = co++;
+                        out.cuboids[at] = c; out.cuboid_material[at] = intern(n.mat); out.cuboid_id[at] = id++;
+                        lv->refs[i] = LGB_PRIM_REF(LGB_PRIM_CUBOID, at);
+                    } else { id = ci.nested_ids[ni++]; continue; }            // the nested level's primitives took the ids in between
                     lv->boxes[i] = b;
                 }
             } catch (const Error& e) {
