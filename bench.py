@@ -129,6 +129,30 @@ def workload(name, args):
     return scenes.CONFIGS[name]()
 
 
+def scene_census(sc):
+    """Primitive counts of a scene description (both arms name the workload with the same keys)."""
+    tri = sph = cub = 0
+
+    def walk(ag):
+        nonlocal tri, sph, cub
+        for item in ag.contents:
+            kind = item[0]
+            if kind == "sphere":
+                sph += 1
+            elif kind == "spheres":
+                sph += len(item[2])
+            elif kind in ("cube", "box"):
+                cub += 1
+            elif kind == "mesh":
+                ref = item[1]
+                mesh = sc.meshes[ref.index] if hasattr(ref, "index") else ref
+                tri += len(mesh.faces) // 3 if not hasattr(mesh.faces, "shape") else int(mesh.faces.size) // 3
+            elif kind == "group":
+                walk(item[1])
+    walk(sc.root)
+    return {"triangles": int(tri), "spheres": int(sph), "cuboids": int(cub)}
+
+
 def reference_sample(osc, w, h, threads, target_s, spp, n_lights):
     """Bounded sample of the frame on the CPU oracle: capture_subset(k, n) for k < threads."""
     probe_n = max(threads, (w * h) // (threads * 64))
@@ -162,7 +186,9 @@ def run_reference(args):
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "impl": "reference",
-        "config": {"workload": args.workload, "film": [w, h], "spp": spp, "lights": nl},
+        # the keys of the device arm's config, so that the two lines name the workload alike (what only a device has is null)
+        "config": {"workload": args.workload, "film": [w, h], "spp": spp, "lights": nl, **scene_census(sc), "bvh_nodes": None, "device_bvh_nodes": None,
+                   "parallelism": f"cpu_threads{threads}", "film_gather": None, "l2_policy": "host CPU arm: none"},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port",
                          "sample": f"capture_subset(k, n={n}) for k in 0..{threads} of the {w}x{h} frame ({rays} rays/step); "
                                    "C++ restatement of the reference algorithm, not the Rust build",
