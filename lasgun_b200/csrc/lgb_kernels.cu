@@ -973,7 +973,7 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 }
 
 #ifndef LGB_MIN_BLOCKS
-#define LGB_MIN_BLOCKS 8
+#define LGB_MIN_BLOCKS 10             // persistent traversal kernels at 8 / 10 / 12 blocks of 128 (64 / 48 / 40 registers): cornell 1.05 / 0.94 / 0.96 ms, simple 0.38 / 0.37 / 0.38, mixed4k through the BVH 36.1 / 36.0 / 36.0
 #endif
 #ifndef LGB_TRAV_THREADS
 #define LGB_TRAV_THREADS 128          // threads per block of the persistent traversal kernels (256 x 4 blocks: the same on large frames, `mesh1m` 0.85 -> 0.68 ms: shorter tails)
