@@ -183,6 +183,57 @@ def test_camera_grid(native, oracle, gpu_ctx, name):
     assert np.array_equal(films[1], films[0])
 
 
+def _columns_scene():
+    """Spheres stacked behind one another as seen from the eye AND from a light beside it: a camera-grid tile and a light-grid cell with
+    more than 1024 entries (the segmented sort), a second column of a few hundred (one warp and shared memory), scattered ones (a warp's
+    lanes).  Every cell list must come out nearest first: the walks stop at the first entry that starts behind the best hit."""
+    sc = Scene()
+    sc.set_ambient_light([0.1, 0.1, 0.1])
+    sc.set_solid_background([0.05, 0.05, 0.1])
+    cam = sc.set_perspective_camera(40.0)
+    cam.look_at([0.0, 0.0, 30.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+    cam.set_supersampling(1)
+    sc.add_point_light([0.4, 0.3, 31.0], [0.8, 0.8, 0.8], [1.0, 0.0, 0.0])
+    sc.add_point_light([25.0, 20.0, 10.0], [0.5, 0.5, 0.5], [1.0, 0.0, 0.0])
+    rng = np.random.default_rng(0x5EED0C01)
+    cols = []
+    for n, x0, y0, r in ((1500, 0.0, 0.0, 0.30), (300, 4.0, 1.0, 0.25)):
+        k = np.arange(n)
+        c = np.stack([x0 + 0.05 * rng.standard_normal(n), y0 + 0.05 * rng.standard_normal(n), 10.0 - 0.11 * k], axis=1)
+        cols.append((c, np.full(n, r)))
+    scat = np.concatenate([-8.0 + 16.0 * rng.random((2000, 2)), -30.0 + 35.0 * rng.random((2000, 1))], axis=1)
+    cols.append((scat, 0.15 + 0.2 * rng.random(2000)))
+    centers = np.concatenate([c for c, _ in cols]); radii = np.concatenate([r for _, r in cols])
+    order = rng.permutation(len(centers))                   # (so that the columns do not arrive nearest first by construction)
+    pal = [Material.plastic([0.8, 0.3, 0.2], [0.4, 0.4, 0.4], 0.2), Material.plastic([0.2, 0.7, 0.3], [0.3, 0.3, 0.3], 0.3), Material.plastic([0.3, 0.4, 0.9], [0.5, 0.5, 0.5], 0.1)]
+    sc.root.add_spheres(centers[order], radii[order], pal, np.arange(len(centers)) % 3)
+    return sc, (96, 96)
+
+
+def test_grid_cells_of_every_length(native, oracle, gpu_ctx):
+    """k_sort_cells / k_sort_medium / the segmented sort (csrc/lgb_grid.cu) through the frames that depend on them: with both grids
+    forced on, ids, t, occlusion bits and film are the oracle's and the film is the one the BVH kernels render."""
+    sc, (w, h) = _columns_scene()
+    ref = oracle.OracleScene(sc).capture(w, h, aov=True)
+    films = {}
+    try:
+        for mode in (1, 0):
+            gpu_ctx.set_camera_grid(mode); gpu_ctx.set_light_grids(mode)
+            dev = native.DeviceScene(gpu_ctx, native.FlatScene(sc))
+            out = dev.capture_aov(w, h)
+            films[mode], st = dev.capture(w, h)
+            dev.destroy()
+            a = parity.aov_report(out, ref)
+            assert a["mismatches"] == 0 and a["hit_miss_flips"] == 0 and a["id_mismatch"] == 0 and a["t_bit_equal"] == a["t_compared"], (mode, a)
+            assert a["occl_diff"] == 0, (mode, a)
+            assert np.array_equal(films[mode], out["rgba"]) and st["primary_rays"] == w * h * sc.camera.num_samples()
+    finally:
+        gpu_ctx.set_camera_grid(-1); gpu_ctx.set_light_grids(-1)
+    assert np.array_equal(films[1], films[0])
+    f = parity.film_report(films[1], ref["rgba"])
+    assert f["alpha_equal"] and f["identical_frac"] >= 0.9999, f
+
+
 @pytest.mark.parametrize("name", ["simple_b_9spp", "mixed_4spp", "nested_groups", "whitted"])
 def test_frames_in_bands(native, gpu_ctx, name):
     """A memory budget far below what the frame's per-sample buffers need (LGB_OPT_WAVE_BUDGET_MB): the frame is rendered band after
