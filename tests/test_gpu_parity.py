@@ -480,6 +480,42 @@ def test_device_built_bvh(native, gpu_ctx, monkeypatch, name):
     assert np.array_equal(film_dev, film_host)
 
 
+def test_device_built_bvh_degenerate(native, gpu_ctx, monkeypatch):
+    """The device builder where the SAH has nothing to go on: 12 000 positions, each holding a sphere, the same sphere again and a
+    cube (coincident centroids: nodes halved by position, leaves split by type, in the level loop and in k_subtrees alike).  The tree
+    must be well formed and the film -- exact-t ties between the twin spheres included -- the one the host-built tree renders."""
+    rng = np.random.default_rng(0x5EED0C02)
+    sc = Scene()
+    sc.set_ambient_light([0.1, 0.1, 0.1])
+    cam = sc.set_perspective_camera(45.0)
+    cam.look_at([0.0, 0.0, 160.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0])
+    sc.add_point_light([80.0, 120.0, 150.0], [0.8, 0.8, 0.8], [1.0, 0.0, 0.0])
+    pos = -50.0 + 100.0 * rng.random((12000, 3)); rad = 0.6 + 0.6 * rng.random(12000)
+    pal = [Material.plastic([0.8, 0.3, 0.2], [0.4, 0.4, 0.4], 0.2), Material.plastic([0.2, 0.7, 0.3], [0.3, 0.3, 0.3], 0.3)]
+    sc.root.add_spheres(np.concatenate([pos, pos]), np.concatenate([rad, rad]), pal, np.arange(24000) % 2)
+    for p, r in zip(pos, rad):
+        sc.root.add_cube((p - 0.4 * r).tolist(), float(0.8 * r), pal[0])
+    w = h = 128
+    flat = native.FlatScene(sc)
+    assert flat.prim_count == 36000
+    dev = native.DeviceScene(gpu_ctx, flat)
+    v = dev.verify()
+    assert v["ranks_ok"] == 1, "expected the device-side builder for this many primitives"
+    assert v["boxes_ok"] == 1 and v["max_leaf"] <= 4 and v["max_depth"] < 64, v
+    out_dev = dev.capture_aov(w, h)
+    film_dev, _ = dev.capture(w, h)
+    dev.destroy()
+    monkeypatch.setenv("LGB_HOST_BUILD", "1")
+    host = native.DeviceScene(gpu_ctx, flat)
+    vh = host.verify()
+    assert vh["ranks_ok"] == 0 and vh["boxes_ok"] == 1
+    out_host = host.capture_aov(w, h)
+    film_host, _ = host.capture(w, h)
+    host.destroy()
+    assert np.array_equal(out_dev["prim_id"], out_host["prim_id"]) and np.array_equal(out_dev["t"], out_host["t"])
+    assert np.array_equal(film_dev, film_host)
+
+
 def test_golden_films(native, gpu_ctx):
     """The committed oracle films of tests/golden/films.npz (a small version of every config + two nested-group scenes): the device
     film must equal them byte for byte -- no oracle is run here."""
